@@ -1,0 +1,250 @@
+/*
+ * rbq.h — C ABI of the B200-native batched propagation engine for rbqoc's hot path.
+ *
+ * Every entry point is what a Julia `ccall` (or Python `ctypes`) stub binds in place of
+ * the reference function cited beside it.  Citations are `file:line` relative to the
+ * reference tree (SchusterLab/rbqoc).  No torch / C++ types cross this boundary: plain
+ * pointers, sizes and POD structs only.
+ *
+ * Conventions
+ *  - All floating point data is IEEE binary64 ("double").
+ *  - Augmented states / controls are dense vectors laid out exactly like the reference's
+ *    `astate` / `acontrol` SVectors (0-based here, 1-based there).
+ *  - Jacobians are column-major n x (n+m) blocks `[A_k B_k]`, the layout
+ *    RobotDynamics' `discrete_jacobian!(::Type{RK3}, ∇f, model, z)` fills.
+ *  - Trajectories are knot-major: X[k*n + i], U[k*m + j]  (what `permutedims` at
+ *    spin13.jl:180-183 produces, seen from C).
+ *  - Every function returns int: 0 = ok, <0 = argument error (RBQ_E_*), >0 = CUDA error
+ *    code.  Nothing throws or aborts across the boundary.  `rbq_last_error` gives text.
+ *  - Host-pointer entry points are synchronous: results are in host memory on return.
+ *    `_dev` entry points take device pointers, enqueue on the handle's stream and
+ *    return without synchronising.
+ *  - A handle is bound to one CUDA device and is not thread-safe; distinct handles are
+ *    independent.
+ *  - There is no CPU fallback: without a usable CUDA device `rbq_create` fails.
+ */
+#ifndef RBQ_H
+#define RBQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBQ_VERSION 100
+
+/* ---- error codes (negative = caller error) ---------------------------------------- */
+#define RBQ_OK 0
+#define RBQ_E_NULL (-1)      /* a required pointer was NULL                        */
+#define RBQ_E_MODEL (-2)     /* unknown model_id / inconsistent model parameters   */
+#define RBQ_E_SIZE (-3)      /* a size/count argument is out of range              */
+#define RBQ_E_GATE (-4)      /* unknown gate id                                    */
+#define RBQ_E_ALGO (-5)      /* unknown propagator algorithm                       */
+#define RBQ_E_NODEVICE (-6)  /* no CUDA device / wrong architecture                */
+#define RBQ_E_ALIGN (-7)     /* device pointer not suitably aligned                */
+
+/* ---- enums mirrored from the reference --------------------------------------------- */
+/* GateType, spin.jl:29-34 */
+#define RBQ_GATE_ZPIBY2 1
+#define RBQ_GATE_YPIBY2 2
+#define RBQ_GATE_XPIBY2 3
+#define RBQ_GATE_XPI 4
+
+/* model ids = the number in the reference file name that defines the Model */
+#define RBQ_MODEL_SPIN11 11 /* derivative robust, d/dfq      spin11.jl:51-117  */
+#define RBQ_MODEL_SPIN12 12 /* sampling robust, fq +- sigma  spin12.jl:52-56,165-192 */
+#define RBQ_MODEL_SPIN13 13 /* nominal                       spin13.jl:37-58   */
+#define RBQ_MODEL_SPIN15 15 /* decay aware / time optimal    spin15.jl:40-73   */
+#define RBQ_MODEL_SPIN17 17 /* derivative robust, d/da       spin17.jl:48-114  */
+#define RBQ_MODEL_SPIN18 18 /* sampling robust, a +- namp    spin18.jl:50-55,162-190 */
+#define RBQ_MODEL_SPIN30 30 /* unscented sampling, fq        spin30.jl:60-202  */
+
+/* propagator algorithm for exp(dt*(f*H0 + a*H1)) */
+#define RBQ_ALGO_SU2 0  /* closed form: (dt H)^2 = -theta^2 I  =>  cos + sinc series  */
+#define RBQ_ALGO_PADE 1 /* reference algorithm: generic 4x4 Pade-3/5/7/9/13 + LU solve
+                           (StaticArrays 0.12.5 `exp`, the call at spin13.jl:46)      */
+
+#define RBQ_MAX_SAMPLE_STATES 4
+#define RBQ_HIST_BINS 256
+
+/*
+ * Plain-old-data mirror of the reference's immutable `Model` structs:
+ *   spin12.jl:52-54  Model(h0_samples)          -> fq_samples[2]
+ *   spin18.jl:50-52  Model(namp)                -> namp
+ *   spin30.jl:60-66  Model(S, nominal_idxs, fq_cov, alpha, sample_state_count)
+ *   spin15.jl:40-42  Model{DA,TO}               -> decay_aware, time_optimal
+ *   spin11.jl:51-52  Model{DO} / spin17.jl      -> derivative_order
+ * `fq` replaces the global constant FQ (spin.jl:148) so that batches of detuned
+ * problems can share one code path; set it to 1.4e-2 for the reference behaviour.
+ */
+typedef struct rbq_model_params {
+    int32_t model_id;
+    int32_t derivative_order;   /* spin11/17: 0,1,2                                   */
+    int32_t decay_aware;        /* spin15 DA                                          */
+    int32_t time_optimal;       /* spin15 TO                                          */
+    int32_t sample_state_count; /* spin30: 1..RBQ_MAX_SAMPLE_STATES                   */
+    int32_t algo;               /* RBQ_ALGO_*                                         */
+    int32_t nominal_offset[RBQ_MAX_SAMPLE_STATES]; /* spin30: 0-based first index of
+                                   the nominal state of sample state i
+                                   (= nominal_idxs[i][1]-1, spin30.jl:62,168)         */
+    int32_t reserved[2];
+    double fq;                  /* GHz                                                */
+    double fq_samples[2];       /* spin12: (FQ+fq_cov), (FQ-fq_cov)  spin12.jl:204-205 */
+    double namp;                /* spin18                                             */
+    double fq_cov;              /* spin30 (used as a variance, spin30.jl:102,138)     */
+    double alpha;               /* spin30                                             */
+    double S_diag[4];           /* spin30 penalty weights, spin30.jl:215              */
+} rbq_model_params;
+
+/* Infidelity statistics of a Monte-Carlo sweep.
+ * Additive across shards: count/nonfinite/hist add, sum/sumsq add, min/max combine. */
+typedef struct rbq_stats {
+    int64_t count;      /* finite samples accumulated                                 */
+    int64_t nonfinite;  /* samples whose infidelity was NaN/Inf (returned, not hidden) */
+    double sum;         /* sum of infidelities 1-F                                    */
+    double sumsq;       /* sum of squares                                             */
+    double min;
+    double max;
+    int64_t hist[RBQ_HIST_BINS]; /* log10 histogram over [1e-16,1): bin =
+                                    floor((log10(e)+16)*16) clamped to [0,255]         */
+} rbq_stats;
+
+typedef struct rbq_handle rbq_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int rbq_version(void);
+/* device = CUDA ordinal.  Fails with RBQ_E_NODEVICE when no sm_100 device is present. */
+int rbq_create(int device, rbq_handle** out);
+int rbq_destroy(rbq_handle* h);
+const char* rbq_last_error(const rbq_handle* h);
+/* cuda_stream = a cudaStream_t (NULL = the legacy default stream). */
+int rbq_set_stream(rbq_handle* h, void* cuda_stream);
+int rbq_synchronize(rbq_handle* h);
+/* number of kernels this handle has launched since creation (bench `gpu_launches`). */
+int64_t rbq_launch_count(const rbq_handle* h);
+
+/* ---- model API: RD.state_dim / RD.control_dim (spin13.jl:39-40, spin30.jl:67-70) ------ */
+int rbq_state_dim(const rbq_model_params* p);   /* <0 on error */
+int rbq_control_dim(const rbq_model_params* p); /* <0 on error */
+
+/* ---- per-knot: RD.discrete_dynamics(::Type{RK3}, model, x, u, t, dt)  (spin13.jl:44-58,
+ *      spin12.jl:165-192, spin30.jl:177-202, spin15.jl:50-73, spin11.jl:64-117,
+ *      spin17.jl:61-114, spin18.jl:162-190).  Host pointers. */
+int rbq_discrete_dynamics(rbq_handle* h, const rbq_model_params* p, const double* x,
+                          const double* u, double t, double dt, double* xnext);
+/* RD.discrete_jacobian!(::Type{RK3}, ∇f, model, z) — default is ForwardDiff.jacobian over
+ * [x;u] (RobotDynamics 0.2.1); AB is column-major n x (n+m). */
+int rbq_discrete_jacobian(rbq_handle* h, const rbq_model_params* p, const double* x,
+                          const double* u, double t, double dt, double* AB);
+
+/* ---- trajectory level (what Altro's `for k = 1:N-1` loops become) ------------------------
+ * rollout: B independent trajectories.  x0[B*n], U[B*(N-1)*m], dt[N-1] (shared by the
+ * batch; ignored by time-optimal spin15 which takes dt = u2^2), X[B*N*n]. */
+int rbq_rollout(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N,
+                const double* x0, const double* U, const double* dt, double* X);
+/* closed-loop rollout used by the iLQR line search: for each candidate alpha_c
+ *   du = K_k (x_k - Xref_k) + alpha_c d_k ;  u_k = Uref_k + du ;  x_{k+1} = f(x_k,u_k)
+ * K[(N-1)*m*n] column-major m x n per knot, d[(N-1)*m].  X[nalpha*N*n], Uout[nalpha*(N-1)*m]. */
+int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N,
+                           const double* Xref, const double* Uref, const double* K,
+                           const double* d, const double* dt, int64_t nalpha,
+                           const double* alphas, double* X, double* Uout);
+/* jacobians: K independent knots (a whole trajectory, or a batch of them, flattened).
+ * X[K*n], U[K*m], dt[K], AB[K*n*(n+m)] (each block column-major). */
+int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X,
+                  const double* U, const double* dt, double* AB);
+int rbq_rollout_dev(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N,
+                    const double* d_x0, const double* d_U, const double* d_dt, double* d_X);
+int rbq_jacobians_dev(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* d_X,
+                      const double* d_U, const double* d_dt, double* d_AB);
+
+/* ---- Monte-Carlo robustness evaluation: run_sim_prop(...; dynamics_type=schroed)
+ *      (spin.jl:1553-1608 -> integrate_prop_schroed! spin.jl:438-452 -> compute_fidelities
+ *      spin.jl:1198-1240), batched over S samples instead of one call per (parameter, seed).
+ *
+ *  controls[nknots]   pulse amplitudes a_j (GHz), nknots = control_knot_count
+ *  dt                 1/controls_dt_inv
+ *  fq[S]              per-sample qubit frequency: negi_h0 = fq[s]*NEGI_H0_ISO  (figures.jl:270)
+ *  da[S] or NULL      per-sample static amplitude offset added to every knot
+ *  psi0[S*4]          per-sample initial iso state (gen_rand_state_iso, spin.jl:1119-1138)
+ *  fid[S*(gate_count+1)] or NULL   fidelities after 0..gate_count gates, sample-major
+ *  stats or NULL      statistics of the infidelity after the last gate
+ */
+int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
+                  int64_t gate_count, int64_t S, const double* fq, const double* da,
+                  const double* psi0, int algo, double* fid, rbq_stats* stats);
+/* device-pointer variant; d_stats points to a device rbq_stats that is ACCUMULATED into
+ * (zero it with rbq_stats_reset_dev first).  d_fid may be NULL. */
+int rbq_mc_static_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
+                      int gate, int64_t gate_count, int64_t S, const double* d_fq,
+                      const double* d_da, const double* d_psi0, int algo, double* d_fid,
+                      rbq_stats* d_stats);
+/* Samples drawn on the device by a counter-based generator keyed by the GLOBAL sample
+ * index (Philox4x32-10; key = seed, counter = index), so any sharding of
+ * [first, first+S) over GPUs reproduces the same samples:
+ *   fq   = fq0*(1 + clip(fq_rel_sigma*N(0,1), +-fq_rel_clip))      (figures.jl:261,386)
+ *   da   = da_sigma*N(0,1)
+ *   psi0 = (u1 + i u2, u3 + i u4)/norm                              (spin.jl:1132-1133)
+ */
+int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
+                             int gate, int64_t gate_count, int64_t first, int64_t S,
+                             uint64_t seed, double fq0, double fq_rel_sigma,
+                             double fq_rel_clip, double da_sigma, int algo, double* d_fid,
+                             rbq_stats* d_stats);
+/* materialise the samples the generator above draws (for parity tests / the oracle) */
+int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0,
+                       double fq_rel_sigma, double fq_rel_clip, double da_sigma, double* fq,
+                       double* da, double* psi0);
+int rbq_stats_reset_dev(rbq_handle* h, rbq_stats* d_stats);
+/* stats helpers on the host: merge b into a (what the NCCL all-reduce computes) */
+int rbq_stats_merge(rbq_stats* a, const rbq_stats* b);
+
+/* ---- time-dependent amplitude noise: run_sim_prop(...; dynamics_type=schroedda)
+ *      (integrate_prop_schroedda! spin.jl:469-484).
+ *  noise[S*noise_len] per-sample noise offsets (already scaled by namp, spin.jl:1571),
+ *  looked up as noise[floor(time*noise_dt_inv)] with `time` accumulated by repeated
+ *  `time += dt` exactly like spin.jl:476-480. */
+int rbq_mc_noise(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
+                 int64_t gate_count, int64_t S, double fq, const double* noise,
+                 int64_t noise_len, double noise_dt_inv, const double* psi0, int algo,
+                 double* fid, rbq_stats* stats);
+int rbq_mc_noise_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
+                     int gate, int64_t gate_count, int64_t S, double fq, const double* d_noise,
+                     int64_t noise_len, double noise_dt_inv, const double* d_psi0, int algo,
+                     double* d_fid, rbq_stats* d_stats);
+/* noise generated on the fly: white N(0,1) from Philox(seed, sample index) through the
+ * 3-pole pink filter of gen_pink_noise (spin.jl:1178-1192), times noise_dt_inv*namp. */
+int rbq_mc_pink_philox_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
+                           int gate, int64_t gate_count, int64_t first, int64_t S,
+                           uint64_t seed, double fq, double namp, double noise_dt_inv,
+                           int algo, double* d_fid, rbq_stats* d_stats);
+/* materialise that noise: noise[S*noise_len] */
+int rbq_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double namp,
+                   double noise_dt_inv, int64_t noise_len, double* noise);
+
+/* ---- Lindblad T1 rollout: run_sim_prop(...; dynamics_type=lindbladt1)
+ *      (integrate_prop_lindbladt1! spin.jl:521-539, fidelity_mat spin.jl:1101-1104).
+ *  rho0[S*8]: per-sample 2x2 complex density, column-major (vec(rho), spin.jl:524), each
+ *  entry (re,im).  da[S] or NULL: static amplitude offset per realisation (enters both the
+ *  Hamiltonian and gamma_1(a)).  t2_gamma_c/t2_gamma_f: extra pure dephasing
+ *  Gamma(t) = gamma_c + 2 gamma_f^2 t of dynamics_lindbladt2_deqjl (spin.jl:542-554),
+ *  evaluated at knot mid-points; pass 0,0 for the T1-only reference path.
+ *  fid[S*(gate_count+1)] or NULL: Uhlmann sqrt-fidelity per gate.  rho_out[S*8] or NULL:
+ *  final density.  stats: of 1-fid after the last gate. */
+int rbq_lindblad(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
+                 int64_t gate_count, int64_t S, double fq, const double* da,
+                 const double* rho0, double t2_gamma_c, double t2_gamma_f, double* fid,
+                 double* rho_out, rbq_stats* stats);
+int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
+                     int gate, int64_t gate_count, int64_t S, double fq, const double* d_da,
+                     const double* d_rho0, double t2_gamma_c, double t2_gamma_f,
+                     double* d_fid, double* d_rho_out, rbq_stats* d_stats);
+
+/* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
+int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBQ_H */

@@ -1,0 +1,941 @@
+// oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference algorithm (SchusterLab/rbqoc) for the propagation hot
+// path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this library; the product (rbqoc_b200 + librbq.so) never does.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or stored pulses and its
+// toolchain (Julia 1.5 + StaticArrays 0.12.5 + ForwardDiff 0.10.23 + RobotDynamics 0.2.1
+// @SchusterLab/rbqoc-stable) is absent from this image, so this restatement is pinned only
+// by (a) the analytic gates embedded in the reference (spin.jl:557,608-612), (b) scipy /
+// mpmath cross-checks of the matrix exponential and (c) a 50-digit mpmath referee
+// (oracle/referee.py).  See DESIGN.md "Oracle".
+//
+// Everything here follows the reference's *algorithm*: generic Higham-2005 Pade `exp` with
+// StaticArrays' branch thresholds + LU solve, per-knot 4x4 propagator products, forward-mode
+// dual numbers with ForwardDiff's conventions.  The engine under test uses a different
+// algorithm (closed-form SU(2) series, lane-split tangents), which is what makes the
+// comparison meaningful.  Citations are file:line in the reference tree.
+#include "../include/rbq.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+// ------------------------------------------------------------------------------------------
+// Dual numbers with ForwardDiff.Dual conventions (ForwardDiff 0.10.23, Manifest.toml:488-492).
+// The partial count is a run-time value so one type serves every model (n+m <= 180).
+// ------------------------------------------------------------------------------------------
+constexpr int MAXP = 184;
+static thread_local int g_np = 0;
+
+struct Dual {
+    double v;
+    double d[MAXP];
+    Dual() : v(0.0) { for (int i = 0; i < g_np; ++i) d[i] = 0.0; }
+    Dual(double x) : v(x) { for (int i = 0; i < g_np; ++i) d[i] = 0.0; }
+};
+inline Dual operator+(const Dual& a, const Dual& b) { Dual r; r.v = a.v + b.v; for (int i = 0; i < g_np; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+inline Dual operator-(const Dual& a, const Dual& b) { Dual r; r.v = a.v - b.v; for (int i = 0; i < g_np; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+inline Dual operator-(const Dual& a) { Dual r; r.v = -a.v; for (int i = 0; i < g_np; ++i) r.d[i] = -a.d[i]; return r; }
+inline Dual operator*(const Dual& a, const Dual& b) { Dual r; r.v = a.v * b.v; for (int i = 0; i < g_np; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+inline Dual operator/(const Dual& a, const Dual& b) { Dual r; r.v = a.v / b.v; double ib = 1.0 / b.v; for (int i = 0; i < g_np; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
+inline Dual operator+(const Dual& a, double b) { Dual r = a; r.v += b; return r; }
+inline Dual operator+(double a, const Dual& b) { return b + a; }
+inline Dual operator-(const Dual& a, double b) { Dual r = a; r.v -= b; return r; }
+inline Dual operator-(double a, const Dual& b) { return (-b) + a; }
+inline Dual operator*(const Dual& a, double b) { Dual r; r.v = a.v * b; for (int i = 0; i < g_np; ++i) r.d[i] = a.d[i] * b; return r; }
+inline Dual operator*(double a, const Dual& b) { return b * a; }
+inline Dual operator/(const Dual& a, double b) { return a * (1.0 / b); }
+inline Dual operator/(double a, const Dual& b) { return Dual(a) / b; }
+inline Dual sqrt(const Dual& a) { Dual r; r.v = std::sqrt(a.v); double s = 0.5 / r.v; for (int i = 0; i < g_np; ++i) r.d[i] = a.d[i] * s; return r; }
+// ForwardDiff: abs(d) = signbit(value(d)) ? -d : d   (derivative +1 at +0.0, -1 at -0.0)
+inline Dual absd(const Dual& a) { return std::signbit(a.v) ? -a : a; }
+inline double absd(double a) { return std::fabs(a); }
+inline double value(double a) { return a; }
+inline double value(const Dual& a) { return a.v; }
+inline double value(const std::complex<double>& a) { return std::abs(a); }  // used only for norms
+inline double magnitude(double a) { return std::fabs(a); }
+inline double magnitude(const Dual& a) { return std::fabs(a.v); }
+inline double magnitude(const std::complex<double>& a) { return std::abs(a); }
+using std::sqrt;
+
+// ------------------------------------------------------------------------------------------
+// constants: spin.jl:122-125, 142-173, 176-206, 220-247, 301-332
+// ------------------------------------------------------------------------------------------
+constexpr double PI = 3.14159265358979323846264338327950288;
+constexpr double FQ = 1.4e-2;                     // spin.jl:148
+constexpr double FBFQ_A = 0.202407;               // spin.jl:157
+constexpr double FBFQ_B = 0.5;                    // spin.jl:158
+constexpr double AYPIBY2 = 1.25e-1;               // spin.jl:159
+constexpr double PFIR_B1 = 0.049922035, PFIR_B2 = -0.095993537, PFIR_B3 = 0.050612699,
+                 PFIR_B4 = -0.004408786;          // spin.jl:166-169
+constexpr double PFIR_A2 = -2.494956002, PFIR_A3 = 2.017265875, PFIR_A4 = -0.522189400;  // 171-173
+constexpr double TTOT_ZPIBY2 = 17.857142857142858;    // spin.jl:557
+constexpr double TX_YPIBY2 = 2.1656249366575766;      // spin.jl:608
+constexpr double TZ_YPIBY2 = 15.1423305995572655;     // spin.jl:609
+
+// raw T1 times in microseconds (spin.jl:192-196); spin.jl:181-185 is the same table * 1e3 (ns)
+static const double T1_ARRAY_REDUCED[18] = {1597.923, 1627.93, 301.86,  269.03,   476.33,   1783.19,
+                                            2131.76,  2634.50, 4364.68, 2587.82,  1661.915, 1794.468,
+                                            2173.88,  1188.83, 1576.493, 965.183, 560.251,  310.88};
+static const double FBFQ_ARRAY[18] = {0.26, 0.28, 0.32,  0.34, 0.36,  0.38,  0.4,   0.42,  0.44,
+                                      0.46, 0.465, 0.47, 0.475, 0.48, 0.484, 0.488, 0.492, 0.5};  // 197-201
+
+// NEGI (spin.jl:220-223) times iso(sigma_z), iso(sigma_x)  (spin.jl:231-236), without the pi.
+static const double N0[4][4] = {{0, 0, 1, 0}, {0, 0, 0, -1}, {-1, 0, 0, 0}, {0, 1, 0, 0}};
+static const double N1[4][4] = {{0, 0, 0, 1}, {0, 0, 1, 0}, {0, -1, 0, 0}, {-1, 0, 0, 0}};
+
+template <class T> struct Mat4 { T a[4][4]; };
+template <class T> struct Vec4 { T a[4]; };
+
+template <class T> Mat4<T> matmul(const Mat4<T>& A, const Mat4<T>& B) {
+    Mat4<T> C;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            T s = A.a[i][0] * B.a[0][j];
+            for (int k = 1; k < 4; ++k) s = s + A.a[i][k] * B.a[k][j];
+            C.a[i][j] = s;
+        }
+    return C;
+}
+template <class T, class V> void matvec(const Mat4<T>& A, const V* x, V* y) {
+    V t[4];
+    for (int i = 0; i < 4; ++i) {
+        V s = A.a[i][0] * x[0];
+        for (int k = 1; k < 4; ++k) s = s + A.a[i][k] * x[k];
+        t[i] = s;
+    }
+    for (int i = 0; i < 4; ++i) y[i] = t[i];
+}
+template <class T> Mat4<T> eye4() {
+    Mat4<T> I;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) I.a[i][j] = T(i == j ? 1.0 : 0.0);
+    return I;
+}
+// c0*I + c1*A2 + c2*A2^2 + ...   (Julia's @evalpoly on a matrix argument, Horner form)
+template <class T> Mat4<T> evalpoly(const Mat4<T>& X, const double* c, int n) {
+    Mat4<T> R;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) R.a[i][j] = T(i == j ? c[n - 1] : 0.0);
+    for (int k = n - 2; k >= 0; --k) {
+        R = matmul(X, R);
+        for (int i = 0; i < 4; ++i) R.a[i][i] = R.a[i][i] + c[k];
+    }
+    return R;
+}
+// X = A \ B by LU with partial pivoting (what StaticArrays falls back to for 4x4).
+template <class T> Mat4<T> solve(Mat4<T> A, Mat4<T> B) {
+    for (int c = 0; c < 4; ++c) {
+        int p = c; double best = magnitude(A.a[c][c]);
+        for (int r = c + 1; r < 4; ++r) { double m = magnitude(A.a[r][c]); if (m > best) { best = m; p = r; } }
+        if (p != c) for (int j = 0; j < 4; ++j) { std::swap(A.a[c][j], A.a[p][j]); std::swap(B.a[c][j], B.a[p][j]); }
+        for (int r = c + 1; r < 4; ++r) {
+            T f = A.a[r][c] / A.a[c][c];
+            for (int j = c; j < 4; ++j) A.a[r][j] = A.a[r][j] - f * A.a[c][j];
+            for (int j = 0; j < 4; ++j) B.a[r][j] = B.a[r][j] - f * B.a[c][j];
+        }
+    }
+    Mat4<T> X;
+    for (int j = 0; j < 4; ++j)
+        for (int r = 3; r >= 0; --r) {
+            T s = B.a[r][j];
+            for (int k = r + 1; k < 4; ++k) s = s - A.a[r][k] * X.a[k][j];
+            X.a[r][j] = s / A.a[r][r];
+        }
+    return X;
+}
+
+// ------------------------------------------------------------------------------------------
+// exp(::SMatrix{4,4}) of StaticArrays 0.12.5 (src/expm.jl), itself adapted from Julia Base
+// `exp!` / Higham 2005: no balancing, 1-norm thresholds 0.015 / 0.25 / 0.95 / 2.1, Pade-13 with
+// scaling by 2^ceil(log2(nA/5.4)) otherwise.  Un-vendored dependency (Manifest.toml:1410-1414):
+// restated from its published algorithm; the degree-13 table is cross-checked against the
+// reference's in-tree copy at spin26.jl:25-40.  Reference call sites: spin13.jl:46,
+// spin12.jl:168,175-176, spin30.jl:108,113,181, spin15.jl:56, spin.jl:445,478,532.
+// ------------------------------------------------------------------------------------------
+template <class T> Mat4<T> expm_ref(const Mat4<T>& A_in, int* degree_out = nullptr) {
+    Mat4<T> A = A_in;
+    double nA = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < 4; ++i) s += magnitude(A.a[i][j]);
+        nA = std::max(nA, s);
+    }
+    Mat4<T> U, V;
+    int si = 0, deg;
+    if (nA <= 2.1) {
+        Mat4<T> A2 = matmul(A, A);
+        if (nA > 0.95) {
+            static const double cu[5] = {8821612800., 302702400., 2162160., 3960., 1.};
+            static const double cv[5] = {17643225600., 2075673600., 30270240., 110880., 90.};
+            U = matmul(A, evalpoly(A2, cu, 5)); V = evalpoly(A2, cv, 5); deg = 9;
+        } else if (nA > 0.25) {
+            static const double cu[4] = {8648640., 277200., 1512., 1.};
+            static const double cv[4] = {17297280., 1995840., 25200., 56.};
+            U = matmul(A, evalpoly(A2, cu, 4)); V = evalpoly(A2, cv, 4); deg = 7;
+        } else if (nA > 0.015) {
+            static const double cu[3] = {15120., 420., 1.};
+            static const double cv[3] = {30240., 3360., 30.};
+            U = matmul(A, evalpoly(A2, cu, 3)); V = evalpoly(A2, cv, 3); deg = 5;
+        } else {
+            static const double cu[2] = {60., 1.};
+            static const double cv[2] = {120., 12.};
+            U = matmul(A, evalpoly(A2, cu, 2)); V = evalpoly(A2, cv, 2); deg = 3;
+        }
+    } else {
+        deg = 13;
+        double s = std::log2(nA / 5.4);
+        if (s > 0) {
+            si = (int)std::ceil(s);
+            double sc = std::ldexp(1.0, -si);
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) A.a[i][j] = A.a[i][j] * sc;
+        }
+        static const double C[14] = {64764752532480000., 32382376266240000., 7771770303897600.,
+                                     1187353796428800.,  129060195264000.,   10559470521600.,
+                                     670442572800.,      33522128640.,       1323241920.,
+                                     40840800.,          960960.,            16380.,
+                                     182.,               1.};
+        Mat4<T> A2 = matmul(A, A), A4 = matmul(A2, A2), A6 = matmul(A2, A4);
+        Mat4<T> t1, t2, u, v;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double id = (i == j) ? 1.0 : 0.0;
+                t1.a[i][j] = C[13] * A6.a[i][j] + C[11] * A4.a[i][j] + C[9] * A2.a[i][j];
+                t2.a[i][j] = C[12] * A6.a[i][j] + C[10] * A4.a[i][j] + C[8] * A2.a[i][j];
+                u.a[i][j] = C[7] * A6.a[i][j] + C[5] * A4.a[i][j] + C[3] * A2.a[i][j] + T(C[1] * id);
+                v.a[i][j] = C[6] * A6.a[i][j] + C[4] * A4.a[i][j] + C[2] * A2.a[i][j] + T(C[0] * id);
+            }
+        Mat4<T> a6t1 = matmul(A6, t1), a6t2 = matmul(A6, t2);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { u.a[i][j] = a6t1.a[i][j] + u.a[i][j]; v.a[i][j] = a6t2.a[i][j] + v.a[i][j]; }
+        U = matmul(A, u); V = v;
+    }
+    Mat4<T> P, Q;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { P.a[i][j] = V.a[i][j] + U.a[i][j]; Q.a[i][j] = V.a[i][j] - U.a[i][j]; }
+    Mat4<T> E = solve(Q, P);
+    for (int t = 0; t < si; ++t) E = matmul(E, E);
+    if (degree_out) *degree_out = deg;
+    return E;
+}
+
+// dt * (f * NEGI_H0_ISO + a * NEGI_H1_ISO)   (spin.jl:234-238)
+template <class T> Mat4<T> generator(const T& f, const T& a, const T& dt) {
+    Mat4<T> G;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) G.a[i][j] = dt * (f * (PI * N0[i][j]) + a * (PI * N1[i][j]));
+    return G;
+}
+template <class T> Mat4<T> propagator(const T& f, const T& a, const T& dt) { return expm_ref(generator(f, a, dt)); }
+
+// ------------------------------------------------------------------------------------------
+// T1(flux) model: spin.jl:203-206 (gridded-linear interpolant, Flat extrapolation), 366, 393, 396
+// Interpolations.jl semantics: clamp to the knot range (a clamped dual loses its partials),
+// interval by searchsortedlast clamped to [1, n-1], value (1-w) y_i + w y_{i+1}.
+// ------------------------------------------------------------------------------------------
+template <class T> T interp_t1(const T& fbfq_in, double scale) {
+    T x = fbfq_in;
+    if (value(x) > FBFQ_ARRAY[17]) x = T(FBFQ_ARRAY[17]);
+    else if (value(x) < FBFQ_ARRAY[0]) x = T(FBFQ_ARRAY[0]);
+    int i = 0;
+    while (i < 16 && FBFQ_ARRAY[i + 1] <= value(x)) ++i;  // searchsortedlast, clamped to n-1
+    T w = (x - FBFQ_ARRAY[i]) / (FBFQ_ARRAY[i + 1] - FBFQ_ARRAY[i]);
+    return (1.0 - w) * (T1_ARRAY_REDUCED[i] * scale) + w * (T1_ARRAY_REDUCED[i + 1] * scale);
+}
+template <class T> T amp_fbfq_lo(const T& a) { return -absd(a) * FBFQ_A + FBFQ_B; }           // spin.jl:366
+template <class T> T amp_t1_spline(const T& a) { return interp_t1(amp_fbfq_lo(a), 1e3); }     // ns, spin.jl:393
+template <class T> T amp_t1_reduced_spline(const T& a) { return interp_t1(amp_fbfq_lo(a), 1.0); }  // us, spin.jl:396
+
+// ------------------------------------------------------------------------------------------
+// model dimensions: spin13.jl:23-26,39-40; spin12.jl:26-33; spin15.jl:43-46; spin11.jl:53-55;
+// spin17.jl state_dim; spin18.jl:23-28; spin30.jl:27-32,67-70
+// ------------------------------------------------------------------------------------------
+static int state_dim(const rbq_model_params* p) {
+    switch (p->model_id) {
+    case RBQ_MODEL_SPIN13: return 11;
+    case RBQ_MODEL_SPIN12: case RBQ_MODEL_SPIN18: return 43;
+    case RBQ_MODEL_SPIN15: return 11 + (p->decay_aware ? 1 : 0);
+    case RBQ_MODEL_SPIN11: case RBQ_MODEL_SPIN17:
+        if (p->derivative_order < 0 || p->derivative_order > 2) return RBQ_E_MODEL;
+        return 11 + 4 * p->derivative_order;
+    case RBQ_MODEL_SPIN30:
+        if (p->sample_state_count < 1 || p->sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
+        return 15 + 41 * p->sample_state_count;
+    default: return RBQ_E_MODEL;
+    }
+}
+static int control_dim(const rbq_model_params* p) {
+    if (p->model_id == RBQ_MODEL_SPIN15) return 1 + (p->time_optimal ? 1 : 0);
+    return state_dim(p) < 0 ? RBQ_E_MODEL : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// discrete dynamics, one function per reference file
+// ------------------------------------------------------------------------------------------
+// the [int a, a, da] Euler chain shared by every model (spin13.jl:49-51)
+template <class T> void control_chain(const T* x, int base, const T& u, const T& dt, T* xn) {
+    xn[base] = x[base] + x[base + 1] * dt;
+    xn[base + 1] = x[base + 1] + x[base + 2] * dt;
+    xn[base + 2] = x[base + 2] + u * dt;
+}
+
+// spin13.jl:44-58
+template <class T> void step_spin13(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    Mat4<T> E = propagator(T(p->fq), x[9], dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    control_chain(x, 8, u[0], dt, xn);
+}
+// spin12.jl:165-192 (the stray `p` at :184 is a typo in the reference and is ignored)
+template <class T> void step_spin12(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    Mat4<T> E = propagator(T(p->fq), x[9], dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    control_chain(x, 8, u[0], dt, xn);
+    Mat4<T> Ep = propagator(T(p->fq_samples[0]), x[9], dt);
+    Mat4<T> En = propagator(T(p->fq_samples[1]), x[9], dt);
+    for (int s = 0; s < 4; ++s) matvec(Ep, x + 11 + 4 * s, xn + 11 + 4 * s);
+    for (int s = 4; s < 8; ++s) matvec(En, x + 11 + 4 * s, xn + 11 + 4 * s);
+}
+// spin18.jl:162-190
+template <class T> void step_spin18(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    Mat4<T> E = propagator(T(p->fq), x[9], dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    control_chain(x, 8, u[0], dt, xn);
+    Mat4<T> Ep = propagator(T(p->fq), x[9] + p->namp, dt);
+    Mat4<T> En = propagator(T(p->fq), x[9] - p->namp, dt);
+    for (int s = 0; s < 4; ++s) matvec(Ep, x + 11 + 4 * s, xn + 11 + 4 * s);
+    for (int s = 4; s < 8; ++s) matvec(En, x + 11 + 4 * s, xn + 11 + 4 * s);
+}
+// spin15.jl:50-73
+template <class T> void step_spin15(const rbq_model_params* p, const T* x, const T* u, const T& dt_in, T* xn) {
+    T dt = dt_in;
+    if (p->time_optimal) dt = u[1] * u[1];                                  // spin15.jl:52-54
+    Mat4<T> E = propagator(T(p->fq), x[9], dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    xn[8] = x[8] + dt * x[9];
+    xn[9] = x[9] + dt * x[10];
+    xn[10] = x[10] + dt * u[0];
+    if (p->decay_aware) xn[11] = x[11] + dt * (1.0 / amp_t1_reduced_spline(x[9]));  // spin15.jl:66-69
+}
+// spin11.jl:64-117 (which = 0, H0) and spin17.jl:61-114 (which = 1, H1)
+template <class T> void step_spin11_17(const rbq_model_params* p, int which, const T* x, const T* u, const T& dt, T* xn) {
+    const double (*NH)[4] = which == 0 ? N0 : N1;
+    Mat4<T> E = propagator(T(p->fq), x[9], dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    control_chain(x, 8, u[0], dt, xn);
+    if (p->derivative_order >= 1) {                                           // spin11.jl:83-86
+        T w[4];
+        for (int i = 0; i < 4; ++i) {
+            T s = T(0.0);
+            for (int k = 0; k < 4; ++k) s = s + dt * (PI * NH[i][k]) * x[k];
+            w[i] = x[11 + i] + s;
+        }
+        matvec(E, w, xn + 11);
+    }
+    if (p->derivative_order >= 2) {                                           // spin11.jl:101-104
+        T w[4];
+        for (int i = 0; i < 4; ++i) {
+            T s = T(0.0);
+            for (int k = 0; k < 4; ++k) s = s + dt * (2.0 * PI * NH[i][k]) * x[11 + k];
+            w[i] = x[15 + i] + s;
+        }
+        matvec(E, w, xn + 15);
+    }
+}
+// generic lower Cholesky, the `cholesky(Symmetric(cov)).L` of spin30.jl:140
+template <class T> void cholesky_lower(int n, const T* A, T* L) {
+    for (int i = 0; i < n * n; ++i) L[i] = T(0.0);
+    for (int j = 0; j < n; ++j) {
+        T s = A[j * n + j];
+        for (int k = 0; k < j; ++k) s = s - L[j * n + k] * L[j * n + k];
+        T ljj = sqrt(s);
+        L[j * n + j] = ljj;
+        for (int i = j + 1; i < n; ++i) {
+            T t = A[i * n + j];
+            for (int k = 0; k < j; ++k) t = t - L[i * n + k] * L[j * n + k];
+            L[i * n + j] = t / ljj;
+        }
+    }
+}
+// spin30.jl:86-174 (unscented_transform) and 177-202
+template <class T> void step_spin30(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    const T a = x[13];
+    Mat4<T> E = propagator(T(p->fq), a, dt);                                  // spin30.jl:181
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    matvec(E, x + 8, xn + 8);
+    control_chain(x, 12, u[0], dt, xn);
+    const double fq_chol5 = std::sqrt(p->fq_cov);                             // spin30.jl:102
+    Mat4<T> Ep = propagator(T(p->fq + fq_chol5), a, dt);                      // spin30.jl:108
+    Mat4<T> En = propagator(T(p->fq - fq_chol5), a, dt);                      // spin30.jl:113
+    for (int c = 0; c < p->sample_state_count; ++c) {
+        const int off = 15 + 41 * c;
+        T s[10][4];
+        for (int j = 0; j < 10; ++j) {
+            const Mat4<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
+            matvec(M, x + off + 4 * j, s[j]);
+        }
+        T sm[4];
+        for (int i = 0; i < 4; ++i) {                                          // spin30.jl:115-118
+            T acc = s[0][i];
+            for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
+            sm[i] = 0.1 * acc;
+        }
+        T d[10][4];
+        for (int j = 0; j < 10; ++j) for (int i = 0; i < 4; ++i) d[j][i] = s[j][i] - sm[i];
+        T cov[25];
+        for (int i = 0; i < 25; ++i) cov[i] = T(0.0);
+        const double cf = 1.0 / (2.0 * p->alpha * p->alpha);                  // spin30.jl:130
+        T scov[4][4];
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 4; ++k) {
+                T acc = d[0][i] * d[0][k];
+                for (int j = 1; j < 10; ++j) acc = acc + d[j][i] * d[j][k];
+                scov[i][k] = cf * acc;
+                cov[i * 5 + k] = scov[i][k];
+            }
+        cov[24] = T(p->fq_cov);                                                // spin30.jl:138
+        T L[25];
+        cholesky_lower(5, cov, L);
+        T snew[10][4];
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) {
+                T col = p->alpha * L[i * 5 + j];                               // spin30.jl:140-145
+                snew[j][i] = sm[i] + col;
+                snew[5 + j][i] = sm[i] - col;
+            }
+        for (int i = 0; i < 4; ++i) { snew[4][i] = sm[i]; snew[9][i] = sm[i]; }
+        for (int j = 0; j < 10; ++j) {                                         // spin30.jl:157-166
+            T nn = snew[j][0] * snew[j][0];
+            for (int i = 1; i < 4; ++i) nn = nn + snew[j][i] * snew[j][i];
+            T nr = sqrt(nn);
+            for (int i = 0; i < 4; ++i) xn[off + 4 * j + i] = snew[j][i] / nr;
+        }
+        T pen = T(0.0);                                                        // spin30.jl:168-169
+        for (int i = 0; i < 4; ++i) pen = pen + scov[i][i] * p->S_diag[i];
+        for (int i = 0; i < 4; ++i) {
+            T dn = sm[i] - x[p->nominal_offset[c] + i];
+            pen = pen + dn * p->S_diag[i] * dn;
+        }
+        xn[off + 40] = pen;
+    }
+}
+
+template <class T> int step(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    switch (p->model_id) {
+    case RBQ_MODEL_SPIN13: step_spin13(p, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN12: step_spin12(p, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN18: step_spin18(p, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN15: step_spin15(p, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN11: step_spin11_17(p, 0, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN17: step_spin11_17(p, 1, x, u, dt, xn); return 0;
+    case RBQ_MODEL_SPIN30: step_spin30(p, x, u, dt, xn); return 0;
+    default: return RBQ_E_MODEL;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gates and fidelities: spin.jl:301-323, 1035-1037, 1101-1104, 1198-1240
+// ------------------------------------------------------------------------------------------
+typedef std::complex<double> cplx;
+static bool gate_matrix(int gate, cplx g[2][2]) {
+    const double r = 1.0 / std::sqrt(2.0);
+    const cplx I(0, 1);
+    switch (gate) {
+    case RBQ_GATE_ZPIBY2: g[0][0] = (1.0 - I) * r; g[0][1] = 0; g[1][0] = 0; g[1][1] = (1.0 + I) * r; return true;
+    case RBQ_GATE_YPIBY2: g[0][0] = r; g[0][1] = -r; g[1][0] = r; g[1][1] = r; return true;
+    case RBQ_GATE_XPIBY2: g[0][0] = r; g[0][1] = -I * r; g[1][0] = -I * r; g[1][1] = r; return true;
+    case RBQ_GATE_XPI: g[0][0] = 0; g[0][1] = -I; g[1][0] = -I; g[1][1] = 0; return true;
+    }
+    return false;
+}
+// get_mat_iso, rbqoc.jl:204-210
+static void mat_iso(const cplx g[2][2], double G[4][4]) {
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            G[i][j] = g[i][j].real(); G[i][j + 2] = -g[i][j].imag();
+            G[i + 2][j] = g[i][j].imag(); G[i + 2][j + 2] = g[i][j].real();
+        }
+}
+// spin.jl:1035-1037
+template <class R> R fidelity_vec_iso2(const R* s1, const R* s2) {
+    R a = s1[0] * s2[0] + s1[1] * s2[1] + s1[2] * s2[2] + s1[3] * s2[3];
+    R b = s1[0] * s2[2] + s1[1] * s2[3] - s1[2] * s2[0] - s1[3] * s2[1];
+    return a * a + b * b;
+}
+
+// Hermitian 2x2 eigen-decomposition -> principal square root (complex when an eigenvalue is
+// negative, as Julia's sqrt(::Hermitian) does).
+static void sqrt_herm2(const cplx m[2][2], cplx out[2][2]) {
+    double a = m[0][0].real(), d = m[1][1].real();
+    cplx b = 0.5 * (m[0][1] + std::conj(m[1][0]));
+    double tr = a + d, df = a - d;
+    double disc = std::sqrt(df * df + 4.0 * std::norm(b));
+    double l1 = 0.5 * (tr + disc), l2 = 0.5 * (tr - disc);
+    cplx v1[2], v2[2];
+    if (std::abs(b) > 0) {
+        v1[0] = b; v1[1] = l1 - a;
+        double n1 = std::sqrt(std::norm(v1[0]) + std::norm(v1[1]));
+        v1[0] /= n1; v1[1] /= n1;
+        v2[0] = -std::conj(v1[1]); v2[1] = std::conj(v1[0]);
+    } else {
+        if (a >= d) { v1[0] = 1; v1[1] = 0; v2[0] = 0; v2[1] = 1; }
+        else { v1[0] = 0; v1[1] = 1; v2[0] = 1; v2[1] = 0; }
+    }
+    cplx s1 = l1 >= 0 ? cplx(std::sqrt(l1), 0) : cplx(0, std::sqrt(-l1));
+    cplx s2 = l2 >= 0 ? cplx(std::sqrt(l2), 0) : cplx(0, std::sqrt(-l2));
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) out[i][j] = s1 * v1[i] * std::conj(v1[j]) + s2 * v2[i] * std::conj(v2[j]);
+}
+// general 2x2 principal square root (the outer `sqrt` of spin.jl:1103 acts on a non-Hermitian
+// -typed product): sqrt(M) = (M + s I)/t, s = sqrt(det M), t = sqrt(tr M + 2 s).
+static cplx tr_sqrt_general2(const cplx m[2][2]) {
+    cplx det = m[0][0] * m[1][1] - m[0][1] * m[1][0];
+    cplx tr = m[0][0] + m[1][1];
+    cplx s = std::sqrt(det);
+    cplx t = std::sqrt(tr + 2.0 * s);
+    if (std::abs(t) == 0) return 0;
+    return (tr + 2.0 * s) / t;
+}
+// spin.jl:1101-1104: real(tr(sqrt(sqrt(m1) * m2 * sqrt(m1))))   (square-ROOT fidelity)
+static double fidelity_mat(const cplx m1[2][2], const cplx m2[2][2]) {
+    cplx r[2][2], t[2][2], q[2][2];
+    sqrt_herm2(m1, r);
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i][j] = r[i][0] * m2[0][j] + r[i][1] * m2[1][j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) q[i][j] = t[i][0] * r[0][j] + t[i][1] * r[1][j];
+    return tr_sqrt_general2(q).real();
+}
+// closed form for 2x2 states: F = sqrt(tr(m1 m2) + 2 sqrt(det m1 det m2)); identical in exact
+// arithmetic, free of the sqrt(rounding) noise the eigen route has for pure targets.
+static double fidelity_mat_closed(const cplx m1[2][2], const cplx m2[2][2]) {
+    double trp = 0;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) trp += (m1[i][j] * m2[j][i]).real();
+    double d1 = (m1[0][0] * m1[1][1] - m1[0][1] * m1[1][0]).real();
+    double d2 = (m2[0][0] * m2[1][1] - m2[0][1] * m2[1][0]).real();
+    double dd = std::max(d1, 0.0) * std::max(d2, 0.0);
+    return std::sqrt(std::max(trp + 2.0 * std::sqrt(dd), 0.0));
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  The reference seeds Julia's MersenneTwister
+// (spin.jl:1131,1179), which cannot be reproduced outside Julia; the engine and this oracle
+// therefore share a counter-based generator keyed by the global sample index.
+//   counter = (index_lo, index_hi, j, stream), key = (seed_lo, seed_hi)
+//   stream 0: j=0,1 -> 4 uniforms of psi0;  stream 1: j=0 -> normals (fq, da);
+//   stream 2: j -> white-noise pair (x_{2j}, x_{2j+1}) of the pink filter.
+// ------------------------------------------------------------------------------------------
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline double u53(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0); }
+static void philox_uniform2(uint64_t index, uint64_t seed, uint32_t j, uint32_t stream, double* u0, double* u1) {
+    uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), j, stream};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    *u0 = u53(o[0], o[1]);
+    *u1 = u53(o[2], o[3]);
+}
+static void philox_normal2(uint64_t index, uint64_t seed, uint32_t j, uint32_t stream, double* z0, double* z1) {
+    double u0, u1;
+    philox_uniform2(index, seed, j, stream, &u0, &u1);
+    double r = std::sqrt(-2.0 * std::log(1.0 - u0));   // 1-u0 in (0,1]
+    double ang = 2.0 * PI * u1;
+    *z0 = r * std::cos(ang);
+    *z1 = r * std::sin(ang);
+}
+// gen_rand_state_iso recipe (spin.jl:1132-1136): rand(2) + im*rand(2), normalised, [re; im]
+static void sample_psi0(uint64_t index, uint64_t seed, double psi[4]) {
+    philox_uniform2(index, seed, 0, 0, &psi[0], &psi[1]);
+    philox_uniform2(index, seed, 1, 0, &psi[2], &psi[3]);
+    double n = std::sqrt(psi[0] * psi[0] + psi[1] * psi[1] + psi[2] * psi[2] + psi[3] * psi[3]);
+    for (int i = 0; i < 4; ++i) psi[i] /= n;
+}
+static void sample_static(uint64_t index, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                          double da_sigma, double* fq, double* da) {
+    double z0, z1;
+    philox_normal2(index, seed, 0, 1, &z0, &z1);
+    double dev = fq_rel_sigma * z0;
+    if (dev > fq_rel_clip) dev = fq_rel_clip;
+    if (dev < -fq_rel_clip) dev = -fq_rel_clip;
+    *fq = fq0 * (1.0 + dev);
+    *da = da_sigma * z1;
+}
+
+// gen_pink_noise, spin.jl:1178-1192, on a given white sequence xs
+static void pink_filter(const double* xs, int64_t count, double dt_inv, double* ys) {
+    for (int64_t i = 0; i < count; ++i) {
+        double y = PFIR_B1 * xs[i];
+        if (i >= 1) y += PFIR_B2 * xs[i - 1] - PFIR_A2 * ys[i - 1];
+        if (i >= 2) y += PFIR_B3 * xs[i - 2] - PFIR_A3 * ys[i - 2];
+        if (i >= 3) y += PFIR_B4 * xs[i - 3] - PFIR_A4 * ys[i - 3];
+        ys[i] = y;
+    }
+    for (int64_t i = 0; i < count; ++i) ys[i] *= dt_inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// compute_fidelities for iso state vectors, spin.jl:1198-1240 (states are BigFloat in
+// run_sim_prop, spin.jl:1581: long double is the widest native type here)
+// ------------------------------------------------------------------------------------------
+typedef long double xreal;
+static void gate_targets(int gate, const xreal* s0, xreal tg[4][4]) {
+    cplx g[2][2];
+    gate_matrix(gate, g);
+    double G1[4][4], G2[4][4], G3[4][4];
+    mat_iso(g, G1);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += G1[i][k] * G1[k][j]; G2[i][j] = s; }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += G2[i][k] * G1[k][j]; G3[i][j] = s; }
+    for (int i = 0; i < 4; ++i) {
+        tg[0][i] = s0[i];
+        xreal a = 0, b = 0, c = 0;
+        for (int k = 0; k < 4; ++k) { a += (xreal)G1[i][k] * s0[k]; b += (xreal)G2[i][k] * s0[k]; c += (xreal)G3[i][k] * s0[k]; }
+        tg[1][i] = a; tg[2][i] = b; tg[3][i] = c;
+    }
+}
+
+// integrate_prop_schroed! (spin.jl:438-452) + compute_fidelities for ONE sample
+static void sim_schroed(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, double fq,
+                        double da, const double* psi0, double* fid, double* state_out) {
+    Mat4<double> prop = eye4<double>();
+    for (int64_t j = 0; j < nk; ++j) {
+        Mat4<double> H;                                   // hamiltonian = negi_h0 + controls[j]*NEGI_H1_ISO
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) H.a[r][c] = (fq * (PI * N0[r][c]) + (controls[j] + da) * (PI * N1[r][c])) * dt;
+        prop = matmul(expm_ref(H), prop);
+    }
+    xreal s0[4], st[4], tg[4][4];
+    for (int i = 0; i < 4; ++i) { s0[i] = psi0[i]; st[i] = psi0[i]; }
+    gate_targets(gate, s0, tg);
+    if (fid) fid[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+    for (int64_t g = 1; g <= gate_count; ++g) {
+        xreal nx[4];
+        for (int i = 0; i < 4; ++i) { xreal s = 0; for (int k = 0; k < 4; ++k) s += (xreal)prop.a[i][k] * st[k]; nx[i] = s; }
+        for (int i = 0; i < 4; ++i) st[i] = nx[i];
+        if (fid) fid[g] = (double)fidelity_vec_iso2<xreal>(st, tg[g % 4]);
+    }
+    if (state_out) for (int i = 0; i < 4; ++i) state_out[i] = (double)st[i];
+}
+
+// integrate_prop_schroedda! (spin.jl:469-484) for ONE sample
+static void sim_schroedda(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, double fq,
+                          const double* noise, int64_t noise_len, double noise_dt_inv, const double* psi0,
+                          double* fid, double* state_out) {
+    xreal s0[4], st[4], tg[4][4];
+    for (int i = 0; i < 4; ++i) { s0[i] = psi0[i]; st[i] = psi0[i]; }
+    gate_targets(gate, s0, tg);
+    if (fid) fid[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+    double time = 0.0;
+    for (int64_t g = 1; g <= gate_count; ++g) {
+        for (int64_t j = 0; j < nk; ++j) {
+            int64_t idx = (int64_t)std::floor(time * noise_dt_inv);   // 0-based version of spin.jl:476
+            if (idx >= noise_len) idx = noise_len - 1;                 // (the reference would throw)
+            double delta_a = noise[idx];
+            Mat4<double> H;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) H.a[r][c] = (fq * (PI * N0[r][c]) + (controls[j] + delta_a) * (PI * N1[r][c])) * dt;
+            Mat4<double> U = expm_ref(H);
+            xreal nx[4];
+            for (int i = 0; i < 4; ++i) { xreal s = 0; for (int k = 0; k < 4; ++k) s += (xreal)U.a[i][k] * st[k]; nx[i] = s; }
+            for (int i = 0; i < 4; ++i) st[i] = nx[i];
+            time = time + dt;
+        }
+        if (fid) fid[g] = (double)fidelity_vec_iso2<xreal>(st, tg[g % 4]);
+    }
+    if (state_out) for (int i = 0; i < 4; ++i) state_out[i] = (double)st[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Lindblad, vec form: spin.jl:240-247, 255-276, 521-539
+// ------------------------------------------------------------------------------------------
+static void kron2(const cplx A[2][2], const cplx B[2][2], cplx K[4][4]) {
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l)
+        K[2 * i + k][2 * j + l] = A[i][j] * B[k][l];
+}
+struct LindbladOps { cplx H0v[4][4], H1v[4][4], LOP[4][4]; };
+static LindbladOps make_lindblad_ops(double fq) {
+    LindbladOps o;
+    const cplx I(0, 1);
+    cplx Id[2][2] = {{1, 0}, {0, 1}};
+    cplx H0[2][2] = {{fq * -I * PI, 0}, {0, -(fq * -I * PI)}};          // FQ_NEGI_H0_, spin.jl:240
+    cplx H1[2][2] = {{0, -I * PI}, {-I * PI, 0}};                        // NEGI_H1_, spin.jl:244
+    cplx H0t[2][2] = {{H0[0][0], H0[1][0]}, {H0[0][1], H0[1][1]}};
+    cplx H1t[2][2] = {{H1[0][0], H1[1][0]}, {H1[0][1], H1[1][1]}};
+    cplx A[4][4], B[4][4];
+    kron2(Id, H0, A); kron2(H0t, Id, B);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) o.H0v[i][j] = A[i][j] - B[i][j];      // spin.jl:242
+    kron2(Id, H1, A); kron2(H1t, Id, B);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) o.H1v[i][j] = A[i][j] - B[i][j];      // spin.jl:246
+    cplx GG[2][2] = {{1, 0}, {0, 0}}, GE[2][2] = {{0, 1}, {0, 0}}, EG[2][2] = {{0, 0}, {1, 0}}, EE[2][2] = {{0, 0}, {0, 1}};
+    cplx k1[4][4], k2[4][4], k3[4][4], k4[4][4], k5[4][4], k6[4][4];
+    kron2(GE, GE, k1); kron2(Id, EE, k2); kron2(EE, Id, k3);              // LOPP_VISO_, spin.jl:267
+    kron2(EG, EG, k4); kron2(Id, GG, k5); kron2(GG, Id, k6);              // LOPM_VISO_, spin.jl:272
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j)
+        o.LOP[i][j] = (k1[i][j] - 0.5 * k2[i][j] - 0.5 * k3[i][j]) + (k4[i][j] - 0.5 * k5[i][j] - 0.5 * k6[i][j]);
+    return o;
+}
+// integrate_prop_lindbladt1! for one realisation.  rho0/rho_out: vec (column-major) 4 complex.
+static void sim_lindbladt1(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, double fq,
+                           double da, const cplx* rho0v, double* fid, double* fid_closed, cplx* rho_out) {
+    LindbladOps o = make_lindblad_ops(fq);
+    Mat4<cplx> prop = eye4<cplx>();
+    for (int64_t j = 0; j < nk; ++j) {
+        double c1 = controls[j] + da;
+        double gamma1 = 1.0 / amp_t1_spline<double>(c1);                      // spin.jl:529
+        Mat4<cplx> L;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) L.a[r][c] = (o.H0v[r][c] + c1 * o.H1v[r][c] + gamma1 * o.LOP[r][c]) * dt;
+        prop = matmul(expm_ref(L), prop);
+    }
+    cplx g[2][2], g2[2][2], g3[2][2];
+    gate_matrix(gate, g);
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g2[i][j] = g[i][0] * g[0][j] + g[i][1] * g[1][j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g3[i][j] = g2[i][0] * g[0][j] + g2[i][1] * g[1][j];
+    cplx r0[2][2] = {{rho0v[0], rho0v[2]}, {rho0v[1], rho0v[3]}};
+    cplx tg[4][2][2];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[0][i][j] = r0[i][j];
+    const cplx (*gs[3])[2] = {g, g2, g3};
+    for (int q = 0; q < 3; ++q) {                                              // id_k = g_k * id0 * g_k'
+        cplx t[2][2];
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i][j] = gs[q][i][0] * r0[0][j] + gs[q][i][1] * r0[1][j];
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[q + 1][i][j] = t[i][0] * std::conj(gs[q][j][0]) + t[i][1] * std::conj(gs[q][j][1]);
+    }
+    cplx v[4] = {rho0v[0], rho0v[1], rho0v[2], rho0v[3]};
+    for (int64_t k = 0; k <= gate_count; ++k) {
+        if (k > 0) matvec(prop, v, v);
+        cplx m[2][2] = {{v[0], v[2]}, {v[1], v[3]}};
+        if (fid) fid[k] = fidelity_mat(m, tg[k % 4]);
+        if (fid_closed) fid_closed[k] = fidelity_mat_closed(m, tg[k % 4]);
+    }
+    if (rho_out) for (int i = 0; i < 4; ++i) rho_out[i] = v[i];
+}
+
+}  // namespace orc
+
+// =============================================================================================
+// C exports (loaded with ctypes by oracle/oracle.py)
+// =============================================================================================
+using namespace orc;
+extern "C" {
+
+int orc_state_dim(const rbq_model_params* p) { return p ? state_dim(p) : RBQ_E_NULL; }
+int orc_control_dim(const rbq_model_params* p) { return p ? control_dim(p) : RBQ_E_NULL; }
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// A, E row-major 4x4.  Returns the Pade degree used.
+int orc_expm4(const double* A, double* E) {
+    Mat4<double> M; for (int i = 0; i < 16; ++i) M.a[i / 4][i % 4] = A[i];
+    int deg; Mat4<double> R = expm_ref(M, &deg);
+    for (int i = 0; i < 16; ++i) E[i] = R.a[i / 4][i % 4];
+    return deg;
+}
+// complex row-major 4x4 as interleaved (re,im)
+int orc_expm4c(const double* A, double* E) {
+    Mat4<cplx> M; for (int i = 0; i < 16; ++i) M.a[i / 4][i % 4] = cplx(A[2 * i], A[2 * i + 1]);
+    int deg; Mat4<cplx> R = expm_ref(M, &deg);
+    for (int i = 0; i < 16; ++i) { E[2 * i] = R.a[i / 4][i % 4].real(); E[2 * i + 1] = R.a[i / 4][i % 4].imag(); }
+    return deg;
+}
+void orc_propagator(double fq, double a, double dt, double* E) {
+    Mat4<double> R = propagator<double>(fq, a, dt);
+    for (int i = 0; i < 16; ++i) E[i] = R.a[i / 4][i % 4];
+}
+double orc_t1_ns(double a) { return amp_t1_spline<double>(a); }
+double orc_t1_reduced_us(double a) { return amp_t1_reduced_spline<double>(a); }
+
+int orc_step(const rbq_model_params* p, const double* x, const double* u, double t, double dt, double* xn) {
+    (void)t;
+    if (!p || !x || !u || !xn) return RBQ_E_NULL;
+    int n = state_dim(p); if (n < 0) return n;
+    std::vector<double> tmp(n);
+    int rc = step<double>(p, x, u, dt, tmp.data());
+    if (rc == 0) std::memcpy(xn, tmp.data(), sizeof(double) * n);
+    return rc;
+}
+// ForwardDiff.jacobian(s -> discrete_dynamics(RK3, model, s[ix], s[iu], t, dt), [x;u]),
+// written column-major n x (n+m)  (RobotDynamics 0.2.1 default discrete_jacobian!)
+int orc_jacobian(const rbq_model_params* p, const double* x, const double* u, double t, double dt, double* AB) {
+    (void)t;
+    if (!p || !x || !u || !AB) return RBQ_E_NULL;
+    int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
+    g_np = n + m;
+    std::vector<Dual> xd(n), ud(m), xo(n);
+    for (int i = 0; i < n; ++i) { xd[i] = Dual(x[i]); xd[i].d[i] = 1.0; }
+    for (int j = 0; j < m; ++j) { ud[j] = Dual(u[j]); ud[j].d[n + j] = 1.0; }
+    int rc = step<Dual>(p, xd.data(), ud.data(), Dual(dt), xo.data());
+    if (rc == 0)
+        for (int c = 0; c < n + m; ++c) for (int r = 0; r < n; ++r) AB[(size_t)c * n + r] = xo[r].d[c];
+    g_np = 0;
+    return rc;
+}
+int orc_jacobians(const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* dt, double* AB) {
+    int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
+    int rc = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < K; ++k) {
+        int r = orc_jacobian(p, X + k * n, U + k * m, 0.0, dt[k], AB + (size_t)k * n * (n + m));
+        if (r) rc = r;
+    }
+    return rc;
+}
+// TO.rollout!: x[k+1] = discrete_dynamics(RK3, model, x[k], u[k], t, dt[k]); B trajectories
+int orc_rollout(const rbq_model_params* p, int64_t B, int64_t N, const double* x0, const double* U, const double* dt, double* X) {
+    int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; ++b) {
+        double* Xb = X + (size_t)b * N * n;
+        std::memcpy(Xb, x0 + b * n, sizeof(double) * n);
+        for (int64_t k = 0; k + 1 < N; ++k)
+            step<double>(p, Xb + k * n, U + ((size_t)b * (N - 1) + k) * m, dt[k], Xb + (k + 1) * n);
+    }
+    return 0;
+}
+// closed-loop rollout of the iLQR forward pass (Altro `rollout!` with gains; external, from its
+// published algorithm): du = K (x - xref) + alpha d
+int orc_rollout_closedloop(const rbq_model_params* p, int64_t N, const double* Xref, const double* Uref, const double* K,
+                           const double* d, const double* dt, int64_t nalpha, const double* alphas, double* X, double* Uout) {
+    int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
+    for (int64_t c = 0; c < nalpha; ++c) {
+        double* Xc = X + (size_t)c * N * n;
+        double* Uc = Uout + (size_t)c * (N - 1) * m;
+        std::memcpy(Xc, Xref, sizeof(double) * n);
+        for (int64_t k = 0; k + 1 < N; ++k) {
+            for (int j = 0; j < m; ++j) {
+                double du = alphas[c] * d[k * m + j];
+                for (int i = 0; i < n; ++i) du += K[(size_t)k * m * n + (size_t)i * m + j] * (Xc[k * n + i] - Xref[k * n + i]);
+                Uc[k * m + j] = Uref[k * m + j] + du;
+            }
+            step<double>(p, Xc + k * n, Uc + k * m, dt[k], Xc + (k + 1) * n);
+        }
+    }
+    return 0;
+}
+
+double orc_fidelity_vec_iso2(const double* s1, const double* s2) { return fidelity_vec_iso2<double>(s1, s2); }
+// m1, m2: 2x2 complex row-major interleaved
+double orc_fidelity_mat(const double* m1, const double* m2, int closed) {
+    cplx a[2][2], b[2][2];
+    for (int i = 0; i < 4; ++i) { a[i / 2][i % 2] = cplx(m1[2 * i], m1[2 * i + 1]); b[i / 2][i % 2] = cplx(m2[2 * i], m2[2 * i + 1]); }
+    return closed ? fidelity_mat_closed(a, b) : fidelity_mat(a, b);
+}
+int orc_gate_iso(int gate, double* G) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+    double M[4][4]; mat_iso(g, M);
+    for (int i = 0; i < 16; ++i) G[i] = M[i / 4][i % 4];
+    return 0;
+}
+
+// run_sim_prop(...; dynamics_type=schroed) over S samples (one reference call per sample).
+// fid[S*(gate_count+1)], states[S*4] (final state) may be NULL.  Returns 0.
+int orc_mc_static(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, int64_t S,
+                  const double* fq, const double* da, const double* psi0, double* fid, double* states, int nthreads) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s)
+        sim_schroed(controls, nk, dt, gate, gate_count, fq[s], da ? da[s] : 0.0, psi0 + 4 * s,
+                    fid ? fid + s * (gate_count + 1) : nullptr, states ? states + 4 * s : nullptr);
+    return 0;
+}
+int orc_mc_noise(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, int64_t S, double fq,
+                 const double* noise, int64_t noise_len, double noise_dt_inv, const double* psi0, double* fid,
+                 double* states, int nthreads) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s)
+        sim_schroedda(controls, nk, dt, gate, gate_count, fq, noise + s * noise_len, noise_len, noise_dt_inv,
+                      psi0 + 4 * s, fid ? fid + s * (gate_count + 1) : nullptr, states ? states + 4 * s : nullptr);
+    return 0;
+}
+// rho0[S*8], fid/fid_closed[S*(gate_count+1)], rho_out[S*8]
+int orc_lindblad_t1(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, int64_t S, double fq,
+                    const double* da, const double* rho0, double* fid, double* fid_closed, double* rho_out, int nthreads) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) {
+        cplx r0[4], ro[4];
+        for (int i = 0; i < 4; ++i) r0[i] = cplx(rho0[8 * s + 2 * i], rho0[8 * s + 2 * i + 1]);
+        sim_lindbladt1(controls, nk, dt, gate, gate_count, fq, da ? da[s] : 0.0, r0,
+                       fid ? fid + s * (gate_count + 1) : nullptr, fid_closed ? fid_closed + s * (gate_count + 1) : nullptr, ro);
+        if (rho_out) for (int i = 0; i < 4; ++i) { rho_out[8 * s + 2 * i] = ro[i].real(); rho_out[8 * s + 2 * i + 1] = ro[i].imag(); }
+    }
+    return 0;
+}
+// the 4x4 complex Liouvillian of spin.jl:530-531 (row-major interleaved), for referee checks
+void orc_lindblad_generator(double fq, double a, double* L) {
+    LindbladOps o = make_lindblad_ops(fq);
+    double gamma1 = 1.0 / amp_t1_spline<double>(a);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+        cplx v = o.H0v[r][c] + a * o.H1v[r][c] + gamma1 * o.LOP[r][c];
+        L[2 * (4 * r + c)] = v.real(); L[2 * (4 * r + c) + 1] = v.imag();
+    }
+}
+
+void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+void orc_philox_samples(int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                        double da_sigma, double* fq, double* da, double* psi0) {
+    for (int64_t s = 0; s < S; ++s) {
+        if (psi0) sample_psi0((uint64_t)(first + s), seed, psi0 + 4 * s);
+        double f, a; sample_static((uint64_t)(first + s), seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma, &f, &a);
+        if (fq) fq[s] = f;
+        if (da) da[s] = a;
+    }
+}
+void orc_pink_filter(const double* xs, int64_t count, double dt_inv, double* ys) { pink_filter(xs, count, dt_inv, ys); }
+// noise[S*noise_len] = namp * gen_pink_noise(noise_len, noise_dt_inv, N(0,1); Philox(seed, first+s))
+void orc_pink_noise(int64_t first, int64_t S, uint64_t seed, double namp, double noise_dt_inv, int64_t noise_len, double* noise) {
+    std::vector<double> xs(noise_len + 1);
+    for (int64_t s = 0; s < S; ++s) {
+        for (int64_t j = 0; 2 * j < noise_len; ++j) philox_normal2((uint64_t)(first + s), seed, (uint32_t)j, 2, &xs[2 * j], &xs[2 * j + 1]);
+        pink_filter(xs.data(), noise_len, noise_dt_inv, noise + s * noise_len);
+        for (int64_t i = 0; i < noise_len; ++i) noise[s * noise_len + i] *= namp;
+    }
+}
+
+// statistics of infidelities e[S] exactly as rbq_stats defines them
+void orc_stats(const double* e, int64_t S, rbq_stats* st) {
+    std::memset(st, 0, sizeof(*st));
+    st->min = INFINITY; st->max = -INFINITY;
+    for (int64_t s = 0; s < S; ++s) {
+        double v = e[s];
+        if (!std::isfinite(v)) { st->nonfinite++; continue; }
+        st->count++; st->sum += v; st->sumsq += v * v;
+        st->min = std::min(st->min, v); st->max = std::max(st->max, v);
+        double l = (std::log10(v > 0 ? v : 0.0) + 16.0) * 16.0;
+        int b = v > 0 ? (int)std::floor(l) : 0;
+        if (b < 0) b = 0; if (b > RBQ_HIST_BINS - 1) b = RBQ_HIST_BINS - 1;
+        st->hist[b]++;
+    }
+}
+
+}  // extern "C"
