@@ -65,6 +65,10 @@ extern "C" {
 #define RBQ_ALGO_PADE 1 /* reference algorithm: generic 4x4 Pade-3/5/7/9/13 + LU solve
                            (StaticArrays 0.12.5 `exp`, the call at spin13.jl:46)      */
 
+/* Lindblad channels (bit mask) */
+#define RBQ_LINDBLAD_T1 1 /* amplitude damping up+down at gamma_1 = 1/T1(a)  spin.jl:529-531 */
+#define RBQ_LINDBLAD_T2 2 /* pure dephasing Gamma(t) = gamma_c + 2 gamma_f^2 t  spin.jl:542-554 */
+
 #define RBQ_MAX_SAMPLE_STATES 4
 #define RBQ_HIST_BINS 256
 
@@ -193,6 +197,11 @@ int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nk
                              double fq_rel_clip, double da_sigma, int algo, double* d_fid,
                              rbq_stats* d_stats);
 /* materialise the samples the generator above draws (for parity tests / the oracle) */
+/* host-pointer form of the above: controls on the host, fid (or NULL) and stats returned to the host */
+int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
+                         int64_t gate_count, int64_t first, int64_t S, uint64_t seed, double fq0,
+                         double fq_rel_sigma, double fq_rel_clip, double da_sigma, int algo,
+                         double* fid, rbq_stats* stats);
 int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0,
                        double fq_rel_sigma, double fq_rel_clip, double da_sigma, double* fq,
                        double* da, double* psi0);
@@ -219,6 +228,9 @@ int rbq_mc_pink_philox_dev(rbq_handle* h, const double* d_controls, int64_t nkno
                            int gate, int64_t gate_count, int64_t first, int64_t S,
                            uint64_t seed, double fq, double namp, double noise_dt_inv,
                            int algo, double* d_fid, rbq_stats* d_stats);
+int rbq_mc_pink_philox(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
+                       int64_t gate_count, int64_t first, int64_t S, uint64_t seed, double fq,
+                       double namp, double noise_dt_inv, int algo, double* fid, rbq_stats* stats);
 /* materialise that noise: noise[S*noise_len] */
 int rbq_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double namp,
                    double noise_dt_inv, int64_t noise_len, double* noise);
@@ -226,19 +238,20 @@ int rbq_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, doubl
 /* ---- Lindblad T1 rollout: run_sim_prop(...; dynamics_type=lindbladt1)
  *      (integrate_prop_lindbladt1! spin.jl:521-539, fidelity_mat spin.jl:1101-1104).
  *  rho0[S*8]: per-sample 2x2 complex density, column-major (vec(rho), spin.jl:524), each
- *  entry (re,im).  da[S] or NULL: static amplitude offset per realisation (enters both the
- *  Hamiltonian and gamma_1(a)).  t2_gamma_c/t2_gamma_f: extra pure dephasing
- *  Gamma(t) = gamma_c + 2 gamma_f^2 t of dynamics_lindbladt2_deqjl (spin.jl:542-554),
- *  evaluated at knot mid-points; pass 0,0 for the T1-only reference path.
+ *  entry (re,im); the Hermitian part is used.  da[S] or NULL: static amplitude offset per
+ *  realisation (enters both the Hamiltonian and gamma_1(a)).  channels: RBQ_LINDBLAD_T1 for the
+ *  reference's lindbladt1 path, RBQ_LINDBLAD_T2 for the pure dephasing
+ *  Gamma(t) = t2_gamma_c + 2 t2_gamma_f^2 t of dynamics_lindbladt2_deqjl (spin.jl:542-554),
+ *  evaluated at knot mid-points, or both.
  *  fid[S*(gate_count+1)] or NULL: Uhlmann sqrt-fidelity per gate.  rho_out[S*8] or NULL:
  *  final density.  stats: of 1-fid after the last gate. */
 int rbq_lindblad(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
                  int64_t gate_count, int64_t S, double fq, const double* da,
-                 const double* rho0, double t2_gamma_c, double t2_gamma_f, double* fid,
-                 double* rho_out, rbq_stats* stats);
+                 const double* rho0, int channels, double t2_gamma_c, double t2_gamma_f,
+                 double* fid, double* rho_out, rbq_stats* stats);
 int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt,
                      int gate, int64_t gate_count, int64_t S, double fq, const double* d_da,
-                     const double* d_rho0, double t2_gamma_c, double t2_gamma_f,
+                     const double* d_rho0, int channels, double t2_gamma_c, double t2_gamma_f,
                      double* d_fid, double* d_rho_out, rbq_stats* d_stats);
 
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */

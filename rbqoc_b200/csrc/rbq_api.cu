@@ -1,0 +1,624 @@
+// rbq_api.cu — the C ABI of include/rbq.h: handle lifetime, argument checking, host<->device staging.
+// No torch types, no exceptions across the boundary, no CPU fallback: every compute entry point
+// ends in a kernel launch on the handle's device or returns an error code.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <complex>
+#include <new>
+
+#include "rbq_internal.h"
+#include "rbq_models.cuh"
+
+using namespace rbq;
+
+// dbuf roles
+enum { B_PULSE = 0, B_PARTIALS, B_SCALARS, B_IN0, B_IN1, B_IN2, B_IN3, B_IN4, B_OUT0, B_OUT1, B_STATS, B_IN5 };
+
+static int fail(rbq_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(h, (int)e_, "%s: %s", #call, cudaGetErrorString(e_));       \
+    } while (0)
+#define CKL(expr)                                                                                      \
+    do {                                                                                               \
+        int r_ = (expr);                                                                               \
+        if (r_ < 0) return fail(h, r_, "%s: argument error %d", #expr, r_);                            \
+        if (r_ > 0) return fail(h, r_, "%s: %s", #expr, cudaGetErrorString((cudaError_t)r_));          \
+    } while (0)
+
+static int dev_buf(rbq_handle* h, int role, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (h->dcap[role] < bytes) {
+        if (h->dbuf[role]) {
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaFree(h->dbuf[role]));
+            h->dbuf[role] = nullptr; h->dcap[role] = 0;
+        }
+        size_t cap = bytes + bytes / 4;
+        cap = (cap + 255) & ~(size_t)255;
+        CK(cudaMalloc(&h->dbuf[role], cap));
+        h->dcap[role] = cap;
+    }
+    *out = h->dbuf[role];
+    return 0;
+}
+static int host_buf(rbq_handle* h, int role, size_t bytes, void** out) {
+    if (h->hcap[role] < bytes) {
+        if (h->hbuf[role]) { CK(cudaFreeHost(h->hbuf[role])); h->hbuf[role] = nullptr; h->hcap[role] = 0; }
+        CK(cudaMallocHost(&h->hbuf[role], bytes));
+        h->hcap[role] = bytes;
+    }
+    *out = h->hbuf[role];
+    return 0;
+}
+#define ENTER(h)                                                \
+    if (!(h)) return RBQ_E_NULL;                                \
+    (h)->err[0] = 0;                                            \
+    CK(cudaSetDevice((h)->device))
+
+// ---- gates (spin.jl:301-323) ---------------------------------------------------------------------------
+typedef std::complex<double> cplx;
+static bool gate_matrix(int gate, cplx g[2][2]) {
+    const double r = 1.0 / sqrt(2.0);
+    const cplx I(0, 1);
+    switch (gate) {
+    case RBQ_GATE_ZPIBY2: g[0][0] = (1.0 - I) * r; g[0][1] = 0; g[1][0] = 0; g[1][1] = (1.0 + I) * r; return true;
+    case RBQ_GATE_YPIBY2: g[0][0] = r; g[0][1] = -r; g[1][0] = r; g[1][1] = r; return true;
+    case RBQ_GATE_XPIBY2: g[0][0] = r; g[0][1] = -I * r; g[1][0] = -I * r; g[1][1] = r; return true;
+    case RBQ_GATE_XPI: g[0][0] = 0; g[0][1] = -I; g[1][0] = -I; g[1][1] = 0; return true;
+    }
+    return false;
+}
+static void mul2(const cplx a[2][2], const cplx b[2][2], cplx c[2][2]) {
+    cplx t[2][2];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) c[i][j] = t[i][j];
+}
+// real isomorphism of rbqoc.jl:204-210, built from the 2x2 power directly (no 4x4 products)
+static void iso_of(const cplx g[2][2], double* G) {
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            G[4 * i + j] = g[i][j].real(); G[4 * i + j + 2] = -g[i][j].imag();
+            G[4 * (i + 2) + j] = g[i][j].imag(); G[4 * (i + 2) + j + 2] = g[i][j].real();
+        }
+}
+// R_ij = tr(sigma_i g sigma_j g^dagger)/2 : how g rho g^dagger moves the Bloch vector
+static void rot_of(const cplx g[2][2], double* R) {
+    const cplx I(0, 1);
+    const cplx sg[3][2][2] = {{{0, 1}, {1, 0}}, {{0, -I}, {I, 0}}, {{1, 0}, {0, -1}}};
+    cplx gd[2][2] = {{std::conj(g[0][0]), std::conj(g[1][0])}, {std::conj(g[0][1]), std::conj(g[1][1])}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            cplx a[2][2], b[2][2];
+            mul2(g, sg[j], a); mul2(a, gd, a); mul2(sg[i], a, b);
+            R[3 * i + j] = 0.5 * (b[0][0] + b[1][1]).real();
+        }
+}
+static bool make_gate_tables(int gate, GateIso* gi, GateRot* gr) {
+    cplx g[3][2][2];
+    if (!gate_matrix(gate, g[0])) return false;
+    mul2(g[0], g[0], g[1]);
+    mul2(g[1], g[0], g[2]);
+    for (int k = 0; k < 3; ++k) {
+        if (gi) iso_of(g[k], gi->g[k]);
+        if (gr) rot_of(g[k], gr->r[k]);
+    }
+    return true;
+}
+
+extern "C" {
+
+int rbq_version(void) { return RBQ_VERSION; }
+
+int rbq_create(int device, rbq_handle** out) {
+    if (!out) return RBQ_E_NULL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return RBQ_E_NODEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RBQ_E_NODEVICE;
+    if (prop.major != 10) return RBQ_E_NODEVICE;   // kernels are built for sm_100a only
+    rbq_handle* h = new (std::nothrow) rbq_handle();
+    if (!h) return RBQ_E_SIZE;
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
+    *out = h;
+    return RBQ_OK;
+}
+int rbq_destroy(rbq_handle* h) {
+    if (!h) return RBQ_E_NULL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < RBQ_NBUF; ++i) if (h->dbuf[i]) cudaFree(h->dbuf[i]);
+    for (int i = 0; i < 2; ++i) if (h->hbuf[i]) cudaFreeHost(h->hbuf[i]);
+    for (int i = 0; i < 2; ++i) cudaStreamDestroy(h->copy_stream[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return RBQ_OK;
+}
+const char* rbq_last_error(const rbq_handle* h) { return h ? h->err : "null handle"; }
+int rbq_set_stream(rbq_handle* h, void* cuda_stream) {
+    if (!h) return RBQ_E_NULL;
+    h->stream = (cudaStream_t)cuda_stream;
+    return RBQ_OK;
+}
+int rbq_synchronize(rbq_handle* h) {
+    ENTER(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int64_t rbq_launch_count(const rbq_handle* h) { return h ? h->launches : -1; }
+
+int rbq_state_dim(const rbq_model_params* p) { return p ? model_state_dim(*p) : RBQ_E_NULL; }
+int rbq_control_dim(const rbq_model_params* p) { return p ? model_control_dim(*p) : RBQ_E_NULL; }
+
+// ---- trajectory level ----------------------------------------------------------------------------------------
+int rbq_rollout_dev(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N, const double* d_x0,
+                    const double* d_U, const double* d_dt, double* d_X) {
+    ENTER(h);
+    if (!p || !d_x0 || !d_U || !d_dt || !d_X) return fail(h, RBQ_E_NULL, "rbq_rollout_dev: null pointer");
+    if (B < 0 || N < 1) return fail(h, RBQ_E_SIZE, "rbq_rollout_dev: B=%lld N=%lld", (long long)B, (long long)N);
+    if (B == 0) return RBQ_OK;
+    CKL(launch_rollout(h, *p, B, N, d_x0, d_U, d_dt, d_X));
+    return RBQ_OK;
+}
+int rbq_jacobians_dev(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* d_X, const double* d_U,
+                      const double* d_dt, double* d_AB) {
+    ENTER(h);
+    if (!p || !d_X || !d_U || !d_dt || !d_AB) return fail(h, RBQ_E_NULL, "rbq_jacobians_dev: null pointer");
+    if (K < 0) return fail(h, RBQ_E_SIZE, "rbq_jacobians_dev: K=%lld", (long long)K);
+    if (K == 0) return RBQ_OK;
+    CKL(launch_jacobians(h, *p, K, d_X, d_U, d_dt, d_AB));
+    return RBQ_OK;
+}
+int rbq_rollout(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N, const double* x0, const double* U,
+                const double* dt, double* X) {
+    ENTER(h);
+    if (!p || !x0 || !X || (N > 1 && (!U || !dt))) return fail(h, RBQ_E_NULL, "rbq_rollout: null pointer");
+    const int n = model_state_dim(*p), m = model_control_dim(*p);
+    if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_rollout: bad model parameters");
+    if (B < 0 || N < 1) return fail(h, RBQ_E_SIZE, "rbq_rollout: B=%lld N=%lld", (long long)B, (long long)N);
+    if (B == 0) return RBQ_OK;
+    void *dx0, *dU, *ddt, *dX;
+    const size_t bx0 = sizeof(double) * B * n, bU = sizeof(double) * B * (N - 1) * m, bdt = sizeof(double) * (N - 1),
+                 bX = sizeof(double) * B * N * n;
+    CKL(dev_buf(h, B_IN0, bx0, &dx0)); CKL(dev_buf(h, B_IN1, bU, &dU)); CKL(dev_buf(h, B_IN2, bdt, &ddt));
+    CKL(dev_buf(h, B_OUT0, bX, &dX));
+    CK(cudaMemcpyAsync(dx0, x0, bx0, cudaMemcpyHostToDevice, h->stream));
+    if (N > 1) {
+        CK(cudaMemcpyAsync(dU, U, bU, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(ddt, dt, bdt, cudaMemcpyHostToDevice, h->stream));
+    }
+    CKL(launch_rollout(h, *p, B, N, (double*)dx0, (double*)dU, (double*)ddt, (double*)dX));
+    CK(cudaMemcpyAsync(X, dX, bX, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N, const double* Xref, const double* Uref,
+                           const double* K, const double* d, const double* dt, int64_t nalpha, const double* alphas,
+                           double* X, double* Uout) {
+    ENTER(h);
+    if (!p || !Xref || !Uref || !K || !d || !dt || !alphas || !X || !Uout) return fail(h, RBQ_E_NULL, "rbq_rollout_closedloop: null pointer");
+    const int n = model_state_dim(*p), m = model_control_dim(*p);
+    if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_rollout_closedloop: bad model parameters");
+    if (N < 2 || nalpha < 0) return fail(h, RBQ_E_SIZE, "rbq_rollout_closedloop: N=%lld nalpha=%lld", (long long)N, (long long)nalpha);
+    if (nalpha == 0) return RBQ_OK;
+    void *dXr, *dUr, *dK, *dd, *ddt, *dal, *dX, *dUo;
+    const size_t bXr = sizeof(double) * N * n, bUr = sizeof(double) * (N - 1) * m, bK = sizeof(double) * (N - 1) * m * n,
+                 bd = bUr, bdt = sizeof(double) * (N - 1), bal = sizeof(double) * nalpha, bX = bXr * nalpha, bUo = bUr * nalpha;
+    CKL(dev_buf(h, B_IN0, bXr, &dXr)); CKL(dev_buf(h, B_IN1, bUr, &dUr)); CKL(dev_buf(h, B_IN2, bdt, &ddt));
+    CKL(dev_buf(h, B_IN3, bK, &dK)); CKL(dev_buf(h, B_IN4, bd, &dd)); CKL(dev_buf(h, B_IN5, bal, &dal));
+    CKL(dev_buf(h, B_OUT0, bX, &dX)); CKL(dev_buf(h, B_OUT1, bUo, &dUo));
+    CK(cudaMemcpyAsync(dXr, Xref, bXr, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dUr, Uref, bUr, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dK, K, bK, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dd, d, bd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(ddt, dt, bdt, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dal, alphas, bal, cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_closedloop(h, *p, N, (double*)dXr, (double*)dUr, (double*)dK, (double*)dd, (double*)ddt, nalpha, (double*)dal,
+                          (double*)dX, (double*)dUo));
+    CK(cudaMemcpyAsync(X, dX, bX, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(Uout, dUo, bUo, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* dt,
+                  double* AB) {
+    ENTER(h);
+    if (!p || !X || !U || !dt || !AB) return fail(h, RBQ_E_NULL, "rbq_jacobians: null pointer");
+    const int n = model_state_dim(*p), m = model_control_dim(*p);
+    if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_jacobians: bad model parameters");
+    if (K < 0) return fail(h, RBQ_E_SIZE, "rbq_jacobians: K=%lld", (long long)K);
+    if (K == 0) return RBQ_OK;
+    void *dX, *dU, *ddt, *dAB;
+    const size_t bX = sizeof(double) * K * n, bU = sizeof(double) * K * m, bdt = sizeof(double) * K,
+                 bAB = sizeof(double) * K * n * (n + m);
+    CKL(dev_buf(h, B_IN0, bX, &dX)); CKL(dev_buf(h, B_IN1, bU, &dU)); CKL(dev_buf(h, B_IN2, bdt, &ddt));
+    CKL(dev_buf(h, B_OUT0, bAB, &dAB));
+    CK(cudaMemcpyAsync(dX, X, bX, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dU, U, bU, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(ddt, dt, bdt, cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_jacobians(h, *p, K, (double*)dX, (double*)dU, (double*)ddt, (double*)dAB));
+    CK(cudaMemcpyAsync(AB, dAB, bAB, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+// per-knot forms: a rollout of two knots / a one-knot Jacobian batch
+int rbq_discrete_dynamics(rbq_handle* h, const rbq_model_params* p, const double* x, const double* u, double t, double dt,
+                          double* xnext) {
+    (void)t;   // none of the reference models is time dependent (the `time` argument is unused in every spinYY.jl)
+    ENTER(h);
+    if (!p || !x || !u || !xnext) return fail(h, RBQ_E_NULL, "rbq_discrete_dynamics: null pointer");
+    const int n = model_state_dim(*p), m = model_control_dim(*p);
+    if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_discrete_dynamics: bad model parameters");
+    void *dx, *du, *ddt, *dX;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * n, &dx)); CKL(dev_buf(h, B_IN1, sizeof(double) * m, &du));
+    CKL(dev_buf(h, B_IN2, sizeof(double), &ddt)); CKL(dev_buf(h, B_OUT0, sizeof(double) * 2 * n, &dX));
+    CK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(du, u, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(ddt, &dt, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_rollout(h, *p, 1, 2, (double*)dx, (double*)du, (double*)ddt, (double*)dX));
+    CK(cudaMemcpyAsync(xnext, (double*)dX + n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_discrete_jacobian(rbq_handle* h, const rbq_model_params* p, const double* x, const double* u, double t, double dt,
+                          double* AB) {
+    (void)t;
+    return rbq_jacobians(h, p, 1, x, u, &dt, AB);
+}
+
+// ---- Monte-Carlo sweeps ----------------------------------------------------------------------------------------
+static int check_mc(rbq_handle* h, const char* who, const void* controls, int64_t nk, double dt, int64_t gate_count, int64_t S,
+                    int algo) {
+    if (!controls) return fail(h, RBQ_E_NULL, "%s: controls is NULL", who);
+    if (nk < 1 || nk > ((int64_t)1 << 40) || gate_count < 0 || S < 0) return fail(h, RBQ_E_SIZE, "%s: nknots=%lld gate_count=%lld S=%lld", who, (long long)nk, (long long)gate_count, (long long)S);
+    if (!(dt == dt)) return fail(h, RBQ_E_SIZE, "%s: dt is NaN", who);
+    if (algo != RBQ_ALGO_SU2 && algo != RBQ_ALGO_PADE) return fail(h, RBQ_E_ALGO, "%s: unknown algo %d", who, algo);
+    return 0;
+}
+// stage the pulse, return device pointers to the staged copy and to max|a|
+static int stage_pulse(rbq_handle* h, const double* d_controls, int64_t nk, const double** staged, const double** amax) {
+    void *pb, *sc;
+    CKL(dev_buf(h, B_PULSE, sizeof(double) * (nk + 2), &pb));
+    CKL(dev_buf(h, B_SCALARS, 64, &sc));
+    CKL(launch_pulse_prep(h, d_controls, nk, (double*)sc));
+    *staged = (const double*)pb; *amax = (const double*)sc;
+    return 0;
+}
+int rbq_stats_reset_dev(rbq_handle* h, rbq_stats* d_stats) {
+    ENTER(h);
+    if (!d_stats) return fail(h, RBQ_E_NULL, "rbq_stats_reset_dev: null pointer");
+    CKL(launch_stats_reset(h, d_stats));
+    return RBQ_OK;
+}
+int rbq_stats_merge(rbq_stats* a, const rbq_stats* b) {
+    if (!a || !b) return RBQ_E_NULL;
+    a->count += b->count; a->nonfinite += b->nonfinite; a->sum += b->sum; a->sumsq += b->sumsq;
+    a->min = fmin(a->min, b->min); a->max = fmax(a->max, b->max);
+    for (int i = 0; i < RBQ_HIST_BINS; ++i) a->hist[i] += b->hist[i];
+    return RBQ_OK;
+}
+
+static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
+                          int64_t first, int64_t S, const double* d_fq, const double* d_da, const double* d_psi0, int philox,
+                          uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip, double da_sigma, int algo,
+                          double* d_fid, rbq_stats* d_stats) {
+    McStaticArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!make_gate_tables(gate, &a.gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
+    if (S == 0) return RBQ_OK;
+    CKL(stage_pulse(h, d_controls, nk, &a.controls, &a.amax));
+    a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S;
+    a.fq = d_fq; a.da = d_da; a.psi0 = d_psi0;
+    a.philox = philox; a.seed = seed; a.fq0 = fq0; a.fq_rel_sigma = fq_rel_sigma; a.fq_rel_clip = fq_rel_clip; a.da_sigma = da_sigma;
+    a.fid = d_fid;
+    if (d_stats) {
+        void* pp;
+        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * mc_static_blocks(h, S, algo), &pp));
+        a.partials = (BlockPartial*)pp;
+        a.hist = (unsigned long long*)d_stats->hist;
+    }
+    int nblocks = 0;
+    CKL(launch_mc_static(h, a, algo, &nblocks));
+    if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
+    return RBQ_OK;
+}
+int rbq_mc_static_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                      int64_t S, const double* d_fq, const double* d_da, const double* d_psi0, int algo, double* d_fid,
+                      rbq_stats* d_stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_static_dev", d_controls, nknots, dt, gate_count, S, algo));
+    if (S > 0 && (!d_fq || !d_psi0)) return fail(h, RBQ_E_NULL, "rbq_mc_static_dev: fq/psi0 is NULL");
+    return mc_static_core(h, d_controls, nknots, dt, gate, gate_count, 0, S, d_fq, d_da, d_psi0, 0, 0, 0, 0, 0, 0, algo, d_fid, d_stats);
+}
+int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                             int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                             double da_sigma, int algo, double* d_fid, rbq_stats* d_stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_static_philox_dev", d_controls, nknots, dt, gate_count, S, algo));
+    if (first < 0) return fail(h, RBQ_E_SIZE, "rbq_mc_static_philox_dev: first=%lld", (long long)first);
+    return mc_static_core(h, d_controls, nknots, dt, gate, gate_count, first, S, nullptr, nullptr, nullptr, 1, seed, fq0,
+                          fq_rel_sigma, fq_rel_clip, da_sigma, algo, d_fid, d_stats);
+}
+
+// host-pointer sweep: samples are streamed through the device in chunks so that the H2D copy of chunk
+// c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+static const int64_t MC_CHUNK = 1 << 18;
+int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
+                  const double* fq, const double* da, const double* psi0, int algo, double* fid, rbq_stats* stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_static", controls, nknots, dt, gate_count, S, algo));
+    if (S > 0 && (!fq || !psi0)) return fail(h, RBQ_E_NULL, "rbq_mc_static: fq/psi0 is NULL");
+    GateIso gi;
+    if (!make_gate_tables(gate, &gi, nullptr)) return fail(h, RBQ_E_GATE, "rbq_mc_static: unknown gate %d", gate);
+    void *dc, *dfq, *dda, *dpsi, *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
+    CKL(dev_buf(h, B_IN1, sizeof(double) * S, &dfq));
+    CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda));
+    CKL(dev_buf(h, B_IN3, sizeof(double) * S * 4, &dpsi));
+    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
+    CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    if (S > 0) {
+        // event choreography: copy_stream[0] uploads, h->stream computes, copy_stream[1] downloads
+        cudaStream_t up = h->copy_stream[0], down = h->copy_stream[1];
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        CK(cudaStreamWaitEvent(up, h->ev[0], 0));   // uploads start after earlier work on the buffers has drained
+        const int64_t nchunks = (S + MC_CHUNK - 1) / MC_CHUNK;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t s0 = c * MC_CHUNK, cnt = (S - s0) < MC_CHUNK ? (S - s0) : MC_CHUNK;
+            CK(cudaMemcpyAsync((double*)dfq + s0, fq + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
+            if (da) CK(cudaMemcpyAsync((double*)dda + s0, da + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
+            CK(cudaMemcpyAsync((double*)dpsi + 4 * s0, psi0 + 4 * s0, sizeof(double) * 4 * cnt, cudaMemcpyHostToDevice, up));
+            CK(cudaEventRecord(h->ev[1 + (c & 1)], up));
+            CK(cudaStreamWaitEvent(h->stream, h->ev[1 + (c & 1)], 0));
+            int rc = mc_static_core(h, (double*)dc, nknots, dt, gate, gate_count, 0, cnt, (double*)dfq + s0,
+                                    da ? (double*)dda + s0 : nullptr, (double*)dpsi + 4 * s0, 0, 0, 0, 0, 0, 0, algo,
+                                    fid ? (double*)dfid + s0 * G1 : nullptr, (rbq_stats*)dst);
+            if (rc) return rc;
+            if (fid) {
+                CK(cudaEventRecord(h->ev[3 + (c & 1)], h->stream));
+                CK(cudaStreamWaitEvent(down, h->ev[3 + (c & 1)], 0));
+                CK(cudaMemcpyAsync(fid + s0 * G1, (double*)dfid + s0 * G1, sizeof(double) * cnt * G1, cudaMemcpyDeviceToHost, down));
+            }
+        }
+        CK(cudaStreamSynchronize(down));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                         int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                         double da_sigma, int algo, double* fid, rbq_stats* stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_static_philox", controls, nknots, dt, gate_count, S, algo));
+    void *dc, *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
+    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
+    CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    int rc = rbq_mc_static_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma,
+                                      fq_rel_clip, da_sigma, algo, (double*)dfid, (rbq_stats*)dst);
+    if (rc) return rc;
+    if (fid && S > 0) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
+                       double fq_rel_clip, double da_sigma, double* fq, double* da, double* psi0) {
+    ENTER(h);
+    if (S < 0 || first < 0) return fail(h, RBQ_E_SIZE, "rbq_philox_samples: first=%lld S=%lld", (long long)first, (long long)S);
+    if (S == 0) return RBQ_OK;
+    void *dfq, *dda, *dpsi;
+    CKL(dev_buf(h, B_IN1, sizeof(double) * S, &dfq)); CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda));
+    CKL(dev_buf(h, B_IN3, sizeof(double) * 4 * S, &dpsi));
+    CKL(launch_philox_samples(h, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma, (double*)dfq, (double*)dda, (double*)dpsi));
+    if (fq) CK(cudaMemcpyAsync(fq, dfq, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream));
+    if (da) CK(cudaMemcpyAsync(da, dda, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream));
+    if (psi0) CK(cudaMemcpyAsync(psi0, dpsi, sizeof(double) * 4 * S, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
+// ---- time-dependent noise -----------------------------------------------------------------------------------------
+static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
+                         int64_t first, int64_t S, double fq, const double* d_noise, int64_t noise_len, double noise_dt_inv,
+                         const double* d_psi0, int philox, uint64_t seed, double namp, int algo, double* d_fid,
+                         rbq_stats* d_stats) {
+    McNoiseArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!make_gate_tables(gate, &a.gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
+    if (S == 0) return RBQ_OK;
+    CKL(stage_pulse(h, d_controls, nk, &a.controls, &a.amax));
+    a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S; a.fq = fq;
+    a.noise = d_noise; a.noise_len = noise_len; a.noise_dt_inv = noise_dt_inv; a.psi0 = d_psi0;
+    a.philox = philox; a.seed = seed; a.namp = namp; a.fid = d_fid;
+    if (d_stats) {
+        void* pp;
+        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * mc_noise_blocks(h, S), &pp));
+        a.partials = (BlockPartial*)pp;
+        a.hist = (unsigned long long*)d_stats->hist;
+    }
+    int nblocks = 0;
+    CKL(launch_mc_noise(h, a, algo, &nblocks));
+    if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
+    return RBQ_OK;
+}
+int rbq_mc_noise_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
+                     double fq, const double* d_noise, int64_t noise_len, double noise_dt_inv, const double* d_psi0, int algo,
+                     double* d_fid, rbq_stats* d_stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_noise_dev", d_controls, nknots, dt, gate_count, S, algo));
+    if (S > 0 && (!d_noise || !d_psi0)) return fail(h, RBQ_E_NULL, "rbq_mc_noise_dev: noise/psi0 is NULL");
+    if (noise_len < 1) return fail(h, RBQ_E_SIZE, "rbq_mc_noise_dev: noise_len=%lld", (long long)noise_len);
+    return mc_noise_core(h, d_controls, nknots, dt, gate, gate_count, 0, S, fq, d_noise, noise_len, noise_dt_inv, d_psi0, 0, 0,
+                         0.0, algo, d_fid, d_stats);
+}
+int rbq_mc_pink_philox_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                           int64_t first, int64_t S, uint64_t seed, double fq, double namp, double noise_dt_inv, int algo,
+                           double* d_fid, rbq_stats* d_stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_pink_philox_dev", d_controls, nknots, dt, gate_count, S, algo));
+    if (first < 0) return fail(h, RBQ_E_SIZE, "rbq_mc_pink_philox_dev: first=%lld", (long long)first);
+    // same length run_sim_prop gives gen_pink_noise: Int(ceil(evolution_time * noise_dt_inv)) + 1  (spin.jl:1569-1570)
+    const int64_t noise_len = (int64_t)ceil((double)nknots * dt * (double)gate_count * noise_dt_inv) + 1;
+    return mc_noise_core(h, d_controls, nknots, dt, gate, gate_count, first, S, fq, nullptr, noise_len, noise_dt_inv, nullptr, 1,
+                         seed, namp, algo, d_fid, d_stats);
+}
+int rbq_mc_noise(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
+                 double fq, const double* noise, int64_t noise_len, double noise_dt_inv, const double* psi0, int algo,
+                 double* fid, rbq_stats* stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_noise", controls, nknots, dt, gate_count, S, algo));
+    if (S > 0 && (!noise || !psi0)) return fail(h, RBQ_E_NULL, "rbq_mc_noise: noise/psi0 is NULL");
+    if (noise_len < 1) return fail(h, RBQ_E_SIZE, "rbq_mc_noise: noise_len=%lld", (long long)noise_len);
+    void *dc, *dn, *dpsi, *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
+    CKL(dev_buf(h, B_IN4, sizeof(double) * S * noise_len, &dn));
+    CKL(dev_buf(h, B_IN3, sizeof(double) * S * 4, &dpsi));
+    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
+    CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    if (S > 0) {
+        CK(cudaMemcpyAsync(dn, noise, sizeof(double) * S * noise_len, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dpsi, psi0, sizeof(double) * S * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = mc_noise_core(h, (double*)dc, nknots, dt, gate, gate_count, 0, S, fq, (double*)dn, noise_len, noise_dt_inv,
+                           (double*)dpsi, 0, 0, 0.0, algo, (double*)dfid, (rbq_stats*)dst);
+    if (rc) return rc;
+    if (fid && S > 0) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_mc_pink_philox(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                       int64_t first, int64_t S, uint64_t seed, double fq, double namp, double noise_dt_inv, int algo,
+                       double* fid, rbq_stats* stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_mc_pink_philox", controls, nknots, dt, gate_count, S, algo));
+    void *dc, *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
+    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
+    CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    int rc = rbq_mc_pink_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first, S, seed, fq, namp, noise_dt_inv, algo,
+                                    (double*)dfid, (rbq_stats*)dst);
+    if (rc) return rc;
+    if (fid && S > 0) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double namp, double noise_dt_inv, int64_t noise_len,
+                   double* noise) {
+    ENTER(h);
+    if (!noise) return fail(h, RBQ_E_NULL, "rbq_pink_noise: null pointer");
+    if (S < 0 || first < 0 || noise_len < 1) return fail(h, RBQ_E_SIZE, "rbq_pink_noise: bad sizes");
+    if (S == 0) return RBQ_OK;
+    void* dn;
+    CKL(dev_buf(h, B_IN4, sizeof(double) * S * noise_len, &dn));
+    CKL(launch_pink_noise(h, first, S, seed, namp, noise_dt_inv, noise_len, (double*)dn));
+    CK(cudaMemcpyAsync(noise, dn, sizeof(double) * S * noise_len, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
+// ---- Lindblad ---------------------------------------------------------------------------------------------------------
+int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
+                     double fq, const double* d_da, const double* d_rho0, int channels, double t2_gamma_c, double t2_gamma_f,
+                     double* d_fid, double* d_rho_out, rbq_stats* d_stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_lindblad_dev", d_controls, nknots, dt, gate_count, S, RBQ_ALGO_SU2));
+    if (S > 0 && !d_rho0) return fail(h, RBQ_E_NULL, "rbq_lindblad_dev: rho0 is NULL");
+    if (channels & ~(RBQ_LINDBLAD_T1 | RBQ_LINDBLAD_T2)) return fail(h, RBQ_E_MODEL, "rbq_lindblad_dev: unknown channel bits %d", channels);
+    LindbladArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!make_gate_tables(gate, nullptr, &a.gate)) return fail(h, RBQ_E_GATE, "rbq_lindblad_dev: unknown gate %d", gate);
+    if (S == 0) return RBQ_OK;
+    CKL(stage_pulse(h, d_controls, nknots, &a.controls, &a.amax));
+    a.nk = nknots; a.dt = dt; a.gate_count = gate_count; a.S = S; a.fq = fq; a.da = d_da; a.rho0 = d_rho0;
+    a.t2_gamma_c = t2_gamma_c; a.t2_gamma_f = t2_gamma_f; a.fid = d_fid; a.rho_out = d_rho_out;
+    if (d_stats) {
+        void* pp;
+        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * lindblad_blocks(h, S), &pp));
+        a.partials = (BlockPartial*)pp;
+        a.hist = (unsigned long long*)d_stats->hist;
+    }
+    int nblocks = 0;
+    CKL(launch_lindblad(h, a, channels, &nblocks));
+    if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
+    return RBQ_OK;
+}
+int rbq_lindblad(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
+                 double fq, const double* da, const double* rho0, int channels, double t2_gamma_c, double t2_gamma_f, double* fid,
+                 double* rho_out, rbq_stats* stats) {
+    ENTER(h);
+    CKL(check_mc(h, "rbq_lindblad", controls, nknots, dt, gate_count, S, RBQ_ALGO_SU2));
+    if (S > 0 && !rho0) return fail(h, RBQ_E_NULL, "rbq_lindblad: rho0 is NULL");
+    void *dc, *dda = nullptr, *drho, *dfid = nullptr, *dro = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
+    CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda));
+    CKL(dev_buf(h, B_IN3, sizeof(double) * S * 8, &drho));
+    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (rho_out) CKL(dev_buf(h, B_OUT1, sizeof(double) * S * 8, &dro));
+    if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
+    CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    if (S > 0) {
+        if (da) CK(cudaMemcpyAsync(dda, da, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(drho, rho0, sizeof(double) * S * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = rbq_lindblad_dev(h, (double*)dc, nknots, dt, gate, gate_count, S, fq, da ? (double*)dda : nullptr, (double*)drho,
+                              channels, t2_gamma_c, t2_gamma_f, (double*)dfid, (double*)dro, (rbq_stats*)dst);
+    if (rc) return rc;
+    if (fid && S > 0) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    if (rho_out && S > 0) CK(cudaMemcpyAsync(rho_out, dro, sizeof(double) * S * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
+// ---- FP64 roofline denominator -------------------------------------------------------------------------------------------
+int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops) {
+    ENTER(h);
+    if (!tflops) return fail(h, RBQ_E_NULL, "rbq_fp64_peak: null pointer");
+    if (iters < 1) return fail(h, RBQ_E_SIZE, "rbq_fp64_peak: iters=%d", iters);
+    void* sink;
+    CKL(dev_buf(h, B_SCALARS, 64, &sink));
+    int nthreads = 0, fpi = 0;
+    CKL(launch_fp64_peak(h, iters / 8 + 1, (double*)sink + 4, &nthreads, &fpi));   // warm-up
+    CK(cudaEventRecord(h->ev[6], h->stream));
+    CKL(launch_fp64_peak(h, iters, (double*)sink + 4, &nthreads, &fpi));
+    CK(cudaEventRecord(h->ev[7], h->stream));
+    CK(cudaEventSynchronize(h->ev[7]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
+    *tflops = (double)nthreads * (double)iters * (double)fpi / ((double)ms * 1e-3) * 1e-12;
+    return RBQ_OK;
+}
+
+}  // extern "C"

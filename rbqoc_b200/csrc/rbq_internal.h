@@ -1,0 +1,88 @@
+// rbq_internal.h — handle layout and kernel launchers shared by the translation units of librbq.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rbq.h"
+
+#define RBQ_NBUF 12
+
+struct rbq_handle {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    cudaStream_t copy_stream[2];   // H2D / D2H overlap for the chunked host-pointer paths
+    cudaEvent_t ev[8];
+    int64_t launches;
+    char err[512];
+    void* dbuf[RBQ_NBUF];          // grow-only device scratch, indexed by role
+    size_t dcap[RBQ_NBUF];
+    void* hbuf[2];                 // pinned host staging (stats, small results)
+    size_t hcap[2];
+};
+
+namespace rbq {
+
+// per-block partial statistics, reduced in block order by stats_finalize_kernel (deterministic)
+struct BlockPartial {
+    double sum, sumsq, mn, mx;
+    long long cnt, nonfinite;
+};
+
+// gate tables passed by value to the MC kernels
+struct GateIso { double g[3][16]; };   // G, G^2, G^3 as row-major 4x4 iso matrices (spin.jl:314-323)
+struct GateRot { double r[3][9]; };    // the same gates as SO(3) rotations of the Bloch vector
+
+struct McStaticArgs {
+    const double* controls; int64_t nk; double dt;
+    int64_t gate_count; int64_t first; int64_t S;
+    const double* fq; const double* da; const double* psi0;   // explicit samples
+    int philox; uint64_t seed; double fq0, fq_rel_sigma, fq_rel_clip, da_sigma;
+    double* fid;                 // S*(gate_count+1) or NULL
+    BlockPartial* partials;      // one per block, or NULL
+    unsigned long long* hist;    // RBQ_HIST_BINS global bins, or NULL
+    const double* amax;          // device scalar: max |controls|
+    GateIso gate;
+};
+struct McNoiseArgs {
+    const double* controls; int64_t nk; double dt;
+    int64_t gate_count; int64_t first; int64_t S; double fq;
+    const double* noise; int64_t noise_len; double noise_dt_inv; const double* psi0;
+    int philox; uint64_t seed; double namp;
+    double* fid; BlockPartial* partials; unsigned long long* hist; const double* amax;
+    GateIso gate;
+};
+struct LindbladArgs {
+    const double* controls; int64_t nk; double dt;
+    int64_t gate_count; int64_t S; double fq;
+    const double* da; const double* rho0; double t2_gamma_c, t2_gamma_f;
+    double* fid; double* rho_out; BlockPartial* partials; unsigned long long* hist; const double* amax;
+    GateRot gate;
+};
+
+// every launcher enqueues on h->stream, bumps h->launches and returns a cudaError_t as int
+int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax);
+int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
+int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
+int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
+int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);
+int mc_noise_blocks(const rbq_handle* h, int64_t S);
+int lindblad_blocks(const rbq_handle* h, int64_t S);
+int launch_stats_finalize(rbq_handle* h, const BlockPartial* partials, int nblocks, rbq_stats* d_stats);
+int launch_stats_reset(rbq_handle* h, rbq_stats* d_stats);
+int launch_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
+                          double fq_rel_clip, double da_sigma, double* d_fq, double* d_da, double* d_psi0);
+int launch_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double namp, double noise_dt_inv,
+                      int64_t noise_len, double* d_noise);
+int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out, int* flops_per_thread_iter);
+
+int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, const double* d_x0,
+                   const double* d_U, const double* d_dt, double* d_X);
+int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const double* d_Xref, const double* d_Uref,
+                      const double* d_K, const double* d_d, const double* d_dt, int64_t nalpha, const double* d_alphas,
+                      double* d_X, double* d_Uout);
+int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
+                     const double* d_dt, double* d_AB);
+
+}  // namespace rbq

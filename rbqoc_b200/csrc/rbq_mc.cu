@@ -1,0 +1,735 @@
+// rbq_mc.cu — Monte-Carlo robustness kernels (one thread per sample, FP64-pipe bound):
+//   mc_static_kernel   run_sim_prop(...; dynamics_type=schroed)    spin.jl:438-452, 1553-1608
+//   mc_noise_kernel    run_sim_prop(...; dynamics_type=schroedda)  spin.jl:469-484
+//   lindblad_kernel    run_sim_prop(...; dynamics_type=lindbladt1) spin.jl:521-539 (+ T2 of 542-554)
+//   compute_fidelities / fidelity_vec_iso2 / fidelity_mat fused into each (spin.jl:1035-1037,
+//   1101-1104, 1198-1240), infidelity statistics reduced with warp shuffles.
+// The pulse is staged into shared memory tile by tile with 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier, double buffered); all threads of a block walk the pulse in lock step.
+// sm_100a only.
+#include "rbq_internal.h"
+#include "rbq_math.cuh"
+
+namespace rbq {
+
+constexpr int MC_THREADS = 256;
+constexpr int MC_TILE = 2048;   // knots per shared-memory tile (16 KB), two tiles in flight
+
+// ---- bulk-TMA / mbarrier primitives ---------------------------------------------------------------
+RBQ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RBQ_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+RBQ_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+RBQ_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RBQ_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+RBQ_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+RBQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// Walks a staged pulse (16-byte aligned, zero padded to a multiple of 2 knots) through two
+// shared-memory tiles.  `pass` counts tiles since kernel start so the pulse can be replayed once per gate.
+struct PulsePipe {
+    double* tile;       // [2][MC_TILE]
+    uint64_t* bar;      // [2]
+    const double* src;
+    int64_t nk;
+    int ntiles;
+    uint32_t pass;
+    RBQ_DEV void init(double* t, uint64_t* b, const double* s, int64_t n) {
+        tile = t; bar = b; src = s; nk = n; pass = 0;
+        ntiles = (int)((n + MC_TILE - 1) / MC_TILE);
+        if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
+    RBQ_DEV int tile_len(int ti) const { const int64_t r = nk - (int64_t)ti * MC_TILE; return r < MC_TILE ? (int)r : MC_TILE; }
+    RBQ_DEV void issue(int ti, uint32_t slot) {
+        const int len = tile_len(ti);
+        const uint32_t bytes = (uint32_t)(((len + 1) & ~1) * sizeof(double));
+        mbar_expect_tx(&bar[slot], bytes);
+        bulk_g2s(tile + slot * MC_TILE, src + (int64_t)ti * MC_TILE, bytes, &bar[slot]);
+    }
+    // call with ti = 0..ntiles-1 in order; returns the tile; every thread of the block must call it
+    RBQ_DEV const double* acquire(int ti, bool more_passes) {
+        const uint32_t slot = pass & 1u;
+        if (threadIdx.x == 0) {
+            if (pass == 0) issue(0, 0);
+            // prefetch the next tile (of this pass, or the first tile of the next pass) into the other slot;
+            // the __syncthreads in release() guarantees nobody still reads it
+            const int nxt = ti + 1 < ntiles ? ti + 1 : (more_passes ? 0 : -1);
+            if (nxt >= 0) issue(nxt, slot ^ 1u);
+        }
+        mbar_wait(&bar[slot], (pass >> 1) & 1u);
+        return tile + slot * MC_TILE;
+    }
+    RBQ_DEV void release() { __syncthreads(); ++pass; }
+};
+
+// ---- statistics ---------------------------------------------------------------------------------------
+struct ThreadStats {
+    double sum = 0.0, sumsq = 0.0, mn = INFINITY, mx = -INFINITY;
+    long long cnt = 0, nonfinite = 0;
+    RBQ_DEV void add(double e, unsigned* hist_s) {
+        if (!isfinite(e)) { ++nonfinite; return; }
+        ++cnt; sum += e; sumsq = fma(e, e, sumsq);
+        mn = fmin(mn, e); mx = fmax(mx, e);
+        int b = 0;
+        if (e > 0.0) {
+            b = (int)floor((log10(e) + 16.0) * 16.0);
+            b = b < 0 ? 0 : (b > RBQ_HIST_BINS - 1 ? RBQ_HIST_BINS - 1 : b);
+        }
+        atomicAdd(&hist_s[b], 1u);
+    }
+};
+// warp shuffle -> shared -> one BlockPartial per block; histogram bins flushed with integer atomics
+RBQ_DEV void block_stats_flush(ThreadStats st, unsigned* hist_s, BlockPartial* red_s, BlockPartial* partials,
+                               unsigned long long* hist_g) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        st.sum += __shfl_down_sync(0xffffffffu, st.sum, o);
+        st.sumsq += __shfl_down_sync(0xffffffffu, st.sumsq, o);
+        st.mn = fmin(st.mn, __shfl_down_sync(0xffffffffu, st.mn, o));
+        st.mx = fmax(st.mx, __shfl_down_sync(0xffffffffu, st.mx, o));
+        st.cnt += __shfl_down_sync(0xffffffffu, st.cnt, o);
+        st.nonfinite += __shfl_down_sync(0xffffffffu, st.nonfinite, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red_s[warp] = BlockPartial{st.sum, st.sumsq, st.mn, st.mx, st.cnt, st.nonfinite};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial r = red_s[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            r.sum += red_s[w].sum; r.sumsq += red_s[w].sumsq;
+            r.mn = fmin(r.mn, red_s[w].mn); r.mx = fmax(r.mx, red_s[w].mx);
+            r.cnt += red_s[w].cnt; r.nonfinite += red_s[w].nonfinite;
+        }
+        partials[blockIdx.x] = r;
+    }
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += blockDim.x)
+        if (hist_s[b]) atomicAdd(&hist_g[b], (unsigned long long)hist_s[b]);
+}
+
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const BlockPartial* __restrict__ partials, int nblocks,
+                                                             rbq_stats* __restrict__ out) {
+    __shared__ BlockPartial red[256];
+    BlockPartial r{0.0, 0.0, INFINITY, -INFINITY, 0, 0};
+    for (int i = threadIdx.x; i < nblocks; i += 256) {   // fixed assignment => deterministic sum order
+        const BlockPartial q = partials[i];
+        r.sum += q.sum; r.sumsq += q.sumsq; r.mn = fmin(r.mn, q.mn); r.mx = fmax(r.mx, q.mx);
+        r.cnt += q.cnt; r.nonfinite += q.nonfinite;
+    }
+    red[threadIdx.x] = r;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            BlockPartial& a = red[threadIdx.x];
+            const BlockPartial& b = red[threadIdx.x + o];
+            a.sum += b.sum; a.sumsq += b.sumsq; a.mn = fmin(a.mn, b.mn); a.mx = fmax(a.mx, b.mx);
+            a.cnt += b.cnt; a.nonfinite += b.nonfinite;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out->count += red[0].cnt; out->nonfinite += red[0].nonfinite;
+        out->sum += red[0].sum; out->sumsq += red[0].sumsq;
+        out->min = fmin(out->min, red[0].mn); out->max = fmax(out->max, red[0].mx);
+    }
+}
+
+__global__ void stats_reset_kernel(rbq_stats* __restrict__ st) {
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += blockDim.x) st->hist[b] = 0;
+    if (threadIdx.x == 0) { st->count = 0; st->nonfinite = 0; st->sum = 0.0; st->sumsq = 0.0; st->min = INFINITY; st->max = -INFINITY; }
+}
+
+// ---- pulse staging: copy into an aligned zero-padded buffer, max |a| for the series-degree bound ----
+__global__ void __launch_bounds__(1024) pulse_prep_kernel(const double* __restrict__ controls, int64_t nk,
+                                                          int64_t padded, double* __restrict__ staged,
+                                                          double* __restrict__ amax) {
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int64_t j = threadIdx.x; j < padded; j += 1024) {
+        const double a = j < nk ? controls[j] : 0.0;
+        staged[j] = a;
+        m = fmax(m, fabs(a));   // NaN controls propagate through the rollout itself
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) m = fmax(m, red[w]);
+        *amax = m;
+    }
+}
+
+// ---- per-sample pieces ----------------------------------------------------------------------------------
+// series degree class from a bound on x = theta^2: 0 -> K=3, 1 -> K=5, 2 -> K=8, 3 -> sincos
+RBQ_DEV int degree_class(double xb) { return xb <= 8.0e-4 ? 0 : (xb <= 4.0e-2 ? 1 : (xb <= 0.7 ? 2 : 3)); }
+RBQ_DEV int block_max_class(int c) {
+    const int ge1 = __syncthreads_or(c >= 1), ge2 = __syncthreads_or(c >= 2), ge3 = __syncthreads_or(c >= 3);
+    return ge3 ? 3 : (ge2 ? 2 : (ge1 ? 1 : 0));
+}
+template <int K> RBQ_DEV void su2_coeffs(double x, double& c, double& s) {
+    if (K > 0) su2_series<(K > 0 ? K : 1)>(x, c, s);
+    else {
+        if (x < 0.5) { su2_series<8>(x, c, s); return; }
+        const double th = sqrt(x);
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        c = cs; s = sn / th;
+    }
+}
+// advance SPT states through `len` knots of a tile:  q_j = w a_j + qd
+template <int K, int SPT>
+RBQ_DEV void su2_tile(const double* __restrict__ tile, int len, double w, const double (&p)[SPT], const double (&p2)[SPT],
+                      const double (&qd)[SPT], double (&v)[SPT][4]) {
+#pragma unroll 4
+    for (int j = 0; j < len; ++j) {
+        const double wa = w * tile[j];
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            const double q = wa + qd[i];
+            const double x = fma(q, q, p2[i]);
+            double c, s;
+            su2_coeffs<K>(x, c, s);
+            Prop<double> E{c, s * p[i], s * q};
+            prop_apply(E, v[i]);
+        }
+    }
+}
+// the 4x4 iso matrix whose first column is v (real iso of an SU(2) element)
+RBQ_DEV void iso_from_column(const double* v, double* E) {
+    E[0] = v[0];  E[1] = -v[1]; E[2] = -v[2];  E[3] = -v[3];
+    E[4] = v[1];  E[5] = v[0];  E[6] = -v[3];  E[7] = v[2];
+    E[8] = v[2];  E[9] = v[3];  E[10] = v[0];  E[11] = -v[1];
+    E[12] = v[3]; E[13] = -v[2]; E[14] = v[1]; E[15] = v[0];
+}
+RBQ_DEV void mv4_to(const double* E, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fma(E[4 * i + 3], x[3], fma(E[4 * i + 2], x[2], fma(E[4 * i + 1], x[1], E[4 * i] * x[0])));
+}
+// compute_fidelities (spin.jl:1198-1240): apply the gate propagator gate_count times, compare with
+// g^(k mod 4) psi0 after each; returns the last fidelity
+RBQ_DEV double gate_train(const double* E, const double* psi0, const GateIso& G, int64_t gate_count, double* fid_row) {
+    double tg[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tg[0][i] = psi0[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv4_to(G.g[k], psi0, tg[k + 1]);
+    double st[4] = {psi0[0], psi0[1], psi0[2], psi0[3]};
+    double f = fidelity_vec_iso2(st, tg[0]);
+    if (fid_row) fid_row[0] = f;
+    for (int64_t g = 1; g <= gate_count; ++g) {
+        mv4(E, st);
+        const int k = (int)(g & 3);
+        const double* t = k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3]));
+        f = fidelity_vec_iso2(st, t);
+        if (fid_row) fid_row[g] = f;
+    }
+    return f;
+}
+
+// ---- static-parameter sweep -------------------------------------------------------------------------------
+template <int ALGO, int SPT>
+__global__ void __launch_bounds__(MC_THREADS) mc_static_kernel(const McStaticArgs a) {
+    __shared__ __align__(128) double tile_s[2 * MC_TILE];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    PulsePipe pipe;
+    pipe.init(tile_s, bar_s, a.controls, a.nk);
+
+    const int64_t base = (int64_t)blockIdx.x * (MC_THREADS * SPT);
+    const double w = RBQ_PI * a.dt;
+    double p[SPT], p2[SPT], qd[SPT], psi0[SPT][4];
+    bool live[SPT];
+    int cls = 0;
+    const double wamax = w * (*a.amax);
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        const int64_t s = base + (int64_t)i * MC_THREADS + tid;
+        live[i] = s < a.S;
+        double fq = 0.0, da = 0.0;
+        psi0[i][0] = 1.0; psi0[i][1] = psi0[i][2] = psi0[i][3] = 0.0;
+        if (live[i]) {
+            if (a.philox) {
+                sample_static((uint64_t)(a.first + s), a.seed, a.fq0, a.fq_rel_sigma, a.fq_rel_clip, a.da_sigma, fq, da);
+                sample_psi0((uint64_t)(a.first + s), a.seed, psi0[i]);
+            } else {
+                fq = a.fq[s];
+                da = a.da ? a.da[s] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) psi0[i][c] = a.psi0[4 * s + c];
+            }
+        }
+        p[i] = w * fq; p2[i] = p[i] * p[i]; qd[i] = w * da;
+        const double qb = wamax + fabs(qd[i]);
+        const double xb = fma(qb, qb, p2[i]);
+        cls = max(cls, xb == xb ? degree_class(xb) : 3);
+    }
+    cls = block_max_class(cls);
+
+    double E[SPT][16];
+    if (ALGO == RBQ_ALGO_SU2) {
+        double v[SPT][4];
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) { v[i][0] = 1.0; v[i][1] = v[i][2] = v[i][3] = 0.0; }
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, false);
+            const int len = pipe.tile_len(ti);
+            if (cls == 0) su2_tile<3, SPT>(tile, len, w, p, p2, qd, v);
+            else if (cls == 1) su2_tile<5, SPT>(tile, len, w, p, p2, qd, v);
+            else if (cls == 2) su2_tile<8, SPT>(tile, len, w, p, p2, qd, v);
+            else su2_tile<0, SPT>(tile, len, w, p, p2, qd, v);
+            pipe.release();
+        }
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) iso_from_column(v[i], E[i]);
+    } else {
+        // reference algorithm (spin.jl:443-447): prop = exp((H0' + a_j H1) dt) * prop with the generic Pade exp
+#pragma unroll
+        for (int i = 0; i < SPT; ++i)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) E[i][c] = (c % 5 == 0) ? 1.0 : 0.0;
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, false);
+            const int len = pipe.tile_len(ti);
+            for (int j = 0; j < len; ++j) {
+                const double wa = w * tile[j];
+#pragma unroll
+                for (int i = 0; i < SPT; ++i) {
+                    double G[16], X[16], T[16];
+                    generator4(p[i], wa + qd[i], G);
+                    expm4_pade(G, X);
+                    mm4(X, E[i], T);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) E[i][c] = T[c];
+                }
+            }
+            pipe.release();
+        }
+    }
+
+    ThreadStats st;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        if (!live[i]) continue;
+        const int64_t s = base + (int64_t)i * MC_THREADS + tid;
+        double* row = a.fid ? a.fid + s * (a.gate_count + 1) : nullptr;
+        const double f = gate_train(E[i], psi0[i], a.gate, a.gate_count, row);
+        if (a.partials) st.add(1.0 - f, hist_s);
+    }
+    if (a.partials) {
+        __syncthreads();
+        block_stats_flush(st, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
+// ---- time-dependent amplitude noise --------------------------------------------------------------------------
+// white -> pink filter state of gen_pink_noise (spin.jl:1178-1192), generated on demand
+struct PinkGen {
+    uint64_t index, seed;
+    double x1 = 0, x2 = 0, x3 = 0, y1 = 0, y2 = 0, y3 = 0, spare = 0;
+    int64_t produced = 0;   // number of pink samples produced so far
+    double scale_dt_inv, namp, last = 0;
+    RBQ_DEV double next() {
+        double x0;
+        if ((produced & 1) == 0) philox_normal2(index, seed, (uint32_t)(produced >> 1), 2u, x0, spare);
+        else x0 = spare;
+        double y = 0.049922035 * x0;
+        if (produced >= 1) y += -0.095993537 * x1 - (-2.494956002) * y1;
+        if (produced >= 2) y += 0.050612699 * x2 - 2.017265875 * y2;
+        if (produced >= 3) y += -0.004408786 * x3 - (-0.522189400) * y3;
+        x3 = x2; x2 = x1; x1 = x0; y3 = y2; y2 = y1; y1 = y;
+        ++produced;
+        last = (y * scale_dt_inv) * namp;
+        return last;
+    }
+    RBQ_DEV double at(int64_t idx) {   // idx is non-decreasing over the rollout
+        while (produced <= idx) next();
+        return last;
+    }
+};
+
+template <int K> RBQ_DEV void noise_tile(const double* __restrict__ tile, int len, double w, double p, double p2, double dt,
+                                         double ndi, int64_t noise_len, const double* __restrict__ row, PinkGen* pg,
+                                         double& time, int64_t& cur, double& qd, double* v) {
+    for (int j = 0; j < len; ++j) {
+        int64_t idx = (int64_t)floor(time * ndi);   // 0-based form of spin.jl:476
+        idx = idx < noise_len - 1 ? idx : noise_len - 1;
+        if (idx != cur) {                           // same `time` in every thread: uniform branch
+            cur = idx;
+            qd = w * (row ? row[idx] : pg->at(idx));
+        }
+        const double q = fma(w, tile[j], qd);
+        const double x = fma(q, q, p2);
+        double c, s;
+        // the noise is unbounded a priori: leave the short series when a sample steps outside its range
+        if (K > 0 && !(x <= (K == 5 ? 4.0e-2 : 0.7))) su2_coeffs<0>(x, c, s);
+        else su2_coeffs<K>(x, c, s);
+        Prop<double> E{c, s * p, s * q};
+        prop_apply(E, v);
+        time = time + dt;                            // accumulated exactly like spin.jl:480
+    }
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs a) {
+    __shared__ __align__(128) double tile_s[2 * MC_TILE];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    PulsePipe pipe;
+    pipe.init(tile_s, bar_s, a.controls, a.nk);
+
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;   // dead lanes shadow the last sample so the block stays in lock step
+    const double w = RBQ_PI * a.dt;
+    const double p = w * a.fq, p2 = p * p;
+    const double* row = a.philox ? nullptr : a.noise + sc * a.noise_len;
+    PinkGen pg;
+    pg.index = (uint64_t)(a.first + sc); pg.seed = a.seed; pg.scale_dt_inv = a.noise_dt_inv; pg.namp = a.namp;
+    double psi0[4];
+    if (a.psi0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) psi0[c] = a.psi0[4 * sc + c];
+    } else sample_psi0((uint64_t)(a.first + sc), a.seed, psi0);
+    // series class from the noiseless pulse with head-room; noise_tile re-checks every step
+    int cls;
+    {
+        const double qb = w * (*a.amax) * 1.05;
+        const double xb = fma(qb, qb, p2);
+        cls = xb == xb ? max(degree_class(xb), 1) : 3;
+    }
+    double tg[4][4], st[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { tg[0][i] = psi0[i]; st[i] = psi0[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv4_to(a.gate.g[k], psi0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (a.gate_count + 1) : nullptr;
+    double f = fidelity_vec_iso2(st, tg[0]);
+    if (frow) frow[0] = f;
+    double time = 0.0, qd = 0.0;
+    int64_t cur = -1;
+    for (int64_t g = 1; g <= a.gate_count; ++g) {
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, g < a.gate_count);
+            const int len = pipe.tile_len(ti);
+            if (ALGO == RBQ_ALGO_SU2) {
+                if (cls == 1) noise_tile<5>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
+                else if (cls == 2) noise_tile<8>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
+                else noise_tile<0>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
+            } else {
+                for (int j = 0; j < len; ++j) {
+                    int64_t idx = (int64_t)floor(time * a.noise_dt_inv);
+                    idx = idx < a.noise_len - 1 ? idx : a.noise_len - 1;
+                    if (idx != cur) { cur = idx; qd = w * (row ? row[idx] : pg.at(idx)); }
+                    double G[16], X[16];
+                    generator4(p, fma(w, tile[j], qd), G);
+                    expm4_pade(G, X);
+                    mv4(X, st);
+                    time = time + a.dt;
+                }
+            }
+            pipe.release();
+        }
+        const int k = (int)(g & 3);
+        f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+        if (frow) frow[g] = f;
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
+// ---- Lindblad T1 (+T2) rollout in the Bloch picture ------------------------------------------------------------
+// rho = (t I + r.sigma)/2.  With equal up/down rates gamma_1 (spin.jl:529-531) the map is unital:
+//   dr/dt = Omega x r - diag(g2, g2, g1) r,  Omega = 2 pi (a, 0, fq),  g2 = gamma_1 + Gamma(t), g1 = 2 gamma_1,
+// the real 3x3 equivalent of the complex 4x4 vec-Liouvillian the reference exponentiates.  exp(M dt) v is
+// summed as a Taylor series whose length comes from a bound on ||M dt||.
+struct BlochGen { double wz, wx, g2, g1; };
+template <int NV> RBQ_DEV void bloch_advance(const BlochGen& m, int kmax, double (&r)[NV][3]) {
+    double t[NV][3];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) { t[c][0] = r[c][0]; t[c][1] = r[c][1]; t[c][2] = r[c][2]; }
+    for (int k = 1; k <= kmax; ++k) {
+        const double ik = 1.0 / (double)k;
+        const double wz = m.wz * ik, wx = m.wx * ik, g2 = m.g2 * ik, g1 = m.g1 * ik;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            const double n0 = fma(-wz, t[c][1], -g2 * t[c][0]);
+            const double n1 = fma(-wx, t[c][2], fma(wz, t[c][0], -g2 * t[c][1]));
+            const double n2 = fma(wx, t[c][1], -g1 * t[c][2]);
+            t[c][0] = n0; t[c][1] = n1; t[c][2] = n2;
+            r[c][0] += n0; r[c][1] += n1; r[c][2] += n2;
+        }
+    }
+}
+RBQ_DEV int taylor_terms(double b) {   // smallest k with b^(k+1)/(k+1)! < 1e-18 (b >= 0), capped
+    double term = b;
+    int k = 1;
+    while (term > 1e-18 && k < 60) { ++k; term *= b / (double)k; }
+    return k;
+}
+// Uhlmann sqrt-fidelity of 2x2 states in Bloch form: sqrt(tr(r1 r2) + 2 sqrt(det r1 det r2))
+RBQ_DEV double fidelity_bloch(double t1, const double* r1, double t2, const double* r2) {
+    const double trp = 0.5 * fma(t1, t2, fma(r1[0], r2[0], fma(r1[1], r2[1], r1[2] * r2[2])));
+    const double d1 = 0.25 * (t1 * t1 - (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]));
+    const double d2 = 0.25 * (t2 * t2 - (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]));
+    const double dd = fmax(d1, 0.0) * fmax(d2, 0.0);
+    return sqrt(fmax(trp + 2.0 * sqrt(dd), 0.0));
+}
+RBQ_DEV void mv3_to(const double* R, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y[i] = fma(R[3 * i + 2], x[2], fma(R[3 * i + 1], x[1], R[3 * i] * x[0]));
+}
+
+__global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs a, int channels) {
+    __shared__ __align__(128) double tile_s[2 * MC_TILE];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    __shared__ int kmax_s;
+    const int tid = threadIdx.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    if (tid == 0) kmax_s = 1;
+    PulsePipe pipe;
+    pipe.init(tile_s, bar_s, a.controls, a.nk);
+
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double da = a.da ? a.da[sc] : 0.0;
+    const bool t1_on = (channels & RBQ_LINDBLAD_T1) != 0, t2_on = (channels & RBQ_LINDBLAD_T2) != 0;
+    const bool time_dep = t2_on && a.t2_gamma_f != 0.0;   // Gamma(t) differs from gate to gate
+    const double w2 = 2.0 * RBQ_PI * a.dt;
+    // rho0: column-major vec, (re,im) pairs: [r00, r10, r01, r11]
+    const double* q = a.rho0 + 8 * sc;
+    const double tr0 = q[0] + q[6];
+    double r0[3] = {q[2] + q[4], q[3] - q[5], q[0] - q[6]};   // x = 2 Re rho10 (Hermitian part), y = 2 Im rho10, z
+    // Taylor length from the largest generator norm this block can see
+    {
+        const double ttot = a.dt * (double)a.nk * (double)a.gate_count;
+        const double gmax = (t1_on ? 2.0 / 269.03e3 : 0.0) + (t2_on ? a.t2_gamma_c + 2.0 * a.t2_gamma_f * a.t2_gamma_f * ttot : 0.0);
+        const double b = w2 * (fabs(a.fq) + *a.amax + fabs(da)) + gmax * a.dt;
+        atomicMax(&kmax_s, b == b ? taylor_terms(b) : 60);
+    }
+    __syncthreads();
+    const int kmax = kmax_s;
+
+    double tg[4][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tg[0][i] = r0[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv3_to(a.gate.r[k], r0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (a.gate_count + 1) : nullptr;
+    double f = fidelity_bloch(tr0, r0, tr0, tg[0]);
+    if (frow) frow[0] = f;
+    double r[3] = {r0[0], r0[1], r0[2]};
+
+    auto generator = [&](double aj, double tmid) {
+        const double c1 = aj + da;
+        BlochGen m;
+        m.wz = w2 * a.fq; m.wx = w2 * c1;
+        const double g1 = t1_on ? a.dt / t1_interp<double>(c1, 1e3) : 0.0;   // gamma_1 dt, T1 in ns (spin.jl:529)
+        const double gphi = t2_on ? a.dt * (a.t2_gamma_c + 2.0 * a.t2_gamma_f * a.t2_gamma_f * tmid) : 0.0;
+        m.g2 = g1 + gphi; m.g1 = 2.0 * g1;
+        return m;
+    };
+
+    if (!time_dep) {
+        // compose the one-gate map from its action on the three basis vectors, then apply it gate_count times
+        double P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};   // P[c] = image of e_c
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, false);
+            const int len = pipe.tile_len(ti);
+            for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, P);
+            pipe.release();
+        }
+        for (int64_t g = 1; g <= a.gate_count; ++g) {
+            const double n0 = fma(P[2][0], r[2], fma(P[1][0], r[1], P[0][0] * r[0]));
+            const double n1 = fma(P[2][1], r[2], fma(P[1][1], r[1], P[0][1] * r[0]));
+            const double n2 = fma(P[2][2], r[2], fma(P[1][2], r[1], P[0][2] * r[0]));
+            r[0] = n0; r[1] = n1; r[2] = n2;
+            const int k = (int)(g & 3);
+            f = fidelity_bloch(tr0, r, tr0, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+            if (frow) frow[g] = f;
+        }
+    } else {
+        double rr[1][3] = {{r[0], r[1], r[2]}};
+        int64_t step = 0;
+        for (int64_t g = 1; g <= a.gate_count; ++g) {
+            for (int ti = 0; ti < pipe.ntiles; ++ti) {
+                const double* tile = pipe.acquire(ti, g < a.gate_count);
+                const int len = pipe.tile_len(ti);
+                for (int j = 0; j < len; ++j, ++step) bloch_advance<1>(generator(tile[j], ((double)step + 0.5) * a.dt), kmax, rr);
+                pipe.release();
+            }
+            const int k = (int)(g & 3);
+            f = fidelity_bloch(tr0, rr[0], tr0, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+            if (frow) frow[g] = f;
+        }
+        r[0] = rr[0][0]; r[1] = rr[0][1]; r[2] = rr[0][2];
+    }
+    if (a.rho_out && live) {
+        double* o = a.rho_out + 8 * s;
+        o[0] = 0.5 * (tr0 + r[2]); o[1] = 0.0;           // rho00
+        o[2] = 0.5 * r[0];         o[3] = 0.5 * r[1];    // rho10 = (x + i y)/2
+        o[4] = 0.5 * r[0];         o[5] = -0.5 * r[1];   // rho01
+        o[6] = 0.5 * (tr0 - r[2]); o[7] = 0.0;           // rho11
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
+// ---- sample materialisation (parity aids) -------------------------------------------------------------------------
+__global__ void philox_samples_kernel(int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
+                                      double fq_rel_clip, double da_sigma, double* __restrict__ fq, double* __restrict__ da,
+                                      double* __restrict__ psi0) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double f, d, psi[4];
+    sample_static((uint64_t)(first + s), seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma, f, d);
+    sample_psi0((uint64_t)(first + s), seed, psi);
+    if (fq) fq[s] = f;
+    if (da) da[s] = d;
+    if (psi0) { psi0[4 * s] = psi[0]; psi0[4 * s + 1] = psi[1]; psi0[4 * s + 2] = psi[2]; psi0[4 * s + 3] = psi[3]; }
+}
+__global__ void pink_noise_kernel(int64_t first, int64_t S, uint64_t seed, double namp, double noise_dt_inv,
+                                  int64_t noise_len, double* __restrict__ noise) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    PinkGen pg;
+    pg.index = (uint64_t)(first + s); pg.seed = seed; pg.scale_dt_inv = noise_dt_inv; pg.namp = namp;
+    for (int64_t i = 0; i < noise_len; ++i) noise[s * noise_len + i] = pg.next();
+}
+
+// ---- DFMA saturation loop: the FP64 roofline denominator --------------------------------------------------------------
+constexpr int PEAK_CHAINS = 16;
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double* __restrict__ sink) {
+    double acc[PEAK_CHAINS];
+    const double m = 1.0 - 1e-9 * (double)(threadIdx.x & 7), c = 1e-9 * (double)(blockIdx.x & 3);
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = (double)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = fma(acc[i], m, c);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; ++i) t += acc[i];
+    if (t == 123456.789) sink[0] = t;   // never true; keeps the loop alive
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------------------------
+static inline int static_spt(int64_t S, int sm_count, int algo) {
+    if (algo != RBQ_ALGO_SU2) return 1;
+    // two samples per thread once every SM can still be given >= 8 blocks
+    return S >= (int64_t)sm_count * 8 * MC_THREADS * 2 ? 2 : 1;
+}
+int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
+    const int per = MC_THREADS * static_spt(S, h->sm_count, algo);
+    return (int)((S + per - 1) / per);
+}
+int mc_noise_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
+int lindblad_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
+
+int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax) {
+    // staged pulse lives in dbuf[0] (sized by the caller), padded to a multiple of 2 knots
+    const int64_t padded = (nk + 1) & ~(int64_t)1;
+    pulse_prep_kernel<<<1, 1024, 0, h->stream>>>(d_controls, nk, padded, (double*)h->dbuf[0], d_amax);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
+    const int spt = static_spt(a.S, h->sm_count, algo);
+    const int blocks = mc_static_blocks(h, a.S, algo);
+    if (nblocks_out) *nblocks_out = blocks;
+    if (algo == RBQ_ALGO_SU2) {
+        if (spt == 2) mc_static_kernel<RBQ_ALGO_SU2, 2><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+        else mc_static_kernel<RBQ_ALGO_SU2, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    } else if (algo == RBQ_ALGO_PADE) {
+        mc_static_kernel<RBQ_ALGO_PADE, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    } else return RBQ_E_ALGO;
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out) {
+    const int blocks = mc_noise_blocks(h, a.S);
+    if (nblocks_out) *nblocks_out = blocks;
+    if (algo == RBQ_ALGO_SU2) mc_noise_kernel<RBQ_ALGO_SU2><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    else if (algo == RBQ_ALGO_PADE) mc_noise_kernel<RBQ_ALGO_PADE><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    else return RBQ_E_ALGO;
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out) {
+    const int blocks = lindblad_blocks(h, a.S);
+    if (nblocks_out) *nblocks_out = blocks;
+    lindblad_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, channels);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_stats_finalize(rbq_handle* h, const BlockPartial* partials, int nblocks, rbq_stats* d_stats) {
+    stats_finalize_kernel<<<1, 256, 0, h->stream>>>(partials, nblocks, d_stats);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_stats_reset(rbq_handle* h, rbq_stats* d_stats) {
+    stats_reset_kernel<<<1, 256, 0, h->stream>>>(d_stats);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
+                          double fq_rel_clip, double da_sigma, double* d_fq, double* d_da, double* d_psi0) {
+    philox_samples_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(first, S, seed, fq0, fq_rel_sigma, fq_rel_clip,
+                                                                            da_sigma, d_fq, d_da, d_psi0);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double namp, double noise_dt_inv,
+                      int64_t noise_len, double* d_noise) {
+    pink_noise_kernel<<<(unsigned)((S + 63) / 64), 64, 0, h->stream>>>(first, S, seed, namp, noise_dt_inv, noise_len, d_noise);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out, int* flops_per_thread_iter) {
+    const int blocks = h->sm_count * 8;
+    fp64_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters, d_sink);
+    h->launches++;
+    if (nthreads_out) *nthreads_out = blocks * 256;
+    if (flops_per_thread_iter) *flops_per_thread_iter = 8 * PEAK_CHAINS * 2;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rbq

@@ -1,0 +1,242 @@
+// rbq_models.cuh — the augmented-state step maps of the reference's `Model` types, written once
+// over a scalar type T (double, or Tan<NT> for the Jacobian kernels) and an IO policy that says
+// where x, u come from and where x' goes (global trajectory arrays, or the [A_k B_k] block).
+//
+// Reference: RD.discrete_dynamics(::Type{RK3}, model, x, u, t, dt) of
+//   spin13.jl:44-58, spin12.jl:165-192, spin18.jl:162-190, spin15.jl:50-73, spin11.jl:64-117,
+//   spin17.jl:61-114, spin30.jl:86-202.
+// The propagator is the closed-form SU(2) expression of rbq_math.cuh, not a generic exp.
+#pragma once
+#include "rbq_math.cuh"
+
+namespace rbq {
+
+// dimensions (RD.state_dim / RD.control_dim): spin13.jl:39-40, spin12.jl:26-33, spin15.jl:43-46,
+// spin11.jl:53-55, spin18.jl:23-28, spin30.jl:29-32,67-70
+__host__ __device__ inline int model_state_dim(const rbq_model_params& p) {
+    switch (p.model_id) {
+    case RBQ_MODEL_SPIN13: return 11;
+    case RBQ_MODEL_SPIN12:
+    case RBQ_MODEL_SPIN18: return 43;
+    case RBQ_MODEL_SPIN15: return 11 + (p.decay_aware ? 1 : 0);
+    case RBQ_MODEL_SPIN11:
+    case RBQ_MODEL_SPIN17:
+        if (p.derivative_order < 0 || p.derivative_order > 2) return RBQ_E_MODEL;
+        return 11 + 4 * p.derivative_order;
+    case RBQ_MODEL_SPIN30:
+        if (p.sample_state_count < 1 || p.sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
+        return 15 + 41 * p.sample_state_count;
+    default: return RBQ_E_MODEL;
+    }
+}
+__host__ __device__ inline int model_control_dim(const rbq_model_params& p) {
+    if (model_state_dim(p) < 0) return RBQ_E_MODEL;
+    if (p.model_id == RBQ_MODEL_SPIN15) return 1 + (p.time_optimal ? 1 : 0);
+    return 1;
+}
+
+// psi' = E psi for the 4-block starting at `at`
+template <class T, class IO> RBQ_DEV void advance_block(const Prop<T>& E, IO& io, int at) {
+    const T a0 = io.x(at), a1 = io.x(at + 1), a2 = io.x(at + 2), a3 = io.x(at + 3);
+    T o0, o1, o2, o3;
+    prop_apply<T>(E, a0, a1, a2, a3, o0, o1, o2, o3);
+    io.out(at, o0); io.out(at + 1, o1); io.out(at + 2, o2); io.out(at + 3, o3);
+}
+// [int a, a, da] Euler chain driven by u = d2a (spin13.jl:49-51)
+template <class T, class DT, class IO> RBQ_DEV void control_chain(IO& io, int base, const DT& dt) {
+    const T ia = io.x(base), a = io.x(base + 1), da = io.x(base + 2), u = io.u(0);
+    io.out(base, ia + a * dt);
+    io.out(base + 1, a + da * dt);
+    io.out(base + 2, da + u * dt);
+}
+template <class T, class DT> RBQ_DEV Prop<T> prop_of(double f, const T& a, const DT& dt) {
+    const DT w = RBQ_PI * dt;
+    const T p = T(w * f), q = a * w;
+    const T x = p * p + q * q;
+    T c, s;
+    su2_general(x, c, s);
+    Prop<T> E; E.c = c; E.sp = s * p; E.sq = s * q;
+    return E;
+}
+
+// ---- spin13 -----------------------------------------------------------------------------------
+template <class T, class IO> RBQ_DEV void step_spin13(const rbq_model_params& p, IO& io, double dt) {
+    const Prop<T> E = prop_of<T, double>(p.fq, io.x(9), dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    control_chain<T, double>(io, 8, dt);
+}
+// ---- spin12 (fq +- sigma) and spin18 (a +- namp) ------------------------------------------------
+template <class T, class IO> RBQ_DEV void step_spin12_18(const rbq_model_params& p, IO& io, double dt) {
+    const T a = io.x(9);
+    const Prop<T> E = prop_of<T, double>(p.fq, a, dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    control_chain<T, double>(io, 8, dt);
+    Prop<T> Ep, En;
+    if (p.model_id == RBQ_MODEL_SPIN12) {
+        Ep = prop_of<T, double>(p.fq_samples[0], a, dt);
+        En = prop_of<T, double>(p.fq_samples[1], a, dt);
+    } else {
+        Ep = prop_of<T, double>(p.fq, a + p.namp, dt);
+        En = prop_of<T, double>(p.fq, a - p.namp, dt);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) advance_block<T>(Ep, io, 11 + 4 * s);
+#pragma unroll
+    for (int s = 4; s < 8; ++s) advance_block<T>(En, io, 11 + 4 * s);
+}
+// ---- spin15: dt = u2^2 when time optimal, int gamma_1 state when decay aware ---------------------
+template <class T, class DT, class IO> RBQ_DEV void step_spin15_dt(const rbq_model_params& p, IO& io, const DT& dt) {
+    const T a = io.x(9);
+    const Prop<T> E = prop_of<T, DT>(p.fq, a, dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    control_chain<T, DT>(io, 8, dt);
+    if (p.decay_aware) {
+        const T t1 = t1_interp<T>(a, 1.0);   // microseconds, spin15.jl:66-69 / spin.jl:396
+        io.out(11, io.x(11) + (1.0 / t1) * dt);
+    }
+}
+template <class T, class IO> RBQ_DEV void step_spin15(const rbq_model_params& p, IO& io, double dt) {
+    if (p.time_optimal) {
+        const T u2 = io.u(1);
+        step_spin15_dt<T, T>(p, io, u2 * u2);
+    } else {
+        step_spin15_dt<T, double>(p, io, dt);
+    }
+}
+// ---- spin11 (d/dfq, H0 source) and spin17 (d/da, H1 source): Lawson-Euler --------------------------
+template <class T, class IO> RBQ_DEV void step_spin11_17(const rbq_model_params& p, IO& io, double dt) {
+    const Prop<T> E = prop_of<T, double>(p.fq, io.x(9), dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    control_chain<T, double>(io, 8, dt);
+    const bool h1 = p.model_id == RBQ_MODEL_SPIN17;
+    const double w = RBQ_PI * dt;
+#pragma unroll
+    for (int o = 1; o <= 2; ++o) {
+        if (p.derivative_order < o) break;
+        // d^o psi' = E (d^o psi + o dt H d^(o-1) psi), source state: psi1 (o=1), d psi (o=2)
+        const int src = (o == 1) ? 0 : 11, dst = 11 + 4 * (o - 1);
+        const T s0 = io.x(src), s1 = io.x(src + 1), s2 = io.x(src + 2), s3 = io.x(src + 3);
+        T g0, g1, g2, g3;
+        if (h1) apply_N1<T>(s0, s1, s2, s3, g0, g1, g2, g3);
+        else apply_N0<T>(s0, s1, s2, s3, g0, g1, g2, g3);
+        const double f = w * (double)o;
+        const T w0 = io.x(dst) + g0 * f, w1 = io.x(dst + 1) + g1 * f, w2 = io.x(dst + 2) + g2 * f,
+                w3 = io.x(dst + 3) + g3 * f;
+        T o0, o1, o2, o3;
+        prop_apply<T>(E, w0, w1, w2, w3, o0, o1, o2, o3);
+        io.out(dst, o0); io.out(dst + 1, o1); io.out(dst + 2, o2); io.out(dst + 3, o3);
+    }
+}
+// ---- spin30: unscented transform ---------------------------------------------------------------
+template <class T, class IO> RBQ_DEV void step_spin30(const rbq_model_params& p, IO& io, double dt) {
+    const T a = io.x(13);
+    const Prop<T> E = prop_of<T, double>(p.fq, a, dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    advance_block<T>(E, io, 8);
+    control_chain<T, double>(io, 12, dt);
+    const double sig = sqrt(p.fq_cov);   // used as a deviation WITHOUT alpha, spin30.jl:102,108,113
+    const Prop<T> Ep = prop_of<T, double>(p.fq + sig, a, dt);
+    const Prop<T> En = prop_of<T, double>(p.fq - sig, a, dt);
+    const double cf = 1.0 / (2.0 * p.alpha * p.alpha);
+    for (int c = 0; c < p.sample_state_count; ++c) {
+        const int off = 15 + 41 * c;
+        T s[10][4];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const Prop<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
+            prop_apply<T>(M, io.x(off + 4 * j), io.x(off + 4 * j + 1), io.x(off + 4 * j + 2), io.x(off + 4 * j + 3),
+                          s[j][0], s[j][1], s[j][2], s[j][3]);
+        }
+        T sm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            T acc = s[0][i];
+#pragma unroll
+            for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
+            sm[i] = acc * 0.1;
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[j][i] = s[j][i] - sm[i];
+        // lower triangle of the 4x4 sample covariance (row-major packed: 00 10 11 20 21 22 30 31 32 33)
+        T P[10];
+        {
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k <= i; ++k) {
+                    T acc = s[0][i] * s[0][k];
+#pragma unroll
+                    for (int j = 1; j < 10; ++j) acc = acc + s[j][i] * s[j][k];
+                    P[q++] = acc * cf;
+                }
+        }
+        // Cholesky of blkdiag(P, fq_cov): the 5th row/column decouples exactly, so only the 4x4
+        // factor is needed (spin30.jl:136-140).  L packed like P.
+        T L[10];
+#define RBQ_TRI(i, k) ((i) * ((i) + 1) / 2 + (k))
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            T d = P[RBQ_TRI(j, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) d = d - L[RBQ_TRI(j, k)] * L[RBQ_TRI(j, k)];
+            const T ljj = tsqrt(d);
+            L[RBQ_TRI(j, j)] = ljj;
+            const T inv = 1.0 / ljj;
+#pragma unroll
+            for (int i = j + 1; i < 4; ++i) {
+                T t = P[RBQ_TRI(i, j)];
+#pragma unroll
+                for (int k = 0; k < j; ++k) t = t - L[RBQ_TRI(i, k)] * L[RBQ_TRI(j, k)];
+                L[RBQ_TRI(i, j)] = t * inv;
+            }
+        }
+        // resample sm +- alpha L[:,j], s5 = s10 = sm, normalise each (spin30.jl:141-166)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            T vp[4], vm[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (j < 4 && i >= j) {
+                    const T col = L[RBQ_TRI(i, j)] * p.alpha;
+                    vp[i] = sm[i] + col; vm[i] = sm[i] - col;
+                } else { vp[i] = sm[i]; vm[i] = sm[i]; }
+            }
+            const T np = 1.0 / tsqrt(vp[0] * vp[0] + vp[1] * vp[1] + vp[2] * vp[2] + vp[3] * vp[3]);
+            const T nm = (j < 4) ? 1.0 / tsqrt(vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[3] * vm[3]) : np;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                io.out(off + 4 * j + i, vp[i] * np);
+                io.out(off + 4 * (j + 5) + i, vm[i] * nm);
+            }
+        }
+#undef RBQ_TRI
+        // penalty = tr(P S) + (sm - psi_nom)' S (sm - psi_nom), psi_nom from the INPUT state
+        T pen = P[0] * p.S_diag[0] + P[2] * p.S_diag[1] + P[5] * p.S_diag[2] + P[9] * p.S_diag[3];
+        const int nom = p.nominal_offset[c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T dn = sm[i] - io.x(nom + i);
+            pen = pen + dn * dn * p.S_diag[i];
+        }
+        io.out(off + 40, pen);
+    }
+}
+
+// MODEL is the reference file number (RBQ_MODEL_*); one kernel instantiation per model family.
+template <int MODEL, class T, class IO> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double dt) {
+    if (MODEL == RBQ_MODEL_SPIN13) step_spin13<T>(p, io, dt);
+    else if (MODEL == RBQ_MODEL_SPIN12) step_spin12_18<T>(p, io, dt);   // also spin18
+    else if (MODEL == RBQ_MODEL_SPIN15) step_spin15<T>(p, io, dt);
+    else if (MODEL == RBQ_MODEL_SPIN11) step_spin11_17<T>(p, io, dt);   // also spin17
+    else step_spin30<T>(p, io, dt);
+}
+
+}  // namespace rbq

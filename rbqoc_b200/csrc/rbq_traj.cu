@@ -1,0 +1,171 @@
+// rbq_traj.cu — trajectory-level kernels behind the RobotDynamics model API:
+//   rollout           x[k+1] = discrete_dynamics(RK3, model, x[k], u[k], t, dt[k])   (TO.rollout!)
+//   closed-loop       the iLQR line-search rollouts, one thread per step-size candidate
+//   jacobians         [A_k B_k] for every knot in one launch; forward-mode tangents written by hand
+//                     (Tan<NT>), replacing RD's default ForwardDiff.jacobian over [x;u]
+// Reference step maps: see rbq_models.cuh.  sm_100a only.
+#include "rbq_internal.h"
+#include "rbq_models.cuh"
+
+namespace rbq {
+
+// ---- IO policies --------------------------------------------------------------------------------
+struct ValueIO {
+    const double* __restrict__ xi;
+    const double* __restrict__ ui;
+    double* __restrict__ xo;
+    RBQ_DEV double x(int i) const { return xi[i]; }
+    RBQ_DEV double u(int j) const { return ui[j]; }
+    RBQ_DEV void out(int i, double v) { xo[i] = v; }
+};
+// lane `c0/NT` of a knot carries the seed columns [c0, c0+NT) of [x;u]
+template <int NT> struct TangentIO {
+    const double* __restrict__ xi;
+    const double* __restrict__ ui;
+    double* __restrict__ ab;   // column-major n x (n+m)
+    int n, ncol, c0;
+    RBQ_DEV Tan<NT> seed(double v, int idx) const {
+        Tan<NT> r; r.v = v;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) r.d[j] = (idx == c0 + j) ? 1.0 : 0.0;
+        return r;
+    }
+    RBQ_DEV Tan<NT> x(int i) const { return seed(xi[i], i); }
+    RBQ_DEV Tan<NT> u(int j) const { return seed(ui[j], n + j); }
+    RBQ_DEV void out(int i, const Tan<NT>& v) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            if (c0 + j < ncol) ab[(size_t)(c0 + j) * n + i] = v.d[j];
+    }
+};
+
+// ---- kernels ------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n, int m, int64_t B, int64_t N,
+                                                      const double* __restrict__ x0, const double* __restrict__ U,
+                                                      const double* __restrict__ dt, double* __restrict__ X) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* Xb = X + (size_t)b * N * n;
+    for (int i = 0; i < n; ++i) Xb[i] = x0[(size_t)b * n + i];
+    const double* Ub = U + (size_t)b * (N - 1) * m;
+    for (int64_t k = 0; k + 1 < N; ++k) {
+        ValueIO io{Xb + k * n, Ub + k * m, Xb + (k + 1) * n};
+        model_step<MODEL, double>(p, io, dt[k]);
+    }
+}
+
+// du = K_k (x_k - xref_k) + alpha d_k ; u_k = uref_k + du   (Altro's forward pass; K col-major m x n)
+template <int MODEL>
+__global__ void __launch_bounds__(32) closedloop_kernel(rbq_model_params p, int n, int m, int64_t N,
+                                                        const double* __restrict__ Xref, const double* __restrict__ Uref,
+                                                        const double* __restrict__ K, const double* __restrict__ d,
+                                                        const double* __restrict__ dt, int64_t nalpha,
+                                                        const double* __restrict__ alphas, double* __restrict__ X,
+                                                        double* __restrict__ Uout) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nalpha) return;
+    const double alpha = alphas[c];
+    double* Xc = X + (size_t)c * N * n;
+    double* Uc = Uout + (size_t)c * (N - 1) * m;
+    for (int i = 0; i < n; ++i) Xc[i] = Xref[i];
+    for (int64_t k = 0; k + 1 < N; ++k) {
+        for (int j = 0; j < m; ++j) {
+            double du = alpha * d[k * m + j];
+            for (int i = 0; i < n; ++i) du = fma(K[(size_t)k * m * n + (size_t)i * m + j], Xc[k * n + i] - Xref[k * n + i], du);
+            Uc[k * m + j] = Uref[k * m + j] + du;
+        }
+        ValueIO io{Xc + k * n, Uc + k * m, Xc + (k + 1) * n};
+        model_step<MODEL, double>(p, io, dt[k]);
+    }
+}
+
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int n, int m, int lanes_per_knot,
+                                                        int64_t K, const double* __restrict__ X,
+                                                        const double* __restrict__ U, const double* __restrict__ dt,
+                                                        double* __restrict__ AB) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = t / lanes_per_knot;
+    if (k >= K) return;
+    const int lane = (int)(t - k * lanes_per_knot);
+    TangentIO<NT> io{X + k * n, U + k * m, AB + (size_t)k * n * (n + m), n, n + m, lane * NT};
+    model_step<MODEL, Tan<NT>>(p, io, dt[k]);
+}
+
+// ---- launchers ------------------------------------------------------------------------------------
+static inline int family(int model_id) {
+    switch (model_id) {
+    case RBQ_MODEL_SPIN13: return RBQ_MODEL_SPIN13;
+    case RBQ_MODEL_SPIN12: case RBQ_MODEL_SPIN18: return RBQ_MODEL_SPIN12;
+    case RBQ_MODEL_SPIN15: return RBQ_MODEL_SPIN15;
+    case RBQ_MODEL_SPIN11: case RBQ_MODEL_SPIN17: return RBQ_MODEL_SPIN11;
+    case RBQ_MODEL_SPIN30: return RBQ_MODEL_SPIN30;
+    }
+    return -1;
+}
+#define RBQ_DISPATCH_FAMILY(fam, CALL)                                   \
+    switch (fam) {                                                       \
+    case RBQ_MODEL_SPIN13: { CALL(RBQ_MODEL_SPIN13); break; }            \
+    case RBQ_MODEL_SPIN12: { CALL(RBQ_MODEL_SPIN12); break; }            \
+    case RBQ_MODEL_SPIN15: { CALL(RBQ_MODEL_SPIN15); break; }            \
+    case RBQ_MODEL_SPIN11: { CALL(RBQ_MODEL_SPIN11); break; }            \
+    case RBQ_MODEL_SPIN30: { CALL(RBQ_MODEL_SPIN30); break; }            \
+    default: return RBQ_E_MODEL;                                         \
+    }
+
+int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, const double* d_x0,
+                   const double* d_U, const double* d_dt, double* d_X) {
+    const int n = model_state_dim(p), m = model_control_dim(p);
+    if (n < 0 || m < 0) return RBQ_E_MODEL;
+    const int threads = B >= 128 ? 128 : 32;
+    const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+#define CALL(M) rollout_kernel<M><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, d_x0, d_U, d_dt, d_X)
+    RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
+#undef CALL
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const double* d_Xref, const double* d_Uref,
+                      const double* d_K, const double* d_d, const double* d_dt, int64_t nalpha, const double* d_alphas,
+                      double* d_X, double* d_Uout) {
+    const int n = model_state_dim(p), m = model_control_dim(p);
+    if (n < 0 || m < 0) return RBQ_E_MODEL;
+    // one candidate per warp-sized block so that candidates spread over SMs
+    const unsigned blocks = (unsigned)nalpha;
+#define CALL(M) closedloop_kernel<M><<<blocks, 1, 0, h->stream>>>(p, n, m, N, d_Xref, d_Uref, d_K, d_d, d_dt, nalpha, d_alphas, d_X, d_Uout)
+    RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
+#undef CALL
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
+                     const double* d_dt, double* d_AB) {
+    const int n = model_state_dim(p), m = model_control_dim(p);
+    if (n < 0 || m < 0) return RBQ_E_MODEL;
+    const int fam = family(p.model_id);
+    // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
+    const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
+    const int lpk = (n + m + nt - 1) / nt;
+    const int threads = 128;
+    const int64_t total = K * lpk;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+#define CALL2(M) jacobians_kernel<M, 2><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
+#define CALL4(M) jacobians_kernel<M, 4><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
+    switch (fam) {
+    case RBQ_MODEL_SPIN13: CALL4(RBQ_MODEL_SPIN13); break;
+    case RBQ_MODEL_SPIN15: CALL4(RBQ_MODEL_SPIN15); break;
+    case RBQ_MODEL_SPIN11: CALL4(RBQ_MODEL_SPIN11); break;
+    case RBQ_MODEL_SPIN12: CALL2(RBQ_MODEL_SPIN12); break;
+    case RBQ_MODEL_SPIN30: CALL2(RBQ_MODEL_SPIN30); break;
+    default: return RBQ_E_MODEL;
+    }
+#undef CALL2
+#undef CALL4
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rbq

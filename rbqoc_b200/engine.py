@@ -1,0 +1,291 @@
+"""Engine: one `rbq_handle` (one CUDA device) behind numpy / torch-tensor friendly calls.
+
+Every method is a thin argument-marshalling layer over one C-ABI entry point of include/rbq.h;
+all arithmetic happens in librbq.so's sm_100a kernels.  Host arrays are numpy float64;
+`*_dev` methods take torch CUDA tensors (device memory and streams are torch's job here,
+nothing else is).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ModelParams, RbqError, Stats
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    # torch tensor on the device
+    if a.dtype.itemsize != 8 or not a.is_contiguous():
+        raise ValueError("device tensors must be contiguous 8-byte element tensors")
+    return C.c_void_p(a.data_ptr())
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.rbq_create(int(device), C.byref(h))
+        if rc:
+            raise RbqError(rc, "rbq_create", "no sm_100 CUDA device; the engine has no CPU fallback")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rbq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc, where):
+        if rc:
+            raise RbqError(rc, where, self._lib.rbq_last_error(self._h).decode(errors="replace"))
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.rbq_set_stream(self._h, C.c_void_p(cuda_stream)), "rbq_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._ck(self._lib.rbq_synchronize(self._h), "rbq_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rbq_launch_count(self._h))
+
+    def fp64_peak(self, iters: int = 20000) -> float:
+        out = C.c_double()
+        self._ck(self._lib.rbq_fp64_peak(self._h, int(iters), C.byref(out)), "rbq_fp64_peak")
+        return out.value
+
+    # ---- model API (RobotDynamics) -------------------------------------------------------------------
+    @staticmethod
+    def state_dim(p: ModelParams) -> int:
+        return _lib.load().rbq_state_dim(C.byref(p))
+
+    @staticmethod
+    def control_dim(p: ModelParams) -> int:
+        return _lib.load().rbq_control_dim(C.byref(p))
+
+    def _dims(self, p):
+        n, m = self.state_dim(p), self.control_dim(p)
+        if n < 0 or m < 0:
+            raise RbqError(_lib.E_MODEL, "model parameters")
+        return n, m
+
+    def discrete_dynamics(self, p, x, u, t, dt):
+        n, m = self._dims(p)
+        x, u = _f64(x), _f64(u)
+        if x.shape != (n,) or u.shape != (m,):
+            raise ValueError(f"expected x of length {n} and u of length {m}")
+        out = np.empty(n)
+        self._ck(self._lib.rbq_discrete_dynamics(self._h, C.byref(p), _ptr(x), _ptr(u), float(t), float(dt), _ptr(out)),
+                 "rbq_discrete_dynamics")
+        return out
+
+    def discrete_jacobian(self, p, x, u, t, dt):
+        """n x (n+m) matrix [A B] (the C side writes it column-major, like RD's ∇f)."""
+        n, m = self._dims(p)
+        x, u = _f64(x), _f64(u)
+        if x.shape != (n,) or u.shape != (m,):
+            raise ValueError(f"expected x of length {n} and u of length {m}")
+        ab = np.empty((n + m, n))
+        self._ck(self._lib.rbq_discrete_jacobian(self._h, C.byref(p), _ptr(x), _ptr(u), float(t), float(dt), _ptr(ab)),
+                 "rbq_discrete_jacobian")
+        return ab.T
+
+    def rollout(self, p, x0, U, dt):
+        """x0 (B,n)|(n,), U (B,N-1,m)|(N-1,m), dt (N-1,) -> X (B,N,n)|(N,n)."""
+        n, m = self._dims(p)
+        x0, U, dt = _f64(x0), _f64(U), _f64(dt)
+        single = x0.ndim == 1
+        x0b = x0.reshape(-1, n)
+        B = x0b.shape[0]
+        Ub = U.reshape(B, -1, m)
+        N = Ub.shape[1] + 1
+        if dt.shape != (N - 1,):
+            raise ValueError("dt must have N-1 entries")
+        X = np.empty((B, N, n))
+        self._ck(self._lib.rbq_rollout(self._h, C.byref(p), B, N, _ptr(x0b), _ptr(Ub), _ptr(dt), _ptr(X)), "rbq_rollout")
+        return X[0] if single else X
+
+    def rollout_closedloop(self, p, Xref, Uref, K, d, dt, alphas):
+        """K (N-1,m,n) gains (numpy row-major m x n per knot is converted to the column-major ABI layout)."""
+        n, m = self._dims(p)
+        Xref, Uref, d, dt, alphas = map(_f64, (Xref, Uref, d, dt, alphas))
+        N = Xref.shape[0]
+        Kc = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(N - 1, m, n).transpose(0, 2, 1))
+        na = alphas.shape[0]
+        X = np.empty((na, N, n))
+        Uo = np.empty((na, N - 1, m))
+        self._ck(self._lib.rbq_rollout_closedloop(self._h, C.byref(p), N, _ptr(Xref), _ptr(Uref), _ptr(Kc), _ptr(d), _ptr(dt),
+                                                  na, _ptr(alphas), _ptr(X), _ptr(Uo)), "rbq_rollout_closedloop")
+        return X, Uo
+
+    def jacobians(self, p, X, U, dt):
+        """X (K,n), U (K,m), dt (K,) -> (K, n, n+m)."""
+        n, m = self._dims(p)
+        X, U, dt = _f64(X).reshape(-1, n), _f64(U).reshape(-1, m), _f64(dt)
+        K = X.shape[0]
+        if U.shape[0] != K or dt.shape != (K,):
+            raise ValueError("X, U, dt disagree on the knot count")
+        ab = np.empty((K, n + m, n))
+        self._ck(self._lib.rbq_jacobians(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(dt), _ptr(ab)), "rbq_jacobians")
+        return ab.transpose(0, 2, 1)
+
+    def rollout_dev(self, p, B, N, x0, U, dt, X):
+        self._ck(self._lib.rbq_rollout_dev(self._h, C.byref(p), B, N, _ptr(x0), _ptr(U), _ptr(dt), _ptr(X)), "rbq_rollout_dev")
+
+    def jacobians_dev(self, p, K, X, U, dt, AB):
+        self._ck(self._lib.rbq_jacobians_dev(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(dt), _ptr(AB)), "rbq_jacobians_dev")
+
+    # ---- Monte-Carlo sweeps ------------------------------------------------------------------------------
+    def mc_static(self, controls, dt, gate, gate_count, fq, da, psi0, algo=_lib.ALGO_SU2, want_fid=True, want_stats=True,
+                  fid_out=None):
+        controls, fq, psi0 = _f64(controls), _f64(fq), _f64(psi0)
+        da = None if da is None else _f64(da)
+        S = fq.shape[0]
+        if psi0.shape != (S, 4) or (da is not None and da.shape != (S,)):
+            raise ValueError("fq (S,), da (S,), psi0 (S,4) expected")
+        fid = fid_out if fid_out is not None else (np.empty((S, gate_count + 1)) if want_fid else None)
+        st = Stats() if want_stats else None
+        self._ck(self._lib.rbq_mc_static(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate), int(gate_count), S,
+                                         _ptr(fq), _ptr(da), _ptr(psi0), int(algo), _ptr(fid),
+                                         C.byref(st) if st is not None else None), "rbq_mc_static")
+        return fid, st
+
+    def mc_static_philox(self, controls, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma,
+                         algo=_lib.ALGO_SU2, want_fid=False):
+        controls = _f64(controls)
+        fid = np.empty((S, gate_count + 1)) if want_fid else None
+        st = Stats()
+        self._ck(self._lib.rbq_mc_static_philox(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate),
+                                                int(gate_count), int(first), int(S), int(seed), float(fq0),
+                                                float(fq_rel_sigma), float(fq_rel_clip), float(da_sigma), int(algo),
+                                                _ptr(fid), C.byref(st)), "rbq_mc_static_philox")
+        return fid, st
+
+    def philox_samples(self, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma):
+        fq, da, psi0 = np.empty(S), np.empty(S), np.empty((S, 4))
+        self._ck(self._lib.rbq_philox_samples(self._h, int(first), int(S), int(seed), float(fq0), float(fq_rel_sigma),
+                                              float(fq_rel_clip), float(da_sigma), _ptr(fq), _ptr(da), _ptr(psi0)),
+                 "rbq_philox_samples")
+        return fq, da, psi0
+
+    def mc_noise(self, controls, dt, gate, gate_count, fq, noise, noise_dt_inv, psi0, algo=_lib.ALGO_SU2):
+        controls, noise, psi0 = _f64(controls), _f64(noise), _f64(psi0)
+        S, nlen = noise.shape
+        fid = np.empty((S, gate_count + 1))
+        st = Stats()
+        self._ck(self._lib.rbq_mc_noise(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate), int(gate_count), S,
+                                        float(fq), _ptr(noise), nlen, float(noise_dt_inv), _ptr(psi0), int(algo), _ptr(fid),
+                                        C.byref(st)), "rbq_mc_noise")
+        return fid, st
+
+    def mc_pink_philox(self, controls, dt, gate, gate_count, first, S, seed, fq, namp, noise_dt_inv, algo=_lib.ALGO_SU2,
+                       want_fid=True):
+        controls = _f64(controls)
+        fid = np.empty((S, gate_count + 1)) if want_fid else None
+        st = Stats()
+        self._ck(self._lib.rbq_mc_pink_philox(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate),
+                                              int(gate_count), int(first), int(S), int(seed), float(fq), float(namp),
+                                              float(noise_dt_inv), int(algo), _ptr(fid), C.byref(st)), "rbq_mc_pink_philox")
+        return fid, st
+
+    def pink_noise(self, first, S, seed, namp, noise_dt_inv, noise_len):
+        out = np.empty((S, noise_len))
+        self._ck(self._lib.rbq_pink_noise(self._h, int(first), int(S), int(seed), float(namp), float(noise_dt_inv),
+                                          int(noise_len), _ptr(out)), "rbq_pink_noise")
+        return out
+
+    def lindblad(self, controls, dt, gate, gate_count, fq, da, rho0, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0,
+                 t2_gamma_f=0.0):
+        """rho0 (S,2,2) complex -> fid (S,gate_count+1), rho_out (S,2,2), stats."""
+        controls = _f64(controls)
+        rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+        S = rho0.shape[0]
+        vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4))   # column-major vec(rho)
+        da = None if da is None else _f64(da)
+        fid = np.empty((S, gate_count + 1))
+        out = np.empty((S, 4), dtype=np.complex128)
+        st = Stats()
+        self._ck(self._lib.rbq_lindblad(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate), int(gate_count), S,
+                                        float(fq), _ptr(da), _ptr(vec), int(channels), float(t2_gamma_c), float(t2_gamma_f),
+                                        _ptr(fid), _ptr(out), C.byref(st)), "rbq_lindblad")
+        return fid, out.reshape(S, 2, 2).transpose(0, 2, 1).copy(), st
+
+    # ---- device-pointer forms (torch CUDA tensors; asynchronous on the handle's stream) ------------------------
+    def stats_reset_dev(self, d_stats):
+        self._ck(self._lib.rbq_stats_reset_dev(self._h, _ptr(d_stats)), "rbq_stats_reset_dev")
+
+    def mc_static_dev(self, d_controls, nknots, dt, gate, gate_count, S, d_fq, d_da, d_psi0, algo, d_fid, d_stats):
+        self._ck(self._lib.rbq_mc_static_dev(self._h, _ptr(d_controls), int(nknots), float(dt), int(gate), int(gate_count),
+                                             int(S), _ptr(d_fq), _ptr(d_da), _ptr(d_psi0), int(algo), _ptr(d_fid),
+                                             _ptr(d_stats)), "rbq_mc_static_dev")
+
+    def mc_static_philox_dev(self, d_controls, nknots, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip,
+                             da_sigma, algo, d_fid, d_stats):
+        self._ck(self._lib.rbq_mc_static_philox_dev(self._h, _ptr(d_controls), int(nknots), float(dt), int(gate),
+                                                    int(gate_count), int(first), int(S), int(seed), float(fq0),
+                                                    float(fq_rel_sigma), float(fq_rel_clip), float(da_sigma), int(algo),
+                                                    _ptr(d_fid), _ptr(d_stats)), "rbq_mc_static_philox_dev")
+
+    def mc_noise_dev(self, d_controls, nknots, dt, gate, gate_count, S, fq, d_noise, noise_len, noise_dt_inv, d_psi0, algo,
+                     d_fid, d_stats):
+        self._ck(self._lib.rbq_mc_noise_dev(self._h, _ptr(d_controls), int(nknots), float(dt), int(gate), int(gate_count),
+                                            int(S), float(fq), _ptr(d_noise), int(noise_len), float(noise_dt_inv),
+                                            _ptr(d_psi0), int(algo), _ptr(d_fid), _ptr(d_stats)), "rbq_mc_noise_dev")
+
+    def mc_pink_philox_dev(self, d_controls, nknots, dt, gate, gate_count, first, S, seed, fq, namp, noise_dt_inv, algo,
+                           d_fid, d_stats):
+        self._ck(self._lib.rbq_mc_pink_philox_dev(self._h, _ptr(d_controls), int(nknots), float(dt), int(gate),
+                                                  int(gate_count), int(first), int(S), int(seed), float(fq), float(namp),
+                                                  float(noise_dt_inv), int(algo), _ptr(d_fid), _ptr(d_stats)),
+                 "rbq_mc_pink_philox_dev")
+
+    def lindblad_dev(self, d_controls, nknots, dt, gate, gate_count, S, fq, d_da, d_rho0, channels, t2_gamma_c, t2_gamma_f,
+                     d_fid, d_rho_out, d_stats):
+        self._ck(self._lib.rbq_lindblad_dev(self._h, _ptr(d_controls), int(nknots), float(dt), int(gate), int(gate_count),
+                                            int(S), float(fq), _ptr(d_da), _ptr(d_rho0), int(channels), float(t2_gamma_c),
+                                            float(t2_gamma_f), _ptr(d_fid), _ptr(d_rho_out), _ptr(d_stats)),
+                 "rbq_lindblad_dev")
+
+
+STATS_INT64_WORDS = C.sizeof(Stats) // 8   # a device rbq_stats is a torch.int64 tensor of this many words
+
+
+def stats_from_words(words) -> Stats:
+    """Reinterpret STATS_INT64_WORDS int64 words (e.g. a torch tensor copied to the host) as Stats."""
+    buf = np.ascontiguousarray(np.asarray(words, dtype=np.int64))
+    st = Stats()
+    C.memmove(C.byref(st), buf.ctypes.data, C.sizeof(Stats))
+    return st
+
+
+def stats_merge(a: Stats, b: Stats) -> Stats:
+    _lib.load().rbq_stats_merge(C.byref(a), C.byref(b))
+    return a

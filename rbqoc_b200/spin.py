@@ -1,0 +1,383 @@
+"""Host-side mirror of the reference's spin-qubit interface for the propagation hot path.
+
+Same names, argument meaning and error behaviour as the Julia side, so that parity tests read like
+the reference's own scripts; everything numeric is forwarded to the CUDA engine (no CPU arithmetic
+beyond building inputs).  Citations are file:line in SchusterLab/rbqoc.
+
+  constants / operators        src/spin/spin.jl:122-345
+  Model, state_dim, ...        src/spin/spin13.jl:37-40, spin12.jl:52-56, spin30.jl:60-70, spin15.jl:40-46,
+                               spin11.jl:51-57, spin17.jl, spin18.jl:50-55
+  discrete_dynamics            RD.discrete_dynamics(::Type{RK3}, model, x, u, t, dt)  (spin13.jl:44-58 ...)
+  discrete_jacobian            RD.discrete_jacobian!(::Type{RK3}, ∇f, model, z) (RobotDynamics default: ForwardDiff)
+  run_sim_prop / evaluate_*    src/spin/spin.jl:1553-1672
+  analytic pulses              src/spin/spin14.py:60-241
+"""
+from __future__ import annotations
+
+import enum
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import ModelParams
+from .engine import Engine
+
+# ---- constants (spin.jl:122-173) --------------------------------------------------------------------
+HDIM = 2
+HDIM_ISO = 4
+FQ = 1.4e-2                       # GHz, spin.jl:148
+MAX_CONTROL_NORM_0 = 0.5          # spin.jl:156
+FBFQ_A = 0.202407
+FBFQ_B = 0.5
+AYPIBY2 = 1.25e-1
+FBFQ_NAMP = 5.21e-6               # spin.jl:163
+NAMP_PREFACTOR = FBFQ_NAMP / FBFQ_A   # spin.jl:164
+GAMMAC = 1 / 3e5                  # spin.jl:162
+DT_NOISE_INV = 1e1
+TTOT_ZPIBY2 = 17.857142857142858  # spin.jl:557
+
+
+class GateType(enum.IntEnum):     # spin.jl:29-34
+    zpiby2 = 1
+    ypiby2 = 2
+    xpiby2 = 3
+    xpi = 4
+
+
+class DynamicsType(enum.IntEnum):  # spin.jl:36-51 (the propagator-based members)
+    schroed = 1
+    schroedda = 2
+    lindbladt1 = 3
+    lindbladt2 = 4
+
+
+class RK3:                        # integrator tag the reference always dispatches on (rbqoc.jl:49-54)
+    pass
+
+
+# real isomorphism helpers (rbqoc.jl:189-210)
+def get_vec_iso(v):
+    v = np.asarray(v, dtype=np.complex128)
+    return np.concatenate([v.real, v.imag])
+
+
+def get_vec_uniso(v):
+    v = np.asarray(v, dtype=np.float64)
+    h = v.shape[0] // 2
+    return v[:h] + 1j * v[h:]
+
+
+def get_mat_iso(m):
+    m = np.asarray(m, dtype=np.complex128)
+    return np.block([[m.real, -m.imag], [m.imag, m.real]])
+
+
+SIGMAX = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+SIGMAZ = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+NEGI_H0_ISO = math.pi * get_mat_iso(-1j * SIGMAZ)     # spin.jl:234
+NEGI_H1_ISO = math.pi * get_mat_iso(-1j * SIGMAX)     # spin.jl:236
+_R2 = 1 / math.sqrt(2)
+GATES = {                                              # spin.jl:301-312
+    GateType.zpiby2: np.array([[1 - 1j, 0], [0, 1 + 1j]]) * _R2,
+    GateType.ypiby2: np.array([[1, -1], [1, 1]], dtype=np.complex128) * _R2,
+    GateType.xpiby2: np.array([[1, -1j], [-1j, 1]]) * _R2,
+    GateType.xpi: np.array([[0, -1j], [-1j, 0]]),
+}
+IS1_ISO = np.array([1.0, 0, 0, 0])                     # spin.jl:325-332
+IS2_ISO = np.array([0.0, 1, 0, 0])
+IS3_ISO = np.array([1.0, 0, 0, 1]) * _R2
+IS4_ISO = np.array([1.0, -1, 0, 0]) * _R2
+
+
+# ---- models ---------------------------------------------------------------------------------------------
+@dataclass
+class Model:
+    """One of the reference's `Model <: RD.AbstractModel` structs, flattened to `rbq_model_params`."""
+
+    params: ModelParams
+    name: str = ""
+
+    @property
+    def n(self) -> int:
+        return state_dim(self)
+
+    @property
+    def m(self) -> int:
+        return control_dim(self)
+
+
+def _params(**kw) -> ModelParams:
+    p = ModelParams()
+    p.fq = FQ
+    p.alpha = 1.0
+    for k, v in kw.items():
+        if k in ("nominal_offset", "fq_samples", "S_diag"):
+            arr = getattr(p, k)
+            for i, x in enumerate(v):
+                arr[i] = x
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def Spin13Model(fq=FQ) -> Model:
+    return Model(_params(model_id=_lib.MODEL_SPIN13, fq=fq), "spin13")
+
+
+def Spin12Model(fq_cov=FQ * 1e-2, fq=FQ) -> Model:
+    """spin12.jl:204-205: h0_samples = (FQ + fq_cov, FQ - fq_cov) (fq_cov used as a deviation)."""
+    return Model(_params(model_id=_lib.MODEL_SPIN12, fq=fq, fq_samples=(fq + fq_cov, fq - fq_cov)), "spin12")
+
+
+def Spin18Model(namp=NAMP_PREFACTOR, fq=FQ) -> Model:
+    return Model(_params(model_id=_lib.MODEL_SPIN18, fq=fq, namp=namp), "spin18")
+
+
+def Spin15Model(DA=False, TO=False, fq=FQ) -> Model:
+    return Model(_params(model_id=_lib.MODEL_SPIN15, fq=fq, decay_aware=int(DA), time_optimal=int(TO)), "spin15")
+
+
+def Spin11Model(DO=0, fq=FQ) -> Model:
+    return Model(_params(model_id=_lib.MODEL_SPIN11, fq=fq, derivative_order=int(DO)), "spin11")
+
+
+def Spin17Model(DO=0, fq=FQ) -> Model:
+    return Model(_params(model_id=_lib.MODEL_SPIN17, fq=fq, derivative_order=int(DO)), "spin17")
+
+
+def Spin30Model(S_diag=(1.0, 1.0, 1.0, 1.0), nominal_idxs=None, fq_cov=FQ * 1e-2, alpha=1.0, sample_state_count=1,
+                fq=FQ) -> Model:
+    """spin30.jl:60-66.  nominal_idxs: 1-based first index of each sample state's nominal block
+    (default STATE1_IDX for every sample state, as run_traj builds it at spin30.jl:216-217)."""
+    if nominal_idxs is None:
+        nominal_idxs = [1] * sample_state_count
+    if len(nominal_idxs) != sample_state_count:
+        raise ValueError("one nominal index block per sample state")
+    return Model(_params(model_id=_lib.MODEL_SPIN30, fq=fq, fq_cov=fq_cov, alpha=alpha,
+                         sample_state_count=int(sample_state_count), S_diag=tuple(S_diag),
+                         nominal_offset=tuple(int(i) - 1 for i in nominal_idxs)), "spin30")
+
+
+def state_dim(model: Model) -> int:
+    n = Engine.state_dim(model.params)
+    if n < 0:
+        raise ValueError("inconsistent model parameters")
+    return n
+
+
+def control_dim(model: Model) -> int:
+    m = Engine.control_dim(model.params)
+    if m < 0:
+        raise ValueError("inconsistent model parameters")
+    return m
+
+
+@dataclass
+class KnotPoint:
+    """RobotDynamics.AbstractKnotPoint: z = [x; u], t, dt."""
+
+    x: np.ndarray
+    u: np.ndarray
+    dt: float
+    t: float = 0.0
+
+
+_default_engine = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def discrete_dynamics(_rk, model: Model, x, u=None, t=0.0, dt=None, engine: Engine | None = None):
+    """RD.discrete_dynamics(::Type{RK3}, model, x, u, t, dt) or (…, model, z::KnotPoint)."""
+    eng = engine or default_engine()
+    if isinstance(x, KnotPoint):
+        z = x
+        return eng.discrete_dynamics(model.params, z.x, z.u, z.t, z.dt)
+    return eng.discrete_dynamics(model.params, x, u, t, dt)
+
+
+def discrete_jacobian(_rk, model: Model, z: KnotPoint, engine: Engine | None = None):
+    """RD.discrete_jacobian!(::Type{RK3}, ∇f, model, z): returns ∇f = [A B], n x (n+m)."""
+    eng = engine or default_engine()
+    return eng.discrete_jacobian(model.params, z.x, z.u, z.t, z.dt)
+
+
+def rollout(model: Model, x0, U, dt, engine: Engine | None = None):
+    """TO.rollout!: X[0]=x0, X[k+1] = discrete_dynamics(RK3, model, X[k], U[k], t, dt[k])."""
+    U = np.asarray(U, dtype=np.float64)
+    dts = np.full(U.shape[-2], float(dt)) if np.isscalar(dt) else dt
+    return (engine or default_engine()).rollout(model.params, x0, U, dts)
+
+
+def dynamics_expansion(model: Model, X, U, dt, engine: Engine | None = None):
+    """TO.dynamics_expansion!: ∇f_k for k = 1..N-1 in one call.  X (N,n) or (N-1,n); U (N-1,m)."""
+    X, U = np.asarray(X, dtype=np.float64), np.asarray(U, dtype=np.float64)
+    K = U.shape[0]
+    dts = np.full(K, float(dt)) if np.isscalar(dt) else dt
+    return (engine or default_engine()).jacobians(model.params, X[:K], U, dts)
+
+
+# initial augmented states the reference's run_traj builds
+def spin13_x0():
+    return np.concatenate([IS1_ISO, IS2_ISO, np.zeros(3)])                       # spin13.jl:78-84
+
+
+def spin12_x0():
+    return np.concatenate([IS1_ISO, IS2_ISO, np.zeros(3)] + [IS1_ISO, IS2_ISO, IS3_ISO, IS4_ISO] * 2)   # spin12.jl:213-218
+
+
+def spin30_x0(state_cov=1e-2, rng=None):
+    """spin30.jl:222-239: nominal IS1..IS3 + zeros(3) + 10 sigma points around IS1 + penalty slot."""
+    rng = rng or np.random.default_rng(0)
+    pts = []
+    for _ in range(10):
+        s = IS1_ISO + math.sqrt(state_cov) * rng.standard_normal(4)
+        pts.append(s / np.linalg.norm(s))
+    return np.concatenate([IS1_ISO, IS2_ISO, IS3_ISO, np.zeros(3)] + pts + [np.zeros(1)])
+
+
+# ---- analytic pulses (spin14.py:60-241), sampled at DT = 1/dt_inv ------------------------------------------
+T_XZ_YPIBY2 = 2.1656249366575766
+T_Z_YPIBY2 = 15.142330599557274
+TTOT_YPIBY2 = 2 * T_XZ_YPIBY2 + T_Z_YPIBY2
+TTOT_XPIBY2 = 2 * TTOT_YPIBY2 + TTOT_ZPIBY2
+
+
+def gen_controls_ypiby2(t):
+    if t <= T_XZ_YPIBY2:
+        return AYPIBY2
+    if t <= T_XZ_YPIBY2 + T_Z_YPIBY2:
+        return 0.0
+    return -AYPIBY2
+
+
+def gen_controls_xpiby2(t):
+    if t <= TTOT_YPIBY2:
+        return -gen_controls_ypiby2(t)
+    if t <= TTOT_YPIBY2 + TTOT_ZPIBY2:
+        return 0.0
+    return gen_controls_ypiby2(t - (TTOT_YPIBY2 + TTOT_ZPIBY2))
+
+
+def _sampled(gen, evolution_time, dt_inv):
+    count = int(math.floor(evolution_time * dt_inv))
+    ts = np.arange(count) / dt_inv
+    c = np.array([gen(t) for t in ts])
+    c[0] = 0.0
+    c[-1] = 0.0                                                                   # spin14.py:121-122
+    return c
+
+
+def controls_ypiby2(dt_inv=100.0):
+    return _sampled(gen_controls_ypiby2, TTOT_YPIBY2, dt_inv)
+
+
+def controls_xpiby2(dt_inv=100.0):
+    return _sampled(gen_controls_xpiby2, TTOT_XPIBY2, dt_inv)
+
+
+def controls_zpiby2(dt_inv=100.0):
+    return np.zeros(int(math.floor(TTOT_ZPIBY2 * dt_inv)))
+
+
+def pulse_sin(N):
+    """Synthetic benchmark pulse P_sin(N) of SURVEY §8(d): a_k on N knots, a_0 = a_{N-1} = 0."""
+    k = np.arange(N)
+    return 0.30 * np.sin(2 * np.pi * k / (N - 1)) + 0.10 * np.sin(6 * np.pi * k / (N - 1))
+
+
+# ---- sample generation (spin.jl:1119-1166) ---------------------------------------------------------------------
+_FIXED_STATES = {-1: [1, 0], -2: [0, 1], -3: [_R2, 1j * _R2], -4: [_R2, -_R2], -5: [_R2, _R2]}
+
+
+def gen_rand_state_iso(seed=0, engine: Engine | None = None):
+    """Seeds -1..-5 are the reference's fixed states.  For seed >= 0 the reference seeds Julia's
+    MersenneTwister, which no other runtime reproduces; here seed k is sample index k of the engine's
+    Philox stream (key 0), drawn with the same recipe `rand(2) + im*rand(2)`, normalised."""
+    if seed in _FIXED_STATES:
+        return get_vec_iso(_FIXED_STATES[seed])
+    if seed < 0:
+        raise ValueError("unknown fixed state seed")
+    _, _, psi0 = (engine or default_engine()).philox_samples(seed, 1, 0, FQ, 0.0, 0.0, 0.0)
+    return psi0[0]
+
+
+def gen_rand_density(seed=0, engine: Engine | None = None):
+    psi = get_vec_uniso(gen_rand_state_iso(seed, engine))
+    return np.outer(psi, psi.conj())
+
+
+# ---- simulation entry points (spin.jl:1553-1672), batched over samples -------------------------------------------
+@dataclass
+class SimResult:
+    fidelities: np.ndarray
+    stats: object = None
+    extra: dict = field(default_factory=dict)
+
+
+def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=NAMP_PREFACTOR, noise_dt_inv=DT_NOISE_INV,
+                 seed=0, state_seed=None, dynamics_type=DynamicsType.schroed, noise=None, engine: Engine | None = None,
+                 algo=_lib.ALGO_SU2):
+    """run_sim_prop for one (seed, state_seed) like the reference, or for arrays of them (batched).
+
+    `controls`/`dt_inv` replace `save_file_path` (what grab_controls returns, rbqoc.jl:98-123);
+    `fq` replaces `negi_h0 = fq * NEGI_H0_ISO`.  Returns a dict with "fidelities" of shape
+    (gate_count+1,) for scalar seeds or (S, gate_count+1) for array seeds."""
+    eng = engine or default_engine()
+    gate_type = GateType(gate_type)
+    dynamics_type = DynamicsType(dynamics_type)
+    scalar = np.isscalar(seed)
+    seeds = np.atleast_1d(np.asarray(seed, dtype=np.int64))
+    sseeds = seeds if state_seed is None else np.broadcast_to(np.atleast_1d(np.asarray(state_seed, dtype=np.int64)), seeds.shape)
+    S = seeds.shape[0]
+    controls = np.ascontiguousarray(controls, dtype=np.float64).reshape(-1)
+    dt = 1.0 / dt_inv
+    fqs = np.broadcast_to(np.asarray(fq, dtype=np.float64), (S,)).copy()
+    psi0 = np.stack([gen_rand_state_iso(int(s), eng) for s in sseeds])
+    if dynamics_type == DynamicsType.schroed:
+        das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
+        fid, st = eng.mc_static(controls, dt, gate_type, gate_count, fqs, das, psi0, algo=algo)
+    elif dynamics_type == DynamicsType.schroedda:
+        nlen = int(math.ceil(controls.shape[0] * dt * gate_count * noise_dt_inv)) + 1     # spin.jl:1569
+        if noise is None:
+            noise = np.concatenate([eng.pink_noise(int(s), 1, 0, namp, noise_dt_inv, nlen) for s in seeds])
+        if not np.all(fqs == fqs[0]):
+            raise ValueError("schroedda sweeps share one fq")
+        fid, st = eng.mc_noise(controls, dt, gate_type, gate_count, float(fqs[0]), noise, noise_dt_inv, psi0, algo=algo)
+    elif dynamics_type in (DynamicsType.lindbladt1, DynamicsType.lindbladt2):
+        rho0 = np.stack([np.outer(get_vec_uniso(p), get_vec_uniso(p).conj()) for p in psi0])
+        das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
+        ch = _lib.LINDBLAD_T1 if dynamics_type == DynamicsType.lindbladt1 else _lib.LINDBLAD_T2
+        fid, rho, st = eng.lindblad(controls, dt, gate_type, gate_count, float(fqs[0]), das, rho0, channels=ch,
+                                    t2_gamma_c=GAMMAC if ch == _lib.LINDBLAD_T2 else 0.0)
+    else:
+        raise ValueError("unsupported dynamics type")
+    return {
+        "gate_count": gate_count, "gate_type": int(gate_type), "seed": seed, "state_seed": state_seed,
+        "fidelities": fid[0] if scalar else fid, "stats": st, "namp": namp, "noise_dt_inv": noise_dt_inv,
+    }
+
+
+def evaluate_fqdev(controls, dt_inv, fq_cov=FQ * 1e-2, trial_count=1000, gate_type=GateType.zpiby2,
+                   engine: Engine | None = None):
+    """spin.jl:1611-1656 in two batched calls instead of 2*(trial_count+4) serial ones."""
+    seeds = np.repeat(np.arange(trial_count), 2)
+    fqs = np.tile([FQ + fq_cov, FQ - fq_cov], trial_count)
+    res = run_sim_prop(1, gate_type, controls, dt_inv, fq=fqs, seed=seeds, engine=engine)
+    bseeds = np.repeat(np.arange(-4, 0), 2)
+    bres = run_sim_prop(1, gate_type, controls, dt_inv, fq=np.tile([FQ + fq_cov, FQ - fq_cov], 4), seed=bseeds, engine=engine)
+    return {"gate_errors": 1 - res["fidelities"][:, -1], "gate_errors_basis": 1 - bres["fidelities"][:, -1]}
+
+
+def evaluate_adev(controls, dt_inv, gate_count=100, gate_type=GateType.xpiby2, trial_count=100, engine: Engine | None = None):
+    """spin.jl:1659-1672."""
+    res = run_sim_prop(gate_count, gate_type, controls, dt_inv, seed=np.arange(1, trial_count + 1),
+                       dynamics_type=DynamicsType.schroedda, engine=engine)
+    return {"gate_errors": 1 - res["fidelities"][:, -1]}

@@ -1,0 +1,178 @@
+"""GPU parity: augmented-state step maps, rollouts and knot-point Jacobians vs the CPU oracle.
+
+Tolerances are the north star's: relative 1e-12 on states, 1e-10 on Jacobians (scaled by the largest
+entry of the block).  Every call goes through the C ABI (librbq.so) via rbqoc_b200.Engine.
+"""
+import numpy as np
+import pytest
+
+from rbqoc_b200 import spin
+
+pytestmark = pytest.mark.gpu
+
+STATE_RTOL = 1e-12
+JAC_RTOL = 1e-10
+
+
+def _models():
+    return [
+        ("spin13", spin.Spin13Model()),
+        ("spin12", spin.Spin12Model()),
+        ("spin18", spin.Spin18Model()),
+        ("spin15", spin.Spin15Model(False, False)),
+        ("spin15_DA", spin.Spin15Model(True, False)),
+        ("spin15_TO", spin.Spin15Model(False, True)),
+        ("spin15_DA_TO", spin.Spin15Model(True, True)),
+        ("spin11_DO0", spin.Spin11Model(0)),
+        ("spin11_DO1", spin.Spin11Model(1)),
+        ("spin11_DO2", spin.Spin11Model(2)),
+        ("spin17_DO1", spin.Spin17Model(1)),
+        ("spin17_DO2", spin.Spin17Model(2)),
+        ("spin30", spin.Spin30Model(S_diag=(1.0, 2.0, 3.0, 4.0))),
+        ("spin30_x2", spin.Spin30Model(sample_state_count=2, nominal_idxs=[1, 5], alpha=1.3)),
+    ]
+
+
+MODELS = _models()
+IDS = [m[0] for m in MODELS]
+
+
+def _random_point(model, rng, a=None):
+    """A generic augmented state: unit-ish psi blocks, a in the control range, spin30 sigma points spread."""
+    n, m = model.n, model.m
+    x = rng.standard_normal(n) * 0.3
+    mid = model.params.model_id
+    if mid == 30:
+        x[:12] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO, spin.IS3_ISO]) + 1e-3 * rng.standard_normal(12)
+        x[12:15] = rng.uniform(-0.4, 0.4, 3)
+        for c in range(model.params.sample_state_count):
+            off = 15 + 41 * c
+            for j in range(10):
+                s = spin.IS1_ISO + 0.1 * rng.standard_normal(4)
+                x[off + 4 * j: off + 4 * j + 4] = s / np.linalg.norm(s)
+            x[off + 40] = rng.uniform(0, 1e-2)
+        if a is not None:
+            x[13] = a
+    else:
+        x[8:11] = rng.uniform(-0.4, 0.4, 3)
+        if a is not None:
+            x[9] = a
+    u = rng.uniform(-0.2, 0.2, m)
+    if mid == 15 and model.params.time_optimal:
+        u[1] = rng.uniform(0.2, 0.4)     # dt = u2^2 in [0.04, 0.16]
+    return x, u
+
+
+def _seed(name, k=0):
+    import zlib
+
+    return (zlib.crc32(name.encode()) + k) % 2**32
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+def test_state_and_control_dims(engine, oracle, name, model):
+    assert model.n == oracle.state_dim(model.params)
+    assert model.m == oracle.control_dim(model.params)
+
+
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+@pytest.mark.parametrize("dt", [0.1, 0.01])
+def test_discrete_dynamics_matches_oracle(engine, oracle, name, model, dt):
+    rng = np.random.default_rng(_seed(name))
+    for a in (None, 0.0, 0.5, -0.37, 1e-9):
+        x, u = _random_point(model, rng, a)
+        got = spin.discrete_dynamics(spin.RK3, model, x, u, 0.0, dt, engine=engine)
+        ref = oracle.step(model.params, x, u, dt)
+        assert got.shape == ref.shape
+        assert _relerr(got, ref) < STATE_RTOL, (name, a)
+
+
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+@pytest.mark.parametrize("dt", [0.1, 0.01])
+def test_discrete_jacobian_matches_oracle_forward_mode(engine, oracle, name, model, dt):
+    rng = np.random.default_rng(_seed(name, 7))
+    for a in (None, 0.0, 0.5, -0.37, -0.0):
+        x, u = _random_point(model, rng, a)
+        z = spin.KnotPoint(x, u, dt)
+        got = spin.discrete_jacobian(spin.RK3, model, z, engine=engine)
+        ref = oracle.jacobian(model.params, x, u, dt)
+        assert got.shape == (model.n, model.n + model.m)
+        assert _relerr(got, ref) < JAC_RTOL, (name, a)
+
+
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+def test_rollout_and_batched_jacobians(engine, oracle, name, model):
+    rng = np.random.default_rng(_seed(name, 11))
+    N = 301
+    dt = np.full(N - 1, 0.1)
+    B = 3
+    x0 = np.stack([_random_point(model, rng)[0] for _ in range(B)])
+    if model.params.model_id != 30:
+        x0[:, 0:8] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO])
+        x0[:, 8:11] = 0.0
+    else:
+        x0[:, 12:15] = 0.0
+    U = rng.uniform(-2e-3, 2e-3, (B, N - 1, model.m))
+    if model.params.model_id == 15 and model.params.time_optimal:
+        U[:, :, 1] = rng.uniform(0.25, 0.35, (B, N - 1))
+    X = engine.rollout(model.params, x0, U, dt)
+    Xr = oracle.rollout(model.params, x0, U, dt)
+    assert X.shape == (B, N, model.n)
+    assert _relerr(X, Xr) < 5e-12, name    # 300 chained steps
+    # all knots of trajectory 0 in one Jacobian call
+    AB = engine.jacobians(model.params, Xr[0, :-1], U[0], dt)
+    ABr = oracle.jacobians(model.params, Xr[0, :-1], U[0], dt)
+    assert AB.shape == (N - 1, model.n, model.n + model.m)
+    scale = np.max(np.abs(ABr), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(AB - ABr) / scale) < JAC_RTOL, name
+
+
+def test_closed_loop_rollout(engine, oracle):
+    model = spin.Spin12Model()
+    rng = np.random.default_rng(5)
+    N = 181
+    dt = np.full(N - 1, 0.1)
+    Uref = rng.uniform(-2e-3, 2e-3, (N - 1, 1))
+    Xref = oracle.rollout(model.params, spin.spin12_x0(), Uref, dt)
+    K = 1e-2 * rng.standard_normal((N - 1, model.m, model.n))
+    d = 1e-3 * rng.standard_normal((N - 1, model.m))
+    alphas = np.array([1.0, 0.5, 0.25, 0.125, 0.0])
+    X, Uo = engine.rollout_closedloop(model.params, Xref, Uref, K, d, dt, alphas)
+    Kc = np.ascontiguousarray(K.transpose(0, 2, 1))
+    Xr, Ur = oracle.rollout_closedloop(model.params, Xref, Uref, Kc, d, dt, alphas)
+    assert _relerr(X, Xr) < 5e-12
+    assert _relerr(Uo, Ur) < 5e-12
+    assert _relerr(X[-1], Xref) < 1e-13      # alpha = 0 reproduces the reference trajectory
+
+
+def test_jacobian_structure_spin13(engine):
+    """A = blkdiag(E, E, chain) + the d/da column; B = dt e_11."""
+    model = spin.Spin13Model()
+    x = np.concatenate([spin.IS3_ISO, spin.IS4_ISO, [0.1, 0.3, -0.2]])
+    AB = engine.discrete_jacobian(model.params, x, np.array([0.05]), 0.0, 0.1)
+    A, B = AB[:, :11], AB[:, 11]
+    assert np.allclose(A[0:4, 0:4], A[4:8, 4:8], atol=0, rtol=0)
+    assert np.allclose(A[0:4, 0:4] @ A[0:4, 0:4].T, np.eye(4), atol=1e-15)
+    assert np.all(A[0:4, 4:9] == 0) and np.all(A[8:11, 0:8] == 0)
+    assert np.allclose(A[8:11, 8:11], [[1, 0.1, 0], [0, 1, 0.1], [0, 0, 1]], atol=0)
+    assert np.allclose(B, np.r_[np.zeros(10), 0.1], atol=0)
+
+
+def test_error_codes(engine):
+    import rbqoc_b200
+
+    bad = spin.Spin11Model(5)
+    with pytest.raises(ValueError):
+        bad.n
+    p = spin.Spin13Model().params
+    with pytest.raises(ValueError):
+        engine.discrete_dynamics(p, np.zeros(5), np.zeros(1), 0.0, 0.1)
+    # NaN inputs are returned, not hidden (iLQR relies on seeing them)
+    x = np.full(11, np.nan)
+    out = engine.discrete_dynamics(p, x, np.zeros(1), 0.0, 0.1)
+    assert np.all(np.isnan(out[:10]))
+    assert isinstance(rbqoc_b200.RbqError(-1, "x"), RuntimeError)
