@@ -32,10 +32,10 @@ DT = 0.1
 S_PER_GPU = 1 << 20
 GATE_COUNT = 1
 # flops the SU(2) kernel executes per trajectory-step on this grid (series degree K=5, 2 samples/thread):
-#   0.5 DMUL (w*a_j shared by 2 samples) + 1 DADD + 1 DFMA (x) + 10 DFMA (cos, sinc) + 2 DMUL (s*p, s*q)
-#   + 4 DMUL + 8 DFMA (E psi)   = 26.5 FP64 instructions = 45.5 flop (FMA = 2)       [DESIGN.md §kernels]
-FLOPS_PER_STEP_SU2 = 45.5
-FP64_INSTR_PER_STEP_SU2 = 26.5
+#   0.5 DMUL (w*a_j shared by 2 samples) + 1 DFMA (q) + 1 DFMA (x) + 10 DFMA (cos, sinc) + 2 DMUL (s*p, s*q)
+#   + 4 DMUL + 8 DFMA (E psi)   ~ 26.25 FP64 instructions = 46.25 flop (FMA = 2)     [DESIGN.md §kernels]
+FLOPS_PER_STEP_SU2 = 46.25      # counted in the SASS of the K=5 loop: (160 DFMA*2 + 50 DMUL) / 8 sample-steps
+FP64_INSTR_PER_STEP_SU2 = 26.25
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 
 
@@ -129,7 +129,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=S_PER_GPU, help="samples per GPU per step")
@@ -195,14 +195,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident, CUDA events on the launching stream, L2 flushed between steps ----
+    stop, rows = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, rows), daemon=True)
+    th.start()
     for _ in range(args.warmup):
         with torch.cuda.stream(stream):
             flush.zero_()
         device_step()
     barrier()
-    stop, rows = threading.Event(), []
-    th = threading.Thread(target=sample_clocks, args=(stop, rows), daemon=True)
-    th.start()
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
@@ -227,9 +227,9 @@ def main():
         with torch.cuda.stream(stream):
             b.record(stream)
     barrier()
-    stop.set()
-    th.join(timeout=2)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    eng.stats_reset_dev(d_stats)      # leave the statistics of exactly one pass in d_stats
+    eng.mc_static_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_stats)
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
     fid_np = fid_p.numpy()
@@ -243,6 +243,8 @@ def main():
                                   fid_out=fid_np)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    stop.set()
+    th.join(timeout=2)
 
     # ---- reduce over ranks (max time), print on rank 0 ----
     times = torch.tensor([dev_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
@@ -273,6 +275,7 @@ def main():
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_tflops if peak_tflops else None, "traffic": None,
+                         "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,
                          "kernel_ms": kern_ms,

@@ -8,6 +8,8 @@
 // (cp.async.bulk + mbarrier, double buffered); all threads of a block walk the pulse in lock step.
 // sm_100a only.
 #include "rbq_internal.h"
+#include <stdlib.h>
+
 #include "rbq_math.cuh"
 
 namespace rbq {
@@ -246,8 +248,8 @@ RBQ_DEV double gate_train(const double* E, const double* psi0, const GateIso& G,
 }
 
 // ---- static-parameter sweep -------------------------------------------------------------------------------
-template <int ALGO, int SPT>
-__global__ void __launch_bounds__(MC_THREADS) mc_static_kernel(const McStaticArgs a) {
+template <int ALGO, int SPT, int MINB>
+__global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McStaticArgs a) {
     __shared__ __align__(128) double tile_s[2 * MC_TILE];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
@@ -301,8 +303,15 @@ __global__ void __launch_bounds__(MC_THREADS) mc_static_kernel(const McStaticArg
             else su2_tile<0, SPT>(tile, len, w, p, p2, qd, v);
             pipe.release();
         }
+        // the exact product is a unit quaternion: dividing out |v| removes the radial rounding error, which
+        // for piecewise-constant pulses accumulates coherently (the same (cos, sinc) rounding at every knot)
 #pragma unroll
-        for (int i = 0; i < SPT; ++i) iso_from_column(v[i], E[i]);
+        for (int i = 0; i < SPT; ++i) {
+            const double inv = 1.0 / sqrt(fma(v[i][3], v[i][3], fma(v[i][2], v[i][2], fma(v[i][1], v[i][1], v[i][0] * v[i][0]))));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[i][c] *= inv;
+            iso_from_column(v[i], E[i]);
+        }
     } else {
         // reference algorithm (spin.jl:443-447): prop = exp((H0' + a_j H1) dt) * prop with the generic Pade exp
 #pragma unroll
@@ -430,6 +439,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
     double* frow = (a.fid && live) ? a.fid + s * (a.gate_count + 1) : nullptr;
     double f = fidelity_vec_iso2(st, tg[0]);
     if (frow) frow[0] = f;
+    const double norm0 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
     double time = 0.0, qd = 0.0;
     int64_t cur = -1;
     for (int64_t g = 1; g <= a.gate_count; ++g) {
@@ -453,6 +463,12 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
                 }
             }
             pipe.release();
+        }
+        if (ALGO == RBQ_ALGO_SU2) {   // unitary evolution preserves the norm; shed the accumulated radial rounding
+            const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+            const double sc = sqrt(norm0 / n2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st[i] *= sc;
         }
         const int k = (int)(g & 3);
         f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
@@ -652,13 +668,22 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double* __res
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------------------------
-static inline int static_spt(int64_t S, int sm_count, int algo) {
-    if (algo != RBQ_ALGO_SU2) return 1;
-    // two samples per thread once every SM can still be given >= 8 blocks
-    return S >= (int64_t)sm_count * 8 * MC_THREADS * 2 ? 2 : 1;
+// (samples per thread, min resident blocks per SM) of the closed-form kernel; RBQ_MC_VARIANT=<spt><minb>
+// overrides the default for tuning runs
+static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, int* minb) {
+    *spt = 1; *minb = 1;
+    if (algo != RBQ_ALGO_SU2) return;
+    int v = 23;
+    if (const char* e = getenv("RBQ_MC_VARIANT")) v = atoi(e);
+    *spt = v / 10; *minb = v % 10;
+    if (!((*spt == 1 || *spt == 2 || *spt == 4) && *minb >= 1 && *minb <= 4)) { *spt = 2; *minb = 3; }
+    // small sweeps: one sample per thread so that every SM gets blocks
+    if (S < (int64_t)sm_count * 4 * MC_THREADS * *spt) *spt = 1;
 }
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
-    const int per = MC_THREADS * static_spt(S, h->sm_count, algo);
+    int spt, minb;
+    static_variant(S, h->sm_count, algo, &spt, &minb);
+    const int per = MC_THREADS * spt;
     return (int)((S + per - 1) / per);
 }
 int mc_noise_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
@@ -672,15 +697,22 @@ int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, doubl
     return (int)cudaGetLastError();
 }
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
-    const int spt = static_spt(a.S, h->sm_count, algo);
+    int spt, minb;
+    static_variant(a.S, h->sm_count, algo, &spt, &minb);
     const int blocks = mc_static_blocks(h, a.S, algo);
     if (nblocks_out) *nblocks_out = blocks;
+#define RBQ_GO(SPT_, MINB_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_><<<blocks, MC_THREADS, 0, h->stream>>>(a)
     if (algo == RBQ_ALGO_SU2) {
-        if (spt == 2) mc_static_kernel<RBQ_ALGO_SU2, 2><<<blocks, MC_THREADS, 0, h->stream>>>(a);
-        else mc_static_kernel<RBQ_ALGO_SU2, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+        switch (spt * 10 + minb) {
+        case 11: RBQ_GO(1, 1); break; case 12: RBQ_GO(1, 2); break; case 13: RBQ_GO(1, 3); break; case 14: RBQ_GO(1, 4); break;
+        case 21: RBQ_GO(2, 1); break; case 22: RBQ_GO(2, 2); break; case 23: RBQ_GO(2, 3); break; case 24: RBQ_GO(2, 4); break;
+        case 41: RBQ_GO(4, 1); break; case 42: RBQ_GO(4, 2); break;
+        default: RBQ_GO(2, 3); break;
+        }
     } else if (algo == RBQ_ALGO_PADE) {
-        mc_static_kernel<RBQ_ALGO_PADE, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+        mc_static_kernel<RBQ_ALGO_PADE, 1, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
     } else return RBQ_E_ALGO;
+#undef RBQ_GO
     h->launches++;
     return (int)cudaGetLastError();
 }
