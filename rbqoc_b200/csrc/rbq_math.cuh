@@ -338,7 +338,7 @@ RBQ_DEV void mv4(const double* E, double* psi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10; stream layout documented in include/rbq.h and oracle/oracle.cpp
+// Philox4x32-10; stream layout (counter = index_lo, index_hi, j, stream; key = seed) as documented in include/rbq.h
 // ---------------------------------------------------------------------------------------------
 RBQ_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
 #pragma unroll

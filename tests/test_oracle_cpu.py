@@ -1,0 +1,161 @@
+"""CPU suite, part 1: the oracle itself.
+
+The reference has no tests, fixtures or stored pulses and cannot run here (Julia), so the oracle is
+"parity unpinned" against reference OUTPUTS.  It is pinned instead against
+  (a) the known answers embedded in the reference (analytic gates, spin.jl:557,608-612; D1 table;
+      1 % detuning gate error),
+  (b) golden vectors from a 50-digit restatement of the same mathematics (tests/golden/make_golden.py),
+  (c) scipy's expm,
+  (d) pulses produced by the reference's own spin14.py generator functions.
+"""
+import numpy as np
+import pytest
+import scipy.linalg
+import scipy.signal
+
+from _cases import GOLDEN, MODEL_KW, golden_model_cases, relerr
+
+FQ = 1.4e-2
+
+
+@pytest.fixture(scope="module")
+def orc(oracle):
+    return oracle
+
+
+def test_expm_matches_scipy_and_picks_reference_branches(orc):
+    rng = np.random.default_rng(0)
+    H0, H1 = np.pi * np.array(orc_N0()), np.pi * np.array(orc_N1())
+    seen = set()
+    for dt, a in [(0.01, 0.0), (0.01, 0.49), (0.1, 0.02), (0.1, 0.5), (0.5, 0.3), (1.0, 0.3), (2.0, 0.5), (5.0, 0.5), (40.0, 0.5)]:
+        G = dt * (FQ * H0 + a * H1)
+        E, deg = orc.expm4(G)
+        seen.add(deg)
+        assert np.max(np.abs(E - scipy.linalg.expm(G))) < 5e-14 * max(1.0, np.abs(G).sum(axis=0).max())
+        assert np.max(np.abs(E @ E.T - np.eye(4))) < 1e-13
+    assert seen == {3, 5, 7, 9, 13}          # every StaticArrays branch exercised
+    A = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    Ec, _ = orc.expm4c(0.3 * A)
+    assert np.max(np.abs(Ec - scipy.linalg.expm(0.3 * A))) < 1e-13
+
+
+def orc_N0():
+    return [[0, 0, 1, 0], [0, 0, 0, -1], [-1, 0, 0, 0], [0, 1, 0, 0]]
+
+
+def orc_N1():
+    return [[0, 0, 0, 1], [0, 0, 1, 0], [0, -1, 0, 0], [-1, 0, 0, 0]]
+
+
+def test_analytic_gates_embedded_in_reference(orc):
+    """spin.jl:557: exp(TTOT_ZPIBY2 * FQ * H0) = Z/2;  spin.jl:608-612: three-segment Y/2."""
+    Z = orc.propagator(FQ, 0.0, 17.857142857142858)
+    assert np.max(np.abs(Z - orc.gate_iso(1))) < 5e-16
+    tx, tz, A = 2.1656249366575766, 15.1423305995572655, 0.125
+    Y = orc.propagator(FQ, -A, tx) @ orc.propagator(FQ, 0.0, tz) @ orc.propagator(FQ, A, tx)
+    assert np.max(np.abs(Y - orc.gate_iso(2))) < 1e-15
+
+
+def test_t1_table_and_d1_pins(orc):
+    """D1 = int dt/T1(a): trials.xlsx spin14 (5.745 / 5.071 / 15.887 e-5), paper main.tex:1077."""
+    assert orc.t1_ns(0.0) == pytest.approx(310.88e3, rel=1e-15)
+    assert orc.t1_reduced_us(0.0) == pytest.approx(310.88, rel=1e-15)
+    assert orc.t1_ns(5.0) == pytest.approx(1597.923e3, rel=1e-15)      # flat extrapolation below the table
+    assert 17.857142857142858 / orc.t1_ns(0.0) == pytest.approx(5.7441e-5, rel=1e-4)
+    tx, tz = 2.1656249366575766, 15.1423305995572655
+    d1_y = 2 * tx / orc.t1_ns(0.125) + tz / orc.t1_ns(0.0)
+    assert d1_y == pytest.approx(5.0722e-5, rel=1e-4)
+    d1_x = 2 * d1_y + 17.857142857142858 / orc.t1_ns(0.0)
+    assert d1_x == pytest.approx(15.888e-5, rel=1e-4)
+
+
+def test_detuning_gate_error_pin(orc):
+    """paper main.tex:857-859: analytic Z/2 at +-1 % detuning, mean over random states ~ 4.7e-5."""
+    rng = np.random.default_rng(1)
+    S = 1000
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    psi0 = np.concatenate([psi.real, psi.imag], axis=1)
+    n = 100
+    ge = []
+    for f in (1.01 * FQ, 0.99 * FQ):
+        fid = orc.mc_static(np.zeros(n), 17.857142857142858 / n, 1, 1, np.full(S, f), None, psi0)
+        ge.append(1 - fid[:, 1])
+    assert np.mean(ge) == pytest.approx(4.66e-5, rel=0.03)
+
+
+@pytest.mark.parametrize("case", golden_model_cases(), ids=lambda c: c[0])
+def test_oracle_step_and_jacobian_match_50_digit_golden(orc, case):
+    key, name, dt, x, u, xn, J = case
+    p = orc.make_params(**MODEL_KW[name])
+    got = orc.step(p, x, u, dt)
+    assert relerr(got, xn) < 2e-15, key
+    Jg = orc.jacobian(p, x, u, dt)
+    assert Jg.shape == J.shape
+    assert relerr(Jg, J) < 1e-13, key
+
+
+def test_forwarddiff_conventions_at_kinks(orc):
+    """abs'(+0.0) = +1, abs'(-0.0) = -1 (ForwardDiff); the T1 table uses the interval searchsortedlast picks."""
+    p = orc.make_params(model_id=15, decay_aware=1)
+    x = np.zeros(12)
+    x[:8] = [1, 0, 0, 0, 0, 1, 0, 0]
+    slope_last = (310.88 - 560.251) / (0.5 - 0.492)            # last table interval, us per fbfq
+    for a, sgn in ((0.0, 1.0), (-0.0, -1.0)):
+        x[9] = a
+        J = orc.jacobian(p, x, np.zeros(1), 0.1)
+        # d/da [dt / T1(fbfq(a))] = -dt T1' fbfq'(a) / T1^2, fbfq' = -sgn * 0.202407
+        want = -0.1 * slope_last * (-sgn * 0.202407) / 310.88**2
+        assert J[11, 9] == pytest.approx(want, rel=1e-12)
+
+
+def test_mc_static_and_lindblad_match_50_digit_golden(orc):
+    z = np.load(GOLDEN + "/mc_static.npz")
+    fid, states = orc.mc_static(z["controls"], float(z["dt"]), int(z["gate"]), int(z["gate_count"]), z["fq"], z["da"], z["psi0"],
+                                want_states=True)
+    # ~1950 generic Pade exponentials and 4x4 products per sample: the reference algorithm's own rounding
+    assert np.max(np.abs(fid - z["fid"])) < 2e-12
+    assert np.max(np.abs(states - z["states"])) < 2e-12
+    z = np.load(GOLDEN + "/lindblad.npz")
+    G = int(z["gate_count"])
+    fid, fidc, rho = orc.lindblad_t1(z["controls"], float(z["dt"]), int(z["gate"]), G, float(z["fq"]), z["da"], z["rho0"])
+    assert np.max(np.abs(rho - z["rho"][:, G])) < 3e-12
+    # closed-form 2x2 Uhlmann fidelity == the reference's sqrtm route where the latter is well conditioned (mixed states)
+    assert np.max(np.abs(fid[2:] - fidc[2:])) < 1e-9
+
+
+def test_fidelity_and_cyclic_targets(orc):
+    s = np.array([0.6, 0.0, 0.0, 0.8])
+    assert orc.fidelity_vec_iso2(s, s) == pytest.approx(1.0, abs=1e-15)
+    assert orc.fidelity_vec_iso2(s, np.array([0.0, 0.6, -0.8, 0.0])) < 1.0
+    # an exact gate applied k times against the 4-cyclic targets stays at fidelity 1 (spin.jl:1198-1240)
+    fid = orc.mc_static(np.zeros(50), 17.857142857142858 / 50, 1, 9, np.array([FQ]), None, np.array([[0.6, 0.0, 0.0, 0.8]]))
+    assert np.max(np.abs(fid - 1)) < 1e-13
+
+
+def test_philox_known_answer(orc):
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    assert list(orc.philox4x32_10([0, 0, 0, 0], [0, 0])) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert list(orc.philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert list(orc.philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_pink_filter_is_the_reference_iir(orc):
+    x = np.zeros(16)
+    x[0] = 1.0
+    y = orc.pink_filter(x, 1.0)
+    b = [0.049922035, -0.095993537, 0.050612699, -0.004408786]
+    a = [1.0, -2.494956002, 2.017265875, -0.522189400]
+    assert np.allclose(y, scipy.signal.lfilter(b, a, x), rtol=1e-13, atol=1e-18)
+    assert np.allclose(orc.pink_filter(x, 10.0), 10.0 * y, rtol=1e-15)
+
+
+def test_stats_definition(orc):
+    e = np.array([1e-17, 1e-16, 3.2e-5, 0.5, 1.0, np.nan, 0.0])
+    st = orc.stats(e)
+    assert st.count == 6 and st.nonfinite == 1
+    assert st.hist[0] == 3            # 1e-17 (clamped), 1e-16 and 0.0
+    assert st.hist[int(np.floor((np.log10(3.2e-5) + 16) * 16))] == 1
+    assert st.hist[255] == 1          # 1.0 clamps into the last bin
+    assert st.min == 0.0 and st.max == 1.0

@@ -46,9 +46,10 @@ def test_mc_static_matches_oracle(engine, oracle, name, algo):
     fid, st = engine.mc_static(controls, dt, gate, gate_count, fq, da, psi0, algo=algo)
     ref = oracle.mc_static(controls, dt, gate, gate_count, fq, da, psi0)
     assert fid.shape == (S, gate_count + 1)
+    assert np.max(np.abs(fid[:, :2] - ref[:, :2])) < FID_RTOL, name        # one gate: the north-star tolerance
     # the oracle (= the reference algorithm) itself sits up to ~4e-13 from the exact answer after 5 gates of a
     # ~2000-knot pulse (50-digit referee, tests/test_oracle_cpu.py), so this is at the reference's own noise floor
-    assert np.max(np.abs(fid - ref)) < FID_RTOL, name
+    assert np.max(np.abs(fid - ref)) < 5 * FID_RTOL, name
     # statistics of the last-gate infidelity are exactly those of the returned fidelities
     e = 1.0 - fid[:, -1]
     assert st.count == S and st.nonfinite == 0
@@ -187,13 +188,34 @@ def test_lindblad_t1_matches_oracle(engine, oracle, name, mixed):
     da = 1e-3 * np.random.default_rng(2).standard_normal(S)
     fid, rho, st = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, da, rho0)
     rfid, rfid_closed, rrho = oracle.lindblad_t1(controls, dt, gate, gate_count, spin.FQ, da, rho0)
-    assert np.max(np.abs(rho - rrho)) < 1e-12
-    assert np.max(np.abs(fid - rfid_closed)) < 1e-12
+    # the oracle's per-knot complex Pade exponentials put it 4e-13..8e-13 from the 50-digit answer after 6 gates of a
+    # ~2000-knot pulse (test_lindblad_matches_50_digit_golden below pins the engine at 1e-13), hence 5e-12 here
+    assert np.max(np.abs(rho - rrho)) < 5e-12
+    assert np.max(np.abs(fid - rfid_closed)) < 5e-12
     # the reference's fidelity_mat goes through two matrix square roots (spin.jl:1101-1104); for (near-)pure
     # targets sqrt() turns its 1e-16 rounding into ~1e-8, so the eigen route only agrees to that level
     assert np.max(np.abs(fid - rfid)) < (5e-7 if not mixed else 1e-9)
     assert st.count == S
     assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1.0, atol=1e-14)
+
+
+def test_mc_static_matches_50_digit_golden(engine):
+    from _cases import GOLDEN
+
+    z = np.load(GOLDEN + "/mc_static.npz")
+    for algo, tol in ((rbq.ALGO_SU2, 1e-13), (rbq.ALGO_PADE, 2e-12)):
+        fid, _ = engine.mc_static(z["controls"], float(z["dt"]), int(z["gate"]), int(z["gate_count"]), z["fq"], z["da"], z["psi0"],
+                                  algo=algo)
+        assert np.max(np.abs(fid - z["fid"])) < tol, algo
+
+
+def test_lindblad_matches_50_digit_golden(engine):
+    from _cases import GOLDEN
+
+    z = np.load(GOLDEN + "/lindblad.npz")
+    G = int(z["gate_count"])
+    fid, rho, _ = engine.lindblad(z["controls"], float(z["dt"]), int(z["gate"]), G, float(z["fq"]), z["da"], z["rho0"])
+    assert np.max(np.abs(rho - z["rho"][:, G])) < 1e-13
 
 
 def test_lindblad_d1_pin(engine):

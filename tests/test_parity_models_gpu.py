@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from rbqoc_b200 import spin
+from _cases import MODEL_KW, golden_model_cases, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -129,6 +130,20 @@ def test_rollout_and_batched_jacobians(engine, oracle, name, model):
     assert AB.shape == (N - 1, model.n, model.n + model.m)
     scale = np.max(np.abs(ABr), axis=(1, 2), keepdims=True)
     assert np.max(np.abs(AB - ABr) / scale) < JAC_RTOL, name
+
+
+@pytest.mark.parametrize("case", golden_model_cases(), ids=lambda c: c[0])
+def test_step_and_jacobian_match_50_digit_golden(engine, case):
+    """Committed fixtures from the rounding-free referee (tests/golden/make_golden.py)."""
+    import rbqoc_b200 as rbq
+
+    key, name, dt, x, u, xn, J = case
+    p = spin._params(**MODEL_KW[name])
+    got = engine.discrete_dynamics(p, x, u, 0.0, dt)
+    assert relerr(got, xn) < 2e-15, key
+    Jg = engine.discrete_jacobian(p, x, u, 0.0, dt)
+    assert Jg.shape == J.shape
+    assert relerr(Jg, J) < 1e-13, key
 
 
 def test_closed_loop_rollout(engine, oracle):
