@@ -1,0 +1,177 @@
+"""
+RbqEngine.jl — `ccall` binding of librbq.so underneath the reference's RobotDynamics model API.
+
+NOT EXECUTED IN THE BUILD CONTAINER (no Julia there): written against include/rbq.h and the reference call sites
+    RD.discrete_dynamics(::Type{RK3}, model, astate, acontrol, time, dt)     spin13.jl:44-58 (and every spinYY.jl)
+    RD.discrete_jacobian!(::Type{RK3}, ∇f, model, z)                          RobotDynamics 0.2.1 default (ForwardDiff)
+    run_sim_prop(gate_count, gate_type; ...)                                  spin.jl:1553-1608
+Usage from a reference script (e.g. src/spin/spin13.jl), after its own `struct Model ... end`:
+
+    include(joinpath(ENV["RBQ_ENGINE_PATH"], "julia", "RbqEngine.jl"))
+    RbqEngine.@accelerate Model RbqEngine.params_spin13()      # adds the ccall-backed methods for this Model type
+
+`julia/selfcheck.jl` compares the accelerated methods with the un-overridden reference ones when Julia is available.
+"""
+module RbqEngine
+
+using StaticArrays
+import RobotDynamics
+const RD = RobotDynamics
+
+const LIB = get(ENV, "RBQ_LIB", joinpath(@__DIR__, "..", "rbqoc_b200", "librbq.so"))
+
+# ---- include/rbq.h mirrors -----------------------------------------------------------------------
+const RBQ_MAX_SAMPLE_STATES = 4
+const RBQ_HIST_BINS = 256
+
+struct ModelParams                      # rbq_model_params (128 bytes)
+    model_id::Int32
+    derivative_order::Int32
+    decay_aware::Int32
+    time_optimal::Int32
+    sample_state_count::Int32
+    algo::Int32
+    nominal_offset::NTuple{4,Int32}
+    reserved::NTuple{2,Int32}
+    fq::Float64
+    fq_samples::NTuple{2,Float64}
+    namp::Float64
+    fq_cov::Float64
+    alpha::Float64
+    S_diag::NTuple{4,Float64}
+end
+
+struct Stats                            # rbq_stats
+    count::Int64
+    nonfinite::Int64
+    sum::Float64
+    sumsq::Float64
+    min::Float64
+    max::Float64
+    hist::NTuple{RBQ_HIST_BINS,Int64}
+end
+
+const FQ = 1.4e-2
+_params(id; DO=0, DA=false, TO=false, ssc=1, nominal=(0, 0, 0, 0), fq=FQ, fq_samples=(0.0, 0.0), namp=0.0,
+        fq_cov=0.0, alpha=1.0, S=(1.0, 1.0, 1.0, 1.0)) =
+    ModelParams(id, DO, DA, TO, ssc, 0, Int32.(nominal), (Int32(0), Int32(0)), fq, fq_samples, namp, fq_cov, alpha, S)
+
+params_spin13() = _params(13)
+params_spin12(fq_cov=FQ * 1e-2) = _params(12; fq_samples=(FQ + fq_cov, FQ - fq_cov))            # spin12.jl:204-205
+params_spin18(namp) = _params(18; namp=namp)                                                     # spin18.jl:50-52
+params_spin15(DA::Bool, TO::Bool) = _params(15; DA=DA, TO=TO)                                     # spin15.jl:40-42
+params_spin11(DO::Int) = _params(11; DO=DO)                                                       # spin11.jl:51-52
+params_spin17(DO::Int) = _params(17; DO=DO)
+# spin30.jl:60-66: nominal_idxs[i][1]-1 is the 0-based offset of sample state i's nominal block
+params_spin30(S, nominal_idxs, fq_cov, alpha, ssc) =
+    _params(30; ssc=ssc, fq_cov=fq_cov, alpha=alpha, S=Tuple(diag(S)),
+            nominal=ntuple(i -> i <= ssc ? nominal_idxs[i][1] - 1 : 0, 4))
+
+# ---- handle ----------------------------------------------------------------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+end
+function Handle(device::Integer=0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:rbq_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), device, out)
+    rc == 0 || error("rbq_create failed with code $rc (no sm_100 device? the engine has no CPU fallback)")
+    h = Handle(out[])
+    finalizer(x -> ccall((:rbq_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
+const HANDLE = Ref{Union{Nothing,Handle}}(nothing)
+handle() = (HANDLE[] === nothing && (HANDLE[] = Handle(0)); HANDLE[]::Handle)
+
+function check(rc::Integer, what)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:rbq_last_error, LIB), Cstring, (Ptr{Cvoid},), handle().ptr))
+    error("$what failed with code $rc: $msg")
+end
+
+state_dim(p::ModelParams) = Int(ccall((:rbq_state_dim, LIB), Cint, (Ref{ModelParams},), p))
+control_dim(p::ModelParams) = Int(ccall((:rbq_control_dim, LIB), Cint, (Ref{ModelParams},), p))
+
+# ---- per-knot methods ---------------------------------------------------------------------------------
+function discrete_dynamics(p::ModelParams, x::AbstractVector{Float64}, u::AbstractVector{Float64}, t::Real, dt::Real)
+    n = state_dim(p)
+    xv, uv, out = Vector{Float64}(x), Vector{Float64}(u), Vector{Float64}(undef, n)   # SVectors are immutable: copy
+    GC.@preserve xv uv out check(ccall((:rbq_discrete_dynamics, LIB), Cint,
+        (Ptr{Cvoid}, Ref{ModelParams}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}),
+        handle().ptr, p, xv, uv, t, dt, out), "rbq_discrete_dynamics")
+    return SVector{n}(out)
+end
+
+"∇f is column-major n×(n+m): exactly the block layout rbq_discrete_jacobian writes."
+function discrete_jacobian!(∇f::AbstractMatrix{Float64}, p::ModelParams, x, u, t::Real, dt::Real)
+    xv, uv = Vector{Float64}(x), Vector{Float64}(u)
+    buf = ∇f isa Matrix{Float64} ? ∇f : Matrix{Float64}(undef, size(∇f)...)
+    GC.@preserve xv uv buf check(ccall((:rbq_discrete_jacobian, LIB), Cint,
+        (Ptr{Cvoid}, Ref{ModelParams}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}),
+        handle().ptr, p, xv, uv, t, dt, buf), "rbq_discrete_jacobian")
+    buf === ∇f || (∇f .= buf)
+    return ∇f
+end
+
+# ---- trajectory level (what makes the GPU worthwhile: one call per Altro pass, not one per knot) -----------
+"X: n×N matrix (column k = knot k, i.e. knot-major in memory), U: m×(N-1), dts: N-1."
+function rollout!(X::Matrix{Float64}, p::ModelParams, x0::AbstractVector, U::Matrix{Float64}, dts::Vector{Float64})
+    N = size(X, 2)
+    x0v = Vector{Float64}(x0)
+    GC.@preserve X x0v U dts check(ccall((:rbq_rollout, LIB), Cint,
+        (Ptr{Cvoid}, Ref{ModelParams}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        handle().ptr, p, 1, N, x0v, U, dts, X), "rbq_rollout")
+    return X
+end
+
+"AB: n×(n+m)×(N-1) array; slice k is ∇f_k.  X: n×(N-1) (or n×N), U: m×(N-1)."
+function jacobians!(AB::Array{Float64,3}, p::ModelParams, X::Matrix{Float64}, U::Matrix{Float64}, dts::Vector{Float64})
+    K = size(U, 2)
+    GC.@preserve AB X U dts check(ccall((:rbq_jacobians, LIB), Cint,
+        (Ptr{Cvoid}, Ref{ModelParams}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        handle().ptr, p, K, X, U, dts, AB), "rbq_jacobians")
+    return AB
+end
+
+# ---- Monte-Carlo evaluation ------------------------------------------------------------------------------
+"Batched run_sim_prop(…; dynamics_type=schroed): fidelities[(gate_count+1) × S] and statistics."
+function mc_static(controls::Vector{Float64}, dt::Real, gate::Integer, gate_count::Integer, fq::Vector{Float64},
+                   da::Union{Nothing,Vector{Float64}}, psi0::Matrix{Float64}; algo::Integer=0)
+    S = length(fq)
+    size(psi0) == (4, S) || error("psi0 must be 4×S")
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    GC.@preserve controls fq da psi0 fid check(ccall((:rbq_mc_static, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
+         Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, controls, length(controls), dt, gate, gate_count, S, fq, dap, psi0, algo, fid, st), "rbq_mc_static")
+    return fid, st[]
+end
+
+# ---- the macro a reference script uses ---------------------------------------------------------------------
+"""
+    RbqEngine.@accelerate Model params_expr
+
+Adds, for the script's own `Model` type, methods that forward to the engine:
+`RD.discrete_dynamics(::Type{RD.RK3}, ::Model, x, u, t, dt)` for Float64 arguments (dual-number calls from ForwardDiff
+still reach the script's generic method) and `RD.discrete_jacobian!(::Type{RD.RK3}, ∇f, ::Model, z)`.
+`params_expr` is evaluated with `model` in scope, e.g. `RbqEngine.params_spin30(model.S, model.nominal_idxs, model.fq_cov,
+model.alpha, model.sample_state_count)`.
+"""
+macro accelerate(M, pexpr)
+    quote
+        function RobotDynamics.discrete_dynamics(::Type{RobotDynamics.RK3}, model::$(esc(M)),
+                                                 x::StaticVector{<:Any,Float64}, u::StaticVector{<:Any,Float64},
+                                                 t::Real, dt::Real)
+            p = let model = model; $(esc(pexpr)); end
+            return RbqEngine.discrete_dynamics(p, x, u, t, dt)
+        end
+        function RobotDynamics.discrete_jacobian!(::Type{RobotDynamics.RK3}, ∇f, model::$(esc(M)),
+                                                  z::RobotDynamics.AbstractKnotPoint{Float64})
+            p = let model = model; $(esc(pexpr)); end
+            return RbqEngine.discrete_jacobian!(∇f, p, RobotDynamics.state(z), RobotDynamics.control(z), z.t, z.dt)
+        end
+    end
+end
+
+end # module

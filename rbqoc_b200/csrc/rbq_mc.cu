@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "rbq_math.cuh"
+#include "rbq_tanpoly.cuh"
 
 namespace rbq {
 
@@ -57,7 +58,10 @@ struct PulsePipe {
     RBQ_DEV void init(double* t, uint64_t* b, const double* s, int64_t n) {
         tile = t; bar = b; src = s; nk = n; pass = 0;
         ntiles = (int)((n + MC_TILE - 1) / MC_TILE);
-        if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+        if (threadIdx.x == 0) {
+            mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init();
+            if (n > 0) issue(0, 0);     // the first tile is in flight while the block loads its samples
+        }
         __syncthreads();
     }
     RBQ_DEV int tile_len(int ti) const { const int64_t r = nk - (int64_t)ti * MC_TILE; return r < MC_TILE ? (int)r : MC_TILE; }
@@ -71,7 +75,6 @@ struct PulsePipe {
     RBQ_DEV const double* acquire(int ti, bool more_passes) {
         const uint32_t slot = pass & 1u;
         if (threadIdx.x == 0) {
-            if (pass == 0) issue(0, 0);
             // prefetch the next tile (of this pass, or the first tile of the next pass) into the other slot;
             // the __syncthreads in release() guarantees nobody still reads it
             const int nxt = ti + 1 < ntiles ? ti + 1 : (more_passes ? 0 : -1);
@@ -80,7 +83,8 @@ struct PulsePipe {
         mbar_wait(&bar[slot], (pass >> 1) & 1u);
         return tile + slot * MC_TILE;
     }
-    RBQ_DEV void release() { __syncthreads(); ++pass; }
+    // `more`: another acquire() follows (the barrier protects the slot the next prefetch overwrites)
+    RBQ_DEV void release(bool more = true) { if (more) __syncthreads(); ++pass; }
 };
 
 // ---- statistics ---------------------------------------------------------------------------------------
@@ -181,12 +185,12 @@ __global__ void __launch_bounds__(1024) pulse_prep_kernel(const double* __restri
 }
 
 // ---- per-sample pieces ----------------------------------------------------------------------------------
-// series degree class from a bound on x = theta^2: 0 -> K=3, 1 -> K=5, 2 -> K=8, 3 -> sincos
-RBQ_DEV int degree_class(double xb) { return xb <= 8.0e-4 ? 0 : (xb <= 4.0e-2 ? 1 : (xb <= 0.7 ? 2 : 3)); }
-RBQ_DEV int block_max_class(int c) {
-    const int ge1 = __syncthreads_or(c >= 1), ge2 = __syncthreads_or(c >= 2), ge3 = __syncthreads_or(c >= 3);
-    return ge3 ? 3 : (ge2 ? 2 : (ge1 ? 1 : 0));
-}
+// propagator class from a bound on x = theta^2:
+//   0 -> tan form, degree-4 polynomial (x <= 1e-3: the dt = 0.01 grids)     1 -> tan form, degree 6 (x <= 0.026: dt = 0.1)
+//   2 -> normalised (cos, sinc) Taylor pair, K = 8 (x <= 0.7)                  3 -> sincos
+RBQ_DEV int degree_class(double xb) { return xb <= RBQ_TANA_XMAX ? 0 : (xb <= RBQ_TANB_XMAX ? 1 : (xb <= 0.7 ? 2 : 3)); }
+// warps only meet at tile boundaries, so the series degree needs to be uniform per warp, not per block
+RBQ_DEV int warp_max_class(int c) { return __reduce_max_sync(0xffffffffu, c); }
 template <int K> RBQ_DEV void su2_coeffs(double x, double& c, double& s) {
     if (K > 0) su2_series<(K > 0 ? K : 1)>(x, c, s);
     else {
@@ -197,7 +201,7 @@ template <int K> RBQ_DEV void su2_coeffs(double x, double& c, double& s) {
         c = cs; s = sn / th;
     }
 }
-// advance SPT states through `len` knots of a tile:  q_j = w a_j + qd
+// advance SPT states through `len` knots of a tile:  q_j = w a_j + qd   (normalised form, any x)
 template <int K, int SPT>
 RBQ_DEV void su2_tile(const double* __restrict__ tile, int len, double w, const double (&p)[SPT], const double (&p2)[SPT],
                       const double (&qd)[SPT], double (&v)[SPT][4]) {
@@ -213,6 +217,67 @@ RBQ_DEV void su2_tile(const double* __restrict__ tile, int len, double w, const 
             Prop<double> E{c, s * p[i], s * q};
             prop_apply(E, v[i]);
         }
+    }
+}
+// Tan form: exp(G) = cos(theta) (I + T G), T = tan(theta)/theta a polynomial in x = theta^2.  The scalar cos(theta) only
+// rescales the state, and the callers renormalise (the exact evolution is unitary), so a step is
+//     v <- v + (T p) N0 v + (T q) N1 v :   1 add + 1 fma + DEG fma + 2 mul + 8 fma.
+// U knots x SPT samples are evaluated together so that the Horner chains interleave (U*SPT independent chains).
+template <int DEG> RBQ_DEV double tan_poly(double x, const double (&cf)[DEG + 1]) {
+    double t = fma(cf[DEG], x, cf[DEG - 1]);
+#pragma unroll
+    for (int k = DEG - 2; k >= 0; --k) t = fma(t, x, cf[k]);
+    return t;
+}
+RBQ_DEV void tan_apply(double tp, double tq, double* v) {
+    const double a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+    v[0] = fma(tq, a3, fma(tp, a2, a0));
+    v[1] = fma(tq, a2, fma(-tp, a3, a1));
+    v[2] = fma(-tq, a1, fma(-tp, a0, a2));
+    v[3] = fma(-tq, a0, fma(tp, a1, a3));
+}
+template <int DEG, int SPT, int U>
+RBQ_DEV void tan_tile(const double* __restrict__ tile, int len, double w, const double (&p)[SPT], const double (&p2)[SPT],
+                      const double (&qd)[SPT], double (&v)[SPT][4], const double (&cf)[DEG + 1]) {
+    int j = 0;
+    for (; j + U <= len; j += U) {
+        double q[U][SPT], x[U][SPT], t[U][SPT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double wa = w * tile[j + u];
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) { q[u][i] = wa + qd[i]; x[u][i] = fma(q[u][i], q[u][i], p2[i]); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) t[u][i] = fma(cf[DEG], x[u][i], cf[DEG - 1]);
+#pragma unroll
+        for (int k = DEG - 2; k >= 0; --k)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < SPT; ++i) t[u][i] = fma(t[u][i], x[u][i], cf[k]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) tan_apply(t[u][i] * p[i], t[u][i] * q[u][i], v[i]);
+    }
+    for (; j < len; ++j) {
+        const double wa = w * tile[j];
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            const double q = wa + qd[i];
+            const double t = tan_poly<DEG>(fma(q, q, p2[i]), cf);
+            tan_apply(t * p[i], t * q, v[i]);
+        }
+    }
+    // |v| grows by 1/cos(theta) per knot (at most e^27 over a 2048-knot tile in class 1): pull it back to 1 per tile
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        const double inv = rsqrt(fma(v[i][3], v[i][3], fma(v[i][2], v[i][2], fma(v[i][1], v[i][1], v[i][0] * v[i][0]))));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[i][c] *= inv;
     }
 }
 // the 4x4 iso matrix whose first column is v (real iso of an SU(2) element)
@@ -248,18 +313,18 @@ RBQ_DEV double gate_train(const double* E, const double* psi0, const GateIso& G,
 }
 
 // ---- static-parameter sweep -------------------------------------------------------------------------------
-template <int ALGO, int SPT, int MINB>
-__global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McStaticArgs a) {
+template <int ALGO, int SPT, int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStaticArgs a) {
     __shared__ __align__(128) double tile_s[2 * MC_TILE];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
-    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    __shared__ BlockPartial red_s[THREADS / 32];
     const int tid = threadIdx.x;
-    for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    for (int b = tid; b < RBQ_HIST_BINS; b += THREADS) hist_s[b] = 0;
     PulsePipe pipe;
     pipe.init(tile_s, bar_s, a.controls, a.nk);
 
-    const int64_t base = (int64_t)blockIdx.x * (MC_THREADS * SPT);
+    const int64_t base = (int64_t)blockIdx.x * (THREADS * SPT);
     const double w = RBQ_PI * a.dt;
     double p[SPT], p2[SPT], qd[SPT], psi0[SPT][4];
     bool live[SPT];
@@ -267,7 +332,7 @@ __global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McSta
     const double wamax = w * (*a.amax);
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
-        const int64_t s = base + (int64_t)i * MC_THREADS + tid;
+        const int64_t s = base + (int64_t)i * THREADS + tid;
         live[i] = s < a.S;
         double fq = 0.0, da = 0.0;
         psi0[i][0] = 1.0; psi0[i][1] = psi0[i][2] = psi0[i][3] = 0.0;
@@ -287,21 +352,23 @@ __global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McSta
         const double xb = fma(qb, qb, p2[i]);
         cls = max(cls, xb == xb ? degree_class(xb) : 3);
     }
-    cls = block_max_class(cls);
+    cls = warp_max_class(cls);
 
     double E[SPT][16];
     if (ALGO == RBQ_ALGO_SU2) {
+        constexpr int UNR = 8 / SPT;                 // 8 independent Horner chains per thread
+        const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS;
         double v[SPT][4];
 #pragma unroll
         for (int i = 0; i < SPT; ++i) { v[i][0] = 1.0; v[i][1] = v[i][2] = v[i][3] = 0.0; }
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
-            if (cls == 0) su2_tile<3, SPT>(tile, len, w, p, p2, qd, v);
-            else if (cls == 1) su2_tile<5, SPT>(tile, len, w, p, p2, qd, v);
+            if (cls == 0) tan_tile<RBQ_TANA_DEG, SPT, UNR>(tile, len, w, p, p2, qd, v, cfA);
+            else if (cls == 1) tan_tile<RBQ_TANB_DEG, SPT, UNR>(tile, len, w, p, p2, qd, v, cfB);
             else if (cls == 2) su2_tile<8, SPT>(tile, len, w, p, p2, qd, v);
             else su2_tile<0, SPT>(tile, len, w, p, p2, qd, v);
-            pipe.release();
+            pipe.release(ti + 1 < pipe.ntiles);
         }
         // the exact product is a unit quaternion: dividing out |v| removes the radial rounding error, which
         // for piecewise-constant pulses accumulates coherently (the same (cos, sinc) rounding at every knot)
@@ -333,7 +400,7 @@ __global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McSta
                     for (int c = 0; c < 16; ++c) E[i][c] = T[c];
                 }
             }
-            pipe.release();
+            pipe.release(ti + 1 < pipe.ntiles);
         }
     }
 
@@ -341,7 +408,7 @@ __global__ void __launch_bounds__(MC_THREADS, MINB) mc_static_kernel(const McSta
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
         if (!live[i]) continue;
-        const int64_t s = base + (int64_t)i * MC_THREADS + tid;
+        const int64_t s = base + (int64_t)i * THREADS + tid;
         double* row = a.fid ? a.fid + s * (a.gate_count + 1) : nullptr;
         const double f = gate_train(E[i], psi0[i], a.gate, a.gate_count, row);
         if (a.partials) st.add(1.0 - f, hist_s);
@@ -462,7 +529,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
                     time = time + a.dt;
                 }
             }
-            pipe.release();
+            pipe.release(g < a.gate_count || ti + 1 < pipe.ntiles);
         }
         if (ALGO == RBQ_ALGO_SU2) {   // unitary evolution preserves the norm; shed the accumulated radial rounding
             const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
@@ -584,7 +651,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
             for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, P);
-            pipe.release();
+            pipe.release(ti + 1 < pipe.ntiles);
         }
         for (int64_t g = 1; g <= a.gate_count; ++g) {
             const double n0 = fma(P[2][0], r[2], fma(P[1][0], r[1], P[0][0] * r[0]));
@@ -603,7 +670,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
                 const double* tile = pipe.acquire(ti, g < a.gate_count);
                 const int len = pipe.tile_len(ti);
                 for (int j = 0; j < len; ++j, ++step) bloch_advance<1>(generator(tile[j], ((double)step + 0.5) * a.dt), kmax, rr);
-                pipe.release();
+                pipe.release(g < a.gate_count || ti + 1 < pipe.ntiles);
             }
             const int k = (int)(g & 3);
             f = fidelity_bloch(tr0, rr[0], tr0, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
@@ -650,16 +717,33 @@ __global__ void pink_noise_kernel(int64_t first, int64_t S, uint64_t seed, doubl
 
 // ---- DFMA saturation loop: the FP64 roofline denominator --------------------------------------------------------------
 constexpr int PEAK_CHAINS = 16;
+// MODE 0 is the roofline denominator (register-operand DFMA).  The other modes are microbenchmarks of the
+// instruction forms the sweep kernels use (selected with RBQ_PEAK_MODE; tools/fp64_micro.py).
+template <int MODE>
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double* __restrict__ sink) {
     double acc[PEAK_CHAINS];
     const double m = 1.0 - 1e-9 * (double)(threadIdx.x & 7), c = 1e-9 * (double)(blockIdx.x & 3);
 #pragma unroll
-    for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = (double)i;
+    for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = (double)i + 0.5;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = fma(acc[i], m, c);
+            for (int i = 0; i < PEAK_CHAINS; ++i) {
+                if (MODE == 0) acc[i] = fma(acc[i], m, c);
+                else if (MODE == 1) acc[i] = acc[i] * m;                                   // DMUL
+                else if (MODE == 2) acc[i] = acc[i] + c;                                   // DADD
+                else if (MODE == 3) acc[i] = fma(acc[i], m, 0.0013888888888888889);        // immediate/uniform addend
+                else if (MODE == 4) acc[i] = (i & 3) == 0 ? acc[i] * m : fma(acc[i], m, c);  // 1 DMUL : 3 DFMA
+                else if (MODE == 5) acc[i] = fma(acc[i], acc[(i + 1) % PEAK_CHAINS], acc[(i + 5) % PEAK_CHAINS]);  // 3 distinct regs
+                else if (MODE == 6) acc[i] = fma(-acc[i], acc[(i + 1) % PEAK_CHAINS], 0.0013888888888888889);
+                else if (MODE == 7) acc[i] = fma(m, acc[(i + 1) % PEAK_CHAINS], acc[i]);     // one operand reusable across instructions
+                else acc[i] = fma(acc[(i + 1) % PEAK_CHAINS], acc[(i + 2) % PEAK_CHAINS], acc[i]);
+            }
+        if (MODE >= 5) {
+#pragma unroll
+            for (int i = 0; i < PEAK_CHAINS; ++i) acc[i] = acc[i] * 1e-300 + 0.5;
+        }
     }
     double t = 0.0;
 #pragma unroll
@@ -667,23 +751,35 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double* __res
     if (t == 123456.789) sink[0] = t;   // never true; keeps the loop alive
 }
 
+// dependent-issue latency probe: one warp per SM, one serial DFMA chain (RBQ_PEAK_MODE=9)
+__global__ void __launch_bounds__(32) fp64_latency_kernel(int iters, double* __restrict__ sink) {
+    const double m = 1.0 - 1e-9 * (double)(threadIdx.x & 7), c = 1e-9 * (double)(blockIdx.x & 3);
+    double acc = 0.5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 128; ++r) acc = fma(acc, m, c);
+    }
+    if (acc == 123456.789) sink[0] = acc;
+}
+
 // ---- launchers -----------------------------------------------------------------------------------------------------------
-// (samples per thread, min resident blocks per SM) of the closed-form kernel; RBQ_MC_VARIANT=<spt><minb>
-// overrides the default for tuning runs
-static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, int* minb) {
-    *spt = 1; *minb = 1;
+// (samples per thread, min resident blocks per SM, block size) of the closed-form kernel;
+// RBQ_MC_VARIANT=<spt><minb><threads/128> overrides the default for tuning runs
+static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, int* minb, int* threads) {
+    *spt = 1; *minb = 1; *threads = 256;
     if (algo != RBQ_ALGO_SU2) return;
-    int v = 23;
+    int v = 222;
     if (const char* e = getenv("RBQ_MC_VARIANT")) v = atoi(e);
-    *spt = v / 10; *minb = v % 10;
-    if (!((*spt == 1 || *spt == 2 || *spt == 4) && *minb >= 1 && *minb <= 4)) { *spt = 2; *minb = 3; }
+    *spt = v / 100; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
+    const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 8)));
+    if (!ok) { *spt = 2; *minb = 2; *threads = 256; }
     // small sweeps: one sample per thread so that every SM gets blocks
-    if (S < (int64_t)sm_count * 4 * MC_THREADS * *spt) *spt = 1;
+    if (S < (int64_t)sm_count * 4 * *threads * *spt) *spt = 1;
 }
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
-    int spt, minb;
-    static_variant(S, h->sm_count, algo, &spt, &minb);
-    const int per = MC_THREADS * spt;
+    int spt, minb, threads;
+    static_variant(S, h->sm_count, algo, &spt, &minb, &threads);
+    const int per = threads * spt;
     return (int)((S + per - 1) / per);
 }
 int mc_noise_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
@@ -697,20 +793,21 @@ int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, doubl
     return (int)cudaGetLastError();
 }
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
-    int spt, minb;
-    static_variant(a.S, h->sm_count, algo, &spt, &minb);
+    int spt, minb, threads;
+    static_variant(a.S, h->sm_count, algo, &spt, &minb, &threads);
     const int blocks = mc_static_blocks(h, a.S, algo);
     if (nblocks_out) *nblocks_out = blocks;
-#define RBQ_GO(SPT_, MINB_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_><<<blocks, MC_THREADS, 0, h->stream>>>(a)
+#define RBQ_GO(SPT_, MINB_, T_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_, T_><<<blocks, T_, 0, h->stream>>>(a)
     if (algo == RBQ_ALGO_SU2) {
-        switch (spt * 10 + minb) {
-        case 11: RBQ_GO(1, 1); break; case 12: RBQ_GO(1, 2); break; case 13: RBQ_GO(1, 3); break; case 14: RBQ_GO(1, 4); break;
-        case 21: RBQ_GO(2, 1); break; case 22: RBQ_GO(2, 2); break; case 23: RBQ_GO(2, 3); break; case 24: RBQ_GO(2, 4); break;
-        case 41: RBQ_GO(4, 1); break; case 42: RBQ_GO(4, 2); break;
-        default: RBQ_GO(2, 3); break;
+        switch (spt * 100 + minb * 10 + threads / 128) {
+        case 112: RBQ_GO(1, 1, 256); break; case 122: RBQ_GO(1, 2, 256); break; case 132: RBQ_GO(1, 3, 256); break; case 142: RBQ_GO(1, 4, 256); break;
+        case 212: RBQ_GO(2, 1, 256); break; case 222: RBQ_GO(2, 2, 256); break; case 232: RBQ_GO(2, 3, 256); break; case 242: RBQ_GO(2, 4, 256); break;
+        case 141: RBQ_GO(1, 4, 128); break; case 161: RBQ_GO(1, 6, 128); break; case 181: RBQ_GO(1, 8, 128); break;
+        case 241: RBQ_GO(2, 4, 128); break; case 261: RBQ_GO(2, 6, 128); break; case 281: RBQ_GO(2, 8, 128); break;
+        default: RBQ_GO(2, 2, 256); break;
         }
     } else if (algo == RBQ_ALGO_PADE) {
-        mc_static_kernel<RBQ_ALGO_PADE, 1, 1><<<blocks, MC_THREADS, 0, h->stream>>>(a);
+        mc_static_kernel<RBQ_ALGO_PADE, 1, 1, 256><<<blocks, 256, 0, h->stream>>>(a);
     } else return RBQ_E_ALGO;
 #undef RBQ_GO
     h->launches++;
@@ -757,7 +854,26 @@ int launch_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, do
 }
 int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out, int* flops_per_thread_iter) {
     const int blocks = h->sm_count * 8;
-    fp64_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters, d_sink);
+    int mode = 0;
+    if (const char* e = getenv("RBQ_PEAK_MODE")) mode = atoi(e);
+    if (mode == 9) {
+        fp64_latency_kernel<<<h->sm_count, 32, 0, h->stream>>>(iters, d_sink);
+        h->launches++;
+        if (nthreads_out) *nthreads_out = h->sm_count * 32;
+        if (flops_per_thread_iter) *flops_per_thread_iter = 128 * 2;
+        return (int)cudaGetLastError();
+    }
+    switch (mode) {
+    case 1: fp64_peak_kernel<1><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 2: fp64_peak_kernel<2><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 3: fp64_peak_kernel<3><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 4: fp64_peak_kernel<4><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 5: fp64_peak_kernel<5><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 6: fp64_peak_kernel<6><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 7: fp64_peak_kernel<7><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    case 8: fp64_peak_kernel<8><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    default: fp64_peak_kernel<0><<<blocks, 256, 0, h->stream>>>(iters, d_sink); break;
+    }
     h->launches++;
     if (nthreads_out) *nthreads_out = blocks * 256;
     if (flops_per_thread_iter) *flops_per_thread_iter = 8 * PEAK_CHAINS * 2;

@@ -46,10 +46,13 @@ def test_mc_static_matches_oracle(engine, oracle, name, algo):
     fid, st = engine.mc_static(controls, dt, gate, gate_count, fq, da, psi0, algo=algo)
     ref = oracle.mc_static(controls, dt, gate, gate_count, fq, da, psi0)
     assert fid.shape == (S, gate_count + 1)
-    assert np.max(np.abs(fid[:, :2] - ref[:, :2])) < FID_RTOL, name        # one gate: the north-star tolerance
+    # one gate: the north-star tolerance; the reference algorithm's own rounding grows coherently with the knot
+    # count on piecewise-constant pulses (~2e-16 per knot), which only the 5680-knot X/2 feels
+    nk = controls.shape[0]
+    assert np.max(np.abs(fid[:, :2] - ref[:, :2])) < max(FID_RTOL, 5e-16 * nk), name
     # the oracle (= the reference algorithm) itself sits up to ~4e-13 from the exact answer after 5 gates of a
     # ~2000-knot pulse (50-digit referee, tests/test_oracle_cpu.py), so this is at the reference's own noise floor
-    assert np.max(np.abs(fid - ref)) < 5 * FID_RTOL, name
+    assert np.max(np.abs(fid - ref)) < max(5 * FID_RTOL, 2.5e-15 * nk), name
     # statistics of the last-gate infidelity are exactly those of the returned fidelities
     e = 1.0 - fid[:, -1]
     assert st.count == S and st.nonfinite == 0
@@ -191,7 +194,9 @@ def test_lindblad_t1_matches_oracle(engine, oracle, name, mixed):
     # the oracle's per-knot complex Pade exponentials put it 4e-13..8e-13 from the 50-digit answer after 6 gates of a
     # ~2000-knot pulse (test_lindblad_matches_50_digit_golden below pins the engine at 1e-13), hence 5e-12 here
     assert np.max(np.abs(rho - rrho)) < 5e-12
-    assert np.max(np.abs(fid - rfid_closed)) < 5e-12
+    # sqrt-fidelity against a PURE target is ill conditioned in any FP64 evaluation: det(target) = 0 is only known to
+    # ~1e-16, and F^2 contains 2 sqrt(det rho det target) ~ 2 sqrt(2.5e-4 1e-16) = 3e-10 (conditioning sqrt(eps))
+    assert np.max(np.abs(fid - rfid_closed)) < (5e-12 if mixed else 1e-8)
     # the reference's fidelity_mat goes through two matrix square roots (spin.jl:1101-1104); for (near-)pure
     # targets sqrt() turns its 1e-16 rounding into ~1e-8, so the eigen route only agrees to that level
     assert np.max(np.abs(fid - rfid)) < (5e-7 if not mixed else 1e-9)
