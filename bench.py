@@ -31,27 +31,34 @@ NK = 1000            # control knots of P_sin(1001)
 DT = 0.1
 S_PER_GPU = 1 << 20
 GATE_COUNT = 1
-# flops the SU(2) kernel executes per trajectory-step on this grid (series degree K=5, 2 samples/thread):
-#   0.5 DMUL (w*a_j shared by 2 samples) + 1 DFMA (q) + 1 DFMA (x) + 10 DFMA (cos, sinc) + 2 DMUL (s*p, s*q)
-#   + 4 DMUL + 8 DFMA (E psi)   ~ 26.25 FP64 instructions = 46.25 flop (FMA = 2)     [DESIGN.md §kernels]
-FLOPS_PER_STEP_SU2 = 46.25      # counted in the SASS of the K=5 loop: (160 DFMA*2 + 50 DMUL) / 8 sample-steps
-FP64_INSTR_PER_STEP_SU2 = 26.25
+# flops the closed-form kernel executes per trajectory-step on this grid (tan form, degree-6 polynomial, class B):
+#   1 DFMA (q = w a_j + w da) + 1 DFMA (x = q^2 + p^2) + 6 DFMA (T(x)) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v)
+#   = 18 FP64 instructions = 34 flop (FMA = 2); counted in the SASS: (128 DFMA*2 + 16 DMUL) / 8 sample-steps  [DESIGN.md §4.2]
+FLOPS_PER_STEP_SU2 = 34.0
+FP64_INSTR_PER_STEP_SU2 = 18.0
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 
 
 def sample_clocks(stop, out):
+    """One long-lived `nvidia-smi -lms 50` (spawning it per sample is too slow for a sub-second timed region)."""
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    while not stop.is_set():
-        try:
-            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=5)
-            for line in r.stdout.strip().splitlines():
-                out.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
-        stop.wait(0.2)
+    try:
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                                 os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+
+    def reader():
+        for line in proc.stdout:
+            out.append([c.strip() for c in line.split(",")])
+
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    proc.terminate()
+    t.join(timeout=2)
 
 
 def clocks_summary(rows):
@@ -270,7 +277,7 @@ def main():
             "config": {"workload": f"mc_static sweep (BASELINE configs[4]): P_sin({NK + 1}) = {NK} knots, dt={DT} ns, "
                                    f"S={S} samples per GPU (Philox keyed by global index; fq~N(0,1%) clipped 3%, "
                                    f"da~N(0,2.574e-5)), gate_count={GATE_COUNT}, per-sample fidelities + statistics",
-                       "samples_per_gpu": S, "knots": NK, "algo": "su2 closed form", "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "samples_per_gpu": S, "knots": NK, "algo": "su2 closed form (tan form, degree-6 polynomial)", "l2": "flushed between steps (256 MiB memset, untimed)",
                        "sharding": "contiguous sample ranges per rank, one all-gather of 2.1 KB statistics" if world > 1 else "single GPU"},
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
