@@ -75,6 +75,14 @@ def clocks_summary(rows):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(orc, controls, n_threads, target_seconds=12.0):
     """Times the oracle (reference algorithm: per-knot Pade exp + 4x4 products, one sample per call)
     on all host threads over a bounded sample of the same workload."""
@@ -111,7 +119,7 @@ def run_reference(args):
 
     orc.build()
     controls = spin.pulse_sin(NK + 1)[:-1]
-    threads = orc.num_threads()
+    threads = host_threads()
     budget = 60.0 / max(args.steps + args.warmup, 1)
     rates, S_used = [], 0
     for i in range(args.warmup + args.steps):
@@ -299,7 +307,7 @@ def main():
             from oracle import oracle as orc
 
             orc.build()
-            threads = orc.num_threads()
+            threads = host_threads()
             rate, S_cpu, t_cpu = cpu_reference_rate(orc, controls_h, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{S_cpu} samples x {NK} knots of the same workload in {t_cpu:.1f} s "
