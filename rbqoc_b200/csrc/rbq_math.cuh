@@ -132,16 +132,20 @@ template <int K, int NT> RBQ_DEV void su2_series(const Tan<NT>& x, Tan<NT>& c, T
 #pragma unroll
     for (int i = 0; i < NT; ++i) { c.d[i] = -dc * x.d[i]; s.d[i] = -ds * x.d[i]; }
 }
-// any x >= 0: series below 0.5, closed form above (used by the trajectory kernels, whose dt may
-// be a decision variable; the MC kernels pick K from a block-uniform bound instead)
+// any x >= 0: the shortest series whose truncation is below 1e-17 for this x, closed form above 0.5 (used by the
+// trajectory kernels, whose dt may be a decision variable; the sweep kernels pick a class per warp instead)
 RBQ_DEV void su2_general(double x, double& c, double& s) {
+    if (x <= 8.0e-4) { su2_series<3>(x, c, s); return; }
+    if (x <= 4.0e-2) { su2_series<5>(x, c, s); return; }
     if (x < 0.5) { su2_series<8>(x, c, s); return; }
     double th = sqrt(x), sn, cs;
     sincos(th, &sn, &cs);
     c = cs; s = sn / th;
 }
 template <int NT> RBQ_DEV void su2_general(const Tan<NT>& x, Tan<NT>& c, Tan<NT>& s) {
-    if (x.v < 0.5) { su2_series<8, NT>(x, c, s); return; }
+    if (x.v <= 8.0e-4) { su2_series<4, NT>(x, c, s); return; }   // one more term than the value needs: d/dx drops a power
+    if (x.v <= 4.0e-2) { su2_series<6, NT>(x, c, s); return; }
+    if (x.v < 0.5) { su2_series<9, NT>(x, c, s); return; }
     double th = sqrt(x.v), sn, cs;
     sincos(th, &sn, &cs);
     c.v = cs; s.v = sn / th;

@@ -6,6 +6,7 @@
 // Reference step maps: see rbq_models.cuh.  sm_100a only.
 #include "rbq_internal.h"
 #include "rbq_models.cuh"
+#include "rbq_warp_rollout.cuh"
 
 namespace rbq {
 
@@ -55,31 +56,6 @@ __global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n,
     }
 }
 
-// du = K_k (x_k - xref_k) + alpha d_k ; u_k = uref_k + du   (Altro's forward pass; K col-major m x n)
-template <int MODEL>
-__global__ void __launch_bounds__(32) closedloop_kernel(rbq_model_params p, int n, int m, int64_t N,
-                                                        const double* __restrict__ Xref, const double* __restrict__ Uref,
-                                                        const double* __restrict__ K, const double* __restrict__ d,
-                                                        const double* __restrict__ dt, int64_t nalpha,
-                                                        const double* __restrict__ alphas, double* __restrict__ X,
-                                                        double* __restrict__ Uout) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nalpha) return;
-    const double alpha = alphas[c];
-    double* Xc = X + (size_t)c * N * n;
-    double* Uc = Uout + (size_t)c * (N - 1) * m;
-    for (int i = 0; i < n; ++i) Xc[i] = Xref[i];
-    for (int64_t k = 0; k + 1 < N; ++k) {
-        for (int j = 0; j < m; ++j) {
-            double du = alpha * d[k * m + j];
-            for (int i = 0; i < n; ++i) du = fma(K[(size_t)k * m * n + (size_t)i * m + j], Xc[k * n + i] - Xref[k * n + i], du);
-            Uc[k * m + j] = Uref[k * m + j] + du;
-        }
-        ValueIO io{Xc + k * n, Uc + k * m, Xc + (k + 1) * n};
-        model_step<MODEL, double>(p, io, dt[k]);
-    }
-}
-
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int n, int m, int lanes_per_knot,
                                                         int64_t K, const double* __restrict__ X,
@@ -114,15 +90,25 @@ static inline int family(int model_id) {
     default: return RBQ_E_MODEL;                                         \
     }
 
+// one warp per trajectory up to this many trajectories; beyond it one thread per trajectory has the better throughput
+static const int64_t WARP_ROLLOUT_MAX = 1 << 16;
+
 int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, const double* d_x0,
                    const double* d_U, const double* d_dt, double* d_X) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
-    const int threads = B >= 128 ? 128 : 32;
-    const unsigned blocks = (unsigned)((B + threads - 1) / threads);
-#define CALL(M) rollout_kernel<M><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, d_x0, d_U, d_dt, d_X)
-    RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
+    if (B <= WARP_ROLLOUT_MAX) {
+        WarpRolloutArgs a{p, n, m, N, B, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
+#define CALL(M) warp_rollout_kernel<M, false><<<(unsigned)B, 32, 0, h->stream>>>(a)
+        RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
+    } else {
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+#define CALL(M) rollout_kernel<M><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, d_x0, d_U, d_dt, d_X)
+        RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
+#undef CALL
+    }
     h->launches++;
     return (int)cudaGetLastError();
 }
@@ -132,9 +118,9 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
                       double* d_X, double* d_Uout) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
-    // one candidate per warp-sized block so that candidates spread over SMs
-    const unsigned blocks = (unsigned)nalpha;
-#define CALL(M) closedloop_kernel<M><<<blocks, 1, 0, h->stream>>>(p, n, m, N, d_Xref, d_Uref, d_K, d_d, d_dt, nalpha, d_alphas, d_X, d_Uout)
+    // one step-size candidate per warp, one warp per block so that candidates spread over SMs
+    WarpRolloutArgs a{p, n, m, N, nalpha, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
+#define CALL(M) warp_rollout_kernel<M, true><<<(unsigned)nalpha, 32, 0, h->stream>>>(a)
     RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     h->launches++;

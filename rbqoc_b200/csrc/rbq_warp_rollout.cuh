@@ -1,0 +1,264 @@
+// rbq_warp_rollout.cuh — one WARP per trajectory: the augmented state lives in registers, each lane owns one
+// 4-real iso block (nominal states, sample states, sigma points, derivative states) and evaluates only the
+// propagator that block needs; the control chain is carried redundantly by every lane.  Used for
+//   * open-loop rollouts      x[k+1] = discrete_dynamics(RK3, model, x[k], u[k], t, dt[k])          (TO.rollout!)
+//   * closed-loop rollouts    u[k] = uref[k] + K[k](x[k] - xref[k]) + alpha d[k]                    (Altro forward pass)
+// The single-thread kernels pay a global store->load round trip per knot (~300 cycles); here a step is a short
+// dependent chain of FMAs plus, where the model needs them, warp shuffles (dot product with the feedback gain,
+// Lawson-Euler source terms, the unscented transform's mean / covariance reductions).
+// Reference step maps: spin13.jl:44-58, spin12.jl:165-192, spin18.jl:162-190, spin15.jl:50-73, spin11.jl:64-117,
+// spin17.jl:61-114, spin30.jl:86-202.
+#pragma once
+#include "rbq_models.cuh"
+
+namespace rbq {
+
+constexpr unsigned FULL = 0xffffffffu;
+RBQ_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+RBQ_DEV double sum16(double v) {   // lanes 0..15 (the xor butterfly leaves the total on each of them)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+struct WarpRolloutArgs {
+    rbq_model_params p;
+    int n, m;
+    int64_t N, count;            // knots per trajectory, number of trajectories / candidates
+    const double* x0;            // open loop: [count][n];  closed loop: Xref [N][n]
+    const double* U;             // open loop: [count][N-1][m];  closed loop: Uref [N-1][m]
+    const double* K;             // closed loop: [N-1] blocks, column-major m x n
+    const double* d;             // closed loop: [N-1][m]
+    const double* dt;            // [N-1]
+    const double* alphas;        // closed loop: [count]
+    double* X;                   // [count][N][n]
+    double* Uout;                // closed loop: [count][N-1][m]
+};
+
+template <int MODEL, bool CLOSED>
+__global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs a) {
+    const rbq_model_params& p = a.p;
+    const int lane = threadIdx.x;
+    const int64_t tr = blockIdx.x;
+    const int n = a.n, m = a.m;
+    const int64_t N = a.N;
+    constexpr bool U30 = (MODEL == RBQ_MODEL_SPIN30);
+    constexpr int NCH = U30 ? RBQ_MAX_SAMPLE_STATES : 1;   // sigma-point chunks a lane may hold
+    const int ssc = U30 ? p.sample_state_count : 1;
+    const int cb = U30 ? 12 : 8;                            // [int a, a, da] chain base
+
+    // ---- lane roles ---------------------------------------------------------------------------------
+    int off = -1;                 // state offset of this lane's block (chunk 0 for sigma lanes)
+    double f = p.fq, da_l = 0.0;  // this lane's generator: f NEGI_H0 + (a + da_l) NEGI_H1
+    if (MODEL == RBQ_MODEL_SPIN13 || MODEL == RBQ_MODEL_SPIN15) {
+        if (lane < 2) off = 4 * lane;
+    } else if (MODEL == RBQ_MODEL_SPIN12) {
+        if (lane < 2) off = 4 * lane;
+        else if (lane < 10) {
+            off = 11 + 4 * (lane - 2);
+            const int grp = (lane - 2) >> 2;
+            if (p.model_id == RBQ_MODEL_SPIN12) f = p.fq_samples[grp];
+            else da_l = grp == 0 ? p.namp : -p.namp;
+        }
+    } else if (MODEL == RBQ_MODEL_SPIN11) {
+        if (lane < 2) off = 4 * lane;
+        else if (lane - 2 < p.derivative_order) off = 11 + 4 * (lane - 2);
+    } else {
+        const double sig = sqrt(p.fq_cov);
+        if (lane < 10) { off = 15 + 4 * lane; if (lane == 4) f = p.fq + sig; if (lane == 9) f = p.fq - sig; }
+        else if (lane < 13) off = 4 * (lane - 10);
+    }
+    const bool sigma_lane = U30 && lane < 10;
+    const bool has_block = off >= 0;
+    const bool src_h1 = p.model_id == RBQ_MODEL_SPIN17;
+
+    const double* __restrict__ x0 = CLOSED ? a.x0 : a.x0 + tr * n;
+    const double* __restrict__ Uin = CLOSED ? a.U : a.U + tr * (N - 1) * m;
+    double* __restrict__ X = a.X + tr * N * n;
+    double* __restrict__ Uo = CLOSED ? a.Uout + tr * (N - 1) * m : nullptr;
+    const double alpha = CLOSED ? a.alphas[tr] : 0.0;
+
+    // ---- state in registers ---------------------------------------------------------------------------
+    double psi[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) psi[c][i] = 0.0;
+    if (has_block) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            if (c == 0 || (sigma_lane && c < ssc))
+#pragma unroll
+                for (int i = 0; i < 4; ++i) psi[c][i] = x0[off + 41 * c + i];
+    }
+    double ci = x0[cb], ca = x0[cb + 1], cd = x0[cb + 2];
+    const bool DA = MODEL == RBQ_MODEL_SPIN15 && p.decay_aware;
+    const bool TO = MODEL == RBQ_MODEL_SPIN15 && p.time_optimal;
+    double gacc = DA ? x0[11] : 0.0;
+    double pen[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pen[c] = (U30 && c < ssc) ? x0[15 + 41 * c + 40] : 0.0;
+    // knot 0
+    for (int i = lane; i < n; i += 32) X[i] = x0[i];
+
+    const double cf = U30 ? 1.0 / (2.0 * p.alpha * p.alpha) : 0.0;
+    // the next knot's control and dt are fetched one step ahead: with a single warp per SM nothing else hides the load
+    double u0_n = 0.0, u1_n = 0.0, dt_n = 0.0;
+    if (N > 1) {
+        if (!CLOSED) { u0_n = Uin[0]; if (m > 1) u1_n = Uin[1]; }
+        dt_n = a.dt[0];
+    }
+
+    for (int64_t k = 0; k + 1 < N; ++k) {
+        // ---- control ---------------------------------------------------------------------------------
+        double u0, u1 = 0.0;
+        if (CLOSED) {
+            const double* __restrict__ Kk = a.K + k * m * n;
+            const double* __restrict__ xr = a.x0 + k * n;
+            double s0 = 0.0, s1 = 0.0;
+            if (has_block) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    if (c == 0 || (sigma_lane && c < ssc))
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = off + 41 * c + i;
+                            const double dx = psi[c][i] - xr[idx];
+                            s0 = fma(Kk[idx * m], dx, s0);
+                            if (m > 1) s1 = fma(Kk[idx * m + 1], dx, s1);
+                        }
+            }
+            if (lane == 15) {   // scalar tail of the state: chain, decay accumulator, unscented penalties (lanes 0..15 hold them)
+                const double tail[3] = {ci - xr[cb], ca - xr[cb + 1], cd - xr[cb + 2]};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { s0 = fma(Kk[(cb + i) * m], tail[i], s0); if (m > 1) s1 = fma(Kk[(cb + i) * m + 1], tail[i], s1); }
+                if (DA) { const double dx = gacc - xr[11]; s0 = fma(Kk[11 * m], dx, s0); if (m > 1) s1 = fma(Kk[11 * m + 1], dx, s1); }
+                if (U30) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        if (c < ssc) { const int idx = 15 + 41 * c + 40; s0 = fma(Kk[idx * m], pen[c] - xr[idx], s0); }
+                }
+            }
+            s0 = warp_sum(s0);
+            u0 = a.U[k * m] + fma(alpha, a.d[k * m], s0);
+            if (m > 1) { s1 = warp_sum(s1); u1 = a.U[k * m + 1] + fma(alpha, a.d[k * m + 1], s1); }
+            if (lane == 0) { Uo[k * m] = u0; if (m > 1) Uo[k * m + 1] = u1; }
+        } else {
+            u0 = u0_n; u1 = u1_n;
+            if (k + 2 < N) { u0_n = Uin[(k + 1) * m]; if (m > 1) u1_n = Uin[(k + 1) * m + 1]; }
+        }
+        const double dt = TO ? u1 * u1 : dt_n;
+        if (k + 2 < N) dt_n = a.dt[k + 1];
+        double* Xn = X + (k + 1) * n;
+
+        // ---- this lane's propagator and block ---------------------------------------------------------
+        const Prop<double> E = prop_of<double, double>(f, ca + da_l, dt);
+        double in0[4] = {psi[0][0], psi[0][1], psi[0][2], psi[0][3]};   // block value at knot k (chunk 0)
+        if (!U30) {
+            double w[4] = {in0[0], in0[1], in0[2], in0[3]};
+            if (MODEL == RBQ_MODEL_SPIN11) {
+                // Lawson-Euler source: d psi += dt H psi1 (lane 2 <- lane 0), d2 psi += 2 dt H d psi (lane 3 <- lane 2)
+                const int src = lane == 3 ? 2 : 0;
+                double s[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[i] = __shfl_sync(FULL, in0[i], src);
+                if (lane == 2 || lane == 3) {
+                    double g[4];
+                    if (src_h1) apply_N1<double>(s[0], s[1], s[2], s[3], g[0], g[1], g[2], g[3]);
+                    else apply_N0<double>(s[0], s[1], s[2], s[3], g[0], g[1], g[2], g[3]);
+                    const double fac = (RBQ_PI * dt) * (double)(lane - 1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[i] = fma(g[i], fac, w[i]);
+                }
+            }
+            if (has_block) {
+                prop_apply<double>(E, w[0], w[1], w[2], w[3], psi[0][0], psi[0][1], psi[0][2], psi[0][3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
+            }
+        } else {
+            // nominal lanes 10..12
+            if (lane >= 10 && lane < 13) {
+                prop_apply<double>(E, in0[0], in0[1], in0[2], in0[3], psi[0][0], psi[0][1], psi[0][2], psi[0][3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (c >= ssc) break;
+                double s[4] = {0.0, 0.0, 0.0, 0.0};
+                if (sigma_lane) prop_apply<double>(E, psi[c][0], psi[c][1], psi[c][2], psi[c][3], s[0], s[1], s[2], s[3]);
+                double sm[4], dv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { sm[i] = 0.1 * sum16(s[i]); dv[i] = sigma_lane ? s[i] - sm[i] : 0.0; }
+                double P[10];   // packed lower triangle 00 10 11 20 21 22 30 31 32 33
+                {
+                    int q = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int kk = 0; kk <= i; ++kk) P[q++] = cf * sum16(dv[i] * dv[kk]);
+                }
+                double L[10];
+#define RBQ_TRI(i, k) ((i) * ((i) + 1) / 2 + (k))
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double dd = P[RBQ_TRI(j, j)];
+#pragma unroll
+                    for (int kk = 0; kk < j; ++kk) dd = fma(-L[RBQ_TRI(j, kk)], L[RBQ_TRI(j, kk)], dd);
+                    const double inv = rsqrt(dd);        // one reciprocal square root instead of sqrt + divide
+                    L[RBQ_TRI(j, j)] = dd * inv;
+#pragma unroll
+                    for (int i = j + 1; i < 4; ++i) {
+                        double t = P[RBQ_TRI(i, j)];
+#pragma unroll
+                        for (int kk = 0; kk < j; ++kk) t = fma(-L[RBQ_TRI(i, kk)], L[RBQ_TRI(j, kk)], t);
+                        L[RBQ_TRI(i, j)] = t * inv;
+                    }
+                }
+                // resample: lanes 0..3 sm + alpha L[:,j], lane 4 sm, lanes 5..8 sm - alpha L[:,j-5], lane 9 sm
+                const int j = lane < 5 ? lane : lane - 5;
+                const double sgn = lane < 5 ? p.alpha : -p.alpha;
+                double v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double col = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (jj <= i && j == jj) col = L[RBQ_TRI(i, jj)];
+                    v[i] = fma(sgn, col, sm[i]);
+                }
+#undef RBQ_TRI
+                const double rn = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+                if (sigma_lane) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { psi[c][i] = v[i] * rn; Xn[off + 41 * c + i] = psi[c][i]; }
+                }
+                // penalty with the nominal state AT KNOT k (lane 10 + nominal block)
+                const int nl = 10 + (p.nominal_offset[c] >> 2);
+                double pv = P[0] * p.S_diag[0] + P[2] * p.S_diag[1] + P[5] * p.S_diag[2] + P[9] * p.S_diag[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double dn = sm[i] - __shfl_sync(FULL, in0[i], nl);
+                    pv = fma(dn * dn, p.S_diag[i], pv);
+                }
+                pen[c] = pv;
+                if (lane == 0) Xn[15 + 41 * c + 40] = pv;
+            }
+        }
+        // ---- scalar tail -----------------------------------------------------------------------------------
+        if (DA) {
+            gacc = fma(1.0 / t1_interp<double>(ca, 1.0), dt, gacc);
+            if (lane == 0) Xn[11] = gacc;
+        }
+        const double ni = fma(ca, dt, ci), na = fma(cd, dt, ca), nd = fma(u0, dt, cd);
+        ci = ni; ca = na; cd = nd;
+        if (lane == 0) { Xn[cb] = ci; Xn[cb + 1] = ca; Xn[cb + 2] = cd; }
+    }
+}
+
+}  // namespace rbq

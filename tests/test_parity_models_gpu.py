@@ -146,22 +146,48 @@ def test_step_and_jacobian_match_50_digit_golden(engine, case):
     assert relerr(Jg, J) < 1e-13, key
 
 
-def test_closed_loop_rollout(engine, oracle):
-    model = spin.Spin12Model()
-    rng = np.random.default_rng(5)
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+def test_closed_loop_rollout(engine, oracle, name, model):
+    """The iLQR line search: u_k = uref_k + K_k (x_k - xref_k) + alpha d_k for several alpha at once."""
+    rng = np.random.default_rng(_seed(name, 5))
     N = 181
     dt = np.full(N - 1, 0.1)
-    Uref = rng.uniform(-2e-3, 2e-3, (N - 1, 1))
-    Xref = oracle.rollout(model.params, spin.spin12_x0(), Uref, dt)
-    K = 1e-2 * rng.standard_normal((N - 1, model.m, model.n))
+    x0 = _random_point(model, rng)[0]
+    if model.params.model_id != 30:
+        x0[0:8] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO])
+        x0[8:11] = 0.0
+    else:
+        x0[12:15] = 0.0
+    Uref = rng.uniform(-2e-3, 2e-3, (N - 1, model.m))
+    if model.params.model_id == 15 and model.params.time_optimal:
+        Uref[:, 1] = rng.uniform(0.25, 0.35, N - 1)
+    Xref = oracle.rollout(model.params, x0, Uref, dt)
+    # gains scaled per state so that the closed loop stays well conditioned (the derivative states of spin11/17 grow
+    # like (pi t)^2; an O(1e-2) gain on them makes the loop amplify rounding noise by many orders of magnitude)
+    K = 1e-2 * rng.standard_normal((N - 1, model.m, model.n)) / (1.0 + np.max(np.abs(Xref), axis=0))
     d = 1e-3 * rng.standard_normal((N - 1, model.m))
     alphas = np.array([1.0, 0.5, 0.25, 0.125, 0.0])
     X, Uo = engine.rollout_closedloop(model.params, Xref, Uref, K, d, dt, alphas)
     Kc = np.ascontiguousarray(K.transpose(0, 2, 1))
     Xr, Ur = oracle.rollout_closedloop(model.params, Xref, Uref, Kc, d, dt, alphas)
-    assert _relerr(X, Xr) < 5e-12
-    assert _relerr(Uo, Ur) < 5e-12
+    assert X.shape == (5, N, model.n) and Uo.shape == (5, N - 1, model.m)
+    assert _relerr(X, Xr) < 5e-12, name
+    assert _relerr(Uo, Ur) < 5e-12, name
     assert _relerr(X[-1], Xref) < 1e-13      # alpha = 0 reproduces the reference trajectory
+
+
+def test_rollout_large_batch_uses_thread_per_trajectory(engine, oracle):
+    """Above 65536 trajectories the engine switches from one warp to one thread per trajectory."""
+    model = spin.Spin13Model()
+    B, N = 70000, 5
+    rng = np.random.default_rng(1)
+    x0 = np.tile(spin.spin13_x0(), (B, 1))
+    U = rng.uniform(-1e-2, 1e-2, (B, N - 1, 1))
+    dt = np.full(N - 1, 0.1)
+    X = engine.rollout(model.params, x0, U, dt)
+    idx = rng.integers(0, B, 64)
+    Xr = oracle.rollout(model.params, x0[idx], U[idx], dt)
+    assert _relerr(X[idx], Xr) < 1e-13
 
 
 def test_jacobian_structure_spin13(engine):
