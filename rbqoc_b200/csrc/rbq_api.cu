@@ -3,6 +3,7 @@
 // ends in a kernel launch on the handle's device or returns an error code.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <complex>
@@ -14,7 +15,7 @@
 using namespace rbq;
 
 // dbuf roles
-enum { B_PULSE = 0, B_PARTIALS, B_SCALARS, B_IN0, B_IN1, B_IN2, B_IN3, B_IN4, B_OUT0, B_OUT1, B_STATS, B_IN5 };
+enum { B_PULSE = 0, B_PARTIALS, B_SCALARS, B_IN0, B_IN1, B_IN2, B_IN3, B_IN4, B_OUT0, B_OUT1, B_STATS, B_IN5, B_IDX };
 
 static int fail(rbq_handle* h, int code, const char* fmt, ...) {
     if (h) {
@@ -148,6 +149,7 @@ int rbq_destroy(rbq_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < RBQ_NBUF; ++i) if (h->dbuf[i]) cudaFree(h->dbuf[i]);
     for (int i = 0; i < 2; ++i) if (h->hbuf[i]) cudaFreeHost(h->hbuf[i]);
+    free(h->idx_host);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(h->copy_stream[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -443,6 +445,48 @@ int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, d
 }
 
 // ---- time-dependent noise -----------------------------------------------------------------------------------------
+// Noise-sample index of every (gate, knot): idx = floor(time * noise_dt_inv) with `time` accumulated by repeated
+// `time += dt` exactly as integrate_prop_schroedda! does (spin.jl:472-481; 0-based, clamped to the last sample).  The
+// sequence does not depend on the sample, so it is built once on the host, cached in the handle and streamed to the
+// kernel next to the pulse.
+static int noise_index_table(rbq_handle* h, int64_t nk, double dt, int64_t gates, double ndi, int64_t noise_len,
+                             const int32_t** d_table, int64_t* stride) {
+    const int64_t nkp = (nk + 3) & ~(int64_t)3;
+    *stride = nkp;
+    if (noise_len >= ((int64_t)1 << 31)) return fail(h, RBQ_E_SIZE, "noise_len %lld does not fit the index table", (long long)noise_len);
+    const size_t count = (size_t)nkp * (size_t)(gates > 0 ? gates : 1);
+    void* dtab;
+    const bool dev_ok = h->dcap[B_IDX] >= count * sizeof(int32_t);
+    CKL(dev_buf(h, B_IDX, count * sizeof(int32_t), &dtab));
+    *d_table = (const int32_t*)dtab;
+    if (dev_ok && h->idx_host && h->idx_nk == nk && h->idx_gates == gates && h->idx_len == noise_len && h->idx_dt == dt && h->idx_ndi == ndi)
+        return 0;
+    if (h->idx_cap < count) {
+        free(h->idx_host);
+        h->idx_host = (int32_t*)malloc(count * sizeof(int32_t));
+        h->idx_cap = h->idx_host ? count : 0;
+        if (!h->idx_host) return fail(h, RBQ_E_SIZE, "out of host memory for the noise index table");
+    }
+    volatile double time = 0.0;   // volatile: no fused or extended-precision shortcuts, the sum is the reference's
+    for (int64_t g = 0; g < gates; ++g) {
+        int32_t* rowp = h->idx_host + g * nkp;
+        for (int64_t j = 0; j < nk; ++j) {
+            const double prod = time * ndi;
+            int64_t idx = (int64_t)floor(prod);
+            if (!(idx < noise_len - 1)) idx = noise_len - 1;
+            if (idx < 0) idx = 0;
+            rowp[j] = (int32_t)idx;
+            time = time + dt;
+        }
+        for (int64_t j = nk; j < nkp; ++j) rowp[j] = rowp[nk - 1];
+    }
+    CK(cudaStreamSynchronize(h->stream));   // an earlier launch may still be reading the device copy
+    CK(cudaMemcpyAsync(dtab, h->idx_host, count * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the host copy is pageable
+    h->idx_nk = nk; h->idx_gates = gates; h->idx_len = noise_len; h->idx_dt = dt; h->idx_ndi = ndi;
+    return 0;
+}
+
 static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
                          int64_t first, int64_t S, double fq, const double* d_noise, int64_t noise_len, double noise_dt_inv,
                          const double* d_psi0, int philox, uint64_t seed, double namp, int algo, double* d_fid,
@@ -455,6 +499,7 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
     a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S; a.fq = fq;
     a.noise = d_noise; a.noise_len = noise_len; a.noise_dt_inv = noise_dt_inv; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.namp = namp; a.fid = d_fid;
+    CKL(noise_index_table(h, nk, dt, gate_count, noise_dt_inv, noise_len, &a.idx_table, &a.idx_stride));
     if (d_stats) {
         void* pp;
         CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * mc_noise_blocks(h, S), &pp));

@@ -6,7 +6,7 @@
 
 #include "../../include/rbq.h"
 
-#define RBQ_NBUF 12
+#define RBQ_NBUF 14
 
 struct rbq_handle {
     int device;
@@ -20,6 +20,9 @@ struct rbq_handle {
     size_t dcap[RBQ_NBUF];
     void* hbuf[2];                 // pinned host staging (stats, small results)
     size_t hcap[2];
+    // cached noise-index table of integrate_prop_schroedda! (host copy + key); the device copy is dbuf[B_IDX]
+    int32_t* idx_host; size_t idx_cap;
+    int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
 };
 
 namespace rbq {
@@ -49,6 +52,7 @@ struct McNoiseArgs {
     const double* controls; int64_t nk; double dt;
     int64_t gate_count; int64_t first; int64_t S; double fq;
     const double* noise; int64_t noise_len; double noise_dt_inv; const double* psi0;
+    const int32_t* idx_table; int64_t idx_stride;   // noise-sample index per (gate, knot), rows padded to 4 entries
     int philox; uint64_t seed; double namp;
     double* fid; BlockPartial* partials; unsigned long long* hist; const double* amax;
     GateIso gate;

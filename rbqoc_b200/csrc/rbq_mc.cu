@@ -48,44 +48,56 @@ RBQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Walks a staged pulse (16-byte aligned, zero padded to a multiple of 2 knots) through two
 // shared-memory tiles.  `pass` counts tiles since kernel start so the pulse can be replayed once per gate.
-struct PulsePipe {
-    double* tile;       // [2][MC_TILE]
+// Optionally a companion int32 table (one row of `aux_stride` entries per replay) rides in the same tiles:
+// the noise-sample index of every (gate, knot) of integrate_prop_schroedda!.
+template <int TILE>
+struct PulsePipeT {
+    double* tile;       // [2][TILE]
+    int32_t* aux_tile;  // [2][TILE] or nullptr
     uint64_t* bar;      // [2]
     const double* src;
+    const int32_t* aux_src;
+    int64_t aux_stride;
     int64_t nk;
     int ntiles;
     uint32_t pass;
-    RBQ_DEV void init(double* t, uint64_t* b, const double* s, int64_t n) {
-        tile = t; bar = b; src = s; nk = n; pass = 0;
-        ntiles = (int)((n + MC_TILE - 1) / MC_TILE);
+    RBQ_DEV void init(double* t, uint64_t* b, const double* s, int64_t n, int32_t* at = nullptr, const int32_t* as = nullptr,
+                      int64_t astride = 0) {
+        tile = t; bar = b; src = s; nk = n; pass = 0; aux_tile = at; aux_src = as; aux_stride = astride;
+        ntiles = (int)((n + TILE - 1) / TILE);
         if (threadIdx.x == 0) {
             mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init();
-            if (n > 0) issue(0, 0);     // the first tile is in flight while the block loads its samples
+            if (n > 0) issue(0, 0, 0);     // the first tile is in flight while the block loads its samples
         }
         __syncthreads();
     }
-    RBQ_DEV int tile_len(int ti) const { const int64_t r = nk - (int64_t)ti * MC_TILE; return r < MC_TILE ? (int)r : MC_TILE; }
-    RBQ_DEV void issue(int ti, uint32_t slot) {
+    RBQ_DEV int tile_len(int ti) const { const int64_t r = nk - (int64_t)ti * TILE; return r < TILE ? (int)r : TILE; }
+    RBQ_DEV void issue(int ti, uint32_t slot, int64_t replay) {
         const int len = tile_len(ti);
         const uint32_t bytes = (uint32_t)(((len + 1) & ~1) * sizeof(double));
-        mbar_expect_tx(&bar[slot], bytes);
-        bulk_g2s(tile + slot * MC_TILE, src + (int64_t)ti * MC_TILE, bytes, &bar[slot]);
+        const uint32_t abytes = aux_src ? (uint32_t)(((len + 3) & ~3) * sizeof(int32_t)) : 0u;
+        mbar_expect_tx(&bar[slot], bytes + abytes);
+        bulk_g2s(tile + slot * TILE, src + (int64_t)ti * TILE, bytes, &bar[slot]);
+        if (aux_src) bulk_g2s(aux_tile + slot * TILE, aux_src + replay * aux_stride + (int64_t)ti * TILE, abytes, &bar[slot]);
     }
-    // call with ti = 0..ntiles-1 in order; returns the tile; every thread of the block must call it
-    RBQ_DEV const double* acquire(int ti, bool more_passes) {
+    // call with ti = 0..ntiles-1 in order, replay = 0,1,..; every thread of the block must call it
+    RBQ_DEV const double* acquire(int ti, bool more_passes, int64_t replay = 0) {
         const uint32_t slot = pass & 1u;
         if (threadIdx.x == 0) {
-            // prefetch the next tile (of this pass, or the first tile of the next pass) into the other slot;
+            // prefetch the next tile (of this replay, or the first tile of the next one) into the other slot;
             // the __syncthreads in release() guarantees nobody still reads it
-            const int nxt = ti + 1 < ntiles ? ti + 1 : (more_passes ? 0 : -1);
-            if (nxt >= 0) issue(nxt, slot ^ 1u);
+            if (ti + 1 < ntiles) issue(ti + 1, slot ^ 1u, replay);
+            else if (more_passes) issue(0, slot ^ 1u, replay + 1);
         }
         mbar_wait(&bar[slot], (pass >> 1) & 1u);
-        return tile + slot * MC_TILE;
+        return tile + slot * TILE;
     }
+    RBQ_DEV const int32_t* aux() const { return aux_tile + (pass & 1u) * TILE; }
     // `more`: another acquire() follows (the barrier protects the slot the next prefetch overwrites)
     RBQ_DEV void release(bool more = true) { if (more) __syncthreads(); ++pass; }
 };
+typedef PulsePipeT<MC_TILE> PulsePipe;
+constexpr int NOISE_TILE = 1024;
 
 // ---- statistics ---------------------------------------------------------------------------------------
 struct ThreadStats {
@@ -445,38 +457,66 @@ struct PinkGen {
     }
 };
 
-template <int K> RBQ_DEV void noise_tile(const double* __restrict__ tile, int len, double w, double p, double p2, double dt,
-                                         double ndi, int64_t noise_len, const double* __restrict__ row, PinkGen* pg,
-                                         double& time, int64_t& cur, double& qd, double* v) {
-    for (int j = 0; j < len; ++j) {
-        int64_t idx = (int64_t)floor(time * ndi);   // 0-based form of spin.jl:476
-        idx = idx < noise_len - 1 ? idx : noise_len - 1;
-        if (idx != cur) {                           // same `time` in every thread: uniform branch
-            cur = idx;
-            qd = w * (row ? row[idx] : pg->at(idx));
+// one normalised step with any x (used where a noise sample pushes x outside the polynomial's range)
+RBQ_DEV void general_step(double p, double q, double x, double* v) {
+    double c, s;
+    su2_general(x, c, s);
+    Prop<double> E{c, s * p, s * q};
+    prop_apply(E, v);
+}
+// `len` knots of one tile.  idx[j] = noise-sample index of knot j (host-built table, same for every sample), the noise
+// amplitude is re-read only when the index changes (a warp-uniform branch).  DEG > 0: tan form in batches of 4 knots.
+template <int DEG>
+RBQ_DEV void noise_tile(const double* __restrict__ tile, const int32_t* __restrict__ idx, int len, double w, double p, double p2,
+                        const double* __restrict__ row, PinkGen* pg, int32_t& cur, double& qd, double* v,
+                        const double (&cf)[(DEG > 0 ? DEG : 1) + 1], double xmax) {
+    int j = 0;
+    if (DEG > 0) {
+        for (; j + 4 <= len; j += 4) {
+            double q[4], x[4], t[4];
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int32_t iu = idx[j + u];
+                if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); }
+                q[u] = fma(w, tile[j + u], qd);
+                x[u] = fma(q[u], q[u], p2);
+                ok = ok && (x[u] <= xmax);
+            }
+            if (ok) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = fma(cf[DEG], x[u], cf[DEG - 1]);
+#pragma unroll
+                for (int k = DEG - 2; k >= 0; --k)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = fma(t[u], x[u], cf[k]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tan_apply(t[u] * p, t[u] * q[u], v);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) general_step(p, q[u], x[u], v);
+            }
         }
+    }
+    for (; j < len; ++j) {
+        const int32_t iu = idx[j];
+        if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); }
         const double q = fma(w, tile[j], qd);
-        const double x = fma(q, q, p2);
-        double c, s;
-        // the noise is unbounded a priori: leave the short series when a sample steps outside its range
-        if (K > 0 && !(x <= (K == 5 ? 4.0e-2 : 0.7))) su2_coeffs<0>(x, c, s);
-        else su2_coeffs<K>(x, c, s);
-        Prop<double> E{c, s * p, s * q};
-        prop_apply(E, v);
-        time = time + dt;                            // accumulated exactly like spin.jl:480
+        general_step(p, q, fma(q, q, p2), v);
     }
 }
 
 template <int ALGO>
 __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs a) {
-    __shared__ __align__(128) double tile_s[2 * MC_TILE];
+    __shared__ __align__(128) double tile_s[2 * NOISE_TILE];
+    __shared__ __align__(128) int32_t idx_s[2 * NOISE_TILE];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
-    PulsePipe pipe;
-    pipe.init(tile_s, bar_s, a.controls, a.nk);
+    PulsePipeT<NOISE_TILE> pipe;
+    pipe.init(tile_s, bar_s, a.controls, a.nk, idx_s, a.idx_table, a.idx_stride);
 
     const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
     const bool live = s < a.S;
@@ -491,13 +531,14 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
 #pragma unroll
         for (int c = 0; c < 4; ++c) psi0[c] = a.psi0[4 * sc + c];
     } else sample_psi0((uint64_t)(a.first + sc), a.seed, psi0);
-    // series class from the noiseless pulse with head-room; noise_tile re-checks every step
+    // propagator class from the noiseless pulse with head-room; noise_tile re-checks x at every knot
     int cls;
     {
         const double qb = w * (*a.amax) * 1.05;
         const double xb = fma(qb, qb, p2);
-        cls = xb == xb ? max(degree_class(xb), 1) : 3;
+        cls = xb == xb ? degree_class(xb) : 3;
     }
+    const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS, cf0[2] = {0.0, 0.0};
     double tg[4][4], st[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { tg[0][i] = psi0[i]; st[i] = psi0[i]; }
@@ -507,35 +548,33 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
     double f = fidelity_vec_iso2(st, tg[0]);
     if (frow) frow[0] = f;
     const double norm0 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
-    double time = 0.0, qd = 0.0;
-    int64_t cur = -1;
+    double qd = 0.0;
+    int32_t cur = -1;
     for (int64_t g = 1; g <= a.gate_count; ++g) {
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
-            const double* tile = pipe.acquire(ti, g < a.gate_count);
+            const double* tile = pipe.acquire(ti, g < a.gate_count, g - 1);
+            const int32_t* idx = pipe.aux();
             const int len = pipe.tile_len(ti);
             if (ALGO == RBQ_ALGO_SU2) {
-                if (cls == 1) noise_tile<5>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
-                else if (cls == 2) noise_tile<8>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
-                else noise_tile<0>(tile, len, w, p, p2, a.dt, a.noise_dt_inv, a.noise_len, row, &pg, time, cur, qd, st);
+                if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cfA, RBQ_TANA_XMAX);
+                else if (cls == 1) noise_tile<RBQ_TANB_DEG>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cfB, RBQ_TANB_XMAX);
+                else noise_tile<0>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cf0, 0.0);
+                // unitary evolution preserves the norm: shed the tan form's 1/cos growth and the radial rounding
+                const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+                const double sc2 = sqrt(norm0 / n2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st[i] *= sc2;
             } else {
                 for (int j = 0; j < len; ++j) {
-                    int64_t idx = (int64_t)floor(time * a.noise_dt_inv);
-                    idx = idx < a.noise_len - 1 ? idx : a.noise_len - 1;
-                    if (idx != cur) { cur = idx; qd = w * (row ? row[idx] : pg.at(idx)); }
+                    const int32_t iu = idx[j];
+                    if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg.at(iu)); }
                     double G[16], X[16];
                     generator4(p, fma(w, tile[j], qd), G);
                     expm4_pade(G, X);
                     mv4(X, st);
-                    time = time + a.dt;
                 }
             }
             pipe.release(g < a.gate_count || ti + 1 < pipe.ntiles);
-        }
-        if (ALGO == RBQ_ALGO_SU2) {   // unitary evolution preserves the norm; shed the accumulated radial rounding
-            const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
-            const double sc = sqrt(norm0 / n2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) st[i] *= sc;
         }
         const int k = (int)(g & 3);
         f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
