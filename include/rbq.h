@@ -125,6 +125,11 @@ const char* rbq_last_error(const rbq_handle* h);
 /* cuda_stream = a cudaStream_t (NULL = the legacy default stream). */
 int rbq_set_stream(rbq_handle* h, void* cuda_stream);
 int rbq_synchronize(rbq_handle* h);
+/* Page-locked host memory for the caller's buffers (e.g. the nabla-f storage a Julia caller hands to rbq_jacobians):
+ * host-pointer entry points accept any host memory, but copies from/to pinned memory run at full PCIe rate and let the
+ * chunked sweeps overlap upload, compute and download.  Free with rbq_host_free. */
+int rbq_host_alloc(rbq_handle* h, int64_t bytes, void** out);
+int rbq_host_free(rbq_handle* h, void* ptr);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`). */
 int64_t rbq_launch_count(const rbq_handle* h);
 

@@ -84,6 +84,8 @@ SIGNATURES = {
     "rbq_last_error": (C.c_char_p, [_P]),
     "rbq_set_stream": (C.c_int, [_P, _P]),
     "rbq_synchronize": (C.c_int, [_P]),
+    "rbq_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
+    "rbq_host_free": (C.c_int, [_P, _P]),
     "rbq_launch_count": (_I64, [_P]),
     "rbq_state_dim": (C.c_int, [_MP]),
     "rbq_control_dim": (C.c_int, [_MP]),

@@ -167,6 +167,19 @@ int rbq_synchronize(rbq_handle* h) {
     return RBQ_OK;
 }
 int64_t rbq_launch_count(const rbq_handle* h) { return h ? h->launches : -1; }
+int rbq_host_alloc(rbq_handle* h, int64_t bytes, void** out) {
+    ENTER(h);
+    if (!out) return fail(h, RBQ_E_NULL, "rbq_host_alloc: null pointer");
+    *out = nullptr;
+    if (bytes <= 0) return fail(h, RBQ_E_SIZE, "rbq_host_alloc: bytes=%lld", (long long)bytes);
+    CK(cudaMallocHost(out, (size_t)bytes));
+    return RBQ_OK;
+}
+int rbq_host_free(rbq_handle* h, void* ptr) {
+    ENTER(h);
+    if (ptr) CK(cudaFreeHost(ptr));
+    return RBQ_OK;
+}
 
 int rbq_state_dim(const rbq_model_params* p) { return p ? model_state_dim(*p) : RBQ_E_NULL; }
 int rbq_control_dim(const rbq_model_params* p) { return p ? model_control_dim(*p) : RBQ_E_NULL; }

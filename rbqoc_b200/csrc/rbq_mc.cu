@@ -594,12 +594,12 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
 // the real 3x3 equivalent of the complex 4x4 vec-Liouvillian the reference exponentiates.  exp(M dt) v is
 // summed as a Taylor series whose length comes from a bound on ||M dt||.
 struct BlochGen { double wz, wx, g2, g1; };
-template <int NV> RBQ_DEV void bloch_advance(const BlochGen& m, int kmax, double (&r)[NV][3]) {
+template <int NV> RBQ_DEV void bloch_advance(const BlochGen& m, int kmax, const double* __restrict__ invk, double (&r)[NV][3]) {
     double t[NV][3];
 #pragma unroll
     for (int c = 0; c < NV; ++c) { t[c][0] = r[c][0]; t[c][1] = r[c][1]; t[c][2] = r[c][2]; }
     for (int k = 1; k <= kmax; ++k) {
-        const double ik = 1.0 / (double)k;
+        const double ik = invk[k];   // 1/k from shared memory: a division per term would cost more than the term
         const double wz = m.wz * ik, wx = m.wx * ik, g2 = m.g2 * ik, g1 = m.g1 * ik;
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
@@ -636,8 +636,10 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
     __shared__ int kmax_s;
+    __shared__ double invk_s[64];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
     if (tid == 0) kmax_s = 1;
     PulsePipe pipe;
     pipe.init(tile_s, bar_s, a.controls, a.nk);
@@ -683,13 +685,15 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
         return m;
     };
 
-    if (!time_dep) {
+    // few gates: carry the state itself (1 vector per knot and gate); many gates: compose the one-gate map once (3 vectors)
+    const bool direct = time_dep || a.gate_count <= 3;
+    if (!direct) {
         // compose the one-gate map from its action on the three basis vectors, then apply it gate_count times
         double P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};   // P[c] = image of e_c
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
-            for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, P);
+            for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, invk_s, P);
             pipe.release(ti + 1 < pipe.ntiles);
         }
         for (int64_t g = 1; g <= a.gate_count; ++g) {
@@ -708,7 +712,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
             for (int ti = 0; ti < pipe.ntiles; ++ti) {
                 const double* tile = pipe.acquire(ti, g < a.gate_count);
                 const int len = pipe.tile_len(ti);
-                for (int j = 0; j < len; ++j, ++step) bloch_advance<1>(generator(tile[j], ((double)step + 0.5) * a.dt), kmax, rr);
+                for (int j = 0; j < len; ++j, ++step) bloch_advance<1>(generator(tile[j], ((double)step + 0.5) * a.dt), kmax, invk_s, rr);
                 pipe.release(g < a.gate_count || ti + 1 < pipe.ntiles);
             }
             const int k = (int)(g & 3);

@@ -4,6 +4,8 @@
 //   jacobians         [A_k B_k] for every knot in one launch; forward-mode tangents written by hand
 //                     (Tan<NT>), replacing RD's default ForwardDiff.jacobian over [x;u]
 // Reference step maps: see rbq_models.cuh.  sm_100a only.
+#include <stdlib.h>
+
 #include "rbq_internal.h"
 #include "rbq_models.cuh"
 #include "rbq_warp_rollout.cuh"
@@ -69,6 +71,38 @@ __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int 
     model_step<MODEL, Tan<NT>>(p, io, dt[k]);
 }
 
+// Same computation, but a block stages the [A_k B_k] blocks of G consecutive knots in shared memory and writes them out
+// with fully coalesced stores (the direct kernel's lanes each scatter 8-byte elements n*NT*8 bytes apart).
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(256) jacobians_staged_kernel(rbq_model_params p, int n, int m, int lanes_per_knot, int G,
+                                                               int64_t K, const double* __restrict__ X,
+                                                               const double* __restrict__ U, const double* __restrict__ dt,
+                                                               double* __restrict__ AB) {
+    extern __shared__ __align__(16) double stage[];
+    const int blk = n * (n + m);
+    const int64_t k0 = (int64_t)blockIdx.x * G;
+    const int g = threadIdx.x / lanes_per_knot;
+    const int lane = threadIdx.x - g * lanes_per_knot;
+    const int64_t k = k0 + g;
+    if (g < G && k < K) {
+        TangentIO<NT> io{X + k * n, U + k * m, stage + (size_t)g * blk, n, n + m, lane * NT};
+        model_step<MODEL, Tan<NT>>(p, io, dt[k]);
+    }
+    __syncthreads();
+    const int64_t here = (K - k0) < G ? (K - k0) : G;
+    const int64_t total = here * blk;
+    double* __restrict__ dst = AB + k0 * blk;
+    if (((k0 * blk) & 1) == 0) {                       // 16-byte aligned destination: 2 doubles per store
+        const int64_t pairs = total >> 1;
+        const double2* __restrict__ s2 = reinterpret_cast<const double2*>(stage);
+        double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+        for (int64_t i = threadIdx.x; i < pairs; i += blockDim.x) d2[i] = s2[i];
+        if ((total & 1) && threadIdx.x == 0) dst[total - 1] = stage[total - 1];
+    } else {
+        for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+    }
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
 static inline int family(int model_id) {
     switch (model_id) {
@@ -127,6 +161,9 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
     return (int)cudaGetLastError();
 }
 
+static const int JAC_STAGE_BYTES = 200 * 1024;   // shared memory a staging block may use (227 KB per SM on sm_100)
+static const int64_t JAC_STAGED_MIN_KNOTS = 4096;  // below this the launch is latency bound and the direct kernel is as fast
+
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_dt, double* d_AB) {
     const int n = model_state_dim(p), m = model_control_dim(p);
@@ -135,21 +172,48 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
     const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
     const int lpk = (n + m + nt - 1) / nt;
-    const int threads = 128;
-    const int64_t total = K * lpk;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const int blk_bytes = n * (n + m) * (int)sizeof(double);
+    int G = JAC_STAGE_BYTES / blk_bytes;
+    if (G > 256 / lpk) G = 256 / lpk;
+    const char* force = getenv("RBQ_JAC_STAGED");
+    const bool staged = G >= 1 && (force ? atoi(force) != 0 : K >= JAC_STAGED_MIN_KNOTS);
+    if (staged) {
+        const int threads = ((G * lpk + 31) / 32) * 32;
+        const unsigned blocks = (unsigned)((K + G - 1) / G);
+        const size_t smem = (size_t)G * blk_bytes;
+#define CALLS(M, NT_)                                                                                                          \
+    {                                                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(jacobians_staged_kernel<M, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                             JAC_STAGE_BYTES);                                                                 \
+        if (e != cudaSuccess) return (int)e;                                                                                   \
+        jacobians_staged_kernel<M, NT_><<<blocks, threads, smem, h->stream>>>(p, n, m, lpk, G, K, d_X, d_U, d_dt, d_AB);       \
+    }
+        switch (fam) {
+        case RBQ_MODEL_SPIN13: CALLS(RBQ_MODEL_SPIN13, 4); break;
+        case RBQ_MODEL_SPIN15: CALLS(RBQ_MODEL_SPIN15, 4); break;
+        case RBQ_MODEL_SPIN11: CALLS(RBQ_MODEL_SPIN11, 4); break;
+        case RBQ_MODEL_SPIN12: CALLS(RBQ_MODEL_SPIN12, 2); break;
+        case RBQ_MODEL_SPIN30: CALLS(RBQ_MODEL_SPIN30, 2); break;
+        default: return RBQ_E_MODEL;
+        }
+#undef CALLS
+    } else {
+        const int threads = 128;
+        const int64_t total = K * lpk;
+        const unsigned blocks = (unsigned)((total + threads - 1) / threads);
 #define CALL2(M) jacobians_kernel<M, 2><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
 #define CALL4(M) jacobians_kernel<M, 4><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
-    switch (fam) {
-    case RBQ_MODEL_SPIN13: CALL4(RBQ_MODEL_SPIN13); break;
-    case RBQ_MODEL_SPIN15: CALL4(RBQ_MODEL_SPIN15); break;
-    case RBQ_MODEL_SPIN11: CALL4(RBQ_MODEL_SPIN11); break;
-    case RBQ_MODEL_SPIN12: CALL2(RBQ_MODEL_SPIN12); break;
-    case RBQ_MODEL_SPIN30: CALL2(RBQ_MODEL_SPIN30); break;
-    default: return RBQ_E_MODEL;
-    }
+        switch (fam) {
+        case RBQ_MODEL_SPIN13: CALL4(RBQ_MODEL_SPIN13); break;
+        case RBQ_MODEL_SPIN15: CALL4(RBQ_MODEL_SPIN15); break;
+        case RBQ_MODEL_SPIN11: CALL4(RBQ_MODEL_SPIN11); break;
+        case RBQ_MODEL_SPIN12: CALL2(RBQ_MODEL_SPIN12); break;
+        case RBQ_MODEL_SPIN30: CALL2(RBQ_MODEL_SPIN30); break;
+        default: return RBQ_E_MODEL;
+        }
 #undef CALL2
 #undef CALL4
+    }
     h->launches++;
     return (int)cudaGetLastError();
 }

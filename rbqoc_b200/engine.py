@@ -42,6 +42,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr in getattr(self, "_pinned", []):
+                self._lib.rbq_host_free(self._h, ptr)
+            self._pinned = []
             self._lib.rbq_destroy(self._h)
             self._h = None
 
@@ -72,6 +75,18 @@ class Engine:
 
     def synchronize(self):
         self._ck(self._lib.rbq_synchronize(self._h), "rbq_synchronize")
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array backed by page-locked memory from rbq_host_alloc (freed when the array's owner is collected)."""
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        self._ck(self._lib.rbq_host_alloc(self._h, max(nbytes, 1), C.byref(ptr)), "rbq_host_alloc")
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        return arr
 
     @property
     def launch_count(self) -> int:
@@ -125,8 +140,10 @@ class Engine:
         single = x0.ndim == 1
         x0b = x0.reshape(-1, n)
         B = x0b.shape[0]
-        Ub = U.reshape(B, -1, m)
-        N = Ub.shape[1] + 1
+        if U.ndim < 2:
+            raise ValueError("U must be (N-1, m) or (B, N-1, m)")
+        N = U.shape[-2] + 1
+        Ub = U.reshape(B, N - 1, m)
         if dt.shape != (N - 1,):
             raise ValueError("dt must have N-1 entries")
         X = np.empty((B, N, n))

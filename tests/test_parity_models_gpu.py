@@ -190,6 +190,48 @@ def test_rollout_large_batch_uses_thread_per_trajectory(engine, oracle):
     assert _relerr(X[idx], Xr) < 1e-13
 
 
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+def test_jacobians_staged_kernel_equals_direct(engine, oracle, name, model, monkeypatch):
+    """Large batches go through the shared-memory staged kernel (coalesced stores); same arithmetic, same bits."""
+    rng = np.random.default_rng(_seed(name, 21))
+    K = 301     # not a multiple of the knots-per-block of any model: exercises the ragged last block
+    pts = [_random_point(model, rng) for _ in range(K)]
+    X = np.stack([p[0] for p in pts])
+    U = np.stack([p[1] for p in pts])
+    dt = rng.choice([0.1, 0.01], K)
+    monkeypatch.setenv("RBQ_JAC_STAGED", "0")
+    direct = engine.jacobians(model.params, X, U, dt).copy()
+    monkeypatch.setenv("RBQ_JAC_STAGED", "1")
+    staged = engine.jacobians(model.params, X, U, dt).copy()
+    assert np.array_equal(direct, staged), name
+    ref = oracle.jacobians(model.params, X[:40], U[:40], dt[:40])
+    scale = np.max(np.abs(ref), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(staged[:40] - ref) / scale) < JAC_RTOL, name
+
+
+def test_pinned_host_buffers(engine):
+    model = spin.Spin13Model()
+    X = engine.pinned_empty((50, 11))
+    X[:] = np.tile(spin.spin13_x0(), (50, 1))
+    U = engine.pinned_empty((50, 1))
+    U[:] = 0.01
+    dt = engine.pinned_empty(50)
+    dt[:] = 0.1
+    AB = engine.jacobians(model.params, X, U, dt)
+    assert AB.shape == (50, 11, 12) and np.all(AB[:, 10, 11] == 0.1)
+
+
+def test_degenerate_sizes(engine):
+    """Empty and one-knot inputs (the edge cases a solver hits with N = 1 or an empty batch)."""
+    model = spin.Spin12Model()
+    X = engine.rollout(model.params, spin.spin12_x0(), np.empty((0, 1)), np.empty(0))
+    assert X.shape == (1, 43) and np.array_equal(X[0], spin.spin12_x0())
+    AB = engine.jacobians(model.params, np.empty((0, 43)), np.empty((0, 1)), np.empty(0))
+    assert AB.shape == (0, 43, 44)
+    Xb = engine.rollout(model.params, np.empty((0, 43)), np.empty((0, 3, 1)), np.full(3, 0.1))
+    assert Xb.shape == (0, 4, 43)
+
+
 def test_jacobian_structure_spin13(engine):
     """A = blkdiag(E, E, chain) + the d/da column; B = dt e_11."""
     model = spin.Spin13Model()
