@@ -40,25 +40,45 @@ BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 
 
 def sample_clocks(stop, out):
-    """One long-lived `nvidia-smi -lms 50` (spawning it per sample is too slow for a sub-second timed region)."""
+    """SM clock, max clock, power and throttle reasons every ~5 ms through NVML (nvidia-smi is too slow to start for a
+    sub-second timed region); rows mimic the nvidia-smi csv layout clocks_summary() reads."""
+    idx = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            r = reasons_fn(h)
+            out.append([str(idx), str(sm), str(mx), f"{pw:.1f}", hex(r)] +
+                       ["Active" if r & bits[k] else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            stop.wait(0.005)
+        return
+    except Exception:
+        pass
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    try:
-        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
-                                 os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except Exception:
-        return
-
-    def reader():
-        for line in proc.stdout:
-            out.append([c.strip() for c in line.split(",")])
-
-    t = threading.Thread(target=reader, daemon=True)
-    t.start()
-    stop.wait()
-    proc.terminate()
-    t.join(timeout=2)
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(idx)],
+                               capture_output=True, text=True, timeout=5)
+            for line in r.stdout.strip().splitlines():
+                out.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+        stop.wait(0.1)
 
 
 def clocks_summary(rows):
@@ -71,7 +91,9 @@ def clocks_summary(rows):
             for name, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+    pw = [float(r[3]) for r in rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -106,6 +128,57 @@ def cpu_reference_rate(orc, controls, n_threads, target_seconds=12.0):
     orc.mc_static(controls, DT, 1, GATE_COUNT, fq, da, psi, nthreads=n_threads)
     t = time.perf_counter() - t0
     return S * NK / t, S, t
+
+
+def other_configs(eng, rbq, spin, torch, dev):
+    """BASELINE configs[0..3] at their named sizes, for context next to the headline (not bench lines of their own):
+    what one ALTRO iteration's worth of hot-path calls costs through the host-pointer C ABI, and the Lindblad sweep."""
+    out = {}
+
+    def timed_host(fn, reps=5):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    N = 1001
+    for name, model, x0 in (("spin13", spin.Spin13Model(), spin.spin13_x0()), ("spin12", spin.Spin12Model(), spin.spin12_x0()),
+                            ("spin30", spin.Spin30Model(), spin.spin30_x0())):
+        n, m = model.n, model.m
+        dtv = np.full(N - 1, 0.1)
+        U = 1e-3 * np.sin(np.arange(N - 1) * 0.05)[:, None] * np.ones((1, m))
+        X = eng.rollout(model.params, x0, U, dtv)
+        K = 1e-3 * np.ones((N - 1, m, n))
+        d = 1e-4 * np.ones((N - 1, m))
+        alphas = 0.5 ** np.arange(8)
+        out[name] = {
+            "knots": N, "n": n,
+            "rollout_ms": timed_host(lambda: eng.rollout(model.params, x0, U, dtv)),
+            "jacobians_ms": timed_host(lambda: eng.jacobians(model.params, X[:-1], U, dtv)),
+            "closedloop_8_candidates_ms": timed_host(lambda: eng.rollout_closedloop(model.params, X, U, K, d, dtv, alphas)),
+            "api": "rbq_rollout / rbq_jacobians / rbq_rollout_closedloop, pageable host buffers, copies included",
+        }
+    S = 100_000
+    rng = np.random.default_rng(0)
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho0 = np.einsum("si,sj->sij", psi, psi.conj())
+    vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4)).view(np.float64)
+    controls = spin.pulse_sin(N)[:-1]
+    dcn, dda, drho = (torch.from_numpy(a).to(dev) for a in (controls, 2.574e-5 * rng.standard_normal(S), vec))
+    dfid = torch.empty(S, 2, dtype=torch.float64, device=dev)
+    dro = torch.empty(S, 8, dtype=torch.float64, device=dev)
+    dst = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
+
+    def lind():
+        eng.lindblad_dev(dcn, N - 1, 0.1, rbq.GATE_XPIBY2, 1, S, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst)
+        eng.synchronize()
+
+    ms = timed_host(lind)
+    out["lindblad_t1"] = {"realisations": S, "knots": N - 1, "gate_count": 1, "ms": ms, "density_steps_per_s": S * (N - 1) / ms * 1e3,
+                          "api": "rbq_lindblad_dev (device resident)"}
+    return out
 
 
 def run_reference(args):
@@ -168,6 +241,9 @@ def main():
     if world > 1:
         import torch.distributed as tdist
 
+        # NCCL prints its version banner to stdout at levels VERSION and WARN; the contract is ONE JSON line on stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         tdist.init_process_group("nccl", device_id=dev)
     S = args.samples
     first = rank * S                      # weak scaling: every rank owns S samples of the global index range
@@ -194,13 +270,55 @@ def main():
         d_fq.copy_(fq_p, non_blocking=True); d_da.copy_(da_p, non_blocking=True); d_psi0.copy_(psi0_p, non_blocking=True)
     stream.synchronize()
 
-    def device_step():
-        eng.stats_reset_dev(d_stats)
-        eng.mc_static_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_stats)
+    # N > 1: the all-gather of step i's 2.1 KB statistics, its copy to pinned host memory and the host merge run on a side
+    # stream / the host while step i+1's kernel computes (two rotating statistics buffers); every merge is complete
+    # before the timed region closes, and the tail after the last kernel is added to the device time.
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    W = rbq.STATS_INT64_WORDS
+    if world > 1:
+        with torch.cuda.stream(stream):
+            d_stats2 = [torch.zeros(W, dtype=torch.int64, device=dev) for _ in range(2)]
+            gathered = [torch.zeros(world * W, dtype=torch.int64, device=dev) for _ in range(2)]
+        pinned_g = [torch.zeros(world * W, dtype=torch.int64).pin_memory() for _ in range(2)]
+        done_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        pending = [False, False]
+    merged = {"last": None, "count": 0}
+
+    def collect(b):
+        """Host side of a finished exchange: wait for its pinned copy, merge the per-rank blocks in rank order."""
+        if not pending[b]:
+            return
+        done_ev[b].synchronize()
+        host = pinned_g[b].numpy().reshape(world, W)
+        total = rbq.stats_from_words(host[0])
+        for r in range(1, world):
+            rbq.stats_merge(total, rbq.stats_from_words(host[r]))
+        merged["last"] = total
+        merged["count"] += 1
+        pending[b] = False
+
+    def device_step(i=0):
+        if world == 1:
+            eng.stats_reset_dev(d_stats)
+            eng.mc_static_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_stats)
+            return
+        b = i & 1
+        collect(b)                                   # the exchange that last used this buffer (two steps ago)
+        eng.stats_reset_dev(d_stats2[b])
+        eng.mc_static_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_stats2[b])
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            tdist.all_gather_into_tensor(gathered[b], d_stats2[b])        # the one collective of the step
+            pinned_g[b].copy_(gathered[b], non_blocking=True)
+            done_ev[b].record(comm)
+        pending[b] = True
+
+    def drain():
         if world > 1:
-            with torch.cuda.stream(stream):
-                return rdist.allgather_merge_stats(d_stats)
-        return None
+            collect(0)
+            collect(1)
 
     def barrier():
         stream.synchronize()
@@ -213,25 +331,32 @@ def main():
     stop, rows = threading.Event(), []
     th = threading.Thread(target=sample_clocks, args=(stop, rows), daemon=True)
     th.start()
-    for _ in range(args.warmup):
+    for wi in range(args.warmup):
         with torch.cuda.stream(stream):
             flush.zero_()
-        device_step()
+        device_step(wi)
+    drain()
     barrier()
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
-    for a, b in ev:
+    merged["count"] = 0
+    for i, (a, b) in enumerate(ev):
         with torch.cuda.stream(stream):
             flush.zero_()
             a.record(stream)
-        device_step()
+        device_step(i)
         with torch.cuda.stream(stream):
             b.record(stream)
+    last_b = (args.steps - 1) & 1
+    drain()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        assert merged["count"] == args.steps, "every step's statistics must have been exchanged and merged"
+        dev_ms += max(0.0, ev[-1][1].elapsed_time(done_ev[last_b]))   # tail: last exchange after the last kernel
     # kernel-only time of the same step (no stats reset / collective): the roofline numerator's clock
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in kev:
@@ -267,7 +392,7 @@ def main():
         tdist.all_reduce(times, op=tdist.ReduceOp.MAX)
     dev_ms, e2e_ms, kern_ms = (float(x) for x in times.cpu())
     stream.synchronize()
-    st = rbq.stats_from_words(d_stats.cpu().numpy())
+    st = rbq.stats_from_words(d_stats.cpu().numpy())     # this rank's last single pass (kernel-only loop epilogue)
     if rank == 0:
         steps_per_step_all = float(world) * S * NK
         value = steps_per_step_all * args.steps / (dev_ms * 1e-3)
@@ -286,7 +411,8 @@ def main():
                                    f"S={S} samples per GPU (Philox keyed by global index; fq~N(0,1%) clipped 3%, "
                                    f"da~N(0,2.574e-5)), gate_count={GATE_COUNT}, per-sample fidelities + statistics",
                        "samples_per_gpu": S, "knots": NK, "algo": "su2 closed form (tan form, degree-6 polynomial)", "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "sharding": "contiguous sample ranges per rank, one all-gather of 2.1 KB statistics" if world > 1 else "single GPU"},
+                       "sharding": ("contiguous sample ranges per rank; per step ONE all-gather of the 2.1 KB statistics, copied to pinned host "
+                                    "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_tflops if peak_tflops else None, "traffic": None,
@@ -301,8 +427,14 @@ def main():
                     "api": "rbq_mc_static (host pointers, pinned)"},
             "gpu_launches": launches,
             "clocks": clocks_summary(rows),
-            "result": {"mean_infidelity": st.mean, "count": st.count},
+            "result": {"mean_infidelity": st.mean, "count": st.count,
+                       "merged_count_all_ranks": merged["last"].count if merged["last"] is not None else None},
         }
+        if world == 1:
+            try:
+                line["other_configs"] = other_configs(eng, rbq, spin, torch, dev)
+            except Exception as exc:   # context only: never let it break the contract line
+                line["other_configs"] = {"error": repr(exc)}
         if not args.no_cpu_baseline:
             from oracle import oracle as orc
 
