@@ -386,6 +386,21 @@ def main():
     stop.set()
     th.join(timeout=2)
 
+    # raw PCIe rates from the same pinned buffers: the ceiling of the explicit-sample e2e path (48 B up, 16 B down per sample)
+    def copy_rate(dst, src, reps=5):
+        with torch.cuda.stream(stream):
+            dst.copy_(src, non_blocking=True)
+        stream.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                dst.copy_(src, non_blocking=True)
+        stream.synchronize()
+        return src.numel() * src.element_size() * reps / (time.perf_counter() - t0) * 1e-9
+
+    h2d_gbs = copy_rate(d_psi0, psi0_p)
+    d2h_gbs = copy_rate(fid_p, d_fid)
+
     # ---- reduce over ranks (max time), print on rank 0 ----
     times = torch.tensor([dev_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -424,7 +439,9 @@ def main():
                                  "note": "algorithmic bytes; shows the path is not HBM bound"}},
             "e2e": {"value": steps_per_step_all / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
                     "h2d_bytes_per_step": S * 48 + NK * 8, "d2h_bytes_per_step": S * 16 + 2096, "ms_per_step": e2e_ms,
-                    "api": "rbq_mc_static (host pointers, pinned)"},
+                    "api": "rbq_mc_static (host pointers, pinned)",
+                    "pcie_measured": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
+                                      "h2d_floor_ms": (S * 48 + NK * 8) / (h2d_gbs * 1e6) if h2d_gbs else None}},
             "gpu_launches": launches,
             "clocks": clocks_summary(rows),
             "result": {"mean_infidelity": st.mean, "count": st.count,

@@ -332,25 +332,32 @@ int rbq_stats_merge(rbq_stats* a, const rbq_stats* b) {
     return RBQ_OK;
 }
 
+// stage the pulse and fill everything of McStaticArgs that does not depend on the sample range
+static int mc_static_prepare(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
+                             int64_t partial_blocks, rbq_stats* d_stats, McStaticArgs* a) {
+    memset(a, 0, sizeof(*a));
+    if (!make_gate_tables(gate, &a->gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
+    CKL(stage_pulse(h, d_controls, nk, &a->controls, &a->amax));
+    a->nk = nk; a->dt = dt; a->gate_count = gate_count;
+    if (d_stats) {
+        void* pp;
+        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * (size_t)(partial_blocks > 0 ? partial_blocks : 1), &pp));
+        a->partials = (BlockPartial*)pp;
+        a->hist = (unsigned long long*)d_stats->hist;
+    }
+    return 0;
+}
 static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
                           int64_t first, int64_t S, const double* d_fq, const double* d_da, const double* d_psi0, int philox,
                           uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip, double da_sigma, int algo,
                           double* d_fid, rbq_stats* d_stats) {
     McStaticArgs a;
-    memset(&a, 0, sizeof(a));
-    if (!make_gate_tables(gate, &a.gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
-    if (S == 0) return RBQ_OK;
-    CKL(stage_pulse(h, d_controls, nk, &a.controls, &a.amax));
-    a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S;
+    if (S == 0) { GateIso gi; return make_gate_tables(gate, &gi, nullptr) ? RBQ_OK : fail(h, RBQ_E_GATE, "unknown gate %d", gate); }
+    CKL(mc_static_prepare(h, d_controls, nk, dt, gate, gate_count, mc_static_blocks(h, S, algo), d_stats, &a));
+    a.first = first; a.S = S;
     a.fq = d_fq; a.da = d_da; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.fq0 = fq0; a.fq_rel_sigma = fq_rel_sigma; a.fq_rel_clip = fq_rel_clip; a.da_sigma = da_sigma;
     a.fid = d_fid;
-    if (d_stats) {
-        void* pp;
-        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * mc_static_blocks(h, S, algo), &pp));
-        a.partials = (BlockPartial*)pp;
-        a.hist = (unsigned long long*)d_stats->hist;
-    }
     int nblocks = 0;
     CKL(launch_mc_static(h, a, algo, &nblocks));
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
@@ -374,9 +381,14 @@ int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nk
                           fq_rel_sigma, fq_rel_clip, da_sigma, algo, d_fid, d_stats);
 }
 
-// host-pointer sweep: samples are streamed through the device in chunks so that the H2D copy of chunk
-// c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
-static const int64_t MC_CHUNK = 1 << 18;
+// host-pointer sweep: samples are streamed through the device in chunks so that the H2D copy of chunk c+1, the kernel
+// of chunk c and the D2H copy of chunk c-1 overlap; the pulse is staged once and the statistics finalised once.
+// chunk c covers [mc_chunk_begin(c), mc_chunk_begin(c+1)): one wave of resident blocks first (compute starts early),
+// two waves afterwards
+static inline int64_t mc_chunk_begin(int64_t c, int64_t wave, int64_t S) {
+    const int64_t b = c == 0 ? 0 : wave * (2 * c - 1);
+    return b < S ? b : S;
+}
 int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
                   const double* fq, const double* da, const double* psi0, int algo, double* fid, rbq_stats* stats) {
     ENTER(h);
@@ -394,28 +406,43 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
     if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
     if (S > 0) {
+        const int64_t wave = mc_static_wave_samples(h, algo);
+        int64_t nchunks = 0;
+        while (mc_chunk_begin(nchunks, wave, S) < S) ++nchunks;
+        int64_t total_blocks = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t s0 = mc_chunk_begin(c, wave, S), cnt = mc_chunk_begin(c + 1, wave, S) - s0;
+            total_blocks += mc_static_blocks(h, cnt, algo);
+        }
+        McStaticArgs a;
+        CKL(mc_static_prepare(h, (double*)dc, nknots, dt, gate, gate_count, total_blocks, (rbq_stats*)dst, &a));
+        BlockPartial* partials0 = a.partials;
         // event choreography: copy_stream[0] uploads, h->stream computes, copy_stream[1] downloads
         cudaStream_t up = h->copy_stream[0], down = h->copy_stream[1];
         CK(cudaEventRecord(h->ev[0], h->stream));
         CK(cudaStreamWaitEvent(up, h->ev[0], 0));   // uploads start after earlier work on the buffers has drained
-        const int64_t nchunks = (S + MC_CHUNK - 1) / MC_CHUNK;
+        int64_t block_off = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
-            const int64_t s0 = c * MC_CHUNK, cnt = (S - s0) < MC_CHUNK ? (S - s0) : MC_CHUNK;
+            const int64_t s0 = mc_chunk_begin(c, wave, S), cnt = mc_chunk_begin(c + 1, wave, S) - s0;
             CK(cudaMemcpyAsync((double*)dfq + s0, fq + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
             if (da) CK(cudaMemcpyAsync((double*)dda + s0, da + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
             CK(cudaMemcpyAsync((double*)dpsi + 4 * s0, psi0 + 4 * s0, sizeof(double) * 4 * cnt, cudaMemcpyHostToDevice, up));
             CK(cudaEventRecord(h->ev[1 + (c & 1)], up));
             CK(cudaStreamWaitEvent(h->stream, h->ev[1 + (c & 1)], 0));
-            int rc = mc_static_core(h, (double*)dc, nknots, dt, gate, gate_count, 0, cnt, (double*)dfq + s0,
-                                    da ? (double*)dda + s0 : nullptr, (double*)dpsi + 4 * s0, 0, 0, 0, 0, 0, 0, algo,
-                                    fid ? (double*)dfid + s0 * G1 : nullptr, (rbq_stats*)dst);
-            if (rc) return rc;
+            a.first = 0; a.S = cnt;
+            a.fq = (double*)dfq + s0; a.da = da ? (double*)dda + s0 : nullptr; a.psi0 = (double*)dpsi + 4 * s0;
+            a.fid = fid ? (double*)dfid + s0 * G1 : nullptr;
+            if (partials0) a.partials = partials0 + block_off;
+            int nblocks = 0;
+            CKL(launch_mc_static(h, a, algo, &nblocks));
+            block_off += nblocks;
             if (fid) {
                 CK(cudaEventRecord(h->ev[3 + (c & 1)], h->stream));
                 CK(cudaStreamWaitEvent(down, h->ev[3 + (c & 1)], 0));
                 CK(cudaMemcpyAsync(fid + s0 * G1, (double*)dfid + s0 * G1, sizeof(double) * cnt * G1, cudaMemcpyDeviceToHost, down));
             }
         }
+        if (stats) CKL(launch_stats_finalize(h, partials0, (int)block_off, (rbq_stats*)dst));
         CK(cudaStreamSynchronize(down));
     }
     if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));

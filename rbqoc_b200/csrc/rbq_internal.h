@@ -71,6 +71,7 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);
+int64_t mc_static_wave_samples(const rbq_handle* h, int algo);
 int mc_noise_blocks(const rbq_handle* h, int64_t S);
 int lindblad_blocks(const rbq_handle* h, int64_t S);
 int launch_stats_finalize(rbq_handle* h, const BlockPartial* partials, int nblocks, rbq_stats* d_stats);

@@ -825,6 +825,14 @@ int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
     const int per = threads * spt;
     return (int)((S + per - 1) / per);
 }
+// samples one full wave of resident blocks of the closed-form kernel processes (chunk sizes of the streamed host
+// sweep are multiples of this, so that chunking adds no partially filled waves)
+int64_t mc_static_wave_samples(const rbq_handle* h, int algo) {
+    int spt, minb, threads;
+    static_variant((int64_t)1 << 40, h->sm_count, algo, &spt, &minb, &threads);
+    if (algo != RBQ_ALGO_SU2) { spt = 1; minb = 1; threads = 256; }
+    return (int64_t)h->sm_count * minb * threads * spt;
+}
 int mc_noise_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
 int lindblad_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
 
