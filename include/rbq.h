@@ -168,6 +168,19 @@ int rbq_rollout_dev(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t
 int rbq_jacobians_dev(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* d_X,
                       const double* d_U, const double* d_dt, double* d_AB);
 
+/* ---- cost-side primitives of the sampling objectives (first "next" row of the scope table):
+ *      gate_error_iso2, jacobian_gate_error_iso2, hessian_gate_error_iso2  (spin.jl:1040-1092), the per-knot terms of
+ *      the custom Cost of spin12.jl:59-161 / spin18.jl:58-160.
+ *  s1: K states of 4 doubles, consecutive states s1_stride doubles apart (so the caller can point into an augmented
+ *      trajectory X at a sample state's offset with stride n);  s2: K targets, s2_stride apart (0 = one shared target).
+ *  err[K]      1 - a^2 - b^2
+ *  grad[K*4]   d err / d s1            (may be NULL)
+ *  hess[K*16]  the constant-in-s1 4x4 matrix the reference returns (row-major; may be NULL) */
+int rbq_gate_error_expansion(rbq_handle* h, int64_t K, const double* s1, int64_t s1_stride, const double* s2,
+                             int64_t s2_stride, double* err, double* grad, double* hess);
+int rbq_gate_error_expansion_dev(rbq_handle* h, int64_t K, const double* d_s1, int64_t s1_stride, const double* d_s2,
+                                 int64_t s2_stride, double* d_err, double* d_grad, double* d_hess);
+
 /* ---- Monte-Carlo robustness evaluation: run_sim_prop(...; dynamics_type=schroed)
  *      (spin.jl:1553-1608 -> integrate_prop_schroed! spin.jl:438-452 -> compute_fidelities
  *      spin.jl:1198-1240), batched over S samples instead of one call per (parameter, seed).

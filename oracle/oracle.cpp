@@ -833,6 +833,26 @@ int orc_rollout_closedloop(const rbq_model_params* p, int64_t N, const double* X
     return 0;
 }
 
+// gate_error_iso2 / jacobian_gate_error_iso2 / hessian_gate_error_iso2, spin.jl:1040-1092 (row-major 4x4 Hessian)
+void orc_gate_error_expansion(const double* s1, const double* s2, double* err, double* grad, double* hess) {
+    const double a = s1[0] * s2[0] + s1[1] * s2[1] + s1[2] * s2[2] + s1[3] * s2[3];
+    const double b = -s1[2] * s2[0] - s1[3] * s2[1] + s1[0] * s2[2] + s1[1] * s2[3];
+    if (err) *err = 1 - a * a - b * b;
+    if (grad) {
+        const double a2 = 2 * a, b2 = 2 * b;
+        grad[0] = -a2 * s2[0] - b2 * s2[2];
+        grad[1] = -a2 * s2[1] - b2 * s2[3];
+        grad[2] = -a2 * s2[2] + b2 * s2[0];
+        grad[3] = -a2 * s2[3] + b2 * s2[1];
+    }
+    if (hess) {
+        const double d11 = -2 * s2[0] * s2[0] - 2 * s2[2] * s2[2], d12 = -2 * s2[0] * s2[1] - 2 * s2[2] * s2[3], d13 = 0;
+        const double d14 = 2 * s2[1] * s2[2] - 2 * s2[0] * s2[3], d22 = -2 * s2[1] * s2[1] - 2 * s2[3] * s2[3];
+        const double d23 = -2 * s2[1] * s2[2] + 2 * s2[0] * s2[3], d24 = 0, d33 = d11, d34 = d12, d44 = d22;
+        const double H[16] = {d11, d12, d13, d14, d12, d22, d23, d24, d13, d23, d33, d34, d14, d24, d34, d44};
+        for (int i = 0; i < 16; ++i) hess[i] = H[i];
+    }
+}
 double orc_fidelity_vec_iso2(const double* s1, const double* s2) { return fidelity_vec_iso2<double>(s1, s2); }
 // m1, m2: 2x2 complex row-major interleaved
 double orc_fidelity_mat(const double* m1, const double* m2, int closed) {

@@ -82,7 +82,7 @@ def lib():
         _lib.orc_t1_reduced_us.restype = C.c_double
         _lib.orc_t1_ns.argtypes = [C.c_double]
         _lib.orc_t1_reduced_us.argtypes = [C.c_double]
-        for name in ("orc_propagator", "orc_lindblad_generator", "orc_philox4x32_10", "orc_philox_samples",
+        for name in ("orc_gate_error_expansion", "orc_propagator", "orc_lindblad_generator", "orc_philox4x32_10", "orc_philox_samples",
                      "orc_pink_filter", "orc_pink_noise", "orc_stats"):
             getattr(_lib, name).restype = None
     return _lib
@@ -220,6 +220,15 @@ def fidelity_mat(m1, m2, closed=False):
     m1 = np.ascontiguousarray(m1, dtype=np.complex128)
     m2 = np.ascontiguousarray(m2, dtype=np.complex128)
     return lib().orc_fidelity_mat(_p(m1), _p(m2), int(closed))
+
+
+def gate_error_expansion(s1, s2):
+    """One state/target pair: (err, grad[4], hess[4,4]) per spin.jl:1040-1092."""
+    s1, s2 = _f64(s1), _f64(s2)
+    err = C.c_double()
+    grad, hess = np.empty(4), np.empty((4, 4))
+    lib().orc_gate_error_expansion(_p(s1), _p(s2), C.byref(err), _p(grad), _p(hess))
+    return err.value, grad, hess
 
 
 def gate_iso(gate):

@@ -300,6 +300,38 @@ int rbq_discrete_jacobian(rbq_handle* h, const rbq_model_params* p, const double
     return rbq_jacobians(h, p, 1, x, u, &dt, AB);
 }
 
+// ---- cost-side primitives ------------------------------------------------------------------------------------------
+int rbq_gate_error_expansion_dev(rbq_handle* h, int64_t K, const double* d_s1, int64_t s1_stride, const double* d_s2,
+                                 int64_t s2_stride, double* d_err, double* d_grad, double* d_hess) {
+    ENTER(h);
+    if (K < 0 || s1_stride < 4 || (s2_stride != 0 && s2_stride < 4)) return fail(h, RBQ_E_SIZE, "rbq_gate_error_expansion_dev: K=%lld strides %lld/%lld", (long long)K, (long long)s1_stride, (long long)s2_stride);
+    if (K == 0) return RBQ_OK;
+    if (!d_s1 || !d_s2) return fail(h, RBQ_E_NULL, "rbq_gate_error_expansion_dev: null pointer");
+    CKL(launch_gate_error(h, K, d_s1, s1_stride, d_s2, s2_stride, d_err, d_grad, d_hess));
+    return RBQ_OK;
+}
+int rbq_gate_error_expansion(rbq_handle* h, int64_t K, const double* s1, int64_t s1_stride, const double* s2, int64_t s2_stride,
+                             double* err, double* grad, double* hess) {
+    ENTER(h);
+    if (K < 0 || s1_stride < 4 || (s2_stride != 0 && s2_stride < 4)) return fail(h, RBQ_E_SIZE, "rbq_gate_error_expansion: K=%lld strides %lld/%lld", (long long)K, (long long)s1_stride, (long long)s2_stride);
+    if (K == 0) return RBQ_OK;
+    if (!s1 || !s2) return fail(h, RBQ_E_NULL, "rbq_gate_error_expansion: null pointer");
+    const size_t b1 = sizeof(double) * ((size_t)(K - 1) * s1_stride + 4), b2 = sizeof(double) * ((size_t)(K - 1) * s2_stride + 4);
+    void *d1, *d2, *de = nullptr, *dg = nullptr, *dh = nullptr;
+    CKL(dev_buf(h, B_IN0, b1, &d1)); CKL(dev_buf(h, B_IN1, b2, &d2));
+    if (err) CKL(dev_buf(h, B_OUT0, sizeof(double) * K, &de));
+    if (grad) CKL(dev_buf(h, B_OUT1, sizeof(double) * 4 * K, &dg));
+    if (hess) CKL(dev_buf(h, B_IN4, sizeof(double) * 16 * K, &dh));
+    CK(cudaMemcpyAsync(d1, s1, b1, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d2, s2, b2, cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_gate_error(h, K, (double*)d1, s1_stride, (double*)d2, s2_stride, (double*)de, (double*)dg, (double*)dh));
+    if (err) CK(cudaMemcpyAsync(err, de, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+    if (grad) CK(cudaMemcpyAsync(grad, dg, sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, h->stream));
+    if (hess) CK(cudaMemcpyAsync(hess, dh, sizeof(double) * 16 * K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
 // ---- Monte-Carlo sweeps ----------------------------------------------------------------------------------------
 static int check_mc(rbq_handle* h, const char* who, const void* controls, int64_t nk, double dt, int64_t gate_count, int64_t S,
                     int algo) {

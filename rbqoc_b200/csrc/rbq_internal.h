@@ -87,6 +87,8 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
 int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const double* d_Xref, const double* d_Uref,
                       const double* d_K, const double* d_d, const double* d_dt, int64_t nalpha, const double* d_alphas,
                       double* d_X, double* d_Uout);
+int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1, const double* d_s2, int64_t st2, double* d_err,
+                      double* d_grad, double* d_hess);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_dt, double* d_AB);
 

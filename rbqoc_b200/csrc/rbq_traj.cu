@@ -103,6 +103,44 @@ __global__ void __launch_bounds__(256) jacobians_staged_kernel(rbq_model_params 
     }
 }
 
+// gate_error_iso2 and its analytic gradient / Hessian (spin.jl:1040-1092), one thread per state
+__global__ void __launch_bounds__(256) gate_error_kernel(int64_t K, const double* __restrict__ s1, int64_t st1,
+                                                         const double* __restrict__ s2, int64_t st2, double* __restrict__ err,
+                                                         double* __restrict__ grad, double* __restrict__ hess) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double* x = s1 + k * st1;
+    const double* y = s2 + k * st2;
+    const double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+    const double a = fma(x3, y3, fma(x2, y2, fma(x1, y1, x0 * y0)));          // gate_error_iso2a
+    const double b = fma(x1, y3, fma(x0, y2, fma(-x3, y1, -x2 * y0)));        // gate_error_iso2b
+    if (err) err[k] = 1.0 - a * a - b * b;
+    if (grad) {
+        const double a2 = 2.0 * a, b2 = 2.0 * b;
+        double* g = grad + 4 * k;
+        g[0] = -a2 * y0 - b2 * y2;
+        g[1] = -a2 * y1 - b2 * y3;
+        g[2] = -a2 * y2 + b2 * y0;
+        g[3] = -a2 * y3 + b2 * y1;
+    }
+    if (hess) {
+        const double d11 = -2.0 * y0 * y0 - 2.0 * y2 * y2, d12 = -2.0 * y0 * y1 - 2.0 * y2 * y3;
+        const double d14 = 2.0 * y1 * y2 - 2.0 * y0 * y3, d22 = -2.0 * y1 * y1 - 2.0 * y3 * y3;
+        const double d23 = -2.0 * y1 * y2 + 2.0 * y0 * y3;
+        double* H = hess + 16 * k;
+        H[0] = d11; H[1] = d12; H[2] = 0.0; H[3] = d14;
+        H[4] = d12; H[5] = d22; H[6] = d23; H[7] = 0.0;
+        H[8] = 0.0; H[9] = d23; H[10] = d11; H[11] = d12;
+        H[12] = d14; H[13] = 0.0; H[14] = d12; H[15] = d22;
+    }
+}
+int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1, const double* d_s2, int64_t st2, double* d_err,
+                      double* d_grad, double* d_hess) {
+    gate_error_kernel<<<(unsigned)((K + 255) / 256), 256, 0, h->stream>>>(K, d_s1, st1, d_s2, st2, d_err, d_grad, d_hess);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
 static inline int family(int model_id) {
     switch (model_id) {

@@ -180,6 +180,22 @@ class Engine:
     def jacobians_dev(self, p, K, X, U, dt, AB):
         self._ck(self._lib.rbq_jacobians_dev(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(dt), _ptr(AB)), "rbq_jacobians_dev")
 
+    # ---- cost-side primitives (spin.jl:1040-1092) ---------------------------------------------------------------
+    def gate_error_expansion(self, s1, s2, want_grad=True, want_hess=True):
+        """s1 (K,4) states, s2 (K,4) or (4,) targets -> err (K,), grad (K,4), hess (K,4,4)."""
+        s1 = _f64(s1).reshape(-1, 4)
+        s2 = _f64(s2)
+        K = s1.shape[0]
+        st2 = 0 if s2.ndim == 1 else 4
+        if s2.ndim == 2 and s2.shape != (K, 4):
+            raise ValueError("s2 must be (4,) or (K,4)")
+        err = np.empty(K)
+        grad = np.empty((K, 4)) if want_grad else None
+        hess = np.empty((K, 4, 4)) if want_hess else None
+        self._ck(self._lib.rbq_gate_error_expansion(self._h, K, _ptr(s1), 4, _ptr(s2), st2, _ptr(err), _ptr(grad), _ptr(hess)),
+                 "rbq_gate_error_expansion")
+        return err, grad, hess
+
     # ---- Monte-Carlo sweeps ------------------------------------------------------------------------------
     def mc_static(self, controls, dt, gate, gate_count, fq, da, psi0, algo=_lib.ALGO_SU2, want_fid=True, want_stats=True,
                   fid_out=None):

@@ -314,6 +314,21 @@ def gen_rand_density(seed=0, engine: Engine | None = None):
     return np.outer(psi, psi.conj())
 
 
+# ---- cost-side primitives (spin.jl:1040-1092), batched ---------------------------------------------------------------
+def gate_error_iso2(s1, s2, engine: Engine | None = None):
+    return (engine or default_engine()).gate_error_expansion(s1, s2, want_grad=False, want_hess=False)[0]
+
+
+def jacobian_gate_error_iso2(s1, s2, engine: Engine | None = None):
+    return (engine or default_engine()).gate_error_expansion(s1, s2, want_hess=False)[1]
+
+
+def hessian_gate_error_iso2(s2, engine: Engine | None = None):
+    s2 = np.asarray(s2, dtype=np.float64)
+    s1 = np.zeros((1, 4)) if s2.ndim == 1 else np.zeros_like(s2)
+    return (engine or default_engine()).gate_error_expansion(s1, s2, want_grad=False)[2]
+
+
 # ---- simulation entry points (spin.jl:1553-1672), batched over samples -------------------------------------------
 @dataclass
 class SimResult:

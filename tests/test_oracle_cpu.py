@@ -133,6 +133,25 @@ def test_fidelity_and_cyclic_targets(orc):
     assert np.max(np.abs(fid - 1)) < 1e-13
 
 
+def test_gate_error_expansion_is_consistent(orc):
+    """gate_error_iso2 = 1 - fidelity_vec_iso2; the analytic gradient (spin.jl:1060-1071) matches central differences; the
+    reference's Hessian (spin.jl:1074-1092) is constant in s1 and symmetric."""
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        s1, s2 = rng.standard_normal(4), rng.standard_normal(4)
+        err, grad, hess = orc.gate_error_expansion(s1, s2)
+        assert err == pytest.approx(1 - orc.fidelity_vec_iso2(s1, s2), abs=1e-14)
+        h = 1e-6
+        fd = np.array([(orc.gate_error_expansion(s1 + h * e, s2)[0] - orc.gate_error_expansion(s1 - h * e, s2)[0]) / (2 * h)
+                       for e in np.eye(4)])
+        assert np.allclose(grad, fd, rtol=1e-6, atol=1e-7)
+        assert np.array_equal(hess, hess.T)
+        # second differences: the exact Hessian of 1 - a^2 - b^2 in s1 (what the closed form of spin.jl:1074-1092 encodes)
+        fd2 = np.array([(orc.gate_error_expansion(s1 + h * e, s2)[1] - orc.gate_error_expansion(s1 - h * e, s2)[1]) / (2 * h)
+                        for e in np.eye(4)])
+        assert np.allclose(hess, fd2, rtol=1e-6, atol=1e-7)
+
+
 def test_philox_known_answer(orc):
     """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
     assert list(orc.philox4x32_10([0, 0, 0, 0], [0, 0])) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]

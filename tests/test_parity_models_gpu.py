@@ -232,6 +232,30 @@ def test_degenerate_sizes(engine):
     assert Xb.shape == (0, 4, 43)
 
 
+def test_gate_error_expansion_matches_oracle(engine, oracle):
+    """Cost-side primitives (spin.jl:1040-1092): batched err / gradient / Hessian, per-knot targets or one shared target."""
+    rng = np.random.default_rng(12)
+    K = 1000
+    s1, s2 = rng.standard_normal((K, 4)), rng.standard_normal((K, 4))
+    err, grad, hess = engine.gate_error_expansion(s1, s2)
+    for k in range(0, K, 37):
+        e, g, h = oracle.gate_error_expansion(s1[k], s2[k])
+        assert abs(err[k] - e) < 1e-13 * max(1.0, abs(e))
+        assert np.max(np.abs(grad[k] - g)) < 1e-13 * max(1.0, np.max(np.abs(g)))
+        assert np.max(np.abs(hess[k] - h)) < 1e-13 * max(1.0, np.max(np.abs(h)))
+    tgt = spin.IS3_ISO
+    err1, grad1, hess1 = engine.gate_error_expansion(s1, tgt)
+    e, g, h = oracle.gate_error_expansion(s1[5], tgt)
+    assert abs(err1[5] - e) < 1e-13 and np.allclose(grad1[5], g, atol=1e-13) and np.allclose(hess1[5], h, atol=1e-13)
+    # mirrors of the reference names
+    assert np.allclose(spin.gate_error_iso2(s1[:3], tgt, engine=engine), err1[:3])
+    assert np.allclose(spin.jacobian_gate_error_iso2(s1[:3], tgt, engine=engine), grad1[:3])
+    assert np.allclose(spin.hessian_gate_error_iso2(tgt, engine=engine)[0], hess1[0])
+    # a state equal to its target has zero gate error and zero gradient component along the error
+    e0, _, _ = engine.gate_error_expansion(tgt[None, :], tgt)
+    assert abs(e0[0]) < 1e-15
+
+
 def test_jacobian_structure_spin13(engine):
     """A = blkdiag(E, E, chain) + the d/da column; B = dt e_11."""
     model = spin.Spin13Model()
