@@ -37,6 +37,10 @@ GATE_COUNT = 1
 FLOPS_PER_STEP_SU2 = 34.0
 FP64_INSTR_PER_STEP_SU2 = 18.0
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default sizes, from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_mc_static_full.csv (50.43 MB read + 0.40 MB written: the 16 MB of
+# fidelities stay in the 126 MB L2); algorithmic bytes are 48 MB in + 16 MB out
+NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_431_744 + 403_968
 
 
 def sample_clocks(stop, out):
@@ -430,7 +434,9 @@ def main():
                                     "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": ach_tflops / peak_tflops if peak_tflops else None, "traffic": None,
+                         "frac": ach_tflops / peak_tflops if peak_tflops else None,
+                         "traffic": NCU_DRAM_TRAFFIC_BYTES_DEFAULT if (S == S_PER_GPU) else None,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_ncu_mc_static_full.csv)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,

@@ -415,10 +415,11 @@ int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nk
 
 // host-pointer sweep: samples are streamed through the device in chunks so that the H2D copy of chunk c+1, the kernel
 // of chunk c and the D2H copy of chunk c-1 overlap; the pulse is staged once and the statistics finalised once.
-// chunk c covers [mc_chunk_begin(c), mc_chunk_begin(c+1)): one wave of resident blocks first (compute starts early),
-// two waves afterwards
+// chunk c covers [mc_chunk_begin(c), mc_chunk_begin(c+1)): whole waves of resident blocks, so chunking adds no partially
+// filled wave and the upload of wave c+1 hides behind the kernel of wave c
+static int g_chunk_first = 1, g_chunk_rest = 1;   // in waves (measured best: tools/tune_e2e.py); RBQ_MC_CHUNK_WAVES="<first>,<rest>" overrides (tuning aid)
 static inline int64_t mc_chunk_begin(int64_t c, int64_t wave, int64_t S) {
-    const int64_t b = c == 0 ? 0 : wave * (2 * c - 1);
+    const int64_t b = c == 0 ? 0 : wave * (g_chunk_first + g_chunk_rest * (c - 1));
     return b < S ? b : S;
 }
 int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
@@ -439,6 +440,10 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
     if (S > 0) {
         const int64_t wave = mc_static_wave_samples(h, algo);
+        if (const char* e = getenv("RBQ_MC_CHUNK_WAVES")) {
+            int a1 = 0, a2 = 0;
+            if (sscanf(e, "%d,%d", &a1, &a2) == 2 && a1 >= 1 && a2 >= 1) { g_chunk_first = a1; g_chunk_rest = a2; }
+        }
         int64_t nchunks = 0;
         while (mc_chunk_begin(nchunks, wave, S) < S) ++nchunks;
         int64_t total_blocks = 0;

@@ -75,6 +75,17 @@ def test_no_cpu_fallback():
     assert _lib.load().rbq_launch_count(None) == -1
 
 
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_plain_c_client_links_and_fails_loudly_without_a_device(tmp_path):
+    """tests/abi_client.c is what a ccall-style consumer looks like; without a GPU it must stop at rbq_create (-6)."""
+    exe = tmp_path / "abi_client"
+    libdir = os.path.join(ROOT, "rbqoc_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "abi_client.c"), "-I",
+                    os.path.join(ROOT, "include"), "-L", libdir, "-lrbq", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "rbq_create(0, &h) -> -6" in r.stderr and "version 100" in r.stdout
+
+
 def test_product_never_imports_the_oracle():
     """Only tests/, smoke() and bench.py's cpu legs may touch oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "rbqoc_b200")):
