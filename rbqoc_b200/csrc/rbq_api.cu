@@ -15,7 +15,7 @@
 using namespace rbq;
 
 // dbuf roles
-enum { B_PULSE = 0, B_PARTIALS, B_SCALARS, B_IN0, B_IN1, B_IN2, B_IN3, B_IN4, B_OUT0, B_OUT1, B_STATS, B_IN5, B_IDX };
+enum { B_PULSE = 0, B_PARTIALS, B_SCALARS, B_IN0, B_IN1, B_IN2, B_IN3, B_IN4, B_OUT0, B_OUT1, B_STATS, B_IN5, B_IDX, B_QUAT, B_NOISE };
 
 static int fail(rbq_handle* h, int code, const char* fmt, ...) {
     if (h) {
@@ -584,7 +584,25 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
         a.hist = (unsigned long long*)d_stats->hist;
     }
     int nblocks = 0;
-    CKL(launch_mc_noise(h, a, algo, &nblocks));
+    // Few samples, several gates: S chains of gate_count * nk dependent knots cannot fill the GPU, S * gate_count gate
+    // propagators can (see mc_noise_gate_kernel).  Large sweeps keep the single-kernel form (no scratch, same throughput).
+    bool gate_parallel = algo == RBQ_ALGO_SU2 && gate_count >= 2 && gate_count <= 65535 && S < (int64_t)h->sm_count * 4096 &&
+                         (double)S * (double)gate_count * 32.0 <= 2.0e9;
+    if (philox && (double)S * (double)noise_len * 8.0 > 2.0e9) gate_parallel = false;   // materialised noise rows must stay modest
+    if (const char* e = getenv("RBQ_NOISE_GATE_PARALLEL")) gate_parallel = gate_parallel && atoi(e) != 0;
+    if (gate_parallel) {
+        if (philox) {   // the pink filter is sequential in time: materialise each sample's noise row first
+            void* dn;
+            CKL(dev_buf(h, B_NOISE, sizeof(double) * (size_t)S * (size_t)noise_len, &dn));
+            CKL(launch_pink_noise(h, first, S, seed, namp, noise_dt_inv, noise_len, (double*)dn));
+            a.noise = (const double*)dn;
+        }
+        void* dq;
+        CKL(dev_buf(h, B_QUAT, sizeof(double) * 4 * (size_t)S * (size_t)gate_count, &dq));
+        CKL(launch_mc_noise_gate_parallel(h, a, (double*)dq, &nblocks));
+    } else {
+        CKL(launch_mc_noise(h, a, algo, &nblocks));
+    }
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
     return RBQ_OK;
 }

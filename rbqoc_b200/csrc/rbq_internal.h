@@ -6,7 +6,7 @@
 
 #include "../../include/rbq.h"
 
-#define RBQ_NBUF 14
+#define RBQ_NBUF 16
 
 struct rbq_handle {
     int device;
@@ -69,6 +69,7 @@ struct LindbladArgs {
 int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax);
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
+int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);
 int64_t mc_static_wave_samples(const rbq_handle* h, int algo);

@@ -62,12 +62,12 @@ struct PulsePipeT {
     int ntiles;
     uint32_t pass;
     RBQ_DEV void init(double* t, uint64_t* b, const double* s, int64_t n, int32_t* at = nullptr, const int32_t* as = nullptr,
-                      int64_t astride = 0) {
+                      int64_t astride = 0, int64_t replay0 = 0) {
         tile = t; bar = b; src = s; nk = n; pass = 0; aux_tile = at; aux_src = as; aux_stride = astride;
         ntiles = (int)((n + TILE - 1) / TILE);
         if (threadIdx.x == 0) {
             mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init();
-            if (n > 0) issue(0, 0, 0);     // the first tile is in flight while the block loads its samples
+            if (n > 0) issue(0, 0, replay0);     // the first tile is in flight while the block loads its samples
         }
         __syncthreads();
     }
@@ -588,6 +588,93 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
     }
 }
 
+// Gate-parallel form of the same sweep for small sample counts: the evolution over one gate is an SU(2) element whatever
+// the state, so thread (sample s, gate g) composes gate g's propagator as a quaternion (S x G independent units instead of
+// S chains of G x N dependent knots), and a second kernel multiplies each sample's G quaternions in order and evaluates the
+// fidelities.  The reference's largest workload (figures.jl gen_3b: 1000 seeds x 200 gates x 5680 knots) has S = 1000.
+__global__ void __launch_bounds__(MC_THREADS) mc_noise_gate_kernel(const McNoiseArgs a, double* __restrict__ quat) {
+    __shared__ __align__(128) double tile_s[2 * NOISE_TILE];
+    __shared__ __align__(128) int32_t idx_s[2 * NOISE_TILE];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    const int64_t g = blockIdx.y;
+    PulsePipeT<NOISE_TILE> pipe;
+    pipe.init(tile_s, bar_s, a.controls, a.nk, idx_s, a.idx_table, a.idx_stride, g);
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double w = RBQ_PI * a.dt;
+    const double p = w * a.fq, p2 = p * p;
+    const double* row = a.noise + sc * a.noise_len;
+    int cls;
+    {
+        const double qb = w * (*a.amax) * 1.05;
+        const double xb = fma(qb, qb, p2);
+        cls = xb == xb ? degree_class(xb) : 3;
+    }
+    const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS, cf0[2] = {0.0, 0.0};
+    double v[4] = {1.0, 0.0, 0.0, 0.0}, qd = 0.0;
+    int32_t cur = -1;
+    for (int ti = 0; ti < pipe.ntiles; ++ti) {
+        const double* tile = pipe.acquire(ti, false, g);
+        const int32_t* idx = pipe.aux();
+        const int len = pipe.tile_len(ti);
+        if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cfA, RBQ_TANA_XMAX);
+        else if (cls == 1) noise_tile<RBQ_TANB_DEG>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cfB, RBQ_TANB_XMAX);
+        else noise_tile<0>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cf0, 0.0);
+        const double inv = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] *= inv;
+        pipe.release(ti + 1 < pipe.ntiles);
+    }
+    if (live) {
+        double* q = quat + (s * a.gate_count + g) * 4;
+        q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = v[3];
+    }
+}
+__global__ void __launch_bounds__(MC_THREADS) mc_noise_combine_kernel(const McNoiseArgs a, const double* __restrict__ quat) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    double psi0[4];
+    if (a.psi0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) psi0[c] = a.psi0[4 * sc + c];
+    } else sample_psi0((uint64_t)(a.first + sc), a.seed, psi0);
+    double tg[4][4], st[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { tg[0][i] = psi0[i]; st[i] = psi0[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv4_to(a.gate.g[k], psi0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (a.gate_count + 1) : nullptr;
+    double f = fidelity_vec_iso2(st, tg[0]);
+    if (frow) frow[0] = f;
+    const double norm0 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+    for (int64_t g = 1; g <= a.gate_count; ++g) {
+        const double* q = quat + (sc * a.gate_count + (g - 1)) * 4;
+        double E[16];
+        iso_from_column(q, E);
+        mv4(E, st);
+        const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+        const double sc2 = sqrt(norm0 / n2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[i] *= sc2;
+        const int k = (int)(g & 3);
+        f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+        if (frow) frow[g] = f;
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
 // ---- Lindblad T1 (+T2) rollout in the Bloch picture ------------------------------------------------------------
 // rho = (t I + r.sigma)/2.  With equal up/down rates gamma_1 (spin.jl:529-531) the map is unital:
 //   dr/dt = Omega x r - diag(g2, g2, g1) r,  Omega = 2 pi (a, 0, fq),  g2 = gamma_1 + Gamma(t), g1 = 2 gamma_1,
@@ -871,6 +958,17 @@ int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_
     else if (algo == RBQ_ALGO_PADE) mc_noise_kernel<RBQ_ALGO_PADE><<<blocks, MC_THREADS, 0, h->stream>>>(a);
     else return RBQ_E_ALGO;
     h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out) {
+    const int blocks = mc_noise_blocks(h, a.S);
+    if (nblocks_out) *nblocks_out = blocks;
+    if (a.gate_count > 65535) return RBQ_E_SIZE;
+    mc_noise_gate_kernel<<<dim3((unsigned)blocks, (unsigned)a.gate_count), MC_THREADS, 0, h->stream>>>(a, d_quat);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    mc_noise_combine_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_quat);
+    h->launches += 2;
     return (int)cudaGetLastError();
 }
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out) {

@@ -140,8 +140,11 @@ def test_mc_static_philox_equals_explicit_samples(engine):
     assert abs(m.sum - st_p.sum) < 1e-12 * st_p.sum
 
 
+@pytest.mark.parametrize("gate_parallel", ["0", "1"], ids=["sequential", "gate_parallel"])
 @pytest.mark.parametrize("algo", [rbq.ALGO_SU2, rbq.ALGO_PADE], ids=["su2", "pade"])
-def test_mc_noise_matches_oracle(engine, oracle, algo):
+def test_mc_noise_matches_oracle(engine, oracle, algo, gate_parallel, monkeypatch):
+    """Both forms of the sweep: one chain per sample, and (few samples) one gate propagator per (sample, gate)."""
+    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
     controls = spin.controls_ypiby2(100.0)
     dt, gate, gate_count, ndi = 0.01, rbq.GATE_YPIBY2, 3, 10.0
     S = 200
@@ -155,7 +158,9 @@ def test_mc_noise_matches_oracle(engine, oracle, algo):
     assert np.std(fid[:, -1]) > 0                  # the noise is actually felt
 
 
-def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle):
+@pytest.mark.parametrize("gate_parallel", ["0", "1"], ids=["sequential", "gate_parallel"])
+def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle, gate_parallel, monkeypatch):
+    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
     nlen = 500
     got = engine.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
     ref = oracle.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
@@ -166,9 +171,14 @@ def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle):
     nl = int(np.ceil(controls.shape[0] * dt * gc * 10.0)) + 1
     noise = engine.pink_noise(first, S, seed, namp, 10.0, nl)
     _, _, psi0 = engine.philox_samples(first, S, seed, spin.FQ, 0, 0, 0)
-    fid_a, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, 10.0, psi0)
-    fid_b, _ = engine.mc_pink_philox(controls, dt, gate, gc, first, S, seed, spin.FQ, namp, 10.0)
+    fid_a, st_a = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, 10.0, psi0)
+    fid_b, st_b = engine.mc_pink_philox(controls, dt, gate, gc, first, S, seed, spin.FQ, namp, 10.0)
     assert np.max(np.abs(fid_a - fid_b)) < 1e-14
+    assert st_a.count == st_b.count == S and abs(st_a.sum - st_b.sum) < 1e-12
+    # the two forms of the sweep agree with each other to rounding
+    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", "1" if gate_parallel == "0" else "0")
+    fid_c, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, 10.0, psi0)
+    assert np.max(np.abs(fid_a - fid_c)) < 1e-13
 
 
 def _rand_rho(S, seed, mixed=False):
