@@ -54,15 +54,6 @@ static int dev_buf(rbq_handle* h, int role, size_t bytes, void** out) {
     *out = h->dbuf[role];
     return 0;
 }
-static int host_buf(rbq_handle* h, int role, size_t bytes, void** out) {
-    if (h->hcap[role] < bytes) {
-        if (h->hbuf[role]) { CK(cudaFreeHost(h->hbuf[role])); h->hbuf[role] = nullptr; h->hcap[role] = 0; }
-        CK(cudaMallocHost(&h->hbuf[role], bytes));
-        h->hcap[role] = bytes;
-    }
-    *out = h->hbuf[role];
-    return 0;
-}
 #define ENTER(h)                                                \
     if (!(h)) return RBQ_E_NULL;                                \
     (h)->err[0] = 0;                                            \
@@ -148,7 +139,6 @@ int rbq_destroy(rbq_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < RBQ_NBUF; ++i) if (h->dbuf[i]) cudaFree(h->dbuf[i]);
-    for (int i = 0; i < 2; ++i) if (h->hbuf[i]) cudaFreeHost(h->hbuf[i]);
     free(h->idx_host);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(h->copy_stream[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
@@ -343,9 +333,9 @@ static int check_mc(rbq_handle* h, const char* who, const void* controls, int64_
 }
 // stage the pulse, return device pointers to the staged copy and to max|a|
 static int stage_pulse(rbq_handle* h, const double* d_controls, int64_t nk, const double** staged, const double** amax) {
-    void *pb, *sc;
+    void *pb = nullptr, *sc = nullptr;
     CKL(dev_buf(h, B_PULSE, sizeof(double) * (nk + 2), &pb));
-    CKL(dev_buf(h, B_SCALARS, 64, &sc));
+    CKL(dev_buf(h, B_SCALARS, 256, &sc));
     CKL(launch_pulse_prep(h, d_controls, nk, (double*)sc));
     *staged = (const double*)pb; *amax = (const double*)sc;
     return 0;
@@ -709,6 +699,15 @@ int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, do
         a.hist = (unsigned long long*)d_stats->hist;
     }
     int nblocks = 0;
+    // no per-realisation amplitude offsets and time-independent rates: the one-gate map is the same for every realisation
+    // (the reference recomputes it per seed, figures.jl:194-205); compose it once when it will be reused enough to matter
+    const bool time_dep = (channels & RBQ_LINDBLAD_T2) && t2_gamma_f != 0.0;
+    if (!d_da && !time_dep && (gate_count > 3 || S >= 64) && !getenv("RBQ_LINDBLAD_NO_SHARED_MAP")) {
+        void* sc;
+        CKL(dev_buf(h, B_SCALARS, 256, &sc));
+        CKL(launch_lindblad_shared_map(h, a, channels, (double*)sc + 8));
+        a.shared_map = (const double*)sc + 8;
+    }
     CKL(launch_lindblad(h, a, channels, &nblocks));
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
     return RBQ_OK;
@@ -748,7 +747,7 @@ int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops) {
     if (!tflops) return fail(h, RBQ_E_NULL, "rbq_fp64_peak: null pointer");
     if (iters < 1) return fail(h, RBQ_E_SIZE, "rbq_fp64_peak: iters=%d", iters);
     void* sink;
-    CKL(dev_buf(h, B_SCALARS, 64, &sink));
+    CKL(dev_buf(h, B_SCALARS, 256, &sink));
     int nthreads = 0, fpi = 0;
     CKL(launch_fp64_peak(h, iters / 8 + 1, (double*)sink + 4, &nthreads, &fpi));   // warm-up
     CK(cudaEventRecord(h->ev[6], h->stream));

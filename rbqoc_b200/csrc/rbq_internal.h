@@ -18,8 +18,6 @@ struct rbq_handle {
     char err[512];
     void* dbuf[RBQ_NBUF];          // grow-only device scratch, indexed by role
     size_t dcap[RBQ_NBUF];
-    void* hbuf[2];                 // pinned host staging (stats, small results)
-    size_t hcap[2];
     // cached noise-index table of integrate_prop_schroedda! (host copy + key); the device copy is dbuf[B_IDX]
     int32_t* idx_host; size_t idx_cap;
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
@@ -62,6 +60,7 @@ struct LindbladArgs {
     int64_t gate_count; int64_t S; double fq;
     const double* da; const double* rho0; double t2_gamma_c, t2_gamma_f;
     double* fid; double* rho_out; BlockPartial* partials; unsigned long long* hist; const double* amax;
+    const double* shared_map;   // 3x3 one-gate Bloch map common to all realisations (column images), or NULL
     GateRot gate;
 };
 
@@ -70,6 +69,7 @@ int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, doubl
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);
+int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);
 int64_t mc_static_wave_samples(const rbq_handle* h, int algo);

@@ -171,14 +171,6 @@ RBQ_DEV void prop_apply(const Prop<double>& E, double* psi) {
     prop_apply<double>(E, psi[0], psi[1], psi[2], psi[3], o0, o1, o2, o3);
     psi[0] = o0; psi[1] = o1; psi[2] = o2; psi[3] = o3;
 }
-// generic-T propagator from (f, a, dt): p = pi dt f, q = pi dt a
-template <class T> RBQ_DEV Prop<T> make_prop(const T& f, const T& a, const T& dt) {
-    T p = (RBQ_PI * dt) * f, q = (RBQ_PI * dt) * a;
-    T x = p * p + q * q, c, s;
-    su2_general(x, c, s);
-    Prop<T> E; E.c = c; E.sp = s * p; E.sq = s * q;
-    return E;
-}
 // G psi / dt for H0 or H1 alone (Lawson-Euler source terms of spin11.jl:85, spin17.jl dstate1)
 template <class T> RBQ_DEV void apply_N0(const T& a0, const T& a1, const T& a2, const T& a3, T& o0, T& o1, T& o2, T& o3) {
     o0 = a2; o1 = -a3; o2 = -a0; o3 = a1;

@@ -729,7 +729,8 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
     if (tid == 0) kmax_s = 1;
     PulsePipe pipe;
-    pipe.init(tile_s, bar_s, a.controls, a.nk);
+    if (!a.shared_map) pipe.init(tile_s, bar_s, a.controls, a.nk);   // with a shared one-gate map the pulse is not walked here
+    else __syncthreads();
 
     const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
     const bool live = s < a.S;
@@ -773,15 +774,22 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     };
 
     // few gates: carry the state itself (1 vector per knot and gate); many gates: compose the one-gate map once (3 vectors)
-    const bool direct = time_dep || a.gate_count <= 3;
+    const bool direct = !a.shared_map && (time_dep || a.gate_count <= 3);
     if (!direct) {
         // compose the one-gate map from its action on the three basis vectors, then apply it gate_count times
         double P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};   // P[c] = image of e_c
-        for (int ti = 0; ti < pipe.ntiles; ++ti) {
-            const double* tile = pipe.acquire(ti, false);
-            const int len = pipe.tile_len(ti);
-            for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, invk_s, P);
-            pipe.release(ti + 1 < pipe.ntiles);
+        if (a.shared_map) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) P[c][i] = a.shared_map[3 * c + i];
+        } else {
+            for (int ti = 0; ti < pipe.ntiles; ++ti) {
+                const double* tile = pipe.acquire(ti, false);
+                const int len = pipe.tile_len(ti);
+                for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, invk_s, P);
+                pipe.release(ti + 1 < pipe.ntiles);
+            }
         }
         for (int64_t g = 1; g <= a.gate_count; ++g) {
             const double n0 = fma(P[2][0], r[2], fma(P[1][0], r[1], P[0][0] * r[0]));
@@ -821,6 +829,72 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
         __syncthreads();
         block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
     }
+}
+
+// One-gate Bloch map shared by every realisation (no per-sample amplitude offsets, time-independent rates): what the
+// reference recomputes for each of its 1000 seeds (figures.jl gen_1c).  One block: thread k exponentiates knot k's
+// generator (3 columns), an ordered tree product in shared memory multiplies 256 knots at a time into the running map.
+__global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const LindbladArgs a, int channels, double* __restrict__ map_out) {
+    __shared__ double M[256][9];
+    __shared__ double invk_s[64];
+    __shared__ double run[9];
+    const int tid = threadIdx.x;
+    if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
+    if (tid < 9) run[tid] = (tid % 4 == 0) ? 1.0 : 0.0;
+    const bool t1_on = (channels & RBQ_LINDBLAD_T1) != 0, t2_on = (channels & RBQ_LINDBLAD_T2) != 0;
+    const double w2 = 2.0 * RBQ_PI * a.dt;
+    const double gmax = (t1_on ? 2.0 / 269.03e3 : 0.0) + (t2_on ? a.t2_gamma_c : 0.0);
+    const double bnd = w2 * (fabs(a.fq) + *a.amax) + gmax * a.dt;
+    const int kmax = bnd == bnd ? taylor_terms(bnd) : 60;
+    __syncthreads();
+    for (int64_t base = 0; base < a.nk; base += 256) {
+        const int64_t k = base + tid;
+        double P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        if (k < a.nk) {
+            const double c1 = a.controls[k];
+            BlochGen m;
+            m.wz = w2 * a.fq; m.wx = w2 * c1;
+            const double g1 = t1_on ? a.dt / t1_interp<double>(c1, 1e3) : 0.0;
+            m.g2 = g1 + (t2_on ? a.dt * a.t2_gamma_c : 0.0); m.g1 = 2.0 * g1;
+            bloch_advance<3>(m, kmax, invk_s, P);
+        }
+        // column-major: M[tid][3c+i] = image of e_c, component i
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) M[tid][3 * c + i] = P[c][i];
+        __syncthreads();
+        // ordered product: after the loop M[0] = E_{base+255} ... E_{base+1} E_{base}
+        for (int stride = 1; stride < 256; stride <<= 1) {
+            double A[9], B[9], Cm[9];
+            const bool act = (tid % (2 * stride)) == 0;
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) { B[i] = M[tid][i]; A[i] = M[tid + stride][i]; }   // later knots multiply from the left
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) Cm[3 * c + i] = fma(A[6 + i], B[3 * c + 2], fma(A[3 + i], B[3 * c + 1], A[i] * B[3 * c]));
+            }
+            __syncthreads();
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) M[tid][i] = Cm[i];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            double A[9], B[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { A[i] = M[0][i]; B[i] = run[i]; }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) run[3 * c + i] = fma(A[6 + i], B[3 * c + 2], fma(A[3 + i], B[3 * c + 1], A[i] * B[3 * c]));
+        }
+        __syncthreads();
+    }
+    if (tid < 9) map_out[tid] = run[tid];
 }
 
 // ---- sample materialisation (parity aids) -------------------------------------------------------------------------
@@ -969,6 +1043,11 @@ int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d
     if (e != cudaSuccess) return (int)e;
     mc_noise_combine_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_quat);
     h->launches += 2;
+    return (int)cudaGetLastError();
+}
+int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map) {
+    lindblad_shared_map_kernel<<<1, 256, 0, h->stream>>>(a, channels, d_map);
+    h->launches++;
     return (int)cudaGetLastError();
 }
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out) {

@@ -233,6 +233,24 @@ def test_lindblad_matches_50_digit_golden(engine):
     assert np.max(np.abs(rho - z["rho"][:, G])) < 1e-13
 
 
+@pytest.mark.parametrize("name", ["sin301_dt0.1", "x2_dt0.01"])
+def test_lindblad_shared_map_path(engine, oracle, name, monkeypatch):
+    """No per-realisation offsets: the one-gate map is composed once (tree product over knots) and shared by all samples."""
+    controls, dt, gate = PULSES[name]
+    S, gate_count = 200, 7
+    rho0 = _rand_rho(S, 11, mixed=True)
+    fid, rho, st = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, None, rho0)
+    monkeypatch.setenv("RBQ_LINDBLAD_NO_SHARED_MAP", "1")
+    fid2, rho2, _ = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, None, rho0)
+    # sequential vs tree-ordered products of the same per-knot maps differ by rounding only (~1e-16 per knot and gate)
+    nk = controls.shape[0]
+    assert np.max(np.abs(rho - rho2)) < max(1e-13, 2e-16 * nk * gate_count) and np.max(np.abs(fid - fid2)) < max(1e-12, 2e-16 * nk * gate_count)
+    rfid, rfid_closed, rrho = oracle.lindblad_t1(controls, dt, gate, gate_count, spin.FQ, None, rho0[:40])
+    assert np.max(np.abs(rho[:40] - rrho)) < max(5e-12, 2.5e-15 * controls.shape[0])
+    assert np.max(np.abs(fid[:40] - rfid_closed)) < max(5e-12, 2.5e-15 * controls.shape[0])
+    assert st.count == S
+
+
 def test_lindblad_d1_pin(engine):
     """D1(Z/2) = T/T1(0) = 5.7441e-5 (paper main.tex:1077, trials.xlsx spin14): the population of a
     z-polarised state relaxes by exactly that much over one idle gate."""
