@@ -58,6 +58,8 @@ extern "C" {
 #define RBQ_MODEL_SPIN15 15 /* decay aware / time optimal    spin15.jl:40-73   */
 #define RBQ_MODEL_SPIN17 17 /* derivative robust, d/da       spin17.jl:48-114  */
 #define RBQ_MODEL_SPIN18 18 /* sampling robust, a +- namp    spin18.jl:50-55,162-190 */
+#define RBQ_MODEL_SPIN25 25 /* unscented sampling, amplitude noise through the pink filter (time dependent)
+                               spin25.jl:67-239 */
 #define RBQ_MODEL_SPIN30 30 /* unscented sampling, fq        spin30.jl:60-202  */
 
 /* propagator algorithm for exp(dt*(f*H0 + a*H1)) */
@@ -77,6 +79,8 @@ extern "C" {
  *   spin12.jl:52-54  Model(h0_samples)          -> fq_samples[2]
  *   spin18.jl:50-52  Model(namp)                -> namp
  *   spin30.jl:60-66  Model(S, nominal_idxs, fq_cov, alpha, sample_state_count)
+ *   spin25.jl:67-74  Model(S, nominal_idxs, namp, wnamp_cov, alpha, sample_state_count)
+ *                    -> namp, fq_cov (= wnamp_cov), alpha, S_diag, sample_state_count
  *   spin15.jl:40-42  Model{DA,TO}               -> decay_aware, time_optimal
  *   spin11.jl:51-52  Model{DO} / spin17.jl      -> derivative_order
  * `fq` replaces the global constant FQ (spin.jl:148) so that batches of detuned
@@ -96,7 +100,7 @@ typedef struct rbq_model_params {
     double fq;                  /* GHz                                                */
     double fq_samples[2];       /* spin12: (FQ+fq_cov), (FQ-fq_cov)  spin12.jl:204-205 */
     double namp;                /* spin18                                             */
-    double fq_cov;              /* spin30 (used as a variance, spin30.jl:102,138)     */
+    double fq_cov;              /* spin30 (used as a variance, spin30.jl:102,138); spin25: wnamp_cov */
     double alpha;               /* spin30                                             */
     double S_diag[4];           /* spin30 penalty weights, spin30.jl:215              */
 } rbq_model_params;
@@ -149,7 +153,8 @@ int rbq_discrete_jacobian(rbq_handle* h, const rbq_model_params* p, const double
 
 /* ---- trajectory level (what Altro's `for k = 1:N-1` loops become) ------------------------
  * rollout: B independent trajectories.  x0[B*n], U[B*(N-1)*m], dt[N-1] (shared by the
- * batch; ignored by time-optimal spin15 which takes dt = u2^2), X[B*N*n]. */
+ * batch; ignored by time-optimal spin15 which takes dt = u2^2), X[B*N*n].  Knot times start at 0 and accumulate
+ * (t[k+1] = t[k] + dt[k]), as the KnotPoints of a TO.Traj do. */
 int rbq_rollout(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N,
                 const double* x0, const double* U, const double* dt, double* X);
 /* closed-loop rollout used by the iLQR line search: for each candidate alpha_c
@@ -160,13 +165,14 @@ int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N,
                            const double* d, const double* dt, int64_t nalpha,
                            const double* alphas, double* X, double* Uout);
 /* jacobians: K independent knots (a whole trajectory, or a batch of them, flattened).
- * X[K*n], U[K*m], dt[K], AB[K*n*(n+m)] (each block column-major). */
+ * X[K*n], U[K*m], dt[K], AB[K*n*(n+m)] (each block column-major).  t[K] = the knot times z.t; may be NULL (= 0) for
+ * every model but spin25, the only one whose dynamics read their time argument (spin25.jl:196). */
 int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X,
-                  const double* U, const double* dt, double* AB);
+                  const double* U, const double* t, const double* dt, double* AB);
 int rbq_rollout_dev(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N,
                     const double* d_x0, const double* d_U, const double* d_dt, double* d_X);
 int rbq_jacobians_dev(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* d_X,
-                      const double* d_U, const double* d_dt, double* d_AB);
+                      const double* d_U, const double* d_t, const double* d_dt, double* d_AB);
 
 /* ---- cost-side primitives of the sampling objectives (first "next" row of the scope table):
  *      gate_error_iso2, jacobian_gate_error_iso2, hessian_gate_error_iso2  (spin.jl:1040-1092), the per-knot terms of

@@ -63,6 +63,10 @@ params_spin15(DA::Bool, TO::Bool) = _params(15; DA=DA, TO=TO)                   
 params_spin11(DO::Int) = _params(11; DO=DO)                                                       # spin11.jl:51-52
 params_spin17(DO::Int) = _params(17; DO=DO)
 # spin30.jl:60-66: nominal_idxs[i][1]-1 is the 0-based offset of sample state i's nominal block
+# spin25.jl:67-74: wnamp_cov travels in the fq_cov slot (include/rbq.h)
+params_spin25(S, nominal_idxs, namp, wnamp_cov, alpha, ssc) =
+    _params(25; ssc=ssc, namp=namp, fq_cov=wnamp_cov, alpha=alpha, S=Tuple(diag(S)),
+            nominal=ntuple(i -> i <= ssc ? nominal_idxs[i][1] - 1 : 0, 4))
 params_spin30(S, nominal_idxs, fq_cov, alpha, ssc) =
     _params(30; ssc=ssc, fq_cov=fq_cov, alpha=alpha, S=Tuple(diag(S)),
             nominal=ntuple(i -> i <= ssc ? nominal_idxs[i][1] - 1 : 0, 4))
@@ -123,12 +127,14 @@ function rollout!(X::Matrix{Float64}, p::ModelParams, x0::AbstractVector, U::Mat
     return X
 end
 
-"AB: n×(n+m)×(N-1) array; slice k is ∇f_k.  X: n×(N-1) (or n×N), U: m×(N-1)."
-function jacobians!(AB::Array{Float64,3}, p::ModelParams, X::Matrix{Float64}, U::Matrix{Float64}, dts::Vector{Float64})
+"AB: n×(n+m)×(N-1) array; slice k is ∇f_k.  X: n×(N-1) (or n×N), U: m×(N-1), ts: knot times z.t (only spin25 reads them)."
+function jacobians!(AB::Array{Float64,3}, p::ModelParams, X::Matrix{Float64}, U::Matrix{Float64}, dts::Vector{Float64},
+                    ts::Union{Nothing,Vector{Float64}}=nothing)
     K = size(U, 2)
-    GC.@preserve AB X U dts check(ccall((:rbq_jacobians, LIB), Cint,
-        (Ptr{Cvoid}, Ref{ModelParams}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        handle().ptr, p, K, X, U, dts, AB), "rbq_jacobians")
+    tp = ts === nothing ? Ptr{Float64}(C_NULL) : pointer(ts)
+    GC.@preserve AB X U dts ts check(ccall((:rbq_jacobians, LIB), Cint,
+        (Ptr{Cvoid}, Ref{ModelParams}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        handle().ptr, p, K, X, U, tp, dts, AB), "rbq_jacobians")
     return AB
 end
 

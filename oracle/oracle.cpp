@@ -268,6 +268,9 @@ static int state_dim(const rbq_model_params* p) {
     case RBQ_MODEL_SPIN30:
         if (p->sample_state_count < 1 || p->sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
         return 15 + 41 * p->sample_state_count;
+    case RBQ_MODEL_SPIN25:   // spin25.jl:28-33, 73-75
+        if (p->sample_state_count < 1 || p->sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
+        return 17 + 41 * p->sample_state_count;
     default: return RBQ_E_MODEL;
     }
 }
@@ -368,7 +371,60 @@ template <class T> void cholesky_lower(int n, const T* A, T* L) {
         }
     }
 }
-// spin30.jl:86-174 (unscented_transform) and 177-202
+// unscented_transform of spin30.jl:86-174 / spin25.jl:91-178 for the chunk at `off`: Ep / En propagate points 5 / 10
+template <class T>
+void unscented_transform(const rbq_model_params* p, const T* x, int off, int nom, const Mat4<T>& E, const Mat4<T>& Ep,
+                         const Mat4<T>& En, double joint_cov, T* xn) {
+    T s[10][4];
+    for (int j = 0; j < 10; ++j) {
+        const Mat4<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
+        matvec(M, x + off + 4 * j, s[j]);
+    }
+    T sm[4];
+    for (int i = 0; i < 4; ++i) {                                          // spin30.jl:115-118
+        T acc = s[0][i];
+        for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
+        sm[i] = 0.1 * acc;
+    }
+    T d[10][4];
+    for (int j = 0; j < 10; ++j) for (int i = 0; i < 4; ++i) d[j][i] = s[j][i] - sm[i];
+    T cov[25];
+    for (int i = 0; i < 25; ++i) cov[i] = T(0.0);
+    const double cf = 1.0 / (2.0 * p->alpha * p->alpha);                  // spin30.jl:130
+    T scov[4][4];
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k) {
+            T acc = d[0][i] * d[0][k];
+            for (int j = 1; j < 10; ++j) acc = acc + d[j][i] * d[j][k];
+            scov[i][k] = cf * acc;
+            cov[i * 5 + k] = scov[i][k];
+        }
+    cov[24] = T(joint_cov);                                                // spin30.jl:138 / spin25.jl:144
+    T L[25];
+    cholesky_lower(5, cov, L);
+    T snew[10][4];
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            T col = p->alpha * L[i * 5 + j];                               // spin30.jl:140-145
+            snew[j][i] = sm[i] + col;
+            snew[5 + j][i] = sm[i] - col;
+        }
+    for (int i = 0; i < 4; ++i) { snew[4][i] = sm[i]; snew[9][i] = sm[i]; }
+    for (int j = 0; j < 10; ++j) {                                         // spin30.jl:157-166
+        T nn = snew[j][0] * snew[j][0];
+        for (int i = 1; i < 4; ++i) nn = nn + snew[j][i] * snew[j][i];
+        T nr = sqrt(nn);
+        for (int i = 0; i < 4; ++i) xn[off + 4 * j + i] = snew[j][i] / nr;
+    }
+    T pen = T(0.0);                                                        // spin30.jl:168-169
+    for (int i = 0; i < 4; ++i) pen = pen + scov[i][i] * p->S_diag[i];
+    for (int i = 0; i < 4; ++i) {
+        T dn = sm[i] - x[nom + i];
+        pen = pen + dn * p->S_diag[i] * dn;
+    }
+    xn[off + 40] = pen;
+}
+// spin30.jl:177-202
 template <class T> void step_spin30(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
     const T a = x[13];
     Mat4<T> E = propagator(T(p->fq), a, dt);                                  // spin30.jl:181
@@ -379,61 +435,38 @@ template <class T> void step_spin30(const rbq_model_params* p, const T* x, const
     const double fq_chol5 = std::sqrt(p->fq_cov);                             // spin30.jl:102
     Mat4<T> Ep = propagator(T(p->fq + fq_chol5), a, dt);                      // spin30.jl:108
     Mat4<T> En = propagator(T(p->fq - fq_chol5), a, dt);                      // spin30.jl:113
-    for (int c = 0; c < p->sample_state_count; ++c) {
-        const int off = 15 + 41 * c;
-        T s[10][4];
-        for (int j = 0; j < 10; ++j) {
-            const Mat4<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
-            matvec(M, x + off + 4 * j, s[j]);
-        }
-        T sm[4];
-        for (int i = 0; i < 4; ++i) {                                          // spin30.jl:115-118
-            T acc = s[0][i];
-            for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
-            sm[i] = 0.1 * acc;
-        }
-        T d[10][4];
-        for (int j = 0; j < 10; ++j) for (int i = 0; i < 4; ++i) d[j][i] = s[j][i] - sm[i];
-        T cov[25];
-        for (int i = 0; i < 25; ++i) cov[i] = T(0.0);
-        const double cf = 1.0 / (2.0 * p->alpha * p->alpha);                  // spin30.jl:130
-        T scov[4][4];
-        for (int i = 0; i < 4; ++i)
-            for (int k = 0; k < 4; ++k) {
-                T acc = d[0][i] * d[0][k];
-                for (int j = 1; j < 10; ++j) acc = acc + d[j][i] * d[j][k];
-                scov[i][k] = cf * acc;
-                cov[i * 5 + k] = scov[i][k];
-            }
-        cov[24] = T(p->fq_cov);                                                // spin30.jl:138
-        T L[25];
-        cholesky_lower(5, cov, L);
-        T snew[10][4];
-        for (int j = 0; j < 4; ++j)
-            for (int i = 0; i < 4; ++i) {
-                T col = p->alpha * L[i * 5 + j];                               // spin30.jl:140-145
-                snew[j][i] = sm[i] + col;
-                snew[5 + j][i] = sm[i] - col;
-            }
-        for (int i = 0; i < 4; ++i) { snew[4][i] = sm[i]; snew[9][i] = sm[i]; }
-        for (int j = 0; j < 10; ++j) {                                         // spin30.jl:157-166
-            T nn = snew[j][0] * snew[j][0];
-            for (int i = 1; i < 4; ++i) nn = nn + snew[j][i] * snew[j][i];
-            T nr = sqrt(nn);
-            for (int i = 0; i < 4; ++i) xn[off + 4 * j + i] = snew[j][i] / nr;
-        }
-        T pen = T(0.0);                                                        // spin30.jl:168-169
-        for (int i = 0; i < 4; ++i) pen = pen + scov[i][i] * p->S_diag[i];
-        for (int i = 0; i < 4; ++i) {
-            T dn = sm[i] - x[p->nominal_offset[c] + i];
-            pen = pen + dn * p->S_diag[i] * dn;
-        }
-        xn[off + 40] = pen;
-    }
+    for (int c = 0; c < p->sample_state_count; ++c)
+        unscented_transform(p, x, 15 + 41 * c, p->nominal_offset[c], E, Ep, En, p->fq_cov, xn);
+}
+// Int(div(time, dt)) with Julia's floating-point div = round((x - rem(x, y)) / y)   (spin25.jl:196)
+static long long knot_point_of(double time, double dt) { return (long long)std::rint((time - std::fmod(time, dt)) / dt); }
+// spin25.jl:181-235: amplitude-noise unscented model; the pink filter's taps are part of the state and its start-up
+// branch depends on the knot index derived from the TIME argument.  `fq_cov` carries wnamp_cov (include/rbq.h).
+template <class T> void step_spin25(const rbq_model_params* p, const T* x, const T* u, double time, const T& dt, T* xn) {
+    const T camp = x[9];
+    Mat4<T> E = propagator(T(p->fq), camp, dt);
+    matvec(E, x + 0, xn + 0);
+    matvec(E, x + 4, xn + 4);
+    control_chain(x, 8, u[0], dt, xn);
+    const double xk = std::sqrt(p->fq_cov);
+    const long long kp = knot_point_of(time, value(dt));
+    const T xp1 = x[11], xp2 = x[12], xp3 = x[13], yp1 = x[14], yp2 = x[15], yp3 = x[16];
+    T yk;
+    if (kp == 1) yk = T(PFIR_B1 * xk);
+    else if (kp == 2) yk = PFIR_B1 * xk + PFIR_B2 * xp1 - PFIR_A2 * yp1;
+    else if (kp == 3) yk = PFIR_B1 * xk + PFIR_B2 * xp1 + PFIR_B3 * xp2 - PFIR_A2 * yp1 - PFIR_A3 * yp2;
+    else yk = PFIR_B1 * xk + PFIR_B2 * xp1 + PFIR_B3 * xp2 + PFIR_B4 * xp3 - PFIR_A2 * yp1 - PFIR_A3 * yp2 - PFIR_A4 * yp3;
+    xn[11] = T(xk); xn[12] = xp1; xn[13] = xp2; xn[14] = yk; xn[15] = yp1; xn[16] = yp2;
+    const T namp = p->namp * yk;
+    Mat4<T> Ep = propagator(T(p->fq), camp + namp, dt);                      // spin25.jl:111
+    Mat4<T> En = propagator(T(p->fq), camp - namp, dt);                      // spin25.jl:116
+    for (int c = 0; c < p->sample_state_count; ++c)
+        unscented_transform(p, x, 17 + 41 * c, p->nominal_offset[c], E, Ep, En, p->fq_cov, xn);
 }
 
-template <class T> int step(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+template <class T> int step(const rbq_model_params* p, const T* x, const T* u, double time, const T& dt, T* xn) {
     switch (p->model_id) {
+    case RBQ_MODEL_SPIN25: step_spin25(p, x, u, time, dt, xn); return 0;
     case RBQ_MODEL_SPIN13: step_spin13(p, x, u, dt, xn); return 0;
     case RBQ_MODEL_SPIN12: step_spin12(p, x, u, dt, xn); return 0;
     case RBQ_MODEL_SPIN18: step_spin18(p, x, u, dt, xn); return 0;
@@ -766,36 +799,34 @@ double orc_t1_ns(double a) { return amp_t1_spline<double>(a); }
 double orc_t1_reduced_us(double a) { return amp_t1_reduced_spline<double>(a); }
 
 int orc_step(const rbq_model_params* p, const double* x, const double* u, double t, double dt, double* xn) {
-    (void)t;
     if (!p || !x || !u || !xn) return RBQ_E_NULL;
     int n = state_dim(p); if (n < 0) return n;
     std::vector<double> tmp(n);
-    int rc = step<double>(p, x, u, dt, tmp.data());
+    int rc = step<double>(p, x, u, t, dt, tmp.data());
     if (rc == 0) std::memcpy(xn, tmp.data(), sizeof(double) * n);
     return rc;
 }
 // ForwardDiff.jacobian(s -> discrete_dynamics(RK3, model, s[ix], s[iu], t, dt), [x;u]),
 // written column-major n x (n+m)  (RobotDynamics 0.2.1 default discrete_jacobian!)
 int orc_jacobian(const rbq_model_params* p, const double* x, const double* u, double t, double dt, double* AB) {
-    (void)t;
     if (!p || !x || !u || !AB) return RBQ_E_NULL;
     int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
     g_np = n + m;
     std::vector<Dual> xd(n), ud(m), xo(n);
     for (int i = 0; i < n; ++i) { xd[i] = Dual(x[i]); xd[i].d[i] = 1.0; }
     for (int j = 0; j < m; ++j) { ud[j] = Dual(u[j]); ud[j].d[n + j] = 1.0; }
-    int rc = step<Dual>(p, xd.data(), ud.data(), Dual(dt), xo.data());
+    int rc = step<Dual>(p, xd.data(), ud.data(), t, Dual(dt), xo.data());
     if (rc == 0)
         for (int c = 0; c < n + m; ++c) for (int r = 0; r < n; ++r) AB[(size_t)c * n + r] = xo[r].d[c];
     g_np = 0;
     return rc;
 }
-int orc_jacobians(const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* dt, double* AB) {
+int orc_jacobians(const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* t, const double* dt, double* AB) {
     int n = state_dim(p), m = control_dim(p); if (n < 0 || m < 0) return RBQ_E_MODEL;
     int rc = 0;
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < K; ++k) {
-        int r = orc_jacobian(p, X + k * n, U + k * m, 0.0, dt[k], AB + (size_t)k * n * (n + m));
+        int r = orc_jacobian(p, X + k * n, U + k * m, t ? t[k] : 0.0, dt[k], AB + (size_t)k * n * (n + m));
         if (r) rc = r;
     }
     return rc;
@@ -807,8 +838,11 @@ int orc_rollout(const rbq_model_params* p, int64_t B, int64_t N, const double* x
     for (int64_t b = 0; b < B; ++b) {
         double* Xb = X + (size_t)b * N * n;
         std::memcpy(Xb, x0 + b * n, sizeof(double) * n);
-        for (int64_t k = 0; k + 1 < N; ++k)
-            step<double>(p, Xb + k * n, U + ((size_t)b * (N - 1) + k) * m, dt[k], Xb + (k + 1) * n);
+        double time = 0.0;                                                  // knot times accumulate like a TO.Traj's
+        for (int64_t k = 0; k + 1 < N; ++k) {
+            step<double>(p, Xb + k * n, U + ((size_t)b * (N - 1) + k) * m, time, dt[k], Xb + (k + 1) * n);
+            time = time + dt[k];
+        }
     }
     return 0;
 }
@@ -821,13 +855,15 @@ int orc_rollout_closedloop(const rbq_model_params* p, int64_t N, const double* X
         double* Xc = X + (size_t)c * N * n;
         double* Uc = Uout + (size_t)c * (N - 1) * m;
         std::memcpy(Xc, Xref, sizeof(double) * n);
+        double time = 0.0;
         for (int64_t k = 0; k + 1 < N; ++k) {
             for (int j = 0; j < m; ++j) {
                 double du = alphas[c] * d[k * m + j];
                 for (int i = 0; i < n; ++i) du += K[(size_t)k * m * n + (size_t)i * m + j] * (Xc[k * n + i] - Xref[k * n + i]);
                 Uc[k * m + j] = Uref[k * m + j] + du;
             }
-            step<double>(p, Xc + k * n, Uc + k * m, dt[k], Xc + (k + 1) * n);
+            step<double>(p, Xc + k * n, Uc + k * m, time, dt[k], Xc + (k + 1) * n);
+            time = time + dt[k];
         }
     }
     return 0;

@@ -170,12 +170,13 @@ def jacobian(p, x, u, dt, t=0.0):
     return AB.T.copy()
 
 
-def jacobians(p, X, U, dt):
+def jacobians(p, X, U, dt, t=None):
     X, U, dt = _f64(X), _f64(U), _f64(dt)
+    t = None if t is None else _f64(t)
     n, m = state_dim(p), control_dim(p)
     K = X.shape[0]
     AB = np.empty((K, n + m, n))
-    rc = lib().orc_jacobians(C.byref(p), C.c_int64(K), _p(X), _p(U), _p(dt), _p(AB))
+    rc = lib().orc_jacobians(C.byref(p), C.c_int64(K), _p(X), _p(U), _p(t), _p(dt), _p(AB))
     if rc:
         raise ValueError(f"orc_jacobians rc={rc}")
     return np.ascontiguousarray(AB.transpose(0, 2, 1))

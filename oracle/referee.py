@@ -55,6 +55,8 @@ def step(model, x, u, dt, **kw):
     x = list(x)
     if model == "spin30":
         return _step_spin30(x, u, dt, fq, kw)
+    if model == "spin25":
+        return _step_spin25(x, u, dt, fq, kw)
     to = kw.get("time_optimal", False)
     if model == "spin15" and to:
         dt = u[1] * u[1]                                           # spin15.jl:52-54
@@ -89,16 +91,47 @@ def step(model, x, u, dt, **kw):
     raise ValueError(model)
 
 
+PFIR_B = [mp.mpf(t) for t in ("0.049922035", "-0.095993537", "0.050612699", "-0.004408786")]   # spin.jl:166-169
+PFIR_A = [mp.mpf(1)] + [mp.mpf(t) for t in ("-2.494956002", "2.017265875", "-0.522189400")]    # spin.jl:170-173
+
+
+def _step_spin25(x, u, dt, fq, kw):
+    """spin25.jl:181-235; kw["time"] is the knot time, kw["fq_cov"] carries wnamp_cov."""
+    camp = x[9]
+    E = propagator(fq, camp, dt)
+    out = _mv(E, x[0:4]) + _mv(E, x[4:8]) + [x[8] + camp * dt, x[9] + x[10] * dt, x[10] + u[0] * dt]
+    xk = mp.sqrt(kw["fq_cov"])
+    time = kw.get("time", mp.mpf(0))
+    kp = int(mp.nint((time - mp.fmod(time, dt)) / dt))
+    xp, yp = x[11:14], x[14:17]
+    yk = PFIR_B[0] * xk
+    if kp != 1:
+        yk += PFIR_B[1] * xp[0] - PFIR_A[1] * yp[0]
+        if kp != 2:
+            yk += PFIR_B[2] * xp[1] - PFIR_A[2] * yp[1]
+            if kp != 3:
+                yk += PFIR_B[3] * xp[2] - PFIR_A[3] * yp[2]
+    out += [xk, xp[0], xp[1], yk, yp[0], yp[1]]
+    namp = kw["namp"] * yk
+    Ep, En = propagator(fq, camp + namp, dt), propagator(fq, camp - namp, dt)
+    return out + _unscented(x, 17, E, Ep, En, kw)
+
+
 def _step_spin30(x, u, dt, fq, kw):
     a = x[13]
     E = propagator(fq, a, dt)
     out = _mv(E, x[0:4]) + _mv(E, x[4:8]) + _mv(E, x[8:12]) + [x[12] + a * dt, x[13] + x[14] * dt, x[14] + u[0] * dt]
+    sig = mp.sqrt(kw["fq_cov"])
+    Ep, En = propagator(fq + sig, a, dt), propagator(fq - sig, a, dt)
+    return out + _unscented(x, 15, E, Ep, En, kw)
+
+
+def _unscented(x, base, E, Ep, En, kw):
+    out = []
     fq_cov, alpha = kw["fq_cov"], kw.get("alpha", mp.mpf(1))
     S = kw.get("S_diag", [mp.mpf(1)] * 4)
-    sig = mp.sqrt(fq_cov)
-    Ep, En = propagator(fq + sig, a, dt), propagator(fq - sig, a, dt)
     for c in range(kw.get("sample_state_count", 1)):
-        off = 15 + 41 * c
+        off = base + 41 * c
         s = [_mv(Ep if j == 4 else En if j == 9 else E, x[off + 4 * j: off + 4 * j + 4]) for j in range(10)]
         sm = [sum(s[j][i] for j in range(10)) / 10 for i in range(4)]
         d = [[s[j][i] - sm[i] for i in range(4)] for j in range(10)]

@@ -18,7 +18,7 @@ MAX_SAMPLE_STATES = 4
 # enums of include/rbq.h
 GATE_ZPIBY2, GATE_YPIBY2, GATE_XPIBY2, GATE_XPI = 1, 2, 3, 4
 MODEL_SPIN11, MODEL_SPIN12, MODEL_SPIN13, MODEL_SPIN15 = 11, 12, 13, 15
-MODEL_SPIN17, MODEL_SPIN18, MODEL_SPIN30 = 17, 18, 30
+MODEL_SPIN17, MODEL_SPIN18, MODEL_SPIN25, MODEL_SPIN30 = 17, 18, 25, 30
 ALGO_SU2, ALGO_PADE = 0, 1
 LINDBLAD_T1, LINDBLAD_T2 = 1, 2
 E_NULL, E_MODEL, E_SIZE, E_GATE, E_ALGO, E_NODEVICE, E_ALIGN = -1, -2, -3, -4, -5, -6, -7
@@ -93,9 +93,9 @@ SIGNATURES = {
     "rbq_discrete_jacobian": (C.c_int, [_P, _MP, _P, _P, _D, _D, _P]),
     "rbq_rollout": (C.c_int, [_P, _MP, _I64, _I64, _P, _P, _P, _P]),
     "rbq_rollout_closedloop": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
-    "rbq_jacobians": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P]),
+    "rbq_jacobians": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P]),
     "rbq_rollout_dev": (C.c_int, [_P, _MP, _I64, _I64, _P, _P, _P, _P]),
-    "rbq_jacobians_dev": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P]),
+    "rbq_jacobians_dev": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P]),
     "rbq_gate_error_expansion": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "rbq_gate_error_expansion_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "rbq_mc_static": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _P, _P, _P, C.c_int, _P, _SP]),

@@ -181,16 +181,16 @@ int rbq_rollout_dev(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t
     if (!p || !d_x0 || !d_U || !d_dt || !d_X) return fail(h, RBQ_E_NULL, "rbq_rollout_dev: null pointer");
     if (B < 0 || N < 1) return fail(h, RBQ_E_SIZE, "rbq_rollout_dev: B=%lld N=%lld", (long long)B, (long long)N);
     if (B == 0) return RBQ_OK;
-    CKL(launch_rollout(h, *p, B, N, d_x0, d_U, d_dt, d_X));
+    CKL(launch_rollout(h, *p, B, N, 0.0, d_x0, d_U, d_dt, d_X));
     return RBQ_OK;
 }
 int rbq_jacobians_dev(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* d_X, const double* d_U,
-                      const double* d_dt, double* d_AB) {
+                      const double* d_t, const double* d_dt, double* d_AB) {
     ENTER(h);
     if (!p || !d_X || !d_U || !d_dt || !d_AB) return fail(h, RBQ_E_NULL, "rbq_jacobians_dev: null pointer");
     if (K < 0) return fail(h, RBQ_E_SIZE, "rbq_jacobians_dev: K=%lld", (long long)K);
     if (K == 0) return RBQ_OK;
-    CKL(launch_jacobians(h, *p, K, d_X, d_U, d_dt, d_AB));
+    CKL(launch_jacobians(h, *p, K, d_X, d_U, d_t, d_dt, d_AB));
     return RBQ_OK;
 }
 int rbq_rollout(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N, const double* x0, const double* U,
@@ -211,7 +211,7 @@ int rbq_rollout(rbq_handle* h, const rbq_model_params* p, int64_t B, int64_t N, 
         CK(cudaMemcpyAsync(dU, U, bU, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(ddt, dt, bdt, cudaMemcpyHostToDevice, h->stream));
     }
-    CKL(launch_rollout(h, *p, B, N, (double*)dx0, (double*)dU, (double*)ddt, (double*)dX));
+    CKL(launch_rollout(h, *p, B, N, 0.0, (double*)dx0, (double*)dU, (double*)ddt, (double*)dX));
     CK(cudaMemcpyAsync(X, dX, bX, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
@@ -244,15 +244,15 @@ int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N, 
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
 }
-int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* dt,
-                  double* AB) {
+int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* t,
+                  const double* dt, double* AB) {
     ENTER(h);
     if (!p || !X || !U || !dt || !AB) return fail(h, RBQ_E_NULL, "rbq_jacobians: null pointer");
     const int n = model_state_dim(*p), m = model_control_dim(*p);
     if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_jacobians: bad model parameters");
     if (K < 0) return fail(h, RBQ_E_SIZE, "rbq_jacobians: K=%lld", (long long)K);
     if (K == 0) return RBQ_OK;
-    void *dX, *dU, *ddt, *dAB;
+    void *dX, *dU, *ddt, *dAB, *dtk = nullptr;
     const size_t bX = sizeof(double) * K * n, bU = sizeof(double) * K * m, bdt = sizeof(double) * K,
                  bAB = sizeof(double) * K * n * (n + m);
     CKL(dev_buf(h, B_IN0, bX, &dX)); CKL(dev_buf(h, B_IN1, bU, &dU)); CKL(dev_buf(h, B_IN2, bdt, &ddt));
@@ -260,7 +260,11 @@ int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const dou
     CK(cudaMemcpyAsync(dX, X, bX, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dU, U, bU, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(ddt, dt, bdt, cudaMemcpyHostToDevice, h->stream));
-    CKL(launch_jacobians(h, *p, K, (double*)dX, (double*)dU, (double*)ddt, (double*)dAB));
+    if (t) {
+        CKL(dev_buf(h, B_IN3, bdt, &dtk));
+        CK(cudaMemcpyAsync(dtk, t, bdt, cudaMemcpyHostToDevice, h->stream));
+    }
+    CKL(launch_jacobians(h, *p, K, (double*)dX, (double*)dU, (double*)dtk, (double*)ddt, (double*)dAB));
     CK(cudaMemcpyAsync(AB, dAB, bAB, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
@@ -268,8 +272,7 @@ int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const dou
 // per-knot forms: a rollout of two knots / a one-knot Jacobian batch
 int rbq_discrete_dynamics(rbq_handle* h, const rbq_model_params* p, const double* x, const double* u, double t, double dt,
                           double* xnext) {
-    (void)t;   // none of the reference models is time dependent (the `time` argument is unused in every spinYY.jl)
-    ENTER(h);
+    ENTER(h);   // `t` matters for spin25 only (Int(div(time, dt)) selects the filter start-up branch, spin25.jl:196-214)
     if (!p || !x || !u || !xnext) return fail(h, RBQ_E_NULL, "rbq_discrete_dynamics: null pointer");
     const int n = model_state_dim(*p), m = model_control_dim(*p);
     if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_discrete_dynamics: bad model parameters");
@@ -279,15 +282,14 @@ int rbq_discrete_dynamics(rbq_handle* h, const rbq_model_params* p, const double
     CK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(du, u, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(ddt, &dt, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CKL(launch_rollout(h, *p, 1, 2, (double*)dx, (double*)du, (double*)ddt, (double*)dX));
+    CKL(launch_rollout(h, *p, 1, 2, t, (double*)dx, (double*)du, (double*)ddt, (double*)dX));
     CK(cudaMemcpyAsync(xnext, (double*)dX + n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
 }
 int rbq_discrete_jacobian(rbq_handle* h, const rbq_model_params* p, const double* x, const double* u, double t, double dt,
                           double* AB) {
-    (void)t;
-    return rbq_jacobians(h, p, 1, x, u, &dt, AB);
+    return rbq_jacobians(h, p, 1, x, u, &t, &dt, AB);
 }
 
 // ---- cost-side primitives ------------------------------------------------------------------------------------------

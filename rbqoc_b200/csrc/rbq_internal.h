@@ -83,7 +83,7 @@ int launch_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, do
                       int64_t noise_len, double* d_noise);
 int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out, int* flops_per_thread_iter);
 
-int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, const double* d_x0,
+int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, double t0, const double* d_x0,
                    const double* d_U, const double* d_dt, double* d_X);
 int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const double* d_Xref, const double* d_Uref,
                       const double* d_K, const double* d_d, const double* d_dt, int64_t nalpha, const double* d_alphas,
@@ -91,6 +91,6 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
 int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1, const double* d_s2, int64_t st2, double* d_err,
                       double* d_grad, double* d_hess);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
-                     const double* d_dt, double* d_AB);
+                     const double* d_t, const double* d_dt, double* d_AB);
 
 }  // namespace rbq

@@ -26,6 +26,9 @@ __host__ __device__ inline int model_state_dim(const rbq_model_params& p) {
     case RBQ_MODEL_SPIN30:
         if (p.sample_state_count < 1 || p.sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
         return 15 + 41 * p.sample_state_count;
+    case RBQ_MODEL_SPIN25:   // spin25.jl:28-33,73-75: 2 states + 3 controls + 6 filter taps + 41 per sample state
+        if (p.sample_state_count < 1 || p.sample_state_count > RBQ_MAX_SAMPLE_STATES) return RBQ_E_MODEL;
+        return 17 + 41 * p.sample_state_count;
     default: return RBQ_E_MODEL;
     }
 }
@@ -131,7 +134,96 @@ template <class T, class IO> RBQ_DEV void step_spin11_17(const rbq_model_params&
         io.out(dst, o0); io.out(dst + 1, o1); io.out(dst + 2, o2); io.out(dst + 3, o3);
     }
 }
-// ---- spin30: unscented transform ---------------------------------------------------------------
+// ---- unscented transform of one sample-state chunk (spin30.jl:86-174, spin25.jl:91-178) --------------------------
+// 10 sigma points at `off`, propagated with E except points 5 and 10 (Ep / En), then mean, covariance, Cholesky,
+// resampling, normalisation and the penalty against the nominal block `nom` of the INPUT state.
+template <class T, class IO>
+RBQ_DEV void unscented_chunk(const rbq_model_params& p, IO& io, int off, int nom, const Prop<T>& E, const Prop<T>& Ep,
+                             const Prop<T>& En) {
+    const double cf = 1.0 / (2.0 * p.alpha * p.alpha);
+    T s[10][4];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const Prop<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
+        prop_apply<T>(M, io.x(off + 4 * j), io.x(off + 4 * j + 1), io.x(off + 4 * j + 2), io.x(off + 4 * j + 3),
+                      s[j][0], s[j][1], s[j][2], s[j][3]);
+    }
+    T sm[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        T acc = s[0][i];
+#pragma unroll
+        for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
+        sm[i] = acc * 0.1;
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[j][i] = s[j][i] - sm[i];
+    // lower triangle of the 4x4 sample covariance (row-major packed: 00 10 11 20 21 22 30 31 32 33)
+    T P[10];
+    {
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k <= i; ++k) {
+                T acc = s[0][i] * s[0][k];
+#pragma unroll
+                for (int j = 1; j < 10; ++j) acc = acc + s[j][i] * s[j][k];
+                P[q++] = acc * cf;
+            }
+    }
+    // Cholesky of blkdiag(P, parameter variance): the 5th row/column decouples exactly, so only the 4x4 factor is
+    // needed (spin30.jl:136-140, spin25.jl:141-146).  L packed like P.
+    T L[10];
+#define RBQ_TRI(i, k) ((i) * ((i) + 1) / 2 + (k))
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T d = P[RBQ_TRI(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = d - L[RBQ_TRI(j, k)] * L[RBQ_TRI(j, k)];
+        const T ljj = tsqrt(d);
+        L[RBQ_TRI(j, j)] = ljj;
+        const T inv = 1.0 / ljj;
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+            T t = P[RBQ_TRI(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = t - L[RBQ_TRI(i, k)] * L[RBQ_TRI(j, k)];
+            L[RBQ_TRI(i, j)] = t * inv;
+        }
+    }
+    // resample sm +- alpha L[:,j], s5 = s10 = sm, normalise each
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        T vp[4], vm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j < 4 && i >= j) {
+                const T col = L[RBQ_TRI(i, j)] * p.alpha;
+                vp[i] = sm[i] + col; vm[i] = sm[i] - col;
+            } else { vp[i] = sm[i]; vm[i] = sm[i]; }
+        }
+        const T np = 1.0 / tsqrt(vp[0] * vp[0] + vp[1] * vp[1] + vp[2] * vp[2] + vp[3] * vp[3]);
+        const T nm = (j < 4) ? 1.0 / tsqrt(vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[3] * vm[3]) : np;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            io.out(off + 4 * j + i, vp[i] * np);
+            io.out(off + 4 * (j + 5) + i, vm[i] * nm);
+        }
+    }
+#undef RBQ_TRI
+    // penalty = tr(P S) + (sm - psi_nom)' S (sm - psi_nom), psi_nom from the INPUT state
+    T pen = P[0] * p.S_diag[0] + P[2] * p.S_diag[1] + P[5] * p.S_diag[2] + P[9] * p.S_diag[3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T dn = sm[i] - io.x(nom + i);
+        pen = pen + dn * dn * p.S_diag[i];
+    }
+    io.out(off + 40, pen);
+}
+// ---- spin30: unscented sampling in fq ----------------------------------------------------------------------------
 template <class T, class IO> RBQ_DEV void step_spin30(const rbq_model_params& p, IO& io, double dt) {
     const T a = io.x(13);
     const Prop<T> E = prop_of<T, double>(p.fq, a, dt);
@@ -142,100 +234,51 @@ template <class T, class IO> RBQ_DEV void step_spin30(const rbq_model_params& p,
     const double sig = sqrt(p.fq_cov);   // used as a deviation WITHOUT alpha, spin30.jl:102,108,113
     const Prop<T> Ep = prop_of<T, double>(p.fq + sig, a, dt);
     const Prop<T> En = prop_of<T, double>(p.fq - sig, a, dt);
-    const double cf = 1.0 / (2.0 * p.alpha * p.alpha);
-    for (int c = 0; c < p.sample_state_count; ++c) {
-        const int off = 15 + 41 * c;
-        T s[10][4];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            const Prop<T>& M = (j == 4) ? Ep : (j == 9) ? En : E;
-            prop_apply<T>(M, io.x(off + 4 * j), io.x(off + 4 * j + 1), io.x(off + 4 * j + 2), io.x(off + 4 * j + 3),
-                          s[j][0], s[j][1], s[j][2], s[j][3]);
-        }
-        T sm[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            T acc = s[0][i];
-#pragma unroll
-            for (int j = 1; j < 10; ++j) acc = acc + s[j][i];
-            sm[i] = acc * 0.1;
-        }
-#pragma unroll
-        for (int j = 0; j < 10; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s[j][i] = s[j][i] - sm[i];
-        // lower triangle of the 4x4 sample covariance (row-major packed: 00 10 11 20 21 22 30 31 32 33)
-        T P[10];
-        {
-            int q = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k <= i; ++k) {
-                    T acc = s[0][i] * s[0][k];
-#pragma unroll
-                    for (int j = 1; j < 10; ++j) acc = acc + s[j][i] * s[j][k];
-                    P[q++] = acc * cf;
-                }
-        }
-        // Cholesky of blkdiag(P, fq_cov): the 5th row/column decouples exactly, so only the 4x4
-        // factor is needed (spin30.jl:136-140).  L packed like P.
-        T L[10];
-#define RBQ_TRI(i, k) ((i) * ((i) + 1) / 2 + (k))
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            T d = P[RBQ_TRI(j, j)];
-#pragma unroll
-            for (int k = 0; k < j; ++k) d = d - L[RBQ_TRI(j, k)] * L[RBQ_TRI(j, k)];
-            const T ljj = tsqrt(d);
-            L[RBQ_TRI(j, j)] = ljj;
-            const T inv = 1.0 / ljj;
-#pragma unroll
-            for (int i = j + 1; i < 4; ++i) {
-                T t = P[RBQ_TRI(i, j)];
-#pragma unroll
-                for (int k = 0; k < j; ++k) t = t - L[RBQ_TRI(i, k)] * L[RBQ_TRI(j, k)];
-                L[RBQ_TRI(i, j)] = t * inv;
-            }
-        }
-        // resample sm +- alpha L[:,j], s5 = s10 = sm, normalise each (spin30.jl:141-166)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            T vp[4], vm[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (j < 4 && i >= j) {
-                    const T col = L[RBQ_TRI(i, j)] * p.alpha;
-                    vp[i] = sm[i] + col; vm[i] = sm[i] - col;
-                } else { vp[i] = sm[i]; vm[i] = sm[i]; }
-            }
-            const T np = 1.0 / tsqrt(vp[0] * vp[0] + vp[1] * vp[1] + vp[2] * vp[2] + vp[3] * vp[3]);
-            const T nm = (j < 4) ? 1.0 / tsqrt(vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[3] * vm[3]) : np;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                io.out(off + 4 * j + i, vp[i] * np);
-                io.out(off + 4 * (j + 5) + i, vm[i] * nm);
-            }
-        }
-#undef RBQ_TRI
-        // penalty = tr(P S) + (sm - psi_nom)' S (sm - psi_nom), psi_nom from the INPUT state
-        T pen = P[0] * p.S_diag[0] + P[2] * p.S_diag[1] + P[5] * p.S_diag[2] + P[9] * p.S_diag[3];
-        const int nom = p.nominal_offset[c];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const T dn = sm[i] - io.x(nom + i);
-            pen = pen + dn * dn * p.S_diag[i];
-        }
-        io.out(off + 40, pen);
+    for (int c = 0; c < p.sample_state_count; ++c) unscented_chunk<T>(p, io, 15 + 41 * c, p.nominal_offset[c], E, Ep, En);
+}
+// knot index the reference derives from the time argument: Int(div(time, dt)) (spin25.jl:196); Julia's float `div` is
+// round((x - rem(x, y)) / y)
+__host__ __device__ inline long long knot_point_of(double time, double dt) {
+    return (long long)rint((time - fmod(time, dt)) / dt);
+}
+// ---- spin25: unscented sampling in the amplitude, pink-filtered noise amplitude carried in the state ------------------
+// state: psi1 0..3, psi2 4..7, [int a, a, da] 8..10, filter inputs xp1..3 11..13, outputs yp1..3 14..16, chunks at 17+41c
+template <class T, class IO> RBQ_DEV void step_spin25(const rbq_model_params& p, IO& io, double time, double dt) {
+    const T camp = io.x(9);
+    const Prop<T> E = prop_of<T, double>(p.fq, camp, dt);
+    advance_block<T>(E, io, 0);
+    advance_block<T>(E, io, 4);
+    control_chain<T, double>(io, 8, dt);
+    // filter white noise (spin25.jl:194-219): x_k = sqrt(wnamp_cov) is a constant input, the taps are states
+    const double xk = sqrt(p.fq_cov);    // `fq_cov` carries wnamp_cov for this model (include/rbq.h)
+    const long long kp = knot_point_of(time, dt);
+    const T xp1 = io.x(11), xp2 = io.x(12), xp3 = io.x(13), yp1 = io.x(14), yp2 = io.x(15), yp3 = io.x(16);
+    T yk = T(0.049922035 * xk);
+    if (kp == 1) {
+    } else if (kp == 2) {
+        yk = yk + xp1 * (-0.095993537) - yp1 * (-2.494956002);
+    } else if (kp == 3) {
+        yk = yk + xp1 * (-0.095993537) + xp2 * 0.050612699 - yp1 * (-2.494956002) - yp2 * 2.017265875;
+    } else {
+        yk = yk + xp1 * (-0.095993537) + xp2 * 0.050612699 + xp3 * (-0.004408786) - yp1 * (-2.494956002) - yp2 * 2.017265875 -
+             yp3 * (-0.522189400);
     }
+    io.out(11, T(xk)); io.out(12, xp1); io.out(13, xp2);
+    io.out(14, yk); io.out(15, yp1); io.out(16, yp2);
+    const T namp = yk * p.namp;
+    const Prop<T> Ep = prop_of<T, double>(p.fq, camp + namp, dt);
+    const Prop<T> En = prop_of<T, double>(p.fq, camp - namp, dt);
+    for (int c = 0; c < p.sample_state_count; ++c) unscented_chunk<T>(p, io, 17 + 41 * c, p.nominal_offset[c], E, Ep, En);
 }
 
 // MODEL is the reference file number (RBQ_MODEL_*); one kernel instantiation per model family.
-template <int MODEL, class T, class IO> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double dt) {
+// `time` is used by spin25 only (every other reference model ignores its time argument).
+template <int MODEL, class T, class IO> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double time, double dt) {
     if (MODEL == RBQ_MODEL_SPIN13) step_spin13<T>(p, io, dt);
     else if (MODEL == RBQ_MODEL_SPIN12) step_spin12_18<T>(p, io, dt);   // also spin18
     else if (MODEL == RBQ_MODEL_SPIN15) step_spin15<T>(p, io, dt);
     else if (MODEL == RBQ_MODEL_SPIN11) step_spin11_17<T>(p, io, dt);   // also spin17
+    else if (MODEL == RBQ_MODEL_SPIN25) step_spin25<T>(p, io, time, dt);
     else step_spin30<T>(p, io, dt);
 }
 

@@ -44,7 +44,7 @@ template <int NT> struct TangentIO {
 
 // ---- kernels ------------------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n, int m, int64_t B, int64_t N,
+__global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n, int m, int64_t B, int64_t N, double t0,
                                                       const double* __restrict__ x0, const double* __restrict__ U,
                                                       const double* __restrict__ dt, double* __restrict__ X) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,23 +52,25 @@ __global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n,
     double* Xb = X + (size_t)b * N * n;
     for (int i = 0; i < n; ++i) Xb[i] = x0[(size_t)b * n + i];
     const double* Ub = U + (size_t)b * (N - 1) * m;
+    double time = t0;
     for (int64_t k = 0; k + 1 < N; ++k) {
         ValueIO io{Xb + k * n, Ub + k * m, Xb + (k + 1) * n};
-        model_step<MODEL, double>(p, io, dt[k]);
+        model_step<MODEL, double>(p, io, time, dt[k]);
+        time = time + dt[k];
     }
 }
 
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int n, int m, int lanes_per_knot,
                                                         int64_t K, const double* __restrict__ X,
-                                                        const double* __restrict__ U, const double* __restrict__ dt,
-                                                        double* __restrict__ AB) {
+                                                        const double* __restrict__ U, const double* __restrict__ tk,
+                                                        const double* __restrict__ dt, double* __restrict__ AB) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t k = t / lanes_per_knot;
     if (k >= K) return;
     const int lane = (int)(t - k * lanes_per_knot);
     TangentIO<NT> io{X + k * n, U + k * m, AB + (size_t)k * n * (n + m), n, n + m, lane * NT};
-    model_step<MODEL, Tan<NT>>(p, io, dt[k]);
+    model_step<MODEL, Tan<NT>>(p, io, tk ? tk[k] : 0.0, dt[k]);
 }
 
 // Same computation, but a block stages the [A_k B_k] blocks of G consecutive knots in shared memory and writes them out
@@ -76,8 +78,8 @@ __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int 
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(256) jacobians_staged_kernel(rbq_model_params p, int n, int m, int lanes_per_knot, int G,
                                                                int64_t K, const double* __restrict__ X,
-                                                               const double* __restrict__ U, const double* __restrict__ dt,
-                                                               double* __restrict__ AB) {
+                                                               const double* __restrict__ U, const double* __restrict__ tk,
+                                                               const double* __restrict__ dt, double* __restrict__ AB) {
     extern __shared__ __align__(16) double stage[];
     const int blk = n * (n + m);
     const int64_t k0 = (int64_t)blockIdx.x * G;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) jacobians_staged_kernel(rbq_model_params 
     const int64_t k = k0 + g;
     if (g < G && k < K) {
         TangentIO<NT> io{X + k * n, U + k * m, stage + (size_t)g * blk, n, n + m, lane * NT};
-        model_step<MODEL, Tan<NT>>(p, io, dt[k]);
+        model_step<MODEL, Tan<NT>>(p, io, tk ? tk[k] : 0.0, dt[k]);
     }
     __syncthreads();
     const int64_t here = (K - k0) < G ? (K - k0) : G;
@@ -149,6 +151,7 @@ static inline int family(int model_id) {
     case RBQ_MODEL_SPIN15: return RBQ_MODEL_SPIN15;
     case RBQ_MODEL_SPIN11: case RBQ_MODEL_SPIN17: return RBQ_MODEL_SPIN11;
     case RBQ_MODEL_SPIN30: return RBQ_MODEL_SPIN30;
+    case RBQ_MODEL_SPIN25: return RBQ_MODEL_SPIN25;
     }
     return -1;
 }
@@ -159,25 +162,26 @@ static inline int family(int model_id) {
     case RBQ_MODEL_SPIN15: { CALL(RBQ_MODEL_SPIN15); break; }            \
     case RBQ_MODEL_SPIN11: { CALL(RBQ_MODEL_SPIN11); break; }            \
     case RBQ_MODEL_SPIN30: { CALL(RBQ_MODEL_SPIN30); break; }            \
+    case RBQ_MODEL_SPIN25: { CALL(RBQ_MODEL_SPIN25); break; }            \
     default: return RBQ_E_MODEL;                                         \
     }
 
 // one warp per trajectory up to this many trajectories; beyond it one thread per trajectory has the better throughput
 static const int64_t WARP_ROLLOUT_MAX = 1 << 16;
 
-int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, const double* d_x0,
+int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t N, double t0, const double* d_x0,
                    const double* d_U, const double* d_dt, double* d_X) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     if (B <= WARP_ROLLOUT_MAX) {
-        WarpRolloutArgs a{p, n, m, N, B, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
+        WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
 #define CALL(M) warp_rollout_kernel<M, false><<<(unsigned)B, 32, 0, h->stream>>>(a)
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     } else {
         const int threads = 128;
         const unsigned blocks = (unsigned)((B + threads - 1) / threads);
-#define CALL(M) rollout_kernel<M><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, d_x0, d_U, d_dt, d_X)
+#define CALL(M) rollout_kernel<M><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, t0, d_x0, d_U, d_dt, d_X)
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     }
@@ -191,7 +195,7 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     // one step-size candidate per warp, one warp per block so that candidates spread over SMs
-    WarpRolloutArgs a{p, n, m, N, nalpha, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
+    WarpRolloutArgs a{p, n, m, N, nalpha, 0.0, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
 #define CALL(M) warp_rollout_kernel<M, true><<<(unsigned)nalpha, 32, 0, h->stream>>>(a)
     RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
@@ -203,12 +207,12 @@ static const int JAC_STAGE_BYTES = 200 * 1024;   // shared memory a staging bloc
 static const int64_t JAC_STAGED_MIN_KNOTS = 4096;  // below this the launch is latency bound and the direct kernel is as fast
 
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
-                     const double* d_dt, double* d_AB) {
+                     const double* d_t, const double* d_dt, double* d_AB) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     const int fam = family(p.model_id);
     // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
-    const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
+    const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
     const int lpk = (n + m + nt - 1) / nt;
     const int blk_bytes = n * (n + m) * (int)sizeof(double);
     int G = JAC_STAGE_BYTES / blk_bytes;
@@ -224,7 +228,7 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         cudaError_t e = cudaFuncSetAttribute(jacobians_staged_kernel<M, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                              JAC_STAGE_BYTES);                                                                 \
         if (e != cudaSuccess) return (int)e;                                                                                   \
-        jacobians_staged_kernel<M, NT_><<<blocks, threads, smem, h->stream>>>(p, n, m, lpk, G, K, d_X, d_U, d_dt, d_AB);       \
+        jacobians_staged_kernel<M, NT_><<<blocks, threads, smem, h->stream>>>(p, n, m, lpk, G, K, d_X, d_U, d_t, d_dt, d_AB);       \
     }
         switch (fam) {
         case RBQ_MODEL_SPIN13: CALLS(RBQ_MODEL_SPIN13, 4); break;
@@ -232,6 +236,7 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         case RBQ_MODEL_SPIN11: CALLS(RBQ_MODEL_SPIN11, 4); break;
         case RBQ_MODEL_SPIN12: CALLS(RBQ_MODEL_SPIN12, 2); break;
         case RBQ_MODEL_SPIN30: CALLS(RBQ_MODEL_SPIN30, 2); break;
+        case RBQ_MODEL_SPIN25: CALLS(RBQ_MODEL_SPIN25, 2); break;
         default: return RBQ_E_MODEL;
         }
 #undef CALLS
@@ -239,14 +244,15 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         const int threads = 128;
         const int64_t total = K * lpk;
         const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-#define CALL2(M) jacobians_kernel<M, 2><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
-#define CALL4(M) jacobians_kernel<M, 4><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_dt, d_AB)
+#define CALL2(M) jacobians_kernel<M, 2><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_t, d_dt, d_AB)
+#define CALL4(M) jacobians_kernel<M, 4><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_t, d_dt, d_AB)
         switch (fam) {
         case RBQ_MODEL_SPIN13: CALL4(RBQ_MODEL_SPIN13); break;
         case RBQ_MODEL_SPIN15: CALL4(RBQ_MODEL_SPIN15); break;
         case RBQ_MODEL_SPIN11: CALL4(RBQ_MODEL_SPIN11); break;
         case RBQ_MODEL_SPIN12: CALL2(RBQ_MODEL_SPIN12); break;
         case RBQ_MODEL_SPIN30: CALL2(RBQ_MODEL_SPIN30); break;
+        case RBQ_MODEL_SPIN25: CALL2(RBQ_MODEL_SPIN25); break;
         default: return RBQ_E_MODEL;
         }
 #undef CALL2

@@ -29,6 +29,7 @@ struct WarpRolloutArgs {
     rbq_model_params p;
     int n, m;
     int64_t N, count;            // knots per trajectory, number of trajectories / candidates
+    double t0;                   // time of knot 0 (knot times accumulate: t[k+1] = t[k] + dt[k])
     const double* x0;            // open loop: [count][n];  closed loop: Xref [N][n]
     const double* U;             // open loop: [count][N-1][m];  closed loop: Uref [N-1][m]
     const double* K;             // closed loop: [N-1] blocks, column-major m x n
@@ -46,10 +47,13 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
     const int64_t tr = blockIdx.x;
     const int n = a.n, m = a.m;
     const int64_t N = a.N;
-    constexpr bool U30 = (MODEL == RBQ_MODEL_SPIN30);
-    constexpr int NCH = U30 ? RBQ_MAX_SAMPLE_STATES : 1;   // sigma-point chunks a lane may hold
+    constexpr bool S25 = (MODEL == RBQ_MODEL_SPIN25);
+    constexpr bool U30 = (MODEL == RBQ_MODEL_SPIN30) || S25;   // the unscented models (sigma points on lanes 0..9)
+    constexpr int NCH = U30 ? RBQ_MAX_SAMPLE_STATES : 1;       // sigma-point chunks a lane may hold
+    constexpr int UB = S25 ? 17 : 15;                          // offset of the first sigma-point chunk
+    constexpr int NNOM = S25 ? 2 : 3;                          // nominal blocks (lanes 10..)
     const int ssc = U30 ? p.sample_state_count : 1;
-    const int cb = U30 ? 12 : 8;                            // [int a, a, da] chain base
+    const int cb = (U30 && !S25) ? 12 : 8;                     // [int a, a, da] chain base
 
     // ---- lane roles ---------------------------------------------------------------------------------
     int off = -1;                 // state offset of this lane's block (chunk 0 for sigma lanes)
@@ -69,8 +73,10 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
         else if (lane - 2 < p.derivative_order) off = 11 + 4 * (lane - 2);
     } else {
         const double sig = sqrt(p.fq_cov);
-        if (lane < 10) { off = 15 + 4 * lane; if (lane == 4) f = p.fq + sig; if (lane == 9) f = p.fq - sig; }
-        else if (lane < 13) off = 4 * (lane - 10);
+        if (lane < 10) {
+            off = UB + 4 * lane;
+            if (!S25) { if (lane == 4) f = p.fq + sig; if (lane == 9) f = p.fq - sig; }   // spin25 shifts the amplitude instead (per knot)
+        } else if (lane < 10 + NNOM) off = 4 * (lane - 10);
     }
     const bool sigma_lane = U30 && lane < 10;
     const bool has_block = off >= 0;
@@ -101,7 +107,11 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
     double gacc = DA ? x0[11] : 0.0;
     double pen[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) pen[c] = (U30 && c < ssc) ? x0[15 + 41 * c + 40] : 0.0;
+    for (int c = 0; c < NCH; ++c) pen[c] = (U30 && c < ssc) ? x0[UB + 41 * c + 40] : 0.0;
+    // spin25: pink-filter taps xp1..3 (11..13), yp1..3 (14..16), carried by every lane
+    double fx1 = 0, fx2 = 0, fx3 = 0, fy1 = 0, fy2 = 0, fy3 = 0;
+    if (S25) { fx1 = x0[11]; fx2 = x0[12]; fx3 = x0[13]; fy1 = x0[14]; fy2 = x0[15]; fy3 = x0[16]; }
+    double time = a.t0;
     // knot 0
     for (int i = lane; i < n; i += 32) X[i] = x0[i];
 
@@ -140,7 +150,12 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                 if (U30) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c)
-                        if (c < ssc) { const int idx = 15 + 41 * c + 40; s0 = fma(Kk[idx * m], pen[c] - xr[idx], s0); }
+                        if (c < ssc) { const int idx = UB + 41 * c + 40; s0 = fma(Kk[idx * m], pen[c] - xr[idx], s0); }
+                }
+                if (S25) {
+                    const double taps[6] = {fx1, fx2, fx3, fy1, fy2, fy3};
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) s0 = fma(Kk[(11 + i) * m], taps[i] - xr[11 + i], s0);
                 }
             }
             s0 = warp_sum(s0);
@@ -155,6 +170,26 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
         if (k + 2 < N) dt_n = a.dt[k + 1];
         double* Xn = X + (k + 1) * n;
 
+        // ---- spin25: advance the pink filter (spin25.jl:194-219); its output scales the amplitude offset of points 5, 10
+        if (S25) {
+            const double xk = sqrt(p.fq_cov);
+            const long long kp = knot_point_of(time, dt);
+            double yk = 0.049922035 * xk;
+            if (kp == 1) {
+            } else if (kp == 2) {
+                yk = yk + fx1 * (-0.095993537) - fy1 * (-2.494956002);
+            } else if (kp == 3) {
+                yk = yk + fx1 * (-0.095993537) + fx2 * 0.050612699 - fy1 * (-2.494956002) - fy2 * 2.017265875;
+            } else {
+                yk = yk + fx1 * (-0.095993537) + fx2 * 0.050612699 + fx3 * (-0.004408786) - fy1 * (-2.494956002) - fy2 * 2.017265875 -
+                     fy3 * (-0.522189400);
+            }
+            fx3 = fx2; fx2 = fx1; fx1 = xk; fy3 = fy2; fy2 = fy1; fy1 = yk;
+            const double namp = yk * p.namp;
+            da_l = lane == 4 ? namp : (lane == 9 ? -namp : 0.0);
+            if (lane == 0) { Xn[11] = fx1; Xn[12] = fx2; Xn[13] = fx3; Xn[14] = fy1; Xn[15] = fy2; Xn[16] = fy3; }
+            time = time + dt;
+        }
         // ---- this lane's propagator and block ---------------------------------------------------------
         const Prop<double> E = prop_of<double, double>(f, ca + da_l, dt);
         double in0[4] = {psi[0][0], psi[0][1], psi[0][2], psi[0][3]};   // block value at knot k (chunk 0)
@@ -181,8 +216,8 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                 for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
             }
         } else {
-            // nominal lanes 10..12
-            if (lane >= 10 && lane < 13) {
+            // nominal lanes 10..
+            if (lane >= 10 && lane < 10 + NNOM) {
                 prop_apply<double>(E, in0[0], in0[1], in0[2], in0[3], psi[0][0], psi[0][1], psi[0][2], psi[0][3]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
@@ -247,7 +282,7 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                     pv = fma(dn * dn, p.S_diag[i], pv);
                 }
                 pen[c] = pv;
-                if (lane == 0) Xn[15 + 41 * c + 40] = pv;
+                if (lane == 0) Xn[UB + 41 * c + 40] = pv;
             }
         }
         // ---- scalar tail -----------------------------------------------------------------------------------

@@ -163,22 +163,26 @@ class Engine:
                                                   na, _ptr(alphas), _ptr(X), _ptr(Uo)), "rbq_rollout_closedloop")
         return X, Uo
 
-    def jacobians(self, p, X, U, dt):
-        """X (K,n), U (K,m), dt (K,) -> (K, n, n+m)."""
+    def jacobians(self, p, X, U, dt, t=None):
+        """X (K,n), U (K,m), dt (K,), t (K,) knot times or None -> (K, n, n+m).  Only spin25 reads t."""
         n, m = self._dims(p)
         X, U, dt = _f64(X).reshape(-1, n), _f64(U).reshape(-1, m), _f64(dt)
         K = X.shape[0]
         if U.shape[0] != K or dt.shape != (K,):
             raise ValueError("X, U, dt disagree on the knot count")
+        if t is not None:
+            t = _f64(t)
+            if t.shape != (K,):
+                raise ValueError("t must have one entry per knot")
         ab = np.empty((K, n + m, n))
-        self._ck(self._lib.rbq_jacobians(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(dt), _ptr(ab)), "rbq_jacobians")
+        self._ck(self._lib.rbq_jacobians(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(t), _ptr(dt), _ptr(ab)), "rbq_jacobians")
         return ab.transpose(0, 2, 1)
 
     def rollout_dev(self, p, B, N, x0, U, dt, X):
         self._ck(self._lib.rbq_rollout_dev(self._h, C.byref(p), B, N, _ptr(x0), _ptr(U), _ptr(dt), _ptr(X)), "rbq_rollout_dev")
 
-    def jacobians_dev(self, p, K, X, U, dt, AB):
-        self._ck(self._lib.rbq_jacobians_dev(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(dt), _ptr(AB)), "rbq_jacobians_dev")
+    def jacobians_dev(self, p, K, X, U, dt, AB, t=None):
+        self._ck(self._lib.rbq_jacobians_dev(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(t), _ptr(dt), _ptr(AB)), "rbq_jacobians_dev")
 
     # ---- cost-side primitives (spin.jl:1040-1092) ---------------------------------------------------------------
     def gate_error_expansion(self, s1, s2, want_grad=True, want_hess=True):

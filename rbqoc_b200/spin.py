@@ -6,7 +6,7 @@ beyond building inputs).  Citations are file:line in SchusterLab/rbqoc.
 
   constants / operators        src/spin/spin.jl:122-345
   Model, state_dim, ...        src/spin/spin13.jl:37-40, spin12.jl:52-56, spin30.jl:60-70, spin15.jl:40-46,
-                               spin11.jl:51-57, spin17.jl, spin18.jl:50-55
+                               spin11.jl:51-57, spin17.jl, spin18.jl:50-55, spin25.jl:67-75
   discrete_dynamics            RD.discrete_dynamics(::Type{RK3}, model, x, u, t, dt)  (spin13.jl:44-58 ...)
   discrete_jacobian            RD.discrete_jacobian!(::Type{RK3}, ∇f, model, z) (RobotDynamics default: ForwardDiff)
   run_sim_prop / evaluate_*    src/spin/spin.jl:1553-1672
@@ -160,6 +160,19 @@ def Spin30Model(S_diag=(1.0, 1.0, 1.0, 1.0), nominal_idxs=None, fq_cov=FQ * 1e-2
                          nominal_offset=tuple(int(i) - 1 for i in nominal_idxs)), "spin30")
 
 
+def Spin25Model(S_diag=(1.0, 1.0, 1.0, 1.0), nominal_idxs=None, namp=NAMP_PREFACTOR, wnamp_cov=1.0, alpha=1.0,
+                sample_state_count=1, fq=FQ) -> Model:
+    """spin25.jl:67-74: unscented sampling of the amplitude noise; the noise amplitude is namp times the output of the
+    pink filter driven by sqrt(wnamp_cov), whose taps are part of the state.  The only model that reads its time argument."""
+    if nominal_idxs is None:
+        nominal_idxs = [1] * sample_state_count
+    if len(nominal_idxs) != sample_state_count:
+        raise ValueError("one nominal index block per sample state")
+    return Model(_params(model_id=_lib.MODEL_SPIN25, fq=fq, namp=namp, fq_cov=wnamp_cov, alpha=alpha,
+                         sample_state_count=int(sample_state_count), S_diag=tuple(S_diag),
+                         nominal_offset=tuple(int(i) - 1 for i in nominal_idxs)), "spin25")
+
+
 def state_dim(model: Model) -> int:
     n = Engine.state_dim(model.params)
     if n < 0:
@@ -216,12 +229,23 @@ def rollout(model: Model, x0, U, dt, engine: Engine | None = None):
     return (engine or default_engine()).rollout(model.params, x0, U, dts)
 
 
+def knot_times(dts):
+    """z.t of a TO.Traj: t_1 = 0, t_{k+1} = t_k + dt_k (accumulated, as the engine's rollouts do)."""
+    dts = np.asarray(dts, dtype=np.float64)
+    t = np.zeros(dts.shape[0])
+    acc = 0.0
+    for k in range(dts.shape[0]):
+        t[k] = acc
+        acc = acc + dts[k]
+    return t
+
+
 def dynamics_expansion(model: Model, X, U, dt, engine: Engine | None = None):
     """TO.dynamics_expansion!: ∇f_k for k = 1..N-1 in one call.  X (N,n) or (N-1,n); U (N-1,m)."""
     X, U = np.asarray(X, dtype=np.float64), np.asarray(U, dtype=np.float64)
     K = U.shape[0]
-    dts = np.full(K, float(dt)) if np.isscalar(dt) else dt
-    return (engine or default_engine()).jacobians(model.params, X[:K], U, dts)
+    dts = np.full(K, float(dt)) if np.isscalar(dt) else np.asarray(dt, dtype=np.float64)
+    return (engine or default_engine()).jacobians(model.params, X[:K], U, dts, t=knot_times(dts))
 
 
 # initial augmented states the reference's run_traj builds
@@ -241,6 +265,16 @@ def spin30_x0(state_cov=1e-2, rng=None):
         s = IS1_ISO + math.sqrt(state_cov) * rng.standard_normal(4)
         pts.append(s / np.linalg.norm(s))
     return np.concatenate([IS1_ISO, IS2_ISO, IS3_ISO, np.zeros(3)] + pts + [np.zeros(1)])
+
+
+def spin25_x0(state_cov=1e-2, rng=None):
+    """spin25.jl run_traj: nominal IS1, IS2 + zeros(3) + zero filter taps + 10 sigma points around IS1 + penalty slot."""
+    rng = rng or np.random.default_rng(0)
+    pts = []
+    for _ in range(10):
+        s = IS1_ISO + math.sqrt(state_cov) * rng.standard_normal(4)
+        pts.append(s / np.linalg.norm(s))
+    return np.concatenate([IS1_ISO, IS2_ISO, np.zeros(3), np.zeros(6)] + pts + [np.zeros(1)])
 
 
 # ---- analytic pulses (spin14.py:60-241), sampled at DT = 1/dt_inv ------------------------------------------

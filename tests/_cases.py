@@ -18,6 +18,10 @@ MODEL_KW = {
                    nominal_offset=(0, 0, 0, 0)),
     "spin30_x2": dict(model_id=30, fq_cov=1.4e-4, alpha=1.3, S_diag=(1.0, 1.0, 1.0, 1.0), sample_state_count=2,
                       nominal_offset=(0, 4, 0, 0)),
+    "spin25_k2": dict(model_id=25, fq_cov=1.0, namp=2.574e-2, alpha=1.0, S_diag=(1.0, 2.0, 3.0, 4.0), sample_state_count=1,
+                      nominal_offset=(4, 0, 0, 0)),
+    "spin25_k7": dict(model_id=25, fq_cov=1.0, namp=2.574e-2, alpha=1.2, S_diag=(1.0, 1.0, 1.0, 1.0), sample_state_count=1,
+                      nominal_offset=(0, 0, 0, 0)),
 }
 
 
@@ -27,7 +31,8 @@ def golden_model_cases():
     for name in MODEL_KW:
         for dt in (0.1, 0.01):
             k = f"{name}_dt{dt}"
-            out.append((k, name, dt, z[k + "_x"], z[k + "_u"], z[k + "_xn"], z[k + "_J"]))
+            t = float(z[k + "_t"]) if (k + "_t") in z else 0.0
+            out.append((k, name, dt, z[k + "_x"], z[k + "_u"], z[k + "_xn"], z[k + "_J"], t))
     return out
 
 

@@ -44,14 +44,24 @@ def model_cases():
                                      "nominal_offset": [0, 0, 0, 0]}),
         ("spin30_x2", "spin30", 97, 1, {"fq_cov": 1.4e-4, "alpha": 1.3, "S_diag": [1.0, 1.0, 1.0, 1.0], "sample_state_count": 2,
                                         "nominal_offset": [0, 4, 0, 0]}),
+        # spin25: time-dependent filter start-up branch (knot 2) and the steady branch (knot 7); namp exaggerated so that the
+        # amplitude-offset sigma points matter
+        ("spin25_k2", "spin25", 58, 1, {"fq_cov": 1.0, "namp": 2.574e-2, "alpha": 1.0, "S_diag": [1.0, 2.0, 3.0, 4.0],
+                                        "sample_state_count": 1, "nominal_offset": [4, 0, 0, 0], "knot": 2}),
+        ("spin25_k7", "spin25", 58, 1, {"fq_cov": 1.0, "namp": 2.574e-2, "alpha": 1.2, "S_diag": [1.0, 1.0, 1.0, 1.0],
+                                        "sample_state_count": 1, "nominal_offset": [0, 0, 0, 0], "knot": 7}),
     ]
     for name, model, n, m, kw in specs:
         for dt in (0.1, 0.01):
             x = rng.standard_normal(n) * 0.3
-            if model == "spin30":
-                x[12:15] = rng.uniform(-0.4, 0.4, 3)
+            if model in ("spin30", "spin25"):
+                base = 15 if model == "spin30" else 17
+                if model == "spin30":
+                    x[12:15] = rng.uniform(-0.4, 0.4, 3)
+                else:
+                    x[8:11] = rng.uniform(-0.4, 0.4, 3)
                 for c in range(kw["sample_state_count"]):
-                    off = 15 + 41 * c
+                    off = base + 41 * c
                     for j in range(10):
                         s = np.array([1.0, 0, 0, 0]) + 0.1 * rng.standard_normal(4)
                         x[off + 4 * j: off + 4 * j + 4] = s / np.linalg.norm(s)
@@ -62,7 +72,14 @@ def model_cases():
             if kw.get("time_optimal"):
                 u[1] = 0.31
             mkw = {}
+            time = 0.0
+            if "knot" in kw:
+                for _ in range(kw["knot"]):
+                    time = time + dt          # accumulated like the knot times of a trajectory
+                mkw["time"] = F(time)
             for k, v in kw.items():
+                if k == "knot":
+                    continue
                 if isinstance(v, list) and k != "nominal_offset":
                     mkw[k] = [F(t) for t in v]
                 elif isinstance(v, float):
@@ -75,6 +92,7 @@ def model_cases():
             key = f"{name}_dt{dt}"
             cases[key + "_x"] = x
             cases[key + "_u"] = u
+            cases[key + "_t"] = np.float64(time)
             cases[key + "_xn"] = ref.to_f64(xn)
             cases[key + "_J"] = np.array([[float(t) for t in row] for row in J])
             print("model case", key, flush=True)
@@ -107,6 +125,8 @@ def reference_pulses():
 
 def main():
     np.savez_compressed(os.path.join(HERE, "models.npz"), **model_cases())
+    if "--models-only" in sys.argv:
+        return
     pulses = reference_pulses() if os.path.exists("/root/reference/src/spin/spin14.py") else None
     if pulses is not None:
         np.savez_compressed(os.path.join(HERE, "spin14_pulses.npz"), **pulses)

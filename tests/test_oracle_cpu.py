@@ -86,11 +86,11 @@ def test_detuning_gate_error_pin(orc):
 
 @pytest.mark.parametrize("case", golden_model_cases(), ids=lambda c: c[0])
 def test_oracle_step_and_jacobian_match_50_digit_golden(orc, case):
-    key, name, dt, x, u, xn, J = case
+    key, name, dt, x, u, xn, J, t = case
     p = orc.make_params(**MODEL_KW[name])
-    got = orc.step(p, x, u, dt)
+    got = orc.step(p, x, u, dt, t=t)
     assert relerr(got, xn) < 2e-15, key
-    Jg = orc.jacobian(p, x, u, dt)
+    Jg = orc.jacobian(p, x, u, dt, t=t)
     assert Jg.shape == J.shape
     assert relerr(Jg, J) < 1e-13, key
 

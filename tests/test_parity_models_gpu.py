@@ -31,6 +31,8 @@ def _models():
         ("spin17_DO2", spin.Spin17Model(2)),
         ("spin30", spin.Spin30Model(S_diag=(1.0, 2.0, 3.0, 4.0))),
         ("spin30_x2", spin.Spin30Model(sample_state_count=2, nominal_idxs=[1, 5], alpha=1.3)),
+        ("spin25", spin.Spin25Model(S_diag=(1.0, 2.0, 3.0, 4.0), namp=2.574e-2, nominal_idxs=[5])),
+        ("spin25_x2", spin.Spin25Model(sample_state_count=2, nominal_idxs=[1, 5], alpha=1.1, namp=1e-2, wnamp_cov=0.7)),
     ]
 
 
@@ -43,17 +45,23 @@ def _random_point(model, rng, a=None):
     n, m = model.n, model.m
     x = rng.standard_normal(n) * 0.3
     mid = model.params.model_id
-    if mid == 30:
-        x[:12] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO, spin.IS3_ISO]) + 1e-3 * rng.standard_normal(12)
-        x[12:15] = rng.uniform(-0.4, 0.4, 3)
+    if mid in (30, 25):
+        base = 15 if mid == 30 else 17
+        if mid == 30:
+            x[:12] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO, spin.IS3_ISO]) + 1e-3 * rng.standard_normal(12)
+            x[12:15] = rng.uniform(-0.4, 0.4, 3)
+        else:
+            x[:8] = np.concatenate([spin.IS1_ISO, spin.IS2_ISO]) + 1e-3 * rng.standard_normal(8)
+            x[8:11] = rng.uniform(-0.4, 0.4, 3)
+            x[11:17] = rng.uniform(-1.0, 1.0, 6)       # pink-filter taps
         for c in range(model.params.sample_state_count):
-            off = 15 + 41 * c
+            off = base + 41 * c
             for j in range(10):
                 s = spin.IS1_ISO + 0.1 * rng.standard_normal(4)
                 x[off + 4 * j: off + 4 * j + 4] = s / np.linalg.norm(s)
             x[off + 40] = rng.uniform(0, 1e-2)
         if a is not None:
-            x[13] = a
+            x[13 if mid == 30 else 9] = a
     else:
         x[8:11] = rng.uniform(-0.4, 0.4, 3)
         if a is not None:
@@ -117,6 +125,8 @@ def test_rollout_and_batched_jacobians(engine, oracle, name, model):
         x0[:, 8:11] = 0.0
     else:
         x0[:, 12:15] = 0.0
+    if model.params.model_id == 25:
+        x0[:, 11:17] = 0.0          # the reference starts the filter from rest
     U = rng.uniform(-2e-3, 2e-3, (B, N - 1, model.m))
     if model.params.model_id == 15 and model.params.time_optimal:
         U[:, :, 1] = rng.uniform(0.25, 0.35, (B, N - 1))
@@ -125,8 +135,9 @@ def test_rollout_and_batched_jacobians(engine, oracle, name, model):
     assert X.shape == (B, N, model.n)
     assert _relerr(X, Xr) < 5e-12, name    # 300 chained steps
     # all knots of trajectory 0 in one Jacobian call
-    AB = engine.jacobians(model.params, Xr[0, :-1], U[0], dt)
-    ABr = oracle.jacobians(model.params, Xr[0, :-1], U[0], dt)
+    tk = spin.knot_times(dt)
+    AB = engine.jacobians(model.params, Xr[0, :-1], U[0], dt, t=tk)
+    ABr = oracle.jacobians(model.params, Xr[0, :-1], U[0], dt, t=tk)
     assert AB.shape == (N - 1, model.n, model.n + model.m)
     scale = np.max(np.abs(ABr), axis=(1, 2), keepdims=True)
     assert np.max(np.abs(AB - ABr) / scale) < JAC_RTOL, name
@@ -137,11 +148,11 @@ def test_step_and_jacobian_match_50_digit_golden(engine, case):
     """Committed fixtures from the rounding-free referee (tests/golden/make_golden.py)."""
     import rbqoc_b200 as rbq
 
-    key, name, dt, x, u, xn, J = case
+    key, name, dt, x, u, xn, J, t = case
     p = spin._params(**MODEL_KW[name])
-    got = engine.discrete_dynamics(p, x, u, 0.0, dt)
+    got = engine.discrete_dynamics(p, x, u, t, dt)
     assert relerr(got, xn) < 2e-15, key
-    Jg = engine.discrete_jacobian(p, x, u, 0.0, dt)
+    Jg = engine.discrete_jacobian(p, x, u, t, dt)
     assert Jg.shape == J.shape
     assert relerr(Jg, J) < 1e-13, key
 
@@ -158,6 +169,8 @@ def test_closed_loop_rollout(engine, oracle, name, model):
         x0[8:11] = 0.0
     else:
         x0[12:15] = 0.0
+    if model.params.model_id == 25:
+        x0[11:17] = 0.0
     Uref = rng.uniform(-2e-3, 2e-3, (N - 1, model.m))
     if model.params.model_id == 15 and model.params.time_optimal:
         Uref[:, 1] = rng.uniform(0.25, 0.35, N - 1)
@@ -230,6 +243,28 @@ def test_degenerate_sizes(engine):
     assert AB.shape == (0, 43, 44)
     Xb = engine.rollout(model.params, np.empty((0, 43)), np.empty((0, 3, 1)), np.full(3, 0.1))
     assert Xb.shape == (0, 4, 43)
+
+
+def test_spin25_reads_its_time_argument(engine, oracle):
+    """spin25.jl:196-214: Int(div(time, dt)) picks the pink filter's start-up branch, for the step and for its Jacobian."""
+    model = spin.Spin25Model(namp=2.574e-2)
+    rng = np.random.default_rng(3)
+    x, u = _random_point(model, rng)
+    dt = 0.1
+    outs = []
+    for k, t in enumerate(spin.knot_times(np.full(7, dt))):
+        got = engine.discrete_dynamics(model.params, x, u, t, dt)
+        ref = oracle.step(model.params, x, u, dt, t=t)
+        assert _relerr(got, ref) < STATE_RTOL, k
+        J = engine.discrete_jacobian(model.params, x, u, t, dt)
+        Jr = oracle.jacobian(model.params, x, u, dt, t=t)
+        assert _relerr(J, Jr) < JAC_RTOL, k
+        outs.append(got[14])
+        # d y_k / d (xp1, xp2, xp3, yp1, yp2, yp3): taps the start-up branch ignores have zero columns
+        active = {0: 6, 1: 0, 2: 2, 3: 4}.get(k, 6)
+        nz = np.count_nonzero(J[14, 11:17])
+        assert nz == active, (k, nz)
+    assert len(set(np.round(outs[:5], 12))) >= 4          # the branches really differ
 
 
 def test_gate_error_expansion_matches_oracle(engine, oracle):
