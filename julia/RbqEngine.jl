@@ -15,6 +15,7 @@ Usage from a reference script (e.g. src/spin/spin13.jl), after its own `struct M
 module RbqEngine
 
 using StaticArrays
+using LinearAlgebra: diag
 import RobotDynamics
 const RD = RobotDynamics
 

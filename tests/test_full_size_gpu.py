@@ -1,0 +1,96 @@
+"""GPU tests at BASELINE.json's full sizes (the oracle cannot run these in seconds), through size-independent
+properties of the domain: unitarity, exact analytic gates, global-phase invariance, sharding invariance of the
+additive statistics, bit-reproducibility, and for the Lindblad map trace preservation / contraction."""
+import numpy as np
+import pytest
+
+import rbqoc_b200 as rbq
+from rbqoc_b200 import spin
+
+pytestmark = pytest.mark.gpu
+
+S_FULL = 1 << 20          # the bench's 1M-sample sweep
+NK = 1000
+
+
+@pytest.fixture(scope="module")
+def sweep(engine):
+    controls = spin.pulse_sin(NK + 1)[:-1]
+    fq, da, psi0 = engine.philox_samples(0, S_FULL, 2026, spin.FQ, 0.01, 0.03, 2.574e-5)
+    fid, st = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
+    return controls, fq, da, psi0, fid, st
+
+
+def test_full_sweep_statistics_are_those_of_the_fidelities(sweep):
+    controls, fq, da, psi0, fid, st = sweep
+    assert fid.shape == (S_FULL, 2)
+    assert np.all(np.abs(fid[:, 0] - 1.0) < 1e-14)                    # F(psi0, psi0) = |psi0|^4 = 1
+    assert np.all(fid[:, 1] <= 1.0 + 1e-13) and np.all(fid[:, 1] >= -1e-13)
+    e = 1.0 - fid[:, 1]
+    assert st.count == S_FULL and st.nonfinite == 0
+    assert abs(st.sum - e.sum()) < 1e-11 * e.sum()
+    assert abs(st.sumsq - np.sum(e * e)) < 1e-11 * np.sum(e * e)
+    assert st.min == e.min() and st.max == e.max()
+    assert sum(st.hist[:]) == S_FULL
+
+
+def test_full_sweep_is_bit_reproducible(engine, sweep):
+    controls, fq, da, psi0, fid, st = sweep
+    fid2, st2 = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
+    assert np.array_equal(fid, fid2)
+    assert st.sum == st2.sum and st.sumsq == st2.sumsq and st.hist[:] == st2.hist[:]
+
+
+def test_full_sweep_sharding_invariance(engine, sweep):
+    """8 contiguous shards drawn by global Philox index merge to the statistics of the whole (what 8 GPUs compute)."""
+    controls, fq, da, psi0, fid, st = sweep
+    total = None
+    for r in range(8):
+        first, cnt = r * (S_FULL // 8), S_FULL // 8
+        _, part = engine.mc_static_philox(controls, 0.1, rbq.GATE_XPIBY2, 1, first, cnt, 2026, spin.FQ, 0.01, 0.03, 2.574e-5)
+        total = part if total is None else rbq.stats_merge(total, part)
+    assert total.count == st.count and total.hist[:] == st.hist[:]
+    assert total.min == st.min and total.max == st.max
+    assert abs(total.sum - st.sum) < 1e-12 * st.sum
+
+
+def test_full_sweep_global_phase_invariance(engine, sweep):
+    """psi0 -> exp(i phi) psi0 is the iso rotation [[c,-s],[s,c]] (x) 1: fidelities cannot change."""
+    controls, fq, da, psi0, fid, st = sweep
+    phi = 0.7321
+    c, s = np.cos(phi), np.sin(phi)
+    rot = np.concatenate([c * psi0[:, :2] - s * psi0[:, 2:], s * psi0[:, :2] + c * psi0[:, 2:]], axis=1)
+    fid2, _ = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, rot)
+    assert np.max(np.abs(fid2 - fid)) < 1e-13
+
+
+def test_full_sweep_exact_gate_has_unit_fidelity(engine, sweep):
+    """The idle Z/2 of spin.jl:557 at zero detuning, 1M random states, 4 consecutive gates (the 4-cyclic targets)."""
+    _, _, _, psi0, _, _ = sweep
+    n = 1786
+    fid, st = engine.mc_static(np.zeros(n), spin.TTOT_ZPIBY2 / n, rbq.GATE_ZPIBY2, 4, np.full(S_FULL, spin.FQ), None, psi0)
+    assert np.max(np.abs(fid - 1.0)) < 2e-13
+    assert st.max < 2e-13
+
+
+def test_full_size_lindblad_map_properties(engine):
+    """1e5 realisations (BASELINE configs[3]): trace preserved, Bloch vector inside the ball, purity non-increasing for
+    the unital T1 map, fidelities in [0, 1]."""
+    S = 100_000
+    rng = np.random.default_rng(5)
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho0 = np.einsum("si,sj->sij", psi, psi.conj())
+    lam = rng.uniform(0.5, 1.0, S)[:, None, None]
+    rho0 = lam * rho0 + (1 - lam) * np.eye(2) / 2
+    da = 2.574e-5 * rng.standard_normal(S)
+    controls = spin.pulse_sin(NK + 1)[:-1]
+    fid, rho, st = engine.lindblad(controls, 0.1, rbq.GATE_XPIBY2, 3, spin.FQ, da, rho0)
+    assert np.max(np.abs(np.trace(rho, axis1=1, axis2=2) - 1.0)) < 1e-14
+    assert np.max(np.abs(rho - rho.conj().transpose(0, 2, 1))) == 0.0
+    purity0 = np.real(np.einsum("sij,sji->s", rho0, rho0))
+    purity = np.real(np.einsum("sij,sji->s", rho, rho))
+    assert np.all(purity <= purity0 + 1e-14)
+    assert np.all(purity >= 0.5 - 1e-14)
+    assert np.all(fid >= 0.0) and np.all(fid <= 1.0 + 1e-13)
+    assert st.count == S
