@@ -187,6 +187,17 @@ int rbq_gate_error_expansion(rbq_handle* h, int64_t K, const double* s1, int64_t
 int rbq_gate_error_expansion_dev(rbq_handle* h, int64_t K, const double* d_s1, int64_t s1_stride, const double* d_s2,
                                  int64_t s2_stride, double* d_err, double* d_grad, double* d_hess);
 
+/* TO.stage_cost and TO.gradient! of the sampling objective `Cost` (spin12.jl:59-161, spin18.jl:58-160) for K knots of the
+ * 43-state spin12/spin18 layout (11 base states + 8 sample states of 4):
+ *   J[k]       = 0.5 x'Qx + q'x + c + sum_{i<8} q_ss[i%4] gate_error_iso2(x[11+4i..], target[i%4])  (+ 0.5 u'Ru if U)
+ *   gx[k*43..] = Qx + q + [0 (11); q_ss[i%4] jacobian_gate_error_iso2(x[11+4i..], target[i%4])]
+ *   gu[k]      = R u                                   (NULL when U is NULL: the terminal cost)
+ * with q = -Q xf and c = 0.5 xf'Q xf as the constructor at spin12.jl:77-79 sets them.  The Hessian of this cost is constant
+ * (hess_astate, spin12.jl:80-100) and stays with the caller.  targets[16] = 4 iso targets, q_ss[4] their weights. */
+int rbq_sampling_cost_expansion(rbq_handle* h, int64_t K, const double* X, const double* U, const double* Qdiag,
+                                const double* Rdiag, const double* xf, const double* targets, const double* q_ss,
+                                double* J, double* gx, double* gu);
+
 /* ---- Monte-Carlo robustness evaluation: run_sim_prop(...; dynamics_type=schroed)
  *      (spin.jl:1553-1608 -> integrate_prop_schroed! spin.jl:438-452 -> compute_fidelities
  *      spin.jl:1198-1240), batched over S samples instead of one call per (parameter, seed).

@@ -98,6 +98,7 @@ SIGNATURES = {
     "rbq_jacobians_dev": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P]),
     "rbq_gate_error_expansion": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
     "rbq_gate_error_expansion_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _P]),
+    "rbq_sampling_cost_expansion": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rbq_mc_static": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _P, _P, _P, C.c_int, _P, _SP]),
     "rbq_mc_static_dev": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _P, _P, _P, C.c_int, _P, _P]),
     "rbq_mc_static_philox_dev": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _I64, C.c_uint64, _D, _D, _D, _D,

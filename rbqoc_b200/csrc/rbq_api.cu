@@ -324,6 +324,32 @@ int rbq_gate_error_expansion(rbq_handle* h, int64_t K, const double* s1, int64_t
     return RBQ_OK;
 }
 
+int rbq_sampling_cost_expansion(rbq_handle* h, int64_t K, const double* X, const double* U, const double* Qdiag,
+                                const double* Rdiag, const double* xf, const double* targets, const double* q_ss, double* J,
+                                double* gx, double* gu) {
+    ENTER(h);
+    if (K < 0) return fail(h, RBQ_E_SIZE, "rbq_sampling_cost_expansion: K=%lld", (long long)K);
+    if (K == 0) return RBQ_OK;
+    if (!X || !Qdiag || !xf || !targets || !q_ss || (U && !Rdiag)) return fail(h, RBQ_E_NULL, "rbq_sampling_cost_expansion: null pointer");
+    void *dX, *dU = nullptr, *dJ = nullptr, *dgx = nullptr, *dgu = nullptr;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * 43 * K, &dX));
+    CK(cudaMemcpyAsync(dX, X, sizeof(double) * 43 * K, cudaMemcpyHostToDevice, h->stream));
+    if (U) {
+        CKL(dev_buf(h, B_IN1, sizeof(double) * K, &dU));
+        CK(cudaMemcpyAsync(dU, U, sizeof(double) * K, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (J) CKL(dev_buf(h, B_OUT0, sizeof(double) * K, &dJ));
+    if (gx) CKL(dev_buf(h, B_OUT1, sizeof(double) * 43 * K, &dgx));
+    if (gu && U) CKL(dev_buf(h, B_IN4, sizeof(double) * K, &dgu));
+    CKL(launch_sampling_cost(h, K, (double*)dX, (double*)dU, Qdiag, U ? Rdiag[0] : 0.0, xf, targets, q_ss, (double*)dJ, (double*)dgx,
+                             (double*)dgu));
+    if (J) CK(cudaMemcpyAsync(J, dJ, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+    if (gx) CK(cudaMemcpyAsync(gx, dgx, sizeof(double) * 43 * K, cudaMemcpyDeviceToHost, h->stream));
+    if (gu && U) CK(cudaMemcpyAsync(gu, dgu, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
 // ---- Monte-Carlo sweeps ----------------------------------------------------------------------------------------
 static int check_mc(rbq_handle* h, const char* who, const void* controls, int64_t nk, double dt, int64_t gate_count, int64_t S,
                     int algo) {

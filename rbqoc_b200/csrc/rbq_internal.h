@@ -90,6 +90,8 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
                       double* d_X, double* d_Uout);
 int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1, const double* d_s2, int64_t st2, double* d_err,
                       double* d_grad, double* d_hess);
+int launch_sampling_cost(rbq_handle* h, int64_t K, const double* d_X, const double* d_U, const double* Qdiag, double R,
+                         const double* xf, const double* targets, const double* q_ss, double* d_J, double* d_gx, double* d_gu);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_t, const double* d_dt, double* d_AB);
 

@@ -143,6 +143,58 @@ int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1,
     return (int)cudaGetLastError();
 }
 
+// stage cost + gradient of the sampling objective (spin12.jl:102-140), one thread per knot
+struct SamplingCostArgs { double Q[43], xf[43], R, tg[16], qss[4]; };
+__global__ void __launch_bounds__(128) sampling_cost_kernel(int64_t K, const double* __restrict__ X, const double* __restrict__ U,
+                                                            SamplingCostArgs a, double* __restrict__ J, double* __restrict__ gx,
+                                                            double* __restrict__ gu) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double* x = X + k * 43;
+    double cost = 0.0;
+    // 0.5 x'Qx + q'x + c with q = -Q xf, c = 0.5 xf'Q xf  ==  evaluated term by term exactly as the reference sums them
+    double quad = 0.0, lin = 0.0, c0 = 0.0;
+    for (int i = 0; i < 43; ++i) {
+        quad = fma(x[i] * a.Q[i], x[i], quad);
+        lin = fma(-a.Q[i] * a.xf[i], x[i], lin);
+        c0 = fma(a.xf[i] * a.Q[i], a.xf[i], c0);
+        if (gx) gx[k * 43 + i] = a.Q[i] * x[i] - a.Q[i] * a.xf[i];
+    }
+    cost = 0.5 * quad + lin + 0.5 * c0;
+    for (int s = 0; s < 8; ++s) {
+        const double* y = a.tg + 4 * (s & 3);
+        const double* z = x + 11 + 4 * s;
+        const double w = a.qss[s & 3];
+        const double aa = fma(z[3], y[3], fma(z[2], y[2], fma(z[1], y[1], z[0] * y[0])));
+        const double bb = fma(z[1], y[3], fma(z[0], y[2], fma(-z[3], y[1], -z[2] * y[0])));
+        cost = fma(w, 1.0 - aa * aa - bb * bb, cost);
+        if (gx) {
+            const double a2 = 2.0 * aa, b2 = 2.0 * bb;
+            double* g = gx + k * 43 + 11 + 4 * s;
+            g[0] += w * (-a2 * y[0] - b2 * y[2]);
+            g[1] += w * (-a2 * y[1] - b2 * y[3]);
+            g[2] += w * (-a2 * y[2] + b2 * y[0]);
+            g[3] += w * (-a2 * y[3] + b2 * y[1]);
+        }
+    }
+    if (U) {
+        cost = fma(0.5 * U[k] * a.R, U[k], cost);
+        if (gu) gu[k] = a.R * U[k];
+    }
+    if (J) J[k] = cost;
+}
+int launch_sampling_cost(rbq_handle* h, int64_t K, const double* d_X, const double* d_U, const double* Qdiag, double R,
+                         const double* xf, const double* targets, const double* q_ss, double* d_J, double* d_gx, double* d_gu) {
+    SamplingCostArgs a;
+    for (int i = 0; i < 43; ++i) { a.Q[i] = Qdiag[i]; a.xf[i] = xf[i]; }
+    for (int i = 0; i < 16; ++i) a.tg[i] = targets[i];
+    for (int i = 0; i < 4; ++i) a.qss[i] = q_ss[i];
+    a.R = R;
+    sampling_cost_kernel<<<(unsigned)((K + 127) / 128), 128, 0, h->stream>>>(K, d_X, d_U, a, d_J, d_gx, d_gu);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
 static inline int family(int model_id) {
     switch (model_id) {

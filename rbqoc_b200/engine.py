@@ -200,6 +200,20 @@ class Engine:
                  "rbq_gate_error_expansion")
         return err, grad, hess
 
+    def sampling_cost_expansion(self, X, U, Qdiag, Rdiag, xf, targets, q_ss):
+        """spin12/spin18 `Cost` (spin12.jl:59-161): X (K,43), U (K,1) or None -> J (K,), gx (K,43), gu (K,1) or None."""
+        X = _f64(X).reshape(-1, 43)
+        K = X.shape[0]
+        U = None if U is None else _f64(U).reshape(K, 1)
+        Qdiag, xf, targets, q_ss = _f64(Qdiag), _f64(xf), _f64(targets).reshape(4, 4), _f64(q_ss)
+        Rdiag = None if Rdiag is None else _f64(Rdiag)
+        J, gx = np.empty(K), np.empty((K, 43))
+        gu = None if U is None else np.empty((K, 1))
+        self._ck(self._lib.rbq_sampling_cost_expansion(self._h, K, _ptr(X), _ptr(U), _ptr(Qdiag), _ptr(Rdiag), _ptr(xf),
+                                                       _ptr(targets), _ptr(q_ss), _ptr(J), _ptr(gx), _ptr(gu)),
+                 "rbq_sampling_cost_expansion")
+        return J, gx, gu
+
     # ---- Monte-Carlo sweeps ------------------------------------------------------------------------------
     def mc_static(self, controls, dt, gate, gate_count, fq, da, psi0, algo=_lib.ALGO_SU2, want_fid=True, want_stats=True,
                   fid_out=None):

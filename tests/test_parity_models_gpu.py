@@ -291,6 +291,39 @@ def test_gate_error_expansion_matches_oracle(engine, oracle):
     assert abs(e0[0]) < 1e-15
 
 
+def test_sampling_cost_expansion_matches_reference_formulas(engine, oracle):
+    """TO.stage_cost / TO.gradient! of the spin12 `Cost` (spin12.jl:102-140), restated here term by term with the oracle's
+    gate-error primitives."""
+    rng = np.random.default_rng(8)
+    K, n = 257, 43
+    X = rng.standard_normal((K, n)) * 0.5
+    U = rng.standard_normal((K, 1)) * 0.1
+    Q = rng.uniform(0.1, 2.0, n)
+    R = np.array([0.37])
+    xf = rng.standard_normal(n)
+    targets = rng.standard_normal((4, 4))
+    targets /= np.linalg.norm(targets, axis=1, keepdims=True)
+    q_ss = np.array([1.0, 2.0, 0.5, 3.0])
+    J, gx, gu = engine.sampling_cost_expansion(X, U, Q, R, xf, targets, q_ss)
+    q = -Q * xf                                             # spin12.jl:77
+    c = 0.5 * xf @ (Q * xf)                                 # spin12.jl:78
+    for k in range(0, K, 16):
+        x = X[k]
+        cost = 0.5 * x @ (Q * x) + q @ x + c
+        grad = Q * x + q
+        for s in range(8):
+            e, g, _ = oracle.gate_error_expansion(x[11 + 4 * s: 15 + 4 * s], targets[s % 4])
+            cost += q_ss[s % 4] * e
+            grad[11 + 4 * s: 15 + 4 * s] += q_ss[s % 4] * g
+        cost += 0.5 * U[k, 0] * R[0] * U[k, 0]             # spin12.jl:116-119
+        assert abs(J[k] - cost) < 1e-12 * max(1.0, abs(cost))
+        assert np.max(np.abs(gx[k] - grad)) < 1e-12 * max(1.0, np.max(np.abs(grad)))
+        assert abs(gu[k, 0] - R[0] * U[k, 0]) < 1e-15
+    # terminal cost: no control term
+    Jt, gxt, gut = engine.sampling_cost_expansion(X[:3], None, Q, None, xf, targets, q_ss)
+    assert gut is None and np.allclose(Jt, J[:3] - 0.5 * R[0] * U[:3, 0] ** 2, rtol=1e-13) and np.array_equal(gxt, gx[:3])
+
+
 def test_jacobian_structure_spin13(engine):
     """A = blkdiag(E, E, chain) + the d/da column; B = dt e_11."""
     model = spin.Spin13Model()
