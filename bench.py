@@ -160,8 +160,10 @@ def other_configs(eng, rbq, spin, torch, dev):
             "knots": N, "n": n,
             "rollout_ms": timed_host(lambda: eng.rollout(model.params, x0, U, dtv)),
             "jacobians_ms": timed_host(lambda: eng.jacobians(model.params, X[:-1], U, dtv)),
+            "jacobians_pinned_out_ms": (lambda buf: timed_host(lambda: eng.jacobians(model.params, X[:-1], U, dtv, out=buf)))(
+                eng.pinned_empty((N - 1, n + m, n))),
             "closedloop_8_candidates_ms": timed_host(lambda: eng.rollout_closedloop(model.params, X, U, K, d, dtv, alphas)),
-            "api": "rbq_rollout / rbq_jacobians / rbq_rollout_closedloop, pageable host buffers, copies included",
+            "api": "rbq_rollout / rbq_jacobians / rbq_rollout_closedloop, pageable host buffers (pinned where named), copies included",
         }
     S = 100_000
     rng = np.random.default_rng(0)

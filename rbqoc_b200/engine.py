@@ -163,8 +163,9 @@ class Engine:
                                                   na, _ptr(alphas), _ptr(X), _ptr(Uo)), "rbq_rollout_closedloop")
         return X, Uo
 
-    def jacobians(self, p, X, U, dt, t=None):
-        """X (K,n), U (K,m), dt (K,), t (K,) knot times or None -> (K, n, n+m).  Only spin25 reads t."""
+    def jacobians(self, p, X, U, dt, t=None, out=None):
+        """X (K,n), U (K,m), dt (K,), t (K,) knot times or None -> (K, n, n+m).  Only spin25 reads t.
+        out: optional (K, n+m, n) float64 buffer (e.g. from pinned_empty) that receives the column-major blocks."""
         n, m = self._dims(p)
         X, U, dt = _f64(X).reshape(-1, n), _f64(U).reshape(-1, m), _f64(dt)
         K = X.shape[0]
@@ -174,7 +175,12 @@ class Engine:
             t = _f64(t)
             if t.shape != (K,):
                 raise ValueError("t must have one entry per knot")
-        ab = np.empty((K, n + m, n))
+        if out is not None:
+            if out.shape != (K, n + m, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape (K, n+m, n)")
+            ab = out
+        else:
+            ab = np.empty((K, n + m, n))
         self._ck(self._lib.rbq_jacobians(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(t), _ptr(dt), _ptr(ab)), "rbq_jacobians")
         return ab.transpose(0, 2, 1)
 

@@ -101,6 +101,38 @@ def test_mc_static_many_gates_and_empty(engine, oracle):
         engine.mc_static(controls, dt, gate, 1, fq, da, psi0, algo=7)
 
 
+def test_long_pulse_many_tiles(engine, oracle):
+    """20 001 knots = 10 shared-memory tiles of the static pipeline, 20 of the noise pipeline (odd length, ragged last tile)."""
+    nk = 20001
+    controls = 0.3 * np.sin(np.arange(nk) * 1e-3) + 0.05 * np.cos(np.arange(nk) * 7e-3)
+    S = 48
+    fq, da, psi0 = _samples(S, seed=21)
+    fid, _ = engine.mc_static(controls, 0.01, rbq.GATE_XPI, 2, fq, da, psi0)
+    ref = oracle.mc_static(controls, 0.01, rbq.GATE_XPI, 2, fq, da, psi0)
+    assert np.max(np.abs(fid - ref)) < max(5e-12, 2.5e-15 * nk)
+    ndi = 10.0
+    nlen = int(np.ceil(nk * 0.01 * 2 * ndi)) + 1
+    noise = oracle.pink_noise(0, S, 3, spin.NAMP_PREFACTOR * 1e3, ndi, nlen)
+    fidn, _ = engine.mc_noise(controls, 0.01, rbq.GATE_XPI, 2, spin.FQ, noise, ndi, psi0)
+    refn = oracle.mc_noise(controls, 0.01, rbq.GATE_XPI, 2, spin.FQ, noise, ndi, psi0)
+    assert np.max(np.abs(fidn - refn)) < max(5e-12, 2.5e-15 * nk * 2)
+
+
+def test_zero_gates(engine):
+    """gate_count = 0: only the initial fidelity F(psi0, psi0) = 1 is reported; the statistics are those of 1 - 1."""
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    fq, da, psi0 = _samples(100, seed=2)
+    fid, st = engine.mc_static(controls, dt, gate, 0, fq, da, psi0)
+    assert fid.shape == (100, 1) and np.max(np.abs(fid - 1)) < 1e-15 and st.count == 100 and st.max < 1e-15
+    noise = np.zeros((100, 1))
+    fidn, stn = engine.mc_noise(controls, dt, gate, 0, spin.FQ, noise, 10.0, psi0)
+    assert fidn.shape == (100, 1) and np.max(np.abs(fidn - 1)) < 1e-15 and stn.count == 100
+    rho0 = _rand_rho(100, 1, mixed=True)
+    fidl, rho, stl = engine.lindblad(controls, dt, gate, 0, spin.FQ, None, rho0)
+    assert fidl.shape == (100, 1) and np.max(np.abs(rho - rho0)) < 1e-15
+    assert np.max(np.abs(fidl[:, 0] - 1.0)) < 1e-12            # sqrt-fidelity of a state with itself
+
+
 def test_mc_static_nonfinite_samples_are_counted(engine):
     controls, dt, gate = PULSES["sin301_dt0.1"]
     fq, da, psi0 = _samples(300, seed=5)
