@@ -248,7 +248,16 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     // one step-size candidate per warp, one warp per block so that candidates spread over SMs
     WarpRolloutArgs a{p, n, m, N, nalpha, 0.0, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
-#define CALL(M) warp_rollout_kernel<M, true><<<(unsigned)nalpha, 32, 0, h->stream>>>(a)
+    const size_t smem = closedloop_smem_bytes(n, m);
+#define CALL(M)                                                                                                               \
+    {                                                                                                                         \
+        if (smem > 48 * 1024) {                                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(warp_rollout_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                 (int)smem);                                                                  \
+            if (e != cudaSuccess) return (int)e;                                                                              \
+        }                                                                                                                     \
+        warp_rollout_kernel<M, true><<<(unsigned)nalpha, 32, smem, h->stream>>>(a);                                           \
+    }
     RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     h->launches++;

@@ -40,8 +40,16 @@ struct WarpRolloutArgs {
     double* Uout;                // closed loop: [count][N-1][m]
 };
 
+constexpr int CL_TILE = 32;   // knots of (K, Xref, Uref, d) staged per shared-memory tile in the closed-loop kernel
+__host__ __device__ inline size_t closedloop_smem_bytes(int n, int m) { return sizeof(double) * CL_TILE * (size_t)(n * m + n + 2 * m); }
+
 template <int MODEL, bool CLOSED>
 __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs a) {
+    extern __shared__ __align__(16) double cl_smem[];
+    double* sK = cl_smem;                                    // [CL_TILE][n][m] (column-major m x n per knot)
+    double* sX = sK + CL_TILE * a.n * a.m;                   // [CL_TILE][n]
+    double* sU = sX + CL_TILE * a.n;                         // [CL_TILE][m]
+    double* sD = sU + CL_TILE * a.m;                         // [CL_TILE][m]
     const rbq_model_params& p = a.p;
     const int lane = threadIdx.x;
     const int64_t tr = blockIdx.x;
@@ -127,8 +135,22 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
         // ---- control ---------------------------------------------------------------------------------
         double u0, u1 = 0.0;
         if (CLOSED) {
-            const double* __restrict__ Kk = a.K + k * m * n;
-            const double* __restrict__ xr = a.x0 + k * n;
+            // Gains, reference states and feed-forward terms do not depend on the state: the warp stages CL_TILE knots of
+            // them in shared memory with coalesced loads, so the L2 round trip is paid once per tile instead of once per
+            // knot on the critical path of the feedback law.
+            const int kt = (int)(k % CL_TILE);
+            if (kt == 0) {
+                __syncwarp();
+                const int64_t len = (N - 1 - k) < CL_TILE ? (N - 1 - k) : CL_TILE;
+                const double* gK = a.K + k * m * n;
+                const double* gX = a.x0 + k * n;
+                for (int64_t i = lane; i < len * m * n; i += 32) sK[i] = gK[i];
+                for (int64_t i = lane; i < len * n; i += 32) sX[i] = gX[i];
+                for (int64_t i = lane; i < len * m; i += 32) { sU[i] = a.U[k * m + i]; sD[i] = a.d[k * m + i]; }
+                __syncwarp();
+            }
+            const double* __restrict__ Kk = sK + kt * m * n;
+            const double* __restrict__ xr = sX + kt * n;
             double s0 = 0.0, s1 = 0.0;
             if (has_block) {
 #pragma unroll
@@ -159,8 +181,8 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                 }
             }
             s0 = warp_sum(s0);
-            u0 = a.U[k * m] + fma(alpha, a.d[k * m], s0);
-            if (m > 1) { s1 = warp_sum(s1); u1 = a.U[k * m + 1] + fma(alpha, a.d[k * m + 1], s1); }
+            u0 = sU[kt * m] + fma(alpha, sD[kt * m], s0);
+            if (m > 1) { s1 = warp_sum(s1); u1 = sU[kt * m + 1] + fma(alpha, sD[kt * m + 1], s1); }
             if (lane == 0) { Uo[k * m] = u0; if (m > 1) Uo[k * m + 1] = u1; }
         } else {
             u0 = u0_n; u1 = u1_n;
