@@ -424,6 +424,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        clk = clocks_summary(rows)
         line = {
             "metric": "fp64_trajectory_steps_per_sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -441,6 +442,12 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_ncu_mc_static_full.csv)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
+                         # register-operand model of the FP64 pipe (profiles/r1_fp64_microbench.txt): 2 issue cycles per warp-DFMA
+                         # with <= 2 fresh 64-bit register operands, ~3 with 3 (the register file feeds two per slot); of the
+                         # 18 instructions of a step 10 are two-operand forms and 8 are the three-operand state updates
+                         "issue_model": {"cycles_per_warp_step_floor": 10 * 2 + 8 * 3,
+                                         "cycles_per_warp_step_measured": (clk["sm_mhz"] or 1965.0) * 1e6 * 4 * 148 * (kern_ms * 1e-3) / (S * NK / 32.0),
+                                         "note": "floor / measured = fraction of the operand-bandwidth-limited issue rate"},
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,
                          "kernel_ms": kern_ms,
                          "hbm": {"achieved_gbs": S * BYTES_PER_SAMPLE / (kern_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
@@ -451,7 +458,7 @@ def main():
                     "pcie_measured": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
                                       "h2d_floor_ms": (S * 48 + NK * 8) / (h2d_gbs * 1e6) if h2d_gbs else None}},
             "gpu_launches": launches,
-            "clocks": clocks_summary(rows),
+            "clocks": clk,
             "result": {"mean_infidelity": st.mean, "count": st.count,
                        "merged_count_all_ranks": merged["last"].count if merged["last"] is not None else None},
         }
