@@ -63,6 +63,51 @@ def test_mc_static_matches_oracle(engine, oracle, name, algo):
     assert sum(st.hist[:]) == S
 
 
+@pytest.mark.parametrize("dt,amp", [(0.5, 0.3), (1.0, 0.4), (2.5, 0.5), (0.2, 0.5)], ids=["class2", "class3", "class3_big", "class2_edge"])
+@pytest.mark.parametrize("algo", [rbq.ALGO_SU2, rbq.ALGO_PADE], ids=["su2", "pade"])
+def test_mc_sweeps_with_large_rotation_angles(engine, oracle, dt, amp, algo):
+    """Coarse grids push x = theta^2 past the tan-form polynomials: the normalised K = 8 series and the sincos class of the
+    sweep kernels, and Pade-7/9/13 (+ squaring) of the reference-algorithm kernels, for the static, noisy and Lindblad sweeps."""
+    nk = 120
+    controls = amp * np.sin(np.arange(nk) * 0.37)
+    S = 300
+    fq, da, psi0 = _samples(S, seed=int(dt * 10))
+    fid, st = engine.mc_static(controls, dt, rbq.GATE_YPIBY2, 3, fq, da, psi0, algo=algo)
+    ref = oracle.mc_static(controls, dt, rbq.GATE_YPIBY2, 3, fq, da, psi0)
+    assert np.max(np.abs(fid - ref)) < FID_RTOL
+    ndi = 1.0 / dt
+    nlen = int(np.ceil(nk * dt * 3 * ndi)) + 1
+    noise = 0.02 * np.random.default_rng(1).standard_normal((S, nlen))
+    fidn, _ = engine.mc_noise(controls, dt, rbq.GATE_YPIBY2, 3, spin.FQ, noise, ndi, psi0, algo=algo)
+    refn = oracle.mc_noise(controls, dt, rbq.GATE_YPIBY2, 3, spin.FQ, noise, ndi, psi0)
+    assert np.max(np.abs(fidn - refn)) < FID_RTOL
+    if algo == rbq.ALGO_SU2:
+        rho0 = _rand_rho(64, 3, mixed=True)
+        fl, rho, _ = engine.lindblad(controls, dt, rbq.GATE_YPIBY2, 5, spin.FQ, da[:64], rho0)
+        rfid, rfc, rrho = oracle.lindblad_t1(controls, dt, rbq.GATE_YPIBY2, 5, spin.FQ, da[:64], rho0)
+        assert np.max(np.abs(rho - rrho)) < 1e-12 and np.max(np.abs(fl - rfc)) < 1e-12
+
+
+def test_mc_noise_sample_leaving_the_polynomial_range(engine, oracle):
+    """A noise burst pushes single knots outside the tan-form polynomial's x range: the per-knot guard must take the
+    general step for them (and only them)."""
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    S, gc, ndi = 96, 2, 10.0
+    _, _, psi0 = _samples(S, seed=13)
+    nlen = int(np.ceil(controls.shape[0] * dt * gc * ndi)) + 1
+    noise = np.zeros((S, nlen))
+    noise[::3, 40:55] = 3.0            # |a + delta a| ~ 3 GHz for a few knots of every third sample
+    for mode in ("0", "1"):
+        import os
+        os.environ["RBQ_NOISE_GATE_PARALLEL"] = mode
+        try:
+            fid, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
+        finally:
+            os.environ.pop("RBQ_NOISE_GATE_PARALLEL", None)
+        ref = oracle.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
+        assert np.max(np.abs(fid - ref)) < FID_RTOL, mode
+
+
 def test_mc_static_analytic_gates_are_exact(engine):
     """Known answers embedded in the reference (spin.jl:557, 608-612): the idle Z/2 and the
     three-segment Y/2 reproduce their gates for every initial state at zero detuning."""

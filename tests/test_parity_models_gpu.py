@@ -114,6 +114,39 @@ def test_discrete_jacobian_matches_oracle_forward_mode(engine, oracle, name, mod
 
 
 @pytest.mark.parametrize("name,model", MODELS, ids=IDS)
+@pytest.mark.parametrize("dt,a", [(0.5, 0.3), (1.0, 0.3), (2.0, 0.5), (5.0, -0.45), (0.3, 0.49)],
+                         ids=["x0.22_series8", "x0.89_sincos", "x9.9_sincos", "x50_sincos", "x0.21_series8"])
+def test_large_rotation_angles(engine, oracle, name, model, dt, a):
+    """x = (pi dt)^2 (fq^2 + a^2) far outside the optimisation grids: the long series and the sincos branch of the closed
+    form (value and tangents) against the oracle's Pade-7/9/13 + scaling-and-squaring."""
+    if model.params.model_id == 15 and model.params.time_optimal:
+        pytest.skip("dt is a control for the time-optimal model (covered below)")
+    rng = np.random.default_rng(_seed(name, 31))
+    x, u = _random_point(model, rng, a)
+    got = engine.discrete_dynamics(model.params, x, u, 0.0, dt)
+    ref = oracle.step(model.params, x, u, dt)
+    assert _relerr(got, ref) < STATE_RTOL, name
+    J = engine.discrete_jacobian(model.params, x, u, 0.0, dt)
+    Jr = oracle.jacobian(model.params, x, u, dt)
+    assert _relerr(J, Jr) < JAC_RTOL, name
+
+
+def test_time_optimal_large_dt_control(engine, oracle):
+    """spin15 TO: dt = u2^2 up to 4 ns, so the tangent of the sincos branch w.r.t. dt is exercised too."""
+    model = spin.Spin15Model(True, True)
+    rng = np.random.default_rng(17)
+    for u2 in (0.7, 1.0, 1.5, 2.0):
+        x, u = _random_point(model, rng, 0.4)
+        u[1] = u2
+        got = engine.discrete_dynamics(model.params, x, u, 0.0, 0.1)
+        ref = oracle.step(model.params, x, u, 0.1)
+        assert _relerr(got, ref) < STATE_RTOL
+        J = engine.discrete_jacobian(model.params, x, u, 0.0, 0.1)
+        Jr = oracle.jacobian(model.params, x, u, 0.1)
+        assert _relerr(J, Jr) < JAC_RTOL
+
+
+@pytest.mark.parametrize("name,model", MODELS, ids=IDS)
 def test_rollout_and_batched_jacobians(engine, oracle, name, model):
     rng = np.random.default_rng(_seed(name, 11))
     N = 301
