@@ -155,6 +155,38 @@ function mc_static(controls::Vector{Float64}, dt::Real, gate::Integer, gate_coun
     return fid, st[]
 end
 
+"Batched run_sim_prop(…; dynamics_type=schroedda): noise is noise_len × S (one column per sample, already scaled by namp)."
+function mc_noise(controls::Vector{Float64}, dt::Real, gate::Integer, gate_count::Integer, fq::Real,
+                  noise::Matrix{Float64}, noise_dt_inv::Real, psi0::Matrix{Float64}; algo::Integer=0)
+    noise_len, S = size(noise)
+    size(psi0) == (4, S) || error("psi0 must be 4×S")
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    st = Ref{Stats}()
+    GC.@preserve controls noise psi0 fid check(ccall((:rbq_mc_noise, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Cint, Int64, Int64, Float64, Ptr{Float64}, Int64, Float64, Ptr{Float64},
+         Cint, Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, controls, length(controls), dt, gate, gate_count, S, fq, noise, noise_len, noise_dt_inv, psi0, algo,
+        fid, st), "rbq_mc_noise")
+    return fid, st[]
+end
+
+"Batched run_sim_prop(…; dynamics_type=lindbladt1): rho0 is 2×2×S ComplexF64 (column-major vec per sample, as get_vec_viso)."
+function lindblad(controls::Vector{Float64}, dt::Real, gate::Integer, gate_count::Integer, fq::Real,
+                  da::Union{Nothing,Vector{Float64}}, rho0::Array{ComplexF64,3}; channels::Integer=1,
+                  t2_gamma_c::Real=0.0, t2_gamma_f::Real=0.0)
+    S = size(rho0, 3)
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    rho = similar(rho0)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    GC.@preserve controls da rho0 fid rho check(ccall((:rbq_lindblad, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Cint, Int64, Int64, Float64, Ptr{Float64}, Ptr{ComplexF64}, Cint,
+         Float64, Float64, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Stats}),
+        handle().ptr, controls, length(controls), dt, gate, gate_count, S, fq, dap, rho0, channels, t2_gamma_c, t2_gamma_f,
+        fid, rho, st), "rbq_lindblad")
+    return fid, rho, st[]
+end
+
 # ---- the macro a reference script uses ---------------------------------------------------------------------
 """
     RbqEngine.@accelerate Model params_expr

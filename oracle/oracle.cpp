@@ -162,6 +162,12 @@ template <class T> Mat4<T> solve(Mat4<T> A, Mat4<T> B) {
 // reference's in-tree copy at spin26.jl:25-40.  Reference call sites: spin13.jl:46,
 // spin12.jl:168,175-176, spin30.jl:108,113,181, spin15.jl:56, spin.jl:445,478,532.
 // ------------------------------------------------------------------------------------------
+// degree-13 Pade numerator coefficients (Higham 2005, table 2.3); the reference carries the same table in-tree at
+// spin26.jl:25-40, which tests/test_oracle_cpu.py compares against
+static const double PADE13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                                  129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
+                                  1323241920.,        40840800.,          960960.,           16380.,
+                                  182.,               1.};
 template <class T> Mat4<T> expm_ref(const Mat4<T>& A_in, int* degree_out = nullptr) {
     Mat4<T> A = A_in;
     double nA = 0.0;
@@ -199,11 +205,7 @@ template <class T> Mat4<T> expm_ref(const Mat4<T>& A_in, int* degree_out = nullp
             double sc = std::ldexp(1.0, -si);
             for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) A.a[i][j] = A.a[i][j] * sc;
         }
-        static const double C[14] = {64764752532480000., 32382376266240000., 7771770303897600.,
-                                     1187353796428800.,  129060195264000.,   10559470521600.,
-                                     670442572800.,      33522128640.,       1323241920.,
-                                     40840800.,          960960.,            16380.,
-                                     182.,               1.};
+        const double* C = PADE13;
         Mat4<T> A2 = matmul(A, A), A4 = matmul(A2, A2), A6 = matmul(A2, A4);
         Mat4<T> t1, t2, u, v;
         for (int i = 0; i < 4; ++i)
@@ -791,6 +793,7 @@ int orc_expm4c(const double* A, double* E) {
     for (int i = 0; i < 16; ++i) { E[2 * i] = R.a[i / 4][i % 4].real(); E[2 * i + 1] = R.a[i / 4][i % 4].imag(); }
     return deg;
 }
+void orc_pade13_coeffs(double* out) { for (int i = 0; i < 14; ++i) out[i] = PADE13[i]; }
 void orc_propagator(double fq, double a, double dt, double* E) {
     Mat4<double> R = propagator<double>(fq, a, dt);
     for (int i = 0; i < 16; ++i) E[i] = R.a[i / 4][i % 4];

@@ -82,7 +82,7 @@ def lib():
         _lib.orc_t1_reduced_us.restype = C.c_double
         _lib.orc_t1_ns.argtypes = [C.c_double]
         _lib.orc_t1_reduced_us.argtypes = [C.c_double]
-        for name in ("orc_gate_error_expansion", "orc_propagator", "orc_lindblad_generator", "orc_philox4x32_10", "orc_philox_samples",
+        for name in ("orc_pade13_coeffs", "orc_gate_error_expansion", "orc_propagator", "orc_lindblad_generator", "orc_philox4x32_10", "orc_philox_samples",
                      "orc_pink_filter", "orc_pink_noise", "orc_stats"):
             getattr(_lib, name).restype = None
     return _lib
@@ -134,6 +134,12 @@ def expm4c(A):
     E = np.empty((4, 4), dtype=np.complex128)
     deg = lib().orc_expm4c(_p(A), _p(E))
     return E, deg
+
+
+def pade13_coeffs():
+    out = np.empty(14)
+    lib().orc_pade13_coeffs(_p(out))
+    return out
 
 
 def propagator(fq, a, dt):

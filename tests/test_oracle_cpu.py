@@ -39,6 +39,28 @@ def test_expm_matches_scipy_and_picks_reference_branches(orc):
     assert np.max(np.abs(Ec - scipy.linalg.expm(0.3 * A))) < 1e-13
 
 
+REF_SPIN26 = "/root/reference/src/spin/spin26.jl"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_SPIN26), reason="reference tree not present (GPU box)")
+def test_pade13_table_equals_the_reference_in_tree_copy(orc):
+    """The reference carries Higham's degree-13 table at spin26.jl:25-40; the oracle's expm uses the same numbers."""
+    import re
+
+    src = open(REF_SPIN26).read()
+    body = src[src.index("const B = ("):]
+    body = body[:body.index(")")]
+    ref = [float(t) for t in re.findall(r"\b\d+\b", body.split("(", 1)[1])]
+    assert len(ref) == 14
+    assert list(orc.pade13_coeffs()) == ref
+    # the lower-degree tables are the classical ones: p_m(x) = sum_j (2m-j)! m! / ((2m)! (m-j)! j!) x^j, scaled to integers
+    from math import factorial as f
+
+    for m, table in ((3, [120, 60, 12, 1]), (5, [30240, 15120, 3360, 420, 30, 1])):
+        c = [f(2 * m - j) * f(m) / (f(2 * m) * f(m - j) * f(j)) for j in range(m + 1)]
+        assert np.allclose(np.array(c) / c[-1] * table[-1], table, rtol=1e-15)
+
+
 def orc_N0():
     return [[0, 0, 1, 0], [0, 0, 0, -1], [-1, 0, 0, 0], [0, 1, 0, 0]]
 
