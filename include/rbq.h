@@ -289,6 +289,23 @@ int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, do
                      const double* d_rho0, int channels, double t2_gamma_c, double t2_gamma_f,
                      double* d_fid, double* d_rho_out, rbq_stats* d_stats);
 
+/* ---- analytic gates: piecewise-constant pulses with PER-SEGMENT durations
+ *      integrate_prop_zpiby2nodis!/zpiby2t1!, ypiby2nodis!/ypiby2t1!, xpiby2nodis!/xpiby2t1!
+ *      (spin.jl:562-594, 651-670, 721-727, 765-785): the gate propagator is the ordered product of exp(segment generator *
+ *      segment duration), applied gate_count times.  amps[nseg] (GHz), durs[nseg] (ns); everything else as in
+ *      rbq_mc_static / rbq_lindblad (da[S] or NULL shifts every segment's amplitude).  Host pointers. */
+int rbq_mc_static_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate,
+                           int64_t gate_count, int64_t S, const double* fq, const double* da, const double* psi0,
+                           double* fid, rbq_stats* stats);
+/* integrate_prop_xpiby2da! (spin.jl:819-905): segment j uses amplitude amps[j] + noise[s][noise_idx[j]]; the same
+ * indices are read in every gate, as in the reference.  noise[S*noise_len], noise_idx[nseg] (0-based, int32). */
+int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
+                          int gate, int64_t gate_count, int64_t S, double fq, const double* noise, int64_t noise_len,
+                          const double* psi0, double* fid, rbq_stats* stats);
+int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate,
+                          int64_t gate_count, int64_t S, double fq, const double* da, const double* rho0, int channels,
+                          double t2_gamma_c, double* fid, double* rho_out, rbq_stats* stats);
+
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);
 

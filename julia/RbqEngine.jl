@@ -187,6 +187,53 @@ function lindblad(controls::Vector{Float64}, dt::Real, gate::Integer, gate_count
     return fid, rho, st[]
 end
 
+"Analytic gates (integrate_prop_zpiby2nodis!/ypiby2nodis/xpiby2nodis, spin.jl:562-570): amps/durs are the pulse's segments."
+function mc_static_segments(amps::Vector{Float64}, durs::Vector{Float64}, gate::Integer, gate_count::Integer,
+                            fq::Vector{Float64}, da::Union{Nothing,Vector{Float64}}, psi0::Matrix{Float64})
+    S = length(fq)
+    size(psi0) == (4, S) || error("psi0 must be 4×S")
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    GC.@preserve amps durs fq da psi0 fid check(ccall((:rbq_mc_static_segments, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, amps, durs, length(amps), gate, gate_count, S, fq, dap, psi0, fid, st), "rbq_mc_static_segments")
+    return fid, st[]
+end
+
+"integrate_prop_xpiby2da! (spin.jl:819-905): segment j sees amps[j] + noise[noise_idx[j] + 1, s]; noise_idx is 0-based."
+function mc_noise_segments(amps::Vector{Float64}, durs::Vector{Float64}, noise_idx::Vector{Int32}, gate::Integer,
+                           gate_count::Integer, fq::Real, noise::Matrix{Float64}, psi0::Matrix{Float64})
+    noise_len, S = size(noise)
+    size(psi0) == (4, S) || error("psi0 must be 4×S")
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    st = Ref{Stats}()
+    GC.@preserve amps durs noise_idx noise psi0 fid check(ccall((:rbq_mc_noise_segments, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int64, Cint, Int64, Int64, Float64, Ptr{Float64}, Int64,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, amps, durs, noise_idx, length(amps), gate, gate_count, S, fq, noise, noise_len, psi0, fid, st),
+        "rbq_mc_noise_segments")
+    return fid, st[]
+end
+
+"integrate_prop_zpiby2t1!/ypiby2t1!/xpiby2t1! (spin.jl:582-594, 651-670, 765-785)."
+function lindblad_segments(amps::Vector{Float64}, durs::Vector{Float64}, gate::Integer, gate_count::Integer, fq::Real,
+                           da::Union{Nothing,Vector{Float64}}, rho0::Array{ComplexF64,3}; channels::Integer=1,
+                           t2_gamma_c::Real=0.0)
+    S = size(rho0, 3)
+    fid = Matrix{Float64}(undef, gate_count + 1, S)
+    rho = similar(rho0)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    GC.@preserve amps durs da rho0 fid rho check(ccall((:rbq_lindblad_segments, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Int64, Int64, Float64, Ptr{Float64}, Ptr{ComplexF64}, Cint,
+         Float64, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Stats}),
+        handle().ptr, amps, durs, length(amps), gate, gate_count, S, fq, dap, rho0, channels, t2_gamma_c, fid, rho, st),
+        "rbq_lindblad_segments")
+    return fid, rho, st[]
+end
+
 # ---- the macro a reference script uses ---------------------------------------------------------------------
 """
     RbqEngine.@accelerate Model params_expr

@@ -670,6 +670,50 @@ static void sim_schroed(const double* controls, int64_t nk, double dt, int gate,
     if (state_out) for (int i = 0; i < 4; ++i) state_out[i] = (double)st[i];
 }
 
+// analytic gates: ordered product of exp(segment generator * segment duration)  (spin.jl:562-570, 721-727)
+static void sim_schroed_segments(const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count, double fq,
+                                 double da, const double* psi0, double* fid) {
+    Mat4<double> prop = eye4<double>();
+    for (int64_t j = 0; j < nseg; ++j) {
+        Mat4<double> H;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) H.a[r][c] = (fq * (PI * N0[r][c]) + (amps[j] + da) * (PI * N1[r][c])) * durs[j];
+        prop = matmul(expm_ref(H), prop);
+    }
+    xreal s0[4], st[4], tg[4][4];
+    for (int i = 0; i < 4; ++i) { s0[i] = psi0[i]; st[i] = psi0[i]; }
+    gate_targets(gate, s0, tg);
+    fid[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+    for (int64_t g = 1; g <= gate_count; ++g) {
+        xreal nx[4];
+        for (int i = 0; i < 4; ++i) { xreal s = 0; for (int k = 0; k < 4; ++k) s += (xreal)prop.a[i][k] * st[k]; nx[i] = s; }
+        for (int i = 0; i < 4; ++i) st[i] = nx[i];
+        fid[g] = (double)fidelity_vec_iso2<xreal>(st, tg[g % 4]);
+    }
+}
+
+// integrate_prop_xpiby2da! (spin.jl:819-905) generalised to any segment list: the state is stepped through every segment of
+// every gate; segment j reads noise[nidx[j]] -- the SAME indices in every gate, as the reference does (it never advances
+// the noise index from one gate to the next)
+static void sim_schroedda_segments(const double* amps, const double* durs, const int32_t* nidx, int64_t nseg, int gate,
+                                   int64_t gate_count, double fq, const double* noise, const double* psi0, double* fid) {
+    xreal s0[4], st[4], tg[4][4];
+    for (int i = 0; i < 4; ++i) { s0[i] = psi0[i]; st[i] = psi0[i]; }
+    gate_targets(gate, s0, tg);
+    fid[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+    for (int64_t g = 1; g <= gate_count; ++g) {
+        for (int64_t j = 0; j < nseg; ++j) {
+            const double amp = amps[j] + noise[nidx[j]];
+            Mat4<double> H;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) H.a[r][c] = durs[j] * (fq * (PI * N0[r][c]) + amp * (PI * N1[r][c]));
+            Mat4<double> U = expm_ref(H);
+            xreal nx[4];
+            for (int i = 0; i < 4; ++i) { xreal s = 0; for (int k = 0; k < 4; ++k) s += (xreal)U.a[i][k] * st[k]; nx[i] = s; }
+            for (int i = 0; i < 4; ++i) st[i] = nx[i];
+        }
+        fid[g] = (double)fidelity_vec_iso2<xreal>(st, tg[g % 4]);
+    }
+}
+
 // integrate_prop_schroedda! (spin.jl:469-484) for ONE sample
 static void sim_schroedda(const double* controls, int64_t nk, double dt, int gate, int64_t gate_count, double fq,
                           const double* noise, int64_t noise_len, double noise_dt_inv, const double* psi0,
@@ -947,6 +991,59 @@ int orc_lindblad_t1(const double* controls, int64_t nk, double dt, int gate, int
         sim_lindbladt1(controls, nk, dt, gate, gate_count, fq, da ? da[s] : 0.0, r0,
                        fid ? fid + s * (gate_count + 1) : nullptr, fid_closed ? fid_closed + s * (gate_count + 1) : nullptr, ro);
         if (rho_out) for (int i = 0; i < 4; ++i) { rho_out[8 * s + 2 * i] = ro[i].real(); rho_out[8 * s + 2 * i + 1] = ro[i].imag(); }
+    }
+    return 0;
+}
+int orc_mc_static_segments(const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count, int64_t S,
+                           const double* fq, const double* da, const double* psi0, double* fid) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s)
+        sim_schroed_segments(amps, durs, nseg, gate, gate_count, fq[s], da ? da[s] : 0.0, psi0 + 4 * s, fid + s * (gate_count + 1));
+    return 0;
+}
+int orc_mc_noise_segments(const double* amps, const double* durs, const int32_t* nidx, int64_t nseg, int gate, int64_t gate_count,
+                          int64_t S, double fq, const double* noise, int64_t noise_len, const double* psi0, double* fid) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+    for (int64_t j = 0; j < nseg; ++j) if (nidx[j] < 0 || nidx[j] >= noise_len) return RBQ_E_SIZE;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s)
+        sim_schroedda_segments(amps, durs, nidx, nseg, gate, gate_count, fq, noise + s * noise_len, psi0 + 4 * s, fid + s * (gate_count + 1));
+    return 0;
+}
+// integrate_prop_ypiby2t1! / xpiby2t1! / zpiby2t1! generalised to any segment list (spin.jl:582-594, 651-670, 765-785)
+int orc_lindblad_segments(const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count, int64_t S, double fq,
+                          const double* da, const double* rho0, double* fid_closed, double* rho_out) {
+    cplx g[2][2], g2[2][2], g3[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g2[i][j] = g[i][0] * g[0][j] + g[i][1] * g[1][j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g3[i][j] = g2[i][0] * g[0][j] + g2[i][1] * g[1][j];
+    LindbladOps o = make_lindblad_ops(fq);
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) {
+        Mat4<cplx> prop = eye4<cplx>();
+        for (int64_t j = 0; j < nseg; ++j) {
+            const double c1 = amps[j] + (da ? da[s] : 0.0);
+            const double gamma1 = 1.0 / amp_t1_spline<double>(c1);
+            Mat4<cplx> L;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) L.a[r][c] = (o.H0v[r][c] + c1 * o.H1v[r][c] + gamma1 * o.LOP[r][c]) * durs[j];
+            prop = matmul(expm_ref(L), prop);
+        }
+        cplx v[4], r0[2][2], tg[4][2][2];
+        for (int i = 0; i < 4; ++i) v[i] = cplx(rho0[8 * s + 2 * i], rho0[8 * s + 2 * i + 1]);
+        r0[0][0] = v[0]; r0[1][0] = v[1]; r0[0][1] = v[2]; r0[1][1] = v[3];
+        const cplx (*gs[3])[2] = {g, g2, g3};
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[0][i][j] = r0[i][j];
+        for (int q = 0; q < 3; ++q) {
+            cplx t[2][2];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i][j] = gs[q][i][0] * r0[0][j] + gs[q][i][1] * r0[1][j];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[q + 1][i][j] = t[i][0] * std::conj(gs[q][j][0]) + t[i][1] * std::conj(gs[q][j][1]);
+        }
+        for (int64_t k = 0; k <= gate_count; ++k) {
+            if (k > 0) matvec(prop, v, v);
+            cplx m[2][2] = {{v[0], v[2]}, {v[1], v[3]}};
+            if (fid_closed) fid_closed[s * (gate_count + 1) + k] = fidelity_mat_closed(m, tg[k % 4]);
+        }
+        if (rho_out) for (int i = 0; i < 4; ++i) { rho_out[8 * s + 2 * i] = v[i].real(); rho_out[8 * s + 2 * i + 1] = v[i].imag(); }
     }
     return 0;
 }

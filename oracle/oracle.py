@@ -290,6 +290,45 @@ def lindblad_t1(controls, dt, gate, gate_count, fq, da, rho0, nthreads=0):
     return fid, fidc, out.reshape(S, 2, 2).transpose(0, 2, 1).copy()
 
 
+def mc_static_segments(amps, durs, gate, gate_count, fq, da, psi0):
+    amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
+    da = None if da is None else _f64(da)
+    S = fq.shape[0]
+    fid = np.empty((S, gate_count + 1))
+    rc = lib().orc_mc_static_segments(_p(amps), _p(durs), C.c_int64(amps.shape[0]), int(gate), C.c_int64(gate_count), C.c_int64(S),
+                                      _p(fq), _p(da), _p(psi0), _p(fid))
+    if rc:
+        raise ValueError(f"orc_mc_static_segments rc={rc}")
+    return fid
+
+
+def mc_noise_segments(amps, durs, nidx, gate, gate_count, fq, noise, psi0):
+    amps, durs, noise, psi0 = _f64(amps), _f64(durs), _f64(noise), _f64(psi0)
+    nidx = np.ascontiguousarray(nidx, dtype=np.int32)
+    S, nlen = noise.shape
+    fid = np.empty((S, gate_count + 1))
+    rc = lib().orc_mc_noise_segments(_p(amps), _p(durs), _p(nidx), C.c_int64(amps.shape[0]), int(gate), C.c_int64(gate_count),
+                                     C.c_int64(S), C.c_double(fq), _p(noise), C.c_int64(nlen), _p(psi0), _p(fid))
+    if rc:
+        raise ValueError(f"orc_mc_noise_segments rc={rc}")
+    return fid
+
+
+def lindblad_segments(amps, durs, gate, gate_count, fq, da, rho0):
+    amps, durs = _f64(amps), _f64(durs)
+    rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+    S = rho0.shape[0]
+    vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4))
+    da = None if da is None else _f64(da)
+    fidc = np.empty((S, gate_count + 1))
+    out = np.empty((S, 4), dtype=np.complex128)
+    rc = lib().orc_lindblad_segments(_p(amps), _p(durs), C.c_int64(amps.shape[0]), int(gate), C.c_int64(gate_count), C.c_int64(S),
+                                     C.c_double(fq), _p(da), _p(vec), _p(fidc), _p(out))
+    if rc:
+        raise ValueError(f"orc_lindblad_segments rc={rc}")
+    return fidc, out.reshape(S, 2, 2).transpose(0, 2, 1).copy()
+
+
 def lindblad_generator(fq, a):
     L = np.empty((4, 4), dtype=np.complex128)
     lib().orc_lindblad_generator(C.c_double(fq), C.c_double(a), _p(L))

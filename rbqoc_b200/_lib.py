@@ -117,6 +117,9 @@ SIGNATURES = {
     "rbq_pink_noise": (C.c_int, [_P, _I64, _I64, C.c_uint64, _D, _D, _I64, _P]),
     "rbq_lindblad": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _D, _P, _P, _SP]),
     "rbq_lindblad_dev": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _D, _P, _P, _P]),
+    "rbq_mc_static_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _P, _P, _P, _P, _SP]),
+    "rbq_mc_noise_segments": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _I64, _P, _P, _SP]),
+    "rbq_lindblad_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _P, _P, _SP]),
     "rbq_fp64_peak": (C.c_int, [_P, C.c_int, C.POINTER(_D)]),
 }
 

@@ -769,6 +769,115 @@ int rbq_lindblad(rbq_handle* h, const double* controls, int64_t nknots, double d
     return RBQ_OK;
 }
 
+// ---- analytic gates (per-segment durations) ----------------------------------------------------------------------------
+static int segments_common(rbq_handle* h, const char* who, const double* amps, const double* durs, int64_t nseg, int gate,
+                           int64_t gate_count, int64_t S, SegmentArgs* a, void** d_fid, void** d_st, double* fid, rbq_stats* stats,
+                           int64_t G1) {
+    if (!amps || !durs) return fail(h, RBQ_E_NULL, "%s: amps/durs is NULL", who);
+    if (nseg < 1 || nseg > (1 << 24) || gate_count < 0 || S < 0) return fail(h, RBQ_E_SIZE, "%s: nseg=%lld gate_count=%lld S=%lld", who, (long long)nseg, (long long)gate_count, (long long)S);
+    memset(a, 0, sizeof(*a));
+    if (!make_gate_tables(gate, &a->gate, &a->rot)) return fail(h, RBQ_E_GATE, "%s: unknown gate %d", who, gate);
+    void *da_, *dd_;
+    CKL(dev_buf(h, B_IN0, sizeof(double) * nseg, &da_)); CKL(dev_buf(h, B_IN5, sizeof(double) * nseg, &dd_));
+    CK(cudaMemcpyAsync(da_, amps, sizeof(double) * nseg, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dd_, durs, sizeof(double) * nseg, cudaMemcpyHostToDevice, h->stream));
+    a->amps = (double*)da_; a->durs = (double*)dd_; a->nseg = nseg; a->gate_count = gate_count; a->S = S;
+    if (fid) { CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, d_fid)); a->fid = (double*)*d_fid; }
+    if (stats) {
+        CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), d_st));
+        CKL(rbq_stats_reset_dev(h, (rbq_stats*)*d_st));
+        void* pp;
+        CKL(dev_buf(h, B_PARTIALS, sizeof(BlockPartial) * (size_t)((S + 255) / 256 + 1), &pp));
+        a->partials = (BlockPartial*)pp;
+        a->hist = (unsigned long long*)((rbq_stats*)*d_st)->hist;
+    }
+    return 0;
+}
+int rbq_mc_static_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count,
+                           int64_t S, const double* fq, const double* da, const double* psi0, double* fid, rbq_stats* stats) {
+    ENTER(h);
+    SegmentArgs a;
+    void *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(segments_common(h, "rbq_mc_static_segments", amps, durs, nseg, gate, gate_count, S, &a, &dfid, &dst, fid, stats, G1));
+    if (S > 0) {
+        if (!fq || !psi0) return fail(h, RBQ_E_NULL, "rbq_mc_static_segments: fq/psi0 is NULL");
+        void *dfq, *dda, *dpsi;
+        CKL(dev_buf(h, B_IN1, sizeof(double) * S, &dfq)); CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda));
+        CKL(dev_buf(h, B_IN3, sizeof(double) * 4 * S, &dpsi));
+        CK(cudaMemcpyAsync(dfq, fq, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        if (da) CK(cudaMemcpyAsync(dda, da, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dpsi, psi0, sizeof(double) * 4 * S, cudaMemcpyHostToDevice, h->stream));
+        a.fq = (double*)dfq; a.da = da ? (double*)dda : nullptr; a.psi0 = (double*)dpsi;
+        int nblocks = 0;
+        CKL(launch_segments(h, a, false, &nblocks));
+        if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
+        if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg, int gate,
+                          int64_t gate_count, int64_t S, double fq, const double* noise, int64_t noise_len, const double* psi0,
+                          double* fid, rbq_stats* stats) {
+    ENTER(h);
+    SegmentArgs a;
+    void *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(segments_common(h, "rbq_mc_noise_segments", amps, durs, nseg, gate, gate_count, S, &a, &dfid, &dst, fid, stats, G1));
+    if (!noise_idx) return fail(h, RBQ_E_NULL, "rbq_mc_noise_segments: noise_idx is NULL");
+    if (noise_len < 1) return fail(h, RBQ_E_SIZE, "rbq_mc_noise_segments: noise_len=%lld", (long long)noise_len);
+    for (int64_t j = 0; j < nseg; ++j)
+        if (noise_idx[j] < 0 || noise_idx[j] >= noise_len)
+            return fail(h, RBQ_E_SIZE, "rbq_mc_noise_segments: noise_idx[%lld]=%d outside [0,%lld)", (long long)j, noise_idx[j], (long long)noise_len);
+    if (S > 0) {
+        if (!noise || !psi0) return fail(h, RBQ_E_NULL, "rbq_mc_noise_segments: noise/psi0 is NULL");
+        void *didx, *dn, *dpsi;
+        CKL(dev_buf(h, B_IN1, sizeof(int32_t) * nseg, &didx)); CKL(dev_buf(h, B_IN4, sizeof(double) * S * noise_len, &dn));
+        CKL(dev_buf(h, B_IN3, sizeof(double) * 4 * S, &dpsi));
+        CK(cudaMemcpyAsync(didx, noise_idx, sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dn, noise, sizeof(double) * S * noise_len, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dpsi, psi0, sizeof(double) * 4 * S, cudaMemcpyHostToDevice, h->stream));
+        a.fq = nullptr; a.fq_scalar = fq; a.noise = (double*)dn; a.nidx = (int32_t*)didx; a.noise_len = noise_len; a.psi0 = (double*)dpsi;
+        int nblocks = 0;
+        CKL(launch_segments(h, a, false, &nblocks));
+        if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
+        if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count,
+                          int64_t S, double fq, const double* da, const double* rho0, int channels, double t2_gamma_c, double* fid,
+                          double* rho_out, rbq_stats* stats) {
+    ENTER(h);
+    if (channels & ~(RBQ_LINDBLAD_T1 | RBQ_LINDBLAD_T2)) return fail(h, RBQ_E_MODEL, "rbq_lindblad_segments: unknown channel bits %d", channels);
+    SegmentArgs a;
+    void *dfid = nullptr, *dst = nullptr;
+    const int64_t G1 = gate_count + 1;
+    CKL(segments_common(h, "rbq_lindblad_segments", amps, durs, nseg, gate, gate_count, S, &a, &dfid, &dst, fid, stats, G1));
+    if (S > 0) {
+        if (!rho0) return fail(h, RBQ_E_NULL, "rbq_lindblad_segments: rho0 is NULL");
+        void *dda, *drho, *dro = nullptr;
+        CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda)); CKL(dev_buf(h, B_IN3, sizeof(double) * 8 * S, &drho));
+        if (da) CK(cudaMemcpyAsync(dda, da, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(drho, rho0, sizeof(double) * 8 * S, cudaMemcpyHostToDevice, h->stream));
+        if (rho_out) CKL(dev_buf(h, B_OUT1, sizeof(double) * 8 * S, &dro));
+        a.fq_scalar = fq; a.da = da ? (double*)dda : nullptr; a.rho0 = (double*)drho; a.rho_out = (double*)dro;
+        a.channels = channels; a.t2_gamma_c = (channels & RBQ_LINDBLAD_T2) ? t2_gamma_c : 0.0;
+        int nblocks = 0;
+        CKL(launch_segments(h, a, true, &nblocks));
+        if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
+        if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+        if (rho_out) CK(cudaMemcpyAsync(rho_out, dro, sizeof(double) * 8 * S, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
 // ---- FP64 roofline denominator -------------------------------------------------------------------------------------------
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops) {
     ENTER(h);

@@ -64,11 +64,22 @@ struct LindbladArgs {
     GateRot gate;
 };
 
+struct SegmentArgs {
+    const double* amps; const double* durs; int64_t nseg;
+    int64_t gate_count, S;
+    const double* fq; double fq_scalar; const double* da; const double* psi0; const double* rho0;
+    const double* noise; const int32_t* nidx; int64_t noise_len;   // optional: amplitude += noise[s][nidx[j]]
+    int channels; double t2_gamma_c;
+    double* fid; double* rho_out; BlockPartial* partials; unsigned long long* hist;
+    GateIso gate; GateRot rot;
+};
+
 // every launcher enqueues on h->stream, bumps h->launches and returns a cudaError_t as int
 int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax);
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);
+int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nblocks_out);
 int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);

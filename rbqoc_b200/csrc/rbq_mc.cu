@@ -897,6 +897,101 @@ __global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const Lindblad
     if (tid < 9) map_out[tid] = run[tid];
 }
 
+// ---- analytic gates: a few segments with their own durations (spin.jl:562-594, 651-670, 765-785) -----------------------
+__global__ void __launch_bounds__(MC_THREADS) mc_static_segments_kernel(const SegmentArgs a) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double fq = a.fq ? a.fq[sc] : a.fq_scalar, da = a.da ? a.da[sc] : 0.0;
+    const double* nrow = a.noise ? a.noise + sc * a.noise_len : nullptr;
+    double v[4] = {1.0, 0.0, 0.0, 0.0};
+    for (int64_t j = 0; j < a.nseg; ++j) {
+        const double w = RBQ_PI * a.durs[j];
+        const double amp = a.amps[j] + (nrow ? nrow[a.nidx[j]] : da);
+        const double p = w * fq, q = w * amp;
+        general_step(p, q, fma(q, q, p * p), v);
+    }
+    const double inv = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] *= inv;
+    double E[16], psi0[4];
+    iso_from_column(v, E);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) psi0[c] = a.psi0[4 * sc + c];
+    ThreadStats st;
+    if (live) {
+        const double f = gate_train(E, psi0, a.gate, a.gate_count, a.fid ? a.fid + s * (a.gate_count + 1) : nullptr);
+        if (a.partials) st.add(1.0 - f, hist_s);
+    }
+    if (a.partials) {
+        __syncthreads();
+        block_stats_flush(st, hist_s, red_s, a.partials, a.hist);
+    }
+}
+__global__ void __launch_bounds__(MC_THREADS) lindblad_segments_kernel(const SegmentArgs a) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    __shared__ double invk_s[64];
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    if (threadIdx.x < 64) invk_s[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double da = a.da ? a.da[sc] : 0.0;
+    const bool t1_on = (a.channels & RBQ_LINDBLAD_T1) != 0, t2_on = (a.channels & RBQ_LINDBLAD_T2) != 0;
+    double P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int64_t j = 0; j < a.nseg; ++j) {
+        const double dt = a.durs[j], c1 = a.amps[j] + da;
+        // long segments: split into equal sub-steps so that the Taylor series stays short and well conditioned
+        const double bnd = 2.0 * RBQ_PI * dt * (fabs(a.fq_scalar) + fabs(c1)) + dt * (2.0 / 269.03e3 + a.t2_gamma_c);
+        const int sub = bnd == bnd && bnd > 1.0 ? (int)fmin(ceil(bnd), 4096.0) : 1;
+        const double h = dt / (double)sub;
+        BlochGen m;
+        m.wz = 2.0 * RBQ_PI * h * a.fq_scalar; m.wx = 2.0 * RBQ_PI * h * c1;
+        const double g1 = t1_on ? h / t1_interp<double>(c1, 1e3) : 0.0;
+        m.g2 = g1 + (t2_on ? h * a.t2_gamma_c : 0.0); m.g1 = 2.0 * g1;
+        const int kmax = taylor_terms(bnd / (double)sub);
+        for (int r = 0; r < sub; ++r) bloch_advance<3>(m, kmax, invk_s, P);
+    }
+    const double* q = a.rho0 + 8 * sc;
+    const double tr0 = q[0] + q[6];
+    double r0[3] = {q[2] + q[4], q[3] - q[5], q[0] - q[6]}, r[3], tg[4][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { tg[0][i] = r0[i]; r[i] = r0[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv3_to(a.rot.r[k], r0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (a.gate_count + 1) : nullptr;
+    double f = fidelity_bloch(tr0, r0, tr0, tg[0]);
+    if (frow) frow[0] = f;
+    for (int64_t g = 1; g <= a.gate_count; ++g) {
+        const double n0 = fma(P[2][0], r[2], fma(P[1][0], r[1], P[0][0] * r[0]));
+        const double n1 = fma(P[2][1], r[2], fma(P[1][1], r[1], P[0][1] * r[0]));
+        const double n2 = fma(P[2][2], r[2], fma(P[1][2], r[1], P[0][2] * r[0]));
+        r[0] = n0; r[1] = n1; r[2] = n2;
+        const int k = (int)(g & 3);
+        f = fidelity_bloch(tr0, r, tr0, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+        if (frow) frow[g] = f;
+    }
+    if (a.rho_out && live) {
+        double* o = a.rho_out + 8 * s;
+        o[0] = 0.5 * (tr0 + r[2]); o[1] = 0.0;
+        o[2] = 0.5 * r[0];         o[3] = 0.5 * r[1];
+        o[4] = 0.5 * r[0];         o[5] = -0.5 * r[1];
+        o[6] = 0.5 * (tr0 - r[2]); o[7] = 0.0;
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
 // ---- sample materialisation (parity aids) -------------------------------------------------------------------------
 __global__ void philox_samples_kernel(int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
                                       double fq_rel_clip, double da_sigma, double* __restrict__ fq, double* __restrict__ da,
@@ -1043,6 +1138,14 @@ int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d
     if (e != cudaSuccess) return (int)e;
     mc_noise_combine_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_quat);
     h->launches += 2;
+    return (int)cudaGetLastError();
+}
+int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nblocks_out) {
+    const int blocks = (int)((a.S + MC_THREADS - 1) / MC_THREADS);
+    if (nblocks_out) *nblocks_out = blocks;
+    if (lindblad) lindblad_segments_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    else mc_static_segments_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    h->launches++;
     return (int)cudaGetLastError();
 }
 int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map) {

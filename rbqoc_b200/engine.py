@@ -295,6 +295,49 @@ class Engine:
                                         _ptr(fid), _ptr(out), C.byref(st)), "rbq_lindblad")
         return fid, out.reshape(S, 2, 2).transpose(0, 2, 1).copy(), st
 
+    # ---- analytic gates: segments with their own durations (spin.jl:562-594, 651-670, 765-785) -------------------------
+    def mc_static_segments(self, amps, durs, gate, gate_count, fq, da, psi0):
+        amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
+        da = None if da is None else _f64(da)
+        S = fq.shape[0]
+        if amps.shape != durs.shape or psi0.shape != (S, 4):
+            raise ValueError("amps/durs must have one entry per segment, psi0 (S,4)")
+        fid = np.empty((S, gate_count + 1))
+        st = Stats()
+        self._ck(self._lib.rbq_mc_static_segments(self._h, _ptr(amps), _ptr(durs), amps.shape[0], int(gate), int(gate_count), S,
+                                                  _ptr(fq), _ptr(da), _ptr(psi0), _ptr(fid), C.byref(st)), "rbq_mc_static_segments")
+        return fid, st
+
+    def mc_noise_segments(self, amps, durs, noise_idx, gate, gate_count, fq, noise, psi0):
+        """integrate_prop_xpiby2da! (spin.jl:819-905): segment j sees amps[j] + noise[s, noise_idx[j]] in every gate."""
+        amps, durs, noise, psi0 = _f64(amps), _f64(durs), _f64(noise), _f64(psi0)
+        nidx = np.ascontiguousarray(noise_idx, dtype=np.int32)
+        if noise.ndim != 2:
+            raise ValueError("noise must be (S, noise_len)")
+        S, nlen = noise.shape
+        if amps.shape != durs.shape or nidx.shape != amps.shape or psi0.shape != (S, 4):
+            raise ValueError("amps/durs/noise_idx must have one entry per segment, psi0 (S,4)")
+        fid = np.empty((S, gate_count + 1))
+        st = Stats()
+        self._ck(self._lib.rbq_mc_noise_segments(self._h, _ptr(amps), _ptr(durs), _ptr(nidx), amps.shape[0], int(gate),
+                                                 int(gate_count), S, float(fq), _ptr(noise), nlen, _ptr(psi0), _ptr(fid),
+                                                 C.byref(st)), "rbq_mc_noise_segments")
+        return fid, st
+
+    def lindblad_segments(self, amps, durs, gate, gate_count, fq, da, rho0, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0):
+        amps, durs = _f64(amps), _f64(durs)
+        rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+        S = rho0.shape[0]
+        vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4))
+        da = None if da is None else _f64(da)
+        fid = np.empty((S, gate_count + 1))
+        out = np.empty((S, 4), dtype=np.complex128)
+        st = Stats()
+        self._ck(self._lib.rbq_lindblad_segments(self._h, _ptr(amps), _ptr(durs), amps.shape[0], int(gate), int(gate_count), S,
+                                                 float(fq), _ptr(da), _ptr(vec), int(channels), float(t2_gamma_c), _ptr(fid),
+                                                 _ptr(out), C.byref(st)), "rbq_lindblad_segments")
+        return fid, out.reshape(S, 2, 2).transpose(0, 2, 1).copy(), st
+
     # ---- device-pointer forms (torch CUDA tensors; asynchronous on the handle's stream) ------------------------
     def stats_reset_dev(self, d_stats):
         self._ck(self._lib.rbq_stats_reset_dev(self._h, _ptr(d_stats)), "rbq_stats_reset_dev")

@@ -46,11 +46,18 @@ class GateType(enum.IntEnum):     # spin.jl:29-34
     xpi = 4
 
 
-class DynamicsType(enum.IntEnum):  # spin.jl:36-51 (the propagator-based members)
+class DynamicsType(enum.IntEnum):  # spin.jl:36-58 (same integer values): the members run_sim_prop integrates (DT_INT, spin.jl:986-996)
     schroed = 1
-    schroedda = 2
     lindbladt1 = 3
-    lindbladt2 = 4
+    ypiby2nodis = 4
+    ypiby2t1 = 5
+    xpiby2nodis = 6
+    xpiby2t1 = 7
+    zpiby2nodis = 9
+    zpiby2t1 = 10
+    xpiby2da = 13
+    lindbladt2 = 15
+    schroedda = 18
 
 
 class RK3:                        # integrator tag the reference always dispatches on (rbqoc.jl:49-54)
@@ -321,6 +328,51 @@ def controls_zpiby2(dt_inv=100.0):
     return np.zeros(int(math.floor(TTOT_ZPIBY2 * dt_inv)))
 
 
+# the analytic gates as (amplitude, duration) segments with the reference's exact durations (spin.jl:557, 603-612, 691-697)
+TX_YPIBY2 = 2.1656249366575766
+TZ_YPIBY2 = 15.1423305995572655
+TTOT_YPIBY2_JL = 19.4735804728724204                 # spin.jl:605 (spin14.py's sum above differs in the last ulp)
+TTOT_XPIBY2_JL = 4 * TX_YPIBY2 + 2 * TZ_YPIBY2 + TTOT_ZPIBY2   # spin.jl:690
+ANALYTIC_SEGMENTS = {
+    GateType.zpiby2: ([0.0], [TTOT_ZPIBY2]),
+    GateType.ypiby2: ([AYPIBY2, 0.0, -AYPIBY2], [TX_YPIBY2, TZ_YPIBY2, TX_YPIBY2]),
+    # X/2 = (-Y/2) Z/2 (Y/2) in time order: -Y/2 first (spin14.py:150-158, spin.jl:691-697)
+    GateType.xpiby2: ([-AYPIBY2, 0.0, AYPIBY2, 0.0, AYPIBY2, 0.0, -AYPIBY2],
+                      [TX_YPIBY2, TZ_YPIBY2, TX_YPIBY2, TTOT_ZPIBY2, TX_YPIBY2, TZ_YPIBY2, TX_YPIBY2]),
+}
+ANALYTIC_DYNAMICS = {   # dynamics type -> (gate whose segments it integrates, density?)   (DT_GTM / DT_ST, spin.jl:76-91, 1000-1013)
+    DynamicsType.zpiby2nodis: (GateType.zpiby2, False), DynamicsType.zpiby2t1: (GateType.zpiby2, True),
+    DynamicsType.ypiby2nodis: (GateType.ypiby2, False), DynamicsType.ypiby2t1: (GateType.ypiby2, True),
+    DynamicsType.xpiby2nodis: (GateType.xpiby2, False), DynamicsType.xpiby2t1: (GateType.xpiby2, True),
+}
+
+
+def xpiby2da_segments():
+    """The segment list integrate_prop_xpiby2da! walks (spin.jl:819-905): the analytic X/2 pulse cut at every 0.1 ns noise
+    bin (noise_dt_inv = 10 assumed there) and at the six amplitude switches.  Returns (amps, durs, noise_idx) with 0-based
+    noise indices; durations are formed with the reference's own expressions (`T1_XPIBY2 - 2.1`, `2.2 - T1_XPIBY2`, ...)."""
+    t = [TX_YPIBY2]                                   # T1..T6 by the reference's chain of additions (spin.jl:691-697)
+    for d in (TZ_YPIBY2, TX_YPIBY2, TTOT_ZPIBY2, TX_YPIBY2, TZ_YPIBY2):
+        t.append(t[-1] + d)
+    level = [-AYPIBY2, 0.0, AYPIBY2, 0.0, AYPIBY2, 0.0, -AYPIBY2]
+    amps, durs, nidx = [], [], []
+    j = 1                                             # 1-based noise knot, as in the reference
+    for seg in range(7):
+        if seg < 6:
+            jb = int(math.floor(t[seg] * 10.0)) + 1   # the bin that contains the switch: 22, 174, 195, 374, 395, 547
+            while j < jb:
+                amps.append(level[seg]); durs.append(1e-1); nidx.append(j - 1); j += 1
+            lo, hi = (jb - 1) / 10.0, jb / 10.0         # the literals 2.1 / 2.2, 17.3 / 17.4, ... of the reference
+            amps.append(level[seg]); durs.append(t[seg] - lo); nidx.append(jb - 1)
+            amps.append(level[seg + 1]); durs.append(hi - t[seg]); nidx.append(jb - 1)
+            j = jb + 1
+        else:
+            while j <= 568:
+                amps.append(level[seg]); durs.append(1e-1); nidx.append(j - 1); j += 1
+            amps.append(level[seg]); durs.append(TTOT_XPIBY2_JL - 56.8); nidx.append(568)
+    return np.array(amps), np.array(durs), np.array(nidx, dtype=np.int32)
+
+
 def pulse_sin(N):
     """Synthetic benchmark pulse P_sin(N) of SURVEY §8(d): a_k on N knots, a_0 = a_{N-1} = 0."""
     k = np.arange(N)
@@ -386,8 +438,8 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
     seeds = np.atleast_1d(np.asarray(seed, dtype=np.int64))
     sseeds = seeds if state_seed is None else np.broadcast_to(np.atleast_1d(np.asarray(state_seed, dtype=np.int64)), seeds.shape)
     S = seeds.shape[0]
-    controls = np.ascontiguousarray(controls, dtype=np.float64).reshape(-1)
-    dt = 1.0 / dt_inv
+    controls = None if controls is None else np.ascontiguousarray(controls, dtype=np.float64).reshape(-1)
+    dt = 1.0 / dt_inv if dt_inv else 0.0
     fqs = np.broadcast_to(np.asarray(fq, dtype=np.float64), (S,)).copy()
     psi0 = np.stack([gen_rand_state_iso(int(s), eng) for s in sseeds])
     if dynamics_type == DynamicsType.schroed:
@@ -406,6 +458,23 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
         ch = _lib.LINDBLAD_T1 if dynamics_type == DynamicsType.lindbladt1 else _lib.LINDBLAD_T2
         fid, rho, st = eng.lindblad(controls, dt, gate_type, gate_count, float(fqs[0]), das, rho0, channels=ch,
                                     t2_gamma_c=GAMMAC if ch == _lib.LINDBLAD_T2 else 0.0)
+    elif dynamics_type in ANALYTIC_DYNAMICS:
+        # analytic gates (DT_AN, spin.jl:94-114): `controls`/`dt_inv` are ignored like the reference ignores save_file_path.
+        # xpiby2nodis is an empty loop in the reference (spin.jl:721-727); here it integrates the X/2 segments for real.
+        g, density = ANALYTIC_DYNAMICS[dynamics_type]
+        amps, durs = ANALYTIC_SEGMENTS[g]
+        das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
+        if density:
+            rho0 = np.stack([np.outer(get_vec_uniso(p), get_vec_uniso(p).conj()) for p in psi0])
+            fid, rho, st = eng.lindblad_segments(amps, durs, gate_type, gate_count, float(fqs[0]), das, rho0)
+        else:
+            fid, st = eng.mc_static_segments(amps, durs, gate_type, gate_count, fqs, das, psi0)
+    elif dynamics_type == DynamicsType.xpiby2da:
+        amps, durs, nidx = xpiby2da_segments()
+        nlen = int(math.ceil(TTOT_XPIBY2_JL * gate_count * noise_dt_inv)) + 1             # spin.jl:1569
+        if noise is None:
+            noise = np.concatenate([eng.pink_noise(int(s), 1, 0, namp, noise_dt_inv, max(nlen, 569)) for s in seeds])
+        fid, st = eng.mc_noise_segments(amps, durs, nidx, gate_type, gate_count, float(fqs[0]), noise, psi0)
     else:
         raise ValueError("unsupported dynamics type")
     return {

@@ -4,6 +4,8 @@
   models.npz        step maps + Jacobians of every model from the 50-digit referee (oracle/referee.py)
   mc_static.npz     integrate_prop_schroed! + compute_fidelities on the analytic Y/2 pulse, 50 digits
   lindblad.npz      integrate_prop_lindbladt1! on the same pulse, 50 digits
+  segments.npz      the analytic gates (spin.jl:562-594, 651-670, 765-785) and integrate_prop_xpiby2da! (spin.jl:819-905)
+                    as segment lists, 50 digits
   spin14_pulses.npz controls produced by the REFERENCE's own generator functions
                     (/root/reference/src/spin/spin14.py:62-220, imported with h5py/matplotlib stubbed)
 
@@ -123,7 +125,74 @@ def reference_pulses():
     return out
 
 
+def segment_cases():
+    """Analytic-gate integrators in 50 digits.  Segment lists come from rbqoc_b200.spin (plain data: amplitudes/durations)."""
+    from rbqoc_b200 import spin
+
+    rng = np.random.default_rng(99)
+    out = {}
+    S, G = 5, 6
+    fq = 1.4e-2 * (1 + 0.01 * rng.standard_normal(S)); fq[0] = 1.4e-2
+    da = 2.574e-5 * rng.standard_normal(S); da[0] = 0.0
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    psi0 = np.concatenate([psi.real, psi.imag], axis=1)
+    rho0 = np.einsum("si,sj->sij", psi, psi.conj())
+    lam = np.array([1.0, 1.0, 0.9, 0.8, 0.6])[:, None, None]
+    rho0 = lam * rho0 + (1 - lam) * np.eye(2) / 2
+    out.update(fq=fq, da=da, psi0=psi0, rho0=rho0, gate_count=G)
+    for gate in (spin.GateType.zpiby2, spin.GateType.ypiby2, spin.GateType.xpiby2):
+        amps, durs = spin.ANALYTIC_SEGMENTS[gate]
+        Gm = ref.mat_iso(ref.GATES[int(gate)]())
+        fid = np.empty((S, G + 1)); rho = np.empty((S, G + 1, 2, 2), dtype=np.complex128)
+        for s in range(S):
+            prop = mp.eye(4)
+            for a, d in zip(amps, durs):
+                prop = ref.propagator(F(fq[s]), F(a) + F(da[s]), F(d)) * prop
+            tg = [mp.matrix([F(t) for t in psi0[s]])]
+            for _ in range(3):
+                tg.append(Gm * tg[-1])
+            st = tg[0].copy()
+            fid[s, 0] = float(ref.fidelity_vec_iso2(list(st), list(tg[0])))
+            for g in range(1, G + 1):
+                st = prop * st
+                fid[s, g] = float(ref.fidelity_vec_iso2(list(st), list(tg[g % 4])))
+            lp = mp.eye(4)
+            for a, d in zip(amps, durs):
+                lp = mp.expm(ref.lindblad_generator(ref.FQ, F(a) + F(da[s])) * F(d)) * lp
+            v = mp.matrix([mp.mpc(complex(rho0[s, 0, 0])), mp.mpc(complex(rho0[s, 1, 0])), mp.mpc(complex(rho0[s, 0, 1])),
+                           mp.mpc(complex(rho0[s, 1, 1]))])
+            for g in range(G + 1):
+                rho[s, g] = [[complex(v[0]), complex(v[2])], [complex(v[1]), complex(v[3])]]
+                v = lp * v
+        out[f"fid_{gate.name}"] = fid
+        out[f"rho_{gate.name}"] = rho
+        print("segments", gate.name, flush=True)
+    # integrate_prop_xpiby2da!: noise exaggerated (1e-3 GHz) so that every segment's offset matters
+    amps, durs, nidx = spin.xpiby2da_segments()
+    S2, G2 = 3, 3
+    noise = 1e-3 * rng.standard_normal((S2, 569))
+    fid = np.empty((S2, G2 + 1))
+    Gm = ref.mat_iso(ref.GATES[int(spin.GateType.xpiby2)]())
+    for s in range(S2):
+        tg = [mp.matrix([F(t) for t in psi0[s]])]
+        for _ in range(3):
+            tg.append(Gm * tg[-1])
+        st = tg[0].copy()
+        fid[s, 0] = float(ref.fidelity_vec_iso2(list(st), list(tg[0])))
+        for g in range(1, G2 + 1):
+            for a, d, k in zip(amps, durs, nidx):
+                st = ref.propagator(ref.FQ, F(a) + F(noise[s, k]), F(d)) * st
+            fid[s, g] = float(ref.fidelity_vec_iso2(list(st), list(tg[g % 4])))
+        print("xpiby2da sample", s, flush=True)
+    out.update(da_noise=noise, da_fid=fid, da_gate_count=G2)
+    return out
+
+
 def main():
+    if "--segments-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "segments.npz"), **segment_cases())
+        return
     np.savez_compressed(os.path.join(HERE, "models.npz"), **model_cases())
     if "--models-only" in sys.argv:
         return
@@ -162,6 +231,7 @@ def main():
         for g, v in enumerate(out):
             rho[s, g] = [[complex(v[0]), complex(v[2])], [complex(v[1]), complex(v[3])]]
         print("lindblad sample", s, flush=True)
+    np.savez_compressed(os.path.join(HERE, "segments.npz"), **segment_cases())
     np.savez_compressed(os.path.join(HERE, "lindblad.npz"), controls=controls, dt=dt, gate=2, gate_count=G, fq=1.4e-2, da=da, rho0=rho0,
                         rho=rho)
 

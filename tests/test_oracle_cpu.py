@@ -200,3 +200,46 @@ def test_stats_definition(orc):
     assert st.hist[int(np.floor((np.log10(3.2e-5) + 16) * 16))] == 1
     assert st.hist[255] == 1          # 1.0 clamps into the last bin
     assert st.min == 0.0 and st.max == 1.0
+
+
+def _spin():
+    from rbqoc_b200 import spin     # plain data (segment lists, constants): importing it needs no GPU
+
+    return spin
+
+
+def test_analytic_gate_segments_are_exact_and_match_50_digit_golden(orc):
+    """integrate_prop_zpiby2nodis!/…t1! family (spin.jl:562-594, 651-670, 765-785) as segment lists: at the nominal
+    qubit frequency the analytic gates are exact (the known answer the reference embeds); with detuning/amplitude
+    offsets and T1 dissipation the oracle must sit on the 50-digit referee."""
+    spin = _spin()
+    z = np.load(GOLDEN + "/segments.npz")
+    G = int(z["gate_count"])
+    for gate in (spin.GateType.zpiby2, spin.GateType.ypiby2, spin.GateType.xpiby2):
+        amps, durs = spin.ANALYTIC_SEGMENTS[gate]
+        fid = orc.mc_static_segments(amps, durs, gate, G, z["fq"], z["da"], z["psi0"])
+        assert np.max(np.abs(fid[0] - 1.0)) < 5e-15, gate.name            # sample 0: fq = FQ, da = 0
+        assert np.max(np.abs(fid - z[f"fid_{gate.name}"])) < 1e-14, gate.name
+        fidc, rho = orc.lindblad_segments(amps, durs, gate, G, FQ, z["da"], z["rho0"])
+        assert np.max(np.abs(rho - z[f"rho_{gate.name}"][:, G])) < 5e-14, gate.name
+        assert np.all(fidc[:, 0] > 1 - 1e-12) and np.all(np.diff(fidc[0]) < 0)   # T1 decay lowers a pure state's fidelity
+
+
+def test_xpiby2da_segment_list_and_oracle(orc):
+    """integrate_prop_xpiby2da! (spin.jl:819-905): 569 noise bins + 6 amplitude switches; the same noise indices every gate."""
+    spin = _spin()
+    amps, durs, nidx = spin.xpiby2da_segments()
+    assert amps.shape == (575,) and nidx[0] == 0 and nidx[-1] == 568
+    assert abs(durs.sum() - spin.TTOT_XPIBY2_JL) < 1e-13
+    assert durs[21] == spin.TX_YPIBY2 - 2.1 and durs[22] == 2.2 - spin.TX_YPIBY2 and nidx[21] == nidx[22] == 21
+    assert durs[-1] == spin.TTOT_XPIBY2_JL - 56.8
+    z = np.load(GOLDEN + "/segments.npz")
+    G = int(z["da_gate_count"])
+    fid = orc.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, G, FQ, z["da_noise"], z["psi0"][:3])
+    # 575 Pade exponentials per gate: the reference algorithm's own rounding floor (~2e-16 per knot)
+    assert np.max(np.abs(fid - z["da_fid"])) < 1e-12
+    # without noise it is the exact X/2 gate
+    fid0 = orc.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 4, FQ, np.zeros((3, 569)), z["psi0"][:3])
+    assert np.max(np.abs(fid0 - 1.0)) < 1e-12
+    with pytest.raises(ValueError):
+        orc.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 1, FQ, np.zeros((1, 100)), z["psi0"][:1])

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import rbqoc_b200 as rbq
+from _cases import GOLDEN
 from rbqoc_b200 import spin
 
 pytestmark = pytest.mark.gpu
@@ -350,3 +351,67 @@ def test_lindblad_t2_dephasing(engine):
     t = 2 * n * dt
     assert abs(abs(rho[0, 0, 1]) - 0.5 * np.exp(-(gc * t + gf * gf * t * t))) < 1e-13
     assert abs(rho[0, 0, 0].real - 0.5) < 1e-15
+
+
+# ---- analytic gates as segment lists (spin.jl:562-594, 651-670, 765-785, 819-905) ----------------------------------------
+@pytest.mark.parametrize("gate", [spin.GateType.zpiby2, spin.GateType.ypiby2, spin.GateType.xpiby2], ids=lambda g: g.name)
+def test_analytic_gate_segments_match_oracle_and_golden(engine, oracle, gate):
+    z = np.load(GOLDEN + "/segments.npz")
+    G = int(z["gate_count"])
+    amps, durs = spin.ANALYTIC_SEGMENTS[gate]
+    # 50-digit golden: segments of up to 17.9 ns (theta ~ 0.8 rad .. 7 rad with the drive on) -> the sincos class
+    fid, st = engine.mc_static_segments(amps, durs, gate, G, z["fq"], z["da"], z["psi0"])
+    assert np.max(np.abs(fid - z[f"fid_{gate.name}"])) < 1e-14
+    assert np.max(np.abs(fid[0] - 1.0)) < 5e-15                       # nominal sample: the gate is exact
+    fidl, rho, stl = engine.lindblad_segments(amps, durs, gate, G, spin.FQ, z["da"], z["rho0"])
+    assert np.max(np.abs(rho - z[f"rho_{gate.name}"][:, G])) < 1e-13
+    # a sweep against the oracle, ragged sample count, statistics on the last gate
+    S = 1237
+    fq, da, psi0 = _samples(S, seed=int(gate))
+    fid, st = engine.mc_static_segments(amps, durs, gate, 7, fq, da, psi0)
+    ref = oracle.mc_static_segments(amps, durs, gate, 7, fq, da, psi0)
+    assert np.max(np.abs(fid - ref)) < FID_RTOL
+    e = 1.0 - fid[:, -1]
+    assert st.count == S and st.min == e.min() and st.max == e.max()
+    psi = psi0[:, :2] + 1j * psi0[:, 2:]
+    rho0 = np.einsum("si,sj->sij", psi, psi.conj())
+    fidl, rho, stl = engine.lindblad_segments(amps, durs, gate, 7, spin.FQ, da, rho0)
+    fidc, rref = oracle.lindblad_segments(amps, durs, gate, 7, spin.FQ, da, rho0)
+    assert np.max(np.abs(rho - rref)) < FID_RTOL
+    assert np.max(np.abs(fidl - fidc)) < 1e-8         # pure targets: sqrt-conditioned in any FP64 evaluation (see test_lindblad_t1_matches_oracle)
+    assert stl.count == S
+
+
+def test_xpiby2da_noise_segments_match_oracle_and_golden(engine, oracle):
+    z = np.load(GOLDEN + "/segments.npz")
+    amps, durs, nidx = spin.xpiby2da_segments()
+    G = int(z["da_gate_count"])
+    fid, st = engine.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, G, spin.FQ, z["da_noise"], z["psi0"][:3])
+    assert np.max(np.abs(fid - z["da_fid"])) < 1e-13
+    S = 333
+    _, _, psi0 = _samples(S, seed=5)
+    noise = spin.NAMP_PREFACTOR * 30 * np.random.default_rng(2).standard_normal((S, 600))
+    fid, st = engine.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 12, spin.FQ, noise, psi0)
+    ref = oracle.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 12, spin.FQ, noise, psi0)
+    assert np.max(np.abs(fid - ref)) < 5 * FID_RTOL     # 12 x 575 chained Pade exponentials on the oracle side
+    assert st.count == S
+    # bad noise index / short rows are argument errors, not reads past the row
+    with pytest.raises(Exception):
+        engine.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 1, spin.FQ, noise[:, :500], psi0)
+    # empty sweep
+    fid, st = engine.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 2, spin.FQ, np.zeros((0, 600)), np.zeros((0, 4)))
+    assert fid.shape == (0, 3) and st.count == 0
+
+
+def test_run_sim_prop_analytic_dynamics_types(engine):
+    """run_sim_prop(..., dynamics_type=zpiby2nodis / ypiby2t1 / xpiby2da ...) without a pulse file (DT_AN, spin.jl:94-114)."""
+    for dyn, gate in ((spin.DynamicsType.zpiby2nodis, spin.GateType.zpiby2), (spin.DynamicsType.ypiby2nodis, spin.GateType.ypiby2),
+                      (spin.DynamicsType.xpiby2nodis, spin.GateType.xpiby2)):
+        r = spin.run_sim_prop(10, gate, None, 0, seed=np.arange(5), dynamics_type=dyn, engine=engine)
+        assert np.max(np.abs(r["fidelities"] - 1)) < 1e-13
+    r = spin.run_sim_prop(50, spin.GateType.ypiby2, None, 0, seed=np.arange(4), dynamics_type=spin.DynamicsType.ypiby2t1, engine=engine)
+    f = r["fidelities"]
+    assert f.shape == (4, 51) and np.all(f[:, -1] < f[:, 0]) and np.all(f[:, -1] > 0.99)
+    r = spin.run_sim_prop(20, spin.GateType.xpiby2, None, 0, seed=np.arange(1, 9), dynamics_type=spin.DynamicsType.xpiby2da, engine=engine)
+    e = 1 - r["fidelities"][:, -1]
+    assert r["fidelities"].shape == (8, 21) and np.all(e >= -1e-13) and np.all(e < 1e-3) and np.any(e > 1e-10)
