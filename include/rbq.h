@@ -129,6 +129,11 @@ const char* rbq_last_error(const rbq_handle* h);
 /* cuda_stream = a cudaStream_t (NULL = the legacy default stream). */
 int rbq_set_stream(rbq_handle* h, void* cuda_stream);
 int rbq_synchronize(rbq_handle* h);
+/* Performance hint for rbq_mc_static(_dev): the point (qubit frequency, amplitude offset) the explicit samples scatter
+ * around.  Default (FQ, 0) = (1.4e-2 GHz, 0), the reference's FQ (spin.jl:148).  Samples near the centre take the
+ * 14-instruction knot-table step, the others the polynomial step; both meet the same accuracy bound, so the centre moves
+ * results by rounding only (~1e-15).  Philox sweeps are centred on their own fq0.  Non-finite values are rejected. */
+int rbq_set_sweep_centre(rbq_handle* h, double fq0, double da0);
 /* Page-locked host memory for the caller's buffers (e.g. the nabla-f storage a Julia caller hands to rbq_jacobians):
  * host-pointer entry points accept any host memory, but copies from/to pinned memory run at full PCIe rate and let the
  * chunked sweeps overlap upload, compute and download.  Free with rbq_host_free. */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rbq_destroy": (C.c_int, [_P]),
     "rbq_last_error": (C.c_char_p, [_P]),
     "rbq_set_stream": (C.c_int, [_P, _P]),
+    "rbq_set_sweep_centre": (C.c_int, [_P, _D, _D]),
     "rbq_synchronize": (C.c_int, [_P]),
     "rbq_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "rbq_host_free": (C.c_int, [_P, _P]),

@@ -126,6 +126,7 @@ int rbq_create(int device, rbq_handle** out) {
     memset(h, 0, sizeof(*h));
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->centre_fq = 1.4e-2; h->centre_da = 0.0;   // FQ (spin.jl:148), no amplitude offset
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
     for (int i = 0; i < 2; ++i)
         if (cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
@@ -149,6 +150,12 @@ const char* rbq_last_error(const rbq_handle* h) { return h ? h->err : "null hand
 int rbq_set_stream(rbq_handle* h, void* cuda_stream) {
     if (!h) return RBQ_E_NULL;
     h->stream = (cudaStream_t)cuda_stream;
+    return RBQ_OK;
+}
+int rbq_set_sweep_centre(rbq_handle* h, double fq0, double da0) {
+    ENTER(h);
+    if (!isfinite(fq0) || !isfinite(da0)) return fail(h, RBQ_E_SIZE, "rbq_set_sweep_centre: fq0=%g da0=%g", fq0, da0);
+    h->centre_fq = fq0; h->centre_da = da0;
     return RBQ_OK;
 }
 int rbq_synchronize(rbq_handle* h) {
@@ -382,12 +389,19 @@ int rbq_stats_merge(rbq_stats* a, const rbq_stats* b) {
     return RBQ_OK;
 }
 
-// stage the pulse and fill everything of McStaticArgs that does not depend on the sample range
+// build the knot table (expanded around the sweep centre) and fill everything of McStaticArgs that does not depend on
+// the sample range
 static int mc_static_prepare(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
-                             int64_t partial_blocks, rbq_stats* d_stats, McStaticArgs* a) {
+                             int64_t partial_blocks, rbq_stats* d_stats, double f0, double a0, McStaticArgs* a) {
     memset(a, 0, sizeof(*a));
     if (!make_gate_tables(gate, &a->gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
-    CKL(stage_pulse(h, d_controls, nk, &a->controls, &a->amax));
+    void *tb = nullptr, *sc = nullptr;
+    CKL(dev_buf(h, B_PULSE, sizeof(double) * 4 * (size_t)nk + 32, &tb));
+    CKL(dev_buf(h, B_SCALARS, 256, &sc));
+    CKL(launch_static_table(h, d_controls, nk, dt, f0, a0, (double*)tb, (double*)sc));
+    a->table = (const double*)tb; a->scal = (const double*)sc;
+    const char* e = getenv("RBQ_NO_TABLE_CLASS");
+    a->no_table_class = (e && atoi(e) != 0) ? 1 : 0;
     a->nk = nk; a->dt = dt; a->gate_count = gate_count;
     if (d_stats) {
         void* pp;
@@ -403,7 +417,9 @@ static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, d
                           double* d_fid, rbq_stats* d_stats) {
     McStaticArgs a;
     if (S == 0) { GateIso gi; return make_gate_tables(gate, &gi, nullptr) ? RBQ_OK : fail(h, RBQ_E_GATE, "unknown gate %d", gate); }
-    CKL(mc_static_prepare(h, d_controls, nk, dt, gate, gate_count, mc_static_blocks(h, S, algo), d_stats, &a));
+    // Philox sweeps are centred on their own (fq0, 0), explicit samples on the handle's centre (rbq_set_sweep_centre)
+    CKL(mc_static_prepare(h, d_controls, nk, dt, gate, gate_count, mc_static_blocks(h, S, algo), d_stats,
+                          philox ? fq0 : h->centre_fq, philox ? 0.0 : h->centre_da, &a));
     a.first = first; a.S = S;
     a.fq = d_fq; a.da = d_da; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.fq0 = fq0; a.fq_rel_sigma = fq_rel_sigma; a.fq_rel_clip = fq_rel_clip; a.da_sigma = da_sigma;
@@ -470,7 +486,8 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
             total_blocks += mc_static_blocks(h, cnt, algo);
         }
         McStaticArgs a;
-        CKL(mc_static_prepare(h, (double*)dc, nknots, dt, gate, gate_count, total_blocks, (rbq_stats*)dst, &a));
+        CKL(mc_static_prepare(h, (double*)dc, nknots, dt, gate, gate_count, total_blocks, (rbq_stats*)dst, h->centre_fq,
+                              h->centre_da, &a));
         BlockPartial* partials0 = a.partials;
         // event choreography: copy_stream[0] uploads, h->stream computes, copy_stream[1] downloads
         cudaStream_t up = h->copy_stream[0], down = h->copy_stream[1];

@@ -21,6 +21,8 @@ struct rbq_handle {
     // cached noise-index table of integrate_prop_schroedda! (host copy + key); the device copy is dbuf[B_IDX]
     int32_t* idx_host; size_t idx_cap;
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
+    // centre (qubit frequency, amplitude offset) the static sweep's knot table is expanded around: rbq_set_sweep_centre
+    double centre_fq, centre_da;
 };
 
 namespace rbq {
@@ -36,14 +38,15 @@ struct GateIso { double g[3][16]; };   // G, G^2, G^3 as row-major 4x4 iso matri
 struct GateRot { double r[3][9]; };    // the same gates as SO(3) rotations of the Bloch vector
 
 struct McStaticArgs {
-    const double* controls; int64_t nk; double dt;
+    const double* table; int64_t nk; double dt;   // knot table (q_j, c0_j, c1_j, c2_j), see static_table_kernel
     int64_t gate_count; int64_t first; int64_t S;
     const double* fq; const double* da; const double* psi0;   // explicit samples
     int philox; uint64_t seed; double fq0, fq_rel_sigma, fq_rel_clip, da_sigma;
     double* fid;                 // S*(gate_count+1) or NULL
     BlockPartial* partials;      // one per block, or NULL
     unsigned long long* hist;    // RBQ_HIST_BINS global bins, or NULL
-    const double* amax;          // device scalar: max |controls|
+    const double* scal;          // device scalars: max|a|, f0, a0, max|q_j|, table_ok, max x_j
+    int no_table_class;          // RBQ_NO_TABLE_CLASS=1: polynomial classes only (A/B measurements, parity of both)
     GateIso gate;
 };
 struct McNoiseArgs {
@@ -76,6 +79,9 @@ struct SegmentArgs {
 
 // every launcher enqueues on h->stream, bumps h->launches and returns a cudaError_t as int
 int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax);
+// knot table of the static sweep, expanded around the sweep centre (f0, a0)
+int launch_static_table(rbq_handle* h, const double* d_controls, int64_t nk, double dt, double f0, double a0, double* d_table,
+                        double* d_scal);
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);

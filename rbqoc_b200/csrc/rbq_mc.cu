@@ -50,9 +50,9 @@ RBQ_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 // shared-memory tiles.  `pass` counts tiles since kernel start so the pulse can be replayed once per gate.
 // Optionally a companion int32 table (one row of `aux_stride` entries per replay) rides in the same tiles:
 // the noise-sample index of every (gate, knot) of integrate_prop_schroedda!.
-template <int TILE>
+template <int TILE, int EPK = 1>
 struct PulsePipeT {
-    double* tile;       // [2][TILE]
+    double* tile;       // [2][TILE * EPK]   (EPK doubles per knot: 1 = the pulse itself, 4 = the static sweep's knot table)
     int32_t* aux_tile;  // [2][TILE] or nullptr
     uint64_t* bar;      // [2]
     const double* src;
@@ -74,10 +74,10 @@ struct PulsePipeT {
     RBQ_DEV int tile_len(int ti) const { const int64_t r = nk - (int64_t)ti * TILE; return r < TILE ? (int)r : TILE; }
     RBQ_DEV void issue(int ti, uint32_t slot, int64_t replay) {
         const int len = tile_len(ti);
-        const uint32_t bytes = (uint32_t)(((len + 1) & ~1) * sizeof(double));
+        const uint32_t bytes = (uint32_t)((EPK == 1 ? ((len + 1) & ~1) : len * EPK) * sizeof(double));
         const uint32_t abytes = aux_src ? (uint32_t)(((len + 3) & ~3) * sizeof(int32_t)) : 0u;
         mbar_expect_tx(&bar[slot], bytes + abytes);
-        bulk_g2s(tile + slot * TILE, src + (int64_t)ti * TILE, bytes, &bar[slot]);
+        bulk_g2s(tile + slot * (TILE * EPK), src + (int64_t)ti * (TILE * EPK), bytes, &bar[slot]);
         if (aux_src) bulk_g2s(aux_tile + slot * TILE, aux_src + replay * aux_stride + (int64_t)ti * TILE, abytes, &bar[slot]);
     }
     // call with ti = 0..ntiles-1 in order, replay = 0,1,..; every thread of the block must call it
@@ -90,7 +90,7 @@ struct PulsePipeT {
             else if (more_passes) issue(0, slot ^ 1u, replay + 1);
         }
         mbar_wait(&bar[slot], (pass >> 1) & 1u);
-        return tile + slot * TILE;
+        return tile + slot * (TILE * EPK);
     }
     RBQ_DEV const int32_t* aux() const { return aux_tile + (pass & 1u) * TILE; }
     // `more`: another acquire() follows (the barrier protects the slot the next prefetch overwrites)
@@ -98,6 +98,8 @@ struct PulsePipeT {
 };
 typedef PulsePipeT<MC_TILE> PulsePipe;
 constexpr int NOISE_TILE = 1024;
+constexpr int ST_TILE = 256;    // knots per tile of the static sweep's knot table (4 doubles per knot: 8 KB)
+constexpr int ST_EPK = 4;
 
 // ---- statistics ---------------------------------------------------------------------------------------
 struct ThreadStats {
@@ -196,6 +198,63 @@ __global__ void __launch_bounds__(1024) pulse_prep_kernel(const double* __restri
     }
 }
 
+// ---- knot table of the static sweep ------------------------------------------------------------------------------------
+// T(x) = tan(sqrt x)/sqrt x = sum t_k x^k (all t_k > 0).  Around the sweep's nominal point (f0, a0) every knot has
+// x_j = q_j^2 + p0^2, q_j = w (a_j + a0), p0 = w f0, and a sample (f, da) sees x = x_j + eps with
+//     eps = 2 q_j dq + dq^2 + (p^2 - p0^2),   dq = w (da - a0),  p = w f,
+// so T(x) = c0_j + eps (c1_j + eps c2_j) + R,  c_i = (i-th derivative of T at x_j)/i!,  0 <= R <= 0.057 eps^3 for x <= 0.03.
+// Table row j = (q_j, c0_j, c1_j, c2_j); scal = (max|a|, f0, a0, max|q_j|, table_ok, max x_j).
+RBQ_DEV void tan_taylor(double x, double& c0, double& c1, double& c2) {
+    constexpr double t[12] = {1.0, 1.0 / 3.0, 2.0 / 15.0, 17.0 / 315.0, 62.0 / 2835.0, 1382.0 / 155925.0, 21844.0 / 6081075.0,
+                              929569.0 / 638512875.0, 6404582.0 / 10854718875.0, 443861162.0 / 1856156927625.0,
+                              18888466084.0 / 194896477400625.0, 113927491862.0 / 2900518163668125.0};
+    double s0 = t[11], s1 = 11.0 * t[11], s2 = 55.0 * t[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) {
+        s0 = fma(s0, x, t[k]);
+        if (k >= 1) s1 = fma(s1, x, (double)k * t[k]);
+        if (k >= 2) s2 = fma(s2, x, (double)(k * (k - 1) / 2) * t[k]);
+    }
+    c0 = s0; c1 = s1; c2 = s2;
+}
+constexpr double DELTA_XMAX = 0.03;       // nominal x up to which the 12-term series and the remainder bound are used
+constexpr double DELTA_R3 = 0.057;        // >= (third derivative of T)/6 on [0, DELTA_XMAX + 1e-4]
+constexpr double DELTA_TOL = 5e-17;       // admitted relative truncation of T per knot
+__global__ void __launch_bounds__(1024) static_table_kernel(const double* __restrict__ controls, int64_t nk, double dt,
+                                                            double f0_in, double a0_in, double* __restrict__ table,
+                                                            double* __restrict__ scal) {
+    __shared__ double red[3][32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double f0 = isfinite(f0_in) ? f0_in : 0.0, a0 = isfinite(a0_in) ? a0_in : 0.0;
+    const double w = RBQ_PI * dt, p0 = w * f0, p02 = p0 * p0;
+    double amax = 0.0, qmax = 0.0, xmax = 0.0;
+    for (int64_t j = tid; j < nk; j += 1024) {
+        const double a = controls[j];
+        const double q = w * (a + a0);
+        const double x = fma(q, q, p02);
+        double c0, c1, c2;
+        tan_taylor(x <= DELTA_XMAX ? x : DELTA_XMAX, c0, c1, c2);   // rows beyond the range are only read for q_j
+        table[4 * j] = q; table[4 * j + 1] = c0; table[4 * j + 2] = c1; table[4 * j + 3] = c2;
+        amax = fmax(amax, fabs(a)); qmax = fmax(qmax, fabs(q));
+        xmax = x == x ? fmax(xmax, x) : INFINITY;                    // NaN controls switch the table class off
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o));
+        qmax = fmax(qmax, __shfl_down_sync(0xffffffffu, qmax, o));
+        xmax = fmax(xmax, __shfl_down_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) { red[0][warp] = amax; red[1][warp] = qmax; red[2][warp] = xmax; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 32; ++i) { amax = fmax(amax, red[0][i]); qmax = fmax(qmax, red[1][i]); xmax = fmax(xmax, red[2][i]); }
+        scal[0] = amax; scal[1] = f0; scal[2] = a0; scal[3] = qmax;
+        scal[4] = (xmax <= DELTA_XMAX) ? 1.0 : 0.0;
+        scal[5] = xmax;
+    }
+}
+
 // ---- per-sample pieces ----------------------------------------------------------------------------------
 // propagator class from a bound on x = theta^2:
 //   0 -> tan form, degree-4 polynomial (x <= 1e-3: the dt = 0.01 grids)     1 -> tan form, degree 6 (x <= 0.026: dt = 0.1)
@@ -213,13 +272,14 @@ template <int K> RBQ_DEV void su2_coeffs(double x, double& c, double& s) {
         c = cs; s = sn / th;
     }
 }
-// advance SPT states through `len` knots of a tile:  q_j = w a_j + qd   (normalised form, any x)
+// advance SPT states through `len` knots of a table tile (row j starts with q_j = w (a_j + a0)):  q = q_j + dq
+// (normalised form, any x)
 template <int K, int SPT>
-RBQ_DEV void su2_tile(const double* __restrict__ tile, int len, double w, const double (&p)[SPT], const double (&p2)[SPT],
+RBQ_DEV void su2_tile(const double* __restrict__ tile, int len, const double (&p)[SPT], const double (&p2)[SPT],
                       const double (&qd)[SPT], double (&v)[SPT][4]) {
 #pragma unroll 4
     for (int j = 0; j < len; ++j) {
-        const double wa = w * tile[j];
+        const double wa = tile[ST_EPK * j];
 #pragma unroll
         for (int i = 0; i < SPT; ++i) {
             const double q = wa + qd[i];
@@ -249,14 +309,14 @@ RBQ_DEV void tan_apply(double tp, double tq, double* v) {
     v[3] = fma(-tq, a0, fma(tp, a1, a3));
 }
 template <int DEG, int SPT, int U>
-RBQ_DEV void tan_tile(const double* __restrict__ tile, int len, double w, const double (&p)[SPT], const double (&p2)[SPT],
+RBQ_DEV void tan_tile(const double* __restrict__ tile, int len, const double (&p)[SPT], const double (&p2)[SPT],
                       const double (&qd)[SPT], double (&v)[SPT][4], const double (&cf)[DEG + 1]) {
     int j = 0;
     for (; j + U <= len; j += U) {
         double q[U][SPT], x[U][SPT], t[U][SPT];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const double wa = w * tile[j + u];
+            const double wa = tile[ST_EPK * (j + u)];
 #pragma unroll
             for (int i = 0; i < SPT; ++i) { q[u][i] = wa + qd[i]; x[u][i] = fma(q[u][i], q[u][i], p2[i]); }
         }
@@ -276,7 +336,7 @@ RBQ_DEV void tan_tile(const double* __restrict__ tile, int len, double w, const 
             for (int i = 0; i < SPT; ++i) tan_apply(t[u][i] * p[i], t[u][i] * q[u][i], v[i]);
     }
     for (; j < len; ++j) {
-        const double wa = w * tile[j];
+        const double wa = tile[ST_EPK * j];
 #pragma unroll
         for (int i = 0; i < SPT; ++i) {
             const double q = wa + qd[i];
@@ -285,6 +345,45 @@ RBQ_DEV void tan_tile(const double* __restrict__ tile, int len, double w, const 
         }
     }
     // |v| grows by 1/cos(theta) per knot (at most e^27 over a 2048-knot tile in class 1): pull it back to 1 per tile
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        const double inv = rsqrt(fma(v[i][3], v[i][3], fma(v[i][2], v[i][2], fma(v[i][1], v[i][1], v[i][0] * v[i][0]))));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[i][c] *= inv;
+    }
+}
+// Table class: T from the knot table's local Taylor polynomial in eps = q_j (2 dq) + e0 (see static_table_kernel):
+//     1 fma (eps) + 2 fma (T) + 1 add (q) + 2 mul + 8 fma = 14 FP64 instructions per knot, U knots interleaved.
+template <int SPT, int U>
+RBQ_DEV void delta_tile(const double* __restrict__ tile, int len, const double (&p)[SPT], const double (&dq)[SPT],
+                        const double (&dq2)[SPT], const double (&e0)[SPT], double (&v)[SPT][4]) {
+    int j = 0;
+    for (; j + U <= len; j += U) {
+        double q[U][SPT], t[U][SPT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double* __restrict__ r = tile + ST_EPK * (j + u);
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                const double eps = fma(r[0], dq2[i], e0[i]);
+                q[u][i] = r[0] + dq[i];
+                t[u][i] = fma(fma(r[3], eps, r[2]), eps, r[1]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) tan_apply(t[u][i] * p[i], t[u][i] * q[u][i], v[i]);
+    }
+    for (; j < len; ++j) {
+        const double* __restrict__ r = tile + ST_EPK * j;
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            const double eps = fma(r[0], dq2[i], e0[i]);
+            const double t = fma(fma(r[3], eps, r[2]), eps, r[1]);
+            tan_apply(t * p[i], t * (r[0] + dq[i]), v[i]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
         const double inv = rsqrt(fma(v[i][3], v[i][3], fma(v[i][2], v[i][2], fma(v[i][1], v[i][1], v[i][0] * v[i][0]))));
@@ -327,21 +426,23 @@ RBQ_DEV double gate_train(const double* E, const double* psi0, const GateIso& G,
 // ---- static-parameter sweep -------------------------------------------------------------------------------
 template <int ALGO, int SPT, int MINB, int THREADS>
 __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStaticArgs a) {
-    __shared__ __align__(128) double tile_s[2 * MC_TILE];
+    __shared__ __align__(128) double tile_s[2 * ST_TILE * ST_EPK];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[THREADS / 32];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += THREADS) hist_s[b] = 0;
-    PulsePipe pipe;
-    pipe.init(tile_s, bar_s, a.controls, a.nk);
+    PulsePipeT<ST_TILE, ST_EPK> pipe;
+    pipe.init(tile_s, bar_s, a.table, a.nk);
 
     const int64_t base = (int64_t)blockIdx.x * (THREADS * SPT);
     const double w = RBQ_PI * a.dt;
-    double p[SPT], p2[SPT], qd[SPT], psi0[SPT][4];
+    // q = q_j + qd with q_j = w (a_j + a0) from the table and qd = w (da - a0)
+    double p[SPT], p2[SPT], qd[SPT], qd2[SPT], e0[SPT], psi0[SPT][4];
     bool live[SPT];
-    int cls = 0;
-    const double wamax = w * (*a.amax);
+    int cls = -1;
+    const double a0 = a.scal[2], qmax = a.scal[3], p0 = w * a.scal[1];
+    const bool table_ok = ALGO == RBQ_ALGO_SU2 && a.scal[4] != 0.0 && !a.no_table_class;
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
         const int64_t s = base + (int64_t)i * THREADS + tid;
@@ -359,10 +460,13 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
                 for (int c = 0; c < 4; ++c) psi0[i][c] = a.psi0[4 * s + c];
             }
         }
-        p[i] = w * fq; p2[i] = p[i] * p[i]; qd[i] = w * da;
-        const double qb = wamax + fabs(qd[i]);
+        p[i] = w * fq; p2[i] = p[i] * p[i]; qd[i] = w * (da - a0);
+        qd2[i] = 2.0 * qd[i]; e0[i] = fma(qd[i], qd[i], (p[i] - p0) * (p[i] + p0));
+        const double epsb = fma(fabs(qd2[i]), qmax, fabs(e0[i]));        // |eps| <= 2 |q_j| |dq| + |e0| at every knot
+        const bool delta_ok = table_ok && DELTA_R3 * epsb * epsb * epsb <= DELTA_TOL;   // false for NaN
+        const double qb = qmax + fabs(qd[i]);
         const double xb = fma(qb, qb, p2[i]);
-        cls = max(cls, xb == xb ? degree_class(xb) : 3);
+        cls = max(cls, delta_ok ? -1 : (xb == xb ? degree_class(xb) : 3));
     }
     cls = warp_max_class(cls);
 
@@ -376,10 +480,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
-            if (cls == 0) tan_tile<RBQ_TANA_DEG, SPT, UNR>(tile, len, w, p, p2, qd, v, cfA);
-            else if (cls == 1) tan_tile<RBQ_TANB_DEG, SPT, UNR>(tile, len, w, p, p2, qd, v, cfB);
-            else if (cls == 2) su2_tile<8, SPT>(tile, len, w, p, p2, qd, v);
-            else su2_tile<0, SPT>(tile, len, w, p, p2, qd, v);
+            if (cls < 0) delta_tile<SPT, UNR>(tile, len, p, qd, qd2, e0, v);
+            else if (cls == 0) tan_tile<RBQ_TANA_DEG, SPT, UNR>(tile, len, p, p2, qd, v, cfA);
+            else if (cls == 1) tan_tile<RBQ_TANB_DEG, SPT, UNR>(tile, len, p, p2, qd, v, cfB);
+            else if (cls == 2) su2_tile<8, SPT>(tile, len, p, p2, qd, v);
+            else su2_tile<0, SPT>(tile, len, p, p2, qd, v);
             pipe.release(ti + 1 < pipe.ntiles);
         }
         // the exact product is a unit quaternion: dividing out |v| removes the radial rounding error, which
@@ -401,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
             for (int j = 0; j < len; ++j) {
-                const double wa = w * tile[j];
+                const double wa = tile[ST_EPK * j];
 #pragma unroll
                 for (int i = 0; i < SPT; ++i) {
                     double G[16], X[16], T[16];
@@ -1096,6 +1201,12 @@ int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, doubl
     // staged pulse lives in dbuf[0] (sized by the caller), padded to a multiple of 2 knots
     const int64_t padded = (nk + 1) & ~(int64_t)1;
     pulse_prep_kernel<<<1, 1024, 0, h->stream>>>(d_controls, nk, padded, (double*)h->dbuf[0], d_amax);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_static_table(rbq_handle* h, const double* d_controls, int64_t nk, double dt, double f0, double a0, double* d_table,
+                        double* d_scal) {
+    static_table_kernel<<<1, 1024, 0, h->stream>>>(d_controls, nk, dt, f0, a0, d_table, d_scal);
     h->launches++;
     return (int)cudaGetLastError();
 }

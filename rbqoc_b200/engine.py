@@ -68,6 +68,10 @@ class Engine:
     def set_stream(self, cuda_stream: int):
         self._ck(self._lib.rbq_set_stream(self._h, C.c_void_p(cuda_stream)), "rbq_set_stream")
 
+    def set_sweep_centre(self, fq0: float, da0: float = 0.0):
+        """Performance hint: where the explicit samples of mc_static scatter (default FQ, 0); see include/rbq.h."""
+        self._ck(self._lib.rbq_set_sweep_centre(self._h, float(fq0), float(da0)), "rbq_set_sweep_centre")
+
     def use_torch_stream(self):
         import torch
 

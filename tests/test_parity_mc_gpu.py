@@ -415,3 +415,54 @@ def test_run_sim_prop_analytic_dynamics_types(engine):
     r = spin.run_sim_prop(20, spin.GateType.xpiby2, None, 0, seed=np.arange(1, 9), dynamics_type=spin.DynamicsType.xpiby2da, engine=engine)
     e = 1 - r["fidelities"][:, -1]
     assert r["fidelities"].shape == (8, 21) and np.all(e >= -1e-13) and np.all(e < 1e-3) and np.any(e > 1e-10)
+
+
+# ---- the knot-table step (local Taylor polynomial of tan(theta)/theta around the sweep centre) ---------------------------
+@pytest.mark.parametrize("name", ["sin1001_dt0.1", "y2_dt0.01", "ragged_2049"])
+def test_table_class_equals_polynomial_classes(engine, oracle, name, monkeypatch):
+    """Samples near the sweep centre take the table step, the rest the Horner/series step; both carry a < 1e-16 relative
+    truncation per knot, so they agree to rounding, and each matches the oracle / the 50-digit golden on its own."""
+    controls, dt, gate = PULSES[name]
+    S = 4096 + 77
+    fq, da, psi0 = _samples(S, seed=21)
+    # blocks with mixed warps: every 5th warp is pushed out of the table's range (eps ~ 2 w^2 a da grows with dt^2)
+    da[np.arange(S) % 160 < 32] += 2e-3 if dt >= 0.05 else 0.2
+    fid_t, st_t = engine.mc_static(controls, dt, gate, 3, fq, da, psi0)
+    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    fid_p, st_p = engine.mc_static(controls, dt, gate, 3, fq, da, psi0)
+    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    assert np.max(np.abs(fid_t - fid_p)) < 5e-14
+    far = np.arange(S) % 160 < 32
+    assert np.array_equal(fid_t[far], fid_p[far])              # out-of-range warps run the same code either way
+    assert not np.array_equal(fid_t[~far], fid_p[~far])        # ... and the in-range ones really took the other path
+    ref = oracle.mc_static(controls, dt, gate, 3, fq[:600], da[:600], psi0[:600])
+    nk = controls.shape[0]
+    assert np.max(np.abs(fid_t[:600] - ref)) < max(3 * FID_RTOL, 2.5e-15 * nk)
+    assert st_t.count == st_p.count == S
+
+
+def test_table_class_golden_and_sweep_centre(engine, monkeypatch):
+    """50-digit golden with the table step on and off; moving the sweep centre (rbq_set_sweep_centre) only moves rounding."""
+    z = np.load(GOLDEN + "/mc_static.npz")
+    args = (z["controls"], float(z["dt"]), int(z["gate"]), int(z["gate_count"]), z["fq"], z["da"], z["psi0"])
+    fid_t, _ = engine.mc_static(*args)
+    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    fid_p, _ = engine.mc_static(*args)
+    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    assert np.max(np.abs(fid_t - z["fid"])) < 1e-13 and np.max(np.abs(fid_p - z["fid"])) < 1e-13
+    assert not np.array_equal(fid_t, fid_p)
+    # a sweep around another qubit frequency: off-centre it falls back to the polynomial step, re-centred it takes the table
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    S = 2000
+    fq, da, psi0 = _samples(S, seed=8)
+    fq *= 3.0
+    da += 1e-3
+    fid_off, _ = engine.mc_static(controls, dt, gate, 2, fq, da, psi0)
+    try:
+        engine.set_sweep_centre(3.0 * spin.FQ, 1e-3)
+        fid_on, _ = engine.mc_static(controls, dt, gate, 2, fq, da, psi0)
+    finally:
+        engine.set_sweep_centre(spin.FQ, 0.0)
+    assert np.max(np.abs(fid_on - fid_off)) < 5e-14 and not np.array_equal(fid_on, fid_off)
+    with pytest.raises(Exception):
+        engine.set_sweep_centre(float("nan"), 0.0)
