@@ -31,16 +31,22 @@ NK = 1000            # control knots of P_sin(1001)
 DT = 0.1
 S_PER_GPU = 1 << 20
 GATE_COUNT = 1
-# flops the closed-form kernel executes per trajectory-step on this grid (tan form, degree-6 polynomial, class B):
-#   1 DFMA (q = w a_j + w da) + 1 DFMA (x = q^2 + p^2) + 6 DFMA (T(x)) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v)
-#   = 18 FP64 instructions = 34 flop (FMA = 2); counted in the SASS: (128 DFMA*2 + 16 DMUL) / 8 sample-steps  [DESIGN.md §4.2]
-FLOPS_PER_STEP_SU2 = 34.0
-FP64_INSTR_PER_STEP_SU2 = 18.0
+# flops the closed-form kernel executes per trajectory-step on this grid (FMA = 2), counted in the SASS [DESIGN.md §4.2]:
+#   knot-table step (samples near the sweep centre -- every warp of this workload but ~0.3 %):
+#     1 DFMA (eps) + 2 DFMA (T) + 1 DADD (q) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v) = 14 FP64 instructions = 25 flop
+#   polynomial step (RBQ_NO_TABLE_CLASS=1, or samples far from the centre; tan form, degree-6 polynomial, class B):
+#     1 DADD (q) + 1 DFMA (x) + 6 DFMA (T(x)) + 2 DMUL + 8 DFMA = 18 FP64 instructions = 33 flop
+TABLE_CLASS = os.environ.get("RBQ_NO_TABLE_CLASS", "0") in ("", "0")
+FLOPS_PER_STEP_SU2 = 25.0 if TABLE_CLASS else 33.0
+FP64_INSTR_PER_STEP_SU2 = 14.0 if TABLE_CLASS else 18.0
+# FP64 instructions per step with three 64-bit register operands (state updates; with the table also eps and the two
+# Horner steps, whose coefficients are per-knot registers instead of constants)
+FP64_INSTR3_PER_STEP_SU2 = 11.0 if TABLE_CLASS else 8.0
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default sizes, from the
-# `ncu --set full` capture summarised in profiles/r1_ncu_mc_static_full.csv (50.43 MB read + 0.40 MB written: the 16 MB of
+# `ncu --set full` capture summarised in profiles/r1b_ncu_mc_static_full.csv (50.44 MB read + 0.38 MB written: the 16 MB of
 # fidelities stay in the 126 MB L2); algorithmic bytes are 48 MB in + 16 MB out
-NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_431_744 + 403_968
+NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_435_072 + 383_232
 
 
 def sample_clocks(stop, out):
@@ -432,20 +438,21 @@ def main():
             "config": {"workload": f"mc_static sweep (BASELINE configs[4]): P_sin({NK + 1}) = {NK} knots, dt={DT} ns, "
                                    f"S={S} samples per GPU (Philox keyed by global index; fq~N(0,1%) clipped 3%, "
                                    f"da~N(0,2.574e-5)), gate_count={GATE_COUNT}, per-sample fidelities + statistics",
-                       "samples_per_gpu": S, "knots": NK, "algo": "su2 closed form (tan form, degree-6 polynomial)", "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "samples_per_gpu": S, "knots": NK,
+                       "algo": ("su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre)"
+                                if TABLE_CLASS else "su2 closed form, tan form, degree-6 polynomial step"), "l2": "flushed between steps (256 MiB memset, untimed)",
                        "sharding": ("contiguous sample ranges per rank; per step ONE all-gather of the 2.1 KB statistics, copied to pinned host "
                                     "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_tflops if peak_tflops else None,
                          "traffic": NCU_DRAM_TRAFFIC_BYTES_DEFAULT if (S == S_PER_GPU) else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_ncu_mc_static_full.csv)",
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1b_ncu_mc_static_full.csv)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
                          # register-operand model of the FP64 pipe (profiles/r1_fp64_microbench.txt): 2 issue cycles per warp-DFMA
-                         # with <= 2 fresh 64-bit register operands, ~3 with 3 (the register file feeds two per slot); of the
-                         # 18 instructions of a step 10 are two-operand forms and 8 are the three-operand state updates
-                         "issue_model": {"cycles_per_warp_step_floor": 10 * 2 + 8 * 3,
+                         # with <= 2 fresh 64-bit register operands, ~3 with 3 (the register file feeds two per slot)
+                         "issue_model": {"cycles_per_warp_step_floor": (FP64_INSTR_PER_STEP_SU2 - FP64_INSTR3_PER_STEP_SU2) * 2 + FP64_INSTR3_PER_STEP_SU2 * 3,
                                          "cycles_per_warp_step_measured": (clk["sm_mhz"] or 1965.0) * 1e6 * 4 * 148 * (kern_ms * 1e-3) / (S * NK / 32.0),
                                          "note": "floor / measured = fraction of the operand-bandwidth-limited issue rate"},
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,
@@ -454,7 +461,8 @@ def main():
                                  "note": "algorithmic bytes; shows the path is not HBM bound"}},
             "e2e": {"value": steps_per_step_all / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
                     "h2d_bytes_per_step": S * 48 + NK * 8, "d2h_bytes_per_step": S * 16 + 2096, "ms_per_step": e2e_ms,
-                    "api": "rbq_mc_static (host pointers, pinned)",
+                    "api": ("rbq_mc_static (host pointers, pinned): " + ("streamed in one-wave chunks" if os.environ.get("RBQ_MC_ZEROCOPY") == "0"
+                                                                          else "zero-copy, the kernel reads the samples and writes the fidelities over PCIe")),
                     "pcie_measured": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
                                       "h2d_floor_ms": (S * 48 + NK * 8) / (h2d_gbs * 1e6) if h2d_gbs else None}},
             "gpu_launches": launches,

@@ -456,6 +456,14 @@ static inline int64_t mc_chunk_begin(int64_t c, int64_t wave, int64_t S) {
     const int64_t b = c == 0 ? 0 : wave * (g_chunk_first + g_chunk_rest * (c - 1));
     return b < S ? b : S;
 }
+// page-locked host memory the device can address directly (cudaMallocHost / cudaHostRegister / torch pin_memory)
+static bool host_mapped(const void* p, void** dptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dptr = at.devicePointer;
+    return true;
+}
 int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count, int64_t S,
                   const double* fq, const double* da, const double* psi0, int algo, double* fid, rbq_stats* stats) {
     ENTER(h);
@@ -463,6 +471,28 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
     if (S > 0 && (!fq || !psi0)) return fail(h, RBQ_E_NULL, "rbq_mc_static: fq/psi0 is NULL");
     GateIso gi;
     if (!make_gate_tables(gate, &gi, nullptr)) return fail(h, RBQ_E_GATE, "rbq_mc_static: unknown gate %d", gate);
+    // Zero-copy form: when every sample buffer is page-locked, ONE kernel reads the samples (48 B each, once, coalesced)
+    // and writes the fidelities straight over PCIe; block start-up staggers the transfers behind the arithmetic of the
+    // other resident blocks, so there are no chunk boundaries, launch gaps or staging copies.  Worth it while the
+    // kernel is compute bound, i.e. few recorded gates per sample.  RBQ_MC_ZEROCOPY=0 forces the streamed form.
+    {
+        void *mfq = nullptr, *mda = nullptr, *mpsi = nullptr, *mfid = nullptr;
+        const char* e = getenv("RBQ_MC_ZEROCOPY");
+        const bool want = !(e && atoi(e) == 0) && algo == RBQ_ALGO_SU2 && S > 0 && gate_count <= 3;
+        if (want && host_mapped(fq, &mfq) && host_mapped(psi0, &mpsi) && (!da || host_mapped(da, &mda)) &&
+            (!fid || host_mapped(fid, &mfid))) {
+            void *dc0, *dst0 = nullptr;
+            CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc0));
+            if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst0)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst0)); }
+            CK(cudaMemcpyAsync(dc0, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+            int rc = mc_static_core(h, (double*)dc0, nknots, dt, gate, gate_count, 0, S, (double*)mfq, (double*)mda, (double*)mpsi,
+                                    0, 0, 0, 0, 0, 0, algo, (double*)mfid, (rbq_stats*)dst0);
+            if (rc) return rc;
+            if (stats) CK(cudaMemcpyAsync(stats, dst0, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return RBQ_OK;
+        }
+    }
     void *dc, *dfq, *dda, *dpsi, *dfid = nullptr, *dst = nullptr;
     const int64_t G1 = gate_count + 1;
     CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));

@@ -145,18 +145,19 @@ RBQ_DEV void block_stats_flush(ThreadStats st, unsigned* hist_s, BlockPartial* r
         if (hist_s[b]) atomicAdd(&hist_g[b], (unsigned long long)hist_s[b]);
 }
 
-__global__ void __launch_bounds__(256) stats_finalize_kernel(const BlockPartial* __restrict__ partials, int nblocks,
+constexpr int FIN_THREADS = 512;    // one block; fixed thread -> partial assignment and tree => deterministic sums
+__global__ void __launch_bounds__(FIN_THREADS) stats_finalize_kernel(const BlockPartial* __restrict__ partials, int nblocks,
                                                              rbq_stats* __restrict__ out) {
-    __shared__ BlockPartial red[256];
+    __shared__ BlockPartial red[FIN_THREADS];
     BlockPartial r{0.0, 0.0, INFINITY, -INFINITY, 0, 0};
-    for (int i = threadIdx.x; i < nblocks; i += 256) {   // fixed assignment => deterministic sum order
+    for (int i = threadIdx.x; i < nblocks; i += FIN_THREADS) {   // fixed assignment => deterministic sum order
         const BlockPartial q = partials[i];
         r.sum += q.sum; r.sumsq += q.sumsq; r.mn = fmin(r.mn, q.mn); r.mx = fmax(r.mx, q.mx);
         r.cnt += q.cnt; r.nonfinite += q.nonfinite;
     }
     red[threadIdx.x] = r;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) {
             BlockPartial& a = red[threadIdx.x];
             const BlockPartial& b = red[threadIdx.x + o];
@@ -412,6 +413,14 @@ RBQ_DEV double gate_train(const double* E, const double* psi0, const GateIso& G,
     for (int k = 0; k < 3; ++k) mv4_to(G.g[k], psi0, tg[k + 1]);
     double st[4] = {psi0[0], psi0[1], psi0[2], psi0[3]};
     double f = fidelity_vec_iso2(st, tg[0]);
+    if (gate_count == 1 && fid_row && (reinterpret_cast<uintptr_t>(fid_row) & 15) == 0) {
+        // one gate: the (before, after) pair leaves as one 16-byte store, so a warp writes 512 contiguous bytes (this
+        // matters when fid_row is mapped host memory: full sectors over PCIe)
+        mv4(E, st);
+        const double f1 = fidelity_vec_iso2(st, tg[1]);
+        *reinterpret_cast<double2*>(fid_row) = make_double2(f, f1);
+        return f1;
+    }
     if (fid_row) fid_row[0] = f;
     for (int64_t g = 1; g <= gate_count; ++g) {
         mv4(E, st);
@@ -1272,7 +1281,7 @@ int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nbl
     return (int)cudaGetLastError();
 }
 int launch_stats_finalize(rbq_handle* h, const BlockPartial* partials, int nblocks, rbq_stats* d_stats) {
-    stats_finalize_kernel<<<1, 256, 0, h->stream>>>(partials, nblocks, d_stats);
+    stats_finalize_kernel<<<1, FIN_THREADS, 0, h->stream>>>(partials, nblocks, d_stats);
     h->launches++;
     return (int)cudaGetLastError();
 }

@@ -466,3 +466,36 @@ def test_table_class_golden_and_sweep_centre(engine, monkeypatch):
     assert np.max(np.abs(fid_on - fid_off)) < 5e-14 and not np.array_equal(fid_on, fid_off)
     with pytest.raises(Exception):
         engine.set_sweep_centre(float("nan"), 0.0)
+
+
+@pytest.mark.parametrize("gate_count", [1, 3], ids=["pair_store", "row_store"])
+def test_mc_static_zero_copy_equals_streamed(engine, monkeypatch, gate_count):
+    """Page-locked sample buffers are read (and the fidelities written) by the kernel itself over PCIe; pageable ones are
+    streamed in chunks.  Same kernel, same samples, same bits; the launch count shows which form ran."""
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    S = 20000 + 13
+    fq, da, psi0 = _samples(S, seed=31)
+    fid_s, st_s = engine.mc_static(controls, dt, gate, gate_count, fq, da, psi0)           # pageable -> streamed
+    pfq, pda, ppsi = engine.pinned_empty(S), engine.pinned_empty(S), engine.pinned_empty((S, 4))
+    pfid = engine.pinned_empty((S, gate_count + 1))
+    pfq[:], pda[:], ppsi[:] = fq, da, psi0
+    pfid[:] = -1.0
+    before = engine.launch_count
+    fid_z, st_z = engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=pfid)
+    launches_zero_copy = engine.launch_count - before
+    assert fid_z is pfid and np.array_equal(pfid, fid_s)
+    assert st_z.count == S and st_z.sum == st_s.sum and st_z.hist[:] == st_s.hist[:]
+    # da = None and no per-sample output
+    _, st_n = engine.mc_static(controls, dt, gate, gate_count, pfq, None, ppsi, want_fid=False)
+    _, st_m = engine.mc_static(controls, dt, gate, gate_count, fq, None, psi0, want_fid=False)
+    assert st_n.sum == st_m.sum and st_n.count == S
+    # a misaligned fidelity buffer (8-byte offset) still works (row stores instead of the 16-byte pair store)
+    raw = engine.pinned_empty(S * (gate_count + 1) + 1)
+    off = raw[1:].reshape(S, gate_count + 1)
+    engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=off)
+    assert np.array_equal(off, fid_s)
+    monkeypatch.setenv("RBQ_MC_ZEROCOPY", "0")
+    before = engine.launch_count
+    fid_c, _ = engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=pfid)
+    assert np.array_equal(fid_c, fid_s)
+    assert engine.launch_count - before >= launches_zero_copy
