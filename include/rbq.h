@@ -311,6 +311,27 @@ int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs,
                           int64_t gate_count, int64_t S, double fq, const double* da, const double* rho0, int channels,
                           double t2_gamma_c, double* fid, double* rho_out, rbq_stats* stats);
 
+/* ---- iLQR backward pass -------------------------------------------------------------------------------
+ * Altro.jl 0.2.0 `backwardpass!` (external: SchusterLab/rbqoc-stable fork, Manifest.toml:26-32) for B independent problems
+ * of N knots, state dimension n <= 64, control dimension m <= 4, one thread block per problem.  It consumes the Jacobian
+ * blocks exactly as rbq_jacobians(_dev) writes them, so they never leave the device between the expansion and the pass.
+ *   AB  [B][N-1][n*(n+m)]  column-major n x (n+m) blocks [A_k B_k]
+ *   Exx [B][N][n*n]        cost Hessian blocks, column-major, symmetric (the lower triangle is read); knot N-1 = terminal
+ *   Ex  [B][N][n]          cost gradients
+ *   Euu [B][N-1][m*m], Eux [B][N-1][m*n] (column-major m x n), Eu [B][N-1][m]
+ *   rho, reg_type          Quu_reg = Quu + rho I (RBQ_REG_CONTROL) or Quu + rho B'B, Qux_reg = Qux + rho B'A (RBQ_REG_STATE)
+ *   K   [B][N-1][m*n] (column-major m x n), d [B][N-1][m], dV [B][2] = (sum d'Qu, sum d'Quu d / 2)
+ *   fail[B]                -1, or the 0-based knot at which Quu_reg was not positive definite (the pass stops there, as the
+ *                          reference does before it raises rho and restarts; gains of later knots are valid, earlier not) */
+#define RBQ_REG_CONTROL 0
+#define RBQ_REG_STATE 1
+int rbq_backward_pass_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
+                          const double* d_Ex, const double* d_Euu, const double* d_Eux, const double* d_Eu, double rho,
+                          int reg_type, double* d_K, double* d_d, double* d_dV, int64_t* d_fail);
+int rbq_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* AB, const double* Exx, const double* Ex,
+                      const double* Euu, const double* Eux, const double* Eu, double rho, int reg_type, double* K, double* d,
+                      double* dV, int64_t* fail);
+
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);
 

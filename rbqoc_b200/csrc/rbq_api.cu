@@ -925,6 +925,60 @@ int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs,
     return RBQ_OK;
 }
 
+// ---- iLQR backward pass ------------------------------------------------------------------------------------------------
+static int check_bp(rbq_handle* h, const char* who, int n, int m, int64_t N, int64_t B, int reg_type) {
+    if (n < 1 || n > 64 || m < 1 || m > 4 || N < 1 || B < 0) return fail(h, RBQ_E_SIZE, "%s: n=%d m=%d N=%lld B=%lld (n <= 64, m <= 4)", who, n, m, (long long)N, (long long)B);
+    if (reg_type != RBQ_REG_CONTROL && reg_type != RBQ_REG_STATE) return fail(h, RBQ_E_MODEL, "%s: unknown reg_type %d", who, reg_type);
+    return 0;
+}
+int rbq_backward_pass_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
+                          const double* d_Ex, const double* d_Euu, const double* d_Eux, const double* d_Eu, double rho,
+                          int reg_type, double* d_K, double* d_d, double* d_dV, int64_t* d_fail) {
+    ENTER(h);
+    CKL(check_bp(h, "rbq_backward_pass_dev", n, m, N, B, reg_type));
+    if (B == 0) return RBQ_OK;
+    if (!d_Exx || !d_Ex || !d_dV || !d_fail || (N > 1 && (!d_AB || !d_Euu || !d_Eux || !d_Eu || !d_K || !d_d)))
+        return fail(h, RBQ_E_NULL, "rbq_backward_pass_dev: null pointer");
+    CKL(launch_backward_pass(h, n, m, N, B, d_AB, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, rho, reg_type, d_K, d_d, d_dV, (long long*)d_fail));
+    return RBQ_OK;
+}
+int rbq_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* AB, const double* Exx, const double* Ex,
+                      const double* Euu, const double* Eux, const double* Eu, double rho, int reg_type, double* K, double* d,
+                      double* dV, int64_t* failed) {
+    ENTER(h);
+    CKL(check_bp(h, "rbq_backward_pass", n, m, N, B, reg_type));
+    if (B == 0) return RBQ_OK;
+    if (!Exx || !Ex || !dV || !failed || (N > 1 && (!AB || !Euu || !Eux || !Eu || !K || !d)))
+        return fail(h, RBQ_E_NULL, "rbq_backward_pass: null pointer");
+    const size_t nm = (size_t)n + m, K1 = (size_t)(N - 1) * B, KN = (size_t)N * B;
+    const size_t bAB = sizeof(double) * K1 * n * nm, bExx = sizeof(double) * KN * n * n, bEx = sizeof(double) * KN * n;
+    const size_t bEuu = sizeof(double) * K1 * m * m, bEux = sizeof(double) * K1 * m * n, bEu = sizeof(double) * K1 * m;
+    void *dAB, *dExx, *dEx, *dEuu, *dEux, *dEu, *dK, *dd, *dsm;
+    CKL(dev_buf(h, B_IN0, bAB, &dAB)); CKL(dev_buf(h, B_IN1, bExx, &dExx)); CKL(dev_buf(h, B_IN2, bEx, &dEx));
+    CKL(dev_buf(h, B_IN3, bEuu, &dEuu)); CKL(dev_buf(h, B_IN4, bEux, &dEux)); CKL(dev_buf(h, B_IN5, bEu, &dEu));
+    CKL(dev_buf(h, B_OUT0, bEux, &dK)); CKL(dev_buf(h, B_OUT1, bEu, &dd));
+    CKL(dev_buf(h, B_SCALARS, 256 + 24 * (size_t)B, &dsm));
+    double* ddV = (double*)dsm + 32; long long* dfail = (long long*)((double*)dsm + 32 + 2 * B);
+    if (N > 1) {
+        CK(cudaMemcpyAsync(dAB, AB, bAB, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dEuu, Euu, bEuu, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dEux, Eux, bEux, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dEu, Eu, bEu, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(dExx, Exx, bExx, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dEx, Ex, bEx, cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_backward_pass(h, n, m, N, B, (double*)dAB, (double*)dExx, (double*)dEx, (double*)dEuu, (double*)dEux, (double*)dEu, rho,
+                             reg_type, (double*)dK, (double*)dd, ddV, dfail));
+    if (N > 1) {
+        CK(cudaMemcpyAsync(K, dK, bEux, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(d, dd, bEu, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaMemcpyAsync(dV, ddV, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(failed, dfail, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
 // ---- FP64 roofline denominator -------------------------------------------------------------------------------------------
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops) {
     ENTER(h);

@@ -109,6 +109,9 @@ int launch_gate_error(rbq_handle* h, int64_t K, const double* d_s1, int64_t st1,
                       double* d_grad, double* d_hess);
 int launch_sampling_cost(rbq_handle* h, int64_t K, const double* d_X, const double* d_U, const double* Qdiag, double R,
                          const double* xf, const double* targets, const double* q_ss, double* d_J, double* d_gx, double* d_gu);
+int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
+                         const double* d_Ex, const double* d_Euu, const double* d_Eux, const double* d_Eu, double rho,
+                         int reg_type, double* d_K, double* d_d, double* d_dV, long long* d_fail);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_t, const double* d_dt, double* d_AB);
 

@@ -1,0 +1,376 @@
+// rbq_riccati.cu — iLQR backward pass (time-varying LQR Riccati recursion) for batches of problems, one CTA per problem.
+//
+// Replaces Altro.jl 0.2.0 `backwardpass!` (external, SchusterLab/rbqoc-stable fork, Manifest.toml:26-32; un-vendored, restated
+// from its published algorithm, see oracle/riccati.py).  It consumes the knot-point Jacobians exactly as rbq_jacobians
+// leaves them in HBM (column-major n x (n+m) blocks), so an ALTRO iteration never moves them over PCIe:
+//
+//   S_N = Exx_N, s_N = Ex_N;  for k = N-1 .. 1:
+//     Qxx = Exx + A'SA   Quu = Euu + B'SB   Qux = Eux + B'SA   Qx = Ex + A's   Qu = Eu + B's
+//     Quu_reg = Quu + rho I (control)  |  Quu + rho B'B, Qux_reg = Qux + rho B'A (state)
+//     K = -Quu_reg^-1 Qux_reg   d = -Quu_reg^-1 Qu
+//     S = sym(Qxx + K'Quu K + K'Qux + Qux'K)   s = Qx + K'Quu d + K'Qu + Qux'd   dV += (d'Qu, d'Quu d / 2)
+//
+// Per knot the work is two dense products, T = S [A B] (n x n x (n+m)) and G = [A B]' T (lower tiles only), on 4x4
+// register tiles out of shared memory; everything else is O(n^2 m^2).  FP64 pipe bound for n >= ~40, latency bound below.
+// The next knot's Jacobian block is fetched with cp.async while the gains and the value update of this knot are computed.
+#include "rbq_internal.h"
+
+#include "rbq_math.cuh"
+
+namespace rbq {
+
+constexpr int BP_THREADS = 256;
+constexpr int BP_MAX_M = 4;
+
+RBQ_DEV void cp_async8(double* smem_dst, const double* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+RBQ_DEV void cp_async16(double* smem_dst, const double* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+RBQ_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+RBQ_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// phase timing for tuning (make EXTRA=-DRBQ_BP_PROFILE; read with rbq_debug_bp_prof): cycles of thread 0 between barriers
+#ifdef RBQ_BP_PROFILE
+__device__ long long g_bp_prof[16];
+#define BP_PROF(i) if (tid == 0) { long long c_ = clock64(); g_bp_prof[i] += c_ - tprev; tprev = c_; }
+#else
+#define BP_PROF(i)
+#endif
+struct BackwardArgs {
+    int n, m;
+    int64_t N, B;
+    const double* AB; const double* Exx; const double* Ex; const double* Euu; const double* Eux; const double* Eu;
+    double rho; int reg_type;
+    double* K; double* d; double* dV; long long* fail;
+};
+
+// Shared-memory layout (doubles), all column-major.  Rows are padded with zeros to a multiple of 8 (the DMMA tile), the
+// contraction length to a multiple of 4; the leading dimensions ld = n8 + 4 and ldg = q8 + 4 are = 4 (mod 8), which makes every
+// fragment load below conflict-free (the four 32-byte pieces a half-warp reads fall into different quarters of the bank window):
+//   S[ld*n4] sv[n8] AB[ld*q8] T[ld*q8] G[ldg*q8] Kk[4*n8] QuuK[4*n8] dk[4]      (q8 = n+m+1 rounded up: one spare column)
+RBQ_DEV int up4(int x) { return (x + 3) & ~3; }
+RBQ_DEV int up8(int x) { return (x + 7) & ~7; }
+
+// FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8).  Fragments (PTX ISA, mma.m8n8k4 .f64): lane l holds
+// A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)] and C[l/4][2(l%4)+1].
+RBQ_DEV void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+constexpr int BP_MAX_TILES = 9;        // 8-row tiles of a column strip: (64 + 4 + 7) / 8
+
+__global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const BackwardArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = a.n, m = a.m, nm = n + m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = BP_THREADS / 32;
+    const int n4 = up4(n), n8 = up8(n), q8 = up8(nm + 1), ld = n8 + 4, ldg = q8 + 4;
+    const int cs = nm;                 // spare column: G(:, cs) = [A B]' s + e, i.e. the gradient g rides in the second product
+    const int64_t N = a.N, b = blockIdx.x;
+    double* S = sm;                    // S(r, kk) at kk * ld + r   (symmetric)
+    double* sv = S + ld * n4;
+    double* AB = sv + n8;              // [A B](kk, c) at c * ld + kk
+    double* T = AB + ld * q8;          // T(r, c) at c * ld + r; scratch of the value update
+    double* G = T + ld * q8;           // G(i, j) at j * ldg + i
+    double* g = G + cs * ldg;          // Qx, Qu: column cs of G
+    double* Kk = G + ldg * q8;         // K(p, j) at j * m + p
+    double* QuuK = Kk + BP_MAX_M * n8;
+    double* dk = QuuK + BP_MAX_M * n8;
+    __shared__ double dv_s[2];
+
+    const double* ABg = a.AB + b * (N - 1) * (int64_t)(n * nm);
+    const double* Exxg = a.Exx + b * N * (int64_t)(n * n);
+    const double* Exg = a.Ex + b * N * (int64_t)n;
+    const double* Euug = a.Euu + b * (N - 1) * (int64_t)(m * m);
+    const double* Euxg = a.Eux + b * (N - 1) * (int64_t)(m * n);
+    const double* Eug = a.Eu + b * (N - 1) * (int64_t)m;
+    double* Kg = a.K + b * (N - 1) * (int64_t)(m * n);
+    double* dg = a.d + b * (N - 1) * (int64_t)m;
+
+    // zero everything once (the padding is never written again), then the terminal value function
+    const int total = ld * n4 + n8 + 2 * ld * q8 + ldg * q8;
+    for (int i = tid; i < total; i += BP_THREADS) sm[i] = 0.0;
+    if (tid == 0) { dv_s[0] = 0.0; dv_s[1] = 0.0; }
+    __syncthreads();
+    for (int j = wid; j < n; j += NW)
+        for (int i = lane; i < n; i += 32)
+            S[j * ld + i] = Exxg[(N - 1) * (int64_t)(n * n) + (i >= j ? j * n + i : i * n + j)];   // lower triangle, mirrored
+    for (int i = tid; i < n; i += BP_THREADS) sv[i] = Exg[(N - 1) * (int64_t)n + i];
+    auto stage_jacobian = [&](int64_t k) {
+        const double* src = ABg + k * (int64_t)(n * nm);
+        if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
+            for (int j = wid; j < nm; j += NW)
+                for (int i = 2 * lane; i < n; i += 64) cp_async16(AB + j * ld + i, src + j * n + i);
+        } else {
+            for (int j = wid; j < nm; j += NW)
+                for (int i = lane; i < n; i += 32) cp_async8(AB + j * ld + i, src + j * n + i);
+        }
+        cp_async_commit();
+    };
+    // cost blocks of knot k -> G (both triangles from the lower one) and g, in flight behind the first product
+    auto stage_cost = [&](int64_t k) {
+        const double* Exxk = Exxg + k * (int64_t)(n * n);
+        const double* Euuk = Euug + k * (int64_t)(m * m);
+        const double* Euxk = Euxg + k * (int64_t)(m * n);
+        for (int j = wid; j < nm; j += NW)
+            for (int i = lane; i < nm; i += 32) {
+                const int lo = i < j ? i : j, hi = i < j ? j : i;                     // (hi, lo) in the lower triangle
+                const double* src = hi < n ? Exxk + lo * n + hi : (lo < n ? Euxk + lo * m + (hi - n) : Euuk + (lo - n) * m + (hi - n));
+                cp_async8(G + j * ldg + i, src);
+            }
+        for (int i = tid; i < nm; i += BP_THREADS) cp_async8(g + i, i < n ? Exg + k * (int64_t)n + i : Eug + k * (int64_t)m + (i - n));
+        cp_async_commit();
+    };
+    if (N > 1) stage_jacobian(N - 2);
+
+    const int rtiles = n8 / 8, ctiles = q8 / 8, ksteps = n4 / 4;
+    const int fr = lane >> 2, fc = lane & 3;          // fragment coordinates of this lane
+    const int ld2 = n8 + 1;                           // odd leading dimension of the value-update scratch: conflict-free transposed reads
+    long long bad = -1;
+#ifdef RBQ_BP_PROFILE
+    long long tprev = clock64();
+#endif
+    for (int64_t k = N - 2; k >= 0; --k) {
+        cp_async_wait_all();
+        __syncthreads();                                           // AB_k, S, sv visible; G and g are free again
+        BP_PROF(0)
+        stage_cost(k);
+        // ---- T = S [A B]: warp -> one 8-column strip, all row tiles; A fragments from S (symmetric), B fragments from [A B] ----
+        for (int ct = wid; ct < ctiles; ct += NW) {
+            double acc[BP_MAX_TILES - 1][2];
+#pragma unroll
+            for (int t = 0; t < BP_MAX_TILES - 1; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+            const double* bp = AB + (8 * ct + fr) * ld + fc;
+            const double* ap = S + fc * ld + fr;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const double bf = bp[4 * ks];
+#pragma unroll
+                for (int t = 0; t < BP_MAX_TILES - 1; ++t)
+                    if (t < rtiles) dmma884(acc[t][0], acc[t][1], ap[4 * ks * ld + 8 * t], bf);
+            }
+#pragma unroll
+            for (int t = 0; t < BP_MAX_TILES - 1; ++t)
+                if (t < rtiles) {
+                    T[(8 * ct + 2 * fc) * ld + 8 * t + fr] = acc[t][0];
+                    T[(8 * ct + 2 * fc + 1) * ld + 8 * t + fr] = acc[t][1];
+                }
+        }
+        cp_async_wait_all();                                       // this thread's share of the cost blocks has landed ...
+        __syncthreads();                                           // ... and everybody's, together with T
+        BP_PROF(1)
+        // ---- G += [A B]' T: warp -> one 8-column strip of G; A fragments are columns of [A B] read along the contraction ----
+        for (int jt = wid; jt < ctiles; jt += NW) {
+            double acc[BP_MAX_TILES][2];
+#pragma unroll
+            for (int t = 0; t < BP_MAX_TILES; ++t)
+                if (t < ctiles) {
+                    acc[t][0] = G[(8 * jt + 2 * fc) * ldg + 8 * t + fr];
+                    acc[t][1] = G[(8 * jt + 2 * fc + 1) * ldg + 8 * t + fr];
+                }
+            const double* bp = (8 * jt + fr == cs) ? sv + fc : T + (8 * jt + fr) * ld + fc;   // column cs of the right factor is s
+            const double* ap = AB + fr * ld + fc;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const double bf = bp[4 * ks];
+#pragma unroll
+                for (int t = 0; t < BP_MAX_TILES; ++t)
+                    if (t < ctiles) dmma884(acc[t][0], acc[t][1], ap[8 * t * ld + 4 * ks], bf);
+            }
+#pragma unroll
+            for (int t = 0; t < BP_MAX_TILES; ++t)
+                if (t < ctiles) {
+                    G[(8 * jt + 2 * fc) * ldg + 8 * t + fr] = acc[t][0];
+                    G[(8 * jt + 2 * fc + 1) * ldg + 8 * t + fr] = acc[t][1];
+                }
+        }
+        BP_PROF(2)
+        BP_PROF(3)
+        __syncthreads();
+        BP_PROF(4)
+        // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
+        bool ok = true;
+        if (tid <= n) {
+            const int j = tid;
+            double L[BP_MAX_M][BP_MAX_M], rhs[BP_MAX_M];
+#pragma unroll
+            for (int p = 0; p < BP_MAX_M; ++p)
+#pragma unroll
+                for (int q = 0; q < BP_MAX_M; ++q) {
+                    double v = 0.0;
+                    if (p < m && q <= p) {
+                        v = G[(n + q) * ldg + (n + p)];
+                        if (a.reg_type == RBQ_REG_STATE) {
+                            double bb = 0.0;
+                            for (int r = 0; r < n; ++r) bb = fma(AB[(n + p) * ld + r], AB[(n + q) * ld + r], bb);
+                            v = fma(a.rho, bb, v);
+                        } else if (p == q) v += a.rho;
+                    }
+                    L[p][q] = v;
+                }
+#pragma unroll
+            for (int c = 0; c < BP_MAX_M; ++c) {                                   // in-place Cholesky (lower), reciprocal pivots
+                if (c >= m) continue;
+                double dj = L[c][c];
+#pragma unroll
+                for (int r = 0; r < BP_MAX_M; ++r) if (r < c) dj -= L[c][r] * L[c][r];
+                if (!(dj > 0.0)) ok = false;                                        // also catches NaN
+                L[c][c] = 1.0 / sqrt(dj);
+#pragma unroll
+                for (int i = 0; i < BP_MAX_M; ++i) {
+                    if (i <= c || i >= m) continue;
+                    double v = L[i][c];
+#pragma unroll
+                    for (int r = 0; r < BP_MAX_M; ++r) if (r < c) v -= L[i][r] * L[c][r];
+                    L[i][c] = v * L[c][c];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < BP_MAX_M; ++p) {
+                double v = 0.0;
+                if (p < m) {
+                    v = j < n ? G[(n + p) * ldg + j] : g[n + p];     // Qxu(j, p): the coalesced half of the symmetric G
+                    if (j < n && a.reg_type == RBQ_REG_STATE) {
+                        double ba = 0.0;
+                        for (int r = 0; r < n; ++r) ba = fma(AB[(n + p) * ld + r], AB[j * ld + r], ba);
+                        v = fma(a.rho, ba, v);
+                    }
+                }
+                rhs[p] = v;
+            }
+#pragma unroll
+            for (int p = 0; p < BP_MAX_M; ++p) {                                  // L y = rhs
+                if (p >= m) continue;
+                double v = rhs[p];
+#pragma unroll
+                for (int r = 0; r < BP_MAX_M; ++r) if (r < p) v -= L[p][r] * rhs[r];
+                rhs[p] = v * L[p][p];
+            }
+#pragma unroll
+            for (int p = BP_MAX_M - 1; p >= 0; --p) {                             // L' x = y
+                if (p >= m) continue;
+                double v = rhs[p];
+#pragma unroll
+                for (int r = 0; r < BP_MAX_M; ++r) if (r > p && r < m) v -= L[r][p] * rhs[r];
+                rhs[p] = v * L[p][p];
+            }
+            if (ok) {
+#pragma unroll
+                for (int p = 0; p < BP_MAX_M; ++p) {
+                    if (p >= m) continue;
+                    if (j < n) { Kk[j * m + p] = -rhs[p]; Kg[k * (int64_t)(m * n) + j * m + p] = -rhs[p]; }
+                    else { dk[p] = -rhs[p]; dg[k * (int64_t)m + p] = -rhs[p]; }
+                }
+                if (j < n) {                                                       // Quu K (unregularised Quu), column j
+#pragma unroll
+                    for (int p = 0; p < BP_MAX_M; ++p) {
+                        if (p >= m) continue;
+                        double v = 0.0;
+#pragma unroll
+                        for (int q = 0; q < BP_MAX_M; ++q) if (q < m) v = fma(G[(n + q) * ldg + (n + p)], -rhs[q], v);
+                        QuuK[j * m + p] = v;
+                    }
+                }
+            }
+        }
+        BP_PROF(5)
+        if (__syncthreads_or(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
+        BP_PROF(6)
+        // the Jacobian block is no longer needed: fetch the next one behind the value update
+        if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
+        BP_PROF(8)
+        // ---- value update: V = Qxx + sym(K'Quu K + K'Qux + Qux'K) into the scratch, then S = (V + V')/2 ----
+        // G is symmetric up to rounding (both halves are computed): the gain terms are symmetrised exactly here, Qxx by
+        // averaging its two computed halves below.  Lane -> row i (its K, Quu K and Qux entries stay in registers), the
+        // warp walks the columns j (whose entries are warp-uniform broadcasts).
+        for (int i = lane; i < n; i += 32) {
+            double ki[BP_MAX_M], qi[BP_MAX_M], hi[BP_MAX_M];
+#pragma unroll
+            for (int p = 0; p < BP_MAX_M; ++p) {
+                const bool on = p < m;
+                ki[p] = on ? Kk[i * m + p] : 0.0; qi[p] = on ? 0.5 * QuuK[i * m + p] : 0.0; hi[p] = on ? G[(n + p) * ldg + i] : 0.0;
+            }
+#pragma unroll 2
+            for (int j = wid; j < n; j += NW) {
+                double v = G[j * ldg + i];
+#pragma unroll
+                for (int p = 0; p < BP_MAX_M; ++p) {
+                    if (p >= m) continue;
+                    const double kj = Kk[j * m + p], hj = G[(n + p) * ldg + j];
+                    v = fma(ki[p], fma(0.5, QuuK[j * m + p], hj), v);          // K'(Quu K)/2 + K'Qux
+                    v = fma(kj, qi[p] + hi[p], v);                             // (Quu K)'K/2 + Qux'K
+                }
+                T[j * ld2 + i] = v;
+            }
+        }
+        BP_PROF(9)
+        if (tid >= BP_THREADS - 64 && tid - (BP_THREADS - 64) < n) {
+            const int i = tid - (BP_THREADS - 64);
+            double v = g[i];
+            for (int p = 0; p < m; ++p) {
+                double qd = g[n + p];                                      // Qu + Quu d
+                for (int q = 0; q < m; ++q) qd = fma(G[(n + q) * ldg + (n + p)], dk[q], qd);
+                v = fma(Kk[i * m + p], qd, v);
+                v = fma(G[(n + p) * ldg + i], dk[p], v);                   // Qux' d
+            }
+            sv[i] = v;                                                    // sv is not read again before the next knot
+        }
+        if (tid == 32) {
+            double d0 = 0.0, d1 = 0.0;
+            for (int p = 0; p < m; ++p) {
+                d0 = fma(dk[p], g[n + p], d0);
+                double qd = 0.0;
+                for (int q = 0; q < m; ++q) qd = fma(G[(n + q) * ldg + (n + p)], dk[q], qd);
+                d1 = fma(dk[p], qd, d1);
+            }
+            dv_s[0] += d0; dv_s[1] += 0.5 * d1;
+        }
+        BP_PROF(10)
+        __syncthreads();
+        BP_PROF(11)
+        // 16 x 16 blocks: the transposed read stays inside 16 columns of the odd-stride scratch
+        for (int blk = wid; blk < ((n + 15) / 16) * ((n + 15) / 16); blk += NW) {
+            const int nb = (n + 15) / 16, bi = (blk % nb) * 16, bj = (blk / nb) * 16;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const int i = bi + (lane & 15), j = bj + 2 * h + (lane >> 4);
+                if (i < n && j < n) S[j * ld + i] = 0.5 * (T[j * ld2 + i] + T[i * ld2 + j]);
+            }
+        }
+        BP_PROF(7)
+        // the barrier at the top of the loop orders these writes against the next knot's reads
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid == 0) {
+        a.dV[2 * b] = dv_s[0]; a.dV[2 * b + 1] = dv_s[1];
+        a.fail[b] = bad;
+    }
+}
+
+size_t backward_pass_smem(int n, int m) {
+    const size_t n4 = (size_t)((n + 3) & ~3), n8 = (size_t)((n + 7) & ~7), q8 = (size_t)((n + m + 8) & ~7), ld = n8 + 4, ldg = q8 + 4;
+    return sizeof(double) * (ld * n4 + n8 + 2 * ld * q8 + ldg * q8 + 2 * BP_MAX_M * n8 + BP_MAX_M);
+}
+
+int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
+                         const double* d_Ex, const double* d_Euu, const double* d_Eux, const double* d_Eu, double rho,
+                         int reg_type, double* d_K, double* d_d, double* d_dV, long long* d_fail) {
+    const size_t smem = backward_pass_smem(n, m);
+    if (smem > 227 * 1024) return RBQ_E_SIZE;
+    cudaError_t e = cudaFuncSetAttribute(backward_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    BackwardArgs a{n, m, N, B, d_AB, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, rho, reg_type, d_K, d_d, d_dV, d_fail};
+    backward_pass_kernel<<<(unsigned)B, BP_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rbq
+#ifdef RBQ_BP_PROFILE
+extern "C" int rbq_debug_bp_prof(long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, rbq::g_bp_prof, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(rbq::g_bp_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

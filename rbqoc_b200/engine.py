@@ -342,6 +342,34 @@ class Engine:
                                                  _ptr(out), C.byref(st)), "rbq_lindblad_segments")
         return fid, out.reshape(S, 2, 2).transpose(0, 2, 1).copy(), st
 
+    # ---- iLQR backward pass (Altro backwardpass!, external) --------------------------------------------------------------
+    def backward_pass(self, AB, Exx, Ex, Euu, Eux, Eu, rho=0.0, reg_type=_lib.REG_CONTROL):
+        """AB (B, N-1, n, n+m) or (N-1, n, n+m) = [A_k B_k] as `jacobians` returns it (a view of the column-major blocks: no
+        copy is made); Exx (.., N, n, n) symmetric, Ex (.., N, n), Euu (.., N-1, m, m), Eux (.., N-1, m, n), Eu (.., N-1, m).
+        Returns K (.., N-1, m, n), d (.., N-1, m), dV (.., 2), fail (-1 or the knot where Quu_reg was not positive definite)."""
+        AB, Exx, Ex, Euu, Eux, Eu = (np.asarray(x, dtype=np.float64) for x in (AB, Exx, Ex, Euu, Eux, Eu))
+        single = Ex.ndim == 2
+        if single:
+            AB, Exx, Ex, Euu, Eux, Eu = (x[None] for x in (AB, Exx, Ex, Euu, Eux, Eu))
+        B, N, n = Ex.shape
+        m = Eu.shape[2]
+        if AB.shape != (B, N - 1, n, n + m) or Exx.shape != (B, N, n, n) or Euu.shape != (B, N - 1, m, m) or \
+                Eux.shape != (B, N - 1, m, n) or Eu.shape != (B, N - 1, m):
+            raise ValueError("inconsistent shapes")
+        col = lambda x: np.ascontiguousarray(np.swapaxes(x, -1, -2))          # column-major blocks for the ABI
+        ABc, Exxc, Euuc, Euxc = col(AB), col(Exx), col(Euu), col(Eux)
+        Ex, Eu = np.ascontiguousarray(Ex), np.ascontiguousarray(Eu)
+        K = np.empty((B, N - 1, n, m)); d = np.empty((B, N - 1, m)); dV = np.empty((B, 2)); fail = np.empty(B, dtype=np.int64)
+        self._ck(self._lib.rbq_backward_pass(self._h, n, m, N, B, _ptr(ABc), _ptr(Exxc), _ptr(Ex), _ptr(Euuc), _ptr(Euxc), _ptr(Eu),
+                                             float(rho), int(reg_type), _ptr(K), _ptr(d), _ptr(dV), _ptr(fail)), "rbq_backward_pass")
+        K = np.swapaxes(K, -1, -2)
+        return (K[0], d[0], dV[0], int(fail[0])) if single else (K, d, dV, fail)
+
+    def backward_pass_dev(self, n, m, N, B, d_AB, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, rho, reg_type, d_K, d_d, d_dV, d_fail):
+        self._ck(self._lib.rbq_backward_pass_dev(self._h, int(n), int(m), int(N), int(B), _ptr(d_AB), _ptr(d_Exx), _ptr(d_Ex),
+                                                 _ptr(d_Euu), _ptr(d_Eux), _ptr(d_Eu), float(rho), int(reg_type), _ptr(d_K),
+                                                 _ptr(d_d), _ptr(d_dV), _ptr(d_fail)), "rbq_backward_pass_dev")
+
     # ---- device-pointer forms (torch CUDA tensors; asynchronous on the handle's stream) ------------------------
     def stats_reset_dev(self, d_stats):
         self._ck(self._lib.rbq_stats_reset_dev(self._h, _ptr(d_stats)), "rbq_stats_reset_dev")

@@ -243,3 +243,50 @@ def test_xpiby2da_segment_list_and_oracle(orc):
     assert np.max(np.abs(fid0 - 1.0)) < 1e-12
     with pytest.raises(ValueError):
         orc.mc_noise_segments(amps, durs, nidx, spin.GateType.xpiby2, 1, FQ, np.zeros((1, 100)), z["psi0"][:1])
+
+
+def _lq_problem(rng, N, n, m):
+    """Random time-varying LQ problem: x' = A_k x + B_k u, cost sum (x'Qx/2 + q'x + u'Ru/2 + r'u + u'Hx)."""
+    A = 0.9 * np.eye(n) + 0.1 * rng.standard_normal((N - 1, n, n))
+    Bm = rng.standard_normal((N - 1, n, m))
+    AB = np.concatenate([A, Bm], axis=2)                                  # [A_k B_k]
+    Q = rng.standard_normal((N, n, n)); Q = Q @ Q.transpose(0, 2, 1) / n + 0.1 * np.eye(n)
+    R = rng.standard_normal((N - 1, m, m)); R = R @ R.transpose(0, 2, 1) + np.eye(m)
+    H = 0.05 * rng.standard_normal((N - 1, m, n))
+    q = rng.standard_normal((N, n)); r = rng.standard_normal((N - 1, m))
+    return A, Bm, AB, Q, q, R, H, H, r
+
+
+def test_riccati_oracle_solves_lq_problems_in_one_pass():
+    """Defining property of the recursion (Altro backwardpass!): on a linear-quadratic problem the gains of one backward
+    pass, rolled forward from x0 with u = K x + d, give the global optimum: the gradient of the total cost with respect to
+    every control vanishes, and the predicted decrease dV matches the realised one."""
+    from oracle import riccati
+
+    rng = np.random.default_rng(5)
+    N, n, m = 12, 5, 2
+    A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
+    K, d, dV, fail = riccati.backward_pass(AB, Q, q, R, Eux, r)
+    assert fail == -1
+
+    def cost(U, x0):
+        x, J = x0, 0.0
+        for k in range(N - 1):
+            J += 0.5 * x @ Q[k] @ x + q[k] @ x + 0.5 * U[k] @ R[k] @ U[k] + r[k] @ U[k] + U[k] @ H[k] @ x
+            x = A[k] @ x + Bm[k] @ U[k]
+        return J + 0.5 * x @ Q[N - 1] @ x + q[N - 1] @ x
+
+    x0 = np.zeros(n)                       # expansion point: (x, u) = 0, so the E blocks ARE the cost derivatives there
+    x, U = x0, np.zeros((N - 1, m))
+    for k in range(N - 1):
+        U[k] = K[k] @ x + d[k]
+        x = A[k] @ x + Bm[k] @ U[k]
+    h = 1e-6
+    grad = np.array([[(cost(U + h * np.eye(1, (N - 1) * m, i).reshape(N - 1, m), x0) -
+                       cost(U - h * np.eye(1, (N - 1) * m, i).reshape(N - 1, m), x0)) / (2 * h)] for i in range((N - 1) * m)])
+    assert np.max(np.abs(grad)) < 1e-7
+    assert cost(U, x0) - cost(np.zeros((N - 1, m)), x0) == pytest.approx(dV[0] + dV[1], rel=1e-10)
+    # an indefinite Quu stops the pass at that knot; control regularisation repairs it
+    R2 = R.copy(); R2[7] = -50.0 * np.eye(m)
+    assert riccati.backward_pass(AB, Q, q, R2, Eux, r)[3] == 7
+    assert riccati.backward_pass(AB, Q, q, R2, Eux, r, rho=100.0)[3] == -1

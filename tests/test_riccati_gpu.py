@@ -1,0 +1,69 @@
+"""GPU parity: the iLQR backward pass (rbq_backward_pass) against the numpy restatement of Altro's backwardpass!
+(oracle/riccati.py).  Tolerance: relative 1e-10 on gains and value decrease (the recursion multiplies ~N products of
+n x n matrices; both sides are plain FP64 sums in different orders)."""
+import numpy as np
+import pytest
+
+import rbqoc_b200 as rbq
+from rbqoc_b200 import spin
+from test_oracle_cpu import _lq_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("n,m,N", [(11, 1, 301), (12, 2, 64), (43, 1, 181), (56, 1, 120), (58, 1, 40), (3, 4, 17), (64, 2, 9), (5, 1, 1)])
+@pytest.mark.parametrize("reg", [rbq.REG_CONTROL, rbq.REG_STATE], ids=["control_reg", "state_reg"])
+def test_backward_pass_matches_oracle(engine, n, m, N, reg):
+    from oracle import riccati
+
+    rng = np.random.default_rng(n * 1000 + m * 10 + N)
+    A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
+    rho = 0.37
+    K, d, dV, fail = engine.backward_pass(AB, Q, q, R, Eux, r, rho=rho, reg_type=reg)
+    Kr, dr, dVr, failr = riccati.backward_pass(AB, Q, q, R, Eux, r, rho=rho, reg_type=reg)
+    assert fail == failr == -1
+    if N > 1:
+        assert _rel(K, Kr) < 1e-10 and _rel(d, dr) < 1e-10
+    assert np.allclose(dV, dVr, rtol=1e-10, atol=1e-300)
+
+
+def test_backward_pass_batch_failure_flags_and_jacobian_layout(engine):
+    """A batch where one problem has an indefinite Quu: its flag names the knot, the others are unaffected.  Then the real
+    thing: Jacobians of a spin13 rollout straight from rbq_jacobians into the pass (same memory layout, no transpose)."""
+    from oracle import riccati
+
+    rng = np.random.default_rng(3)
+    N, n, m, B = 33, 11, 1, 5
+    probs = [_lq_problem(rng, N, n, m) for _ in range(B)]
+    st = lambda i: np.stack([p[i] for p in probs])
+    AB, Q, q, R, Eux, r = st(2), st(3), st(4), st(5), st(6), st(8)
+    R[3, 20] = -1e3
+    K, d, dV, fail = engine.backward_pass(AB, Q, q, R, Eux, r)
+    assert list(fail) == [-1, -1, -1, 20, -1]
+    for b in (0, 1, 2, 4):
+        Kr, dr, dVr, _ = riccati.backward_pass(AB[b], Q[b], q[b], R[b], Eux[b], r[b])
+        assert _rel(K[b], Kr) < 1e-10 and _rel(d[b], dr) < 1e-10 and np.allclose(dV[b], dVr, rtol=1e-10)
+    Kr, dr, _, failr = riccati.backward_pass(AB[3], Q[3], q[3], R[3], Eux[3], r[3])
+    assert failr == 20 and _rel(K[3, 21:], Kr[21:]) < 1e-10          # gains after the failing knot were already final
+    # spin13: LQR objective of spin13.jl:128-135 (Q = diag(qs), R = qs[5], Qf = N Q) expanded about a rollout
+    model = spin.Spin13Model()
+    Nk = 101
+    U = 1e-2 * rng.standard_normal((Nk - 1, 1))
+    X = spin.rollout(model, spin.spin13_x0(), U, 0.1, engine=engine)
+    ABj = spin.dynamics_expansion(model, X, U, 0.1, engine=engine)
+    xf = np.zeros(11); xf[:8] = [1 / np.sqrt(2), 0, -1 / np.sqrt(2), 0, 0, 1 / np.sqrt(2), 0, 1 / np.sqrt(2)]
+    Qd = np.array([1.0] * 8 + [1.0, 1.0, 0.1])
+    Exx = np.tile(np.diag(Qd), (Nk, 1, 1)); Exx[-1] *= Nk
+    Ex = (X - xf) * Qd; Ex[-1] *= Nk
+    Euu = np.full((Nk - 1, 1, 1), 0.1); Eux0 = np.zeros((Nk - 1, 1, 11)); Eu = 0.1 * U
+    K, d, dV, fail = engine.backward_pass(ABj, Exx, Ex, Euu, Eux0, Eu, rho=1e-3)
+    Kr, dr, dVr, failr = riccati.backward_pass(ABj, Exx, Ex, Euu, Eux0, Eu, rho=1e-3)
+    assert fail == failr == -1 and _rel(K, Kr) < 1e-9 and _rel(d, dr) < 1e-9 and np.allclose(dV, dVr, rtol=1e-9)
+    assert dV[0] < 0                                                  # a descent direction
+    with pytest.raises(Exception):
+        engine.backward_pass(np.zeros((3, 65, 70)), np.zeros((4, 65, 65)), np.zeros((4, 65)), np.zeros((3, 5, 5)), np.zeros((3, 5, 65)),
+                             np.zeros((3, 5)))
