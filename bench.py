@@ -250,8 +250,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
         import torch.distributed as tdist
+
+        # one process per GPU: keep the process (and the pinned buffers it first-touches) on the GPU's own NUMA node
+        if os.environ.get("RBQ_NO_NUMA_BIND", "0") in ("", "0"):
+            numa_cpus = rdist.bind_to_gpu_numa_node(local)
 
         # NCCL prints its version banner to stdout at levels VERSION and WARN; the contract is ONE JSON line on stdout
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
@@ -461,6 +466,7 @@ def main():
                                  "note": "algorithmic bytes; shows the path is not HBM bound"}},
             "e2e": {"value": steps_per_step_all / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
                     "h2d_bytes_per_step": S * 48 + NK * 8, "d2h_bytes_per_step": S * 16 + 2096, "ms_per_step": e2e_ms,
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
                     "api": ("rbq_mc_static (host pointers, pinned): " + ("streamed in one-wave chunks" if os.environ.get("RBQ_MC_ZEROCOPY") == "0"
                                                                           else "zero-copy, the kernel reads the samples and writes the fidelities over PCIe")),
                     "pcie_measured": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,

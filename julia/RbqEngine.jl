@@ -234,6 +234,31 @@ function lindblad_segments(amps::Vector{Float64}, durs::Vector{Float64}, gate::I
     return fid, rho, st[]
 end
 
+"""
+iLQR backward pass (Altro `backwardpass!`) for B problems on the device.  AB is n×(n+m)×(N-1)×B exactly as `jacobians!`
+fills it; Exx n×n×N×B (symmetric, lower triangle read), Ex n×N×B, Euu m×m×(N-1)×B, Eux m×n×(N-1)×B, Eu m×(N-1)×B.
+Returns K (m×n×(N-1)×B), d (m×(N-1)×B), ΔV (2×B) and the failure flags (-1, or the 0-based knot where Quu_reg was not
+positive definite: raise ρ and call again, as Altro's regularization_update! does).
+"""
+function backward_pass(AB::Array{Float64,4}, Exx::Array{Float64,4}, Ex::Array{Float64,3}, Euu::Array{Float64,4},
+                       Eux::Array{Float64,4}, Eu::Array{Float64,3}; rho::Real=0.0, state_reg::Bool=false)
+    n, N, B = size(Ex)
+    m = size(Eu, 1)
+    K = Array{Float64,4}(undef, m, n, N - 1, B)
+    d = Array{Float64,3}(undef, m, N - 1, B)
+    dV = Matrix{Float64}(undef, 2, B)
+    failed = Vector{Int64}(undef, B)
+    GC.@preserve AB Exx Ex Euu Eux Eu K d dV failed check(ccall((:rbq_backward_pass, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+        handle().ptr, n, m, N, B, AB, Exx, Ex, Euu, Eux, Eu, rho, state_reg ? 1 : 0, K, d, dV, failed), "rbq_backward_pass")
+    return K, d, dV, failed
+end
+
+"Performance hint for mc_static: the (qubit frequency, amplitude offset) the explicit samples scatter around (default FQ, 0)."
+set_sweep_centre(fq0::Real, da0::Real=0.0) =
+    check(ccall((:rbq_set_sweep_centre, LIB), Cint, (Ptr{Cvoid}, Float64, Float64), handle().ptr, fq0, da0), "rbq_set_sweep_centre")
+
 # ---- the macro a reference script uses ---------------------------------------------------------------------
 """
     RbqEngine.@accelerate Model params_expr
