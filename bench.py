@@ -171,6 +171,45 @@ def other_configs(eng, rbq, spin, torch, dev):
             "closedloop_8_candidates_ms": timed_host(lambda: eng.rollout_closedloop(model.params, X, U, K, d, dtv, alphas)),
             "api": "rbq_rollout / rbq_jacobians / rbq_rollout_closedloop, pageable host buffers (pinned where named), copies included",
         }
+        # the backward pass on the Jacobians where rbq_jacobians_dev leaves them (device resident; LQR blocks of spin13.jl:128-135)
+        dd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dX, dU, ddt = dd(X[:-1]), dd(U), dd(dtv)
+        dAB = torch.empty(N - 1, n * (n + m), dtype=torch.float64, device=dev)
+        dExx = dd(np.tile(np.eye(n), (N, 1, 1))); dEx = dd(0.1 * X)
+        dEuu = dd(np.tile(0.1 * np.eye(m), (N - 1, 1, 1))); dEux = dd(np.zeros((N - 1, n, m))); dEu = dd(0.1 * U)
+        dK = torch.empty(N - 1, n * m, dtype=torch.float64, device=dev); dd_ = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
+        ddV = torch.empty(2, dtype=torch.float64, device=dev); dfl = torch.empty(1, dtype=torch.int64, device=dev)
+
+        def expansion_and_pass():
+            eng.jacobians_dev(model.params, N - 1, dX, dU, ddt, dAB)
+            eng.backward_pass_dev(n, m, N, 1, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
+            eng.synchronize()
+
+        out[name]["jacobians_plus_backward_pass_dev_ms"] = timed_host(expansion_and_pass)
+        # BASELINE's metric read literally (rollout + Jacobians): a batch of independent problems, device resident.  One
+        # trajectory-step = one 4-real iso state vector advanced one knot (spin13 carries 2, spin12 10, spin30 13 per knot).
+        Bt = {"spin13": 4096, "spin12": 1024, "spin30": 512}[name]
+        iso_vectors = {"spin13": 2, "spin12": 10, "spin30": 13}[name]
+        bX0 = dd(np.tile(x0, (Bt, 1))); bU = dd(np.tile(U, (Bt, 1, 1)))
+        bX = torch.empty(Bt, N, n, dtype=torch.float64, device=dev)
+        # Jacobians at every state the rollout wrote, the terminal one included (N per trajectory, counted as N-1 below), so
+        # that the kernel reads X in place: no repacking between the two calls
+        bU2 = dd(np.tile(np.concatenate([U, U[-1:]]), (Bt, 1, 1))); bdt2 = dd(np.tile(np.concatenate([dtv, dtv[-1:]]), Bt))
+        chunk = 256
+        bAB = torch.empty(chunk * N, n * (n + m), dtype=torch.float64, device=dev)      # one chunk of blocks, overwritten
+
+        def batch_rollout_jacobians():
+            eng.rollout_dev(model.params, Bt, N, bX0, bU, ddt, bX)
+            for b0 in range(0, Bt, chunk):
+                cnt = min(chunk, Bt - b0)
+                eng.jacobians_dev(model.params, cnt * N, bX[b0:b0 + cnt], bU2[b0:b0 + cnt], bdt2[b0 * N:(b0 + cnt) * N], bAB)
+            eng.synchronize()
+
+        ms_b = timed_host(batch_rollout_jacobians, reps=2)
+        out[name]["batch_rollout_plus_jacobians"] = {"problems": Bt, "ms": ms_b, "iso_vectors_per_knot": iso_vectors,
+                                                     "trajectory_steps_per_s": Bt * (N - 1) * iso_vectors / ms_b * 1e3,
+                                                     "jacobian_bytes_written": Bt * N * n * (n + m) * 8}
+        del bX0, bU, bX, bAB, bU2, bdt2
     S = 100_000
     rng = np.random.default_rng(0)
     psi = rng.random((S, 2)) + 1j * rng.random((S, 2))

@@ -637,7 +637,15 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
     memset(&a, 0, sizeof(a));
     if (!make_gate_tables(gate, &a.gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
     if (S == 0) return RBQ_OK;
-    CKL(stage_pulse(h, d_controls, nk, &a.controls, &a.amax));
+    {   // knot table around (fq, 0): every sample of a noise sweep shares the qubit frequency
+        void *tb = nullptr, *sc = nullptr;
+        CKL(dev_buf(h, B_PULSE, sizeof(double) * 4 * (size_t)nk + 32, &tb));
+        CKL(dev_buf(h, B_SCALARS, 256, &sc));
+        CKL(launch_static_table(h, d_controls, nk, dt, fq, 0.0, (double*)tb, (double*)sc));
+        a.table = (const double*)tb; a.scal = (const double*)sc;
+        const char* e = getenv("RBQ_NO_TABLE_CLASS");
+        a.no_table_class = (e && atoi(e) != 0) ? 1 : 0;
+    }
     a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S; a.fq = fq;
     a.noise = d_noise; a.noise_len = noise_len; a.noise_dt_inv = noise_dt_inv; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.namp = namp; a.fid = d_fid;

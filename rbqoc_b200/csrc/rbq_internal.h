@@ -50,12 +50,14 @@ struct McStaticArgs {
     GateIso gate;
 };
 struct McNoiseArgs {
-    const double* controls; int64_t nk; double dt;
+    const double* table; int64_t nk; double dt;    // knot table centred on (fq, 0), see static_table_kernel
     int64_t gate_count; int64_t first; int64_t S; double fq;
     const double* noise; int64_t noise_len; double noise_dt_inv; const double* psi0;
     const int32_t* idx_table; int64_t idx_stride;   // noise-sample index per (gate, knot), rows padded to 4 entries
     int philox; uint64_t seed; double namp;
-    double* fid; BlockPartial* partials; unsigned long long* hist; const double* amax;
+    double* fid; BlockPartial* partials; unsigned long long* hist;
+    const double* scal;          // device scalars of the table: max|a|, f0, a0, max|q_j|, table_ok, max x_j
+    int no_table_class;
     GateIso gate;
 };
 struct LindbladArgs {

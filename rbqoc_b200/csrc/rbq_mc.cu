@@ -97,7 +97,7 @@ struct PulsePipeT {
     RBQ_DEV void release(bool more = true) { if (more) __syncthreads(); ++pass; }
 };
 typedef PulsePipeT<MC_TILE> PulsePipe;
-constexpr int NOISE_TILE = 1024;
+constexpr int NOISE_TILE = 512;   // knots per tile of the noise sweeps: 16 KB of knot-table rows + 2 KB of noise indices
 constexpr int ST_TILE = 256;    // knots per tile of the static sweep's knot table (4 doubles per knot: 8 KB)
 constexpr int ST_EPK = 4;
 
@@ -593,7 +593,7 @@ RBQ_DEV void noise_tile(const double* __restrict__ tile, const int32_t* __restri
             for (int u = 0; u < 4; ++u) {
                 const int32_t iu = idx[j + u];
                 if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); }
-                q[u] = fma(w, tile[j + u], qd);
+                q[u] = tile[ST_EPK * (j + u)] + qd;
                 x[u] = fma(q[u], q[u], p2);
                 ok = ok && (x[u] <= xmax);
             }
@@ -615,22 +615,67 @@ RBQ_DEV void noise_tile(const double* __restrict__ tile, const int32_t* __restri
     for (; j < len; ++j) {
         const int32_t iu = idx[j];
         if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); }
-        const double q = fma(w, tile[j], qd);
+        const double q = tile[ST_EPK * j] + qd;
+        general_step(p, q, fma(q, q, p2), v);
+    }
+}
+
+// Table class of the noise sweeps (all samples share f_q = the table's centre, so eps = q_j (2 dq) + dq^2 with dq = w * noise):
+// the noise amplitude and everything derived from it -- dq, 2 dq, dq^2 and the verdict "eps stays inside the table's range" --
+// change only when the noise index does (a warp-uniform branch), so a knot costs 14 FP64 instructions and no compare.
+RBQ_DEV void noise_tile_table(const double* __restrict__ tile, const int32_t* __restrict__ idx, int len, double w, double p, double p2,
+                              double qmax, const double* __restrict__ row, PinkGen* pg, int32_t& cur, double& qd, double& qd2,
+                              double& qsq, bool& in_range, double* v) {
+    int j = 0;
+    constexpr int NU = 4;                                    // knots per batch (independent chains; 8 gains nothing and spills)
+    for (; j + NU <= len; j += NU) {
+        double q[NU], t[NU];
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int32_t iu = idx[j + u];
+            if (iu != cur) {
+                cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); qd2 = 2.0 * qd; qsq = qd * qd;
+                const double eb = fma(fabs(qd2), qmax, qsq);
+                in_range = DELTA_R3 * eb * eb * eb <= DELTA_TOL;             // false for NaN
+            }
+            ok = ok && in_range;
+            const double* __restrict__ r = tile + ST_EPK * (j + u);
+            const double eps = fma(r[0], qd2, qsq);
+            q[u] = r[0] + qd;
+            t[u] = fma(fma(r[3], eps, r[2]), eps, r[1]);
+        }
+        if (ok) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) tan_apply(t[u] * p, t[u] * q[u], v);
+        } else {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) general_step(p, q[u], fma(q[u], q[u], p2), v);
+        }
+    }
+    for (; j < len; ++j) {
+        const int32_t iu = idx[j];
+        if (iu != cur) {
+            cur = iu; qd = w * (row ? row[iu] : pg->at(iu)); qd2 = 2.0 * qd; qsq = qd * qd;
+            const double eb = fma(fabs(qd2), qmax, qsq);
+            in_range = DELTA_R3 * eb * eb * eb <= DELTA_TOL;
+        }
+        const double q = tile[ST_EPK * j] + qd;
         general_step(p, q, fma(q, q, p2), v);
     }
 }
 
 template <int ALGO>
 __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs a) {
-    __shared__ __align__(128) double tile_s[2 * NOISE_TILE];
+    __shared__ __align__(128) double tile_s[2 * NOISE_TILE * ST_EPK];
     __shared__ __align__(128) int32_t idx_s[2 * NOISE_TILE];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
-    PulsePipeT<NOISE_TILE> pipe;
-    pipe.init(tile_s, bar_s, a.controls, a.nk, idx_s, a.idx_table, a.idx_stride);
+    PulsePipeT<NOISE_TILE, ST_EPK> pipe;
+    pipe.init(tile_s, bar_s, a.table, a.nk, idx_s, a.idx_table, a.idx_stride);
 
     const int64_t s = (int64_t)blockIdx.x * MC_THREADS + tid;
     const bool live = s < a.S;
@@ -648,10 +693,15 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
     // propagator class from the noiseless pulse with head-room; noise_tile re-checks x at every knot
     int cls;
     {
-        const double qb = w * (*a.amax) * 1.05;
+        const double qb = a.scal[3] * 1.05;                  // max |q_j| of the noiseless pulse
         const double xb = fma(qb, qb, p2);
         cls = xb == xb ? degree_class(xb) : 3;
     }
+    // every sample shares f_q, the centre the knot table was built around: the table step applies wherever the noise is small
+    const bool use_table = a.scal[4] != 0.0 && !a.no_table_class;
+    const double qmax = a.scal[3];
+    double qd2 = 0.0, qsq = 0.0;
+    bool in_range = true;
     const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS, cf0[2] = {0.0, 0.0};
     double tg[4][4], st[4];
 #pragma unroll
@@ -670,7 +720,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
             const int32_t* idx = pipe.aux();
             const int len = pipe.tile_len(ti);
             if (ALGO == RBQ_ALGO_SU2) {
-                if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cfA, RBQ_TANA_XMAX);
+                if (use_table) noise_tile_table(tile, idx, len, w, p, p2, qmax, row, &pg, cur, qd, qd2, qsq, in_range, st);
+                else if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cfA, RBQ_TANA_XMAX);
                 else if (cls == 1) noise_tile<RBQ_TANB_DEG>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cfB, RBQ_TANB_XMAX);
                 else noise_tile<0>(tile, idx, len, w, p, p2, row, &pg, cur, qd, st, cf0, 0.0);
                 // unitary evolution preserves the norm: shed the tan form's 1/cos growth and the radial rounding
@@ -683,7 +734,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
                     const int32_t iu = idx[j];
                     if (iu != cur) { cur = iu; qd = w * (row ? row[iu] : pg.at(iu)); }
                     double G[16], X[16];
-                    generator4(p, fma(w, tile[j], qd), G);
+                    generator4(p, tile[ST_EPK * j] + qd, G);
                     expm4_pade(G, X);
                     mv4(X, st);
                 }
@@ -707,12 +758,12 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_kernel(const McNoiseArgs 
 // S chains of G x N dependent knots), and a second kernel multiplies each sample's G quaternions in order and evaluates the
 // fidelities.  The reference's largest workload (figures.jl gen_3b: 1000 seeds x 200 gates x 5680 knots) has S = 1000.
 __global__ void __launch_bounds__(MC_THREADS) mc_noise_gate_kernel(const McNoiseArgs a, double* __restrict__ quat) {
-    __shared__ __align__(128) double tile_s[2 * NOISE_TILE];
+    __shared__ __align__(128) double tile_s[2 * NOISE_TILE * ST_EPK];
     __shared__ __align__(128) int32_t idx_s[2 * NOISE_TILE];
     __shared__ __align__(8) uint64_t bar_s[2];
     const int64_t g = blockIdx.y;
-    PulsePipeT<NOISE_TILE> pipe;
-    pipe.init(tile_s, bar_s, a.controls, a.nk, idx_s, a.idx_table, a.idx_stride, g);
+    PulsePipeT<NOISE_TILE, ST_EPK> pipe;
+    pipe.init(tile_s, bar_s, a.table, a.nk, idx_s, a.idx_table, a.idx_stride, g);
     const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     const bool live = s < a.S;
     const int64_t sc = live ? s : a.S - 1;
@@ -721,10 +772,15 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_gate_kernel(const McNoise
     const double* row = a.noise + sc * a.noise_len;
     int cls;
     {
-        const double qb = w * (*a.amax) * 1.05;
+        const double qb = a.scal[3] * 1.05;                  // max |q_j| of the noiseless pulse
         const double xb = fma(qb, qb, p2);
         cls = xb == xb ? degree_class(xb) : 3;
     }
+    // every sample shares f_q, the centre the knot table was built around: the table step applies wherever the noise is small
+    const bool use_table = a.scal[4] != 0.0 && !a.no_table_class;
+    const double qmax = a.scal[3];
+    double qd2 = 0.0, qsq = 0.0;
+    bool in_range = true;
     const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS, cf0[2] = {0.0, 0.0};
     double v[4] = {1.0, 0.0, 0.0, 0.0}, qd = 0.0;
     int32_t cur = -1;
@@ -732,7 +788,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_gate_kernel(const McNoise
         const double* tile = pipe.acquire(ti, false, g);
         const int32_t* idx = pipe.aux();
         const int len = pipe.tile_len(ti);
-        if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cfA, RBQ_TANA_XMAX);
+        if (use_table) noise_tile_table(tile, idx, len, w, p, p2, qmax, row, nullptr, cur, qd, qd2, qsq, in_range, v);
+        else if (cls == 0) noise_tile<RBQ_TANA_DEG>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cfA, RBQ_TANA_XMAX);
         else if (cls == 1) noise_tile<RBQ_TANB_DEG>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cfB, RBQ_TANB_XMAX);
         else noise_tile<0>(tile, idx, len, w, p, p2, row, nullptr, cur, qd, v, cf0, 0.0);
         const double inv = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));

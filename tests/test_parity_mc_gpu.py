@@ -499,3 +499,23 @@ def test_mc_static_zero_copy_equals_streamed(engine, monkeypatch, gate_count):
     fid_c, _ = engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=pfid)
     assert np.array_equal(fid_c, fid_s)
     assert engine.launch_count - before >= launches_zero_copy
+
+
+@pytest.mark.parametrize("gate_parallel", ["0", "1"], ids=["sequential", "gate_parallel"])
+def test_noise_table_class_equals_polynomial_classes(engine, oracle, gate_parallel, monkeypatch):
+    """The noise sweeps take the knot-table step wherever the noise keeps eps inside the table's range (decided when the
+    noise index changes), the polynomial step otherwise; both agree to rounding and each matches the oracle."""
+    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    S, gc, ndi = 700, 4, 10.0
+    _, _, psi0 = _samples(S, seed=17)
+    nlen = int(np.ceil(controls.shape[0] * dt * gc * ndi)) + 1
+    noise = engine.pink_noise(3, S, 9, spin.NAMP_PREFACTOR, ndi, nlen)
+    noise[::7, 30:60] += 5e-3                      # bursts that leave the table's range (but not the polynomial's)
+    fid_t, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
+    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    fid_p, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
+    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    assert np.max(np.abs(fid_t - fid_p)) < 5e-14 and not np.array_equal(fid_t, fid_p)
+    ref = oracle.mc_noise(controls, dt, gate, gc, spin.FQ, noise[:200], ndi, psi0[:200])
+    assert np.max(np.abs(fid_t[:200] - ref)) < FID_RTOL and np.max(np.abs(fid_p[:200] - ref)) < FID_RTOL
