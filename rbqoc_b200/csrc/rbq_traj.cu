@@ -276,7 +276,13 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
     const int lpk = (n + m + nt - 1) / nt;
     const int blk_bytes = n * (n + m) * (int)sizeof(double);
-    int G = JAC_STAGE_BYTES / blk_bytes;
+    // Staging budget per block, measured (tools/proto/jac_sweep.py, 1e6 / 2.6e5 / 1.3e5 knots): small stages leave room for many
+    // resident blocks, whose compute and write-out phases then overlap -- 20 KB: 4.75 TB/s written (spin13) and 4.8 TB/s
+    // (spin12, one knot per block) against 3.7 / 3.1 TB/s with 200 KB; the unscented models are compute bound and like ~110 KB
+    int stage_bytes = blk_bytes > 20 * 1024 ? 110 * 1024 : 20 * 1024;
+    if (const char* e = getenv("RBQ_JAC_STAGE_KB")) { const int kb = atoi(e); if (kb >= 1 && kb <= 200) stage_bytes = kb * 1024; }
+    int G = stage_bytes / blk_bytes;
+    if (G < 1 && blk_bytes <= JAC_STAGE_BYTES) G = 1;
     if (G > 256 / lpk) G = 256 / lpk;
     const char* force = getenv("RBQ_JAC_STAGED");
     const bool staged = G >= 1 && (force ? atoi(force) != 0 : K >= JAC_STAGED_MIN_KNOTS);
