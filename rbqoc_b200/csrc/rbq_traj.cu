@@ -273,13 +273,17 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     const int fam = family(p.model_id);
     // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
-    const int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
+    int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
+    const bool unscented = fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25;
+    // the unscented step is register hungry: one tangent per lane (254 registers, no spills) beats two (255 + 868 B of spills)
+    // by 1.4x on batches although every lane repeats the value path; RBQ_JAC_NT_UNSCENTED=2 selects the old split
+    if (unscented) { const char* e = getenv("RBQ_JAC_NT_UNSCENTED"); nt = (e && atoi(e) == 2) ? 2 : 1; }
     const int lpk = (n + m + nt - 1) / nt;
     const int blk_bytes = n * (n + m) * (int)sizeof(double);
     // Staging budget per block, measured (tools/proto/jac_sweep.py, 1e6 / 2.6e5 / 1.3e5 knots): small stages leave room for many
     // resident blocks, whose compute and write-out phases then overlap -- 20 KB: 4.75 TB/s written (spin13) and 4.8 TB/s
-    // (spin12, one knot per block) against 3.7 / 3.1 TB/s with 200 KB; the unscented models are compute bound and like ~110 KB
-    int stage_bytes = blk_bytes > 20 * 1024 ? 110 * 1024 : 20 * 1024;
+    // (spin12, one knot per block) against 3.7 / 3.1 TB/s with 200 KB; the unscented models are compute bound (1.7 TB/s), one knot per block is best there too
+    int stage_bytes = blk_bytes > 20 * 1024 ? 30 * 1024 : 20 * 1024;
     if (const char* e = getenv("RBQ_JAC_STAGE_KB")) { const int kb = atoi(e); if (kb >= 1 && kb <= 200) stage_bytes = kb * 1024; }
     int G = stage_bytes / blk_bytes;
     if (G < 1 && blk_bytes <= JAC_STAGE_BYTES) G = 1;
@@ -302,8 +306,8 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         case RBQ_MODEL_SPIN15: CALLS(RBQ_MODEL_SPIN15, 4); break;
         case RBQ_MODEL_SPIN11: CALLS(RBQ_MODEL_SPIN11, 4); break;
         case RBQ_MODEL_SPIN12: CALLS(RBQ_MODEL_SPIN12, 2); break;
-        case RBQ_MODEL_SPIN30: CALLS(RBQ_MODEL_SPIN30, 2); break;
-        case RBQ_MODEL_SPIN25: CALLS(RBQ_MODEL_SPIN25, 2); break;
+        case RBQ_MODEL_SPIN30: if (nt == 1) CALLS(RBQ_MODEL_SPIN30, 1) else CALLS(RBQ_MODEL_SPIN30, 2) break;
+        case RBQ_MODEL_SPIN25: if (nt == 1) CALLS(RBQ_MODEL_SPIN25, 1) else CALLS(RBQ_MODEL_SPIN25, 2) break;
         default: return RBQ_E_MODEL;
         }
 #undef CALLS
@@ -311,6 +315,7 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         const int threads = 128;
         const int64_t total = K * lpk;
         const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+#define CALL1(M) jacobians_kernel<M, 1><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_t, d_dt, d_AB)
 #define CALL2(M) jacobians_kernel<M, 2><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_t, d_dt, d_AB)
 #define CALL4(M) jacobians_kernel<M, 4><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk, K, d_X, d_U, d_t, d_dt, d_AB)
         switch (fam) {
@@ -318,10 +323,11 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
         case RBQ_MODEL_SPIN15: CALL4(RBQ_MODEL_SPIN15); break;
         case RBQ_MODEL_SPIN11: CALL4(RBQ_MODEL_SPIN11); break;
         case RBQ_MODEL_SPIN12: CALL2(RBQ_MODEL_SPIN12); break;
-        case RBQ_MODEL_SPIN30: CALL2(RBQ_MODEL_SPIN30); break;
-        case RBQ_MODEL_SPIN25: CALL2(RBQ_MODEL_SPIN25); break;
+        case RBQ_MODEL_SPIN30: if (nt == 1) CALL1(RBQ_MODEL_SPIN30); else CALL2(RBQ_MODEL_SPIN30); break;
+        case RBQ_MODEL_SPIN25: if (nt == 1) CALL1(RBQ_MODEL_SPIN25); else CALL2(RBQ_MODEL_SPIN25); break;
         default: return RBQ_E_MODEL;
         }
+#undef CALL1
 #undef CALL2
 #undef CALL4
     }
