@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
     double* S = sm;                    // S(r, kk) at kk * ld + r   (symmetric)
     double* sv = S + ld * n4;
     double* AB = sv + n8;              // [A B](kk, c) at c * ld + kk
-    double* T = AB + ld * q8;          // T(r, c) at c * ld + r; scratch of the value update
+    double* T = AB + ld * q8;          // T(r, c) at c * ld + r
     double* G = T + ld * q8;           // G(i, j) at j * ldg + i
     double* g = G + cs * ldg;          // Qx, Qu: column cs of G
     double* Kk = G + ldg * q8;         // K(p, j) at j * m + p
@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         for (int i = lane; i < n; i += 32)
             S[j * ld + i] = Exxg[(N - 1) * (int64_t)(n * n) + (i >= j ? j * n + i : i * n + j)];   // lower triangle, mirrored
     for (int i = tid; i < n; i += BP_THREADS) sv[i] = Exg[(N - 1) * (int64_t)n + i];
+    // (One bulk TMA copy per column was tried instead of the per-element cp.async: 57 UBLKCP issued by one warp serialise and
+    // take longer -- 3.8 k cycles against 2.4 k -- and a single copy of the whole block would need the unpadded layout.)
     auto stage_jacobian = [&](int64_t k) {
         const double* src = ABg + k * (int64_t)(n * nm);
         if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
@@ -127,7 +129,6 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
 
     const int rtiles = n8 / 8, ctiles = q8 / 8, ksteps = n4 / 4;
     const int fr = lane >> 2, fc = lane & 3;          // fragment coordinates of this lane
-    const int ld2 = n8 + 1;                           // odd leading dimension of the value-update scratch: conflict-free transposed reads
     long long bad = -1;
 #ifdef RBQ_BP_PROFILE
     long long tprev = clock64();
@@ -280,8 +281,9 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
         BP_PROF(8)
         // ---- value update: V = Qxx + sym(K'Quu K + K'Qux + Qux'K) into the scratch, then S = (V + V')/2 ----
-        // G is symmetric up to rounding (both halves are computed): the gain terms are symmetrised exactly here, Qxx by
-        // averaging its two computed halves below.  Lane -> row i (its K, Quu K and Qux entries stay in registers), the
+        // S = sym(Qxx) + sym(K'Quu K + K'Qux + Qux'K), written in one pass.  The symmetrisation is not cosmetic: the recursion
+        // contracts symmetric errors through the closed loop (A - BK) but maps an antisymmetric part as A' . A, which grows
+        // whenever rho(A) > 1 -- without (S + S')/2 the rounding-level asymmetry of Qxx wrecks a 180-knot pass.  Lane -> row i (its K, Quu K and Qux entries stay in registers), the
         // warp walks the columns j (whose entries are warp-uniform broadcasts).
         for (int i = lane; i < n; i += 32) {
             double ki[BP_MAX_M], qi[BP_MAX_M], hi[BP_MAX_M];
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
             }
 #pragma unroll 2
             for (int j = wid; j < n; j += NW) {
-                double v = G[j * ldg + i];
+                double v = 0.5 * (G[j * ldg + i] + G[i * ldg + j]);      // the transposed read costs a 4-way bank conflict, no barrier
 #pragma unroll
                 for (int p = 0; p < BP_MAX_M; ++p) {
                     if (p >= m) continue;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
                     v = fma(ki[p], fma(0.5, QuuK[j * m + p], hj), v);          // K'(Quu K)/2 + K'Qux
                     v = fma(kj, qi[p] + hi[p], v);                             // (Quu K)'K/2 + Qux'K
                 }
-                T[j * ld2 + i] = v;
+                S[j * ld + i] = v;
             }
         }
         BP_PROF(9)
@@ -324,18 +326,6 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
                 d1 = fma(dk[p], qd, d1);
             }
             dv_s[0] += d0; dv_s[1] += 0.5 * d1;
-        }
-        BP_PROF(10)
-        __syncthreads();
-        BP_PROF(11)
-        // 16 x 16 blocks: the transposed read stays inside 16 columns of the odd-stride scratch
-        for (int blk = wid; blk < ((n + 15) / 16) * ((n + 15) / 16); blk += NW) {
-            const int nb = (n + 15) / 16, bi = (blk % nb) * 16, bj = (blk / nb) * 16;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const int i = bi + (lane & 15), j = bj + 2 * h + (lane >> 4);
-                if (i < n && j < n) S[j * ld + i] = 0.5 * (T[j * ld2 + i] + T[i * ld2 + j]);
-            }
         }
         BP_PROF(7)
         // the barrier at the top of the loop orders these writes against the next knot's reads
