@@ -136,10 +136,6 @@ for mname, model, x0, N in (("spin13", spin.Spin13Model(), spin.spin13_x0(), 100
     out(f"rollout {mname} N={N} host pointers", ms_h, N - 1, "knot-steps/s", n=n)
 
 # ---- iLQR backward pass fed by the Jacobians above (device resident) --------------------------------
-import time
-
-from oracle import riccati  # CPU restatement, timed beside the kernel as the baseline (checker code, measurement only)
-
 for mname, model, x0, N in (("spin13", spin.Spin13Model(), spin.spin13_x0(), 1001), ("spin12", spin.Spin12Model(), spin.spin12_x0(), 1001),
                             ("spin30", spin.Spin30Model(), spin.spin30_x0(), 1001)):
     n, m = model.n, model.m
@@ -149,7 +145,6 @@ for mname, model, x0, N in (("spin13", spin.Spin13Model(), spin.spin13_x0(), 100
     AB = eng.jacobians(model.params, X[:-1], U, dtv)                    # (N-1, n, n+m) view of the column-major blocks
     Exx = np.tile(np.eye(n), (N, 1, 1)); Exx[-1] *= N
     Ex = 0.1 * X; Euu = np.full((N - 1, m, m), 0.0) + 0.1 * np.eye(m); Eux = np.zeros((N - 1, m, n)); Eu = 0.1 * U
-    t0 = time.perf_counter(); riccati.backward_pass(AB, Exx, Ex, Euu, Eux, Eu, rho=1e-3); cpu_ms = (time.perf_counter() - t0) * 1e3
     col = lambda x: np.ascontiguousarray(np.swapaxes(x, -1, -2))
     for B in (1, 148, 592):
         rep = lambda x: d(np.tile(x[None], (B,) + (1,) * x.ndim))
@@ -159,5 +154,5 @@ for mname, model, x0, N in (("spin13", spin.Spin13Model(), spin.spin13_x0(), 100
         ms = timed(lambda: eng.backward_pass_dev(n, m, N, B, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd, ddV, dfl), reps=3, warm=1)
         flops = 2.0 * (n * n * (n + m) + 0.5 * (n + m) * (n + m) * n) * (N - 1) * B
         out(f"backward_pass {mname} N={N} B={B}", ms, B * (N - 1), "knot-updates/s", n=n, us_per_knot=ms * 1e3 / (N - 1),
-            tflops=flops / ms * 1e-9, cpu_numpy_ms_one_problem=round(cpu_ms, 2))
+            tflops=flops / ms * 1e-9)
         assert int(dfl.max().item()) == -1
