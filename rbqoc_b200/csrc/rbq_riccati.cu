@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         for (int i = lane; i < n; i += 32)
             S[j * ld + i] = Exxg[(N - 1) * (int64_t)(n * n) + (i >= j ? j * n + i : i * n + j)];   // lower triangle, mirrored
     for (int i = tid; i < n; i += BP_THREADS) sv[i] = Exg[(N - 1) * (int64_t)n + i];
-    // (One bulk TMA copy per column was tried instead of the per-element cp.async: 57 UBLKCP issued by one warp serialise and
-    // take longer -- 3.8 k cycles against 2.4 k -- and a single copy of the whole block would need the unpadded layout.)
+    // Staging cost, measured (make EXTRA=-DRBQ_BP_PROFILE): ~270 cycles per cp.async instruction of a warp whatever its width
+    // -- one CTA keeps only ~9 KB in flight, so a 25 KB block is bound by its own latency x bandwidth (2.3 k cycles), not by
+    // instruction issue.  One bulk TMA copy per column is slower still (57 UBLKCP from one warp serialise: 3.8 k cycles); a
+    // single bulk copy needs the unpadded layout (bank conflicts in every fragment load) or a padded-box tensor map.  Issuing
+    // the cost blocks a knot ahead moves this time between phases without shortening the knot.
     auto stage_jacobian = [&](int64_t k) {
         const double* src = ABg + k * (int64_t)(n * nm);
         if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
