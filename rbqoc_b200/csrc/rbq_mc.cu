@@ -825,22 +825,55 @@ __global__ void __launch_bounds__(MC_THREADS) mc_noise_combine_kernel(const McNo
 // the real 3x3 equivalent of the complex 4x4 vec-Liouvillian the reference exponentiates.  exp(M dt) v is
 // summed as a Taylor series whose length comes from a bound on ||M dt||.
 struct BlochGen { double wz, wx, g2, g1; };
+// r <- exp(M) r for M = [[-g2, -wz, 0], [wz, -g2, -wx], [0, wx, -g1]].  The scalar part is factored out, exp(M) = e^{-g2} exp(N)
+// with N = M + g2 I (two rotation rates and the one leftover rate g1 - g2), and the truncated series is summed in Horner form,
+//     exp(N) v ~ v + N/1 (v + N/2 (v + ... (v + N/K v))),
+// innermost term first: 5 multiply-adds for N u and 3 for v + (N u)/k per term and vector -- no scaling of the generator and
+// no separate accumulation (the plain term-by-term sum costs 14).  g2 <= ~1e-6 per knot, so e^{-g2} is its cubic Taylor polynomial.
 template <int NV> RBQ_DEV void bloch_advance(const BlochGen& m, int kmax, const double* __restrict__ invk, double (&r)[NV][3]) {
-    double t[NV][3];
+    const double wz = m.wz, wx = m.wx, dl = m.g1 - m.g2, g2 = m.g2;
+    double u[NV][3];
 #pragma unroll
-    for (int c = 0; c < NV; ++c) { t[c][0] = r[c][0]; t[c][1] = r[c][1]; t[c][2] = r[c][2]; }
-    for (int k = 1; k <= kmax; ++k) {
-        const double ik = invk[k];   // 1/k from shared memory: a division per term would cost more than the term
-        const double wz = m.wz * ik, wx = m.wx * ik, g2 = m.g2 * ik, g1 = m.g1 * ik;
+    for (int c = 0; c < NV; ++c) { u[c][0] = r[c][0]; u[c][1] = r[c][1]; u[c][2] = r[c][2]; }
+    for (int k = kmax; k >= 1; --k) {
+        const double ik = invk[k];   // 1/k from shared memory
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
-            const double n0 = fma(-wz, t[c][1], -g2 * t[c][0]);
-            const double n1 = fma(-wx, t[c][2], fma(wz, t[c][0], -g2 * t[c][1]));
-            const double n2 = fma(wx, t[c][1], -g1 * t[c][2]);
-            t[c][0] = n0; t[c][1] = n1; t[c][2] = n2;
-            r[c][0] += n0; r[c][1] += n1; r[c][2] += n2;
+            const double n0 = -wz * u[c][1];
+            const double n1 = fma(wz, u[c][0], -wx * u[c][2]);
+            const double n2 = fma(wx, u[c][1], -dl * u[c][2]);
+            u[c][0] = fma(n0, ik, r[c][0]); u[c][1] = fma(n1, ik, r[c][1]); u[c][2] = fma(n2, ik, r[c][2]);
         }
     }
+    // e^{-g2} - 1 = -g2 + g2^2/2 - g2^3/6 (+ g2^4/24 < 1e-17 for g2 < 1e-4; larger decay per knot takes the library expm1),
+    // applied as u + (e^{-g2} - 1) u: a factor e^{-g2} rounded to binary64 would carry the same ~1e-16 relative error at every
+    // knot of a constant-amplitude segment and bias the norm coherently (1.6e-13 after 6 gates of the 1947-knot Y/2 pulse)
+    const double dec = g2 < 1e-4 && g2 > -1e-4 ? g2 * fma(g2, fma(g2, -1.0 / 6.0, 0.5), -1.0) : expm1(-g2);
+#pragma unroll
+    for (int c = 0; c < NV; ++c) { r[c][0] = fma(dec, u[c][0], u[c][0]); r[c][1] = fma(dec, u[c][1], u[c][1]); r[c][2] = fma(dec, u[c][2], u[c][2]); }
+}
+// T1 (ns) of amp_t1_spline (spin.jl:366, 393): gridded-linear in fbfq = 0.5 - 0.202407 |a| with flat extrapolation, for plain
+// doubles.  The table's knots are multiples of 0.001, so the interval comes from a 241-entry shared-memory index of 0.001-wide
+// cells plus a fix-up for arguments within rounding of a knot (same interval choice as t1_interp's search: the last knot <= x).
+RBQ_DEV void t1_cells_init(unsigned char* cells, int tid, int nthreads) {
+    for (int c = tid; c < 241; c += nthreads) {
+        const double x = 0.26 + 0.001 * (double)c + 0.0005;      // cell centre
+        int i = 0;
+        while (i < 16 && kFbfq[i + 1] <= x) ++i;
+        cells[c] = (unsigned char)i;
+    }
+}
+RBQ_DEV double t1_ns_fast(double amplitude, const unsigned char* __restrict__ cells) {
+    double x = fma(-fabs(amplitude), 0.202407, 0.5);
+    x = x > kFbfq[17] ? kFbfq[17] : (x < kFbfq[0] ? kFbfq[0] : x);                 // NaN falls through and propagates
+    int c = (int)((x - 0.26) * 1000.0);
+    c = c < 0 ? 0 : (c > 240 ? 240 : c);
+    int i = cells[c];
+    if (x < kFbfq[i]) --i;                                      // x sits within rounding of the knot that bounds its cell
+    else if (i < 16 && kFbfq[i + 1] <= x) ++i;
+    const double x0 = kFbfq[i], h = kFbfq[i + 1] - kFbfq[i];
+    const double w = (x - x0) * (1.0 / h);
+    return (1.0 - w) * (kT1us[i] * 1e3) + w * (kT1us[i + 1] * 1e3);   // the same expression t1_interp evaluates
 }
 RBQ_DEV int taylor_terms(double b) {   // smallest k with b^(k+1)/(k+1)! < 1e-18 (b >= 0), capped
     double term = b;
@@ -868,9 +901,11 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     __shared__ BlockPartial red_s[MC_THREADS / 32];
     __shared__ int kmax_s;
     __shared__ double invk_s[64];
+    __shared__ unsigned char t1cells_s[244];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
     if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
+    t1_cells_init(t1cells_s, tid, (int)blockDim.x);
     if (tid == 0) kmax_s = 1;
     PulsePipe pipe;
     if (!a.shared_map) pipe.init(tile_s, bar_s, a.controls, a.nk);   // with a shared one-gate map the pulse is not walked here
@@ -911,7 +946,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
         const double c1 = aj + da;
         BlochGen m;
         m.wz = w2 * a.fq; m.wx = w2 * c1;
-        const double g1 = t1_on ? a.dt / t1_interp<double>(c1, 1e3) : 0.0;   // gamma_1 dt, T1 in ns (spin.jl:529)
+        const double g1 = t1_on ? a.dt / t1_ns_fast(c1, t1cells_s) : 0.0;   // gamma_1 dt, T1 in ns (spin.jl:529)
         const double gphi = t2_on ? a.dt * (a.t2_gamma_c + 2.0 * a.t2_gamma_f * a.t2_gamma_f * tmid) : 0.0;
         m.g2 = g1 + gphi; m.g1 = 2.0 * g1;
         return m;
@@ -981,9 +1016,11 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
 __global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const LindbladArgs a, int channels, double* __restrict__ map_out) {
     __shared__ double M[256][9];
     __shared__ double invk_s[64];
+    __shared__ unsigned char t1cells_s[244];
     __shared__ double run[9];
     const int tid = threadIdx.x;
     if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
+    t1_cells_init(t1cells_s, tid, (int)blockDim.x);
     if (tid < 9) run[tid] = (tid % 4 == 0) ? 1.0 : 0.0;
     const bool t1_on = (channels & RBQ_LINDBLAD_T1) != 0, t2_on = (channels & RBQ_LINDBLAD_T2) != 0;
     const double w2 = 2.0 * RBQ_PI * a.dt;
@@ -998,7 +1035,7 @@ __global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const Lindblad
             const double c1 = a.controls[k];
             BlochGen m;
             m.wz = w2 * a.fq; m.wx = w2 * c1;
-            const double g1 = t1_on ? a.dt / t1_interp<double>(c1, 1e3) : 0.0;
+            const double g1 = t1_on ? a.dt / t1_ns_fast(c1, t1cells_s) : 0.0;
             m.g2 = g1 + (t2_on ? a.dt * a.t2_gamma_c : 0.0); m.g1 = 2.0 * g1;
             bloch_advance<3>(m, kmax, invk_s, P);
         }
@@ -1080,8 +1117,10 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_segments_kernel(const Seg
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
     __shared__ double invk_s[64];
+    __shared__ unsigned char t1cells_s[244];
     for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
     if (threadIdx.x < 64) invk_s[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    t1_cells_init(t1cells_s, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     const bool live = s < a.S;
@@ -1097,7 +1136,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_segments_kernel(const Seg
         const double h = dt / (double)sub;
         BlochGen m;
         m.wz = 2.0 * RBQ_PI * h * a.fq_scalar; m.wx = 2.0 * RBQ_PI * h * c1;
-        const double g1 = t1_on ? h / t1_interp<double>(c1, 1e3) : 0.0;
+        const double g1 = t1_on ? h / t1_ns_fast(c1, t1cells_s) : 0.0;
         m.g2 = g1 + (t2_on ? h * a.t2_gamma_c : 0.0); m.g1 = 2.0 * g1;
         const int kmax = taylor_terms(bnd / (double)sub);
         for (int r = 0; r < sub; ++r) bloch_advance<3>(m, kmax, invk_s, P);
