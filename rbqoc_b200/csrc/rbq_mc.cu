@@ -899,14 +899,14 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
-    __shared__ int kmax_s;
+    __shared__ int kmax_s, sub_s;
     __shared__ double invk_s[64];
     __shared__ unsigned char t1cells_s[244];
     const int tid = threadIdx.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
     if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
     t1_cells_init(t1cells_s, tid, (int)blockDim.x);
-    if (tid == 0) kmax_s = 1;
+    if (tid == 0) { kmax_s = 1; sub_s = 1; }
     PulsePipe pipe;
     if (!a.shared_map) pipe.init(tile_s, bar_s, a.controls, a.nk);   // with a shared one-gate map the pulse is not walked here
     else __syncthreads();
@@ -927,10 +927,16 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
         const double ttot = a.dt * (double)a.nk * (double)a.gate_count;
         const double gmax = (t1_on ? 2.0 / 269.03e3 : 0.0) + (t2_on ? a.t2_gamma_c + 2.0 * a.t2_gamma_f * a.t2_gamma_f * ttot : 0.0);
         const double b = w2 * (fabs(a.fq) + *a.amax + fabs(da)) + gmax * a.dt;
-        atomicMax(&kmax_s, b == b ? taylor_terms(b) : 60);
+        // coarse grids (||M dt|| > 1): equal sub-steps keep the series short and free of cancellation (its terms peak at
+        // ||M||^k/k!); the sub-step count is block uniform like the series length
+        const int sub = b == b && b > 1.0 ? (int)fmin(ceil(b), 4096.0) : 1;
+        atomicMax(&sub_s, sub);
+        __syncthreads();
+        atomicMax(&kmax_s, b == b ? taylor_terms(b / (double)sub_s) : 60);
     }
     __syncthreads();
-    const int kmax = kmax_s;
+    const int kmax = kmax_s, nsub = sub_s;
+    const double hsub = 1.0 / (double)nsub;
 
     double tg[4][3];
 #pragma unroll
@@ -966,7 +972,12 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
             for (int ti = 0; ti < pipe.ntiles; ++ti) {
                 const double* tile = pipe.acquire(ti, false);
                 const int len = pipe.tile_len(ti);
-                for (int j = 0; j < len; ++j) bloch_advance<3>(generator(tile[j], 0.0), kmax, invk_s, P);
+                for (int j = 0; j < len; ++j) {
+                    BlochGen mj = generator(tile[j], 0.0);
+                    if (nsub > 1) { mj.wz *= hsub; mj.wx *= hsub; mj.g2 *= hsub; mj.g1 *= hsub; }   // one of nsub equal sub-steps
+                    if (nsub == 1) bloch_advance<3>(mj, kmax, invk_s, P);
+                    else for (int q2 = 0; q2 < nsub; ++q2) bloch_advance<3>(mj, kmax, invk_s, P);
+                }
                 pipe.release(ti + 1 < pipe.ntiles);
             }
         }
@@ -986,7 +997,12 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
             for (int ti = 0; ti < pipe.ntiles; ++ti) {
                 const double* tile = pipe.acquire(ti, g < a.gate_count);
                 const int len = pipe.tile_len(ti);
-                for (int j = 0; j < len; ++j, ++step) bloch_advance<1>(generator(tile[j], ((double)step + 0.5) * a.dt), kmax, invk_s, rr);
+                for (int j = 0; j < len; ++j, ++step) {
+                    BlochGen mj = generator(tile[j], ((double)step + 0.5) * a.dt);
+                    if (nsub > 1) { mj.wz *= hsub; mj.wx *= hsub; mj.g2 *= hsub; mj.g1 *= hsub; }
+                    if (nsub == 1) bloch_advance<1>(mj, kmax, invk_s, rr);
+                    else for (int q2 = 0; q2 < nsub; ++q2) bloch_advance<1>(mj, kmax, invk_s, rr);
+                }
                 pipe.release(g < a.gate_count || ti + 1 < pipe.ntiles);
             }
             const int k = (int)(g & 3);
@@ -1026,7 +1042,9 @@ __global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const Lindblad
     const double w2 = 2.0 * RBQ_PI * a.dt;
     const double gmax = (t1_on ? 2.0 / 269.03e3 : 0.0) + (t2_on ? a.t2_gamma_c : 0.0);
     const double bnd = w2 * (fabs(a.fq) + *a.amax) + gmax * a.dt;
-    const int kmax = bnd == bnd ? taylor_terms(bnd) : 60;
+    const int nsub = bnd == bnd && bnd > 1.0 ? (int)fmin(ceil(bnd), 4096.0) : 1;     // coarse grids: equal sub-steps
+    const double hsub = 1.0 / (double)nsub;
+    const int kmax = bnd == bnd ? taylor_terms(bnd * hsub) : 60;
     __syncthreads();
     for (int64_t base = 0; base < a.nk; base += 256) {
         const int64_t k = base + tid;
@@ -1037,7 +1055,8 @@ __global__ void __launch_bounds__(256) lindblad_shared_map_kernel(const Lindblad
             m.wz = w2 * a.fq; m.wx = w2 * c1;
             const double g1 = t1_on ? a.dt / t1_ns_fast(c1, t1cells_s) : 0.0;
             m.g2 = g1 + (t2_on ? a.dt * a.t2_gamma_c : 0.0); m.g1 = 2.0 * g1;
-            bloch_advance<3>(m, kmax, invk_s, P);
+            if (nsub > 1) { m.wz *= hsub; m.wx *= hsub; m.g2 *= hsub; m.g1 *= hsub; }
+            for (int q2 = 0; q2 < nsub; ++q2) bloch_advance<3>(m, kmax, invk_s, P);
         }
         // column-major: M[tid][3c+i] = image of e_c, component i
 #pragma unroll
