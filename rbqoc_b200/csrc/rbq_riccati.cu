@@ -194,7 +194,31 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         BP_PROF(4)
         // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
         bool ok = true;
-        if (tid <= n) {
+        if (m == 1 && tid <= n) {
+            // one control (every reference model but the time-optimal spin15): Quu_reg is a scalar, its "factorisation" one
+            // reciprocal -- a much shorter dependent chain than the general path's sqrt, divisions and guarded loops
+            const int j = tid;
+            const double quu = G[n * ldg + n];
+            double quu_reg = quu + a.rho, bb = 0.0;
+            if (a.reg_type == RBQ_REG_STATE) {
+                for (int r = 0; r < n; ++r) bb = fma(AB[n * ld + r], AB[n * ld + r], bb);
+                quu_reg = fma(a.rho, bb, quu);
+            }
+            ok = quu_reg > 0.0;                                                     // also catches NaN
+            double rhs = j < n ? G[n * ldg + j] : g[n];                             // Qxu(j): the coalesced half of the symmetric G
+            if (j < n && a.reg_type == RBQ_REG_STATE) {
+                double ba = 0.0;
+                for (int r = 0; r < n; ++r) ba = fma(AB[n * ld + r], AB[j * ld + r], ba);
+                rhs = fma(a.rho, ba, rhs);
+            }
+            // the reference solves through the Cholesky factor: x = (rhs / l) / l with l = sqrt(Quu_reg); one division by
+            // Quu_reg differs from that by rounding only
+            const double x = -rhs / quu_reg;
+            if (ok) {
+                if (j < n) { Kk[j] = x; Kg[k * (int64_t)n + j] = x; QuuK[j] = quu * x; }
+                else { dk[0] = x; dg[k] = x; }
+            }
+        } else if (tid <= n) {
             const int j = tid;
             double L[BP_MAX_M][BP_MAX_M], rhs[BP_MAX_M];
 #pragma unroll
