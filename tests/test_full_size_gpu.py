@@ -94,3 +94,39 @@ def test_full_size_lindblad_map_properties(engine):
     assert np.all(purity >= 0.5 - 1e-14)
     assert np.all(fid >= 0.0) and np.all(fid <= 1.0 + 1e-13)
     assert st.count == S
+
+
+def test_full_sweep_zero_copy_streamed_and_polynomial_forms_agree(engine, sweep, monkeypatch):
+    """The 1M-sample sweep through page-locked buffers (zero-copy: the kernel reads / writes over PCIe) returns the bits of the
+    streamed form; the polynomial step (table class off) agrees with the knot-table step to rounding on every sample."""
+    controls, fq, da, psi0, fid, st = sweep
+    pfq, pda, ppsi = engine.pinned_empty(S_FULL), engine.pinned_empty(S_FULL), engine.pinned_empty((S_FULL, 4))
+    pfid = engine.pinned_empty((S_FULL, 2))
+    pfq[:], pda[:], ppsi[:] = fq, da, psi0
+    fz, stz = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, pfq, pda, ppsi, fid_out=pfid)
+    assert np.array_equal(fz, fid) and stz.sum == st.sum and stz.hist[:] == st.hist[:]
+    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    fp, stp = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
+    assert np.max(np.abs(fp - fid)) < 2e-14 and stp.count == S_FULL
+    assert abs(stp.sum - st.sum) < 1e-12 * st.sum
+
+
+def test_full_size_backward_pass(engine):
+    """1001 knots, n = 56 (the unscented model's dimensions), 6 problems: gains and value decrease against the numpy
+    restatement; a batch returns the same bits for the same problem wherever it sits in the batch."""
+    from oracle import riccati
+    from test_oracle_cpu import _lq_problem
+
+    rng = np.random.default_rng(8)
+    N, n, m = 1001, 56, 1
+    A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
+    A *= 0.55                                            # rho(A) < 1: a 1000-knot recursion that stays well conditioned
+    AB = np.concatenate([A, Bm], axis=2)
+    st = lambda x: np.stack([x] * 6)
+    K, d, dV, fail = engine.backward_pass(st(AB), st(Q), st(q), st(R), st(Eux), st(r), rho=1e-2)
+    Kr, dr, dVr, failr = riccati.backward_pass(AB, Q, q, R, Eux, r, rho=1e-2)
+    assert list(fail) == [-1] * 6 and failr == -1
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    assert rel(K[0], Kr) < 1e-10 and rel(d[0], dr) < 1e-10 and np.allclose(dV[0], dVr, rtol=1e-10)
+    for b in range(1, 6):
+        assert np.array_equal(K[b], K[0]) and np.array_equal(d[b], d[0]) and np.array_equal(dV[b], dV[0])
