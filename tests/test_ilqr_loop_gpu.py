@@ -1,0 +1,72 @@
+"""End-to-end consistency of the hot-path pieces: a plain iLQR loop on the reference's spin13 problem data (LQR objective of
+spin13.jl:118-135, Z/2 target of spin13.jl:80-93, N = 301 knots, dt = 0.1 ns, U0 = 1e-4) driven entirely through the engine:
+
+    rbq_rollout -> (LQR cost blocks on the host) -> rbq_jacobians -> rbq_backward_pass -> rbq_rollout_closedloop (line search)
+
+Parity tests compare each piece with its oracle; this test checks that their CONVENTIONS agree with each other (layouts and
+signs of A, B, K, d, the closed-loop law u = u_ref + K (x - x_ref) + alpha d): if any were off, the predicted decrease
+alpha dV1 + alpha^2 dV2 would not match the realised one and the cost would not go down."""
+import numpy as np
+import pytest
+
+import rbqoc_b200 as rbq
+from rbqoc_b200 import spin
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ilqr_iterations_on_spin13_decrease_the_cost_as_predicted(engine):
+    model = spin.Spin13Model()
+    n, m, N, dt = 11, 1, 301, 0.1
+    qs = [1.0, 1.0, 1.0, 1e-1, 1e-1]                                   # spin13.jl:66
+    Qd = np.array([qs[0]] * 8 + [qs[1], qs[2], qs[3]])
+    R = qs[4]
+    g = spin.GATES[spin.GateType.zpiby2]
+    xf = np.zeros(n)
+    xf[0:4] = spin.get_vec_iso(g @ np.array([1.0, 0.0]))
+    xf[4:8] = spin.get_vec_iso(g @ np.array([0.0, 1.0]))
+    x0 = spin.spin13_x0()
+    dts = np.full(N - 1, dt)
+
+    def cost(X, U):
+        dx = X - xf
+        w = np.ones(N); w[-1] = N                                      # Qf = N Q (spin13.jl:134)
+        return 0.5 * np.sum(w[:, None] * Qd * dx * dx) + 0.5 * R * np.sum(U * U)
+
+    U = np.full((N - 1, m), 1e-4)
+    X = spin.rollout(model, x0, U, dt, engine=engine)
+    J = cost(X, U)
+    J0 = J
+    alphas = 0.5 ** np.arange(10)
+    checked = 0
+    for it in range(12):
+        AB = spin.dynamics_expansion(model, X, U, dt, engine=engine)
+        Exx = np.tile(np.diag(Qd), (N, 1, 1)); Exx[-1] *= N
+        Ex = (X - xf) * Qd; Ex[-1] *= N
+        Euu = np.full((N - 1, 1, 1), R); Eux = np.zeros((N - 1, 1, n)); Eu = R * U
+        rho = 0.0
+        while True:
+            K, d, dV, fail = engine.backward_pass(AB, Exx, Ex, Euu, Eux, Eu, rho=rho)
+            if fail < 0:
+                break
+            rho = max(10.0 * rho, 1e-6)                                # Altro's regularization_update!(:increase)
+            assert rho < 1e6
+        assert dV[0] < 0
+        Xc, Uc = engine.rollout_closedloop(model.params, X, U, K, d, dts, alphas)
+        Jc = np.array([cost(Xc[i], Uc[i]) for i in range(alphas.shape[0])])
+        # quadratic model of the decrease along the search direction: dJ(alpha) ~ alpha dV1 + alpha^2 dV2; for small alpha the
+        # linearisation error of the dynamics is O(alpha^2), so the ratio tends to 1
+        small = alphas.shape[0] - 1
+        pred = alphas[small] * dV[0] + alphas[small] ** 2 * dV[1]
+        if abs(pred) > 1e-9 * J:
+            assert (Jc[small] - J) / pred == pytest.approx(1.0, abs=0.15), (it, Jc[small] - J, pred)
+            checked += 1
+        ok = np.nonzero(Jc < J)[0]
+        assert ok.size > 0, (it, J, Jc)
+        i = int(ok[0])
+        assert np.allclose(Xc[i, 0], x0)
+        X, U, J = Xc[i], Uc[i], float(Jc[i])
+    assert checked >= 6
+    assert J < 0.2 * J0                                                # the loop makes real progress towards the Z/2 target
+    # the closed-loop states ARE a rollout of the closed-loop controls
+    assert np.max(np.abs(spin.rollout(model, x0, U, dt, engine=engine) - X)) < 1e-12
