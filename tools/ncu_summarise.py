@@ -17,7 +17,9 @@ FULL_KEYS = [
     "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "pcie__read_bytes.sum", "pcie__write_bytes.sum",
-    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__inst_executed_pipe_tensor_op_dmma.sum", "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "sm__warps_active.avg.per_cycle_active",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
