@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
     // -- one CTA keeps only ~9 KB in flight, so a 25 KB block is bound by its own latency x bandwidth (2.3 k cycles), not by
     // instruction issue.  One bulk TMA copy per column is slower still (57 UBLKCP from one warp serialise: 3.8 k cycles); a
     // single bulk copy needs the unpadded layout (bank conflicts in every fragment load) or a padded-box tensor map.  Issuing
-    // the cost blocks a knot ahead moves this time between phases without shortening the knot.
+    // the cost blocks a knot ahead moves this time between phases without shortening the knot, and issuing the copies one
+    // column per contraction step inside the tensor-core loops (double-buffered [A B]) makes it worse (11.5 against 10.0 us per
+    // knot at n = 56): a warp stalls on its cp.async until the copy is accepted, which delays its DMMAs.
     auto stage_jacobian = [&](int64_t k) {
         const double* src = ABg + k * (int64_t)(n * nm);
         if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
