@@ -214,6 +214,11 @@ int rbq_sampling_cost_expansion(rbq_handle* h, int64_t K, const double* X, const
  *  psi0[S*4]          per-sample initial iso state (gen_rand_state_iso, spin.jl:1119-1138)
  *  fid[S*(gate_count+1)] or NULL   fidelities after 0..gate_count gates, sample-major
  *  stats or NULL      statistics of the infidelity after the last gate
+ *
+ *  Host buffers may be any host memory.  If fq, da, psi0 and fid are all page-locked (rbq_host_alloc, cudaHostRegister,
+ *  torch pin_memory) and gate_count <= 3, the sweep runs zero-copy: one kernel reads the samples and writes the
+ *  fidelities over PCIe itself; otherwise the samples are streamed through the device in chunks.  Same results, bit
+ *  for bit (RBQ_MC_ZEROCOPY=0 forces the streamed form).
  */
 int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double dt, int gate,
                   int64_t gate_count, int64_t S, const double* fq, const double* da,
