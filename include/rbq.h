@@ -312,6 +312,16 @@ int rbq_mc_static_segments(rbq_handle* h, const double* amps, const double* durs
 int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
                           int gate, int64_t gate_count, int64_t S, double fq, const double* noise, int64_t noise_len,
                           const double* psi0, double* fid, rbq_stats* stats);
+/* run_sim_deqjl(...; dynamics_type = schroed / schroedda) (spin.jl:1277-1380): the ODE the reference hands to Vern9 has a
+ * right-hand side that is constant between the breakpoints of the control grid (index floor(t dt_inv) mod knot count,
+ * spin.jl:425, 456), the noise grid (floor(t noise_dt_inv), spin.jl:457) and the save times (multiples of the gate time), so
+ * its exact solution is the ordered product of segment exponentials.  The caller supplies that segment list: amplitude,
+ * duration and (optional) noise index per segment, and save_after[g] = number of segments before save point g+1 (ascending).
+ * fid[S*(nsave+1)]: fidelity against the 4-cyclic targets at t = 0 and at every save point; da[S] or NULL is a static
+ * offset; noise[S*noise_len] with noise_idx[nseg], or both NULL. */
+int rbq_mc_timeline(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
+                    const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
+                    const double* noise, int64_t noise_len, const double* psi0, double* fid, rbq_stats* stats);
 int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate,
                           int64_t gate_count, int64_t S, double fq, const double* da, const double* rho0, int channels,
                           double t2_gamma_c, double* fid, double* rho_out, rbq_stats* stats);

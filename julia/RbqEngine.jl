@@ -217,6 +217,26 @@ function mc_noise_segments(amps::Vector{Float64}, durs::Vector{Float64}, noise_i
     return fid, st[]
 end
 
+"run_sim_deqjl's ODE solved exactly (spin.jl:424-467, 1277-1380): segment list (amps, durs[, noise_idx]), saves after save_after[g] segments."
+function mc_timeline(amps::Vector{Float64}, durs::Vector{Float64}, save_after::Vector{Int64}, gate::Integer, fq::Vector{Float64},
+                     psi0::Matrix{Float64}; da::Union{Nothing,Vector{Float64}}=nothing,
+                     noise::Union{Nothing,Matrix{Float64}}=nothing, noise_idx::Union{Nothing,Vector{Int32}}=nothing)
+    S = length(fq)
+    size(psi0) == (4, S) || error("psi0 must be 4×S")
+    nsave = length(save_after)
+    fid = Matrix{Float64}(undef, nsave + 1, S)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    np = noise === nothing ? Ptr{Float64}(C_NULL) : pointer(noise)
+    ip = noise_idx === nothing ? Ptr{Int32}(C_NULL) : pointer(noise_idx)
+    nlen = noise === nothing ? 0 : size(noise, 1)
+    GC.@preserve amps durs save_after fq psi0 da noise noise_idx fid check(ccall((:rbq_mc_timeline, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int64, Ptr{Int64}, Int64, Cint, Int64, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, amps, durs, ip, length(amps), save_after, nsave, gate, S, fq, dap, np, nlen, psi0, fid, st), "rbq_mc_timeline")
+    return fid, st[]
+end
+
 "integrate_prop_zpiby2t1!/ypiby2t1!/xpiby2t1! (spin.jl:582-594, 651-670, 765-785)."
 function lindblad_segments(amps::Vector{Float64}, durs::Vector{Float64}, gate::Integer, gate_count::Integer, fq::Real,
                            da::Union{Nothing,Vector{Float64}}, rho0::Array{ComplexF64,3}; channels::Integer=1,

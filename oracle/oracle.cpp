@@ -1011,6 +1011,37 @@ int orc_mc_noise_segments(const double* amps, const double* durs, const int32_t*
         sim_schroedda_segments(amps, durs, nidx, nseg, gate, gate_count, fq, noise + s * noise_len, psi0 + 4 * s, fid + s * (gate_count + 1));
     return 0;
 }
+// run_sim_deqjl's ODE (dynamics_schroed_deqjl / dynamics_schroedda_deqjl, spin.jl:424-467) solved exactly segment by segment: the
+// right-hand side is constant between breakpoints, so state <- exp(segment generator * duration) * state (generic Pade exp,
+// extended-precision state, as in integrate_prop_schroedda!); fidelities at t = 0 and after save_after[g] segments
+int orc_mc_timeline(const double* amps, const double* durs, const int32_t* nidx, int64_t nseg, const int64_t* save_after, int64_t nsave,
+                    int gate, int64_t S, const double* fq, const double* da, const double* noise, int64_t noise_len,
+                    const double* psi0, double* fid) {
+    cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+    if (noise) for (int64_t j = 0; j < nseg; ++j) if (nidx[j] < 0 || nidx[j] >= noise_len) return RBQ_E_SIZE;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) {
+        xreal s0[4], st[4], tg[4][4];
+        for (int i = 0; i < 4; ++i) { s0[i] = psi0[4 * s + i]; st[i] = s0[i]; }
+        gate_targets(gate, s0, tg);
+        double* f = fid + s * (nsave + 1);
+        f[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+        int64_t j = 0;
+        for (int64_t q = 1; q <= nsave; ++q) {
+            for (; j < save_after[q - 1]; ++j) {
+                const double amp = amps[j] + (da ? da[s] : 0.0) + (noise ? noise[s * noise_len + nidx[j]] : 0.0);
+                Mat4<double> H;
+                for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) H.a[r][c] = durs[j] * (fq[s] * (PI * N0[r][c]) + amp * (PI * N1[r][c]));
+                Mat4<double> U = expm_ref(H);
+                xreal nx[4];
+                for (int i = 0; i < 4; ++i) { xreal t = 0; for (int k = 0; k < 4; ++k) t += (xreal)U.a[i][k] * st[k]; nx[i] = t; }
+                for (int i = 0; i < 4; ++i) st[i] = nx[i];
+            }
+            f[q] = (double)fidelity_vec_iso2<xreal>(st, tg[q % 4]);
+        }
+    }
+    return 0;
+}
 // integrate_prop_ypiby2t1! / xpiby2t1! / zpiby2t1! generalised to any segment list (spin.jl:582-594, 651-670, 765-785)
 int orc_lindblad_segments(const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count, int64_t S, double fq,
                           const double* da, const double* rho0, double* fid_closed, double* rho_out) {

@@ -314,6 +314,26 @@ def mc_noise_segments(amps, durs, nidx, gate, gate_count, fq, noise, psi0):
     return fid
 
 
+def mc_timeline(amps, durs, nidx, save_after, gate, fq, da, noise, psi0):
+    amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
+    save_after = np.ascontiguousarray(save_after, dtype=np.int64)
+    da = None if da is None else _f64(da)
+    nlen = 0
+    if noise is not None:
+        noise = _f64(noise)
+        nidx = np.ascontiguousarray(nidx, dtype=np.int32)
+        nlen = noise.shape[1]
+    else:
+        nidx = None
+    S, nsave = fq.shape[0], save_after.shape[0]
+    fid = np.empty((S, nsave + 1))
+    rc = lib().orc_mc_timeline(_p(amps), _p(durs), _p(nidx), C.c_int64(amps.shape[0]), _p(save_after), C.c_int64(nsave), int(gate),
+                               C.c_int64(S), _p(fq), _p(da), _p(noise), C.c_int64(nlen), _p(psi0), _p(fid))
+    if rc:
+        raise ValueError(f"orc_mc_timeline rc={rc}")
+    return fid
+
+
 def lindblad_segments(amps, durs, gate, gate_count, fq, da, rho0):
     amps, durs = _f64(amps), _f64(durs)
     rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)

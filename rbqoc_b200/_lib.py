@@ -121,6 +121,7 @@ SIGNATURES = {
     "rbq_lindblad_dev": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _D, _P, _P, _P]),
     "rbq_mc_static_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _P, _P, _P, _P, _SP]),
     "rbq_mc_noise_segments": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _I64, _P, _P, _SP]),
+    "rbq_mc_timeline": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, C.c_int, _I64, _P, _P, _P, _I64, _P, _P, _SP]),
     "rbq_lindblad_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _P, _P, _SP]),
     "rbq_backward_pass": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
     "rbq_backward_pass_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),

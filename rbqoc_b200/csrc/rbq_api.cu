@@ -904,6 +904,52 @@ int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs,
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
 }
+int rbq_mc_timeline(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
+                    const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
+                    const double* noise, int64_t noise_len, const double* psi0, double* fid, rbq_stats* stats) {
+    ENTER(h);
+    SegmentArgs a;
+    void *dfid = nullptr, *dst = nullptr;
+    if (nsave < 0 || !save_after) return fail(h, nsave < 0 ? RBQ_E_SIZE : RBQ_E_NULL, "rbq_mc_timeline: save_after/nsave");
+    CKL(segments_common(h, "rbq_mc_timeline", amps, durs, nseg, gate, nsave, S, &a, &dfid, &dst, fid, stats, nsave + 1));
+    int64_t prev = 0;
+    for (int64_t g = 0; g < nsave; ++g) {
+        if (save_after[g] < prev || save_after[g] > nseg) return fail(h, RBQ_E_SIZE, "rbq_mc_timeline: save_after[%lld]=%lld not ascending within [0,%lld]", (long long)g, (long long)save_after[g], (long long)nseg);
+        prev = save_after[g];
+    }
+    if ((noise != nullptr) != (noise_idx != nullptr)) return fail(h, RBQ_E_NULL, "rbq_mc_timeline: noise and noise_idx go together");
+    if (noise) {
+        if (noise_len < 1) return fail(h, RBQ_E_SIZE, "rbq_mc_timeline: noise_len=%lld", (long long)noise_len);
+        for (int64_t j = 0; j < nseg; ++j)
+            if (noise_idx[j] < 0 || noise_idx[j] >= noise_len)
+                return fail(h, RBQ_E_SIZE, "rbq_mc_timeline: noise_idx[%lld]=%d outside [0,%lld)", (long long)j, noise_idx[j], (long long)noise_len);
+    }
+    if (S > 0) {
+        if (!fq || !psi0) return fail(h, RBQ_E_NULL, "rbq_mc_timeline: fq/psi0 is NULL");
+        void *dfq, *dda, *dpsi, *didx = nullptr, *dn = nullptr, *dsave;
+        CKL(dev_buf(h, B_IN1, sizeof(double) * S, &dfq)); CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda));
+        CKL(dev_buf(h, B_IN3, sizeof(double) * 4 * S, &dpsi));
+        CKL(dev_buf(h, B_QUAT, sizeof(int64_t) * (size_t)(nsave > 0 ? nsave : 1), &dsave));
+        CK(cudaMemcpyAsync(dfq, fq, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        if (da) CK(cudaMemcpyAsync(dda, da, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dpsi, psi0, sizeof(double) * 4 * S, cudaMemcpyHostToDevice, h->stream));
+        if (nsave > 0) CK(cudaMemcpyAsync(dsave, save_after, sizeof(int64_t) * nsave, cudaMemcpyHostToDevice, h->stream));
+        if (noise) {
+            CKL(dev_buf(h, B_NOISE, sizeof(int32_t) * nseg, &didx)); CKL(dev_buf(h, B_IN4, sizeof(double) * S * noise_len, &dn));
+            CK(cudaMemcpyAsync(didx, noise_idx, sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(dn, noise, sizeof(double) * S * noise_len, cudaMemcpyHostToDevice, h->stream));
+        }
+        a.fq = (double*)dfq; a.da = da ? (double*)dda : nullptr; a.psi0 = (double*)dpsi;
+        a.noise = (double*)dn; a.nidx = (int32_t*)didx; a.noise_len = noise_len;
+        int nblocks = 0;
+        CKL(launch_timeline(h, a, (const int64_t*)dsave, nsave, &nblocks));
+        if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
+        if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * (nsave + 1), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
 int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate, int64_t gate_count,
                           int64_t S, double fq, const double* da, const double* rho0, int channels, double t2_gamma_c, double* fid,
                           double* rho_out, rbq_stats* stats) {

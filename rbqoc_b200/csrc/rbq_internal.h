@@ -88,6 +88,7 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);
 int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nblocks_out);
+int launch_timeline(rbq_handle* h, const SegmentArgs& a, const int64_t* d_save_after, int64_t nsave, int* nblocks_out);
 int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);

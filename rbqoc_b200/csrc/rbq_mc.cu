@@ -1132,6 +1132,54 @@ __global__ void __launch_bounds__(MC_THREADS) mc_static_segments_kernel(const Se
         block_stats_flush(st, hist_s, red_s, a.partials, a.hist);
     }
 }
+// ---- piecewise-constant timeline with save points: the exact solution of the ODE run_sim_deqjl hands to Vern9
+//      (dynamics_schroed_deqjl / dynamics_schroedda_deqjl, spin.jl:424-467; run_sim_deqjl, spin.jl:1277-1380).  The right-hand
+//      side is constant between the breakpoints of the control grid, the noise grid and the save times, so the state after
+//      each segment is exp(segment generator * duration) * state; the host mirror builds the segment list. ----------------------
+__global__ void __launch_bounds__(MC_THREADS) mc_timeline_kernel(const SegmentArgs a, const int64_t* __restrict__ save_after, int64_t nsave) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double fq = a.fq ? a.fq[sc] : a.fq_scalar, da = a.da ? a.da[sc] : 0.0;
+    const double* nrow = a.noise ? a.noise + sc * a.noise_len : nullptr;
+    double psi0[4], st[4], tg[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { psi0[c] = a.psi0[4 * sc + c]; st[c] = psi0[c]; tg[0][c] = psi0[c]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv4_to(a.gate.g[k], psi0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (nsave + 1) : nullptr;
+    double f = fidelity_vec_iso2(st, tg[0]);
+    if (frow) frow[0] = f;
+    const double norm0 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+    int64_t j = 0;
+    for (int64_t g = 1; g <= nsave; ++g) {
+        const int64_t end = save_after[g - 1];
+        for (; j < end; ++j) {
+            const double w = RBQ_PI * a.durs[j];
+            const double amp = a.amps[j] + da + (nrow ? nrow[a.nidx[j]] : 0.0);
+            const double p = w * fq, q = w * amp;
+            general_step(p, q, fma(q, q, p * p), st);
+        }
+        // unitary evolution preserves the norm: shed the radial rounding before the fidelity is taken
+        const double n2 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
+        const double sc2 = sqrt(norm0 / n2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[i] *= sc2;
+        const int k = (int)(g & 3);
+        f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+        if (frow) frow[g] = f;
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
 __global__ void __launch_bounds__(MC_THREADS) lindblad_segments_kernel(const SegmentArgs a) {
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[MC_THREADS / 32];
@@ -1353,6 +1401,13 @@ int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nbl
     if (nblocks_out) *nblocks_out = blocks;
     if (lindblad) lindblad_segments_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a);
     else mc_static_segments_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a);
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+int launch_timeline(rbq_handle* h, const SegmentArgs& a, const int64_t* d_save_after, int64_t nsave, int* nblocks_out) {
+    const int blocks = (int)((a.S + MC_THREADS - 1) / MC_THREADS);
+    if (nblocks_out) *nblocks_out = blocks;
+    mc_timeline_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_save_after, nsave);
     h->launches++;
     return (int)cudaGetLastError();
 }

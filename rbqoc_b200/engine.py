@@ -328,6 +328,29 @@ class Engine:
                                                  C.byref(st)), "rbq_mc_noise_segments")
         return fid, st
 
+    def mc_timeline(self, amps, durs, save_after, gate, fq, psi0, da=None, noise=None, noise_idx=None):
+        """run_sim_deqjl's piecewise-constant ODE solved exactly (spin.jl:424-467, 1277-1380): segments (amps, durs[, noise_idx]),
+        fidelities at t = 0 and after save_after[g] segments -> (S, nsave + 1)."""
+        amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
+        save_after = np.ascontiguousarray(save_after, dtype=np.int64)
+        da = None if da is None else _f64(da)
+        S, nsave = fq.shape[0], save_after.shape[0]
+        if amps.shape != durs.shape or psi0.shape != (S, 4) or (da is not None and da.shape != (S,)):
+            raise ValueError("amps/durs one entry per segment, fq (S,), da (S,), psi0 (S,4)")
+        nlen, nidx = 0, None
+        if noise is not None:
+            noise = _f64(noise)
+            nidx = np.ascontiguousarray(noise_idx, dtype=np.int32)
+            if noise.ndim != 2 or noise.shape[0] != S or nidx.shape != amps.shape:
+                raise ValueError("noise (S, noise_len) with one noise_idx per segment")
+            nlen = noise.shape[1]
+        fid = np.empty((S, nsave + 1))
+        st = Stats()
+        self._ck(self._lib.rbq_mc_timeline(self._h, _ptr(amps), _ptr(durs), _ptr(nidx), amps.shape[0], _ptr(save_after), nsave,
+                                           int(gate), S, _ptr(fq), _ptr(da), _ptr(noise), nlen, _ptr(psi0), _ptr(fid), C.byref(st)),
+                 "rbq_mc_timeline")
+        return fid, st
+
     def lindblad_segments(self, amps, durs, gate, gate_count, fq, da, rho0, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0):
         amps, durs = _f64(amps), _f64(durs)
         rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)

@@ -483,6 +483,67 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
     }
 
 
+def deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv=None):
+    """Segment list of the ODE run_sim_deqjl integrates (spin.jl:424-467, 1277-1380).  Its right-hand side reads
+    controls[floor(t controls_dt_inv) mod control_knot_count] (the pulse repeats with period knot_count / dt_inv, which is NOT
+    the gate time when gate_time * dt_inv is not an integer -- the reference's own wrap-around, kept) and, for schroedda,
+    noise_offsets[floor(t noise_dt_inv)]; states are saved at multiples of gate_time.  Between the breakpoints of those three
+    grids the right-hand side is constant.  Returns (amps, durs, noise_idx or None, save_after)."""
+    controls = np.asarray(controls, dtype=np.float64).reshape(-1)
+    count = int(math.floor(gate_time * controls_dt_inv))                  # control_knot_count, spin.jl:1299
+    if count < 1 or count > controls.shape[0]:
+        raise ValueError("gate_time * controls_dt_inv must select between 1 and len(controls) knots")
+    t_end = gate_time * gate_count
+    saves = gate_time * np.arange(1, gate_count + 1)
+    pts = [np.arange(0, int(math.floor(t_end * controls_dt_inv)) + 1) / controls_dt_inv, saves]
+    if noise_dt_inv:
+        pts.append(np.arange(0, int(math.floor(t_end * noise_dt_inv)) + 1) / noise_dt_inv)
+    t = np.unique(np.concatenate(pts))
+    t = t[(t >= 0.0) & (t <= t_end)]
+    if t[-1] < t_end:
+        t = np.append(t, t_end)
+    durs = np.diff(t)
+    keep = durs > 0.0
+    mid = 0.5 * (t[:-1] + t[1:])[keep]                                    # the index of a segment is that of its midpoint
+    durs = durs[keep]
+    amps = controls[np.floor(mid * controls_dt_inv).astype(np.int64) % count]
+    nidx = np.floor(mid * noise_dt_inv).astype(np.int32) if noise_dt_inv else None
+    ends = np.cumsum(durs)
+    save_after = np.searchsorted(ends, saves - 1e-12 * max(t_end, 1.0), side="left") + 1
+    return amps, durs, nidx, np.minimum(save_after, durs.shape[0]).astype(np.int64)
+
+
+def run_sim_deqjl(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq=FQ, da=None, namp=NAMP_PREFACTOR,
+                  noise_dt_inv=DT_NOISE_INV, seed=0, state_seed=None, dynamics_type=DynamicsType.schroed, noise=None,
+                  engine: Engine | None = None):
+    """run_sim_deqjl (spin.jl:1277-1380) for dynamics_type schroed / schroedda, batched over seeds.  The reference lets Vern9
+    integrate a piecewise-constant right-hand side to reltol = abstol = 1e-12; this evaluates the exact solution of the same ODE
+    (the ordered product of segment exponentials, `deqjl_timeline`), so the two agree to the solver's tolerance.  `gate_time`
+    replaces the evolution time grab_controls reads from the pulse file."""
+    eng = engine or default_engine()
+    gate_type = GateType(gate_type)
+    dynamics_type = DynamicsType(dynamics_type)
+    if dynamics_type not in (DynamicsType.schroed, DynamicsType.schroedda):
+        raise ValueError("run_sim_deqjl mirrors the Schroedinger dynamics (schroed, schroedda)")
+    scalar = np.isscalar(seed)
+    seeds = np.atleast_1d(np.asarray(seed, dtype=np.int64))
+    sseeds = seeds if state_seed is None else np.broadcast_to(np.atleast_1d(np.asarray(state_seed, dtype=np.int64)), seeds.shape)
+    S = seeds.shape[0]
+    fqs = np.broadcast_to(np.asarray(fq, dtype=np.float64), (S,)).copy()
+    das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
+    psi0 = np.stack([gen_rand_state_iso(int(s), eng) for s in sseeds])
+    noisy = dynamics_type == DynamicsType.schroedda
+    amps, durs, nidx, save_after = deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv if noisy else None)
+    if noisy and noise is None:
+        nlen = int(math.ceil(gate_time * gate_count * noise_dt_inv)) + 1                  # spin.jl:1305
+        noise = np.concatenate([eng.pink_noise(int(s), 1, 0, namp, noise_dt_inv, nlen) for s in seeds])
+    fid, st = eng.mc_timeline(amps, durs, save_after, gate_type, fqs, psi0, da=das, noise=noise if noisy else None,
+                              noise_idx=nidx if noisy else None)
+    return {"gate_count": gate_count, "gate_type": int(gate_type), "gate_time": gate_time, "seed": seed,
+            "fidelities": fid[0] if scalar else fid, "stats": st, "dt": 1.0 / controls_dt_inv, "namp": namp,
+            "noise_dt_inv": noise_dt_inv}
+
+
 def evaluate_fqdev(controls, dt_inv, fq_cov=FQ * 1e-2, trial_count=1000, gate_type=GateType.zpiby2,
                    engine: Engine | None = None):
     """spin.jl:1611-1656 in two batched calls instead of 2*(trial_count+4) serial ones."""

@@ -290,3 +290,52 @@ def test_riccati_oracle_solves_lq_problems_in_one_pass():
     R2 = R.copy(); R2[7] = -50.0 * np.eye(m)
     assert riccati.backward_pass(AB, Q, q, R2, Eux, r)[3] == 7
     assert riccati.backward_pass(AB, Q, q, R2, Eux, r, rho=100.0)[3] == -1
+
+
+def test_deqjl_timeline_is_the_exact_solution_of_the_reference_ode(orc):
+    """run_sim_deqjl (spin.jl:1277-1380) hands Vern9 the right-hand side of spin.jl:424-467:
+        d psi/dt = (fq NEGI_H0 + (controls[floor(t dt_inv) mod count] + noise[floor(t noise_dt_inv)]) NEGI_H1) psi.
+    The segment list of spin.deqjl_timeline + the oracle's per-segment exponentials must reproduce an adaptive high-order
+    integration of exactly that right-hand side (scipy DOP853, restarted at the breakpoints so that it keeps its order)."""
+    import scipy.integrate
+
+    spin = _spin()
+    rng = np.random.default_rng(12)
+    H0, H1 = np.pi * np.array(orc_N0()), np.pi * np.array(orc_N1())
+    cdi, ndi, gate_time, gates = 10.0, 4.0, 2.37, 3                     # 23 control knots per period, wrap-around of 0.07
+    controls = 0.3 * rng.standard_normal(40)
+    count = int(np.floor(gate_time * cdi))
+    nlen = int(np.ceil(gate_time * gates * ndi)) + 1
+    noise = 0.05 * rng.standard_normal((2, nlen))
+    fq = np.array([FQ, 1.03 * FQ])
+    psi = rng.random((2, 2)) + 1j * rng.random((2, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    psi0 = np.concatenate([psi.real, psi.imag], axis=1)
+    amps, durs, nidx, save_after = spin.deqjl_timeline(controls, cdi, gate_time, gates, ndi)
+    assert abs(durs.sum() - gates * gate_time) < 1e-12 and save_after[-1] == durs.shape[0]
+    fid = orc.mc_timeline(amps, durs, nidx, save_after, spin.GateType.xpiby2, fq, None, noise, psi0)
+
+    def rhs(t, y, s):                                                  # the reference's indexing, literally
+        a = controls[int(np.floor(t * cdi)) % count] + noise[s, int(np.floor(t * ndi))]
+        return (fq[s] * H0 + a * H1) @ y
+
+    edges = np.concatenate([[0.0], np.cumsum(durs)])
+    G = np.array(spin.GATES[spin.GateType.xpiby2])
+    for s in range(2):
+        y = psi0[s].copy()
+        want = [1.0]
+        k = 0
+        for j in range(durs.shape[0]):
+            tm = 0.5 * (edges[j] + edges[j + 1])                       # constant on the segment: evaluate the indices at its midpoint
+            sol = scipy.integrate.solve_ivp(lambda t, y: rhs(tm, y, s), (edges[j], edges[j + 1]), y, method="DOP853", rtol=1e-13, atol=1e-14)
+            y = sol.y[:, -1]
+            if j + 1 == save_after[k]:
+                k += 1
+                c = y[:2] + 1j * y[2:]
+                tgt = np.linalg.matrix_power(G, k % 4) @ (psi0[s, :2] + 1j * psi0[s, 2:])
+                want.append(abs(np.vdot(tgt, c)) ** 2)
+        assert np.max(np.abs(fid[s] - np.array(want))) < 1e-10
+    # the timeline indices are the reference's: spot-check interior times of every segment
+    for j in rng.integers(0, durs.shape[0], 50):
+        t = edges[j] + rng.uniform(0.05, 0.95) * durs[j]
+        assert amps[j] == controls[int(np.floor(t * cdi)) % count] and nidx[j] == int(np.floor(t * ndi))
