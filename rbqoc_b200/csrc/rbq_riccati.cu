@@ -19,7 +19,8 @@
 
 namespace rbq {
 
-constexpr int BP_THREADS = 256;
+constexpr int BP_WARPS_LARGE = 8;    // warps per problem: 8 for n > 16, 1 (no block-wide barriers at all) for the small models
+constexpr int BP_WARPS_SMALL = 1;
 constexpr int BP_MAX_M = 4;
 
 RBQ_DEV void cp_async8(double* smem_dst, const double* gsrc) {
@@ -62,10 +63,15 @@ RBQ_DEV void dmma884(double& c0, double& c1, double a, double b) {
 }
 constexpr int BP_MAX_TILES = 9;        // 8-row tiles of a column strip: (64 + 4 + 7) / 8
 
-__global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const BackwardArgs a) {
+// barrier among the warps that share a problem: a real one for the 8-warp form, a warp barrier for the 1-warp form
+template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __syncthreads(); }
+template <int NW_> RBQ_DEV bool bp_sync_or(bool pred) { return NW_ == 1 ? __any_sync(0xffffffffu, pred) != 0 : __syncthreads_or(pred) != 0; }
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel(const BackwardArgs a) {
+    constexpr int BP_THREADS = 32 * NW;
     extern __shared__ __align__(16) double sm[];
     const int n = a.n, m = a.m, nm = n + m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int NW = BP_THREADS / 32;
     const int n4 = up4(n), n8 = up8(n), q8 = up8(nm + 1), ld = n8 + 4, ldg = q8 + 4;
     const int cs = nm;                 // spare column: G(:, cs) = [A B]' s + e, i.e. the gradient g rides in the second product
     const int64_t N = a.N, b = blockIdx.x;
@@ -92,8 +98,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
     // zero everything once (the padding is never written again), then the terminal value function
     const int total = ld * n4 + n8 + 2 * ld * q8 + ldg * q8;
     for (int i = tid; i < total; i += BP_THREADS) sm[i] = 0.0;
-    if (tid == 0) { dv_s[0] = 0.0; dv_s[1] = 0.0; }
-    __syncthreads();
+    if (tid == BP_THREADS - 1) { dv_s[0] = 0.0; dv_s[1] = 0.0; }
+    bp_sync<NW>();
     for (int j = wid; j < n; j += NW)
         for (int i = lane; i < n; i += 32)
             S[j * ld + i] = Exxg[(N - 1) * (int64_t)(n * n) + (i >= j ? j * n + i : i * n + j)];   // lower triangle, mirrored
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
 #endif
     for (int64_t k = N - 2; k >= 0; --k) {
         cp_async_wait_all();
-        __syncthreads();                                           // AB_k, S, sv visible; G and g are free again
+        bp_sync<NW>();                                             // AB_k, S, sv visible; G and g are free again
         BP_PROF(0)
         stage_cost(k);
         // ---- T = S [A B]: warp -> one 8-column strip, all row tiles; A fragments from S (symmetric), B fragments from [A B] ----
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
                 }
         }
         cp_async_wait_all();                                       // this thread's share of the cost blocks has landed ...
-        __syncthreads();                                           // ... and everybody's, together with T
+        bp_sync<NW>();                                             // ... and everybody's, together with T
         BP_PROF(1)
         // ---- G += [A B]' T: warp -> one 8-column strip of G; A fragments are columns of [A B] read along the contraction ----
         for (int jt = wid; jt < ctiles; jt += NW) {
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         }
         BP_PROF(2)
         BP_PROF(3)
-        __syncthreads();
+        bp_sync<NW>();
         BP_PROF(4)
         // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
         bool ok = true;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
             }
         }
         BP_PROF(5)
-        if (__syncthreads_or(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
+        if (bp_sync_or<NW>(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
         BP_PROF(6)
         // the Jacobian block is no longer needed: fetch the next one behind the value update
         if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
@@ -335,8 +341,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
             }
         }
         BP_PROF(9)
-        if (tid >= BP_THREADS - 64 && tid - (BP_THREADS - 64) < n) {
-            const int i = tid - (BP_THREADS - 64);
+        for (int i = BP_THREADS - 1 - tid; i < n; i += BP_THREADS) {   // dealt from the last thread down: the first warps carry the tail of the pass above
             double v = g[i];
             for (int p = 0; p < m; ++p) {
                 double qd = g[n + p];                                      // Qu + Quu d
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
             }
             sv[i] = v;                                                    // sv is not read again before the next knot
         }
-        if (tid == 32) {
+        if (tid == BP_THREADS - 1) {
             double d0 = 0.0, d1 = 0.0;
             for (int p = 0; p < m; ++p) {
                 d0 = fma(dk[p], g[n + p], d0);
@@ -360,8 +365,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1) backward_pass_kernel(const Back
         // the barrier at the top of the loop orders these writes against the next knot's reads
     }
     cp_async_wait_all();
-    __syncthreads();
-    if (tid == 0) {
+    bp_sync<NW>();
+    if (tid == BP_THREADS - 1) {
         a.dV[2 * b] = dv_s[0]; a.dV[2 * b + 1] = dv_s[1];
         a.fail[b] = bad;
     }
@@ -377,10 +382,23 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
                          int reg_type, double* d_K, double* d_d, double* d_dV, long long* d_fail) {
     const size_t smem = backward_pass_smem(n, m);
     if (smem > 227 * 1024) return RBQ_E_SIZE;
-    cudaError_t e = cudaFuncSetAttribute(backward_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     BackwardArgs a{n, m, N, B, d_AB, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, rho, reg_type, d_K, d_d, d_dV, d_fail};
-    backward_pass_kernel<<<(unsigned)B, BP_THREADS, smem, h->stream>>>(a);
+    // n <= 16 (spin13, spin15, spin11 up to first order) in large batches: one warp per problem, warp barriers only, eight
+    // problems resident per SM.  Measured at n = 11, 1001 knots: one problem takes 7.3 ms as one warp against 2.7 ms as eight
+    // (more serial work per lane), but 592 problems take 7.3 ms against 10.7 ms -- so the warp form is used from ~2.5 problems
+    // per SM upwards.  RBQ_BP_WARPS=1 / 8 forces a form (A/B measurements, tests).
+    bool small = n <= 16 && B * 2 > (int64_t)h->sm_count * 5;
+    if (const char* e = getenv("RBQ_BP_WARPS")) small = n <= 16 && atoi(e) == 1;
+    cudaError_t e;
+    if (small) {
+        e = cudaFuncSetAttribute(backward_pass_kernel<BP_WARPS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        backward_pass_kernel<BP_WARPS_SMALL><<<(unsigned)B, 32 * BP_WARPS_SMALL, smem, h->stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(backward_pass_kernel<BP_WARPS_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        backward_pass_kernel<BP_WARPS_LARGE><<<(unsigned)B, 32 * BP_WARPS_LARGE, smem, h->stream>>>(a);
+    }
     h->launches++;
     return (int)cudaGetLastError();
 }

@@ -67,3 +67,28 @@ def test_backward_pass_batch_failure_flags_and_jacobian_layout(engine):
     with pytest.raises(Exception):
         engine.backward_pass(np.zeros((3, 65, 70)), np.zeros((4, 65, 65)), np.zeros((4, 65)), np.zeros((3, 5, 5)), np.zeros((3, 5, 65)),
                              np.zeros((3, 5)))
+
+
+def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
+    """n <= 16 in large batches runs one warp per problem (warp barriers only); same recursion, same tolerance, and both forms
+    agree with each other to rounding."""
+    from oracle import riccati
+
+    rng = np.random.default_rng(77)
+    for n, m, N in ((11, 1, 140), (12, 2, 60), (16, 3, 25), (3, 1, 9)):
+        A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
+        st = lambda x: np.stack([x] * 3)
+        monkeypatch.setenv("RBQ_BP_WARPS", "1")
+        K1, d1, dV1, f1 = engine.backward_pass(st(AB), st(Q), st(q), st(R), st(Eux), st(r), rho=0.2, reg_type=rbq.REG_STATE)
+        monkeypatch.setenv("RBQ_BP_WARPS", "8")
+        K8, d8, dV8, f8 = engine.backward_pass(st(AB), st(Q), st(q), st(R), st(Eux), st(r), rho=0.2, reg_type=rbq.REG_STATE)
+        monkeypatch.delenv("RBQ_BP_WARPS")
+        Kr, dr, dVr, fr = riccati.backward_pass(AB, Q, q, R, Eux, r, rho=0.2, reg_type=rbq.REG_STATE)
+        assert list(f1) == list(f8) == [-1] * 3 and fr == -1
+        for K, d, dV in ((K1, d1, dV1), (K8, d8, dV8)):
+            assert _rel(K[1], Kr) < 1e-10 and _rel(d[2], dr) < 1e-10 and np.allclose(dV[0], dVr, rtol=1e-10)
+    # a failing problem in the warp form
+    A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, 30, 11, 1)
+    R[12] = -1e3
+    monkeypatch.setenv("RBQ_BP_WARPS", "1")
+    assert engine.backward_pass(AB, Q, q, R, Eux, r)[3] == 12
