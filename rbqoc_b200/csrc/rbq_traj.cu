@@ -225,7 +225,24 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
                    const double* d_U, const double* d_dt, double* d_X) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
-    if (B <= WARP_ROLLOUT_MAX) {
+    const int fam0 = family(p.model_id);
+    const bool independent_blocks = fam0 == RBQ_MODEL_SPIN13 || fam0 == RBQ_MODEL_SPIN15 || fam0 == RBQ_MODEL_SPIN12;
+    const char* pk = getenv("RBQ_ROLLOUT_PACKED");
+    // measured (tools/proto/rollout_batch.py, 1001 knots): spin13 4096 / 32768 trajectories 0.33 / 2.3 ms packed against
+    // 0.60 / 4.2 ms one warp each; spin12 0.50 against 0.55 ms at 4096 but 6.6 against 3.9 ms at 32768 (43 doubles per
+    // knot leave as scattered 32-byte stores), so the 10-block models switch back above 8192
+    const bool packed_default = B >= 16 && (fam0 != RBQ_MODEL_SPIN12 || B <= 8192);
+    if (independent_blocks && (pk ? atoi(pk) != 0 : packed_default)) {
+        // one thread per (trajectory, block): all lanes busy (see packed_rollout_kernel); 32-thread blocks spread small
+        // batches over the SMs
+        WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
+        const int nb = fam0 == RBQ_MODEL_SPIN12 ? 10 : 2;
+        const int pt = 32;
+        const unsigned blocks = (unsigned)((B * nb + pt - 1) / pt);
+        if (fam0 == RBQ_MODEL_SPIN13) packed_rollout_kernel<RBQ_MODEL_SPIN13><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
+        else if (fam0 == RBQ_MODEL_SPIN15) packed_rollout_kernel<RBQ_MODEL_SPIN15><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
+        else packed_rollout_kernel<RBQ_MODEL_SPIN12><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
+    } else if (B <= WARP_ROLLOUT_MAX) {
         WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
 #define CALL(M) warp_rollout_kernel<M, false><<<(unsigned)B, 32, 0, h->stream>>>(a)
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)

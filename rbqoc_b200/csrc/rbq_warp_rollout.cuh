@@ -318,4 +318,63 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
     }
 }
 
+// Batches of open-loop rollouts for the models whose 4-real blocks evolve independently (spin13 / spin15: 2 blocks, spin12 /
+// spin18: 10): ONE THREAD per (trajectory, block), the control chain carried redundantly.  The warp-per-trajectory kernel
+// above keeps 2 (10) of 32 lanes busy while every FP64 instruction still occupies the pipe for the whole warp; here all lanes
+// work, the arithmetic per block is the same expression by expression, so the states are bit-identical.
+template <int MODEL>
+__global__ void __launch_bounds__(128) packed_rollout_kernel(const WarpRolloutArgs a, int nb, int threads) {
+    const rbq_model_params& p = a.p;
+    const int64_t gid = (int64_t)blockIdx.x * threads + threadIdx.x;
+    const int64_t tr = gid / nb;
+    const int blk = (int)(gid - tr * nb);
+    if (tr >= a.count) return;
+    const int n = a.n, m = a.m;
+    const int64_t N = a.N;
+    int off;
+    double f = p.fq, da_l = 0.0;
+    if (MODEL == RBQ_MODEL_SPIN12) {
+        if (blk < 2) off = 4 * blk;
+        else {
+            off = 11 + 4 * (blk - 2);
+            const int grp = (blk - 2) >> 2;
+            if (p.model_id == RBQ_MODEL_SPIN12) f = p.fq_samples[grp];
+            else da_l = grp == 0 ? p.namp : -p.namp;
+        }
+    } else off = 4 * blk;
+    const int cb = 8;
+    const double* __restrict__ x0 = a.x0 + tr * n;
+    const double* __restrict__ Uin = a.U + tr * (N - 1) * m;
+    double* __restrict__ X = a.X + tr * N * n;
+    double psi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { psi[i] = x0[off + i]; X[off + i] = psi[i]; }
+    double ci = x0[cb], ca = x0[cb + 1], cd = x0[cb + 2];
+    const bool DA = MODEL == RBQ_MODEL_SPIN15 && p.decay_aware;
+    const bool TO = MODEL == RBQ_MODEL_SPIN15 && p.time_optimal;
+    double gacc = DA ? x0[11] : 0.0;
+    if (blk == 0) { X[cb] = ci; X[cb + 1] = ca; X[cb + 2] = cd; if (DA) X[11] = gacc; }
+    // the next knot's control and dt are fetched one step ahead (nothing else hides the load in a small batch)
+    double u0_n = 0.0, u1_n = 0.0, dt_n = 0.0;
+    if (N > 1) { u0_n = Uin[0]; if (TO) u1_n = Uin[1]; dt_n = a.dt[0]; }
+    for (int64_t k = 0; k + 1 < N; ++k) {
+        const double u0 = u0_n;
+        const double dt = TO ? u1_n * u1_n : dt_n;
+        if (k + 2 < N) { u0_n = Uin[(k + 1) * m]; if (TO) u1_n = Uin[(k + 1) * m + 1]; dt_n = a.dt[k + 1]; }
+        double* Xn = X + (k + 1) * n;
+        const Prop<double> E = prop_of<double, double>(f, ca + da_l, dt);
+        const double w0 = psi[0], w1 = psi[1], w2 = psi[2], w3 = psi[3];
+        prop_apply<double>(E, w0, w1, w2, w3, psi[0], psi[1], psi[2], psi[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Xn[off + i] = psi[i];
+        if (DA) {
+            gacc = fma(1.0 / t1_interp<double>(ca, 1.0), dt, gacc);
+            if (blk == 0) Xn[11] = gacc;
+        }
+        const double ni = fma(ca, dt, ci), na = fma(cd, dt, ca), nd = fma(u0, dt, cd);
+        ci = ni; ca = na; cd = nd;
+        if (blk == 0) { Xn[cb] = ci; Xn[cb + 1] = ca; Xn[cb + 2] = cd; }
+    }
+}
+
 }  // namespace rbq

@@ -384,3 +384,23 @@ def test_error_codes(engine):
     out = engine.discrete_dynamics(p, x, np.zeros(1), 0.0, 0.1)
     assert np.all(np.isnan(out[:10]))
     assert isinstance(rbqoc_b200.RbqError(-1, "x"), RuntimeError)
+
+
+@pytest.mark.parametrize("name,model", [mm for mm in MODELS if mm[1].params.model_id in (13, 15, 12, 18)], ids=lambda v: v if isinstance(v, str) else "")
+def test_packed_batch_rollout_equals_warp_rollout(engine, oracle, name, model, monkeypatch):
+    """Batches of the independent-block models run one thread per (trajectory, block) instead of one warp per trajectory: the
+    same expressions per block, so the same bits; and the oracle's rollout within the usual tolerance."""
+    rng = np.random.default_rng(_seed(name, 31))
+    B, N = 37, 120
+    dt = rng.choice([0.1, 0.01], N - 1)
+    x0 = np.stack([_random_point(model, rng)[0] for _ in range(B)])
+    U = rng.uniform(-2e-3, 2e-3, (B, N - 1, model.m))
+    if model.params.model_id == 15 and model.params.time_optimal:
+        U[:, :, 1] = rng.uniform(0.25, 0.35, (B, N - 1))
+    monkeypatch.setenv("RBQ_ROLLOUT_PACKED", "0")
+    Xw = engine.rollout(model.params, x0, U, dt)
+    monkeypatch.setenv("RBQ_ROLLOUT_PACKED", "1")
+    Xp = engine.rollout(model.params, x0, U, dt)
+    assert np.array_equal(Xw, Xp), name
+    Xr = oracle.rollout(model.params, x0[:5], U[:5], dt)
+    assert _relerr(Xp[:5], Xr) < 5e-12, name
