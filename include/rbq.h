@@ -139,6 +139,11 @@ int rbq_set_sweep_centre(rbq_handle* h, double fq0, double da0);
  * chunked sweeps overlap upload, compute and download.  Free with rbq_host_free. */
 int rbq_host_alloc(rbq_handle* h, int64_t bytes, void** out);
 int rbq_host_free(rbq_handle* h, void* ptr);
+/* Page-lock (and map for the device) memory the caller already owns -- e.g. a Julia Array that is reused across calls --
+ * so that rbq_mc_static can read it in place (zero-copy form) and the other host-pointer calls copy at full PCIe rate.
+ * cudaHostRegister / cudaHostUnregister underneath; the range must stay allocated until it is unregistered. */
+int rbq_host_register(rbq_handle* h, void* ptr, int64_t bytes);
+int rbq_host_unregister(rbq_handle* h, void* ptr);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`). */
 int64_t rbq_launch_count(const rbq_handle* h);
 

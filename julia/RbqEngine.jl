@@ -275,6 +275,10 @@ function backward_pass(AB::Array{Float64,4}, Exx::Array{Float64,4}, Ex::Array{Fl
     return K, d, dV, failed
 end
 
+"Page-lock a Julia array in place so that mc_static reads it over PCIe directly (zero-copy); unregister before it is freed."
+host_register(A::Array) = check(ccall((:rbq_host_register, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), handle().ptr, A, sizeof(A)), "rbq_host_register")
+host_unregister(A::Array) = check(ccall((:rbq_host_unregister, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, A), "rbq_host_unregister")
+
 "Performance hint for mc_static: the (qubit frequency, amplitude offset) the explicit samples scatter around (default FQ, 0)."
 set_sweep_centre(fq0::Real, da0::Real=0.0) =
     check(ccall((:rbq_set_sweep_centre, LIB), Cint, (Ptr{Cvoid}, Float64, Float64), handle().ptr, fq0, da0), "rbq_set_sweep_centre")

@@ -87,6 +87,8 @@ SIGNATURES = {
     "rbq_set_sweep_centre": (C.c_int, [_P, _D, _D]),
     "rbq_synchronize": (C.c_int, [_P]),
     "rbq_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
+    "rbq_host_register": (C.c_int, [_P, _P, _I64]),
+    "rbq_host_unregister": (C.c_int, [_P, _P]),
     "rbq_host_free": (C.c_int, [_P, _P]),
     "rbq_launch_count": (_I64, [_P]),
     "rbq_state_dim": (C.c_int, [_MP]),

@@ -172,6 +172,18 @@ int rbq_host_alloc(rbq_handle* h, int64_t bytes, void** out) {
     CK(cudaMallocHost(out, (size_t)bytes));
     return RBQ_OK;
 }
+int rbq_host_register(rbq_handle* h, void* ptr, int64_t bytes) {
+    ENTER(h);
+    if (!ptr) return fail(h, RBQ_E_NULL, "rbq_host_register: null pointer");
+    if (bytes <= 0) return fail(h, RBQ_E_SIZE, "rbq_host_register: bytes=%lld", (long long)bytes);
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RBQ_OK;
+}
+int rbq_host_unregister(rbq_handle* h, void* ptr) {
+    ENTER(h);
+    if (ptr) CK(cudaHostUnregister(ptr));
+    return RBQ_OK;
+}
 int rbq_host_free(rbq_handle* h, void* ptr) {
     ENTER(h);
     if (ptr) CK(cudaFreeHost(ptr));

@@ -92,6 +92,13 @@ class Engine:
         self._pinned.append(ptr)
         return arr
 
+    def host_register(self, arr: np.ndarray):
+        """Page-lock a numpy array in place (rbq_host_register); pair with host_unregister before the array is freed."""
+        self._ck(self._lib.rbq_host_register(self._h, arr.ctypes.data_as(C.c_void_p), arr.nbytes), "rbq_host_register")
+
+    def host_unregister(self, arr: np.ndarray):
+        self._ck(self._lib.rbq_host_unregister(self._h, arr.ctypes.data_as(C.c_void_p)), "rbq_host_unregister")
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.rbq_launch_count(self._h))

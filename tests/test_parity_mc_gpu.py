@@ -562,3 +562,27 @@ def test_run_sim_deqjl_agrees_with_run_sim_prop_where_the_grids_coincide(engine)
     y = spin.run_sim_deqjl(1, spin.GateType.ypiby2, spin.controls_ypiby2(100.0), 100.0, spin.TTOT_YPIBY2_JL, seed=seeds, engine=engine)
     e = 1 - y["fidelities"][:, -1]
     assert np.all(e < 1e-4) and np.all(e >= -1e-13)            # the sampled Y/2 pulse (zeroed end samples, wrap) is a Y/2 gate to ~1e-5
+
+
+def test_host_register_enables_zero_copy_for_caller_owned_arrays(engine):
+    """rbq_host_register page-locks memory the caller already owns (a Julia Array, a numpy array): the sweep then takes the
+    zero-copy form (one sweep kernel instead of one per chunk) and returns the same bits."""
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    S = 300000                                             # several one-wave chunks in the streamed form
+    fq, da, psi0 = _samples(S, seed=51)
+    fid = np.empty((S, 2))
+    before = engine.launch_count
+    f_s, st_s = engine.mc_static(controls, dt, gate, 1, fq, da, psi0, fid_out=fid)
+    streamed = engine.launch_count - before
+    keep = f_s.copy()
+    for a in (fq, da, psi0, fid):
+        engine.host_register(a)
+    try:
+        before = engine.launch_count
+        f_z, st_z = engine.mc_static(controls, dt, gate, 1, fq, da, psi0, fid_out=fid)
+        zero_copy = engine.launch_count - before
+    finally:
+        for a in (fq, da, psi0, fid):
+            engine.host_unregister(a)
+    assert np.array_equal(f_z, keep) and st_z.sum == st_s.sum
+    assert zero_copy < streamed
