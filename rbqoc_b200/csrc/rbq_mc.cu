@@ -1317,11 +1317,11 @@ __global__ void __launch_bounds__(32) fp64_latency_kernel(int iters, double* __r
 static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, int* minb, int* threads) {
     *spt = 1; *minb = 1; *threads = 256;
     if (algo != RBQ_ALGO_SU2) return;
-    int v = 161;   // measured best of the compiled variants (tools/tune_mc.py): 1 sample per thread, 128-thread blocks, 6 per SM
+    int v = 171;   // measured best of the compiled variants (tools/tune_mc.py, tools/proto/bv.sh): 1 sample per thread, 128-thread blocks, 7 per SM
     if (const char* e = getenv("RBQ_MC_VARIANT")) v = atoi(e);
     *spt = v / 100; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
-    const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 8)));
-    if (!ok) { *spt = 1; *minb = 6; *threads = 128; }
+    const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 7 || *minb == 8)));
+    if (!ok) { *spt = 1; *minb = 7; *threads = 128; }
     // small sweeps: one sample per thread so that every SM gets blocks
     if (S < (int64_t)sm_count * 4 * *threads * *spt) *spt = 1;
 }
@@ -1365,9 +1365,9 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
         switch (spt * 100 + minb * 10 + threads / 128) {
         case 112: RBQ_GO(1, 1, 256); break; case 122: RBQ_GO(1, 2, 256); break; case 132: RBQ_GO(1, 3, 256); break; case 142: RBQ_GO(1, 4, 256); break;
         case 212: RBQ_GO(2, 1, 256); break; case 222: RBQ_GO(2, 2, 256); break; case 232: RBQ_GO(2, 3, 256); break; case 242: RBQ_GO(2, 4, 256); break;
-        case 141: RBQ_GO(1, 4, 128); break; case 161: RBQ_GO(1, 6, 128); break; case 181: RBQ_GO(1, 8, 128); break;
+        case 141: RBQ_GO(1, 4, 128); break; case 161: RBQ_GO(1, 6, 128); break; case 171: RBQ_GO(1, 7, 128); break; case 181: RBQ_GO(1, 8, 128); break;
         case 241: RBQ_GO(2, 4, 128); break; case 261: RBQ_GO(2, 6, 128); break; case 281: RBQ_GO(2, 8, 128); break;
-        default: RBQ_GO(1, 6, 128); break;
+        default: RBQ_GO(1, 7, 128); break;
         }
     } else if (algo == RBQ_ALGO_PADE) {
         mc_static_kernel<RBQ_ALGO_PADE, 1, 1, 256><<<blocks, 256, 0, h->stream>>>(a);
