@@ -44,9 +44,9 @@ FP64_INSTR_PER_STEP_SU2 = 14.0 if TABLE_CLASS else 18.0
 FP64_INSTR3_PER_STEP_SU2 = 11.0 if TABLE_CLASS else 8.0
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default sizes, from the
-# `ncu --set full` capture summarised in profiles/r1b_ncu_mc_static_full.csv (50.44 MB read + 0.38 MB written: the 16 MB of
+# `ncu --set full` capture summarised in profiles/r1b_ncu_mc_static_full.csv (50.44 MB read + 1.79 MB written: the 16 MB of
 # fidelities stay in the 126 MB L2); algorithmic bytes are 48 MB in + 16 MB out
-NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_435_072 + 383_232
+NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_435_072 + 1_789_952
 
 
 def sample_clocks(stop, out):
