@@ -174,6 +174,12 @@ int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N,
                            const double* Xref, const double* Uref, const double* K,
                            const double* d, const double* dt, int64_t nalpha,
                            const double* alphas, double* X, double* Uout);
+/* device-pointer variant (asynchronous on the handle's stream): with rbq_jacobians_dev and rbq_backward_pass_dev an
+ * iLQR iteration keeps X, U, the Jacobians and the gains on the device */
+int rbq_rollout_closedloop_dev(rbq_handle* h, const rbq_model_params* p, int64_t N,
+                           const double* d_Xref, const double* d_Uref, const double* K,
+                           const double* d, const double* dt, int64_t nalpha,
+                           const double* alphas, double* X, double* Uout);
 /* jacobians: K independent knots (a whole trajectory, or a batch of them, flattened).
  * X[K*n], U[K*m], dt[K], AB[K*n*(n+m)] (each block column-major).  t[K] = the knot times z.t; may be NULL (= 0) for
  * every model but spin25, the only one whose dynamics read their time argument (spin25.jl:196). */

@@ -97,6 +97,7 @@ SIGNATURES = {
     "rbq_discrete_jacobian": (C.c_int, [_P, _MP, _P, _P, _D, _D, _P]),
     "rbq_rollout": (C.c_int, [_P, _MP, _I64, _I64, _P, _P, _P, _P]),
     "rbq_rollout_closedloop": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "rbq_rollout_closedloop_dev": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "rbq_jacobians": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P]),
     "rbq_rollout_dev": (C.c_int, [_P, _MP, _I64, _I64, _P, _P, _P, _P]),
     "rbq_jacobians_dev": (C.c_int, [_P, _MP, _I64, _P, _P, _P, _P, _P]),

@@ -263,6 +263,18 @@ int rbq_rollout_closedloop(rbq_handle* h, const rbq_model_params* p, int64_t N, 
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
 }
+int rbq_rollout_closedloop_dev(rbq_handle* h, const rbq_model_params* p, int64_t N, const double* d_Xref, const double* d_Uref,
+                               const double* K, const double* d, const double* dt, int64_t nalpha, const double* alphas,
+                               double* X, double* Uout) {
+    ENTER(h);
+    if (!p || !d_Xref || !d_Uref || !K || !d || !dt || !alphas || !X || !Uout) return fail(h, RBQ_E_NULL, "rbq_rollout_closedloop_dev: null pointer");
+    const int n = model_state_dim(*p), m = model_control_dim(*p);
+    if (n < 0 || m < 0) return fail(h, RBQ_E_MODEL, "rbq_rollout_closedloop_dev: bad model parameters");
+    if (N < 2 || nalpha < 0) return fail(h, RBQ_E_SIZE, "rbq_rollout_closedloop_dev: N=%lld nalpha=%lld", (long long)N, (long long)nalpha);
+    if (nalpha == 0) return RBQ_OK;
+    CKL(launch_closedloop(h, *p, N, d_Xref, d_Uref, K, d, dt, nalpha, alphas, X, Uout));
+    return RBQ_OK;
+}
 int rbq_jacobians(rbq_handle* h, const rbq_model_params* p, int64_t K, const double* X, const double* U, const double* t,
                   const double* dt, double* AB) {
     ENTER(h);

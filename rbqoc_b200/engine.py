@@ -198,6 +198,11 @@ class Engine:
     def rollout_dev(self, p, B, N, x0, U, dt, X):
         self._ck(self._lib.rbq_rollout_dev(self._h, C.byref(p), B, N, _ptr(x0), _ptr(U), _ptr(dt), _ptr(X)), "rbq_rollout_dev")
 
+    def rollout_closedloop_dev(self, p, N, Xref, Uref, K, d, dt, nalpha, alphas, X, Uout):
+        """Device tensors throughout; K column-major m x n per knot, as backward_pass_dev writes it."""
+        self._ck(self._lib.rbq_rollout_closedloop_dev(self._h, C.byref(p), int(N), _ptr(Xref), _ptr(Uref), _ptr(K), _ptr(d), _ptr(dt),
+                                                      int(nalpha), _ptr(alphas), _ptr(X), _ptr(Uout)), "rbq_rollout_closedloop_dev")
+
     def jacobians_dev(self, p, K, X, U, dt, AB, t=None):
         self._ck(self._lib.rbq_jacobians_dev(self._h, C.byref(p), K, _ptr(X), _ptr(U), _ptr(t), _ptr(dt), _ptr(AB)), "rbq_jacobians_dev")
 

@@ -70,3 +70,49 @@ def test_ilqr_iterations_on_spin13_decrease_the_cost_as_predicted(engine):
     assert J < 0.2 * J0                                                # the loop makes real progress towards the Z/2 target
     # the closed-loop states ARE a rollout of the closed-loop controls
     assert np.max(np.abs(spin.rollout(model, x0, U, dt, engine=engine) - X)) < 1e-12
+
+
+def test_device_resident_iteration_matches_host_pointer_iteration(engine):
+    """One iLQR iteration with every array on the device (rbq_jacobians_dev -> rbq_backward_pass_dev ->
+    rbq_rollout_closedloop_dev on a torch stream): the Jacobians and gains never cross PCIe, and the candidates are the bits
+    the host-pointer calls return."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    model = spin.Spin12Model()
+    n, m, N, dt = model.n, model.m, 181, 0.1                         # spin12.jl defaults: T = 18 ns
+    rng = np.random.default_rng(5)
+    U = 1e-3 * rng.standard_normal((N - 1, m))
+    dts = np.full(N - 1, dt)
+    X = spin.rollout(model, spin.spin12_x0(), U, dt, engine=engine)
+    Qd = np.ones(n)
+    xf = X[-1] * 0.9
+    Exx = np.tile(np.diag(Qd), (N, 1, 1)); Ex = (X - xf) * Qd
+    Euu = np.full((N - 1, 1, 1), 0.1); Eux = np.zeros((N - 1, m, n)); Eu = 0.1 * U
+    alphas = 0.5 ** np.arange(4)
+    # host-pointer reference of the same iteration
+    AB = spin.dynamics_expansion(model, X, U, dt, engine=engine)
+    K, d, dV, fail = engine.backward_pass(AB, Exx, Ex, Euu, Eux, Eu, rho=1e-3)
+    assert fail == -1
+    Xc, Uc = engine.rollout_closedloop(model.params, X, U, K, d, dts, alphas)
+    # device-resident
+    eng = rbq.Engine(0)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    col = lambda x: np.ascontiguousarray(np.swapaxes(x, -1, -2))
+    with torch.cuda.stream(stream):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dX, dU, ddt, dal = t(X), t(U), t(dts), t(alphas)
+        dExx, dEx, dEuu, dEux, dEu = t(col(Exx)), t(Ex), t(col(Euu)), t(col(Eux)), t(Eu)
+        dAB = torch.empty(N - 1, n * (n + m), dtype=torch.float64, device=dev)
+        dK = torch.empty(N - 1, n * m, dtype=torch.float64, device=dev); dd = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
+        ddV = torch.empty(2, dtype=torch.float64, device=dev); dfl = torch.empty(1, dtype=torch.int64, device=dev)
+        dXc = torch.empty(4, N, n, dtype=torch.float64, device=dev); dUc = torch.empty(4, N - 1, m, dtype=torch.float64, device=dev)
+    stream.synchronize()
+    eng.jacobians_dev(model.params, N - 1, dX, dU, ddt, dAB)          # reads the first N-1 states of X in place
+    eng.backward_pass_dev(n, m, N, 1, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd, ddV, dfl)
+    eng.rollout_closedloop_dev(model.params, N, dX, dU, dK, dd, ddt, 4, dal, dXc, dUc)
+    eng.synchronize()
+    assert int(dfl.cpu()[0]) == -1
+    assert np.array_equal(dK.cpu().numpy().reshape(N - 1, n, m).transpose(0, 2, 1), K)
+    assert np.array_equal(dXc.cpu().numpy(), Xc) and np.array_equal(dUc.cpu().numpy(), Uc)
+    eng.close()
