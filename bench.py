@@ -186,6 +186,17 @@ def other_configs(eng, rbq, spin, torch, dev):
             eng.synchronize()
 
         out[name]["jacobians_plus_backward_pass_dev_ms"] = timed_host(expansion_and_pass)
+        # ... and the whole hot path of one iLQR iteration on the device: expansion, backward pass, 8 line-search candidates
+        dXfull, dal = dd(X), dd(alphas)
+        dXc = torch.empty(8, N, n, dtype=torch.float64, device=dev); dUc = torch.empty(8, N - 1, m, dtype=torch.float64, device=dev)
+
+        def iteration_dev():
+            eng.jacobians_dev(model.params, N - 1, dXfull, dU, ddt, dAB)
+            eng.backward_pass_dev(n, m, N, 1, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
+            eng.rollout_closedloop_dev(model.params, N, dXfull, dU, dK, dd_, ddt, 8, dal, dXc, dUc)
+            eng.synchronize()
+
+        out[name]["ilqr_iteration_dev_ms"] = timed_host(iteration_dev)
         # BASELINE's metric read literally (rollout + Jacobians): a batch of independent problems, device resident.  One
         # trajectory-step = one 4-real iso state vector advanced one knot (spin13 carries 2, spin12 10, spin30 13 per knot).
         Bt = {"spin13": 4096, "spin12": 1024, "spin30": 512}[name]
