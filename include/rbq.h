@@ -342,7 +342,8 @@ int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs,
  * of N knots, state dimension n <= 64, control dimension m <= 4, one thread block per problem.  It consumes the Jacobian
  * blocks exactly as rbq_jacobians(_dev) writes them, so they never leave the device between the expansion and the pass.
  *   AB  [B][N-1][n*(n+m)]  column-major n x (n+m) blocks [A_k B_k]
- *   Exx [B][N][n*n]        cost Hessian blocks, column-major, symmetric (the lower triangle is read); knot N-1 = terminal
+ *   Exx [B][N][n*n]        cost Hessian blocks, column-major, symmetric with BOTH triangles stored (even n copies whole
+ *                          columns by TMA; odd n and the terminal block read the lower triangle); knot N-1 = terminal
  *   Ex  [B][N][n]          cost gradients
  *   Euu [B][N-1][m*m], Eux [B][N-1][m*n] (column-major m x n), Eu [B][N-1][m]
  *   rho, reg_type          Quu_reg = Quu + rho I (RBQ_REG_CONTROL) or Quu + rho B'B, Qux_reg = Qux + rho B'A (RBQ_REG_STATE)

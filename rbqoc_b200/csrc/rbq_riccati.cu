@@ -16,6 +16,7 @@
 #include "rbq_internal.h"
 
 #include "rbq_math.cuh"
+#include "rbq_tma.cuh"
 
 namespace rbq {
 
@@ -49,6 +50,9 @@ struct BackwardArgs {
     double* K; double* d; double* dV; long long* fail;
 };
 
+// staging modes of backward_pass_kernel (template parameter MODE)
+constexpr int BP_TMA_J = 1, BP_TMA_C = 2, BP_DENSE_J = 4;
+
 // Shared-memory layout (doubles), all column-major.  Rows are padded with zeros to a multiple of 8 (the DMMA tile), the
 // contraction length to a multiple of 4; the leading dimensions ld = n8 + 4 and ldg = q8 + 4 are = 4 (mod 8), which makes every
 // fragment load below conflict-free (the four 32-byte pieces a half-warp reads fall into different quarters of the bank window):
@@ -67,7 +71,7 @@ constexpr int BP_MAX_TILES = 9;        // 8-row tiles of a column strip: (64 + 4
 template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __syncthreads(); }
 template <int NW_> RBQ_DEV bool bp_sync_or(bool pred) { return NW_ == 1 ? __any_sync(0xffffffffu, pred) != 0 : __syncthreads_or(pred) != 0; }
 
-template <int NW>
+template <int NW, int MODE>
 __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel(const BackwardArgs a) {
     constexpr int BP_THREADS = 32 * NW;
     extern __shared__ __align__(16) double sm[];
@@ -84,7 +88,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
     double* Kk = G + ldg * q8;         // K(p, j) at j * m + p
     double* QuuK = Kk + BP_MAX_M * n8;
     double* dk = QuuK + BP_MAX_M * n8;
+    double* Qd = dk + BP_MAX_M;        // dense landing zone of the cost Hessian block: n*n + 2 doubles, 16-byte aligned
     __shared__ double dv_s[2];
+    __shared__ __align__(8) uint64_t bar_s[2];       // bulk-copy arrival: [0] Jacobian block, [1] cost Hessian block
 
     const double* ABg = a.AB + b * (N - 1) * (int64_t)(n * nm);
     const double* Exxg = a.Exx + b * N * (int64_t)(n * n);
@@ -98,22 +104,47 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
     // zero everything once (the padding is never written again), then the terminal value function
     const int total = ld * n4 + n8 + 2 * ld * q8 + ldg * q8;
     for (int i = tid; i < total; i += BP_THREADS) sm[i] = 0.0;
-    if (tid == BP_THREADS - 1) { dv_s[0] = 0.0; dv_s[1] = 0.0; }
+    if (tid == BP_THREADS - 1) { dv_s[0] = 0.0; dv_s[1] = 0.0; mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_fence_init(); }
     bp_sync<NW>();
     for (int j = wid; j < n; j += NW)
         for (int i = lane; i < n; i += 32)
             S[j * ld + i] = Exxg[(N - 1) * (int64_t)(n * n) + (i >= j ? j * n + i : i * n + j)];   // lower triangle, mirrored
     for (int i = tid; i < n; i += BP_THREADS) sv[i] = Exg[(N - 1) * (int64_t)n + i];
-    // Staging cost, measured (make EXTRA=-DRBQ_BP_PROFILE): ~270 cycles per cp.async instruction of a warp whatever its width
-    // -- one CTA keeps only ~9 KB in flight, so a 25 KB block is bound by its own latency x bandwidth (2.3 k cycles), not by
-    // instruction issue.  One bulk TMA copy per column is slower still (57 UBLKCP from one warp serialise: 3.8 k cycles); a
-    // single bulk copy needs the unpadded layout (bank conflicts in every fragment load) or a padded-box tensor map.  Issuing
-    // the cost blocks a knot ahead moves this time between phases without shortening the knot, and issuing the copies one
-    // column per contraction step inside the tensor-core loops (double-buffered [A B]) makes it worse (11.5 against 10.0 us per
-    // knot at n = 56): a warp stalls on its cp.async until the copy is accepted, which delays its DMMAs.
+    // Staging cost, measured (make EXTRA=-DRBQ_BP_PROFILE): a warp waits ~270 cycles on every cp.async instruction whatever its
+    // width, so a 25 KB block staged by cp.async costs each warp ~2.3 k cycles in which it issues no DMMA.  Even n (every column
+    // 16-byte aligned in HBM and in the padded layout): one bulk TMA copy per column instead, the columns dealt over the lanes
+    // of all warps (57 copies from a single warp serialise: 3.8 k cycles; spread out, ~0.9 k for the block, which looks like the
+    // TMA unit's request rate), and the small cost blocks through registers (load before the first product, store after it).
+    // That takes the n = 56 knot from 10.0 to 9.3 us.  RBQ_BP_TMA=0 forces the cp.async path (bit 0: Jacobian, bit 1: cost).
+    // A single bulk copy per block needs the unpadded layout (bank conflicts in every fragment load) or a padded-box tensor
+    // map.  Issuing the next Jacobian's copies from the warps the gains leave idle changes nothing (9.31 us), issuing the cost
+    // blocks a knot ahead moves time between phases without shortening the knot, and issuing cp.async
+    // copies one column per contraction step inside the tensor-core loops (double-buffered [A B]) makes it worse (11.5 us).
+    // The staging mode is a template parameter chosen by the launcher (bp_stage_mode): with the choice made at run time
+    // inside one kernel, the mere presence of the unused paths cost 0.3-0.8 us per knot (2.63 -> 3.1 us at n = 11).
+    // BP_DENSE_J: Jacobian block dense in shared memory (leading dimension n) where that keeps the fragment loads off each
+    // other's banks (odd n, n = 4 mod 8): the whole block is then ONE bulk copy.  The rows a tile reads past n belong to the
+    // next column; they meet zero rows / columns of S and T, so they only need to be finite.
+    // BP_TMA_J: padded layout, one bulk copy per column (even n).
+    // BP_TMA_C: cost Hessian block as ONE bulk copy into the dense buffer Qd (the second product's accumulators start from
+    // it; its few loads do not care about banks); a block that starts on an odd double is copied from the double before it.
+    // Small blocks stay on cp.async (a copy or two per thread costs less than the bulk copy's latency, which the short first
+    // product cannot hide: 3.0 against 3.4 us per knot at n = 11).
+    constexpr bool dense_j = (MODE & BP_DENSE_J) != 0, tma_j = (MODE & BP_TMA_J) != 0, tma_c = (MODE & BP_TMA_C) != 0;
+    const int lda = dense_j ? n : ld;
+    const double* Qk = Qd;
     auto stage_jacobian = [&](int64_t k) {
         const double* src = ABg + k * (int64_t)(n * nm);
-        if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
+        if (dense_j) {
+            if (tid == 0) {
+                mbar_expect_tx(&bar_s[0], (uint32_t)(n * nm * sizeof(double)));
+                bulk_g2s(AB, src, (uint32_t)(n * nm * sizeof(double)), &bar_s[0]);
+            }
+        } else if (tma_j) {
+            if (tid == 0) mbar_expect_tx(&bar_s[0], (uint32_t)(n * nm * sizeof(double)));
+            for (int j = wid + NW * lane; j < nm; j += NW * 32)
+                bulk_g2s(AB + j * ld, src + j * n, (uint32_t)(n * sizeof(double)), &bar_s[0]);
+        } else if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {          // every column starts 16-byte aligned
             for (int j = wid; j < nm; j += NW)
                 for (int i = 2 * lane; i < n; i += 64) cp_async16(AB + j * ld + i, src + j * n + i);
         } else {
@@ -127,6 +158,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
         const double* Exxk = Exxg + k * (int64_t)(n * n);
         const double* Euuk = Euug + k * (int64_t)(m * m);
         const double* Euxk = Euxg + k * (int64_t)(m * n);
+        if (tma_c) {
+            const int shift = (int)((reinterpret_cast<uintptr_t>(Exxk) >> 3) & 1);
+            Qk = Qd + shift;
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)(((n * n + shift + 1) & ~1) * sizeof(double));
+                mbar_expect_tx(&bar_s[1], bytes);
+                bulk_g2s(Qd, Exxk - shift, bytes, &bar_s[1]);
+            }
+            return;                                                 // the small blocks travel through registers: extra_src/_store
+        }
         for (int j = wid; j < nm; j += NW)
             for (int i = lane; i < nm; i += 32) {
                 const int lo = i < j ? i : j, hi = i < j ? j : i;                     // (hi, lo) in the lower triangle
@@ -136,6 +177,22 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
         for (int i = tid; i < nm; i += BP_THREADS) cp_async8(g + i, i < n ? Exg + k * (int64_t)n + i : Eug + k * (int64_t)m + (i - n));
         cp_async_commit();
     };
+    // the small cost blocks (Eux, Euu, Ex, Eu: m n + m^2 + n + m <= 2 per thread) as plain loads issued before the first
+    // product and stored after it: no cp.async instruction for a warp to wait on
+    const int n_extra = m * n + m * m + nm;
+    auto extra_src = [&](int e, int64_t k) -> const double* {
+        if (e < m * n) return Euxg + k * (int64_t)(m * n) + e;
+        e -= m * n;
+        if (e < m * m) { const int p = e / m, q = e % m; return Euug + k * (int64_t)(m * m) + (p < q ? p * m + q : q * m + p); }
+        e -= m * m;
+        return e < n ? Exg + k * (int64_t)n + e : Eug + k * (int64_t)m + (e - n);
+    };
+    auto extra_store = [&](int e, double v) {
+        if (e < m * n) { const int x = e / m, u = e % m; G[(n + u) * ldg + x] = v; G[x * ldg + n + u] = v; return; }
+        e -= m * n;
+        if (e < m * m) { G[(n + e / m) * ldg + n + e % m] = v; return; }
+        g[e - m * m] = v;
+    };
     if (N > 1) stage_jacobian(N - 2);
 
     const int rtiles = n8 / 8, ctiles = q8 / 8, ksteps = n4 / 4;
@@ -144,17 +201,24 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
 #ifdef RBQ_BP_PROFILE
     long long tprev = clock64();
 #endif
-    for (int64_t k = N - 2; k >= 0; --k) {
+    uint32_t phase = 0;
+    for (int64_t k = N - 2; k >= 0; --k, phase ^= 1u) {
         cp_async_wait_all();
+        if (tma_j || dense_j) mbar_wait(&bar_s[0], phase);
         bp_sync<NW>();                                             // AB_k, S, sv visible; G and g are free again
         BP_PROF(0)
         stage_cost(k);
+        double ex0 = 0.0, ex1 = 0.0;
+        if (tma_c) {
+            if (tid < n_extra) ex0 = *extra_src(tid, k);
+            if (tid + BP_THREADS < n_extra) ex1 = *extra_src(tid + BP_THREADS, k);
+        }
         // ---- T = S [A B]: warp -> one 8-column strip, all row tiles; A fragments from S (symmetric), B fragments from [A B] ----
         for (int ct = wid; ct < ctiles; ct += NW) {
             double acc[BP_MAX_TILES - 1][2];
 #pragma unroll
             for (int t = 0; t < BP_MAX_TILES - 1; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-            const double* bp = AB + (8 * ct + fr) * ld + fc;
+            const double* bp = AB + (8 * ct + fr) * lda + fc;
             const double* ap = S + fc * ld + fr;
             for (int ks = 0; ks < ksteps; ++ks) {
                 const double bf = bp[4 * ks];
@@ -170,6 +234,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
                 }
         }
         cp_async_wait_all();                                       // this thread's share of the cost blocks has landed ...
+        if (tma_c) {
+            if (tid < n_extra) extra_store(tid, ex0);
+            if (tid + BP_THREADS < n_extra) extra_store(tid + BP_THREADS, ex1);
+            mbar_wait(&bar_s[1], phase);
+        }
         bp_sync<NW>();                                             // ... and everybody's, together with T
         BP_PROF(1)
         // ---- G += [A B]' T: warp -> one 8-column strip of G; A fragments are columns of [A B] read along the contraction ----
@@ -178,16 +247,19 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
 #pragma unroll
             for (int t = 0; t < BP_MAX_TILES; ++t)
                 if (t < ctiles) {
-                    acc[t][0] = G[(8 * jt + 2 * fc) * ldg + 8 * t + fr];
-                    acc[t][1] = G[(8 * jt + 2 * fc + 1) * ldg + 8 * t + fr];
+                    const int r = 8 * t + fr, c = 8 * jt + 2 * fc;                 // one load each, the address selected
+                    const bool dq = tma_c && r < n;
+                    const double* s0 = dq && c < n ? Qk + c * n + r : G + c * ldg + r;
+                    const double* s1 = dq && c + 1 < n ? Qk + (c + 1) * n + r : G + (c + 1) * ldg + r;
+                    acc[t][0] = *s0; acc[t][1] = *s1;
                 }
             const double* bp = (8 * jt + fr == cs) ? sv + fc : T + (8 * jt + fr) * ld + fc;   // column cs of the right factor is s
-            const double* ap = AB + fr * ld + fc;
+            const double* ap = AB + fr * lda + fc;
             for (int ks = 0; ks < ksteps; ++ks) {
                 const double bf = bp[4 * ks];
 #pragma unroll
                 for (int t = 0; t < BP_MAX_TILES; ++t)
-                    if (t < ctiles) dmma884(acc[t][0], acc[t][1], ap[8 * t * ld + 4 * ks], bf);
+                    if (t < ctiles) dmma884(acc[t][0], acc[t][1], ap[8 * t * lda + 4 * ks], bf);
             }
 #pragma unroll
             for (int t = 0; t < BP_MAX_TILES; ++t)
@@ -209,14 +281,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
             const double quu = G[n * ldg + n];
             double quu_reg = quu + a.rho, bb = 0.0;
             if (a.reg_type == RBQ_REG_STATE) {
-                for (int r = 0; r < n; ++r) bb = fma(AB[n * ld + r], AB[n * ld + r], bb);
+                for (int r = 0; r < n; ++r) bb = fma(AB[n * lda + r], AB[n * lda + r], bb);
                 quu_reg = fma(a.rho, bb, quu);
             }
             ok = quu_reg > 0.0;                                                     // also catches NaN
             double rhs = j < n ? G[n * ldg + j] : g[n];                             // Qxu(j): the coalesced half of the symmetric G
             if (j < n && a.reg_type == RBQ_REG_STATE) {
                 double ba = 0.0;
-                for (int r = 0; r < n; ++r) ba = fma(AB[n * ld + r], AB[j * ld + r], ba);
+                for (int r = 0; r < n; ++r) ba = fma(AB[n * lda + r], AB[j * lda + r], ba);
                 rhs = fma(a.rho, ba, rhs);
             }
             // the reference solves through the Cholesky factor: x = (rhs / l) / l with l = sqrt(Quu_reg); one division by
@@ -238,7 +310,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
                         v = G[(n + q) * ldg + (n + p)];
                         if (a.reg_type == RBQ_REG_STATE) {
                             double bb = 0.0;
-                            for (int r = 0; r < n; ++r) bb = fma(AB[(n + p) * ld + r], AB[(n + q) * ld + r], bb);
+                            for (int r = 0; r < n; ++r) bb = fma(AB[(n + p) * lda + r], AB[(n + q) * lda + r], bb);
                             v = fma(a.rho, bb, v);
                         } else if (p == q) v += a.rho;
                     }
@@ -268,7 +340,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
                     v = j < n ? G[(n + p) * ldg + j] : g[n + p];     // Qxu(j, p): the coalesced half of the symmetric G
                     if (j < n && a.reg_type == RBQ_REG_STATE) {
                         double ba = 0.0;
-                        for (int r = 0; r < n; ++r) ba = fma(AB[(n + p) * ld + r], AB[j * ld + r], ba);
+                        for (int r = 0; r < n; ++r) ba = fma(AB[(n + p) * lda + r], AB[j * lda + r], ba);
                         v = fma(a.rho, ba, v);
                     }
                 }
@@ -374,7 +446,29 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
 
 size_t backward_pass_smem(int n, int m) {
     const size_t n4 = (size_t)((n + 3) & ~3), n8 = (size_t)((n + 7) & ~7), q8 = (size_t)((n + m + 8) & ~7), ld = n8 + 4, ldg = q8 + 4;
-    return sizeof(double) * (ld * n4 + n8 + 2 * ld * q8 + ldg * q8 + 2 * BP_MAX_M * n8 + BP_MAX_M);
+    return sizeof(double) * (ld * n4 + n8 + 2 * ld * q8 + ldg * q8 + 2 * BP_MAX_M * n8 + BP_MAX_M + (size_t)n * n + 2);
+}
+
+// staging mode for a problem shape and its buffers (see backward_pass_kernel); RBQ_BP_TMA masks the bits (0 = cp.async only)
+static int bp_stage_mode(int n, int m, const double* d_AB, const double* d_Exx) {
+    const int nm = n + m;
+    int mode = 0;
+    if (n >= 28) {
+        const bool ab16 = (reinterpret_cast<uintptr_t>(d_AB) & 15) == 0, exx16 = (reinterpret_cast<uintptr_t>(d_Exx) & 15) == 0;
+        if (ab16 && ((n * nm) & 1) == 0 && ((n & 1) || (n & 7) == 4)) mode |= BP_DENSE_J;   // every block 16-byte aligned
+        else if (ab16 && (n & 1) == 0) mode |= BP_TMA_J;                                      // every column 16-byte aligned
+        if (exx16 && m * n + m * m + n + m <= 2 * 32 * BP_WARPS_LARGE) mode |= BP_TMA_C;
+    }
+    if (const char* e = getenv("RBQ_BP_TMA")) mode &= atoi(e);
+    return mode;
+}
+
+template <int NW, int MODE>
+static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(backward_pass_kernel<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    backward_pass_kernel<NW, MODE><<<(unsigned)B, 32 * NW, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
@@ -391,16 +485,19 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     if (const char* e = getenv("RBQ_BP_WARPS")) small = n <= 16 && atoi(e) == 1;
     cudaError_t e;
     if (small) {
-        e = cudaFuncSetAttribute(backward_pass_kernel<BP_WARPS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        backward_pass_kernel<BP_WARPS_SMALL><<<(unsigned)B, 32 * BP_WARPS_SMALL, smem, h->stream>>>(a);
+        e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream);
     } else {
-        e = cudaFuncSetAttribute(backward_pass_kernel<BP_WARPS_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        backward_pass_kernel<BP_WARPS_LARGE><<<(unsigned)B, 32 * BP_WARPS_LARGE, smem, h->stream>>>(a);
+        switch (bp_stage_mode(n, m, d_AB, d_Exx)) {
+            case BP_DENSE_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_DENSE_J | BP_TMA_C>(a, B, smem, h->stream); break;
+            case BP_TMA_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C>(a, B, smem, h->stream); break;
+            case BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_C>(a, B, smem, h->stream); break;
+            case BP_DENSE_J: e = bp_launch<BP_WARPS_LARGE, BP_DENSE_J>(a, B, smem, h->stream); break;
+            case BP_TMA_J: e = bp_launch<BP_WARPS_LARGE, BP_TMA_J>(a, B, smem, h->stream); break;
+            default: e = bp_launch<BP_WARPS_LARGE, 0>(a, B, smem, h->stream); break;
+        }
     }
     h->launches++;
-    return (int)cudaGetLastError();
+    return (int)e;
 }
 
 }  // namespace rbq
