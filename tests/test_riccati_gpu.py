@@ -92,3 +92,61 @@ def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
     R[12] = -1e3
     monkeypatch.setenv("RBQ_BP_WARPS", "1")
     assert engine.backward_pass(AB, Q, q, R, Eux, r)[3] == 12
+
+
+@pytest.mark.parametrize("n,N", [(11, 60), (36, 33), (43, 21), (44, 20), (56, 24), (58, 17)])
+def test_backward_pass_staging_modes_and_specialised_shapes_agree(engine, monkeypatch, n, N):
+    """The launcher picks a staging mode (cp.async / bulk TMA copies, dense or padded Jacobian block) and, for the reference
+    models' shapes, a kernel with n known at compile time.  Every choice is the same recursion: all agree with the oracle, on a
+    batch whose second and third problems start on odd doubles when n is odd (the shifted bulk copy of the cost block)."""
+    from oracle import riccati
+
+    rng = np.random.default_rng(900 + n)
+    probs = [_lq_problem(rng, N, n, 1) for _ in range(3)]
+    stack = lambda i: np.stack([p[i] for p in probs])
+    AB, Q, q, R, Eux, r = (stack(i) for i in (2, 3, 4, 5, 6, 8))
+    ref = [riccati.backward_pass(p[2], p[3], p[4], p[5], p[6], p[8], rho=0.11, reg_type=rbq.REG_CONTROL) for p in probs]
+    outs = []
+    for env in ({}, {"RBQ_BP_GENERIC": "1"}, {"RBQ_BP_TMA": "0"}, {"RBQ_BP_TMA": "2"}, {"RBQ_BP_GENERIC": "1", "RBQ_BP_TMA": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs.append(engine.backward_pass(AB, Q, q, R, Eux, r, rho=0.11, reg_type=rbq.REG_CONTROL))
+        for k in env:
+            monkeypatch.delenv(k)
+    for K, d, dV, fail in outs:
+        assert list(fail) == [-1] * 3
+        for b, (Kr, dr, dVr, fr) in enumerate(ref):
+            assert _rel(K[b], Kr) < 1e-10 and _rel(d[b], dr) < 1e-10 and np.allclose(dV[b], dVr, rtol=1e-10)
+
+
+def test_backward_pass_dev_unaligned_buffers_fall_back(engine):
+    """Device buffers that start on an odd double cannot be bulk-copied (16-byte alignment): the launcher must fall back to
+    the cp.async staging, with the same result."""
+    import torch
+    from oracle import riccati
+
+    n, m, N = 56, 1, 12
+    rng = np.random.default_rng(5)
+    A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
+    Kr, dr, dVr, fr = riccati.backward_pass(AB, Q, q, R, Eux, r, rho=0.3, reg_type=rbq.REG_CONTROL)
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0)
+    eng.use_torch_stream()
+
+    def odd(a):     # column-major blocks, placed one double into a fresh allocation
+        flat = np.ascontiguousarray(np.swapaxes(a, -1, -2)).reshape(-1) if a.ndim >= 3 else np.ascontiguousarray(a).reshape(-1)
+        buf = torch.empty(flat.size + 1, dtype=torch.float64, device=dev)
+        buf[1:] = torch.from_numpy(flat).to(dev)
+        assert buf[1:].data_ptr() % 16 == 8
+        return buf[1:]
+
+    K = torch.empty((N - 1) * n * m, dtype=torch.float64, device=dev)
+    d = torch.empty((N - 1) * m, dtype=torch.float64, device=dev)
+    dV = torch.empty(2, dtype=torch.float64, device=dev)
+    fail = torch.empty(1, dtype=torch.int64, device=dev)
+    eng.backward_pass_dev(n, m, N, 1, odd(AB), odd(Q), odd(q), odd(R), odd(Eux), odd(r), 0.3, rbq.REG_CONTROL, K, d, dV, fail)
+    torch.cuda.synchronize()
+    assert int(fail[0]) == -1
+    Kh = K.cpu().numpy().reshape(N - 1, n, m).swapaxes(-1, -2)
+    assert _rel(Kh, Kr) < 1e-10 and _rel(d.cpu().numpy().reshape(N - 1, m), dr) < 1e-10
+    assert np.allclose(dV.cpu().numpy(), dVr, rtol=1e-10)
