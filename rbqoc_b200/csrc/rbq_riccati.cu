@@ -501,10 +501,11 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     if (smem > 227 * 1024) return RBQ_E_SIZE;
     BackwardArgs a{n, m, N, B, d_AB, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, rho, reg_type, d_K, d_d, d_dV, d_fail};
     // n <= 16 (spin13, spin15, spin11 up to first order) in large batches: one warp per problem, warp barriers only, eight
-    // problems resident per SM.  Measured at n = 11, 1001 knots: one problem takes 7.3 ms as one warp against 2.7 ms as eight
-    // (more serial work per lane), but 592 problems take 7.3 ms against 10.7 ms -- so the warp form is used from ~2.5 problems
-    // per SM upwards.  RBQ_BP_WARPS=1 / 8 forces a form (A/B measurements, tests).
-    bool small = n <= 16 && B * 2 > (int64_t)h->sm_count * 5;
+    // problems resident per SM.  Measured at n = 11, 1001 knots (tools/proto/bp_batch.py): one problem takes 1.47 ms as one
+    // warp against 1.20 ms as eight; 296 problems 1.80 against 1.77 ms; 370 problems 1.81 against 3.41 ms (the eight-warp
+    // form runs two problems per SM at a time); 1184 problems 2.05 against 7.0 ms -- so the warp form is used above two
+    // problems per SM.  RBQ_BP_WARPS=1 / 8 forces a form (A/B measurements, tests).
+    bool small = n <= 16 && B > 2 * (int64_t)h->sm_count;
     if (const char* e = getenv("RBQ_BP_WARPS")) small = n <= 16 && atoi(e) == 1;
     cudaError_t e;
     if (small) {
