@@ -66,6 +66,7 @@ RBQ_DEV void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 constexpr int BP_MAX_TILES = 9;        // 8-row tiles of a column strip: (64 + 4 + 7) / 8
+constexpr int BP_GSLOTS = 8;           // tiles of the second product per warp: 53 over 8 warps at n = 64, 8 for one warp at n = 16
 
 // barrier among the warps that share a problem: a real one for the 8-warp form, a warp barrier for the 1-warp form
 template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __syncthreads(); }
@@ -199,6 +200,25 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
 
     const int rtiles = n8 / 8, ctiles = q8 / 8, ksteps = n4 / 4;
     const int fr = lane >> 2, fc = lane & 3;          // fragment coordinates of this lane
+    // tiles of the second product dealt to this warp: the lower triangle row by row, then the tiles above the diagonal in
+    // the strip jtc that holds the gradient column cs
+    const int jtc = cs >> 3, nlow = ctiles * (ctiles + 1) / 2, ntile = nlow + jtc;
+    // every warp runs GC = ceil(ntile / NW) slots without predicates (GC is a constant in the shape-specialised kernels); a
+    // warp that was dealt one tile fewer repeats its last one (same values stored twice), a warp without tiles sits out
+    const int gt0 = ntile * wid / NW, gcnt = ntile * (wid + 1) / NW - gt0, GC = (ntile + NW - 1) / NW;
+    int gt_r[BP_GSLOTS], gt_c[BP_GSLOTS];
+    const double* gt_a[BP_GSLOTS];
+    const double* gt_b[BP_GSLOTS];
+#pragma unroll
+    for (int s_ = 0; s_ < BP_GSLOTS; ++s_) {
+        int idx = gt0 + (s_ < gcnt ? s_ : gcnt - 1), t = 0, jt = 0;
+        if (idx < 0) idx = 0;
+        if (idx >= nlow) { t = idx - nlow; jt = jtc; }
+        else { while (idx > t) { idx -= t + 1; ++t; } jt = idx; }
+        gt_r[s_] = t; gt_c[s_] = jt;
+        gt_a[s_] = AB + (8 * t + fr) * lda + fc;
+        gt_b[s_] = (8 * jt + fr == cs) ? sv + fc : T + (8 * jt + fr) * ld + fc;    // column cs of the right factor is s
+    }
     long long bad = -1;
 #ifdef RBQ_BP_PROFILE
     long long tprev = clock64();
@@ -243,31 +263,33 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel
         }
         bp_sync<NW>();                                             // ... and everybody's, together with T
         BP_PROF(1)
-        // ---- G += [A B]' T: warp -> one 8-column strip of G; A fragments are columns of [A B] read along the contraction ----
-        for (int jt = wid; jt < ctiles; jt += NW) {
-            double acc[BP_MAX_TILES][2];
+        // ---- G += [A B]' T: G is symmetric, so only its lower tiles are computed and mirrored into the upper half (bitwise
+        // symmetric there), plus the upper tiles of the strip that holds the gradient column; the tiles were dealt evenly
+        // over the warps before the loop (gt_r / gt_c).  A fragments are columns of [A B] read along the contraction. ----
+        if (gcnt > 0) {
+            double acc[BP_GSLOTS][2];
 #pragma unroll
-            for (int t = 0; t < BP_MAX_TILES; ++t)
-                if (t < ctiles) {
-                    const int r = 8 * t + fr, c = 8 * jt + 2 * fc;                 // one load each, the address selected
+            for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                if (s_ < GC) {
+                    const int r = 8 * gt_r[s_] + fr, c = 8 * gt_c[s_] + 2 * fc;    // one load each, the address selected
                     const bool dq = tma_c && r < n;
                     const double* s0 = dq && c < n ? Qk + c * n + r : G + c * ldg + r;
                     const double* s1 = dq && c + 1 < n ? Qk + (c + 1) * n + r : G + (c + 1) * ldg + r;
-                    acc[t][0] = *s0; acc[t][1] = *s1;
+                    acc[s_][0] = *s0; acc[s_][1] = *s1;
                 }
-            const double* bp = (8 * jt + fr == cs) ? sv + fc : T + (8 * jt + fr) * ld + fc;   // column cs of the right factor is s
-            const double* ap = AB + fr * lda + fc;
             for (int ks = 0; ks < ksteps; ++ks) {
-                const double bf = bp[4 * ks];
 #pragma unroll
-                for (int t = 0; t < BP_MAX_TILES; ++t)
-                    if (t < ctiles) dmma884(acc[t][0], acc[t][1], ap[8 * t * lda + 4 * ks], bf);
+                for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                    if (s_ < GC) dmma884(acc[s_][0], acc[s_][1], gt_a[s_][4 * ks], gt_b[s_][4 * ks]);
             }
 #pragma unroll
-            for (int t = 0; t < BP_MAX_TILES; ++t)
-                if (t < ctiles) {
-                    G[(8 * jt + 2 * fc) * ldg + 8 * t + fr] = acc[t][0];
-                    G[(8 * jt + 2 * fc + 1) * ldg + 8 * t + fr] = acc[t][1];
+            for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                if (s_ < GC) {
+                    const int r = 8 * gt_r[s_] + fr, c = 8 * gt_c[s_] + 2 * fc;
+                    G[c * ldg + r] = acc[s_][0];
+                    G[(c + 1) * ldg + r] = acc[s_][1];
+                    if (gt_r[s_] > gt_c[s_] && gt_r[s_] != jtc)                     // mirror (c even, ldg a multiple of 4: 16-byte aligned)
+                        *reinterpret_cast<double2*>(G + r * ldg + c) = make_double2(acc[s_][0], acc[s_][1]);
                 }
         }
         BP_PROF(2)
