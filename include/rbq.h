@@ -359,6 +359,38 @@ int rbq_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const d
                       const double* Euu, const double* Eux, const double* Eu, double rho, int reg_type, double* K, double* d,
                       double* dV, int64_t* fail);
 
+/* ---- augmented-Lagrangian cost expansion (constraint side) ---------------------------------------------
+ * What Altro / TrajectoryOptimization (external, Manifest.toml:26-32, 1523-1529) do per knot on the host in
+ * cost_expansion!(E, ::ALObjective, Z), for the problem class the reference sets up (spin13.jl:122-153 and siblings):
+ * a diagonal LQRObjective (Q, R, Qf, xf) plus BoundConstraint / GoalConstraint / NormConstraint, all knots in one launch,
+ * written where rbq_backward_pass_dev reads:
+ *   J[k]   = w_k (1/2 (x-xf)'Q(x-xf) + 1/2 u'Ru)  [Qf, no control term at k = N-1]  + sum_con lambda'c + 1/2 c' I_mu c
+ *   Exx_k  = w_k Q + sum_con cx' I_mu cx,      Ex_k = w_k Q (x-xf) + sum_con cx'(lambda + I_mu c)      (same for Euu, Eu; Eux = 0)
+ * with I_mu = diag(a .* mu), a_j = 1 for equalities and (c_j >= 0) | (lambda_j > 0) for inequalities (first-order
+ * constraint expansion, as the reference solver's).  w (N per-knot weights, NULL = 1) carries the solver's dt scaling of
+ * stage costs where its version applies one.
+ * A constraint covers knots [k0, k1) (0-based) and owns p entries per knot of lambda / mu / c at dual_off + (k - k0) p:
+ *   RBQ_CON_BOUND  p = 2(n+m): z - zmax <= 0 (z = [x; u]) then zmin - z <= 0; val_pool[val_off..] = zmax[n+m], zmin[n+m],
+ *                  +-infinity = no bound (c = -inf is written); control entries are skipped at the last knot
+ *   RBQ_CON_GOAL   p = nidx: x[idx_j] - val_pool[val_off + j] = 0               (indices distinct)
+ *   RBQ_CON_NORM   p = 1:    sum_j x[idx_j]^2 - val_pool[val_off] = 0
+ * d_Exx = NULL: values only (J and c), e.g. the merit function of line-search candidates.  All pointers are device
+ * pointers; asynchronous on the handle's stream. */
+#define RBQ_CON_BOUND 0
+#define RBQ_CON_GOAL 1
+#define RBQ_CON_NORM 2
+typedef struct rbq_constraint {
+    int32_t kind, p;
+    int64_t k0, k1;
+    int32_t nidx, idx_off;
+    int64_t val_off, dual_off;
+} rbq_constraint;
+int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, const double* d_X, const double* d_U,
+                              const double* d_Qdiag, const double* d_Rdiag, const double* d_Qfdiag, const double* d_xf,
+                              const double* d_w, int ncon, const rbq_constraint* d_cons, const int32_t* d_idx_pool,
+                              const double* d_val_pool, const double* d_lambda, const double* d_mu, double* d_Exx,
+                              double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J);
+
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);
 

@@ -256,7 +256,7 @@ end
 
 """
 iLQR backward pass (Altro `backwardpass!`) for B problems on the device.  AB is n×(n+m)×(N-1)×B exactly as `jacobians!`
-fills it; Exx n×n×N×B (symmetric, lower triangle read), Ex n×N×B, Euu m×m×(N-1)×B, Eux m×n×(N-1)×B, Eu m×(N-1)×B.
+fills it; Exx n×n×N×B (symmetric, both triangles stored), Ex n×N×B, Euu m×m×(N-1)×B, Eux m×n×(N-1)×B, Eu m×(N-1)×B.
 Returns K (m×n×(N-1)×B), d (m×(N-1)×B), ΔV (2×B) and the failure flags (-1, or the 0-based knot where Quu_reg was not
 positive definite: raise ρ and call again, as Altro's regularization_update! does).
 """
@@ -273,6 +273,33 @@ function backward_pass(AB::Array{Float64,4}, Exx::Array{Float64,4}, Ex::Array{Fl
          Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
         handle().ptr, n, m, N, B, AB, Exx, Ex, Euu, Eux, Eu, rho, state_reg ? 1 : 0, K, d, dV, failed), "rbq_backward_pass")
     return K, d, dV, failed
+end
+
+"Row of the constraint table of `al_cost_expansion_dev!` (rbq_constraint in include/rbq.h); knot ranges are 0-based, half-open."
+struct RbqConstraint
+    kind::Int32      # 0 BoundConstraint on [x; u] (±Inf = absent), 1 GoalConstraint, 2 NormConstraint
+    p::Int32
+    k0::Int64
+    k1::Int64
+    nidx::Int32
+    idx_off::Int32
+    val_off::Int64
+    dual_off::Int64
+end
+
+"""
+Augmented-Lagrangian cost expansion of every knot on the device (TrajectoryOptimization `cost_expansion!(E, ::ALObjective, Z)`
+for a diagonal LQRObjective plus Bound/Goal/Norm constraints).  All array arguments are device pointers (e.g. `pointer(::CuArray)`
+reinterpreted as `Ptr{Cvoid}`), laid out as in include/rbq.h; pass `C_NULL` for `Exx` to evaluate J and c only.
+"""
+function al_cost_expansion_dev!(n::Integer, m::Integer, N::Integer, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon::Integer, cons, idx_pool,
+                                val_pool, lambda, mu, Exx, Ex, Euu, Eux, Eu, c, J)
+    check(ccall((:rbq_al_cost_expansion_dev, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint,
+         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+         Ptr{Cvoid}, Ptr{Cvoid}),
+        handle().ptr, n, m, N, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon, cons, idx_pool, val_pool, lambda, mu, Exx, Ex, Euu, Eux,
+        Eu, c, J), "rbq_al_cost_expansion_dev")
 end
 
 "Page-lock a Julia array in place so that mc_static reads it over PCIe directly (zero-copy); unregister before it is freed."

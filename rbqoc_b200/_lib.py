@@ -22,6 +22,7 @@ MODEL_SPIN17, MODEL_SPIN18, MODEL_SPIN25, MODEL_SPIN30 = 17, 18, 25, 30
 ALGO_SU2, ALGO_PADE = 0, 1
 LINDBLAD_T1, LINDBLAD_T2 = 1, 2
 REG_CONTROL, REG_STATE = 0, 1
+CON_BOUND, CON_GOAL, CON_NORM = 0, 1, 2
 E_NULL, E_MODEL, E_SIZE, E_GATE, E_ALGO, E_NODEVICE, E_ALIGN = -1, -2, -3, -4, -5, -6, -7
 
 
@@ -44,6 +45,12 @@ class ModelParams(C.Structure):
         ("alpha", C.c_double),
         ("S_diag", C.c_double * 4),
     ]
+
+
+class Constraint(C.Structure):
+    """rbq_constraint (include/rbq.h): one row of the constraint table of rbq_al_cost_expansion_dev."""
+    _fields_ = [("kind", C.c_int32), ("p", C.c_int32), ("k0", C.c_int64), ("k1", C.c_int64), ("nidx", C.c_int32),
+                ("idx_off", C.c_int32), ("val_off", C.c_int64), ("dual_off", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -128,6 +135,7 @@ SIGNATURES = {
     "rbq_lindblad_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _P, _P, _SP]),
     "rbq_backward_pass": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
     "rbq_backward_pass_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
+    "rbq_al_cost_expansion_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64] + [_P] * 7 + [C.c_int] + [_P] * 12),
     "rbq_fp64_peak": (C.c_int, [_P, C.c_int, C.POINTER(_D)]),
 }
 

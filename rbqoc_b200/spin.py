@@ -560,3 +560,81 @@ def evaluate_adev(controls, dt_inv, gate_count=100, gate_type=GateType.xpiby2, t
     res = run_sim_prop(gate_count, gate_type, controls, dt_inv, seed=np.arange(1, trial_count + 1),
                        dynamics_type=DynamicsType.schroedda, engine=engine)
     return {"gate_errors": 1 - res["fidelities"][:, -1]}
+
+
+# ---- constraint table of the AL cost expansion (spin13.jl:95-153 and siblings) ---------------------------------------
+class ConstraintTable:
+    """Host-side builder of the rbq_constraint table: the reference's ConstraintList (spin13.jl:145-152) restricted to
+    the three constraint types it uses.  Knot ranges are 0-based and half-open here ([k0, k1)); the reference's `2:N-2`
+    is `bound(1, N - 2, ...)`.  `specs` keeps the plain description (what tests hand to the oracle)."""
+
+    def __init__(self, n: int, m: int, N: int):
+        self.n, self.m, self.N = n, m, N
+        self.rows, self.idx, self.val, self.specs = [], [], [], []
+        self.dual_size = 0
+        self.d_cons = self.d_idx = self.d_val = None
+
+    @property
+    def ncon(self) -> int:
+        return len(self.rows)
+
+    def _add(self, kind, p, k0, k1, idx, vals, spec):
+        if not (0 <= k0 <= k1 <= self.N):
+            raise ValueError("knot range outside the trajectory")
+        self.rows.append(_lib.Constraint(kind, p, k0, k1, len(idx), len(self.idx), len(self.val), self.dual_size))
+        self.idx += [int(i) for i in idx]
+        self.val += [float(v) for v in vals]
+        self.dual_size += (k1 - k0) * p
+        self.specs.append(dict(spec, k0=k0, k1=k1))
+        return self
+
+    def bound(self, k0, k1, x_max=None, x_min=None, u_max=None, u_min=None):
+        """BoundConstraint(n, m, x_max=, x_min=, u_max=, u_min=): missing sides are infinite."""
+        full = lambda v, size, fill: np.full(size, fill) if v is None else np.asarray(v, dtype=float)
+        zmax = np.concatenate([full(x_max, self.n, np.inf), full(u_max, self.m, np.inf)])
+        zmin = np.concatenate([full(x_min, self.n, -np.inf), full(u_min, self.m, -np.inf)])
+        return self._add(_lib.CON_BOUND, 2 * (self.n + self.m), k0, k1, [], np.concatenate([zmax, zmin]),
+                         {"kind": "bound", "zmax": zmax, "zmin": zmin})
+
+    def goal(self, k0, k1, xf, idx):
+        """GoalConstraint(xf, idx): x[idx] = xf[idx]."""
+        idx = [int(i) for i in idx]
+        tgt = np.asarray(xf, dtype=float)[idx]
+        return self._add(_lib.CON_GOAL, len(idx), k0, k1, idx, tgt, {"kind": "goal", "idx": idx, "target": tgt})
+
+    def norm(self, k0, k1, idx, val=1.0):
+        """NormConstraint(n, m, val, Equality(), idx): sum x[idx]^2 = val."""
+        idx = [int(i) for i in idx]
+        return self._add(_lib.CON_NORM, 1, k0, k1, idx, [val], {"kind": "norm", "idx": idx, "val": float(val)})
+
+    def dual_slices(self):
+        """(offset, knots, p) of every constraint inside the flat lambda / mu / c arrays."""
+        return [(r.dual_off, r.k1 - r.k0, r.p) for r in self.rows]
+
+    def upload(self, device):
+        import ctypes as C
+
+        import torch
+
+        raw = bytes((_lib.Constraint * max(len(self.rows), 1))(*self.rows))
+        self.d_cons = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.d_idx = torch.tensor(self.idx or [0], dtype=torch.int32, device=device)
+        self.d_val = torch.tensor(self.val or [0.0], dtype=torch.float64, device=device)
+        assert C.sizeof(_lib.Constraint) == 48
+        return self
+
+
+def spin13_constraints(N, xf, max_control=MAX_CONTROL_NORM_0):
+    """The ConstraintList of spin13.jl:136-152 (states 0-3, 4-7; integral of the control 8; control 9; its derivative 10)."""
+    n, m = 11, 1
+    ctrl = 9
+    x_max = np.full(n, np.inf); x_min = np.full(n, -np.inf)
+    x_max[ctrl], x_min[ctrl] = max_control, -max_control
+    xb_max = np.full(n, np.inf); xb_min = np.full(n, -np.inf)
+    xb_max[ctrl] = xb_min[ctrl] = 0.0
+    t = ConstraintTable(n, m, N)
+    t.bound(1, N - 2, x_max=x_max, x_min=x_min)              # 2:N-2
+    t.bound(N - 2, N - 1, x_max=xb_max, x_min=xb_min)        # N-1:N-1
+    t.goal(N - 1, N, xf, list(range(0, 9)))                  # N:N, [STATE1_IDX; STATE2_IDX; INTCONTROLS_IDX]
+    t.norm(1, N - 1, range(0, 4)); t.norm(1, N - 1, range(4, 8))   # 2:N-1
+    return t

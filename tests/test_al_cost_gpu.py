@@ -1,0 +1,95 @@
+"""GPU parity: rbq_al_cost_expansion_dev against the numpy restatement (oracle/al_cost.py) of the solver's
+cost_expansion!(E, ::ALObjective, Z).  Tolerance: relative 1e-12 (the same few products and sums per entry, summed in a
+different order only for the knot cost and the norm constraint)."""
+import numpy as np
+import pytest
+import torch
+
+import rbqoc_b200 as rbq
+from rbqoc_b200 import spin
+from test_oracle_cpu import _al_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(eng, dev, X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, expand=True):
+    N, n = X.shape
+    m = U.shape[1]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    z = lambda *s: torch.full(s, float("nan"), dtype=torch.float64, device=dev)
+    table.upload(dev)
+    Exx, Ex, Euu, Eux, Eu = (z(N, n, n), z(N, n), z(N - 1, m, m), z(N - 1, n, m), z(N - 1, m)) if expand else (None,) * 5
+    c, J = z(table.dual_size), z(N)
+    eng.al_cost_expansion_dev(n, m, N, d(X), d(U), d(Qd), d(Rd), d(Qfd), d(xf), None if w is None else d(w), table, d(lam), d(mu),
+                              Exx, Ex, Euu, Eux, Eu, c, J)
+    torch.cuda.synchronize()
+    host = lambda t: None if t is None else t.cpu().numpy()
+    return tuple(host(t) for t in (J, Exx, Ex, Euu, Eux, Eu, c))
+
+
+@pytest.mark.parametrize("seed,N,n,m", [(1, 9, 11, 1), (2, 40, 11, 1), (3, 6, 11, 1)])
+def test_al_cost_expansion_matches_oracle(seed, N, n, m):
+    from oracle import al_cost
+
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0); eng.use_torch_stream()
+    rng = np.random.default_rng(seed)
+    X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals = _al_problem(rng, N, n, m)
+    Jr, Exxr, Exr, Euur, Euxr, Eur, cr = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, table.specs, duals, w)
+    J, Exx, Ex, Euu, Eux, Eu, c = _run(eng, dev, X, U, Qd, Rd, Qfd, xf, w, table, lam, mu)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    assert rel(J, Jr) < 1e-12 and rel(Ex, Exr) < 1e-12 and rel(Eu, Eur) < 1e-12
+    # blocks are column-major on the device; Exx and Euu are symmetric, Eux (m x n column-major) is zero
+    assert rel(np.swapaxes(Exx, -1, -2), Exxr) < 1e-12 and rel(Euu, Euur) < 1e-12 and np.all(Eux == 0)
+    for (o, kn, p), ref in zip(table.dual_slices(), cr):
+        got = c[o:o + kn * p].reshape(kn, p)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and rel(got[fin], ref[fin]) < 1e-12
+    # values only (merit function of a line-search candidate): same J and c, no blocks touched
+    J2, *_, c2 = _run(eng, dev, X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, expand=False)
+    assert np.array_equal(J2, J) and np.array_equal(c2, c, equal_nan=True)
+    # unit weights when w is NULL
+    J3 = _run(eng, dev, X, U, Qd, Rd, Qfd, xf, None, table, lam, mu)[0]
+    assert rel(J3, al_cost.expansion(X, U, Qd, Rd, Qfd, xf, table.specs, duals, None)[0]) < 1e-12
+
+
+def test_al_cost_blocks_feed_the_backward_pass_on_device():
+    """cost expansion -> Jacobians -> backward pass without leaving the device: the gains equal those of the host path fed
+    with the oracle's blocks."""
+    from oracle import al_cost, riccati
+
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0); eng.use_torch_stream()
+    model = spin.Spin13Model()
+    n, m, N = model.n, model.m, 61
+    dtv = np.full(N - 1, 0.1)
+    U = 0.05 * np.sin(np.arange(N - 1) * 0.3)[:, None]
+    X = eng.rollout(model.params, spin.spin13_x0(), U, dtv)
+    xf = np.zeros(n); xf[:8] = X[-1, :8]
+    table = spin.spin13_constraints(N, xf)
+    rng = np.random.default_rng(4)
+    lam = 0.01 * rng.standard_normal(table.dual_size); mu = np.full(table.dual_size, 10.0)
+    Qd = np.array([1.0] * 8 + [1.0, 1.0, 0.1]); Rd = np.array([0.1]); Qfd = Qd * N
+    duals = [(lam[o:o + k * p].reshape(k, p), mu[o:o + k * p].reshape(k, p)) for o, k, p in table.dual_slices()]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    table.upload(dev)
+    dX, dU, ddt = d(X), d(U), d(dtv)
+    Exx = torch.empty(N, n * n, dtype=torch.float64, device=dev); Ex = torch.empty(N, n, dtype=torch.float64, device=dev)
+    Euu = torch.empty(N - 1, m * m, dtype=torch.float64, device=dev); Eux = torch.empty(N - 1, m * n, dtype=torch.float64, device=dev)
+    Eu = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
+    c = torch.empty(table.dual_size, dtype=torch.float64, device=dev); J = torch.empty(N, dtype=torch.float64, device=dev)
+    AB = torch.empty(N - 1, n * (n + m), dtype=torch.float64, device=dev)
+    K = torch.empty(N - 1, n * m, dtype=torch.float64, device=dev); dd = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
+    dV = torch.empty(2, dtype=torch.float64, device=dev); fl = torch.empty(1, dtype=torch.int64, device=dev)
+    eng.al_cost_expansion_dev(n, m, N, dX, dU, d(Qd), d(Rd), d(Qfd), d(xf), None, table, d(lam), d(mu), Exx, Ex, Euu, Eux, Eu, c, J)
+    eng.jacobians_dev(model.params, N - 1, dX, dU, ddt, AB)
+    eng.backward_pass_dev(n, m, N, 1, AB, Exx, Ex, Euu, Eux, Eu, 1e-3, rbq.REG_CONTROL, K, dd, dV, fl)
+    torch.cuda.synchronize()
+    assert int(fl[0]) == -1
+    Jr, Exxr, Exr, Euur, Euxr, Eur, cr = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, table.specs, duals, None)
+    ABh = eng.jacobians(model.params, X[:-1], U, dtv)
+    Kr, dr, dVr, fr = riccati.backward_pass(ABh, Exxr, Exr, Euur, Euxr, Eur, rho=1e-3, reg_type=rbq.REG_CONTROL)
+    Kh = K.cpu().numpy().reshape(N - 1, n, m).swapaxes(-1, -2)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    assert rel(Kh, Kr) < 1e-9 and rel(dd.cpu().numpy(), dr) < 1e-9 and np.allclose(dV.cpu().numpy(), dVr, rtol=1e-9)
+    assert abs(float(J.sum()) - Jr.sum()) < 1e-12 * abs(Jr.sum())

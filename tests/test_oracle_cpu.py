@@ -339,3 +339,68 @@ def test_deqjl_timeline_is_the_exact_solution_of_the_reference_ode(orc):
     for j in rng.integers(0, durs.shape[0], 50):
         t = edges[j] + rng.uniform(0.05, 0.95) * durs[j]
         assert amps[j] == controls[int(np.floor(t * cdi)) % count] and nidx[j] == int(np.floor(t * ndi))
+
+
+# ---- augmented-Lagrangian cost expansion (oracle/al_cost.py) ----------------------------------------------------------
+def _al_problem(rng, N=9, n=11, m=1):
+    """spin13-shaped problem with every constraint type, some bounds active, non-zero multipliers."""
+    from rbqoc_b200 import spin
+
+    X = 0.6 * rng.standard_normal((N, n)); U = rng.standard_normal((N - 1, m))
+    X[:, 9] = np.linspace(-0.8, 0.8, N)                       # the bounded control state crosses both bounds
+    xf = rng.standard_normal(n)
+    table = spin.spin13_constraints(N, xf)
+    table.bound(0, N, u_max=[0.3], u_min=[-0.2])              # a control bound that also covers the last knot
+    lam = rng.standard_normal(table.dual_size) * 0.3
+    mu = 10.0 ** rng.uniform(-1, 2, table.dual_size)
+    Qd, Rd, Qfd = rng.uniform(0.1, 2, n), rng.uniform(0.1, 2, m), rng.uniform(1, 20, n)
+    w = rng.uniform(0.05, 0.2, N)
+    duals = [(lam[o:o + k * p].reshape(k, p), mu[o:o + k * p].reshape(k, p)) for o, k, p in table.dual_slices()]
+    return X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals
+
+
+def test_al_cost_gradient_matches_finite_differences_of_the_merit_function():
+    from oracle import al_cost
+
+    rng = np.random.default_rng(11)
+    X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals = _al_problem(rng)
+    J, Exx, Ex, Euu, Eux, Eu, c = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, table.specs, duals, w)
+    assert np.all(Eux == 0)
+    h = 1e-6
+    for k, i in ((0, 3), (2, 9), (4, 9), (5, 0), (7, 9), (8, 2), (8, 8), (3, 6)):
+        Xp, Xm = X.copy(), X.copy(); Xp[k, i] += h; Xm[k, i] -= h
+        fd = (al_cost.expansion(Xp, U, Qd, Rd, Qfd, xf, table.specs, duals, w)[0].sum()
+              - al_cost.expansion(Xm, U, Qd, Rd, Qfd, xf, table.specs, duals, w)[0].sum()) / (2 * h)
+        assert abs(fd - Ex[k, i]) < 1e-6 * max(1.0, abs(fd)), (k, i, fd, Ex[k, i])
+    for k in (0, 3, 7):
+        Up, Um = U.copy(), U.copy(); Up[k, 0] += h; Um[k, 0] -= h
+        fd = (al_cost.expansion(X, Up, Qd, Rd, Qfd, xf, table.specs, duals, w)[0].sum()
+              - al_cost.expansion(X, Um, Qd, Rd, Qfd, xf, table.specs, duals, w)[0].sum()) / (2 * h)
+        assert abs(fd - Eu[k, 0]) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_al_cost_hessian_exact_for_linear_constraints_and_active_set_rule():
+    from oracle import al_cost
+
+    rng = np.random.default_rng(12)
+    X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals = _al_problem(rng)
+    lin = [i for i, s in enumerate(table.specs) if s["kind"] != "norm"]
+    specs = [table.specs[i] for i in lin]; dl = [duals[i] for i in lin]
+    J, Exx, Ex, Euu, Eux, Eu, c = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, specs, dl, w)
+    h = 1e-4
+    k = 4                                                  # second difference of the merit function along e_9 at an interior knot
+    f = lambda d: al_cost.expansion(X + d, U, Qd, Rd, Qfd, xf, specs, dl, w)[0].sum()
+    e = np.zeros_like(X); e[k, 9] = h
+    assert abs((f(e) - 2 * f(0 * e) + f(-e)) / h ** 2 - Exx[k, 9, 9]) < 1e-5 * Exx[k, 9, 9]
+    # inactive inequality (c < 0, lambda <= 0): no penalty curvature; active through lambda > 0 alone: curvature mu
+    o, kn, p = table.dual_slices()[0]
+    kk = 3 - table.specs[0]["k0"]
+    cu = X[3, 9] - 0.5
+    assert cu < 0
+    lam2 = dl[0][0].copy(); lam2[kk, 9] = -0.1
+    E0 = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, specs, [(lam2, dl[0][1])] + dl[1:], w)[1][3, 9, 9]
+    lam2[kk, 9] = +0.1
+    E1 = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, specs, [(lam2, dl[0][1])] + dl[1:], w)[1][3, 9, 9]
+    assert np.isclose(E1 - E0, dl[0][1][kk, 9])
+    # an absent bound writes -inf and contributes nothing
+    assert np.all(np.isneginf(c[0][:, 0])) and np.isfinite(J).all()
