@@ -186,13 +186,30 @@ def other_configs(eng, rbq, spin, torch, dev):
             eng.synchronize()
 
         out[name]["jacobians_plus_backward_pass_dev_ms"] = timed_host(expansion_and_pass)
-        # ... and the whole hot path of one iLQR iteration on the device: expansion, backward pass, 8 line-search candidates
+        # ... and the whole hot path of one iLQR iteration on the device: cost expansion (below), dynamics expansion,
+        # backward pass, 8 line-search candidates
         dXfull, dal = dd(X), dd(alphas)
         dXc = torch.empty(8, N, n, dtype=torch.float64, device=dev); dUc = torch.empty(8, N - 1, m, dtype=torch.float64, device=dev)
 
+        # the cost side of the iteration: LQR objective + the reference's constraint list as augmented-Lagrangian terms
+        table = {"spin13": spin.spin13_constraints, "spin12": spin.spin12_constraints, "spin30": spin.spin30_constraints}[name](N, X[-1])
+        table.upload(dev)
+        dlam = torch.zeros(table.dual_size, dtype=torch.float64, device=dev); dmu = torch.ones(table.dual_size, dtype=torch.float64, device=dev)
+        dc = torch.empty(table.dual_size, dtype=torch.float64, device=dev); dJ = torch.empty(N, dtype=torch.float64, device=dev)
+        dQ = dd(np.ones(n)); dR = dd(0.1 * np.ones(m)); dQf = dd(float(N) * np.ones(n)); dxf = dd(X[-1])
+        dExxa = torch.empty(N, n * n, dtype=torch.float64, device=dev); dExa = torch.empty(N, n, dtype=torch.float64, device=dev)
+        dEuua = torch.empty(N - 1, m * m, dtype=torch.float64, device=dev); dEuxa = torch.empty(N - 1, m * n, dtype=torch.float64, device=dev)
+        dEua = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
+
+        def al_cost():
+            eng.al_cost_expansion_dev(n, m, N, dXfull, dU, dQ, dR, dQf, dxf, None, table, dlam, dmu, dExxa, dExa, dEuua, dEuxa, dEua, dc, dJ)
+
+        out[name]["al_cost_expansion_dev_ms"] = timed_host(lambda: (al_cost(), eng.synchronize()))
+
         def iteration_dev():
+            al_cost()
             eng.jacobians_dev(model.params, N - 1, dXfull, dU, ddt, dAB)
-            eng.backward_pass_dev(n, m, N, 1, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
+            eng.backward_pass_dev(n, m, N, 1, dAB, dExxa, dExa, dEuua, dEuxa, dEua, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
             eng.rollout_closedloop_dev(model.params, N, dXfull, dU, dK, dd_, ddt, 8, dal, dXc, dUc)
             eng.synchronize()
 

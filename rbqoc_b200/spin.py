@@ -624,17 +624,35 @@ class ConstraintTable:
         return self
 
 
-def spin13_constraints(N, xf, max_control=MAX_CONTROL_NORM_0):
-    """The ConstraintList of spin13.jl:136-152 (states 0-3, 4-7; integral of the control 8; control 9; its derivative 10)."""
-    n, m = 11, 1
-    ctrl = 9
+def _reference_constraints(n, N, xf, ctrl, goal_idx, norm_blocks, max_control):
+    """The ConstraintList every run_traj of the reference builds (spin13.jl:136-152, spin12.jl:280-296, spin30.jl:301-320):
+    amplitude bound on the control state over 2:N-2, zero control at N-1, goal at N, unit norm of the iso states over 2:N-1."""
     x_max = np.full(n, np.inf); x_min = np.full(n, -np.inf)
     x_max[ctrl], x_min[ctrl] = max_control, -max_control
     xb_max = np.full(n, np.inf); xb_min = np.full(n, -np.inf)
     xb_max[ctrl] = xb_min[ctrl] = 0.0
-    t = ConstraintTable(n, m, N)
+    t = ConstraintTable(n, 1, N)
     t.bound(1, N - 2, x_max=x_max, x_min=x_min)              # 2:N-2
     t.bound(N - 2, N - 1, x_max=xb_max, x_min=xb_min)        # N-1:N-1
-    t.goal(N - 1, N, xf, list(range(0, 9)))                  # N:N, [STATE1_IDX; STATE2_IDX; INTCONTROLS_IDX]
-    t.norm(1, N - 1, range(0, 4)); t.norm(1, N - 1, range(4, 8))   # 2:N-1
+    t.goal(N - 1, N, xf, goal_idx)                           # N:N
+    for b in norm_blocks:
+        t.norm(1, N - 1, range(b, b + 4))                    # 2:N-1
     return t
+
+
+def spin13_constraints(N, xf, max_control=MAX_CONTROL_NORM_0):
+    """spin13.jl:136-152 (states 0-3, 4-7; integral of the control 8; control 9; its derivative 10)."""
+    return _reference_constraints(11, N, xf, 9, list(range(0, 9)), [0, 4], max_control)
+
+
+def spin12_constraints(N, xf, max_control=MAX_CONTROL_NORM_0):
+    """spin12.jl:280-296 (spin18 alike): spin13's list plus unit norm of the 8 sample states at 11 + 4i."""
+    return _reference_constraints(43, N, xf, 9, list(range(0, 9)), [0, 4] + [11 + 4 * i for i in range(8)], max_control)
+
+
+def spin30_constraints(N, xf, sample_state_count=1, max_control=MAX_CONTROL_NORM_0):
+    """spin30.jl:301-320: three nominal states 0-11, integral 12, control 13, derivative 14, then chunks of 41 (10 sigma
+    points and a penalty); goal on STATE1, STATE2 and the integral; unit norm of every sigma point and nominal state."""
+    n = 15 + 41 * sample_state_count
+    blocks = [15 + 41 * c + 4 * i for c in range(sample_state_count) for i in range(10)] + [0, 4, 8]
+    return _reference_constraints(n, N, xf, 13, list(range(0, 8)) + [12], blocks, max_control)
