@@ -6,6 +6,8 @@ spin13.jl:118-135, Z/2 target of spin13.jl:80-93, N = 301 knots, dt = 0.1 ns, U0
 Parity tests compare each piece with its oracle; this test checks that their CONVENTIONS agree with each other (layouts and
 signs of A, B, K, d, the closed-loop law u = u_ref + K (x - x_ref) + alpha d): if any were off, the predicted decrease
 alpha dV1 + alpha^2 dV2 would not match the realised one and the cost would not go down."""
+import os
+
 import numpy as np
 import pytest
 
@@ -115,4 +117,88 @@ def test_device_resident_iteration_matches_host_pointer_iteration(engine):
     assert int(dfl.cpu()[0]) == -1
     assert np.array_equal(dK.cpu().numpy().reshape(N - 1, n, m).transpose(0, 2, 1), K)
     assert np.array_equal(dXc.cpu().numpy(), Xc) and np.array_equal(dUc.cpu().numpy(), Uc)
+    eng.close()
+
+
+def test_al_ilqr_on_device_reduces_merit_as_predicted_and_constraint_violation(engine):
+    """Augmented-Lagrangian iLQR on the spin13 problem with the reference's constraint list (spin13.jl:136-152), every inner
+    iteration on the device: rbq_al_cost_expansion_dev -> rbq_jacobians_dev -> rbq_backward_pass_dev ->
+    rbq_rollout_closedloop_dev -> rbq_al_cost_expansion_dev (values only, per candidate).  The merit function the cost
+    kernel reports must fall as the backward pass predicts (its expansion IS the quadratic model the pass minimises), and
+    the outer multiplier / penalty updates must drive the constraint violation down."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0); eng.use_torch_stream()
+    model = spin.Spin13Model()
+    n, m, N, dt = 11, 1, 301, 0.1
+    g = spin.GATES[spin.GateType.zpiby2]
+    xf = np.zeros(n)
+    xf[0:4] = spin.get_vec_iso(g @ np.array([1.0, 0.0])); xf[4:8] = spin.get_vec_iso(g @ np.array([0.0, 1.0]))
+    table = spin.spin13_constraints(N, xf).upload(dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    e = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+    dQ, dR, dQf, dxf = t([1.0] * 8 + [1.0, 1.0, 0.1]), t([0.1]), t(np.array([1.0] * 8 + [1.0, 1.0, 0.1]) * N), t(xf)
+    ddt = t(np.full(N - 1, dt))
+    nal = 8
+    dal = t(0.5 ** np.arange(nal))
+    dU = t(np.full((N - 1, m), 1e-4))
+    dX = e(1, N, n)
+    eng.rollout_dev(model.params, 1, N, t(spin.spin13_x0()), dU, ddt, dX)
+    dX = dX[0]
+    lam = torch.zeros(table.dual_size, dtype=torch.float64, device=dev); mu = torch.ones(table.dual_size, dtype=torch.float64, device=dev)
+    ineq = torch.zeros(table.dual_size, dtype=torch.bool, device=dev)
+    for row, (o, kn, p) in zip(table.rows, table.dual_slices()):
+        ineq[o:o + kn * p] = row.kind == rbq.CON_BOUND
+    Exx, Ex, Euu, Eux, Eu = e(N, n * n), e(N, n), e(N - 1, m * m), e(N - 1, m * n), e(N - 1, m)
+    c, J, cc, Jc = e(table.dual_size), e(N), e(table.dual_size), e(N)
+    AB, K, d, dV, fl = e(N - 1, n * (n + m)), e(N - 1, n * m), e(N - 1, m), e(2), torch.empty(1, dtype=torch.int64, device=dev)
+    Xc, Uc = e(nal, N, n), e(nal, N - 1, m)
+
+    def violation(cv):
+        v = torch.where(ineq, torch.clamp(cv, min=0.0), cv.abs())
+        return float(torch.where(torch.isfinite(v), v, torch.zeros_like(v)).max())
+
+    checked, viol = 0, []
+    for outer in range(4):
+        for inner in range(10):
+            eng.al_cost_expansion_dev(n, m, N, dX, dU, dQ, dR, dQf, dxf, None, table, lam, mu, Exx, Ex, Euu, Eux, Eu, c, J)
+            eng.jacobians_dev(model.params, N - 1, dX, dU, ddt, AB)
+            rho = 0.0
+            while True:
+                eng.backward_pass_dev(n, m, N, 1, AB, Exx, Ex, Euu, Eux, Eu, rho, rbq.REG_CONTROL, K, d, dV, fl)
+                if int(fl[0]) < 0:
+                    break
+                rho = max(10.0 * rho, 1e-6)
+                assert rho < 1e8
+            eng.rollout_closedloop_dev(model.params, N, dX, dU, K, d, ddt, nal, dal, Xc, Uc)
+            merit = float(J.sum())
+            dVh = dV.cpu().numpy()
+            assert dVh[0] <= 0
+            Jcand = []
+            for i in range(nal):
+                eng.al_cost_expansion_dev(n, m, N, Xc[i], Uc[i], dQ, dR, dQf, dxf, None, table, lam, mu, None, None, None, None, None, cc, Jc)
+                Jcand.append(float(Jc.sum()))
+            a = float(dal[nal - 1])
+            pred = a * dVh[0] + a * a * dVh[1]
+            if abs(pred) > 1e-10 * abs(merit):
+                # small step: the realised change of the merit function is the predicted one (the active set rarely flips)
+                assert (Jcand[-1] - merit) / pred == pytest.approx(1.0, abs=0.05), (outer, inner, Jcand[-1] - merit, pred)
+                checked += 1
+            better = [i for i in range(nal) if Jcand[i] < merit]
+            if not better:
+                break
+            i = better[0]
+            dX, dU = Xc[i].clone(), Uc[i].clone()
+            if os.environ.get("RBQ_TEST_VERBOSE"):
+                print(outer, inner, "merit", merit, "->", Jcand[i], "alpha", float(dal[i]), "pred small", pred, "real small", Jcand[-1] - merit)
+        eng.al_cost_expansion_dev(n, m, N, dX, dU, dQ, dR, dQf, dxf, None, table, lam, mu, None, None, None, None, None, c, J)
+        torch.cuda.synchronize()
+        viol.append(violation(c))
+        if os.environ.get("RBQ_TEST_VERBOSE"):
+            print("outer", outer, "violation", viol[-1], "merit", float(J.sum()))
+        cfin = torch.where(torch.isfinite(c), c, torch.zeros_like(c))
+        lam = torch.where(ineq, torch.clamp(lam + mu * cfin, min=0.0), lam + mu * cfin)      # dual update, then penalty x10
+        mu = mu * 10.0
+    assert checked >= 10
+    assert viol[-1] < 0.5 * viol[0] and all(b <= a for a, b in zip(viol, viol[1:])), viol
     eng.close()
