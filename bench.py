@@ -187,7 +187,7 @@ def other_configs(eng, rbq, spin, torch, dev):
 
         out[name]["jacobians_plus_backward_pass_dev_ms"] = timed_host(expansion_and_pass)
         # ... and the whole hot path of one iLQR iteration on the device: cost expansion (below), dynamics expansion,
-        # backward pass, 8 line-search candidates
+        # backward pass, 8 line-search candidates and their merit values
         dXfull, dal = dd(X), dd(alphas)
         dXc = torch.empty(8, N, n, dtype=torch.float64, device=dev); dUc = torch.empty(8, N - 1, m, dtype=torch.float64, device=dev)
 
@@ -196,6 +196,7 @@ def other_configs(eng, rbq, spin, torch, dev):
         table.upload(dev)
         dlam = torch.zeros(table.dual_size, dtype=torch.float64, device=dev); dmu = torch.ones(table.dual_size, dtype=torch.float64, device=dev)
         dc = torch.empty(table.dual_size, dtype=torch.float64, device=dev); dJ = torch.empty(N, dtype=torch.float64, device=dev)
+        dcc = torch.empty(8, table.dual_size, dtype=torch.float64, device=dev); dJc = torch.empty(8, N, dtype=torch.float64, device=dev)
         dQ = dd(np.ones(n)); dR = dd(0.1 * np.ones(m)); dQf = dd(float(N) * np.ones(n)); dxf = dd(X[-1])
         dExxa = torch.empty(N, n * n, dtype=torch.float64, device=dev); dExa = torch.empty(N, n, dtype=torch.float64, device=dev)
         dEuua = torch.empty(N - 1, m * m, dtype=torch.float64, device=dev); dEuxa = torch.empty(N - 1, m * n, dtype=torch.float64, device=dev)
@@ -211,6 +212,7 @@ def other_configs(eng, rbq, spin, torch, dev):
             eng.jacobians_dev(model.params, N - 1, dXfull, dU, ddt, dAB)
             eng.backward_pass_dev(n, m, N, 1, dAB, dExxa, dExa, dEuua, dEuxa, dEua, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
             eng.rollout_closedloop_dev(model.params, N, dXfull, dU, dK, dd_, ddt, 8, dal, dXc, dUc)
+            eng.al_cost_expansion_dev(n, m, N, dXc, dUc, dQ, dR, dQf, dxf, None, table, dlam, dmu, None, None, None, None, None, dcc, dJc, B=8)
             eng.synchronize()
 
         out[name]["ilqr_iteration_dev_ms"] = timed_host(iteration_dev)

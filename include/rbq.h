@@ -374,8 +374,11 @@ int rbq_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const d
  *                  +-infinity = no bound (c = -inf is written); control entries are skipped at the last knot
  *   RBQ_CON_GOAL   p = nidx: x[idx_j] - val_pool[val_off + j] = 0               (indices distinct)
  *   RBQ_CON_NORM   p = 1:    sum_j x[idx_j]^2 - val_pool[val_off] = 0
- * d_Exx = NULL: values only (J and c), e.g. the merit function of line-search candidates.  All pointers are device
- * pointers; asynchronous on the handle's stream. */
+ * d_Exx = NULL: values only (J and c), e.g. the merit function of line-search candidates.
+ * B trajectories at once (B <= 65535): X[B][N][n], U[B][N-1][m], every output with a leading batch dimension (c: the table's
+ * total dual length per trajectory; the table's rows must be in increasing dual_off order); lambda / mu are shared
+ * (dual_stride = 0: candidates of one problem) or per trajectory, dual_stride doubles apart (independent problems).
+ * All pointers are device pointers; asynchronous on the handle's stream. */
 #define RBQ_CON_BOUND 0
 #define RBQ_CON_GOAL 1
 #define RBQ_CON_NORM 2
@@ -385,11 +388,11 @@ typedef struct rbq_constraint {
     int32_t nidx, idx_off;
     int64_t val_off, dual_off;
 } rbq_constraint;
-int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, const double* d_X, const double* d_U,
+int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_X, const double* d_U,
                               const double* d_Qdiag, const double* d_Rdiag, const double* d_Qfdiag, const double* d_xf,
                               const double* d_w, int ncon, const rbq_constraint* d_cons, const int32_t* d_idx_pool,
-                              const double* d_val_pool, const double* d_lambda, const double* d_mu, double* d_Exx,
-                              double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J);
+                              const double* d_val_pool, const double* d_lambda, const double* d_mu, int64_t dual_stride,
+                              double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J);
 
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);

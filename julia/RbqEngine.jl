@@ -292,14 +292,14 @@ Augmented-Lagrangian cost expansion of every knot on the device (TrajectoryOptim
 for a diagonal LQRObjective plus Bound/Goal/Norm constraints).  All array arguments are device pointers (e.g. `pointer(::CuArray)`
 reinterpreted as `Ptr{Cvoid}`), laid out as in include/rbq.h; pass `C_NULL` for `Exx` to evaluate J and c only.
 """
-function al_cost_expansion_dev!(n::Integer, m::Integer, N::Integer, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon::Integer, cons, idx_pool,
-                                val_pool, lambda, mu, Exx, Ex, Euu, Eux, Eu, c, J)
+function al_cost_expansion_dev!(n::Integer, m::Integer, N::Integer, B::Integer, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon::Integer, cons,
+                                idx_pool, val_pool, lambda, mu, dual_stride::Integer, Exx, Ex, Euu, Eux, Eu, c, J)
     check(ccall((:rbq_al_cost_expansion_dev, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint,
-         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+        (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint,
+         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
          Ptr{Cvoid}, Ptr{Cvoid}),
-        handle().ptr, n, m, N, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon, cons, idx_pool, val_pool, lambda, mu, Exx, Ex, Euu, Eux,
-        Eu, c, J), "rbq_al_cost_expansion_dev")
+        handle().ptr, n, m, N, B, X, U, Qdiag, Rdiag, Qfdiag, xf, w, ncon, cons, idx_pool, val_pool, lambda, mu, dual_stride, Exx, Ex,
+        Euu, Eux, Eu, c, J), "rbq_al_cost_expansion_dev")
 end
 
 "Page-lock a Julia array in place so that mc_static reads it over PCIe directly (zero-copy); unregister before it is freed."

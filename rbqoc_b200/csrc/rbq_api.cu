@@ -1058,17 +1058,19 @@ int rbq_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const d
 }
 
 // ---- augmented-Lagrangian cost expansion (device resident) ---------------------------------------------------------------
-int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, const double* d_X, const double* d_U,
+int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_X, const double* d_U,
                               const double* d_Qdiag, const double* d_Rdiag, const double* d_Qfdiag, const double* d_xf,
                               const double* d_w, int ncon, const rbq_constraint* d_cons, const int32_t* d_idx_pool,
-                              const double* d_val_pool, const double* d_lambda, const double* d_mu, double* d_Exx,
-                              double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J) {
+                              const double* d_val_pool, const double* d_lambda, const double* d_mu, int64_t dual_stride,
+                              double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J) {
     ENTER(h);
-    if (n < 1 || m < 1 || N < 1 || ncon < 0) return fail(h, RBQ_E_SIZE, "rbq_al_cost_expansion_dev: n=%d m=%d N=%lld ncon=%d", n, m, (long long)N, ncon);
+    if (n < 1 || m < 1 || N < 1 || B < 0 || B > 65535 || ncon < 0 || dual_stride < 0)
+        return fail(h, RBQ_E_SIZE, "rbq_al_cost_expansion_dev: n=%d m=%d N=%lld B=%lld ncon=%d", n, m, (long long)N, (long long)B, ncon);
+    if (B == 0) return RBQ_OK;
     if (!d_X || (N > 1 && !d_U) || !d_Qdiag || !d_Rdiag || !d_Qfdiag || !d_xf) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion_dev: null pointer");
     if (ncon > 0 && (!d_cons || !d_val_pool || !d_lambda || !d_mu)) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion_dev: null constraint data");
     if (d_Exx && (!d_Ex || (N > 1 && (!d_Euu || !d_Eux || !d_Eu)))) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion_dev: Exx given without the other blocks");
-    CKL(launch_al_cost(h, n, m, N, d_X, d_U, d_Qdiag, d_Rdiag, d_Qfdiag, d_xf, d_w, ncon, d_cons, d_idx_pool, d_val_pool, d_lambda,
+    CKL(launch_al_cost(h, n, m, N, B, dual_stride, d_X, d_U, d_Qdiag, d_Rdiag, d_Qfdiag, d_xf, d_w, ncon, d_cons, d_idx_pool, d_val_pool, d_lambda,
                        d_mu, d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, d_c, d_J));
     return RBQ_OK;
 }

@@ -19,7 +19,7 @@ namespace rbq {
 constexpr int AL_THREADS = 128;
 
 struct AlArgs {
-    int n, m; int64_t N;
+    int n, m; int64_t N, B, dual_stride;
     const double* X; const double* U;
     const double* Qd; const double* Rd; const double* Qfd; const double* xf; const double* w;
     int ncon; const rbq_constraint* cons; const int32_t* idx_pool; const double* val_pool;
@@ -29,23 +29,26 @@ struct AlArgs {
 
 __global__ void __launch_bounds__(AL_THREADS) al_cost_kernel(const AlArgs a) {
     const int n = a.n, m = a.m, tid = threadIdx.x;
-    const int64_t k = blockIdx.x;
+    const int64_t k = blockIdx.x, b = blockIdx.y;              // knot, trajectory of the batch
     const bool term = k == a.N - 1;
-    const double* x = a.X + k * n;
-    const double* u = term ? nullptr : a.U + k * m;
+    const double* x = a.X + (b * a.N + k) * n;
+    const double* u = term ? nullptr : a.U + (b * (a.N - 1) + k) * m;
     const double wk = a.w ? a.w[k] : 1.0;
     const bool expand = a.Exx != nullptr;
-    double* Exx = expand ? a.Exx + k * (int64_t)(n * n) : nullptr;
-    double* Ex = expand ? a.Ex + k * (int64_t)n : nullptr;
-    double* Euu = expand && !term ? a.Euu + k * (int64_t)(m * m) : nullptr;
-    double* Eu = expand && !term ? a.Eu + k * (int64_t)m : nullptr;
+    double* Exx = expand ? a.Exx + (b * a.N + k) * (int64_t)(n * n) : nullptr;
+    double* Ex = expand ? a.Ex + (b * a.N + k) * (int64_t)n : nullptr;
+    double* Euu = expand && !term ? a.Euu + (b * (a.N - 1) + k) * (int64_t)(m * m) : nullptr;
+    double* Eu = expand && !term ? a.Eu + (b * (a.N - 1) + k) * (int64_t)m : nullptr;
     double Jp = 0.0;                                             // this thread's share of the knot's cost
+    // c of trajectory b starts at b * (total dual length); the table's rows are in dual_off order, the last one ends it
+    int64_t dual_size = 0;
+    if (a.ncon > 0) { const rbq_constraint last = a.cons[a.ncon - 1]; dual_size = last.dual_off + (last.k1 - last.k0) * last.p; }
 
     // ---- objective: 1/2 (x - xf)'Q(x - xf) + 1/2 u'Ru, Q -> Qf at the last knot, scaled by w[k] ----
     if (expand) {
         for (int i = tid; i < n * n; i += AL_THREADS) Exx[i] = 0.0;
         if (!term) {
-            for (int i = tid; i < m * n; i += AL_THREADS) a.Eux[k * (int64_t)(m * n) + i] = 0.0;
+            for (int i = tid; i < m * n; i += AL_THREADS) a.Eux[(b * (a.N - 1) + k) * (int64_t)(m * n) + i] = 0.0;
             for (int i = tid; i < m * m; i += AL_THREADS) Euu[i] = 0.0;
         }
     }
@@ -68,9 +71,9 @@ __global__ void __launch_bounds__(AL_THREADS) al_cost_kernel(const AlArgs a) {
         if (k < cn.k0 || k >= cn.k1) continue;                   // uniform over the block
         __syncthreads();
         const int64_t doff = cn.dual_off + (k - cn.k0) * cn.p;
-        const double* lam = a.lambda + doff;
-        const double* mu = a.mu + doff;
-        double* cv = a.c ? a.c + doff : nullptr;
+        const double* lam = a.lambda + b * a.dual_stride + doff;
+        const double* mu = a.mu + b * a.dual_stride + doff;
+        double* cv = a.c ? a.c + b * dual_size + doff : nullptr;
         if (cn.kind == RBQ_CON_BOUND) {
             // p = 2(n+m): z <= zmax (entries 0..n+m-1) then zmin <= z; thread j owns both entries of z_j
             const int nz = n + m;
@@ -131,17 +134,17 @@ __global__ void __launch_bounds__(AL_THREADS) al_cost_kernel(const AlArgs a) {
         if (tid < s) red[tid] += red[tid + s];
         __syncthreads();
     }
-    if (tid == 0 && a.J) a.J[k] = red[0];
+    if (tid == 0 && a.J) a.J[b * a.N + k] = red[0];
 }
 
-int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, const double* d_X, const double* d_U, const double* d_Qd,
+int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, int64_t B, int64_t dual_stride, const double* d_X, const double* d_U, const double* d_Qd,
                    const double* d_Rd, const double* d_Qfd, const double* d_xf, const double* d_w, int ncon,
                    const rbq_constraint* d_cons, const int32_t* d_idx_pool, const double* d_val_pool, const double* d_lambda,
                    const double* d_mu, double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c,
                    double* d_J) {
-    AlArgs a{n, m, N, d_X, d_U, d_Qd, d_Rd, d_Qfd, d_xf, d_w, ncon, d_cons, d_idx_pool, d_val_pool, d_lambda, d_mu,
+    AlArgs a{n, m, N, B, dual_stride, d_X, d_U, d_Qd, d_Rd, d_Qfd, d_xf, d_w, ncon, d_cons, d_idx_pool, d_val_pool, d_lambda, d_mu,
              d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, d_c, d_J};
-    al_cost_kernel<<<(unsigned)N, AL_THREADS, 0, h->stream>>>(a);
+    al_cost_kernel<<<dim3((unsigned)N, (unsigned)B), AL_THREADS, 0, h->stream>>>(a);
     h->launches++;
     return (int)cudaGetLastError();
 }

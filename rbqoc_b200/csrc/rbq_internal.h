@@ -115,7 +115,7 @@ int launch_sampling_cost(rbq_handle* h, int64_t K, const double* d_X, const doub
 int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
                          const double* d_Ex, const double* d_Euu, const double* d_Eux, const double* d_Eu, double rho,
                          int reg_type, double* d_K, double* d_d, double* d_dV, long long* d_fail);
-int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, const double* d_X, const double* d_U, const double* d_Qd,
+int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, int64_t B, int64_t dual_stride, const double* d_X, const double* d_U, const double* d_Qd,
                    const double* d_Rd, const double* d_Qfd, const double* d_xf, const double* d_w, int ncon,
                    const rbq_constraint* d_cons, const int32_t* d_idx_pool, const double* d_val_pool, const double* d_lambda,
                    const double* d_mu, double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c,

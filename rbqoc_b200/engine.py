@@ -406,14 +406,15 @@ class Engine:
                                                  _ptr(d_d), _ptr(d_dV), _ptr(d_fail)), "rbq_backward_pass_dev")
 
     def al_cost_expansion_dev(self, n, m, N, d_X, d_U, d_Qdiag, d_Rdiag, d_Qfdiag, d_xf, d_w, table, d_lambda, d_mu,
-                              d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, d_c, d_J):
+                              d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, d_c, d_J, B=1, dual_stride=0):
         """Augmented-Lagrangian cost blocks of all knots (rbq_al_cost_expansion_dev).  `table` is a spin.ConstraintTable
-        already uploaded (`table.upload(device)`); d_Exx = None evaluates J and c only."""
+        already uploaded (`table.upload(device)`); d_Exx = None evaluates J and c only; B > 1: a batch of trajectories
+        (line-search candidates with shared multipliers, or independent problems dual_stride apart)."""
         raw = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        self._ck(self._lib.rbq_al_cost_expansion_dev(self._h, int(n), int(m), int(N), _ptr(d_X), _ptr(d_U), _ptr(d_Qdiag),
+        self._ck(self._lib.rbq_al_cost_expansion_dev(self._h, int(n), int(m), int(N), int(B), _ptr(d_X), _ptr(d_U), _ptr(d_Qdiag),
                                                      _ptr(d_Rdiag), _ptr(d_Qfdiag), _ptr(d_xf), _ptr(d_w), int(table.ncon),
                                                      raw(table.d_cons), raw(table.d_idx), raw(table.d_val), _ptr(d_lambda),
-                                                     _ptr(d_mu), _ptr(d_Exx), _ptr(d_Ex), _ptr(d_Euu), _ptr(d_Eux), _ptr(d_Eu),
+                                                     _ptr(d_mu), int(dual_stride), _ptr(d_Exx), _ptr(d_Ex), _ptr(d_Euu), _ptr(d_Eux), _ptr(d_Eu),
                                                      _ptr(d_c), _ptr(d_J)), "rbq_al_cost_expansion_dev")
 
     # ---- device-pointer forms (torch CUDA tensors; asynchronous on the handle's stream) ------------------------

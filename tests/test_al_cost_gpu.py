@@ -93,3 +93,30 @@ def test_al_cost_blocks_feed_the_backward_pass_on_device():
     rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
     assert rel(Kh, Kr) < 1e-9 and rel(dd.cpu().numpy(), dr) < 1e-9 and np.allclose(dV.cpu().numpy(), dVr, rtol=1e-9)
     assert abs(float(J.sum()) - Jr.sum()) < 1e-12 * abs(Jr.sum())
+
+
+def test_al_cost_expansion_batch_equals_single_calls():
+    """B trajectories in one launch: shared multipliers (line-search candidates) and per-trajectory multipliers
+    (independent problems) both reproduce the single-trajectory results bit for bit."""
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0); eng.use_torch_stream()
+    rng = np.random.default_rng(21)
+    X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals = _al_problem(rng, 12, 11, 1)
+    B = 3
+    Xs = np.stack([X + 0.05 * b for b in range(B)]); Us = np.stack([U * (1 + b) for b in range(B)])
+    lams = np.stack([lam * (1 + 0.5 * b) for b in range(B)]); mus = np.stack([mu * (1 + b) for b in range(B)])
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    z = lambda *s: torch.full(s, float("nan"), dtype=torch.float64, device=dev)
+    table.upload(dev)
+    N, n, m = 12, 11, 1
+    for shared in (True, False):
+        out = [z(B, N, n, n), z(B, N, n), z(B, N - 1, m, m), z(B, N - 1, n, m), z(B, N - 1, m), z(B, table.dual_size), z(B, N)]
+        eng.al_cost_expansion_dev(n, m, N, d(Xs), d(Us), d(Qd), d(Rd), d(Qfd), d(xf), d(w), table, d(lam if shared else lams),
+                                  d(mu if shared else mus), *out, B=B, dual_stride=0 if shared else table.dual_size)
+        torch.cuda.synchronize()
+        for b in range(B):
+            single = _run(eng, dev, Xs[b], Us[b], Qd, Rd, Qfd, xf, w, table, lam if shared else lams[b], mu if shared else mus[b])
+            J1, Exx1, Ex1, Euu1, Eux1, Eu1, c1 = single
+            got = [t[b].cpu().numpy() for t in out]
+            assert np.array_equal(got[6], J1) and np.array_equal(got[0], Exx1) and np.array_equal(got[1], Ex1)
+            assert np.array_equal(got[2], Euu1) and np.array_equal(got[4], Eu1) and np.array_equal(got[5], c1)

@@ -150,7 +150,7 @@ def test_al_ilqr_on_device_reduces_merit_as_predicted_and_constraint_violation(e
     for row, (o, kn, p) in zip(table.rows, table.dual_slices()):
         ineq[o:o + kn * p] = row.kind == rbq.CON_BOUND
     Exx, Ex, Euu, Eux, Eu = e(N, n * n), e(N, n), e(N - 1, m * m), e(N - 1, m * n), e(N - 1, m)
-    c, J, cc, Jc = e(table.dual_size), e(N), e(table.dual_size), e(N)
+    c, J, cc, Jc = e(table.dual_size), e(N), e(nal, table.dual_size), e(nal, N)
     AB, K, d, dV, fl = e(N - 1, n * (n + m)), e(N - 1, n * m), e(N - 1, m), e(2), torch.empty(1, dtype=torch.int64, device=dev)
     Xc, Uc = e(nal, N, n), e(nal, N - 1, m)
 
@@ -174,10 +174,9 @@ def test_al_ilqr_on_device_reduces_merit_as_predicted_and_constraint_violation(e
             merit = float(J.sum())
             dVh = dV.cpu().numpy()
             assert dVh[0] <= 0
-            Jcand = []
-            for i in range(nal):
-                eng.al_cost_expansion_dev(n, m, N, Xc[i], Uc[i], dQ, dR, dQf, dxf, None, table, lam, mu, None, None, None, None, None, cc, Jc)
-                Jcand.append(float(Jc.sum()))
+            # the merit function of all candidates in one batched, values-only call (shared multipliers)
+            eng.al_cost_expansion_dev(n, m, N, Xc, Uc, dQ, dR, dQf, dxf, None, table, lam, mu, None, None, None, None, None, cc, Jc, B=nal)
+            Jcand = [float(v) for v in Jc.sum(dim=1)]
             a = float(dal[nal - 1])
             pred = a * dVh[0] + a * a * dVh[1]
             if abs(pred) > 1e-10 * abs(merit):
