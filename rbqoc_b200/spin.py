@@ -656,3 +656,71 @@ def spin30_constraints(N, xf, sample_state_count=1, max_control=MAX_CONTROL_NORM
     n = 15 + 41 * sample_state_count
     blocks = [15 + 41 * c + 4 * i for c in range(sample_state_count) for i in range(10)] + [0, 4, 8]
     return _reference_constraints(n, N, xf, 13, list(range(0, 8)) + [12], blocks, max_control)
+
+
+# ---- pulse I/O on the caller's side of the path (rbqoc.jl:98-139, spin.jl:1485-1530) ---------------------------------
+DT_PREF, DT_PREF_INV = 1e-2, 1e2                     # spin.jl:24-25
+
+
+class SaveType(enum.IntEnum):                        # rbqoc.jl:27-31
+    jl = 1
+    samplejl = 2
+    py = 3
+
+
+def read_save(save):
+    """rbqoc.jl:129-139.  `save` is either the mapping read_save would return (key -> array / scalar, arrays with the shapes
+    Julia sees, index lists 1-based as stored) or a path to the .h5 file.  Reading a path needs h5py, which this image does
+    not have (and the reference ships no .h5 file to test against): arrays are transposed on the way in because HDF5.jl
+    stores Julia's column-major arrays with reversed dimensions."""
+    if isinstance(save, (str, bytes)) or hasattr(save, "__fspath__"):
+        try:
+            import h5py
+        except ImportError as exc:
+            raise RuntimeError("reading a .h5 pulse file needs h5py; pass the mapping of its datasets instead") from exc
+        with h5py.File(save, "r") as f:
+            return {k: (np.asarray(v).T if getattr(v, "ndim", 0) > 1 else np.asarray(v)[()]) for k, v in f.items()}
+    return save
+
+
+def _cols(idx):
+    return np.atleast_1d(np.asarray(idx, dtype=np.int64)) - 1      # 1-based, as the reference stores them
+
+
+def grab_controls(save):
+    """rbqoc.jl:98-123: (controls, controls_dt_inv, evolution_time) of a saved pulse, for the three save formats."""
+    s = read_save(save)
+    st = SaveType(int(s["save_type"]))
+    if st == SaveType.jl:
+        controls = np.asarray(s["astates"], dtype=np.float64)[:-1][:, _cols(s["controls_idx"])]
+        dt_inv = 1.0 / float(s["dt"]) if "dt" in s else DT_PREF_INV
+        return controls, dt_inv, float(s["evolution_time"])
+    if st == SaveType.samplejl:
+        return np.asarray(s["controls_sample"], dtype=np.float64)[:-1], DT_PREF_INV, float(s["evolution_time_sample"])
+    return np.asarray(s["controls"], dtype=np.float64).T, DT_PREF_INV, float(s["evolution_time"])
+
+
+def sample_controls(save, dt=DT_PREF, dt_inv=DT_PREF_INV):
+    """spin.jl:1485-1530: resample an optimised pulse (controls = the control column of the augmented states, and the second
+    derivative that is the solver's actual control) onto the dt grid with interpolating cubic splines.  The reference uses
+    Dierckx.Spline1D (k = 3, s = 0), i.e. FITPACK's curfit -- the routine scipy.interpolate.splrep wraps.
+    Returns (controls_sample, d2controls_dt2_sample, final_time_sample)."""
+    from scipy.interpolate import splev, splrep
+
+    s = read_save(save)
+    controls = np.asarray(s["astates"], dtype=np.float64)[:-1][:, _cols(s["controls_idx"])]
+    d2 = np.asarray(s["acontrols"], dtype=np.float64)[:, _cols(s["d2controls_dt2_idx"])]
+    knots = controls.shape[0]
+    if "dt_idx" in s:
+        dts = np.asarray(s["acontrols"], dtype=np.float64)[:, int(np.atleast_1d(s["dt_idx"])[0]) - 1]
+    else:
+        dts = float(s["dt"]) * np.ones(knots)
+    time_axis = np.concatenate([[0.0], np.cumsum(dts)[:-1]])
+    final_time = float(np.sum(dts))
+    count = int(math.floor(final_time * dt_inv))
+    t_sample = np.arange(count) * dt                      # the last control is dt before final_time
+    out_c = np.empty((count, controls.shape[1])); out_d = np.empty((count, d2.shape[1]))
+    for i in range(controls.shape[1]):
+        out_c[:, i] = splev(t_sample, splrep(time_axis, controls[:, i], k=3, s=0))
+        out_d[:, i] = splev(t_sample, splrep(time_axis, d2[:, i], k=3, s=0))
+    return out_c, out_d, final_time

@@ -404,3 +404,37 @@ def test_al_cost_hessian_exact_for_linear_constraints_and_active_set_rule():
     assert np.isclose(E1 - E0, dl[0][1][kk, 9])
     # an absent bound writes -inf and contributes nothing
     assert np.all(np.isneginf(c[0][:, 0])) and np.isfinite(J).all()
+
+
+# ---- pulse I/O mirror (rbqoc.jl:98-139, spin.jl:1485-1530) --------------------------------------------------------------
+def test_grab_and_sample_controls_follow_the_reference_save_formats():
+    from rbqoc_b200 import spin
+
+    N, n, dt = 31, 11, 0.1
+    t = np.arange(N) * dt
+    a = 0.02 * t ** 3 - 0.05 * t ** 2 + 0.1 * t                     # a cubic: an interpolating cubic spline reproduces it
+    astates = np.zeros((N, n)); astates[:, 9] = a
+    acontrols = np.zeros((N - 1, 1)); acontrols[:, 0] = (0.12 * t - 0.1)[:-1]
+    save = {"save_type": 1, "astates": astates, "acontrols": acontrols, "controls_idx": [10], "d2controls_dt2_idx": [1],
+            "dt": dt, "evolution_time": (N - 1) * dt}
+    c, dt_inv, T = spin.grab_controls(save)
+    assert c.shape == (N - 1, 1) and np.array_equal(c[:, 0], a[:-1]) and dt_inv == pytest.approx(10.0) and T == pytest.approx(3.0)
+    cs, ds, Tf = spin.sample_controls(save)
+    count = int(np.floor(Tf * 100.0))
+    assert Tf == pytest.approx(3.0) and cs.shape == (count, 1) and ds.shape == (count, 1)
+    ts = np.arange(count) * 1e-2
+    # the reference fits the spline on the first N-1 knots and evaluates up to T - dt_pref: the last 0.1 ns is extrapolated
+    assert np.max(np.abs(cs[:, 0] - (0.02 * ts ** 3 - 0.05 * ts ** 2 + 0.1 * ts))) < 1e-12
+    assert np.max(np.abs(ds[:, 0] - (0.12 * ts - 0.1))) < 1e-12
+    # per-knot dt stored as a control column (time-optimal runs)
+    ac2 = np.hstack([acontrols, np.full((N - 1, 1), dt)])
+    save2 = dict(save, acontrols=ac2, dt_idx=[2]); del save2["dt"]
+    cs2, _, Tf2 = spin.sample_controls(save2)
+    assert Tf2 == pytest.approx(Tf) and np.allclose(cs2, cs, atol=1e-13)
+    # the resampled and the python formats
+    c3, dti3, T3 = spin.grab_controls({"save_type": 2, "controls_sample": cs, "evolution_time_sample": Tf})
+    assert c3.shape == (count - 1, 1) and dti3 == 100.0 and T3 == Tf
+    c4, _, _ = spin.grab_controls({"save_type": 3, "controls": cs.T, "evolution_time": Tf})
+    assert np.array_equal(c4, cs)
+    with pytest.raises(RuntimeError, match="h5py"):
+        spin.read_save("/nonexistent/pulse.h5")
