@@ -72,13 +72,14 @@ constexpr int BP_GSLOTS = 8;           // tiles of the second product per warp: 
 template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __syncthreads(); }
 template <int NW_> RBQ_DEV bool bp_sync_or(bool pred) { return NW_ == 1 ? __any_sync(0xffffffffu, pred) != 0 : __syncthreads_or(pred) != 0; }
 
-template <int NW, int MODE, bool M1, int NN>
+template <int NW, int MODE, int MM, int NN>
 __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel(const BackwardArgs a) {
     constexpr int BP_THREADS = 32 * NW;
     extern __shared__ __align__(16) double sm[];
-    // M1: one control, known at compile time (every reference model but spin15) -- the m-loops below fold to one iteration
+    // MM: the number of controls when known at compile time (1 for every reference model but the time-optimal spin15, which
+    // has 2; 0: any) -- the m-loops below fold to MM iterations
     // NN: the state dimension itself for the reference models' shapes (0: any) -- strides and tile counts become constants
-    const int n = NN ? NN : a.n, m = M1 ? 1 : a.m, nm = n + m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = NN ? NN : a.n, m = MM ? MM : a.m, nm = n + m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n4 = up4(n), n8 = up8(n), q8 = up8(nm + 1), ld = n8 + 4, ldg = q8 + 4;
     const int cs = nm;                 // spare column: G(:, cs) = [A B]' s + e, i.e. the gradient g rides in the second product
     const int64_t N = a.N, b = blockIdx.x;
@@ -487,33 +488,45 @@ static int bp_stage_mode(int n, int m, const double* d_AB, const double* d_Exx) 
     return mode;
 }
 
-template <int NW, int MODE, bool M1, int NN>
+template <int NW, int MODE, int MM, int NN>
 static cudaError_t bp_launch2(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream) {
-    auto kern = backward_pass_kernel<NW, MODE, M1, NN>;
+    auto kern = backward_pass_kernel<NW, MODE, MM, NN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)B, 32 * NW, smem, stream>>>(a);
     return cudaGetLastError();
 }
-// the shapes of the reference models (n = 11, 43, 56, 58 with one control) get kernels with n known at compile time: tile
+// the shapes of the reference models (n = 11, 12, 15, 19, 43, 56, 58 with one control) get kernels with n known at compile time: tile
 // loops fully unrolled, constant strides.  RBQ_BP_GENERIC=1 forces the any-shape kernels (tests compare the two).
 template <int NW, int MODE>
 static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream) {
-    if (a.m != 1) return bp_launch2<NW, MODE, false, 0>(a, B, smem, stream);
     const char* g = getenv("RBQ_BP_GENERIC");
-    if (!(g && atoi(g) != 0)) {
+    const bool specialised = !(g && atoi(g) != 0);
+    if (a.m == 2 && specialised) {                                      // spin15 time-optimal: u = (d2a/dt2, sqrt(dt))
         if constexpr (MODE == 0) {
-            if (a.n == 11) return bp_launch2<NW, MODE, true, 11>(a, B, smem, stream);
-        }
-        if constexpr (NW == BP_WARPS_LARGE && MODE == (BP_DENSE_J | BP_TMA_C)) {
-            if (a.n == 43) return bp_launch2<NW, MODE, true, 43>(a, B, smem, stream);
-        }
-        if constexpr (NW == BP_WARPS_LARGE && MODE == (BP_TMA_J | BP_TMA_C)) {
-            if (a.n == 56) return bp_launch2<NW, MODE, true, 56>(a, B, smem, stream);
-            if (a.n == 58) return bp_launch2<NW, MODE, true, 58>(a, B, smem, stream);
+            if (a.n == 11) return bp_launch2<NW, MODE, 2, 11>(a, B, smem, stream);
+            if (a.n == 12) return bp_launch2<NW, MODE, 2, 12>(a, B, smem, stream);
         }
     }
-    return bp_launch2<NW, MODE, true, 0>(a, B, smem, stream);
+    if (a.m != 1) return bp_launch2<NW, MODE, 0, 0>(a, B, smem, stream);
+    if (specialised) {
+        if constexpr (MODE == 0) {
+            if (a.n == 11) return bp_launch2<NW, MODE, 1, 11>(a, B, smem, stream);
+            if (a.n == 12) return bp_launch2<NW, MODE, 1, 12>(a, B, smem, stream);      // spin15, decay aware
+            if (a.n == 15) return bp_launch2<NW, MODE, 1, 15>(a, B, smem, stream);      // spin11 / spin17, first order
+            if constexpr (NW == BP_WARPS_LARGE) {
+                if (a.n == 19) return bp_launch2<NW, MODE, 1, 19>(a, B, smem, stream);  // spin11 / spin17, second order
+            }
+        }
+        if constexpr (NW == BP_WARPS_LARGE && MODE == (BP_DENSE_J | BP_TMA_C)) {
+            if (a.n == 43) return bp_launch2<NW, MODE, 1, 43>(a, B, smem, stream);
+        }
+        if constexpr (NW == BP_WARPS_LARGE && MODE == (BP_TMA_J | BP_TMA_C)) {
+            if (a.n == 56) return bp_launch2<NW, MODE, 1, 56>(a, B, smem, stream);
+            if (a.n == 58) return bp_launch2<NW, MODE, 1, 58>(a, B, smem, stream);
+        }
+    }
+    return bp_launch2<NW, MODE, 1, 0>(a, B, smem, stream);
 }
 
 int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,

@@ -15,7 +15,8 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-@pytest.mark.parametrize("n,m,N", [(11, 1, 301), (12, 2, 64), (43, 1, 181), (56, 1, 120), (58, 1, 40), (3, 4, 17), (64, 2, 9), (5, 1, 1)])
+@pytest.mark.parametrize("n,m,N", [(11, 1, 301), (11, 2, 90), (12, 2, 64), (12, 1, 50), (15, 1, 70), (19, 1, 45), (43, 1, 181), (56, 1, 120), (58, 1, 40),
+                                   (3, 4, 17), (64, 2, 9), (5, 1, 1)])
 @pytest.mark.parametrize("reg", [rbq.REG_CONTROL, rbq.REG_STATE], ids=["control_reg", "state_reg"])
 def test_backward_pass_matches_oracle(engine, n, m, N, reg):
     from oracle import riccati
@@ -75,7 +76,7 @@ def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
     from oracle import riccati
 
     rng = np.random.default_rng(77)
-    for n, m, N in ((11, 1, 140), (12, 2, 60), (16, 3, 25), (3, 1, 9)):
+    for n, m, N in ((11, 1, 140), (12, 2, 60), (12, 1, 33), (15, 1, 40), (16, 3, 25), (3, 1, 9)):
         A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
         st = lambda x: np.stack([x] * 3)
         monkeypatch.setenv("RBQ_BP_WARPS", "1")
@@ -94,7 +95,7 @@ def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
     assert engine.backward_pass(AB, Q, q, R, Eux, r)[3] == 12
 
 
-@pytest.mark.parametrize("n,N", [(11, 60), (36, 33), (43, 21), (44, 20), (56, 24), (58, 17)])
+@pytest.mark.parametrize("n,N", [(11, 60), (15, 30), (36, 33), (43, 21), (44, 20), (56, 24), (58, 17)])
 def test_backward_pass_staging_modes_and_specialised_shapes_agree(engine, monkeypatch, n, N):
     """The launcher picks a staging mode (cp.async / bulk TMA copies, dense or padded Jacobian block) and, for the reference
     models' shapes, a kernel with n known at compile time.  Every choice is the same recursion: all agree with the oracle, on a

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import rbqoc_b200 as rbq
 dev = torch.device("cuda", 0)
 eng = rbq.Engine(0); eng.use_torch_stream()
-n, m, N, B = int(sys.argv[1]), 1, (int(sys.argv[2]) if len(sys.argv) > 2 else 201), (int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+n, m, N, B = int(sys.argv[1]), int(os.environ.get("BP_M", "1")), (int(sys.argv[2]) if len(sys.argv) > 2 else 201), (int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 rng = np.random.default_rng(0)
 d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 AB = d(0.1 * rng.standard_normal((B, N - 1, n + m, n))); Exx = d(np.tile(np.eye(n), (B, N, 1, 1))); Ex = d(rng.standard_normal((B, N, n)))
