@@ -196,6 +196,23 @@ int launch_sampling_cost(rbq_handle* h, int64_t K, const double* d_X, const doub
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
+// launch of the warp-per-trajectory kernel; the unscented models with one sigma-point chunk get the SSC = 1 instantiation
+template <int M, bool CLOSED>
+static cudaError_t launch_warp_rollout(const WarpRolloutArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, 32, smem, stream>>>(a);
+        return cudaSuccess;
+    };
+    if constexpr (M == RBQ_MODEL_SPIN30 || M == RBQ_MODEL_SPIN25) {
+        if (a.p.sample_state_count == 1) return go(warp_rollout_kernel<M, CLOSED, 1>);
+    }
+    return go(warp_rollout_kernel<M, CLOSED, 0>);
+}
+
 static inline int family(int model_id) {
     switch (model_id) {
     case RBQ_MODEL_SPIN13: return RBQ_MODEL_SPIN13;
@@ -244,7 +261,7 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
         else packed_rollout_kernel<RBQ_MODEL_SPIN12><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
     } else if (B <= WARP_ROLLOUT_MAX) {
         WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
-#define CALL(M) warp_rollout_kernel<M, false><<<(unsigned)B, 32, 0, h->stream>>>(a)
+#define CALL(M) { cudaError_t e_ = launch_warp_rollout<M, false>(a, (unsigned)B, 0, h->stream); if (e_ != cudaSuccess) return (int)e_; }
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     } else {
@@ -266,15 +283,7 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
     // one step-size candidate per warp, one warp per block so that candidates spread over SMs
     WarpRolloutArgs a{p, n, m, N, nalpha, 0.0, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
     const size_t smem = closedloop_smem_bytes(n, m);
-#define CALL(M)                                                                                                               \
-    {                                                                                                                         \
-        if (smem > 48 * 1024) {                                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(warp_rollout_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                                 (int)smem);                                                                  \
-            if (e != cudaSuccess) return (int)e;                                                                              \
-        }                                                                                                                     \
-        warp_rollout_kernel<M, true><<<(unsigned)nalpha, 32, smem, h->stream>>>(a);                                           \
-    }
+#define CALL(M) { cudaError_t e_ = launch_warp_rollout<M, true>(a, (unsigned)nalpha, smem, h->stream); if (e_ != cudaSuccess) return (int)e_; }
     RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
     h->launches++;

@@ -43,7 +43,9 @@ struct WarpRolloutArgs {
 constexpr int CL_TILE = 32;   // knots of (K, Xref, Uref, d) staged per shared-memory tile in the closed-loop kernel
 __host__ __device__ inline size_t closedloop_smem_bytes(int n, int m) { return sizeof(double) * CL_TILE * (size_t)(n * m + n + 2 * m); }
 
-template <int MODEL, bool CLOSED>
+// SSC: the number of sigma-point chunks of the unscented models when known at compile time (1 in every run of the
+// reference; 0: read it from the parameters) -- the chunk loops and their register arrays fold away
+template <int MODEL, bool CLOSED, int SSC = 0>
 __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs a) {
     extern __shared__ __align__(16) double cl_smem[];
     double* sK = cl_smem;                                    // [CL_TILE][n][m] (column-major m x n per knot)
@@ -53,14 +55,16 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
     const rbq_model_params& p = a.p;
     const int lane = threadIdx.x;
     const int64_t tr = blockIdx.x;
-    const int n = a.n, m = a.m;
+    // what the model fixes is a constant here: one control for every model but the time-optimal spin15, n of spin13 / spin12
+    const int n = MODEL == RBQ_MODEL_SPIN13 ? 11 : (MODEL == RBQ_MODEL_SPIN12 ? 43 : a.n);
+    const int m = MODEL == RBQ_MODEL_SPIN15 ? a.m : 1;
     const int64_t N = a.N;
     constexpr bool S25 = (MODEL == RBQ_MODEL_SPIN25);
     constexpr bool U30 = (MODEL == RBQ_MODEL_SPIN30) || S25;   // the unscented models (sigma points on lanes 0..9)
-    constexpr int NCH = U30 ? RBQ_MAX_SAMPLE_STATES : 1;       // sigma-point chunks a lane may hold
+    constexpr int NCH = U30 ? (SSC ? SSC : RBQ_MAX_SAMPLE_STATES) : 1;   // sigma-point chunks a lane may hold
     constexpr int UB = S25 ? 17 : 15;                          // offset of the first sigma-point chunk
     constexpr int NNOM = S25 ? 2 : 3;                          // nominal blocks (lanes 10..)
-    const int ssc = U30 ? p.sample_state_count : 1;
+    const int ssc = U30 ? (SSC ? SSC : p.sample_state_count) : 1;
     const int cb = (U30 && !S25) ? 12 : 8;                     // [int a, a, da] chain base
 
     // ---- lane roles ---------------------------------------------------------------------------------
