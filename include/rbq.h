@@ -393,6 +393,12 @@ int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B,
                               const double* d_w, int ncon, const rbq_constraint* d_cons, const int32_t* d_idx_pool,
                               const double* d_val_pool, const double* d_lambda, const double* d_mu, int64_t dual_stride,
                               double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J);
+/* host-pointer form (synchronous): the same with every array in host memory; nidx / nval = lengths of the two pools. */
+int rbq_al_cost_expansion(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* X, const double* U,
+                          const double* Qdiag, const double* Rdiag, const double* Qfdiag, const double* xf, const double* w,
+                          int ncon, const rbq_constraint* cons, const int32_t* idx_pool, int64_t nidx, const double* val_pool,
+                          int64_t nval, const double* lambda, const double* mu, int64_t dual_stride, double* Exx, double* Ex,
+                          double* Euu, double* Eux, double* Eu, double* c, double* J);
 
 /* ---- measurement aid: saturating DFMA loop, returns achieved FP64 TFLOP/s -------------- */
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops);

@@ -302,6 +302,29 @@ function al_cost_expansion_dev!(n::Integer, m::Integer, N::Integer, B::Integer, 
         Euu, Eux, Eu, c, J), "rbq_al_cost_expansion_dev")
 end
 
+"""
+Host-array form of the same expansion for one trajectory: X n×N, U m×(N-1), `cons::Vector{RbqConstraint}`, `idx_pool::Vector{Int32}`
+(0-based state indices), `val_pool`, `lambda`, `mu` flat in table order.  Returns (J, c, Exx, Ex, Euu, Eux, Eu).
+"""
+function al_cost_expansion(X::Matrix{Float64}, U::Matrix{Float64}, Qdiag::Vector{Float64}, Rdiag::Vector{Float64},
+                           Qfdiag::Vector{Float64}, xf::Vector{Float64}, cons::Vector{RbqConstraint}, idx_pool::Vector{Int32},
+                           val_pool::Vector{Float64}, lambda::Vector{Float64}, mu::Vector{Float64}; w=nothing)
+    n, N = size(X)
+    m = size(U, 1)
+    Exx = Array{Float64,3}(undef, n, n, N); Ex = Matrix{Float64}(undef, n, N)
+    Euu = Array{Float64,3}(undef, m, m, N - 1); Eux = Array{Float64,3}(undef, m, n, N - 1); Eu = Matrix{Float64}(undef, m, N - 1)
+    c = Vector{Float64}(undef, length(lambda)); J = Vector{Float64}(undef, N)
+    wp = w === nothing ? Ptr{Float64}(C_NULL) : pointer(w)
+    GC.@preserve X U Qdiag Rdiag Qfdiag xf cons idx_pool val_pool lambda mu w Exx Ex Euu Eux Eu c J check(ccall(
+        (:rbq_al_cost_expansion, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Cint, Ptr{RbqConstraint}, Ptr{Int32}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        handle().ptr, n, m, N, 1, X, U, Qdiag, Rdiag, Qfdiag, xf, wp, length(cons), cons, idx_pool, length(idx_pool), val_pool,
+        length(val_pool), lambda, mu, 0, Exx, Ex, Euu, Eux, Eu, c, J), "rbq_al_cost_expansion")
+    return J, c, Exx, Ex, Euu, Eux, Eu
+end
+
 "Page-lock a Julia array in place so that mc_static reads it over PCIe directly (zero-copy); unregister before it is freed."
 host_register(A::Array) = check(ccall((:rbq_host_register, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), handle().ptr, A, sizeof(A)), "rbq_host_register")
 host_unregister(A::Array) = check(ccall((:rbq_host_unregister, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, A), "rbq_host_unregister")

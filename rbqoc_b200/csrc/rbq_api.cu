@@ -1075,6 +1075,61 @@ int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B,
     return RBQ_OK;
 }
 
+// host-pointer form: every input is packed into one device arena, every output into another
+int rbq_al_cost_expansion(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* X, const double* U, const double* Qdiag,
+                          const double* Rdiag, const double* Qfdiag, const double* xf, const double* w, int ncon,
+                          const rbq_constraint* cons, const int32_t* idx_pool, int64_t nidx, const double* val_pool, int64_t nval,
+                          const double* lambda, const double* mu, int64_t dual_stride, double* Exx, double* Ex, double* Euu,
+                          double* Eux, double* Eu, double* c, double* J) {
+    ENTER(h);
+    if (n < 1 || m < 1 || N < 1 || B < 0 || B > 65535 || ncon < 0 || dual_stride < 0 || nidx < 0 || nval < 0)
+        return fail(h, RBQ_E_SIZE, "rbq_al_cost_expansion: n=%d m=%d N=%lld B=%lld ncon=%d", n, m, (long long)N, (long long)B, ncon);
+    if (B == 0) return RBQ_OK;
+    if (!X || (N > 1 && !U) || !Qdiag || !Rdiag || !Qfdiag || !xf) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion: null pointer");
+    if (ncon > 0 && (!cons || !val_pool || !lambda || !mu || (nidx > 0 && !idx_pool))) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion: null constraint data");
+    if (Exx && (!Ex || (N > 1 && (!Euu || !Eux || !Eu)))) return fail(h, RBQ_E_NULL, "rbq_al_cost_expansion: Exx given without the other blocks");
+    int64_t dual_size = 0;
+    for (int i = 0; i < ncon; ++i) {
+        const int64_t end = cons[i].dual_off + (cons[i].k1 - cons[i].k0) * cons[i].p;
+        if (cons[i].dual_off < dual_size || cons[i].k0 < 0 || cons[i].k1 > N || cons[i].k1 < cons[i].k0)
+            return fail(h, RBQ_E_SIZE, "rbq_al_cost_expansion: constraint %d: rows must be in dual_off order with knots inside [0, N]", i);
+        dual_size = end;
+    }
+    if (dual_stride != 0 && dual_stride < dual_size) return fail(h, RBQ_E_SIZE, "rbq_al_cost_expansion: dual_stride too small");
+    const int64_t nd = dual_stride ? dual_stride * (B - 1) + dual_size : dual_size;     // doubles of lambda / mu read
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // arena layout (bytes)
+    const size_t sX = sizeof(double) * B * N * n, sU = sizeof(double) * B * (N - 1) * m, sn = sizeof(double) * n, sm_ = sizeof(double) * m;
+    const size_t sW = w ? sizeof(double) * N : 0, sC = sizeof(rbq_constraint) * ncon, sI = sizeof(int32_t) * nidx, sV = sizeof(double) * nval;
+    const size_t sD = sizeof(double) * nd;
+    size_t off = 0;
+    auto take = [&](size_t b) { const size_t o = off; off += up(b ? b : 16); return o; };
+    const size_t oX = take(sX), oU = take(sU), oQ = take(sn), oR = take(sm_), oQf = take(sn), oxf = take(sn), oW = take(sW), oC = take(sC),
+                 oI = take(sI), oV = take(sV), oL = take(sD), oM = take(sD);
+    void* in; CKL(dev_buf(h, B_IN0, off, &in));
+    char* ib = (char*)in;
+    auto put = [&](size_t o, const void* src, size_t b) -> cudaError_t { return b && src ? cudaMemcpyAsync(ib + o, src, b, cudaMemcpyHostToDevice, h->stream) : cudaSuccess; };
+    CK(put(oX, X, sX)); CK(put(oU, U, sU)); CK(put(oQ, Qdiag, sn)); CK(put(oR, Rdiag, sm_)); CK(put(oQf, Qfdiag, sn)); CK(put(oxf, xf, sn));
+    CK(put(oW, w, sW)); CK(put(oC, cons, sC)); CK(put(oI, idx_pool, sI)); CK(put(oV, val_pool, sV)); CK(put(oL, lambda, sD)); CK(put(oM, mu, sD));
+    const size_t sExx = Exx ? sizeof(double) * B * N * n * n : 0, sEx = Exx ? sizeof(double) * B * N * n : 0;
+    const size_t sEuu = Exx ? sizeof(double) * B * (N - 1) * m * m : 0, sEux = Exx ? sizeof(double) * B * (N - 1) * m * n : 0;
+    const size_t sEu = Exx ? sizeof(double) * B * (N - 1) * m : 0, sc = c ? sizeof(double) * B * dual_size : 0, sJ = J ? sizeof(double) * B * N : 0;
+    off = 0;
+    const size_t oExx = take(sExx), oEx = take(sEx), oEuu = take(sEuu), oEux = take(sEux), oEu = take(sEu), oc = take(sc), oJ = take(sJ);
+    void* out; CKL(dev_buf(h, B_OUT0, off, &out));
+    char* ob = (char*)out;
+    auto dp = [&](size_t o, const void* host) -> double* { return host ? (double*)(ob + o) : nullptr; };
+    CKL(launch_al_cost(h, n, m, N, B, dual_stride, (double*)(ib + oX), (double*)(ib + oU), (double*)(ib + oQ), (double*)(ib + oR),
+                       (double*)(ib + oQf), (double*)(ib + oxf), w ? (double*)(ib + oW) : nullptr, ncon, (rbq_constraint*)(ib + oC),
+                       (int32_t*)(ib + oI), (double*)(ib + oV), (double*)(ib + oL), (double*)(ib + oM), dp(oExx, Exx), dp(oEx, Exx),
+                       dp(oEuu, Exx), dp(oEux, Exx), dp(oEu, Exx), dp(oc, c), dp(oJ, J)));
+    auto get = [&](void* dst, size_t o, size_t b) -> cudaError_t { return b && dst ? cudaMemcpyAsync(dst, ob + o, b, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess; };
+    CK(get(Exx, oExx, sExx)); CK(get(Ex, oEx, sEx)); CK(get(Euu, oEuu, sEuu)); CK(get(Eux, oEux, sEux)); CK(get(Eu, oEu, sEu));
+    CK(get(c, oc, sc)); CK(get(J, oJ, sJ));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+
 // ---- FP64 roofline denominator -------------------------------------------------------------------------------------------
 int rbq_fp64_peak(rbq_handle* h, int iters, double* tflops) {
     ENTER(h);

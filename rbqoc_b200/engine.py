@@ -405,6 +405,35 @@ class Engine:
                                                  _ptr(d_Euu), _ptr(d_Eux), _ptr(d_Eu), float(rho), int(reg_type), _ptr(d_K),
                                                  _ptr(d_d), _ptr(d_dV), _ptr(d_fail)), "rbq_backward_pass_dev")
 
+    def al_cost_expansion(self, X, U, Qdiag, Rdiag, Qfdiag, xf, table, lam, mu, w=None, expand=True, shared_duals=True):
+        """Host-array form of the AL cost expansion.  X (N, n) or (B, N, n), U (N-1, m) or (B, N-1, m); `table` a
+        spin.ConstraintTable; lam / mu flat (dual_size,) or (B, dual_size) when not shared.  Returns a dict with J (.., N),
+        c (.., dual_size) and, if `expand`, Exx (.., N, n, n), Ex, Euu, Eux (.., N-1, m, n), Eu in math layout."""
+        X = _f64(X); U = _f64(U)
+        single = X.ndim == 2
+        if single:
+            X, U = X[None], U[None]
+        B, N, n = X.shape
+        m = U.shape[2]
+        lam, mu = _f64(lam), _f64(mu)
+        rows = (_lib.Constraint * max(table.ncon, 1))(*table.rows)
+        idx = np.asarray(table.idx or [0], dtype=np.int32); val = np.asarray(table.val or [0.0], dtype=np.float64)
+        J = np.empty((B, N)); c = np.empty((B, table.dual_size))
+        if expand:
+            Exx = np.empty((B, N, n, n)); Ex = np.empty((B, N, n)); Euu = np.empty((B, N - 1, m, m))
+            Eux = np.empty((B, N - 1, n, m)); Eu = np.empty((B, N - 1, m))
+        else:
+            Exx = Ex = Euu = Eux = Eu = None
+        self._ck(self._lib.rbq_al_cost_expansion(self._h, n, m, N, B, _ptr(X), _ptr(U), _ptr(_f64(Qdiag)), _ptr(_f64(Rdiag)),
+                                                 _ptr(_f64(Qfdiag)), _ptr(_f64(xf)), _ptr(None if w is None else _f64(w)), table.ncon,
+                                                 C.cast(rows, C.c_void_p), _ptr(idx), len(table.idx), _ptr(val), len(table.val),
+                                                 _ptr(lam), _ptr(mu), 0 if shared_duals else table.dual_size, _ptr(Exx), _ptr(Ex),
+                                                 _ptr(Euu), _ptr(Eux), _ptr(Eu), _ptr(c), _ptr(J)), "rbq_al_cost_expansion")
+        out = {"J": J, "c": c}
+        if expand:
+            out.update(Exx=np.swapaxes(Exx, -1, -2), Ex=Ex, Euu=np.swapaxes(Euu, -1, -2), Eux=np.swapaxes(Eux, -1, -2), Eu=Eu)
+        return {k: v[0] for k, v in out.items()} if single else out
+
     def al_cost_expansion_dev(self, n, m, N, d_X, d_U, d_Qdiag, d_Rdiag, d_Qfdiag, d_xf, d_w, table, d_lambda, d_mu,
                               d_Exx, d_Ex, d_Euu, d_Eux, d_Eu, d_c, d_J, B=1, dual_stride=0):
         """Augmented-Lagrangian cost blocks of all knots (rbq_al_cost_expansion_dev).  `table` is a spin.ConstraintTable

@@ -120,3 +120,33 @@ def test_al_cost_expansion_batch_equals_single_calls():
             got = [t[b].cpu().numpy() for t in out]
             assert np.array_equal(got[6], J1) and np.array_equal(got[0], Exx1) and np.array_equal(got[1], Ex1)
             assert np.array_equal(got[2], Euu1) and np.array_equal(got[4], Eu1) and np.array_equal(got[5], c1)
+
+
+def test_al_cost_expansion_host_pointer_form(engine):
+    """rbq_al_cost_expansion (host arrays in, host arrays out) returns what the oracle states; batch with per-trajectory
+    multipliers; values-only mode; argument errors come back as codes, not crashes."""
+    from oracle import al_cost
+
+    rng = np.random.default_rng(31)
+    X, U, Qd, Rd, Qfd, xf, w, table, lam, mu, duals = _al_problem(rng, 10, 11, 1)
+    Jr, Exxr, Exr, Euur, Euxr, Eur, cr = al_cost.expansion(X, U, Qd, Rd, Qfd, xf, table.specs, duals, w)
+    got = engine.al_cost_expansion(X, U, Qd, Rd, Qfd, xf, table, lam, mu, w=w)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+    assert rel(got["J"], Jr) < 1e-12 and rel(got["Exx"], Exxr) < 1e-12 and rel(got["Ex"], Exr) < 1e-12
+    assert rel(got["Euu"], Euur) < 1e-12 and rel(got["Eu"], Eur) < 1e-12 and np.all(got["Eux"] == 0)
+    cflat = np.concatenate([c.reshape(-1) for c in cr])
+    fin = np.isfinite(cflat)
+    assert np.array_equal(np.isneginf(got["c"]), np.isneginf(cflat)) and rel(got["c"][fin], cflat[fin]) < 1e-12
+    vals = engine.al_cost_expansion(X, U, Qd, Rd, Qfd, xf, table, lam, mu, w=w, expand=False)
+    assert np.array_equal(vals["J"], got["J"]) and "Exx" not in vals
+    # two independent problems with their own multipliers
+    Xs, Us = np.stack([X, X * 0.9]), np.stack([U, -U])
+    lams, mus = np.stack([lam, 2 * lam]), np.stack([mu, 3 * mu])
+    both = engine.al_cost_expansion(Xs, Us, Qd, Rd, Qfd, xf, table, lams, mus, w=w, shared_duals=False)
+    one = engine.al_cost_expansion(Xs[1], Us[1], Qd, Rd, Qfd, xf, table, lams[1], mus[1], w=w)
+    assert np.array_equal(both["J"][0], got["J"]) and np.array_equal(both["J"][1], one["J"]) and np.array_equal(both["Exx"][1], one["Exx"])
+    # a table whose knot range leaves the trajectory is refused
+    bad = spin.ConstraintTable(11, 1, 10).norm(0, 10, range(4))
+    bad.rows[0].k1 = 11
+    with pytest.raises(rbq.RbqError):
+        engine.al_cost_expansion(X, U, Qd, Rd, Qfd, xf, bad, np.zeros(11), np.ones(11))
