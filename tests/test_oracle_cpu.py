@@ -438,3 +438,32 @@ def test_grab_and_sample_controls_follow_the_reference_save_formats():
     assert np.array_equal(c4, cs)
     with pytest.raises(RuntimeError, match="h5py"):
         spin.read_save("/nonexistent/pulse.h5")
+
+
+def test_reference_constraint_lists_have_the_reference_layout():
+    """spin13.jl:136-152, spin12.jl:280-296, spin30.jl:301-320: knot ranges (1-based 2:N-2, N-1:N-1, N:N, 2:N-1) and the index
+    sets of the goal and unit-norm constraints."""
+    from rbqoc_b200 import _lib, spin
+
+    N = 21
+    for make, n, ctrl, goal, blocks in (
+            (spin.spin13_constraints, 11, 9, list(range(9)), [0, 4]),
+            (spin.spin12_constraints, 43, 9, list(range(9)), [0, 4] + list(range(11, 43, 4))),
+            (spin.spin30_constraints, 56, 13, list(range(8)) + [12], list(range(15, 55, 4)) + [0, 4, 8])):
+        t = make(N, np.arange(n, dtype=float))
+        assert t.n == n and t.ncon == 3 + len(blocks)
+        b0, b1, g = t.specs[0], t.specs[1], t.specs[2]
+        assert (b0["k0"], b0["k1"]) == (1, N - 2) and (b1["k0"], b1["k1"]) == (N - 2, N - 1) and (g["k0"], g["k1"]) == (N - 1, N)
+        fin = np.isfinite(b0["zmax"])
+        assert list(np.nonzero(fin)[0]) == [ctrl] and b0["zmax"][ctrl] == 0.5 and b0["zmin"][ctrl] == -0.5
+        assert b1["zmax"][ctrl] == 0.0 and b1["zmin"][ctrl] == 0.0
+        assert g["idx"] == goal and np.array_equal(g["target"], np.asarray(goal, dtype=float))
+        norms = t.specs[3:]
+        assert sorted(s["idx"][0] for s in norms) == sorted(blocks)
+        assert all(s["kind"] == "norm" and (s["k0"], s["k1"]) == (1, N - 1) and s["val"] == 1.0 and len(s["idx"]) == 4 for s in norms)
+        # the packed rows agree with the description, duals laid out back to back
+        off = 0
+        for row, spec in zip(t.rows, t.specs):
+            assert row.dual_off == off and (row.k0, row.k1) == (spec["k0"], spec["k1"])
+            off += (row.k1 - row.k0) * row.p
+        assert off == t.dual_size and t.rows[0].kind == _lib.CON_BOUND and t.rows[0].p == 2 * (n + 1)
