@@ -393,6 +393,15 @@ int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B,
                               const double* d_w, int ncon, const rbq_constraint* d_cons, const int32_t* d_idx_pool,
                               const double* d_val_pool, const double* d_lambda, const double* d_mu, int64_t dual_stride,
                               double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c, double* d_J);
+/* Outer-loop updates of the same table on the device (Altro dual_update!, penalty_update!, max_violation; external):
+ *   lambda <- clamp(lambda + mu c, lo, lambda_max), lo = 0 for RBQ_CON_BOUND (inequalities), -lambda_max for equalities;
+ *   mu <- min(phi mu, mu_max);   *d_max_violation = max over entries of |c| (equalities) or max(c, 0) (inequalities).
+ * c as rbq_al_cost_expansion_dev wrote it (entries of absent bounds, -inf, are skipped); update = 0: violation only.
+ * max_p = the largest p of the table (sizes the grid); with dual_stride = 0 and B > 1 the violation covers all B
+ * trajectories and the shared multipliers are updated from trajectory 0. */
+int rbq_al_dual_update_dev(rbq_handle* h, int64_t N, int64_t B, int ncon, const rbq_constraint* d_cons, int64_t max_p,
+                           const double* d_c, double* d_lambda, double* d_mu, int64_t dual_stride, double phi, double mu_max,
+                           double lambda_max, int update, double* d_max_violation);
 /* host-pointer form (synchronous): the same with every array in host memory; nidx / nval = lengths of the two pools. */
 int rbq_al_cost_expansion(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* X, const double* U,
                           const double* Qdiag, const double* Rdiag, const double* Qfdiag, const double* xf, const double* w,

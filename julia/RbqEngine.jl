@@ -302,6 +302,14 @@ function al_cost_expansion_dev!(n::Integer, m::Integer, N::Integer, B::Integer, 
         Euu, Eux, Eu, c, J), "rbq_al_cost_expansion_dev")
 end
 
+"Multiplier / penalty update and largest violation on the device (Altro dual_update!, penalty_update!, max_violation); device pointers."
+al_dual_update_dev!(N::Integer, B::Integer, ncon::Integer, cons, max_p::Integer, c, lambda, mu, dual_stride::Integer, phi::Real, mu_max::Real,
+                    lambda_max::Real, update::Bool, max_violation) =
+    check(ccall((:rbq_al_dual_update_dev, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Float64, Float64, Float64, Cint, Ptr{Cvoid}),
+        handle().ptr, N, B, ncon, cons, max_p, c, lambda, mu, dual_stride, phi, mu_max, lambda_max, update ? 1 : 0, max_violation),
+        "rbq_al_dual_update_dev")
+
 """
 Host-array form of the same expansion for one trajectory: X n×N, U m×(N-1), `cons::Vector{RbqConstraint}`, `idx_pool::Vector{Int32}`
 (0-based state indices), `val_pool`, `lambda`, `mu` flat in table order.  Returns (J, c, Exx, Ex, Euu, Eux, Eu).

@@ -136,6 +136,7 @@ SIGNATURES = {
     "rbq_backward_pass": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
     "rbq_backward_pass_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
     "rbq_al_cost_expansion_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64] + [_P] * 7 + [C.c_int] + [_P] * 5 + [_I64] + [_P] * 7),
+    "rbq_al_dual_update_dev": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _I64, _P, _P, _P, _I64, _D, _D, _D, C.c_int, _P]),
     "rbq_al_cost_expansion": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64] + [_P] * 7 + [C.c_int, _P, _P, _I64, _P, _I64, _P, _P, _I64] + [_P] * 7),
     "rbq_fp64_peak": (C.c_int, [_P, C.c_int, C.POINTER(_D)]),
 }

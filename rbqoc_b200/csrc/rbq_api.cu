@@ -1075,6 +1075,19 @@ int rbq_al_cost_expansion_dev(rbq_handle* h, int n, int m, int64_t N, int64_t B,
     return RBQ_OK;
 }
 
+// outer-loop updates on the device: multipliers, penalties, largest violation
+int rbq_al_dual_update_dev(rbq_handle* h, int64_t N, int64_t B, int ncon, const rbq_constraint* d_cons, int64_t max_p,
+                           const double* d_c, double* d_lambda, double* d_mu, int64_t dual_stride, double phi, double mu_max,
+                           double lambda_max, int update, double* d_max_violation) {
+    ENTER(h);
+    if (N < 1 || B < 0 || ncon < 0 || max_p < 1 || dual_stride < 0) return fail(h, RBQ_E_SIZE, "rbq_al_dual_update_dev: N=%lld B=%lld ncon=%d max_p=%lld", (long long)N, (long long)B, ncon, (long long)max_p);
+    if (!d_max_violation) return fail(h, RBQ_E_NULL, "rbq_al_dual_update_dev: null pointer");
+    if (ncon == 0 || B == 0) { CK(cudaMemsetAsync(d_max_violation, 0, sizeof(double), h->stream)); return RBQ_OK; }
+    if (!d_cons || !d_c || (update && (!d_lambda || !d_mu))) return fail(h, RBQ_E_NULL, "rbq_al_dual_update_dev: null pointer");
+    CKL(launch_al_dual_update(h, ncon, d_cons, N * max_p, B, dual_stride, d_c, d_lambda, d_mu, phi, mu_max, lambda_max, update, d_max_violation));
+    return RBQ_OK;
+}
+
 // host-pointer form: every input is packed into one device arena, every output into another
 int rbq_al_cost_expansion(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* X, const double* U, const double* Qdiag,
                           const double* Rdiag, const double* Qfdiag, const double* xf, const double* w, int ncon,

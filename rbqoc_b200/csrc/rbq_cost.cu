@@ -149,4 +149,57 @@ int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, int64_t B, int64_t du
     return (int)cudaGetLastError();
 }
 
+// ---- outer-loop updates of the augmented Lagrangian (Altro dual_update! / penalty_update! / max_violation) ----
+// One block row per constraint, blockIdx.y walks its entries in chunks.  lambda <- clamp(lambda + mu c, lo, lambda_max) with
+// lo = 0 for inequalities (BoundConstraint) and -lambda_max for equalities; then mu <- min(phi mu, mu_max).  Entries whose c
+// is -inf (absent bounds) are left alone.  The largest violation (|c| for equalities, max(c, 0) for inequalities) is
+// reduced per block and folded into viol[0] with an atomic max on the bit pattern (non-negative doubles order like integers).
+constexpr int DU_THREADS = 256, DU_CHUNK = 4096;
+__global__ void __launch_bounds__(DU_THREADS) al_dual_update_kernel(int ncon, const rbq_constraint* __restrict__ cons, int64_t B,
+                                                                    int64_t dual_stride, const double* __restrict__ c,
+                                                                    double* __restrict__ lambda, double* __restrict__ mu, double phi,
+                                                                    double mu_max, double lambda_max, int update,
+                                                                    unsigned long long* __restrict__ viol) {
+    const rbq_constraint cn = cons[blockIdx.x];
+    const rbq_constraint last = cons[ncon - 1];
+    const int64_t dual_size = last.dual_off + (last.k1 - last.k0) * last.p;
+    const int64_t len = (cn.k1 - cn.k0) * cn.p;
+    const bool ineq = cn.kind == RBQ_CON_BOUND;
+    double vmax = 0.0;
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t base = (int64_t)blockIdx.y * DU_CHUNK;
+        for (int64_t e = base + threadIdx.x; e < len && e < base + DU_CHUNK; e += DU_THREADS) {
+            const double cv = c[b * dual_size + cn.dual_off + e];
+            if (!(cv > -INFINITY)) continue;                                  // absent bound (NaN would be a caller error: skipped too)
+            vmax = fmax(vmax, ineq ? fmax(cv, 0.0) : fabs(cv));
+            if (update && (dual_stride != 0 || b == 0)) {                     // shared multipliers: updated from trajectory 0 only
+                const int64_t i = b * dual_stride + cn.dual_off + e;
+                const double l = fma(mu[i], cv, lambda[i]);
+                lambda[i] = fmin(fmax(l, ineq ? 0.0 : -lambda_max), lambda_max);
+                mu[i] = fmin(phi * mu[i], mu_max);
+            }
+        }
+    }
+    __shared__ double red[DU_THREADS];
+    red[threadIdx.x] = vmax;
+    __syncthreads();
+    for (int s = DU_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && red[0] > 0.0) atomicMax(viol, (unsigned long long)__double_as_longlong(red[0]));
+}
+
+int launch_al_dual_update(rbq_handle* h, int ncon, const rbq_constraint* d_cons, int64_t max_len, int64_t B, int64_t dual_stride,
+                          const double* d_c, double* d_lambda, double* d_mu, double phi, double mu_max, double lambda_max,
+                          int update, double* d_viol) {
+    cudaError_t e = cudaMemsetAsync(d_viol, 0, sizeof(double), h->stream);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned chunks = (unsigned)((max_len + DU_CHUNK - 1) / DU_CHUNK);
+    al_dual_update_kernel<<<dim3((unsigned)ncon, chunks ? chunks : 1), DU_THREADS, 0, h->stream>>>(
+        ncon, d_cons, B, dual_stride, d_c, d_lambda, d_mu, phi, mu_max, lambda_max, update, reinterpret_cast<unsigned long long*>(d_viol));
+    h->launches++;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace rbq

@@ -120,6 +120,9 @@ int launch_al_cost(rbq_handle* h, int n, int m, int64_t N, int64_t B, int64_t du
                    const rbq_constraint* d_cons, const int32_t* d_idx_pool, const double* d_val_pool, const double* d_lambda,
                    const double* d_mu, double* d_Exx, double* d_Ex, double* d_Euu, double* d_Eux, double* d_Eu, double* d_c,
                    double* d_J);
+int launch_al_dual_update(rbq_handle* h, int ncon, const rbq_constraint* d_cons, int64_t max_len, int64_t B, int64_t dual_stride,
+                          const double* d_c, double* d_lambda, double* d_mu, double phi, double mu_max, double lambda_max,
+                          int update, double* d_viol);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_t, const double* d_dt, double* d_AB);
 

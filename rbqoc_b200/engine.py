@@ -405,6 +405,15 @@ class Engine:
                                                  _ptr(d_Euu), _ptr(d_Eux), _ptr(d_Eu), float(rho), int(reg_type), _ptr(d_K),
                                                  _ptr(d_d), _ptr(d_dV), _ptr(d_fail)), "rbq_backward_pass_dev")
 
+    def al_dual_update_dev(self, N, table, d_c, d_lambda, d_mu, d_max_violation, phi=10.0, mu_max=1e8, lambda_max=1e8, update=True,
+                           B=1, dual_stride=0):
+        """Multiplier / penalty update and largest constraint violation on the device (rbq_al_dual_update_dev)."""
+        max_p = max((r.p for r in table.rows), default=1)
+        self._ck(self._lib.rbq_al_dual_update_dev(self._h, int(N), int(B), int(table.ncon), C.c_void_p(table.d_cons.data_ptr()),
+                                                  int(max_p), _ptr(d_c), _ptr(d_lambda), _ptr(d_mu), int(dual_stride), float(phi),
+                                                  float(mu_max), float(lambda_max), 1 if update else 0, _ptr(d_max_violation)),
+                 "rbq_al_dual_update_dev")
+
     def al_cost_expansion(self, X, U, Qdiag, Rdiag, Qfdiag, xf, table, lam, mu, w=None, expand=True, shared_duals=True):
         """Host-array form of the AL cost expansion.  X (N, n) or (B, N, n), U (N-1, m) or (B, N-1, m); `table` a
         spin.ConstraintTable; lam / mu flat (dual_size,) or (B, dual_size) when not shared.  Returns a dict with J (.., N),

@@ -195,9 +195,15 @@ def test_al_ilqr_on_device_reduces_merit_as_predicted_and_constraint_violation(e
         viol.append(violation(c))
         if os.environ.get("RBQ_TEST_VERBOSE"):
             print("outer", outer, "violation", viol[-1], "merit", float(J.sum()))
+        # dual update, then penalty x10, on the device; checked against the same update in torch
         cfin = torch.where(torch.isfinite(c), c, torch.zeros_like(c))
-        lam = torch.where(ineq, torch.clamp(lam + mu * cfin, min=0.0), lam + mu * cfin)      # dual update, then penalty x10
-        mu = mu * 10.0
+        lam_ref = torch.where(ineq, torch.clamp(lam + mu * cfin, min=0.0), lam + mu * cfin)
+        mu_ref = torch.where(torch.isfinite(c), mu * 10.0, mu)
+        dviol = torch.empty(1, dtype=torch.float64, device=dev)
+        eng.al_dual_update_dev(N, table, c, lam, mu, dviol, phi=10.0)
+        torch.cuda.synchronize()
+        assert float(dviol[0]) == viol[-1]
+        assert torch.allclose(lam, lam_ref, rtol=1e-12, atol=1e-14) and torch.equal(mu, mu_ref)
     assert checked >= 10
     assert viol[-1] < 0.5 * viol[0] and all(b <= a for a, b in zip(viol, viol[1:])), viol
     eng.close()
