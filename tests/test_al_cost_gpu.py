@@ -150,3 +150,37 @@ def test_al_cost_expansion_host_pointer_form(engine):
     bad.rows[0].k1 = 11
     with pytest.raises(rbq.RbqError):
         engine.al_cost_expansion(X, U, Qd, Rd, Qfd, xf, bad, np.zeros(11), np.ones(11))
+
+
+def test_al_dual_update_matches_numpy():
+    """lambda <- clamp(lambda + mu c) (projected at 0 for bounds), mu <- min(phi mu, mu_max), largest violation; absent bounds
+    (-inf) untouched; violation-only mode leaves the duals alone; clamps at lambda_max."""
+    dev = torch.device("cuda", 0)
+    eng = rbq.Engine(0); eng.use_torch_stream()
+    rng = np.random.default_rng(41)
+    N = 57
+    table = spin.spin13_constraints(N, rng.standard_normal(11)).upload(dev)
+    D = table.dual_size
+    c = rng.standard_normal(D); lam = rng.standard_normal(D); mu = 10.0 ** rng.uniform(0, 9, D)
+    ineq = np.zeros(D, dtype=bool)
+    for row, (o, kn, p) in zip(table.rows, table.dual_slices()):
+        ineq[o:o + kn * p] = row.kind == rbq.CON_BOUND
+    absent = ineq & (rng.uniform(size=D) < 0.5)
+    c[absent] = -np.inf
+    lmax, mmax, phi = 5.0e3, 1.0e8, 10.0
+    live = ~absent
+    lam_ref, mu_ref = lam.copy(), mu.copy()
+    l = lam + mu * np.where(live, c, 0.0)
+    lam_ref[live] = np.clip(l, np.where(ineq, 0.0, -lmax), lmax)[live]
+    mu_ref[live] = np.minimum(phi * mu, mmax)[live]
+    viol_ref = max(np.max(np.abs(c[live & ~ineq])), np.max(np.maximum(c[live & ineq], 0.0)))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dc, dl, dm, dv = d(c), d(lam), d(mu), torch.empty(1, dtype=torch.float64, device=dev)
+    eng.al_dual_update_dev(N, table, dc, dl, dm, dv, phi=phi, mu_max=mmax, lambda_max=lmax, update=False)
+    torch.cuda.synchronize()
+    assert float(dv[0]) == viol_ref and np.array_equal(dl.cpu().numpy(), lam) and np.array_equal(dm.cpu().numpy(), mu)
+    eng.al_dual_update_dev(N, table, dc, dl, dm, dv, phi=phi, mu_max=mmax, lambda_max=lmax)
+    torch.cuda.synchronize()
+    assert float(dv[0]) == viol_ref
+    assert np.allclose(dl.cpu().numpy(), lam_ref, rtol=1e-12, atol=1e-9) and np.array_equal(dm.cpu().numpy(), mu_ref)
+    assert np.any(lam_ref == lmax) and np.any(mu_ref == mmax) and np.any(lam_ref[ineq & live] == 0.0)
