@@ -73,7 +73,9 @@ template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __s
 template <int NW_> RBQ_DEV bool bp_sync_or(bool pred) { return NW_ == 1 ? __any_sync(0xffffffffu, pred) != 0 : __syncthreads_or(pred) != 0; }
 
 template <int NW, int MODE, int MM, int NN>
-__global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : 1) backward_pass_kernel(const BackwardArgs a) {
+// two problems per SM where the shared memory allows it (n <= 44: under 100 KB each): batches of mid-size problems then run
+// two per SM at a time, which needs the kernel within 128 registers
+__global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 2 : 1)) backward_pass_kernel(const BackwardArgs a) {
     constexpr int BP_THREADS = 32 * NW;
     extern __shared__ __align__(16) double sm[];
     // MM: the number of controls when known at compile time (1 for every reference model but the time-optimal spin15, which
