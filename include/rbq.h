@@ -136,7 +136,8 @@ int rbq_synchronize(rbq_handle* h);
 int rbq_set_sweep_centre(rbq_handle* h, double fq0, double da0);
 /* Page-locked host memory for the caller's buffers (e.g. the nabla-f storage a Julia caller hands to rbq_jacobians):
  * host-pointer entry points accept any host memory, but copies from/to pinned memory run at full PCIe rate and let the
- * chunked sweeps overlap upload, compute and download.  Free with rbq_host_free. */
+ * chunked sweeps overlap upload, compute and download.  Free with rbq_host_free (h may be NULL there: page-locked memory
+ * is process wide and may outlive the handle that allocated it). */
 int rbq_host_alloc(rbq_handle* h, int64_t bytes, void** out);
 int rbq_host_free(rbq_handle* h, void* ptr);
 /* Page-lock (and map for the device) memory the caller already owns -- e.g. a Julia Array that is reused across calls --
@@ -144,6 +145,14 @@ int rbq_host_free(rbq_handle* h, void* ptr);
  * cudaHostRegister / cudaHostUnregister underneath; the range must stay allocated until it is unregistered. */
 int rbq_host_register(rbq_handle* h, void* ptr, int64_t bytes);
 int rbq_host_unregister(rbq_handle* h, void* ptr);
+/* Tuning / A-B switches.  The library reads its RBQ_* environment variables ONCE, in rbq_create, into the handle; no call
+ * reads the environment afterwards.  rbq_set_option changes one switch of one handle later on (same names and value
+ * syntax as the environment variables; value NULL or "" restores the default).  Names: RBQ_NO_TABLE_CLASS, RBQ_MC_ZEROCOPY,
+ * RBQ_MC_CHUNK_WAVES ("first,rest"), RBQ_MC_VARIANT, RBQ_PEAK_MODE, RBQ_NOISE_GATE_PARALLEL, RBQ_LINDBLAD_NO_SHARED_MAP,
+ * RBQ_LINDBLAD_TABLE, RBQ_ROLLOUT_PACKED, RBQ_ROLLOUT_SCAN, RBQ_JAC_NT_UNSCENTED, RBQ_JAC_STRUCTURED, RBQ_JAC_STAGE_KB,
+ * RBQ_JAC_STAGED, RBQ_BP_TMA, RBQ_BP_GENERIC, RBQ_BP_WARPS.  Every switch selects between kernels that meet the same parity
+ * bound; none changes results beyond rounding.  Unknown names / malformed values return RBQ_E_SIZE. */
+int rbq_set_option(rbq_handle* h, const char* name, const char* value);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`). */
 int64_t rbq_launch_count(const rbq_handle* h);
 

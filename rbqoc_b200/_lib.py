@@ -93,6 +93,7 @@ SIGNATURES = {
     "rbq_set_stream": (C.c_int, [_P, _P]),
     "rbq_set_sweep_centre": (C.c_int, [_P, _D, _D]),
     "rbq_synchronize": (C.c_int, [_P]),
+    "rbq_set_option": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "rbq_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "rbq_host_register": (C.c_int, [_P, _P, _I64]),
     "rbq_host_unregister": (C.c_int, [_P, _P]),

@@ -109,9 +109,54 @@ static bool make_gate_tables(int gate, GateIso* gi, GateRot* gr) {
     return true;
 }
 
+// ---- tuning options: latched from the environment in rbq_create, changed later only by rbq_set_option ----------------
+static const char* const kOptionNames[] = {"RBQ_NO_TABLE_CLASS", "RBQ_MC_ZEROCOPY", "RBQ_MC_CHUNK_WAVES", "RBQ_MC_VARIANT", "RBQ_PEAK_MODE",
+                                           "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE",
+                                           "RBQ_ROLLOUT_PACKED", "RBQ_ROLLOUT_SCAN", "RBQ_JAC_NT_UNSCENTED", "RBQ_JAC_STRUCTURED",
+                                           "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED", "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS"};
+int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
+    const bool unset = !value || !*value;
+    const int v = unset ? -1 : atoi(value);
+    auto is = [&](const char* n) { return strcmp(name, n) == 0; };
+    if (is("RBQ_NO_TABLE_CLASS")) h->opt.no_table_class = unset ? 0 : (v != 0);
+    else if (is("RBQ_MC_ZEROCOPY")) h->opt.mc_zerocopy = unset ? 1 : (v != 0);
+    else if (is("RBQ_MC_CHUNK_WAVES")) {
+        int a1 = 0, a2 = 0;
+        h->opt.chunk_first = 1; h->opt.chunk_rest = 1;   // in waves (measured best: tools/tune_e2e.py)
+        if (!unset) {
+            if (sscanf(value, "%d,%d", &a1, &a2) != 2 || a1 < 1 || a2 < 1) return RBQ_E_SIZE;
+            h->opt.chunk_first = a1; h->opt.chunk_rest = a2;
+        }
+    }
+    else if (is("RBQ_MC_VARIANT")) h->opt.mc_variant = v;
+    else if (is("RBQ_PEAK_MODE")) h->opt.peak_mode = unset ? 0 : v;
+    else if (is("RBQ_NOISE_GATE_PARALLEL")) h->opt.noise_gate_parallel = unset ? -1 : (v != 0);
+    else if (is("RBQ_LINDBLAD_NO_SHARED_MAP")) h->opt.lindblad_shared_map = unset ? 1 : (v == 0);
+    else if (is("RBQ_LINDBLAD_TABLE")) h->opt.lindblad_table = unset ? 1 : (v != 0);
+    else if (is("RBQ_ROLLOUT_PACKED")) h->opt.rollout_packed = unset ? -1 : (v != 0);
+    else if (is("RBQ_ROLLOUT_SCAN")) h->opt.rollout_scan = unset ? -1 : (v != 0);
+    else if (is("RBQ_JAC_NT_UNSCENTED")) h->opt.jac_nt_unscented = (v == 2) ? 2 : 1;
+    else if (is("RBQ_JAC_STRUCTURED")) h->opt.jac_structured = unset ? 1 : (v != 0);
+    else if (is("RBQ_JAC_STAGE_KB")) h->opt.jac_stage_kb = (v >= 1 && v <= 200) ? v : -1;
+    else if (is("RBQ_JAC_STAGED")) h->opt.jac_staged = unset ? -1 : (v != 0);
+    else if (is("RBQ_BP_TMA")) h->opt.bp_tma = v;
+    else if (is("RBQ_BP_GENERIC")) h->opt.bp_generic = unset ? 0 : (v != 0);
+    else if (is("RBQ_BP_WARPS")) h->opt.bp_warps = v;
+    else return RBQ_E_NULL;
+    return RBQ_OK;
+}
+
 extern "C" {
 
 int rbq_version(void) { return RBQ_VERSION; }
+int rbq_set_option(rbq_handle* h, const char* name, const char* value) {
+    if (!h || !name) return RBQ_E_NULL;
+    h->err[0] = 0;
+    const int rc = rbq_apply_option(h, name, value);
+    if (rc == RBQ_E_NULL) return fail(h, RBQ_E_SIZE, "rbq_set_option: unknown option %s", name);
+    if (rc) return fail(h, rc, "rbq_set_option: bad value for %s", name);
+    return RBQ_OK;
+}
 
 int rbq_create(int device, rbq_handle** out) {
     if (!out) return RBQ_E_NULL;
@@ -127,11 +172,23 @@ int rbq_create(int device, rbq_handle** out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->centre_fq = 1.4e-2; h->centre_da = 0.0;   // FQ (spin.jl:148), no amplitude offset
+    // tuning switches are read from the environment here and nowhere else (per handle, immutable unless rbq_set_option)
+    for (const char* name : kOptionNames) {
+        if (rbq_apply_option(h, name, nullptr) != RBQ_OK) { delete h; return RBQ_E_SIZE; }
+        const char* e = getenv(name);
+        if (e && *e) rbq_apply_option(h, name, e);   // a malformed value keeps the default
+    }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
-    for (int i = 0; i < 2; ++i)
-        if (cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
-    for (int i = 0; i < 8; ++i)
-        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) { delete h; return RBQ_E_NODEVICE; }
+    bool ok = true;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    if (!ok) {   // release whatever was created before the failure
+        for (int i = 0; i < 2; ++i) if (h->copy_stream[i]) cudaStreamDestroy(h->copy_stream[i]);
+        for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        cudaGetLastError();
+        delete h;
+        return RBQ_E_NODEVICE;
+    }
     *out = h;
     return RBQ_OK;
 }
@@ -185,8 +242,12 @@ int rbq_host_unregister(rbq_handle* h, void* ptr) {
     return RBQ_OK;
 }
 int rbq_host_free(rbq_handle* h, void* ptr) {
-    ENTER(h);
-    if (ptr) CK(cudaFreeHost(ptr));
+    // page-locked memory is process wide, not tied to a handle: h may be NULL (the owner of the buffer outlived its handle)
+    if (h) { ENTER(h); }
+    if (ptr) {
+        cudaError_t e = cudaFreeHost(ptr);
+        if (e != cudaSuccess) return h ? fail(h, (int)e, "cudaFreeHost: %s", cudaGetErrorString(e)) : (int)e;
+    }
     return RBQ_OK;
 }
 
@@ -424,8 +485,7 @@ static int mc_static_prepare(rbq_handle* h, const double* d_controls, int64_t nk
     CKL(dev_buf(h, B_SCALARS, 256, &sc));
     CKL(launch_static_table(h, d_controls, nk, dt, f0, a0, (double*)tb, (double*)sc));
     a->table = (const double*)tb; a->scal = (const double*)sc;
-    const char* e = getenv("RBQ_NO_TABLE_CLASS");
-    a->no_table_class = (e && atoi(e) != 0) ? 1 : 0;
+    a->no_table_class = h->opt.no_table_class;
     a->nk = nk; a->dt = dt; a->gate_count = gate_count;
     if (d_stats) {
         void* pp;
@@ -475,9 +535,8 @@ int rbq_mc_static_philox_dev(rbq_handle* h, const double* d_controls, int64_t nk
 // of chunk c and the D2H copy of chunk c-1 overlap; the pulse is staged once and the statistics finalised once.
 // chunk c covers [mc_chunk_begin(c), mc_chunk_begin(c+1)): whole waves of resident blocks, so chunking adds no partially
 // filled wave and the upload of wave c+1 hides behind the kernel of wave c
-static int g_chunk_first = 1, g_chunk_rest = 1;   // in waves (measured best: tools/tune_e2e.py); RBQ_MC_CHUNK_WAVES="<first>,<rest>" overrides (tuning aid)
-static inline int64_t mc_chunk_begin(int64_t c, int64_t wave, int64_t S) {
-    const int64_t b = c == 0 ? 0 : wave * (g_chunk_first + g_chunk_rest * (c - 1));
+static inline int64_t mc_chunk_begin(const rbq_handle* h, int64_t c, int64_t wave, int64_t S) {
+    const int64_t b = c == 0 ? 0 : wave * (h->opt.chunk_first + (int64_t)h->opt.chunk_rest * (c - 1));
     return b < S ? b : S;
 }
 // page-locked host memory the device can address directly (cudaMallocHost / cudaHostRegister / torch pin_memory)
@@ -501,8 +560,7 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
     // kernel is compute bound, i.e. few recorded gates per sample.  RBQ_MC_ZEROCOPY=0 forces the streamed form.
     {
         void *mfq = nullptr, *mda = nullptr, *mpsi = nullptr, *mfid = nullptr;
-        const char* e = getenv("RBQ_MC_ZEROCOPY");
-        const bool want = !(e && atoi(e) == 0) && algo == RBQ_ALGO_SU2 && S > 0 && gate_count <= 3;
+        const bool want = h->opt.mc_zerocopy && algo == RBQ_ALGO_SU2 && S > 0 && gate_count <= 3;
         if (want && host_mapped(fq, &mfq) && host_mapped(psi0, &mpsi) && (!da || host_mapped(da, &mda)) &&
             (!fid || host_mapped(fid, &mfid))) {
             void *dc0, *dst0 = nullptr;
@@ -528,15 +586,11 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
     if (S > 0) {
         const int64_t wave = mc_static_wave_samples(h, algo);
-        if (const char* e = getenv("RBQ_MC_CHUNK_WAVES")) {
-            int a1 = 0, a2 = 0;
-            if (sscanf(e, "%d,%d", &a1, &a2) == 2 && a1 >= 1 && a2 >= 1) { g_chunk_first = a1; g_chunk_rest = a2; }
-        }
         int64_t nchunks = 0;
-        while (mc_chunk_begin(nchunks, wave, S) < S) ++nchunks;
+        while (mc_chunk_begin(h, nchunks, wave, S) < S) ++nchunks;
         int64_t total_blocks = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
-            const int64_t s0 = mc_chunk_begin(c, wave, S), cnt = mc_chunk_begin(c + 1, wave, S) - s0;
+            const int64_t s0 = mc_chunk_begin(h, c, wave, S), cnt = mc_chunk_begin(h, c + 1, wave, S) - s0;
             total_blocks += mc_static_blocks(h, cnt, algo);
         }
         McStaticArgs a;
@@ -549,7 +603,7 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
         CK(cudaStreamWaitEvent(up, h->ev[0], 0));   // uploads start after earlier work on the buffers has drained
         int64_t block_off = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
-            const int64_t s0 = mc_chunk_begin(c, wave, S), cnt = mc_chunk_begin(c + 1, wave, S) - s0;
+            const int64_t s0 = mc_chunk_begin(h, c, wave, S), cnt = mc_chunk_begin(h, c + 1, wave, S) - s0;
             CK(cudaMemcpyAsync((double*)dfq + s0, fq + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
             if (da) CK(cudaMemcpyAsync((double*)dda + s0, da + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, up));
             CK(cudaMemcpyAsync((double*)dpsi + 4 * s0, psi0 + 4 * s0, sizeof(double) * 4 * cnt, cudaMemcpyHostToDevice, up));
@@ -667,8 +721,7 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
         CKL(dev_buf(h, B_SCALARS, 256, &sc));
         CKL(launch_static_table(h, d_controls, nk, dt, fq, 0.0, (double*)tb, (double*)sc));
         a.table = (const double*)tb; a.scal = (const double*)sc;
-        const char* e = getenv("RBQ_NO_TABLE_CLASS");
-        a.no_table_class = (e && atoi(e) != 0) ? 1 : 0;
+        a.no_table_class = h->opt.no_table_class;
     }
     a.nk = nk; a.dt = dt; a.gate_count = gate_count; a.first = first; a.S = S; a.fq = fq;
     a.noise = d_noise; a.noise_len = noise_len; a.noise_dt_inv = noise_dt_inv; a.psi0 = d_psi0;
@@ -686,7 +739,7 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
     bool gate_parallel = algo == RBQ_ALGO_SU2 && gate_count >= 2 && gate_count <= 65535 && S < (int64_t)h->sm_count * 4096 &&
                          (double)S * (double)gate_count * 32.0 <= 2.0e9;
     if (philox && (double)S * (double)noise_len * 8.0 > 2.0e9) gate_parallel = false;   // materialised noise rows must stay modest
-    if (const char* e = getenv("RBQ_NOISE_GATE_PARALLEL")) gate_parallel = gate_parallel && atoi(e) != 0;
+    if (h->opt.noise_gate_parallel == 0) gate_parallel = false;
     if (gate_parallel) {
         if (philox) {   // the pink filter is sequential in time: materialise each sample's noise row first
             void* dn;
@@ -809,7 +862,7 @@ int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, do
     // no per-realisation amplitude offsets and time-independent rates: the one-gate map is the same for every realisation
     // (the reference recomputes it per seed, figures.jl:194-205); compose it once when it will be reused enough to matter
     const bool time_dep = (channels & RBQ_LINDBLAD_T2) && t2_gamma_f != 0.0;
-    if (!d_da && !time_dep && (gate_count > 3 || S >= 64) && !getenv("RBQ_LINDBLAD_NO_SHARED_MAP")) {
+    if (!d_da && !time_dep && (gate_count > 3 || S >= 64) && h->opt.lindblad_shared_map) {
         void* sc;
         CKL(dev_buf(h, B_SCALARS, 256, &sc));
         CKL(launch_lindblad_shared_map(h, a, channels, (double*)sc + 8));

@@ -23,7 +23,30 @@ struct rbq_handle {
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
     // centre (qubit frequency, amplitude offset) the static sweep's knot table is expanded around: rbq_set_sweep_centre
     double centre_fq, centre_da;
+    // tuning / A-B switches: read from the environment ONCE in rbq_create (RBQ_* names), changed afterwards only through
+    // rbq_set_option; never read from the environment inside a call.  -1 = "library default / heuristic".
+    struct {
+        int no_table_class;        // RBQ_NO_TABLE_CLASS      1: polynomial step classes only
+        int mc_zerocopy;           // RBQ_MC_ZEROCOPY         0: streamed host sweep even for page-locked buffers
+        int chunk_first, chunk_rest;   // RBQ_MC_CHUNK_WAVES  "<first>,<rest>" chunk sizes of the streamed sweep, in waves
+        int mc_variant;            // RBQ_MC_VARIANT          <spt><minb><threads/128> of mc_static_kernel
+        int peak_mode;             // RBQ_PEAK_MODE           operand form of the DFMA saturation loop
+        int noise_gate_parallel;   // RBQ_NOISE_GATE_PARALLEL 0: never the gate-parallel pair
+        int lindblad_shared_map;   // RBQ_LINDBLAD_NO_SHARED_MAP (inverted): 0 = every realisation composes its own map
+        int lindblad_table;        // RBQ_LINDBLAD_TABLE      0: series step only (no per-knot Frechet table)
+        int rollout_packed;        // RBQ_ROLLOUT_PACKED      0 / 1 force
+        int rollout_scan;          // RBQ_ROLLOUT_SCAN        0 / 1 force the prefix-product open-loop rollout
+        int jac_nt_unscented;      // RBQ_JAC_NT_UNSCENTED    generic unscented Jacobian kernel: tangents per lane (1 or 2)
+        int jac_structured;        // RBQ_JAC_STRUCTURED      0: generic forward mode for the unscented models too
+        int jac_stage_kb;          // RBQ_JAC_STAGE_KB
+        int jac_staged;            // RBQ_JAC_STAGED          0 / 1 force
+        int bp_tma;                // RBQ_BP_TMA              staging mode mask of the backward pass
+        int bp_generic;            // RBQ_BP_GENERIC          1: any-shape kernels only
+        int bp_warps;              // RBQ_BP_WARPS            1 / 8 force warp-per-problem or block-per-problem
+    } opt;
 };
+// option parsing shared by rbq_create (environment) and rbq_set_option; value NULL or "" restores the default
+int rbq_apply_option(rbq_handle* h, const char* name, const char* value);
 
 namespace rbq {
 

@@ -1314,11 +1314,12 @@ __global__ void __launch_bounds__(32) fp64_latency_kernel(int iters, double* __r
 // ---- launchers -----------------------------------------------------------------------------------------------------------
 // (samples per thread, min resident blocks per SM, block size) of the closed-form kernel;
 // RBQ_MC_VARIANT=<spt><minb><threads/128> overrides the default for tuning runs
-static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, int* minb, int* threads) {
+static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int* spt, int* minb, int* threads) {
+    const int sm_count = h->sm_count;
     *spt = 1; *minb = 1; *threads = 256;
     if (algo != RBQ_ALGO_SU2) return;
     int v = 171;   // measured best of the compiled variants (tools/tune_mc.py, tools/proto/bv.sh): 1 sample per thread, 128-thread blocks, 7 per SM
-    if (const char* e = getenv("RBQ_MC_VARIANT")) v = atoi(e);
+    if (h->opt.mc_variant > 0) v = h->opt.mc_variant;
     *spt = v / 100; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
     const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 7 || *minb == 8)));
     if (!ok) { *spt = 1; *minb = 7; *threads = 128; }
@@ -1327,7 +1328,7 @@ static inline void static_variant(int64_t S, int sm_count, int algo, int* spt, i
 }
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
     int spt, minb, threads;
-    static_variant(S, h->sm_count, algo, &spt, &minb, &threads);
+    static_variant(h, S, algo, &spt, &minb, &threads);
     const int per = threads * spt;
     return (int)((S + per - 1) / per);
 }
@@ -1335,7 +1336,7 @@ int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
 // sweep are multiples of this, so that chunking adds no partially filled waves)
 int64_t mc_static_wave_samples(const rbq_handle* h, int algo) {
     int spt, minb, threads;
-    static_variant((int64_t)1 << 40, h->sm_count, algo, &spt, &minb, &threads);
+    static_variant(h, (int64_t)1 << 40, algo, &spt, &minb, &threads);
     if (algo != RBQ_ALGO_SU2) { spt = 1; minb = 1; threads = 256; }
     return (int64_t)h->sm_count * minb * threads * spt;
 }
@@ -1357,7 +1358,7 @@ int launch_static_table(rbq_handle* h, const double* d_controls, int64_t nk, dou
 }
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
     int spt, minb, threads;
-    static_variant(a.S, h->sm_count, algo, &spt, &minb, &threads);
+    static_variant(h, a.S, algo, &spt, &minb, &threads);
     const int blocks = mc_static_blocks(h, a.S, algo);
     if (nblocks_out) *nblocks_out = blocks;
 #define RBQ_GO(SPT_, MINB_, T_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_, T_><<<blocks, T_, 0, h->stream>>>(a)
@@ -1448,8 +1449,7 @@ int launch_pink_noise(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, do
 }
 int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out, int* flops_per_thread_iter) {
     const int blocks = h->sm_count * 8;
-    int mode = 0;
-    if (const char* e = getenv("RBQ_PEAK_MODE")) mode = atoi(e);
+    const int mode = h->opt.peak_mode;
     if (mode == 9) {
         fp64_latency_kernel<<<h->sm_count, 32, 0, h->stream>>>(iters, d_sink);
         h->launches++;

@@ -10,9 +10,10 @@
 //     K = -Quu_reg^-1 Qux_reg   d = -Quu_reg^-1 Qu
 //     S = sym(Qxx + K'Quu K + K'Qux + Qux'K)   s = Qx + K'Quu d + K'Qu + Qux'd   dV += (d'Qu, d'Quu d / 2)
 //
-// Per knot the work is two dense products, T = S [A B] (n x n x (n+m)) and G = [A B]' T (lower tiles only), on 4x4
-// register tiles out of shared memory; everything else is O(n^2 m^2).  FP64 pipe bound for n >= ~40, latency bound below.
-// The next knot's Jacobian block is fetched with cp.async while the gains and the value update of this knot are computed.
+// Per knot the work is two dense products, T = S [A B] (n x n x (n+m)) and G = [A B]' T (lower 8x8 tiles only), on the FP64
+// tensor cores (mma.sync.m8n8k4.f64, SASS DMMA; tcgen05 has no FP64 kind) out of shared memory; everything else is
+// O(n^2 m^2).  DMMA-issue bound for n >= ~40, barrier/latency bound below.  The next knot's Jacobian and cost blocks arrive by
+// bulk TMA copies (cp.async below n = 28) while the gains and the value update of this knot are computed.
 #include "rbq_internal.h"
 
 #include "rbq_math.cuh"
@@ -477,7 +478,7 @@ size_t backward_pass_smem(int n, int m) {
 }
 
 // staging mode for a problem shape and its buffers (see backward_pass_kernel); RBQ_BP_TMA masks the bits (0 = cp.async only)
-static int bp_stage_mode(int n, int m, const double* d_AB, const double* d_Exx) {
+static int bp_stage_mode(const rbq_handle* h, int n, int m, const double* d_AB, const double* d_Exx) {
     const int nm = n + m;
     int mode = 0;
     if (n >= 28) {
@@ -486,7 +487,7 @@ static int bp_stage_mode(int n, int m, const double* d_AB, const double* d_Exx) 
         else if (ab16 && (n & 1) == 0) mode |= BP_TMA_J;                                      // every column 16-byte aligned
         if (exx16 && m * n + m * m + n + m <= 2 * 32 * BP_WARPS_LARGE) mode |= BP_TMA_C;
     }
-    if (const char* e = getenv("RBQ_BP_TMA")) mode &= atoi(e);
+    if (h->opt.bp_tma >= 0) mode &= h->opt.bp_tma;
     return mode;
 }
 
@@ -501,9 +502,7 @@ static cudaError_t bp_launch2(const BackwardArgs& a, int64_t B, size_t smem, cud
 // the shapes of the reference models (n = 11, 12, 15, 19, 43, 56, 58 with one control) get kernels with n known at compile time: tile
 // loops fully unrolled, constant strides.  RBQ_BP_GENERIC=1 forces the any-shape kernels (tests compare the two).
 template <int NW, int MODE>
-static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream) {
-    const char* g = getenv("RBQ_BP_GENERIC");
-    const bool specialised = !(g && atoi(g) != 0);
+static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream, bool specialised) {
     if (a.m == 2 && specialised) {                                      // spin15 time-optimal: u = (d2a/dt2, sqrt(dt))
         if constexpr (MODE == 0) {
             if (a.n == 11) return bp_launch2<NW, MODE, 2, 11>(a, B, smem, stream);
@@ -543,16 +542,16 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     // form runs two problems per SM at a time); 1184 problems 2.05 against 7.0 ms -- so the warp form is used above two
     // problems per SM.  RBQ_BP_WARPS=1 / 8 forces a form (A/B measurements, tests).
     bool small = n <= 16 && B > 2 * (int64_t)h->sm_count;
-    if (const char* e = getenv("RBQ_BP_WARPS")) small = n <= 16 && atoi(e) == 1;
+    if (h->opt.bp_warps > 0) small = n <= 16 && h->opt.bp_warps == 1;
     cudaError_t e;
     if (small) {
-        e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream);
+        e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream, !h->opt.bp_generic);
     } else {
-        switch (bp_stage_mode(n, m, d_AB, d_Exx)) {
-            case BP_DENSE_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_DENSE_J | BP_TMA_C>(a, B, smem, h->stream); break;
-            case BP_TMA_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C>(a, B, smem, h->stream); break;
-            case BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_C>(a, B, smem, h->stream); break;
-            default: e = bp_launch<BP_WARPS_LARGE, 0>(a, B, smem, h->stream); break;
+        switch (bp_stage_mode(h, n, m, d_AB, d_Exx)) {
+            case BP_DENSE_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_DENSE_J | BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
+            case BP_TMA_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
+            case BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
+            default: e = bp_launch<BP_WARPS_LARGE, 0>(a, B, smem, h->stream, !h->opt.bp_generic); break;
         }
     }
     h->launches++;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) jacobians_staged_kernel(rbq_model_params 
     const int64_t here = (K - k0) < G ? (K - k0) : G;
     const int64_t total = here * blk;
     double* __restrict__ dst = AB + k0 * blk;
-    if (((k0 * blk) & 1) == 0) {                       // 16-byte aligned destination: 2 doubles per store
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {   // 16-byte aligned destination (tested on the pointer: d_AB may be any view): 2 doubles per store
         const int64_t pairs = total >> 1;
         const double2* __restrict__ s2 = reinterpret_cast<const double2*>(stage);
         double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
@@ -244,12 +244,11 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     const int fam0 = family(p.model_id);
     const bool independent_blocks = fam0 == RBQ_MODEL_SPIN13 || fam0 == RBQ_MODEL_SPIN15 || fam0 == RBQ_MODEL_SPIN12;
-    const char* pk = getenv("RBQ_ROLLOUT_PACKED");
     // measured (tools/proto/rollout_batch.py, 1001 knots): spin13 4096 / 32768 trajectories 0.33 / 2.3 ms packed against
     // 0.60 / 4.2 ms one warp each; spin12 0.50 against 0.55 ms at 4096 but 6.6 against 3.9 ms at 32768 (43 doubles per
     // knot leave as scattered 32-byte stores), so the 10-block models switch back above 8192
     const bool packed_default = B >= 16 && (fam0 != RBQ_MODEL_SPIN12 || B <= 8192);
-    if (independent_blocks && (pk ? atoi(pk) != 0 : packed_default)) {
+    if (independent_blocks && (h->opt.rollout_packed >= 0 ? h->opt.rollout_packed != 0 : packed_default)) {
         // one thread per (trajectory, block): all lanes busy (see packed_rollout_kernel); 32-thread blocks spread small
         // batches over the SMs
         WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
@@ -303,19 +302,18 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     const bool unscented = fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25;
     // the unscented step is register hungry: one tangent per lane (254 registers, no spills) beats two (255 + 868 B of spills)
     // by 1.4x on batches although every lane repeats the value path; RBQ_JAC_NT_UNSCENTED=2 selects the old split
-    if (unscented) { const char* e = getenv("RBQ_JAC_NT_UNSCENTED"); nt = (e && atoi(e) == 2) ? 2 : 1; }
+    if (unscented) nt = h->opt.jac_nt_unscented == 2 ? 2 : 1;
     const int lpk = (n + m + nt - 1) / nt;
     const int blk_bytes = n * (n + m) * (int)sizeof(double);
     // Staging budget per block, measured (tools/proto/jac_sweep.py, 1e6 / 2.6e5 / 1.3e5 knots): small stages leave room for many
     // resident blocks, whose compute and write-out phases then overlap -- 20 KB: 4.75 TB/s written (spin13) and 4.8 TB/s
     // (spin12, one knot per block) against 3.7 / 3.1 TB/s with 200 KB; the unscented models are compute bound (1.7 TB/s), one knot per block is best there too
     int stage_bytes = blk_bytes > 20 * 1024 ? 30 * 1024 : 20 * 1024;
-    if (const char* e = getenv("RBQ_JAC_STAGE_KB")) { const int kb = atoi(e); if (kb >= 1 && kb <= 200) stage_bytes = kb * 1024; }
+    if (h->opt.jac_stage_kb > 0) stage_bytes = h->opt.jac_stage_kb * 1024;
     int G = stage_bytes / blk_bytes;
     if (G < 1 && blk_bytes <= JAC_STAGE_BYTES) G = 1;
     if (G > 256 / lpk) G = 256 / lpk;
-    const char* force = getenv("RBQ_JAC_STAGED");
-    const bool staged = G >= 1 && (force ? atoi(force) != 0 : K >= JAC_STAGED_MIN_KNOTS);
+    const bool staged = G >= 1 && (h->opt.jac_staged >= 0 ? h->opt.jac_staged != 0 : K >= JAC_STAGED_MIN_KNOTS);
     if (staged) {
         const int threads = ((G * lpk + 31) / 32) * 32;
         const unsigned blocks = (unsigned)((K + G - 1) / G);

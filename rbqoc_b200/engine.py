@@ -41,10 +41,9 @@ class Engine:
         self.device = int(device)
 
     def close(self):
+        """Destroys the handle.  Page-locked arrays from pinned_empty own their memory (freed when the last view of the
+        array is collected, through cudaFreeHost directly), so they stay valid after close()."""
         if getattr(self, "_h", None):
-            for ptr in getattr(self, "_pinned", []):
-                self._lib.rbq_host_free(self._h, ptr)
-            self._pinned = []
             self._lib.rbq_destroy(self._h)
             self._h = None
 
@@ -72,6 +71,12 @@ class Engine:
         """Performance hint: where the explicit samples of mc_static scatter (default FQ, 0); see include/rbq.h."""
         self._ck(self._lib.rbq_set_sweep_centre(self._h, float(fq0), float(da0)), "rbq_set_sweep_centre")
 
+    def set_option(self, name: str, value=None):
+        """One tuning / A-B switch of this handle (rbq_set_option): same names and values as the RBQ_* environment
+        variables the library latches in rbq_create; value None restores the default."""
+        v = None if value is None else str(value).encode()
+        self._ck(self._lib.rbq_set_option(self._h, name.encode(), v), "rbq_set_option")
+
     def use_torch_stream(self):
         import torch
 
@@ -81,16 +86,18 @@ class Engine:
         self._ck(self._lib.rbq_synchronize(self._h), "rbq_synchronize")
 
     def pinned_empty(self, shape, dtype=np.float64):
-        """numpy array backed by page-locked memory from rbq_host_alloc (freed when the array's owner is collected)."""
+        """numpy array backed by page-locked memory from rbq_host_alloc.  The memory belongs to the array: a finalizer on
+        the ctypes buffer every view keeps alive returns it with rbq_host_free(NULL handle -> cudaFreeHost) when the last
+        view is collected, whether or not this Engine still exists."""
+        import weakref
+
         shape = tuple(int(x) for x in np.atleast_1d(shape))
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p()
         self._ck(self._lib.rbq_host_alloc(self._h, max(nbytes, 1), C.byref(ptr)), "rbq_host_alloc")
         buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        self._pinned = getattr(self, "_pinned", [])
-        self._pinned.append(ptr)
-        return arr
+        weakref.finalize(buf, self._lib.rbq_host_free, None, C.c_void_p(ptr.value))
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def host_register(self, arr: np.ndarray):
         """Page-lock a numpy array in place (rbq_host_register); pair with host_unregister before the array is freed."""

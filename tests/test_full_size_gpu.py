@@ -105,7 +105,7 @@ def test_full_sweep_zero_copy_streamed_and_polynomial_forms_agree(engine, sweep,
     pfq[:], pda[:], ppsi[:] = fq, da, psi0
     fz, stz = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, pfq, pda, ppsi, fid_out=pfid)
     assert np.array_equal(fz, fid) and stz.sum == st.sum and stz.hist[:] == st.hist[:]
-    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    engine.set_option("RBQ_NO_TABLE_CLASS", "1")
     fp, stp = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
     assert np.max(np.abs(fp - fid)) < 2e-14 and stp.count == S_FULL
     assert abs(stp.sum - st.sum) < 1e-12 * st.sum

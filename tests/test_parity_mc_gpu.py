@@ -100,11 +100,11 @@ def test_mc_noise_sample_leaving_the_polynomial_range(engine, oracle):
     noise[::3, 40:55] = 3.0            # |a + delta a| ~ 3 GHz for a few knots of every third sample
     for mode in ("0", "1"):
         import os
-        os.environ["RBQ_NOISE_GATE_PARALLEL"] = mode
+        engine.set_option("RBQ_NOISE_GATE_PARALLEL", mode)
         try:
             fid, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
         finally:
-            os.environ.pop("RBQ_NOISE_GATE_PARALLEL", None)
+            engine.set_option("RBQ_NOISE_GATE_PARALLEL", None)
         ref = oracle.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
         assert np.max(np.abs(fid - ref)) < FID_RTOL, mode
 
@@ -222,7 +222,7 @@ def test_mc_static_philox_equals_explicit_samples(engine):
 @pytest.mark.parametrize("algo", [rbq.ALGO_SU2, rbq.ALGO_PADE], ids=["su2", "pade"])
 def test_mc_noise_matches_oracle(engine, oracle, algo, gate_parallel, monkeypatch):
     """Both forms of the sweep: one chain per sample, and (few samples) one gate propagator per (sample, gate)."""
-    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
+    engine.set_option("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
     controls = spin.controls_ypiby2(100.0)
     dt, gate, gate_count, ndi = 0.01, rbq.GATE_YPIBY2, 3, 10.0
     S = 200
@@ -238,7 +238,7 @@ def test_mc_noise_matches_oracle(engine, oracle, algo, gate_parallel, monkeypatc
 
 @pytest.mark.parametrize("gate_parallel", ["0", "1"], ids=["sequential", "gate_parallel"])
 def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle, gate_parallel, monkeypatch):
-    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
+    engine.set_option("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
     nlen = 500
     got = engine.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
     ref = oracle.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
@@ -254,7 +254,7 @@ def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle, gate_paralle
     assert np.max(np.abs(fid_a - fid_b)) < 1e-14
     assert st_a.count == st_b.count == S and abs(st_a.sum - st_b.sum) < 1e-12
     # the two forms of the sweep agree with each other to rounding
-    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", "1" if gate_parallel == "0" else "0")
+    engine.set_option("RBQ_NOISE_GATE_PARALLEL", "1" if gate_parallel == "0" else "0")
     fid_c, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, 10.0, psi0)
     assert np.max(np.abs(fid_a - fid_c)) < 1e-13
 
@@ -318,7 +318,7 @@ def test_lindblad_shared_map_path(engine, oracle, name, monkeypatch):
     S, gate_count = 200, 7
     rho0 = _rand_rho(S, 11, mixed=True)
     fid, rho, st = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, None, rho0)
-    monkeypatch.setenv("RBQ_LINDBLAD_NO_SHARED_MAP", "1")
+    engine.set_option("RBQ_LINDBLAD_NO_SHARED_MAP", "1")
     fid2, rho2, _ = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, None, rho0)
     # sequential vs tree-ordered products of the same per-knot maps differ by rounding only (~1e-16 per knot and gate)
     nk = controls.shape[0]
@@ -428,9 +428,9 @@ def test_table_class_equals_polynomial_classes(engine, oracle, name, monkeypatch
     # blocks with mixed warps: every 5th warp is pushed out of the table's range (eps ~ 2 w^2 a da grows with dt^2)
     da[np.arange(S) % 160 < 32] += 2e-3 if dt >= 0.05 else 0.2
     fid_t, st_t = engine.mc_static(controls, dt, gate, 3, fq, da, psi0)
-    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    engine.set_option("RBQ_NO_TABLE_CLASS", "1")
     fid_p, st_p = engine.mc_static(controls, dt, gate, 3, fq, da, psi0)
-    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    engine.set_option("RBQ_NO_TABLE_CLASS", None)
     assert np.max(np.abs(fid_t - fid_p)) < 5e-14
     far = np.arange(S) % 160 < 32
     assert np.array_equal(fid_t[far], fid_p[far])              # out-of-range warps run the same code either way
@@ -446,9 +446,9 @@ def test_table_class_golden_and_sweep_centre(engine, monkeypatch):
     z = np.load(GOLDEN + "/mc_static.npz")
     args = (z["controls"], float(z["dt"]), int(z["gate"]), int(z["gate_count"]), z["fq"], z["da"], z["psi0"])
     fid_t, _ = engine.mc_static(*args)
-    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    engine.set_option("RBQ_NO_TABLE_CLASS", "1")
     fid_p, _ = engine.mc_static(*args)
-    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    engine.set_option("RBQ_NO_TABLE_CLASS", None)
     assert np.max(np.abs(fid_t - z["fid"])) < 1e-13 and np.max(np.abs(fid_p - z["fid"])) < 1e-13
     assert not np.array_equal(fid_t, fid_p)
     # a sweep around another qubit frequency: off-centre it falls back to the polynomial step, re-centred it takes the table
@@ -494,7 +494,7 @@ def test_mc_static_zero_copy_equals_streamed(engine, monkeypatch, gate_count):
     off = raw[1:].reshape(S, gate_count + 1)
     engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=off)
     assert np.array_equal(off, fid_s)
-    monkeypatch.setenv("RBQ_MC_ZEROCOPY", "0")
+    engine.set_option("RBQ_MC_ZEROCOPY", "0")
     before = engine.launch_count
     fid_c, _ = engine.mc_static(controls, dt, gate, gate_count, pfq, pda, ppsi, fid_out=pfid)
     assert np.array_equal(fid_c, fid_s)
@@ -505,7 +505,7 @@ def test_mc_static_zero_copy_equals_streamed(engine, monkeypatch, gate_count):
 def test_noise_table_class_equals_polynomial_classes(engine, oracle, gate_parallel, monkeypatch):
     """The noise sweeps take the knot-table step wherever the noise keeps eps inside the table's range (decided when the
     noise index changes), the polynomial step otherwise; both agree to rounding and each matches the oracle."""
-    monkeypatch.setenv("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
+    engine.set_option("RBQ_NOISE_GATE_PARALLEL", gate_parallel)
     controls, dt, gate = PULSES["sin301_dt0.1"]
     S, gc, ndi = 700, 4, 10.0
     _, _, psi0 = _samples(S, seed=17)
@@ -513,9 +513,9 @@ def test_noise_table_class_equals_polynomial_classes(engine, oracle, gate_parall
     noise = engine.pink_noise(3, S, 9, spin.NAMP_PREFACTOR, ndi, nlen)
     noise[::7, 30:60] += 5e-3                      # bursts that leave the table's range (but not the polynomial's)
     fid_t, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
-    monkeypatch.setenv("RBQ_NO_TABLE_CLASS", "1")
+    engine.set_option("RBQ_NO_TABLE_CLASS", "1")
     fid_p, _ = engine.mc_noise(controls, dt, gate, gc, spin.FQ, noise, ndi, psi0)
-    monkeypatch.delenv("RBQ_NO_TABLE_CLASS")
+    engine.set_option("RBQ_NO_TABLE_CLASS", None)
     assert np.max(np.abs(fid_t - fid_p)) < 5e-14 and not np.array_equal(fid_t, fid_p)
     ref = oracle.mc_noise(controls, dt, gate, gc, spin.FQ, noise[:200], ndi, psi0[:200])
     assert np.max(np.abs(fid_t[:200] - ref)) < FID_RTOL and np.max(np.abs(fid_p[:200] - ref)) < FID_RTOL

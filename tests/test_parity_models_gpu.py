@@ -245,9 +245,9 @@ def test_jacobians_staged_kernel_equals_direct(engine, oracle, name, model, monk
     X = np.stack([p[0] for p in pts])
     U = np.stack([p[1] for p in pts])
     dt = rng.choice([0.1, 0.01], K)
-    monkeypatch.setenv("RBQ_JAC_STAGED", "0")
+    engine.set_option("RBQ_JAC_STAGED", "0")
     direct = engine.jacobians(model.params, X, U, dt).copy()
-    monkeypatch.setenv("RBQ_JAC_STAGED", "1")
+    engine.set_option("RBQ_JAC_STAGED", "1")
     staged = engine.jacobians(model.params, X, U, dt).copy()
     assert np.array_equal(direct, staged), name
     ref = oracle.jacobians(model.params, X[:40], U[:40], dt[:40])
@@ -397,9 +397,9 @@ def test_packed_batch_rollout_equals_warp_rollout(engine, oracle, name, model, m
     U = rng.uniform(-2e-3, 2e-3, (B, N - 1, model.m))
     if model.params.model_id == 15 and model.params.time_optimal:
         U[:, :, 1] = rng.uniform(0.25, 0.35, (B, N - 1))
-    monkeypatch.setenv("RBQ_ROLLOUT_PACKED", "0")
+    engine.set_option("RBQ_ROLLOUT_PACKED", "0")
     Xw = engine.rollout(model.params, x0, U, dt)
-    monkeypatch.setenv("RBQ_ROLLOUT_PACKED", "1")
+    engine.set_option("RBQ_ROLLOUT_PACKED", "1")
     Xp = engine.rollout(model.params, x0, U, dt)
     assert np.array_equal(Xw, Xp), name
     Xr = oracle.rollout(model.params, x0[:5], U[:5], dt)

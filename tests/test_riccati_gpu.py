@@ -79,11 +79,11 @@ def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
     for n, m, N in ((11, 1, 140), (12, 2, 60), (12, 1, 33), (15, 1, 40), (16, 3, 25), (3, 1, 9)):
         A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, N, n, m)
         st = lambda x: np.stack([x] * 3)
-        monkeypatch.setenv("RBQ_BP_WARPS", "1")
+        engine.set_option("RBQ_BP_WARPS", "1")
         K1, d1, dV1, f1 = engine.backward_pass(st(AB), st(Q), st(q), st(R), st(Eux), st(r), rho=0.2, reg_type=rbq.REG_STATE)
-        monkeypatch.setenv("RBQ_BP_WARPS", "8")
+        engine.set_option("RBQ_BP_WARPS", "8")
         K8, d8, dV8, f8 = engine.backward_pass(st(AB), st(Q), st(q), st(R), st(Eux), st(r), rho=0.2, reg_type=rbq.REG_STATE)
-        monkeypatch.delenv("RBQ_BP_WARPS")
+        engine.set_option("RBQ_BP_WARPS", None)
         Kr, dr, dVr, fr = riccati.backward_pass(AB, Q, q, R, Eux, r, rho=0.2, reg_type=rbq.REG_STATE)
         assert list(f1) == list(f8) == [-1] * 3 and fr == -1
         for K, d, dV in ((K1, d1, dV1), (K8, d8, dV8)):
@@ -91,7 +91,7 @@ def test_backward_pass_one_warp_form_for_small_models(engine, monkeypatch):
     # a failing problem in the warp form
     A, Bm, AB, Q, q, R, Eux, H, r = _lq_problem(rng, 30, 11, 1)
     R[12] = -1e3
-    monkeypatch.setenv("RBQ_BP_WARPS", "1")
+    engine.set_option("RBQ_BP_WARPS", "1")
     assert engine.backward_pass(AB, Q, q, R, Eux, r)[3] == 12
 
 
@@ -110,10 +110,10 @@ def test_backward_pass_staging_modes_and_specialised_shapes_agree(engine, monkey
     outs = []
     for env in ({}, {"RBQ_BP_GENERIC": "1"}, {"RBQ_BP_TMA": "0"}, {"RBQ_BP_TMA": "2"}, {"RBQ_BP_GENERIC": "1", "RBQ_BP_TMA": "0"}):
         for k, v in env.items():
-            monkeypatch.setenv(k, v)
+            engine.set_option(k, v)
         outs.append(engine.backward_pass(AB, Q, q, R, Eux, r, rho=0.11, reg_type=rbq.REG_CONTROL))
         for k in env:
-            monkeypatch.delenv(k)
+            engine.set_option(k, None)
     for K, d, dV, fail in outs:
         assert list(fail) == [-1] * 3
         for b, (Kr, dr, dVr, fr) in enumerate(ref):

@@ -83,12 +83,12 @@ dnoise3 = torch.empty(S3, nlen3, dtype=torch.float64, device=dev)
 dnoise3[:] = d(eng.pink_noise(0, S3, 7, spin.NAMP_PREFACTOR, ndi, nlen3))
 dfid3 = torch.empty(S3, gates3 + 1, dtype=torch.float64, device=dev)
 for mode in ("0", "1"):
-    os.environ["RBQ_NOISE_GATE_PARALLEL"] = mode
+    eng.set_option("RBQ_NOISE_GATE_PARALLEL", mode)
     ms = timed(lambda: eng.mc_noise_dev(dc, nk, dt, rbq.GATE_XPIBY2, gates3, S3, spin.FQ, dnoise3, nlen3, ndi, dpsi, rbq.ALGO_SU2, dfid3, stats),
                reps=2, warm=1)
     out(f"mc_noise gen_3b shape (1000 samples x 200 gates x 5680 knots), {'gate-parallel' if mode == '1' else 'sequential'} form", ms,
         S3 * nk * gates3, "trajectory-steps/s", S=S3, knots=nk, gates=gates3)
-os.environ.pop("RBQ_NOISE_GATE_PARALLEL", None)
+eng.set_option("RBQ_NOISE_GATE_PARALLEL", None)
 
 # ---- Lindblad T1: 1e5 realisations (BASELINE configs[3]) ----------------------------------------------------------
 S = 100_000

@@ -18,7 +18,7 @@ fq, da, psi0 = pin(fq), pin(da), pin(psi0)
 fid = torch.empty(S, 2, dtype=torch.float64).pin_memory().numpy()
 controls = spin.pulse_sin(NK + 1)[:-1]
 for sched in sys.argv[1:] or ["1,2", "1,3", "1,6", "2,2", "1,1", "7,7"]:
-    os.environ["RBQ_MC_CHUNK_WAVES"] = sched
+    eng.set_option("RBQ_MC_CHUNK_WAVES", sched)
     for _ in range(3):
         eng.mc_static(controls, DT, rbq.GATE_ZPIBY2, 1, fq, da, psi0, fid_out=fid)
     t0 = time.perf_counter()

@@ -20,7 +20,7 @@ d_c, d_fq, d_da, d_psi0 = d(spin.pulse_sin(NK + 1)[:-1]), d(fq), d(da), d(psi0)
 d_fid = torch.empty(S, 2, dtype=torch.float64, device=dev)
 d_st = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
 for v in sys.argv[3:] or ["112", "122", "132", "142", "212", "222", "232", "242", "141", "161", "181", "241", "261", "281"]:
-    os.environ["RBQ_MC_VARIANT"] = v
+    eng.set_option("RBQ_MC_VARIANT", v)
     for _ in range(3):
         eng.mc_static_dev(d_c, NK, DT, rbq.GATE_ZPIBY2, 1, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_st)
     torch.cuda.synchronize()
