@@ -1078,6 +1078,136 @@ int orc_lindblad_segments(const double* amps, const double* durs, int64_t nseg, 
     }
     return 0;
 }
+// ------------------------------------------------------------------------------------------
+// The density-matrix ODEs the reference hands to DifferentialEquations.Vern9 (reltol = abstol = 1e-12, spin.jl:1277-1380):
+//   dynamics_lindbladt1_deqjl (spin.jl:505-518)  and  dynamics_lindbladt2_deqjl (spin.jl:542-554)
+// on the 4x4 REAL iso density  rho_iso = [[Re rho, -Im rho], [Im rho, Re rho]]:
+//   d rho/dt = negi_h rho - rho negi_h
+//            + gamma_1 (GE rho EG + NEG_EE_BY2 rho + rho NEG_EE_BY2) + gamma_1 (EG rho GE + NEG_GG_BY2 rho + rho NEG_GG_BY2)   [T1]
+//            + (GAMMAC + 2 gammaf^2 t) NEG_DOP_ISO .* rho                                                                    [T2]
+// with negi_h = fq NEGI_H0_ISO + a NEGI_H1_ISO and a piecewise-constant amplitude.  Between amplitude breakpoints the
+// right-hand side is L_A rho + (t - t0) L_1 rho (L_1 = the 2 gammaf^2 dephasing mask), so the exact solution has the Taylor
+// coefficients  (n+1) c_{n+1} = L_A c_n + L_1 c_{n-1},  rho(t0 + h) = sum c_n h^n,  summed here in long double until the terms
+// vanish: the rounding-free solution of the reference's ODE, not an approximation of it by another integrator.
+// Both channels may be switched on together (the engine offers T1 + T2; the reference has one function per channel).
+// ------------------------------------------------------------------------------------------
+typedef long double xr;
+struct IsoDensityRhs {
+    xr h[4][4];        // negi_h
+    xr gamma1, gam0;   // T1 rate; dephasing rate at the segment start
+    // T1 dissipator matrices of spin.jl:278-297 and the dephasing mask spin.jl:291-295
+    void apply(const xr r[4][4], xr out[4][4]) const {
+        static const int GE[4][4] = {{0, 1, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 1}, {0, 0, 0, 0}};
+        static const int EG[4][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 1, 0}};
+        static const int GGd[4] = {1, 0, 1, 0}, EEd[4] = {0, 1, 0, 1};      // diagonals of -2 NEG_GG_BY2_ISO, -2 NEG_EE_BY2_ISO
+        static const int DOP[4][4] = {{0, 1, 0, 1}, {1, 0, 1, 0}, {0, 1, 0, 1}, {1, 0, 1, 0}};
+        xr t1[4][4], t2[4][4];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+            xr s = 0;
+            for (int k = 0; k < 4; ++k) s += h[i][k] * r[k][j] - r[i][k] * h[k][j];
+            out[i][j] = s;
+        }
+        if (gamma1 != 0) {
+            // GE rho EG and EG rho GE
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+                xr a = 0, b = 0;
+                for (int k = 0; k < 4; ++k) { a += GE[i][k] * r[k][j]; b += EG[i][k] * r[k][j]; }
+                t1[i][j] = a; t2[i][j] = b;
+            }
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+                xr a = 0, b = 0;
+                for (int k = 0; k < 4; ++k) { a += t1[i][k] * EG[k][j]; b += t2[i][k] * GE[k][j]; }
+                out[i][j] += gamma1 * (a - (xr)0.5 * (EEd[i] + EEd[j]) * r[i][j]) + gamma1 * (b - (xr)0.5 * (GGd[i] + GGd[j]) * r[i][j]);
+            }
+        }
+        if (gam0 != 0) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[i][j] -= gam0 * DOP[i][j] * r[i][j];
+    }
+};
+// advance the iso density over one constant-amplitude segment [t0, t0 + dur)
+static void iso_density_segment(xr rho[4][4], double fq, double amp, xr t0, xr dur, int channels, double gamma_c, double gamma_f) {
+    static const int DOP[4][4] = {{0, 1, 0, 1}, {1, 0, 1, 0}, {0, 1, 0, 1}, {1, 0, 1, 0}};
+    IsoDensityRhs f;
+    const xr pil = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) f.h[i][j] = pil * ((xr)fq * N0[i][j] + (xr)amp * N1[i][j]);
+    f.gamma1 = (channels & RBQ_LINDBLAD_T1) ? (xr)1.0 / (xr)amp_t1_spline<double>(amp) : 0;            // spin.jl:508
+    const bool t2 = (channels & RBQ_LINDBLAD_T2) != 0;
+    const xr g1coef = t2 ? (xr)2.0 * (xr)gamma_f * (xr)gamma_f : 0;                                      // spin.jl:552
+    f.gam0 = t2 ? (xr)gamma_c + g1coef * t0 : 0;
+    // sub-steps keep ||L h|| <= ~0.5 so that the series is short and free of cancellation
+    const xr nrm = 2 * pil * (std::fabs((xr)fq) + std::fabs((xr)amp)) + 2 * f.gamma1 + f.gam0;
+    int sub = (int)std::ceil((double)(nrm * dur / 0.5L)); if (sub < 1) sub = 1;
+    const xr hh = dur / sub;
+    for (int q = 0; q < sub; ++q) {
+        xr cprev[4][4], c[4][4], acc[4][4], nxt[4][4];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { c[i][j] = rho[i][j]; cprev[i][j] = 0; acc[i][j] = rho[i][j]; }
+        xr hp = 1;
+        for (int n = 0; n < 60; ++n) {
+            f.apply(c, nxt);
+            xr big = 0;
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+                nxt[i][j] = (nxt[i][j] - g1coef * DOP[i][j] * cprev[i][j]) / (xr)(n + 1);
+                cprev[i][j] = c[i][j];
+            }
+            hp *= hh;
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { c[i][j] = nxt[i][j]; acc[i][j] += c[i][j] * hp; big = std::max(big, std::fabs(c[i][j] * hp)); }
+            if (big < 1e-24L && n > 2) break;
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) rho[i][j] = acc[i][j];
+        f.gam0 += g1coef * hh;
+    }
+}
+// Exact solution of the reference's density ODEs over a segment timeline with save points (the shape run_sim_deqjl /
+// run_sim_fine_deqjl integrate, spin.jl:1277-1478).  rho0[S*8] column-major vec (re,im); fid_closed[S*(nsave+1)] Uhlmann
+// sqrt-fidelity against the 4-cyclic targets (NULL to skip); rho_saves[S*(nsave+1)*8] (NULL to skip).
+int orc_lindblad_ode(const double* amps, const double* durs, int64_t nseg, const int64_t* save_after, int64_t nsave, int gate,
+                     int64_t S, double fq, const double* da, const double* rho0, int channels, double gamma_c, double gamma_f,
+                     double* fid_closed, double* rho_saves, int nthreads) {
+    cplx g[2][2], g2[2][2], g3[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g2[i][j] = g[i][0] * g[0][j] + g[i][1] * g[1][j];
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) g3[i][j] = g2[i][0] * g[0][j] + g2[i][1] * g[1][j];
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) {
+        cplx v[4], r0[2][2], tg[4][2][2];
+        for (int i = 0; i < 4; ++i) v[i] = cplx(rho0[8 * s + 2 * i], rho0[8 * s + 2 * i + 1]);
+        r0[0][0] = v[0]; r0[1][0] = v[1]; r0[0][1] = v[2]; r0[1][1] = v[3];
+        const cplx (*gs[3])[2] = {g, g2, g3};
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[0][i][j] = r0[i][j];
+        for (int q = 0; q < 3; ++q) {
+            cplx t[2][2];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) t[i][j] = gs[q][i][0] * r0[0][j] + gs[q][i][1] * r0[1][j];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) tg[q + 1][i][j] = t[i][0] * std::conj(gs[q][j][0]) + t[i][1] * std::conj(gs[q][j][1]);
+        }
+        // get_mat_iso of the density (rbqoc.jl:204-210)
+        xr rho[4][4];
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+            rho[i][j] = r0[i][j].real(); rho[i][j + 2] = -r0[i][j].imag(); rho[i + 2][j] = r0[i][j].imag(); rho[i + 2][j + 2] = r0[i][j].real();
+        }
+        auto record = [&](int64_t k) {
+            cplx m[2][2];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) m[i][j] = cplx((double)rho[i][j], (double)rho[i + 2][j]);
+            if (fid_closed) fid_closed[s * (nsave + 1) + k] = fidelity_mat_closed(m, tg[k % 4]);
+            if (rho_saves) {
+                double* o = rho_saves + (s * (nsave + 1) + k) * 8;
+                o[0] = m[0][0].real(); o[1] = m[0][0].imag(); o[2] = m[1][0].real(); o[3] = m[1][0].imag();
+                o[4] = m[0][1].real(); o[5] = m[0][1].imag(); o[6] = m[1][1].real(); o[7] = m[1][1].imag();
+            }
+        };
+        record(0);
+        xr t = 0;
+        int64_t j = 0;
+        for (int64_t k = 1; k <= nsave; ++k) {
+            for (; j < save_after[k - 1] && j < nseg; ++j) {
+                iso_density_segment(rho, fq, amps[j] + (da ? da[s] : 0.0), t, (xr)durs[j], channels, gamma_c, gamma_f);
+                t += (xr)durs[j];
+            }
+            record(k);
+        }
+    }
+    return 0;
+}
 // the 4x4 complex Liouvillian of spin.jl:530-531 (row-major interleaved), for referee checks
 void orc_lindblad_generator(double fq, double a, double* L) {
     LindbladOps o = make_lindblad_ops(fq);

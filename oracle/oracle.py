@@ -349,6 +349,39 @@ def lindblad_segments(amps, durs, gate, gate_count, fq, da, rho0):
     return fidc, out.reshape(S, 2, 2).transpose(0, 2, 1).copy()
 
 
+def lindblad_ode(amps, durs, save_after, gate, fq, da, rho0, channels=1, gamma_c=0.0, gamma_f=0.0, nthreads=0):
+    """Exact (long-double Taylor) solution of the reference's density ODEs dynamics_lindbladt1_deqjl / lindbladt2_deqjl
+    (spin.jl:505-518, 542-554) over a piecewise-constant segment timeline.  rho0 (S,2,2) complex.
+    Returns fid_closed (S, nsave+1), rho (S, nsave+1, 2, 2)."""
+    amps, durs = _f64(amps), _f64(durs)
+    save_after = np.ascontiguousarray(save_after, dtype=np.int64)
+    nsave = save_after.shape[0]
+    rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+    S = rho0.shape[0]
+    vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4))
+    da = None if da is None else _f64(da)
+    fidc = np.empty((S, nsave + 1))
+    out = np.empty((S, nsave + 1, 4), dtype=np.complex128)
+    rc = lib().orc_lindblad_ode(_p(amps), _p(durs), C.c_int64(amps.shape[0]), _p(save_after), C.c_int64(nsave), int(gate),
+                                C.c_int64(S), C.c_double(fq), _p(da), _p(vec), int(channels), C.c_double(gamma_c),
+                                C.c_double(gamma_f), _p(fidc), _p(out), int(nthreads))
+    if rc:
+        raise ValueError(f"orc_lindblad_ode rc={rc}")
+    return fidc, out.reshape(S, nsave + 1, 2, 2).transpose(0, 1, 3, 2).copy()
+
+
+def lindblad_knots(controls, dt, gate, gate_count, fq, da, rho0, channels=1, gamma_c=0.0, gamma_f=0.0, nthreads=0):
+    """lindblad_ode on the knot grid: `gate_count` repetitions of the pulse, saved after every gate (what run_sim_prop's
+    lindblad types integrate, with the T2 rate running on through the gates).  Returns fid_closed (S, gate_count+1), rho_final."""
+    controls = _f64(controls).reshape(-1)
+    nk = controls.shape[0]
+    amps = np.tile(controls, gate_count)
+    durs = np.full(nk * gate_count, float(dt))
+    save_after = nk * np.arange(1, gate_count + 1)
+    fidc, rho = lindblad_ode(amps, durs, save_after, gate, fq, da, rho0, channels, gamma_c, gamma_f, nthreads)
+    return fidc, rho[:, -1]
+
+
 def lindblad_generator(fq, a):
     L = np.empty((4, 4), dtype=np.complex128)
     lib().orc_lindblad_generator(C.c_double(fq), C.c_double(a), _p(L))

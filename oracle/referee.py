@@ -252,5 +252,65 @@ def sim_lindblad(controls, dt, gate_count, fq, da, rho0):
     return out
 
 
+def sim_density_ode(controls, dt, gate_count, fq, da, rho0, t1=False, t2=False, gamma_c=0, gamma_f=0):
+    """Exact solution, in 50 digits, of the iso-density ODEs the reference gives to Vern9: dynamics_lindbladt1_deqjl
+    (spin.jl:505-518) and dynamics_lindbladt2_deqjl (spin.jl:542-554), pulse repeated `gate_count` times on its knot grid.
+    The right-hand side is written exactly as the reference writes it (4x4 real iso density, commutator with negi_h, the
+    GE/EG dissipators, the elementwise NEG_DOP_ISO mask with rate GAMMAC + 2 gammaf^2 t); inside a knot it is
+    L_A rho + (t - t0) L_1 rho, whose Taylor coefficients obey (n+1) c_{n+1} = L_A c_n + L_1 c_{n-1}.
+    Returns the complex 2x2 densities after 0..gate_count gates."""
+    GE = mp.matrix([[0, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 1], [0, 0, 0, 0]])
+    EG = GE.T
+    NGG = mp.diag([1, 0, 1, 0]) * mp.mpf(-0.5)
+    NEE = mp.diag([0, 1, 0, 1]) * mp.mpf(-0.5)
+    DOP = [[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]]
+    rho = mp.matrix(4, 4)
+    for i in range(2):
+        for j in range(2):
+            rho[i, j] = mp.re(rho0[i][j]); rho[i, j + 2] = -mp.im(rho0[i][j])
+            rho[i + 2, j] = mp.im(rho0[i][j]); rho[i + 2, j + 2] = mp.re(rho0[i][j])
+    g1coef = 2 * gamma_f * gamma_f if t2 else mp.mpf(0)
+
+    def mask(m, c):
+        out = mp.matrix(4, 4)
+        for i in range(4):
+            for j in range(4):
+                out[i, j] = -c * DOP[i][j] * m[i, j]
+        return out
+
+    def unpack(m):
+        return [[mp.mpc(m[0, 0], m[2, 0]), mp.mpc(m[0, 1], m[2, 1])], [mp.mpc(m[1, 0], m[3, 0]), mp.mpc(m[1, 1], m[3, 1])]]
+
+    out = [unpack(rho)]
+    step = 0
+    for _ in range(gate_count):
+        for a in controls:
+            c1 = a + da
+            H = PI * (fq * N0 + c1 * N1)
+            gamma1 = 1 / (t1_us(c1) * 1000) if t1 else mp.mpf(0)
+            gam0 = (gamma_c + g1coef * (step * dt)) if t2 else mp.mpf(0)
+
+            def rhs(m):
+                r = H * m - m * H
+                if t1:
+                    r += gamma1 * (GE * m * EG + NEE * m + m * NEE) + gamma1 * (EG * m * GE + NGG * m + m * NGG)
+                if t2:
+                    r += mask(m, gam0)
+                return r
+
+            cprev, c, acc, hp = mp.matrix(4, 4), rho.copy(), rho.copy(), mp.mpf(1)
+            for n in range(80):
+                nxt = (rhs(c) + mask(cprev, g1coef)) / (n + 1)
+                cprev, c = c, nxt
+                hp *= dt
+                acc += c * hp
+                if max(abs(x) for x in c) * hp < mp.mpf("1e-45"):
+                    break
+            rho = acc
+            step += 1
+        out.append(unpack(rho))
+    return out
+
+
 def to_f64(v):
     return np.array([float(t) for t in v], dtype=np.float64)

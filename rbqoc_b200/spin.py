@@ -35,6 +35,8 @@ AYPIBY2 = 1.25e-1
 FBFQ_NAMP = 5.21e-6               # spin.jl:163
 NAMP_PREFACTOR = FBFQ_NAMP / FBFQ_A   # spin.jl:164
 GAMMAC = 1 / 3e5                  # spin.jl:162
+SQRTLNIR = 4                      # spin.jl:163
+GAMMAF_PREFACTOR = FBFQ_NAMP * SQRTLNIR * 2 * math.pi   # spin.jl:165: Gamma(t) = GAMMAC + 2 GAMMAF_PREFACTOR^2 t (spin.jl:549-552)
 DT_NOISE_INV = 1e1
 TTOT_ZPIBY2 = 17.857142857142858  # spin.jl:557
 
@@ -425,12 +427,14 @@ class SimResult:
 
 def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=NAMP_PREFACTOR, noise_dt_inv=DT_NOISE_INV,
                  seed=0, state_seed=None, dynamics_type=DynamicsType.schroed, noise=None, engine: Engine | None = None,
-                 algo=_lib.ALGO_SU2):
+                 algo=_lib.ALGO_SU2, gate_time=None, t2_gamma_c=GAMMAC, t2_gamma_f=GAMMAF_PREFACTOR):
     """run_sim_prop for one (seed, state_seed) like the reference, or for arrays of them (batched).
 
-    `controls`/`dt_inv` replace `save_file_path` (what grab_controls returns, rbqoc.jl:98-123);
-    `fq` replaces `negi_h0 = fq * NEGI_H0_ISO`.  Returns a dict with "fidelities" of shape
-    (gate_count+1,) for scalar seeds or (S, gate_count+1) for array seeds."""
+    `controls`/`dt_inv`/`gate_time` replace `save_file_path` (what grab_controls returns, rbqoc.jl:98-123; gate_time
+    defaults to len(controls)/dt_inv and only sets the length of the noise row, spin.jl:1567-1570);
+    `fq` replaces `negi_h0 = fq * NEGI_H0_ISO`.  lindbladt2 uses the reference's dephasing rate
+    Gamma(t) = GAMMAC + 2 GAMMAF_PREFACTOR^2 t (spin.jl:549-552) unless t2_gamma_c / t2_gamma_f say otherwise.
+    Returns a dict with "fidelities" of shape (gate_count+1,) for scalar seeds or (S, gate_count+1) for array seeds."""
     eng = engine or default_engine()
     gate_type = GateType(gate_type)
     dynamics_type = DynamicsType(dynamics_type)
@@ -446,7 +450,8 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
         das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
         fid, st = eng.mc_static(controls, dt, gate_type, gate_count, fqs, das, psi0, algo=algo)
     elif dynamics_type == DynamicsType.schroedda:
-        nlen = int(math.ceil(controls.shape[0] * dt * gate_count * noise_dt_inv)) + 1     # spin.jl:1569
+        gt = controls.shape[0] * dt if gate_time is None else float(gate_time)
+        nlen = int(math.ceil(gt * gate_count * noise_dt_inv)) + 1                         # spin.jl:1567-1570
         if noise is None:
             noise = np.concatenate([eng.pink_noise(int(s), 1, 0, namp, noise_dt_inv, nlen) for s in seeds])
         if not np.all(fqs == fqs[0]):
@@ -456,8 +461,9 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
         rho0 = np.stack([np.outer(get_vec_uniso(p), get_vec_uniso(p).conj()) for p in psi0])
         das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
         ch = _lib.LINDBLAD_T1 if dynamics_type == DynamicsType.lindbladt1 else _lib.LINDBLAD_T2
+        t2 = ch == _lib.LINDBLAD_T2
         fid, rho, st = eng.lindblad(controls, dt, gate_type, gate_count, float(fqs[0]), das, rho0, channels=ch,
-                                    t2_gamma_c=GAMMAC if ch == _lib.LINDBLAD_T2 else 0.0)
+                                    t2_gamma_c=t2_gamma_c if t2 else 0.0, t2_gamma_f=t2_gamma_f if t2 else 0.0)
     elif dynamics_type in ANALYTIC_DYNAMICS:
         # analytic gates (DT_AN, spin.jl:94-114): `controls`/`dt_inv` are ignored like the reference ignores save_file_path.
         # xpiby2nodis is an empty loop in the reference (spin.jl:721-727); here it integrates the X/2 segments for real.

@@ -467,3 +467,76 @@ def test_reference_constraint_lists_have_the_reference_layout():
             assert row.dual_off == off and (row.k0, row.k1) == (spec["k0"], spec["k1"])
             off += (row.k1 - row.k0) * row.p
         assert off == t.dual_size and t.rows[0].kind == _lib.CON_BOUND and t.rows[0].p == 2 * (n + 1)
+
+
+# ---- density ODEs with dephasing (dynamics_lindbladt1_deqjl / dynamics_lindbladt2_deqjl, spin.jl:505-518, 542-554) ----------
+def _mixed_rho(S, seed):
+    rng = np.random.default_rng(seed)
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho = np.einsum("si,sj->sij", psi, psi.conj())
+    lam = rng.uniform(0.6, 1.0, S)[:, None, None]
+    return lam * rho + (1 - lam) * np.eye(2) / 2
+
+
+def test_density_ode_oracle_equals_the_vec_propagator_oracle_for_t1(orc):
+    """Two different reference functions, one answer: the ODE right-hand side on the 4x4 iso density (spin.jl:505-518)
+    solved exactly, and integrate_prop_lindbladt1!'s complex vec-Liouvillian exponentials (spin.jl:521-539)."""
+    from rbqoc_b200 import spin
+
+    controls = spin.pulse_sin(301)[:-1]
+    rho0 = _mixed_rho(5, 3)
+    da = 1e-3 * np.random.default_rng(1).standard_normal(5)
+    _, fc1, r1 = orc.lindblad_t1(controls, 0.1, 3, 3, FQ, da, rho0)
+    fc2, r2 = orc.lindblad_knots(controls, 0.1, 3, 3, FQ, da, rho0, channels=1)
+    assert np.max(np.abs(r1 - r2)) < 5e-14 and np.max(np.abs(fc1 - fc2)) < 5e-14
+
+
+def test_density_ode_oracle_matches_an_adaptive_integration_of_the_reference_rhs(orc):
+    """scipy DOP853 (rtol = atol = 1e-13) on the right-hand side written as the reference writes it, T2 with the drive on and
+    T1+T2: what Vern9 at reltol 1e-12 would return, to the solver's tolerance."""
+    from scipy.integrate import solve_ivp
+
+    from rbqoc_b200 import spin
+
+    N0 = np.pi * np.array(orc_N0()); N1 = np.pi * np.array(orc_N1())
+    GE = np.array([[0, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 1], [0, 0, 0, 0]], dtype=float); EG = GE.T
+    NGG = -0.5 * np.diag([1.0, 0, 1, 0]); NEE = -0.5 * np.diag([0.0, 1, 0, 1])
+    NEG_DOP = -np.array([[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]], dtype=float)
+    controls = spin.pulse_sin(61)[:-1]
+    dt, nk = 0.1, 60
+    gc, gf = spin.GAMMAC, 30 * spin.GAMMAF_PREFACTOR
+    rho0 = _mixed_rho(2, 9)
+    for channels in (2, 3):
+        fid, rho = orc.lindblad_knots(controls, dt, 1, 2, FQ, None, rho0, channels=channels, gamma_c=gc, gamma_f=gf)
+
+        def rhs(t, y):
+            m = y.reshape(4, 4)
+            k = int(np.floor(t / dt + 1e-9)) % nk
+            a = controls[k]
+            h = FQ * N0 + a * N1
+            out = h @ m - m @ h + (gc + 2 * gf * gf * t) * NEG_DOP * m
+            if channels & 1:
+                g1 = 1.0 / orc.t1_ns(a)
+                out = out + g1 * (GE @ m @ EG + NEE @ m + m @ NEE) + g1 * (EG @ m @ GE + NGG @ m + m @ NGG)
+            return out.reshape(-1)
+
+        for s in range(2):
+            r = rho0[s]
+            y = np.block([[r.real, -r.imag], [r.imag, r.real]]).reshape(-1)
+            t = 0.0
+            for _ in range(2 * nk):                          # restart at every knot: the right-hand side jumps there
+                sol = solve_ivp(rhs, (t, t + dt), y, method="DOP853", rtol=1e-13, atol=1e-13, first_step=dt / 4)
+                y, t = sol.y[:, -1], t + dt
+            m = y.reshape(4, 4)
+            got = m[:2, :2] + 1j * m[2:, :2]
+            assert np.max(np.abs(got - rho[s])) < 2e-11, (channels, s)
+
+
+def test_density_ode_oracle_matches_50_digit_golden(orc):
+    z = np.load(GOLDEN + "/lindblad_t2.npz")
+    G = int(z["gate_count"])
+    for name, ch in (("t2", 2), ("t1t2", 3), ("t2c", 2), ("t2big", 2)):
+        _, rho = orc.lindblad_knots(z["controls"], float(z["dt"]), int(z["gate"]), G, float(z["fq"]), z["da"], z["rho0"], channels=ch,
+                                    gamma_c=float(z["gamma_c"]), gamma_f=float(z["gf_" + name]))
+        assert np.max(np.abs(rho - z["rho_" + name][:, G])) < 1e-15, name
