@@ -8,10 +8,16 @@ fidelity per sample + infidelity statistics.  A trajectory-step is one 4-real is
 one knot, so a step is S * 1000 trajectory-steps per GPU.
 
   value      device-resident inputs, rbq_mc_static_dev + (N>1) the one all-gather of rbq_stats
-  e2e        the host-pointer C-ABI call rbq_mc_static with pinned host buffers (H2D + D2H inside)
+  e2e        the reference-facing call: seeds in, per-sample fidelities + statistics out in HOST memory
+             (rbq_mc_static_philox, the shape of run_sim_prop(...; seed, state_seed), spin.jl:1553-1608); the second
+             form, explicit host sample arrays through rbq_mc_static (48 B/sample up), is reported beside it
+  parity     the first 10 000 samples of this very sweep against the CPU oracle, element-wise (tol 1e-12); a miss fails the run
   roofline   FP64 pipe: flops the SU(2) kernel executes per trajectory-step / measured DFMA peak
-  cpu_baseline / --impl reference: the CPU oracle (port of the reference algorithm; the Julia
-             reference cannot run in this image) on all host threads, bounded sample
+  configs    BASELINE configs[0..3] (spin13 / spin12 / spin30 rollout + Jacobians, Lindblad 1e5) each with its own value, e2e,
+             roofline and CPU baseline (all host threads and one thread)
+  strong_scaling  S_total = 1e6 / 1e7 / 1e8 samples split over the ranks of this run (seed-in form, statistics only)
+  cpu_baseline / --impl reference: the CPU restatement of the reference algorithm (the Julia reference cannot run in this
+             image or on the GPU box: `julia` is absent on both), built -O3 -march=native on the box, all host threads
 """
 import argparse
 import json
@@ -31,22 +37,22 @@ NK = 1000            # control knots of P_sin(1001)
 DT = 0.1
 S_PER_GPU = 1 << 20
 GATE_COUNT = 1
-# flops the closed-form kernel executes per trajectory-step on this grid (FMA = 2), counted in the SASS [DESIGN.md §4.2]:
+SEED = 2026
+PHILOX = (0.01, 0.03, 2.574e-5)   # fq_rel_sigma, fq_rel_clip, da_sigma (figures.jl:261,386; spin.jl:164)
+PARITY_N = 10_000
+PARITY_TOL = 1e-12
+# flops the closed-form kernel executes per trajectory-step on this grid (FMA = 2), counted in the SASS [DESIGN.md §4.2] and
+# cross-checked against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/):
 #   knot-table step (samples near the sweep centre -- every warp of this workload but ~0.3 %):
 #     1 DFMA (eps) + 2 DFMA (T) + 1 DADD (q) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v) = 14 FP64 instructions = 25 flop
-#   polynomial step (RBQ_NO_TABLE_CLASS=1, or samples far from the centre; tan form, degree-6 polynomial, class B):
-#     1 DADD (q) + 1 DFMA (x) + 6 DFMA (T(x)) + 2 DMUL + 8 DFMA = 18 FP64 instructions = 33 flop
-TABLE_CLASS = os.environ.get("RBQ_NO_TABLE_CLASS", "0") in ("", "0")
-FLOPS_PER_STEP_SU2 = 25.0 if TABLE_CLASS else 33.0
-FP64_INSTR_PER_STEP_SU2 = 14.0 if TABLE_CLASS else 18.0
-# FP64 instructions per step with three 64-bit register operands (state updates; with the table also eps and the two
-# Horner steps, whose coefficients are per-knot registers instead of constants)
-FP64_INSTR3_PER_STEP_SU2 = 11.0 if TABLE_CLASS else 8.0
+FLOPS_PER_STEP_SU2 = 25.0
+FP64_INSTR_PER_STEP_SU2 = 14.0
+FP64_INSTR3_PER_STEP_SU2 = 11.0   # of those, instructions with three fresh 64-bit register operands (3 issue cycles, not 2)
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default sizes, from the
-# `ncu --set full` capture summarised in profiles/r1b_ncu_mc_static_full.csv (50.44 MB read + 1.79 MB written: the 16 MB of
-# fidelities stay in the 126 MB L2); algorithmic bytes are 48 MB in + 16 MB out
-NCU_DRAM_TRAFFIC_BYTES_DEFAULT = 50_435_072 + 1_789_952
+# FP64 instructions per density-step of the Lindblad table step (lindblad_kernel): 27 DFMA (Horner of the 9
+# entries of E_k + da (L1_k + da (L2_k + da L3_k))) + 3 DMUL + 6 DFMA (apply) = 36 instructions = 69 flop
+LINDBLAD_INSTR_PER_STEP = 36.0
+LINDBLAD_FLOPS_PER_STEP = 69.0
 
 
 def sample_clocks(stop, out):
@@ -115,111 +121,121 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_rate(orc, controls, n_threads, target_seconds=12.0):
-    """Times the oracle (reference algorithm: per-knot Pade exp + 4x4 products, one sample per call)
-    on all host threads over a bounded sample of the same workload."""
-    rng = np.random.default_rng(0)
+WORKLOAD = (f"mc_static sweep (BASELINE configs[4]): P_sin({NK + 1}) = {NK} knots, dt={DT} ns, S={{S}} samples per GPU "
+            f"(Philox seed {SEED} keyed by global index; fq~N(0,1%) clipped 3%, da~N(0,2.574e-5)), target Z/2, "
+            f"gate_count={GATE_COUNT}, per-sample fidelities + statistics")
 
-    def inputs(S):
-        fq = 1.4e-2 * (1 + np.clip(0.01 * rng.standard_normal(S), -0.03, 0.03))
-        da = 2.574e-5 * rng.standard_normal(S)
-        psi = rng.random((S, 4))
-        psi /= np.linalg.norm(psi, axis=1, keepdims=True)
-        return fq, da, psi
 
-    S0 = 256 * n_threads
-    fq, da, psi = inputs(S0)
-    t0 = time.perf_counter()
-    orc.mc_static(controls, DT, 1, GATE_COUNT, fq, da, psi, nthreads=n_threads)
-    t_probe = time.perf_counter() - t0
-    S = int(max(S0, min(S0 * target_seconds / max(t_probe, 1e-6), 4_000_000)))
-    fq, da, psi = inputs(S)
+def cpu_arm_inputs(orc, S, first=0):
+    """The bench sweep's own samples (same Philox stream as the GPU arm), drawn by the oracle's generator."""
+    from rbqoc_b200 import spin
+
+    return orc.philox_samples(first, S, SEED, spin.FQ, *PHILOX)
+
+
+def cpu_reference_rate(orc, controls, n_threads, S):
+    """Times the CPU arm (reference algorithm: per-knot Pade exp + 4x4 products, one sample per call) on S samples of the
+    bench sweep."""
+    fq, da, psi = cpu_arm_inputs(orc, S)
     t0 = time.perf_counter()
     orc.mc_static(controls, DT, 1, GATE_COUNT, fq, da, psi, nthreads=n_threads)
     t = time.perf_counter() - t0
-    return S * NK / t, S, t
+    return S * NK / t, t
 
 
-def other_configs(eng, rbq, spin, torch, dev):
-    """BASELINE configs[0..3] at their named sizes, for context next to the headline (not bench lines of their own):
-    what one ALTRO iteration's worth of hot-path calls costs through the host-pointer C ABI, and the Lindblad sweep."""
+def cpu_baseline_block(orc, controls, threads, S_full, budget_s=12.0):
+    """cpu_baseline of the headline workload: the full S when it fits the time budget, else a bounded slice (stated)."""
+    rate0, t0 = cpu_reference_rate(orc, controls, threads, 256 * threads)          # probe (also warms the threads up)
+    S = int(min(S_full, max(256 * threads, budget_s * rate0 / NK)))
+    rate, t = cpu_reference_rate(orc, controls, threads, S)
+    rate1, t1 = cpu_reference_rate(orc, controls, 1, max(64, int(min(S, 2.0 * rate / threads / NK))))
+    return {"value": rate, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
+            "build": "g++ " + " ".join(orc.NATIVE_FLAGS[:2]) + " (oracle/_native, built on this host)",
+            "sample": (f"{S} of the sweep's {S_full} samples x {NK} knots in {t:.1f} s" if S < S_full else
+                       f"the full workload: {S} samples x {NK} knots in {t:.1f} s") +
+                      " (reference algorithm: generic Pade exp + 4x4 product per knot, OpenMP over samples)",
+            "one_thread": {"value": rate1, "unit": "trajectory-steps/s", "cores": 1}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0..3]: each with its own value / e2e / roofline / cpu_baseline
+# ---------------------------------------------------------------------------------------------------------------------------
+def measured_configs(eng, rbq, spin, torch, dev, stream, flush, orc, peaks, fp64_peak):
     out = {}
+    threads = host_threads()
+    hbm = peaks.get("hbm_gbs") or 6542.0
 
-    def timed_host(fn, reps=5):
-        fn()
-        t0 = time.perf_counter()
-        for _ in range(reps):
+    def dev_ms(fn, reps=5, warm=2):
+        """median device time of fn (which only enqueues on the engine's stream), L2 flushed before every repetition"""
+        for _ in range(warm):
             fn()
-        return (time.perf_counter() - t0) / reps * 1e3
+        evs = []
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+            fn()
+            with torch.cuda.stream(stream):
+                b.record(stream)
+            evs.append((a, b))
+        stream.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in evs]))
 
+    def host_ms(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)) * 1e3
+
+    def cpu_ms(fn, reps=3):
+        fn()
+        return min(host_ms(fn, reps=1) for _ in range(reps))
+
+    dd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     N = 1001
-    for name, model, x0 in (("spin13", spin.Spin13Model(), spin.spin13_x0()), ("spin12", spin.Spin12Model(), spin.spin12_x0()),
-                            ("spin30", spin.Spin30Model(), spin.spin30_x0())):
+    K1 = N - 1
+    for name, model, x0, iso in (("spin13", spin.Spin13Model(), spin.spin13_x0(), 2), ("spin12", spin.Spin12Model(), spin.spin12_x0(), 10),
+                                 ("spin30", spin.Spin30Model(), spin.spin30_x0(), 13)):
         n, m = model.n, model.m
-        dtv = np.full(N - 1, 0.1)
-        U = 1e-3 * np.sin(np.arange(N - 1) * 0.05)[:, None] * np.ones((1, m))
+        blk = n * (n + m) * 8
+        dtv = np.full(K1, 0.1)
+        U = 1e-3 * np.sin(np.arange(K1) * 0.05)[:, None] * np.ones((1, m))
         X = eng.rollout(model.params, x0, U, dtv)
-        K = 1e-3 * np.ones((N - 1, m, n))
-        d = 1e-4 * np.ones((N - 1, m))
-        alphas = 0.5 ** np.arange(8)
-        out[name] = {
-            "knots": N, "n": n,
-            "rollout_ms": timed_host(lambda: eng.rollout(model.params, x0, U, dtv)),
-            "jacobians_ms": timed_host(lambda: eng.jacobians(model.params, X[:-1], U, dtv)),
-            "jacobians_pinned_out_ms": (lambda buf: timed_host(lambda: eng.jacobians(model.params, X[:-1], U, dtv, out=buf)))(
-                eng.pinned_empty((N - 1, n + m, n))),
-            "closedloop_8_candidates_ms": timed_host(lambda: eng.rollout_closedloop(model.params, X, U, K, d, dtv, alphas)),
-            "api": "rbq_rollout / rbq_jacobians / rbq_rollout_closedloop, pageable host buffers (pinned where named), copies included",
+        # --- one trajectory (what one ALTRO iteration asks for): rollout + all Jacobians -------------------------------
+        dx0, dU, ddt = dd(x0[None]), dd(U), dd(dtv)
+        dX = torch.empty(N, n, dtype=torch.float64, device=dev)
+        dAB = torch.empty(K1, n * (n + m), dtype=torch.float64, device=dev)
+        ms_ro = dev_ms(lambda: eng.rollout_dev(model.params, 1, N, dx0, dU, ddt, dX))
+        ms_jac = dev_ms(lambda: eng.jacobians_dev(model.params, K1, dX, dU, ddt, dAB))
+        ab_pin = eng.pinned_empty((K1, n + m, n))
+        e2e_ms = host_ms(lambda: (eng.rollout(model.params, x0, U, dtv), eng.jacobians(model.params, X[:-1], U, dtv, out=ab_pin)))
+        orc.set_num_threads(threads)
+        cpu_all = cpu_ms(lambda: (orc.rollout(model.params, x0, U, dtv), orc.jacobians(model.params, X[:-1], U, dtv)))
+        orc.set_num_threads(1)
+        cpu_one = cpu_ms(lambda: (orc.rollout(model.params, x0, U, dtv), orc.jacobians(model.params, X[:-1], U, dtv)))
+        steps1 = K1 * iso
+        single = {
+            "workload": f"{name}: one trajectory, N={N} knots (n={n}): open-loop rollout + all {K1} knot-point Jacobians [A_k B_k]",
+            "value": steps1 / ((ms_ro + ms_jac) * 1e-3), "unit": "trajectory-steps/s", "rollout_ms": ms_ro, "jacobians_ms": ms_jac,
+            "e2e": {"value": steps1 / (e2e_ms * 1e-3), "unit": "trajectory-steps/s", "ms": e2e_ms,
+                    "h2d_bytes": (n + K1 * m + K1) * 8 + (K1 * n + K1 * m + K1) * 8, "d2h_bytes": N * n * 8 + K1 * blk,
+                    "api": "rbq_rollout + rbq_jacobians (host pointers, Jacobians into page-locked memory)"},
+            "roofline": {"bound": "latency", "frac": None,
+                         "how": ("one trajectory cannot fill the GPU: the floor is 2 kernel launches (~2-3 us each), the sequential control "
+                                 "chain of the rollout and, through the host ABI, 2 synchronous calls with their PCIe round trips "
+                                 f"(~10 us each) plus {K1 * blk / 1e6:.1f} MB of Jacobians over PCIe (~{K1 * blk / 55e9 * 1e3:.2f} ms at 55 GB/s)"),
+                         "jacobian_write_gbs": K1 * blk / (ms_jac * 1e-3) * 1e-9, "hbm_peak_gbs": hbm},
+            "cpu_baseline": {"value": steps1 / (cpu_all * 1e-3), "unit": "trajectory-steps/s", "cores": threads, "ms": cpu_all, "kind": "port",
+                             "sample": "the same trajectory: orc.rollout + orc.jacobians (reference step maps under forward-mode duals, "
+                                       "OpenMP over knots for the Jacobians)",
+                             "one_thread": {"value": steps1 / (cpu_one * 1e-3), "ms": cpu_one, "cores": 1}},
         }
-        # the backward pass on the Jacobians where rbq_jacobians_dev leaves them (device resident; LQR blocks of spin13.jl:128-135)
-        dd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        dX, dU, ddt = dd(X[:-1]), dd(U), dd(dtv)
-        dAB = torch.empty(N - 1, n * (n + m), dtype=torch.float64, device=dev)
-        dExx = dd(np.tile(np.eye(n), (N, 1, 1))); dEx = dd(0.1 * X)
-        dEuu = dd(np.tile(0.1 * np.eye(m), (N - 1, 1, 1))); dEux = dd(np.zeros((N - 1, n, m))); dEu = dd(0.1 * U)
-        dK = torch.empty(N - 1, n * m, dtype=torch.float64, device=dev); dd_ = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
-        ddV = torch.empty(2, dtype=torch.float64, device=dev); dfl = torch.empty(1, dtype=torch.int64, device=dev)
-
-        def expansion_and_pass():
-            eng.jacobians_dev(model.params, N - 1, dX, dU, ddt, dAB)
-            eng.backward_pass_dev(n, m, N, 1, dAB, dExx, dEx, dEuu, dEux, dEu, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
-            eng.synchronize()
-
-        out[name]["jacobians_plus_backward_pass_dev_ms"] = timed_host(expansion_and_pass)
-        # ... and the whole hot path of one iLQR iteration on the device: cost expansion (below), dynamics expansion,
-        # backward pass, 8 line-search candidates and their merit values
-        dXfull, dal = dd(X), dd(alphas)
-        dXc = torch.empty(8, N, n, dtype=torch.float64, device=dev); dUc = torch.empty(8, N - 1, m, dtype=torch.float64, device=dev)
-
-        # the cost side of the iteration: LQR objective + the reference's constraint list as augmented-Lagrangian terms
-        table = {"spin13": spin.spin13_constraints, "spin12": spin.spin12_constraints, "spin30": spin.spin30_constraints}[name](N, X[-1])
-        table.upload(dev)
-        dlam = torch.zeros(table.dual_size, dtype=torch.float64, device=dev); dmu = torch.ones(table.dual_size, dtype=torch.float64, device=dev)
-        dc = torch.empty(table.dual_size, dtype=torch.float64, device=dev); dJ = torch.empty(N, dtype=torch.float64, device=dev)
-        dcc = torch.empty(8, table.dual_size, dtype=torch.float64, device=dev); dJc = torch.empty(8, N, dtype=torch.float64, device=dev)
-        dQ = dd(np.ones(n)); dR = dd(0.1 * np.ones(m)); dQf = dd(float(N) * np.ones(n)); dxf = dd(X[-1])
-        dExxa = torch.empty(N, n * n, dtype=torch.float64, device=dev); dExa = torch.empty(N, n, dtype=torch.float64, device=dev)
-        dEuua = torch.empty(N - 1, m * m, dtype=torch.float64, device=dev); dEuxa = torch.empty(N - 1, m * n, dtype=torch.float64, device=dev)
-        dEua = torch.empty(N - 1, m, dtype=torch.float64, device=dev)
-
-        def al_cost():
-            eng.al_cost_expansion_dev(n, m, N, dXfull, dU, dQ, dR, dQf, dxf, None, table, dlam, dmu, dExxa, dExa, dEuua, dEuxa, dEua, dc, dJ)
-
-        out[name]["al_cost_expansion_dev_ms"] = timed_host(lambda: (al_cost(), eng.synchronize()))
-
-        def iteration_dev():
-            al_cost()
-            eng.jacobians_dev(model.params, N - 1, dXfull, dU, ddt, dAB)
-            eng.backward_pass_dev(n, m, N, 1, dAB, dExxa, dExa, dEuua, dEuxa, dEua, 1e-3, rbq.REG_CONTROL, dK, dd_, ddV, dfl)
-            eng.rollout_closedloop_dev(model.params, N, dXfull, dU, dK, dd_, ddt, 8, dal, dXc, dUc)
-            eng.al_cost_expansion_dev(n, m, N, dXc, dUc, dQ, dR, dQf, dxf, None, table, dlam, dmu, None, None, None, None, None, dcc, dJc, B=8)
-            eng.synchronize()
-
-        out[name]["ilqr_iteration_dev_ms"] = timed_host(iteration_dev)
-        # BASELINE's metric read literally (rollout + Jacobians): a batch of independent problems, device resident.  One
-        # trajectory-step = one 4-real iso state vector advanced one knot (spin13 carries 2, spin12 10, spin30 13 per knot).
+        # --- a batch of independent problems (hyper-parameter sweeps): the metric read literally -----------------------------
         Bt = {"spin13": 4096, "spin12": 1024, "spin30": 512}[name]
-        iso_vectors = {"spin13": 2, "spin12": 10, "spin30": 13}[name]
         bX0 = dd(np.tile(x0, (Bt, 1))); bU = dd(np.tile(U, (Bt, 1, 1)))
         bX = torch.empty(Bt, N, n, dtype=torch.float64, device=dev)
         # Jacobians at every state the rollout wrote, the terminal one included (N per trajectory, counted as N-1 below), so
@@ -228,18 +244,48 @@ def other_configs(eng, rbq, spin, torch, dev):
         chunk = 256
         bAB = torch.empty(chunk * N, n * (n + m), dtype=torch.float64, device=dev)      # one chunk of blocks, overwritten
 
-        def batch_rollout_jacobians():
+        def batch_rollout():
             eng.rollout_dev(model.params, Bt, N, bX0, bU, ddt, bX)
+
+        def batch_jacobians():
             for b0 in range(0, Bt, chunk):
                 cnt = min(chunk, Bt - b0)
                 eng.jacobians_dev(model.params, cnt * N, bX[b0:b0 + cnt], bU2[b0:b0 + cnt], bdt2[b0 * N:(b0 + cnt) * N], bAB)
-            eng.synchronize()
 
-        ms_b = timed_host(batch_rollout_jacobians, reps=2)
-        out[name]["batch_rollout_plus_jacobians"] = {"problems": Bt, "ms": ms_b, "iso_vectors_per_knot": iso_vectors,
-                                                     "trajectory_steps_per_s": Bt * (N - 1) * iso_vectors / ms_b * 1e3,
-                                                     "jacobian_bytes_written": Bt * N * n * (n + m) * 8}
-        del bX0, bU, bX, bAB, bU2, bdt2
+        ms_bro = dev_ms(batch_rollout, reps=3, warm=1)
+        ms_bjac = dev_ms(batch_jacobians, reps=3, warm=1)
+        stepsB = Bt * K1 * iso
+        jac_bytes = Bt * N * blk
+        # e2e of the batch through host buffers: a smaller batch (pinned output), PCIe bound by construction
+        Be = {"spin13": 256, "spin12": 32, "spin30": 16}[name]
+        x0e = np.tile(x0, (Be, 1)); Ue = np.tile(U, (Be, 1, 1))
+        Xe = eng.rollout(model.params, x0e, Ue, dtv)
+        abe = eng.pinned_empty((Be * K1, n + m, n))
+        Xk, Uk, dk = Xe[:, :-1].reshape(-1, n), Ue.reshape(-1, m), np.tile(dtv, Be)
+        e2e_b = host_ms(lambda: (eng.rollout(model.params, x0e, Ue, dtv), eng.jacobians(model.params, Xk, Uk, dk, out=abe)), reps=3)
+        # CPU arm on a bounded slice of the batch
+        Bc = {"spin13": 64, "spin12": 8, "spin30": 4}[name]
+        x0c = np.tile(x0, (Bc, 1)); Uc = np.tile(U, (Bc, 1, 1))
+        Xc = orc.rollout(model.params, x0c, Uc, dtv)
+        Xck, Uck, dck = Xc[:, :-1].reshape(-1, n), Uc.reshape(-1, m), np.tile(dtv, Bc)
+        orc.set_num_threads(threads)
+        cpu_b = cpu_ms(lambda: (orc.rollout(model.params, x0c, Uc, dtv), orc.jacobians(model.params, Xck, Uck, dck)), reps=2)
+        batched = {
+            "workload": f"{name}: {Bt} independent problems x N={N} knots, device resident: rollout + Jacobians at every knot",
+            "value": stepsB / ((ms_bro + ms_bjac) * 1e-3), "unit": "trajectory-steps/s", "rollout_ms": ms_bro, "jacobians_ms": ms_bjac,
+            "e2e": {"value": Be * K1 * iso / (e2e_b * 1e-3), "unit": "trajectory-steps/s", "ms": e2e_b, "problems": Be,
+                    "d2h_bytes": Be * N * n * 8 + Be * K1 * blk, "pcie_floor_ms": Be * K1 * blk / 55e9 * 1e3,
+                    "api": "rbq_rollout + rbq_jacobians (host pointers): PCIe bound, the Jacobian blocks are the payload"},
+            "roofline": {"bound": "hbm", "achieved": jac_bytes / (ms_bjac * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+                         "frac": jac_bytes / (ms_bjac * 1e-3) * 1e-9 / hbm, "traffic": None,
+                         "how": f"Jacobian kernel: n(n+m) 8 B = {blk} B written per knot x {Bt * N} knots / kernel time, against the measured copy peak "
+                                "(MEASURED_PEAKS.json hbm_gbs)"},
+            "cpu_baseline": {"value": Bc * K1 * iso / (cpu_b * 1e-3), "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{Bc} of the {Bt} problems in {cpu_b:.0f} ms (OpenMP over trajectories / knots)"},
+        }
+        out[name] = {"single_trajectory": single, "batched": batched}
+        del bX0, bU, bX, bAB, bU2, bdt2, ab_pin, abe
+    # --- configs[3]: Lindblad T1 rollout over 1e5 noise realisations ---------------------------------------------------------
     S = 100_000
     rng = np.random.default_rng(0)
     psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
@@ -247,24 +293,38 @@ def other_configs(eng, rbq, spin, torch, dev):
     rho0 = np.einsum("si,sj->sij", psi, psi.conj())
     vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4)).view(np.float64)
     controls = spin.pulse_sin(N)[:-1]
-    dcn, dda, drho = (torch.from_numpy(a).to(dev) for a in (controls, 2.574e-5 * rng.standard_normal(S), vec))
+    da_h = 2.574e-5 * rng.standard_normal(S)
+    dcn, dda, drho = (torch.from_numpy(a).to(dev) for a in (controls, da_h, vec))
     dfid = torch.empty(S, 2, dtype=torch.float64, device=dev)
     dro = torch.empty(S, 8, dtype=torch.float64, device=dev)
     dst = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
-
-    def lind():
-        eng.lindblad_dev(dcn, N - 1, 0.1, rbq.GATE_XPIBY2, 1, S, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst)
-        eng.synchronize()
-
-    ms = timed_host(lind)
-    out["lindblad_t1"] = {"realisations": S, "knots": N - 1, "gate_count": 1, "ms": ms, "density_steps_per_s": S * (N - 1) / ms * 1e3,
-                          "api": "rbq_lindblad_dev (device resident)"}
+    ms_l = dev_ms(lambda: eng.lindblad_dev(dcn, K1, 0.1, rbq.GATE_XPIBY2, 1, S, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst))
+    e2e_l = host_ms(lambda: eng.lindblad(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h, rho0), reps=3)
+    Sc = 2000
+    orc.set_num_threads(threads)
+    cpu_l = cpu_ms(lambda: orc.lindblad_t1(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h[:Sc], rho0[:Sc], nthreads=threads), reps=2)
+    cpu_l1 = cpu_ms(lambda: orc.lindblad_t1(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h[:128], rho0[:128], nthreads=1), reps=2)
+    ach = S * K1 * LINDBLAD_FLOPS_PER_STEP / (ms_l * 1e-3) * 1e-12
+    out["lindblad_t1"] = {
+        "workload": f"Lindblad T1 rollout (BASELINE configs[3]): P_sin({N}), {S} realisations (random pure rho0, static da~N(0,2.574e-5)), "
+                    "1 gate, sqrt-fidelity + final density per realisation",
+        "value": S * K1 / (ms_l * 1e-3), "unit": "density-steps/s", "ms": ms_l,
+        "e2e": {"value": S * K1 / (e2e_l * 1e-3), "unit": "density-steps/s", "ms": e2e_l, "h2d_bytes": S * 72 + K1 * 8, "d2h_bytes": S * 80 + 2096,
+                "api": "rbq_lindblad (host pointers, pageable numpy buffers)"},
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
+                     "fp64_instr_per_density_step": LINDBLAD_INSTR_PER_STEP, "flops_per_density_step": LINDBLAD_FLOPS_PER_STEP,
+                     "fp64_pipe_issue_util": S * K1 * LINDBLAD_INSTR_PER_STEP / (ms_l * 1e-3) * 2e-12 / fp64_peak if fp64_peak else None,
+                     "how": "table step: 36 FP64 instructions per density-step counted in the SASS of lindblad_kernel (DESIGN.md §4.4)"},
+        "cpu_baseline": {"value": Sc * K1 / (cpu_l * 1e-3), "unit": "density-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{Sc} of the {S} realisations in {cpu_l:.0f} ms (integrate_prop_lindbladt1!: complex 4x4 Pade exp + product per knot)",
+                         "one_thread": {"value": 128 * K1 / (cpu_l1 * 1e-3), "cores": 1}},
+    }
     return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The reference is Julia (absent here), so this is the
-    oracle port of its algorithm, all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU path.  The reference is Julia (absent here and on the GPU box), so this is the
+    C++ restatement of its algorithm built -O3 -march=native on this host, all host threads, the FULL per-step workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -272,23 +332,33 @@ def run_reference(args):
     from rbqoc_b200 import spin
 
     orc.build()
+    orc.use_native_build()
     controls = spin.pulse_sin(NK + 1)[:-1]
     threads = host_threads()
-    budget = 60.0 / max(args.steps + args.warmup, 1)
-    rates, S_used = [], 0
+    S = args.samples
+    # a probe decides whether the full S fits ~6 s per step; otherwise the step is a bounded slice (stated in `sample`)
+    rate0, _ = cpu_reference_rate(orc, controls, threads, 256 * threads)
+    S_step = int(min(S, max(256 * threads, 6.0 * rate0 / NK)))
+    fq, da, psi = cpu_arm_inputs(orc, S_step)
+    times = []
     for i in range(args.warmup + args.steps):
-        rate, S_used, _ = cpu_reference_rate(orc, controls, threads, target_seconds=min(budget, 10.0))
+        t0 = time.perf_counter()
+        orc.mc_static(controls, DT, 1, GATE_COUNT, fq, da, psi, nthreads=threads)
         if i >= args.warmup:
-            rates.append(rate)
-    value = float(np.mean(rates))
+            times.append(time.perf_counter() - t0)
+    ms = float(np.mean(times)) * 1e3
+    value = S_step * NK / (ms * 1e-3)
+    sample = (f"the full workload per step: {S_step} samples x {NK} knots" if S_step == S else
+              f"bounded slice per step: {S_step} of {S} samples x {NK} knots (throughput normalised)")
     line = {
         "impl": "reference", "metric": "fp64_trajectory_steps_per_sec", "value": value, "unit": "trajectory-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * S_used * NK / value,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"mc_static P_sin({NK + 1}) dt={DT} gate_count={GATE_COUNT}, bounded sample of {S_used} samples per step",
-                   "l2": "n/a (CPU)"},
+        "config": {"workload": WORKLOAD.format(S=S), "samples_per_gpu": S, "knots": NK, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{S_used} samples x {NK} knots per step, OpenMP over samples"},
+                         "build": "g++ " + " ".join(orc.NATIVE_FLAGS[:2]) + " (oracle/_native, built on this host)",
+                         "sample": sample + ", OpenMP over samples; reference algorithm = generic Pade exp + 4x4 product per knot "
+                                            "(the Julia reference itself cannot run: no julia on this box)"},
         "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -303,6 +373,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=S_PER_GPU, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[0..3] and the strong-scaling table")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -338,7 +409,6 @@ def main():
     eng.set_stream(stream.cuda_stream)
 
     controls_h = spin.pulse_sin(NK + 1)[:-1]
-    seed = 2026
     with torch.cuda.stream(stream):
         d_controls = torch.from_numpy(controls_h).to(dev)
         d_fq = torch.empty(S, dtype=torch.float64, device=dev)
@@ -348,10 +418,11 @@ def main():
         d_stats = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     # the sample set: Philox keyed by global index (materialised once; resident in HBM for `value`)
-    fq_h, da_h, psi0_h = eng.philox_samples(first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5)
+    fq_h, da_h, psi0_h = eng.philox_samples(first, S, SEED, spin.FQ, *PHILOX)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     fq_p, da_p, psi0_p = pin(fq_h), pin(da_h), pin(psi0_h)
     fid_p = torch.empty(S, GATE_COUNT + 1, dtype=torch.float64).pin_memory()
+    fid_p2 = torch.empty(S, GATE_COUNT + 1, dtype=torch.float64).pin_memory()
     with torch.cuda.stream(stream):
         d_fq.copy_(fq_p, non_blocking=True); d_da.copy_(da_p, non_blocking=True); d_psi0.copy_(psi0_p, non_blocking=True)
     stream.synchronize()
@@ -457,18 +528,26 @@ def main():
     eng.stats_reset_dev(d_stats)      # leave the statistics of exactly one pass in d_stats
     eng.mc_static_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, S, d_fq, d_da, d_psi0, rbq.ALGO_SU2, d_fid, d_stats)
 
-    # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
-    fid_np = fid_p.numpy()
-    for _ in range(max(1, args.warmup // 2)):
-        eng.mc_static(controls_h, DT, rbq.GATE_ZPIBY2, GATE_COUNT, fq_p.numpy(), da_p.numpy(), psi0_p.numpy(), fid_out=fid_np)
-    barrier()
+    # ---- e2e (headline): the seed-in call -- host controls + (seed, first, S) in, per-sample fidelities + statistics out in
+    #      page-locked HOST memory (rbq_mc_static_philox); the reference's API takes seeds, not sample arrays ----
+    fid_np, fid_np2 = fid_p.numpy(), fid_p2.numpy()
     e2e_steps = max(3, args.steps // 2)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _, st_e2e = eng.mc_static(controls_h, DT, rbq.GATE_ZPIBY2, GATE_COUNT, fq_p.numpy(), da_p.numpy(), psi0_p.numpy(),
-                                  fid_out=fid_np)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    def timed_host_calls(call):
+        for _ in range(max(1, args.warmup // 2)):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = call()
+        barrier()
+        return (time.perf_counter() - t0) / e2e_steps, res
+
+    seed_call = lambda: eng.mc_static_philox(controls_h, DT, rbq.GATE_ZPIBY2, GATE_COUNT, first, S, SEED, spin.FQ, *PHILOX, fid_out=fid_np2)
+    e2e_seed_s, (_, st_seed) = timed_host_calls(seed_call)
+    # ---- e2e, second form: explicit host sample arrays (48 B per sample up), zero-copy kernel over PCIe ----
+    arr_call = lambda: eng.mc_static(controls_h, DT, rbq.GATE_ZPIBY2, GATE_COUNT, fq_p.numpy(), da_p.numpy(), psi0_p.numpy(), fid_out=fid_np)
+    e2e_arr_s, (_, st_e2e) = timed_host_calls(arr_call)
     stop.set()
     th.join(timeout=2)
 
@@ -487,11 +566,48 @@ def main():
     h2d_gbs = copy_rate(d_psi0, psi0_p)
     d2h_gbs = copy_rate(fid_p, d_fid)
 
+    # ---- strong scaling: S_total samples split over the ranks of this run (seed-in form, statistics only) ----
+    strong = {}
+    if not args.no_configs:
+        d_st_s = torch.zeros(W, dtype=torch.int64, device=dev)
+        g_s = torch.zeros(world * W, dtype=torch.int64, device=dev)
+        for S_total in (10 ** 6, 10 ** 7, 10 ** 8):
+            f0, cnt = rdist.shard_range(S_total, rank, world)
+
+            def strong_step():
+                eng.stats_reset_dev(d_st_s)
+                eng.mc_static_philox_dev(d_controls, NK, DT, rbq.GATE_ZPIBY2, GATE_COUNT, f0, cnt, SEED, spin.FQ, *PHILOX, rbq.ALGO_SU2, None, d_st_s)
+                if world > 1:
+                    with torch.cuda.stream(stream):
+                        tdist.all_gather_into_tensor(g_s, d_st_s)
+
+            strong_step()
+            barrier()
+            reps = 3
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                a.record(stream)
+            for _ in range(reps):
+                strong_step()
+            with torch.cuda.stream(stream):
+                b.record(stream)
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = float(t.cpu())
+            host = (g_s if world > 1 else d_st_s).cpu().numpy().reshape(world, W)
+            total = rbq.stats_from_words(host[0])
+            for r in range(1, world):
+                rbq.stats_merge(total, rbq.stats_from_words(host[r]))
+            strong[f"{S_total:.0e}"] = {"samples_total": S_total, "ms": ms, "value": S_total * NK / (ms * 1e-3), "merged_count": int(total.count),
+                                        "mean_infidelity": total.mean}
+
     # ---- reduce over ranks (max time), print on rank 0 ----
-    times = torch.tensor([dev_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_seed_s * 1e3, e2e_arr_s * 1e3, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(times, op=tdist.ReduceOp.MAX)
-    dev_ms, e2e_ms, kern_ms = (float(x) for x in times.cpu())
+    dev_ms, e2e_seed_ms, e2e_arr_ms, kern_ms = (float(x) for x in times.cpu())
     stream.synchronize()
     st = rbq.stats_from_words(d_stats.cpu().numpy())     # this rank's last single pass (kernel-only loop epilogue)
     if rank == 0:
@@ -505,23 +621,36 @@ def main():
         except Exception:
             pass
         clk = clocks_summary(rows)
+        # ---- parity of this very sweep: first PARITY_N samples against the CPU oracle (parity build, not the timing build) ----
+        from oracle import oracle as orc
+
+        orc.build()
+        npar = min(PARITY_N, S)
+        ref = orc.mc_static(controls_h, DT, rbq.GATE_ZPIBY2, GATE_COUNT, fq_h[:npar], da_h[:npar], psi0_h[:npar])
+        got = d_fid[:npar].cpu().numpy()
+        par_abs = float(np.max(np.abs(got - ref)))
+        # the seed-in call draws the same samples on the device (Philox keyed by global index): same numbers, bit for bit
+        seed_vs_arrays = float(np.max(np.abs(fid_np2 - d_fid.cpu().numpy())))
+        ofq, oda, opsi = orc.philox_samples(first, npar, SEED, spin.FQ, *PHILOX)
+        samples_abs = float(max(np.max(np.abs(ofq - fq_h[:npar])), np.max(np.abs(oda - da_h[:npar])), np.max(np.abs(opsi - psi0_h[:npar]))))
+        parity = {"n": npar, "max_abs": par_abs, "tol": PARITY_TOL, "against": "orc.mc_static (reference algorithm, parity build) on the sweep's own first samples",
+                  "seed_in_vs_sample_arrays_max_abs": seed_vs_arrays, "device_vs_oracle_philox_samples_max_abs": samples_abs}
         line = {
             "metric": "fp64_trajectory_steps_per_sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"mc_static sweep (BASELINE configs[4]): P_sin({NK + 1}) = {NK} knots, dt={DT} ns, "
-                                   f"S={S} samples per GPU (Philox keyed by global index; fq~N(0,1%) clipped 3%, "
-                                   f"da~N(0,2.574e-5)), gate_count={GATE_COUNT}, per-sample fidelities + statistics",
-                       "samples_per_gpu": S, "knots": NK,
-                       "algo": ("su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre)"
-                                if TABLE_CLASS else "su2 closed form, tan form, degree-6 polynomial step"), "l2": "flushed between steps (256 MiB memset, untimed)",
+            "config": {"workload": WORKLOAD.format(S=S), "samples_per_gpu": S, "knots": NK,
+                       "algo": "su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre)",
+                       "l2": "flushed between steps (256 MiB memset, untimed)",
                        "sharding": ("contiguous sample ranges per rank; per step ONE all-gather of the 2.1 KB statistics, copied to pinned host "
                                     "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},
             "wall_s_timed_region": t_wall,
+            "parity": parity,
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_tflops if peak_tflops else None,
-                         "traffic": NCU_DRAM_TRAFFIC_BYTES_DEFAULT if (S == S_PER_GPU) else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1b_ncu_mc_static_full.csv)",
+                         "traffic": None,
+                         "traffic_note": "per-launch dram read+write of this kernel: see the `ncu --set full` capture of this round under profiles/ "
+                                         "(r1: 50.4 MB read + 1.8 MB written against 64 MB algorithmic; the 16 MB of fidelities stay in L2)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
                          # register-operand model of the FP64 pipe (profiles/r1_fp64_microbench.txt): 2 issue cycles per warp-DFMA
@@ -533,33 +662,51 @@ def main():
                          "kernel_ms": kern_ms,
                          "hbm": {"achieved_gbs": S * BYTES_PER_SAMPLE / (kern_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "algorithmic bytes; shows the path is not HBM bound"}},
-            "e2e": {"value": steps_per_step_all / (e2e_ms * 1e-3), "unit": "trajectory-steps/s",
-                    "h2d_bytes_per_step": S * 48 + NK * 8, "d2h_bytes_per_step": S * 16 + 2096, "ms_per_step": e2e_ms,
+            "e2e": {"value": steps_per_step_all / (e2e_seed_ms * 1e-3), "unit": "trajectory-steps/s",
+                    "h2d_bytes_per_step": NK * 8, "d2h_bytes_per_step": S * 16 + 2096, "ms_per_step": e2e_seed_ms,
                     "numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
-                    "api": ("rbq_mc_static (host pointers, pinned): " + ("streamed in one-wave chunks" if os.environ.get("RBQ_MC_ZEROCOPY") == "0"
-                                                                          else "zero-copy, the kernel reads the samples and writes the fidelities over PCIe")),
+                    "api": "rbq_mc_static_philox: host controls + (seed, first, S) in; S x 2 fidelities + rbq_stats out in page-locked host memory "
+                           "(written by the kernel over PCIe while it computes); the shape of the reference's run_sim_prop(...; seed, state_seed)",
+                    "explicit_sample_arrays": {"value": steps_per_step_all / (e2e_arr_ms * 1e-3), "ms_per_step": e2e_arr_ms,
+                                               "h2d_bytes_per_step": S * 48 + NK * 8, "d2h_bytes_per_step": S * 16 + 2096,
+                                               "api": "rbq_mc_static (host sample arrays, pinned): zero-copy, the kernel reads the samples and writes the "
+                                                      "fidelities over PCIe"},
                     "pcie_measured": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
-                                      "h2d_floor_ms": (S * 48 + NK * 8) / (h2d_gbs * 1e6) if h2d_gbs else None}},
+                                      "h2d_floor_ms_explicit": (S * 48 + NK * 8) / (h2d_gbs * 1e6) if h2d_gbs else None,
+                                      "d2h_floor_ms": (S * 16) / (d2h_gbs * 1e6) if d2h_gbs else None}},
             "gpu_launches": launches,
             "clocks": clk,
-            "result": {"mean_infidelity": st.mean, "count": st.count,
+            "result": {"mean_infidelity": st.mean, "count": st.count, "mean_infidelity_seed_in_call": st_seed.mean,
                        "merged_count_all_ranks": merged["last"].count if merged["last"] is not None else None},
         }
-        if world == 1:
+        if strong:
+            line["strong_scaling"] = dict(strong, note="S_total samples split over this run's ranks (contiguous global index ranges), "
+                                                       "rbq_mc_static_philox_dev + one all-gather of the statistics per pass; device time, max over ranks")
+        native_ok = False
+        if not args.no_cpu_baseline or (world == 1 and not args.no_configs):
             try:
-                line["other_configs"] = other_configs(eng, rbq, spin, torch, dev)
-            except Exception as exc:   # context only: never let it break the contract line
-                line["other_configs"] = {"error": repr(exc)}
+                orc.use_native_build()      # timing build of the CPU arm from here on (parity above used the parity build)
+                native_ok = True
+            except Exception as exc:
+                line["cpu_native_build_error"] = repr(exc)
+        if world == 1 and not args.no_configs:
+            try:
+                line["configs"] = measured_configs(eng, rbq, spin, torch, dev, stream, flush, orc, peaks, peak_tflops)
+            except Exception as exc:   # never let the extra configurations break the contract line
+                line["configs"] = {"error": repr(exc)}
         if not args.no_cpu_baseline:
-            from oracle import oracle as orc
-
-            orc.build()
             threads = host_threads()
-            rate, S_cpu, t_cpu = cpu_reference_rate(orc, controls_h, threads)
-            line["cpu_baseline"] = {"value": rate, "unit": "trajectory-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{S_cpu} samples x {NK} knots of the same workload in {t_cpu:.1f} s "
-                                              "(reference algorithm: generic Pade exp + 4x4 product per knot, OpenMP over samples)"}
+            cb = cpu_baseline_block(orc, controls_h, threads, S)
+            if not native_ok:
+                cb["build"] = "liboracle.so (-O2 -mavx2 -ffp-contract=off; the native build failed)"
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
+        if par_abs > PARITY_TOL or seed_vs_arrays > PARITY_TOL:
+            print(f"PARITY FAILURE: max_abs={par_abs:.3e} (tol {PARITY_TOL}), seed-in vs arrays {seed_vs_arrays:.3e}", file=sys.stderr, flush=True)
+            if world > 1:
+                tdist.barrier()
+                tdist.destroy_process_group()
+            sys.exit(3)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()

@@ -824,6 +824,14 @@ int orc_num_threads(void) {
 }
 
 // A, E row-major 4x4.  Returns the Pade degree used.
+// thread count of the OpenMP loops that take no nthreads argument (orc_jacobians, orc_rollout, ...); n <= 0: all
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}
 int orc_expm4(const double* A, double* E) {
     Mat4<double> M; for (int i = 0; i < 16; ++i) M.a[i / 4][i % 4] = A[i];
     int deg; Mat4<double> R = expm_ref(M, &deg);

@@ -57,6 +57,49 @@ class Stats(C.Structure):
     ]
 
 
+_NATIVE_DIR = os.path.join(_HERE, "_native")
+_NATIVE_LIB = os.path.join(_NATIVE_DIR, "liboracle_native.so")
+NATIVE_FLAGS = ["-O3", "-march=native", "-std=c++17", "-fPIC", "-fopenmp", "-shared"]
+
+
+def _cpu_tag() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+
+                    return hashlib.sha1(line.encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
+def use_native_build() -> str:
+    """TIMING ARM ONLY (bench.py cpu_baseline / --impl reference): rebuild the restatement with the flags BASELINE.md §4
+    names for the CPU baseline, `-O3 -march=native` (contraction left at the compiler's default), for the host this runs on,
+    and route this module's calls to it.  The parity suite keeps liboracle.so (-O2 -ffp-contract=off, Julia's evaluation
+    order).  The build lands in oracle/_native/ (git- and gpurun-ignored: it is specific to the CPU it was built on)."""
+    global _lib
+    tag_path = os.path.join(_NATIVE_DIR, "cpu.tag")
+    src = os.path.join(_HERE, "oracle.cpp")
+    fresh = (os.path.exists(_NATIVE_LIB) and os.path.exists(tag_path) and open(tag_path).read() == _cpu_tag()
+             and os.path.getmtime(_NATIVE_LIB) >= os.path.getmtime(src))
+    if not fresh:
+        os.makedirs(_NATIVE_DIR, exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx] + NATIVE_FLAGS + ["-o", _NATIVE_LIB, src], check=True)
+        with open(tag_path, "w") as f:
+            f.write(_cpu_tag())
+    _lib = None
+    lib(_NATIVE_LIB)
+    return _NATIVE_LIB
+
+
+def set_num_threads(n: int = 0):
+    lib().orc_set_num_threads(int(n))
+
+
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the Makefile next to this file (building the checker is not
     using it)."""
@@ -70,12 +113,12 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
-def lib():
+def lib(path: str | None = None):
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if path is None and not os.path.exists(_LIB_PATH):
             build()
-        _lib = C.CDLL(_LIB_PATH)
+        _lib = C.CDLL(path or _LIB_PATH)
         _lib.orc_fidelity_vec_iso2.restype = C.c_double
         _lib.orc_fidelity_mat.restype = C.c_double
         _lib.orc_t1_ns.restype = C.c_double
@@ -83,7 +126,7 @@ def lib():
         _lib.orc_t1_ns.argtypes = [C.c_double]
         _lib.orc_t1_reduced_us.argtypes = [C.c_double]
         for name in ("orc_pade13_coeffs", "orc_gate_error_expansion", "orc_propagator", "orc_lindblad_generator", "orc_philox4x32_10", "orc_philox_samples",
-                     "orc_pink_filter", "orc_pink_noise", "orc_stats"):
+                     "orc_pink_filter", "orc_pink_noise", "orc_stats", "orc_set_num_threads"):
             getattr(_lib, name).restype = None
     return _lib
 

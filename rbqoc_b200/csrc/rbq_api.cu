@@ -637,13 +637,18 @@ int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, 
     void *dc, *dfid = nullptr, *dst = nullptr;
     const int64_t G1 = gate_count + 1;
     CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc));
-    if (fid) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    // page-locked fid (rbq_host_alloc / rbq_host_register / torch pin_memory) and few recorded gates: the kernel writes the
+    // fidelities straight to host memory while it computes (no staging buffer, no trailing copy), as rbq_mc_static does
+    void* mfid = nullptr;
+    const bool direct = fid && S > 0 && h->opt.mc_zerocopy && algo == RBQ_ALGO_SU2 && gate_count <= 3 && host_mapped(fid, &mfid);
+    if (fid && !direct) CKL(dev_buf(h, B_OUT0, sizeof(double) * S * G1, &dfid));
+    if (direct) dfid = mfid;
     if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
     int rc = rbq_mc_static_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma,
                                       fq_rel_clip, da_sigma, algo, (double*)dfid, (rbq_stats*)dst);
     if (rc) return rc;
-    if (fid && S > 0) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
+    if (fid && S > 0 && !direct) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
     if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;

@@ -259,9 +259,12 @@ class Engine:
         return fid, st
 
     def mc_static_philox(self, controls, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma,
-                         algo=_lib.ALGO_SU2, want_fid=False):
+                         algo=_lib.ALGO_SU2, want_fid=False, fid_out=None):
+        """Seeds in, fidelities / statistics out (the shape of the reference's run_sim_prop(...; seed, state_seed)).
+        fid_out: optional (S, gate_count+1) float64 buffer; when it is page-locked (pinned_empty, torch pin_memory) the kernel
+        writes it directly."""
         controls = _f64(controls)
-        fid = np.empty((S, gate_count + 1)) if want_fid else None
+        fid = fid_out if fid_out is not None else (np.empty((S, gate_count + 1)) if want_fid else None)
         st = Stats()
         self._ck(self._lib.rbq_mc_static_philox(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate),
                                                 int(gate_count), int(first), int(S), int(seed), float(fq0),
