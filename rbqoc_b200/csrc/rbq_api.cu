@@ -54,6 +54,7 @@ static int dev_buf(rbq_handle* h, int role, size_t bytes, void** out) {
     *out = h->dbuf[role];
     return 0;
 }
+int rbq_scratch(rbq_handle* h, int role, size_t bytes, void** out) { return dev_buf(h, role, bytes, out); }
 #define ENTER(h)                                                \
     if (!(h)) return RBQ_E_NULL;                                \
     (h)->err[0] = 0;                                            \
@@ -873,7 +874,14 @@ int rbq_lindblad_dev(rbq_handle* h, const double* d_controls, int64_t nknots, do
         CKL(launch_lindblad_shared_map(h, a, channels, (double*)sc + 8));
         a.shared_map = (const double*)sc + 8;
     }
-    CKL(launch_lindblad(h, a, channels, &nblocks));
+    // per-realisation offsets with time-independent rates: per-knot Frechet table instead of the series (rbq_mc.cu)
+    if (d_da && !time_dep && h->opt.lindblad_table && nknots <= ((int64_t)1 << 24)) {
+        void* tb;
+        CKL(dev_buf(h, B_QUAT, sizeof(double) * 48 * (size_t)nknots, &tb));
+        CKL(launch_lindblad_table(h, a, channels, d_controls, (double*)tb, &nblocks));
+    } else {
+        CKL(launch_lindblad(h, a, channels, &nblocks));
+    }
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
     return RBQ_OK;
 }

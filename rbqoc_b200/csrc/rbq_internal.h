@@ -48,6 +48,10 @@ struct rbq_handle {
 // option parsing shared by rbq_create (environment) and rbq_set_option; value NULL or "" restores the default
 int rbq_apply_option(rbq_handle* h, const char* name, const char* value);
 
+// grow-only device scratch of the handle for the launchers (role = one of the RBQ_SCR_* slots); returns 0 or an error code
+#define RBQ_SCR_JACREC 15
+int rbq_scratch(rbq_handle* h, int role, size_t bytes, void** out);
+
 namespace rbq {
 
 // per-block partial statistics, reduced in block order by stats_finalize_kernel (deterministic)
@@ -114,6 +118,9 @@ int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nbl
 int launch_timeline(rbq_handle* h, const SegmentArgs& a, const int64_t* d_save_after, int64_t nsave, int* nblocks_out);
 int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channels, double* d_map);
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out);
+// per-knot Frechet table (d_table: nk rows of 48 doubles) + the sweep kernel that reads it; needs a.da != NULL
+int launch_lindblad_table(rbq_handle* h, const LindbladArgs& a, int channels, const double* d_controls, double* d_table,
+                          int* nblocks_out);
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo);
 int64_t mc_static_wave_samples(const rbq_handle* h, int algo);
 int mc_noise_blocks(const rbq_handle* h, int64_t S);
@@ -148,5 +155,9 @@ int launch_al_dual_update(rbq_handle* h, int ncon, const rbq_constraint* d_cons,
                           int update, double* d_viol);
 int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                      const double* d_t, const double* d_dt, double* d_AB);
+// structured Jacobians of the unscented models (rbq_jac_unscented.cu): one sample state, d_AB 16-byte aligned
+size_t unscented_record_bytes(int64_t K);
+int launch_jacobians_unscented(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
+                               const double* d_t, const double* d_dt, double* d_rec, double* d_AB);
 
 }  // namespace rbq

@@ -1033,6 +1033,263 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
     }
 }
 
+// ---- Lindblad sweep with per-realisation amplitude offsets: per-knot Frechet table -------------------------------------------
+// A realisation's generator at knot k is M_k(d) = M_k + d D1_k + d^2 D2_k + d^3 D3_k + O(d^4), d = its static offset
+// (D1 = the rotation about x plus the slope of gamma_1 = 1/T1(a); D2, D3 = the curvature of 1/T1 inside a linear cell of the
+// T1 table), so exp(M_k(d)) = E_k + d L1_k + d^2 L2_k + d^3 L3_k + O(d^4) with 3x3 coefficient matrices that depend on the
+// knot only.  lindblad_table_kernel computes them once per sweep (one thread per knot: the Taylor series of exp in
+// truncated-polynomial arithmetic, E_k itself in double-double so that its rounding does not repeat coherently along a
+// constant-amplitude segment), and the sweep kernel advances a Bloch vector with
+//     r <- E_hi r + (E_lo + d (L1 + d (L2 + d L3))) r          27 + 18 = 45 FP64 instructions
+// instead of the ~105 of the 13-term series.  Rows with flag != 0 (the offset range straddles a kink of the T1 table or of
+// |a|, the curvature terms are not negligible, or ||M dt|| > 1) and realisations with |d| > da_tab take the series step.
+constexpr int LT_ROW = 48;      // doubles per table row: E_hi, E_lo, L1, L2, L3 (9 each, row-major), a_k, flag, pad
+constexpr int LT_TILE = 32;     // knots per shared-memory tile (12 KB), two tiles in flight
+struct dd { double h, l; };
+RBQ_DEV dd dd_two_sum(double a, double b) { const double s = __dadd_rn(a, b), bb = __dadd_rn(s, -a); return {s, __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb))}; }
+RBQ_DEV dd dd_add(dd a, dd b) { dd s = dd_two_sum(a.h, b.h); const double e = __dadd_rn(s.l, __dadd_rn(a.l, b.l)); const double h = __dadd_rn(s.h, e); return {h, __dadd_rn(e, -__dadd_rn(h, -s.h))}; }
+RBQ_DEV dd dd_mul(dd a, dd b) { const double p = __dmul_rn(a.h, b.h); double e = __fma_rn(a.h, b.h, -p); e = __fma_rn(a.h, b.l, __fma_rn(a.l, b.h, e)); const double h = __dadd_rn(p, e); return {h, __dadd_rn(e, -__dadd_rn(h, -p))}; }
+// a / n for a small positive integer n, to double-double accuracy
+RBQ_DEV dd dd_div_int(dd a, int n) {
+    const double dn = (double)n, q = __ddiv_rn(a.h, dn);
+    const double rem = __dadd_rn(__fma_rn(-q, dn, a.h), a.l);      // a.h - q n is exact in one FMA
+    const double q2 = __ddiv_rn(rem, dn), h = __dadd_rn(q, q2);
+    return {h, __dadd_rn(q2, -__dadd_rn(h, -q))};
+}
+__global__ void __launch_bounds__(128) lindblad_table_kernel(const double* __restrict__ controls, int64_t nk, double dt, double fq,
+                                                             int channels, double t2_gamma_c, double da_tab, double* __restrict__ table) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    const bool t1_on = (channels & RBQ_LINDBLAD_T1) != 0, t2_on = (channels & RBQ_LINDBLAD_T2) != 0;
+    const double a = controls[k], w2 = 2.0 * RBQ_PI * dt;
+    // gamma_1(a + d) dt = dt / (T + T' d) = g1 (1 - rho d + rho^2 d^2 - rho^3 d^3 + ...), rho = T'/T, inside one cell of the table
+    double g1 = 0.0, rho = 0.0;
+    bool flag = !(fabs(a) > da_tab);                      // |a + d| has its kink inside the offset range (also catches NaN)
+    if (t1_on) {
+        Tan<1> ta; ta.v = a; ta.d[0] = 1.0;
+        const Tan<1> T = t1_interp<Tan<1>>(ta, 1e3);
+        g1 = dt / T.v; rho = T.d[0] / T.v;
+        // same cell over the whole offset range?  compare the interpolant with its linear model at both ends
+        const double Tp = t1_interp<double>(a + da_tab, 1e3), Tm = t1_interp<double>(a - da_tab, 1e3);
+        const double lin_p = fma(T.d[0], da_tab, T.v), lin_m = fma(-T.d[0], da_tab, T.v);
+        if (fabs(Tp - lin_p) > 1e-9 * T.v || fabs(Tm - lin_m) > 1e-9 * T.v) flag = true;
+        const double x = rho * da_tab;
+        if (x * x * x * x * g1 > 1e-18) flag = true;      // the dropped fourth-order curvature term
+    }
+    const double gphi = t2_on ? dt * t2_gamma_c : 0.0;
+    const double wz = w2 * fq, wx = w2 * a;
+    if (!(w2 * (fabs(fq) + fabs(a) + da_tab) + 2.0 * g1 + gphi <= 1.0)) flag = true;   // the sweep kernel sub-steps such knots
+    // generator polynomial in d: D[0] = M, D[1] = w2 Lx - g1 rho diag(1,1,2), D[2] = g1 rho^2 (-diag), D[3] = -g1 rho^3 (-diag)
+    double D[4][9];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) D[j][i] = 0.0;
+    D[0][0] = -(g1 + gphi); D[0][1] = -wz; D[0][3] = wz; D[0][4] = -(g1 + gphi); D[0][5] = -wx; D[0][7] = wx; D[0][8] = -2.0 * g1;
+    double cj = g1;
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        cj *= -rho;                                       // g1 (-rho)^j
+        D[j][0] = -cj; D[j][4] = -cj; D[j][8] = -2.0 * cj;
+    }
+    D[1][5] = -w2; D[1][7] = w2;
+    // Taylor series of exp(sum_j d^j D_j) truncated at d^3: T_n[j] = sum_{i<=j} T_{n-1}[j-i] D_i / n; order 0 in double-double
+    dd T0[9], A0[9];
+    double T[3][9], A[3][9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        T0[i] = dd{(i % 4 == 0) ? 1.0 : 0.0, 0.0}; A0[i] = T0[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { T[j][i] = 0.0; A[j][i] = 0.0; }
+    }
+    for (int n = 1; n <= 30; ++n) {
+        const double in = 1.0 / (double)n;
+        dd N0[9];
+        double N[3][9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                dd acc0{0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) acc0 = dd_add(acc0, dd_mul(T0[3 * r + q], dd{D[0][3 * q + c], 0.0}));
+                N0[3 * r + c] = dd_div_int(acc0, n);
+#pragma unroll
+                for (int j = 1; j <= 3; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i <= j; ++i)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const double t = (j - i == 0) ? T0[3 * r + q].h : T[j - i - 1][3 * r + q];
+                            acc = fma(t, D[i][3 * q + c], acc);
+                        }
+                    N[j - 1][3 * r + c] = acc * in;
+                }
+            }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            T0[i] = N0[i]; A0[i] = dd_add(A0[i], N0[i]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { T[j][i] = N[j][i]; A[j][i] += N[j][i]; }
+        }
+    }
+    double* row = table + (size_t)k * LT_ROW;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        row[i] = A0[i].h; row[9 + i] = A0[i].l; row[18 + i] = A[0][i]; row[27 + i] = A[1][i]; row[36 + i] = A[2][i];
+    }
+    row[45] = a; row[46] = flag ? 1.0 : 0.0; row[47] = 0.0;
+}
+
+// series step for one (sub-stepped if needed) knot with the realisation's own amplitude: the fallback of the table kernel
+template <int NV>
+RBQ_DEV void bloch_series_knot(double c1, double fq, double dt, bool t1_on, double gphi_rate, const double* __restrict__ invk,
+                               const unsigned char* __restrict__ cells, double (&r)[NV][3]) {
+    const double b = 2.0 * RBQ_PI * dt * (fabs(fq) + fabs(c1)) + dt * ((t1_on ? 2.0 / 269.03e3 : 0.0) + gphi_rate);
+    const int nsub = b == b && b > 1.0 ? (int)fmin(ceil(b), 4096.0) : 1;
+    const int kmax = b == b ? taylor_terms(b / (double)nsub) : 60;
+    const double h = dt / (double)nsub, w2h = 2.0 * RBQ_PI * h;
+    BlochGen m;
+    m.wz = w2h * fq; m.wxa = m.wxb = w2h * c1;
+    const double g1 = t1_on ? h / t1_ns_fast(c1, cells) : 0.0;
+    m.g2 = g1 + h * gphi_rate; m.g1 = 2.0 * g1;
+    for (int q = 0; q < nsub; ++q) bloch_advance<NV>(m, kmax, invk, r);
+}
+
+// SPT realisations per thread (they share the table row's registers), NV = 1 (the state itself, gate_count <= 3) or 3 (the
+// one-gate map's three columns, applied gate_count times afterwards)
+template <int SPT, int NV>
+__global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs a, int channels, const double* __restrict__ table,
+                                                              double da_tab) {
+    __shared__ __align__(128) double tile_s[2 * LT_TILE * LT_ROW];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[16];
+    __shared__ double invk_s[64];
+    __shared__ unsigned char t1cells_s[244];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += nth) hist_s[b] = 0;
+    if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
+    t1_cells_init(t1cells_s, tid, nth);
+    PulsePipeT<LT_TILE, LT_ROW> pipe;
+    pipe.init(tile_s, bar_s, table, a.nk);
+
+    const bool t1_on = (channels & RBQ_LINDBLAD_T1) != 0, t2_on = (channels & RBQ_LINDBLAD_T2) != 0;
+    const double gphi_rate = t2_on ? a.t2_gamma_c : 0.0;
+    const int64_t base = (int64_t)blockIdx.x * nth * SPT;
+    int64_t s[SPT]; bool live[SPT]; double d[SPT], tr0[SPT], r0[SPT][3];
+    double st[SPT][NV][3];
+    bool in_range = true;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        s[i] = base + (int64_t)i * nth + tid;
+        live[i] = s[i] < a.S;
+        const int64_t sc = live[i] ? s[i] : a.S - 1;
+        d[i] = a.da[sc];
+        in_range = in_range && (fabs(d[i]) <= da_tab);
+        const double* q = a.rho0 + 8 * sc;
+        tr0[i] = q[0] + q[6];
+        r0[i][0] = q[2] + q[4]; r0[i][1] = q[3] - q[5]; r0[i][2] = q[0] - q[6];
+#pragma unroll
+        for (int c = 0; c < NV; ++c)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) st[i][c][x] = NV == 1 ? r0[i][x] : (c == x ? 1.0 : 0.0);
+    }
+    const bool warp_table = __all_sync(0xffffffffu, in_range);
+    const int64_t passes = NV == 1 ? a.gate_count : 1;
+    for (int64_t g = 0; g < passes; ++g) {
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, g + 1 < passes);
+            const int len = pipe.tile_len(ti);
+            for (int j = 0; j < len; ++j) {
+                const double2* __restrict__ row = reinterpret_cast<const double2*>(tile + j * LT_ROW);
+                const double2 af = row[22];                            // (E/L3 tail, a_k) sits in row[22] = doubles 44, 45
+                const double flag = tile[j * LT_ROW + 46];
+                if (warp_table && flag == 0.0) {
+                    double tb[46];
+#pragma unroll
+                    for (int q = 0; q < 23; ++q) { const double2 v = row[q]; tb[2 * q] = v.x; tb[2 * q + 1] = v.y; }
+#pragma unroll
+                    for (int i = 0; i < SPT; ++i) {
+                        double F[9];
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) F[e] = fma(d[i], fma(d[i], fma(d[i], tb[36 + e], tb[27 + e]), tb[18 + e]), tb[9 + e]);
+#pragma unroll
+                        for (int c = 0; c < NV; ++c) {
+                            const double x0 = st[i][c][0], x1 = st[i][c][1], x2 = st[i][c][2];
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr) {
+                                const double lo = fma(F[3 * rr + 2], x2, fma(F[3 * rr + 1], x1, F[3 * rr] * x0));
+                                st[i][c][rr] = fma(tb[3 * rr + 2], x2, fma(tb[3 * rr + 1], x1, fma(tb[3 * rr], x0, lo)));
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SPT; ++i) bloch_series_knot<NV>(af.y + d[i], a.fq, a.dt, t1_on, gphi_rate, invk_s, t1cells_s, st[i]);
+                }
+            }
+            pipe.release(g + 1 < passes || ti + 1 < pipe.ntiles);
+        }
+        if (NV == 1) {
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                if (a.fid && live[i]) {
+                    double tg[3];
+                    const int k = (int)((g + 1) & 3);
+                    if (k == 0) { tg[0] = r0[i][0]; tg[1] = r0[i][1]; tg[2] = r0[i][2]; }
+                    else mv3_to(a.gate.r[k - 1], r0[i], tg);
+                    a.fid[s[i] * (a.gate_count + 1) + g + 1] = fidelity_bloch(tr0[i], st[i][0], tr0[i], tg);
+                }
+            }
+        }
+    }
+    ThreadStats ts;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        double r[3] = {r0[i][0], r0[i][1], r0[i][2]};
+        double f = fidelity_bloch(tr0[i], r, tr0[i], r);
+        double* frow = (a.fid && live[i]) ? a.fid + s[i] * (a.gate_count + 1) : nullptr;
+        if (frow) frow[0] = f;
+        if (NV == 1) {
+            if (a.gate_count > 0) {
+                r[0] = st[i][0][0]; r[1] = st[i][0][1]; r[2] = st[i][0][2];
+                double tg[3];
+                const int k = (int)(a.gate_count & 3);
+                if (k == 0) { tg[0] = r0[i][0]; tg[1] = r0[i][1]; tg[2] = r0[i][2]; }
+                else mv3_to(a.gate.r[k - 1], r0[i], tg);
+                f = fidelity_bloch(tr0[i], r, tr0[i], tg);
+            }
+        } else {
+            for (int64_t g = 1; g <= a.gate_count; ++g) {
+                const double n0 = fma(st[i][2][0], r[2], fma(st[i][1][0], r[1], st[i][0][0] * r[0]));
+                const double n1 = fma(st[i][2][1], r[2], fma(st[i][1][1], r[1], st[i][0][1] * r[0]));
+                const double n2 = fma(st[i][2][2], r[2], fma(st[i][1][2], r[1], st[i][0][2] * r[0]));
+                r[0] = n0; r[1] = n1; r[2] = n2;
+                double tg[3];
+                const int k = (int)(g & 3);
+                if (k == 0) { tg[0] = r0[i][0]; tg[1] = r0[i][1]; tg[2] = r0[i][2]; }
+                else mv3_to(a.gate.r[k - 1], r0[i], tg);
+                f = fidelity_bloch(tr0[i], r, tr0[i], tg);
+                if (frow) frow[g] = f;
+            }
+        }
+        if (a.rho_out && live[i]) {
+            double* o = a.rho_out + 8 * s[i];
+            o[0] = 0.5 * (tr0[i] + r[2]); o[1] = 0.0;
+            o[2] = 0.5 * r[0];            o[3] = 0.5 * r[1];
+            o[4] = 0.5 * r[0];            o[5] = -0.5 * r[1];
+            o[6] = 0.5 * (tr0[i] - r[2]); o[7] = 0.0;
+        }
+        if (a.partials && live[i]) ts.add(1.0 - f, hist_s);
+    }
+    if (a.partials) {
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
 // One-gate Bloch map shared by every realisation (no per-sample amplitude offsets, time-independent rates): what the
 // reference recomputes for each of its 1000 seeds (figures.jl gen_1c).  One block: thread k exponentiates knot k's
 // generator (3 columns), an ordered tree product in shared memory multiplies 256 knots at a time into the running map.
@@ -1348,7 +1605,8 @@ int64_t mc_static_wave_samples(const rbq_handle* h, int algo) {
     return (int64_t)h->sm_count * minb * threads * spt;
 }
 int mc_noise_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
-int lindblad_blocks(const rbq_handle*, int64_t S) { return (int)((S + MC_THREADS - 1) / MC_THREADS); }
+// upper bound of the grid of either Lindblad sweep kernel (sizes the per-block partials)
+int lindblad_blocks(const rbq_handle* h, int64_t S) { return (int)((S + 31) / 32) + h->sm_count; }
 
 int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax) {
     // staged pulse lives in dbuf[0] (sized by the caller), padded to a multiple of 2 knots
@@ -1425,10 +1683,37 @@ int launch_lindblad_shared_map(rbq_handle* h, const LindbladArgs& a, int channel
     return (int)cudaGetLastError();
 }
 int launch_lindblad(rbq_handle* h, const LindbladArgs& a, int channels, int* nblocks_out) {
-    const int blocks = lindblad_blocks(h, a.S);
+    const int blocks = (int)((a.S + MC_THREADS - 1) / MC_THREADS);
     if (nblocks_out) *nblocks_out = blocks;
     lindblad_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, channels);
     h->launches++;
+    return (int)cudaGetLastError();
+}
+// largest offset the Frechet table serves: the dropped term (w2 d)^4 / 24 of the rotation stays below 5e-18
+double lindblad_table_range(double dt) { return 1.05e-4 / (2.0 * RBQ_PI * fabs(dt)); }
+int launch_lindblad_table(rbq_handle* h, const LindbladArgs& a, int channels, const double* d_controls, double* d_table,
+                          int* nblocks_out) {
+    const double da_tab = lindblad_table_range(a.dt);
+    lindblad_table_kernel<<<(unsigned)((a.nk + 127) / 128), 128, 0, h->stream>>>(d_controls, a.nk, a.dt, a.fq, channels, a.t2_gamma_c, da_tab, d_table);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    // Whole waves: the kernel is FP64-pipe bound, so an SM with one warp more than its neighbours finishes later by that warp's
+    // whole run.  Spread the warps evenly: `waves` blocks per SM, every block the same number of warps (<= 16: 128 registers).
+    const bool compose = a.gate_count > 3;
+    const int64_t warps1 = (a.S + 31) / 32;
+    const int spt = (!compose && warps1 >= (int64_t)h->sm_count * 8) ? 2 : 1;      // two realisations share a table row's loads
+    const int64_t warps = (a.S + 32 * spt - 1) / (32 * spt);
+    const int64_t per_sm = (warps + h->sm_count - 1) / h->sm_count;
+    const int64_t waves = (per_sm + 15) / 16;
+    int wpb = (int)((warps + h->sm_count * waves - 1) / (h->sm_count * waves));
+    if (wpb < 1) wpb = 1;
+    const int threads = 32 * wpb;
+    const int blocks = (int)((a.S + (int64_t)threads * spt - 1) / ((int64_t)threads * spt));
+    if (nblocks_out) *nblocks_out = blocks;
+    if (compose) lindblad_tab_kernel<1, 3><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
+    else if (spt == 2) lindblad_tab_kernel<2, 1><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
+    else lindblad_tab_kernel<1, 1><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
+    h->launches += 2;
     return (int)cudaGetLastError();
 }
 int launch_stats_finalize(rbq_handle* h, const BlockPartial* partials, int nblocks, rbq_stats* d_stats) {

@@ -300,6 +300,15 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
     int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
     const bool unscented = fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25;
+    // unscented models with one sample state (every run of the reference): the block is assembled from its structure, the value
+    // path evaluated once per knot instead of once per seed column (rbq_jac_unscented.cu); RBQ_JAC_STRUCTURED=0 keeps the
+    // generic forward-mode kernel below (tests compare the two)
+    if (unscented && p.sample_state_count == 1 && h->opt.jac_structured && (reinterpret_cast<uintptr_t>(d_AB) & 15) == 0) {
+        void* rec = nullptr;
+        const int rc = rbq_scratch(h, RBQ_SCR_JACREC, unscented_record_bytes(K), &rec);
+        if (rc) return rc;
+        return launch_jacobians_unscented(h, p, K, d_X, d_U, d_t, d_dt, (double*)rec, d_AB);
+    }
     // the unscented step is register hungry: one tangent per lane (254 registers, no spills) beats two (255 + 868 B of spills)
     // by 1.4x on batches although every lane repeats the value path; RBQ_JAC_NT_UNSCENTED=2 selects the old split
     if (unscented) nt = h->opt.jac_nt_unscented == 2 ? 2 : 1;

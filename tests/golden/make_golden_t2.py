@@ -46,6 +46,19 @@ def main():
             print(name, "sample", s, flush=True)
         out["rho_" + name] = rho
         out["gf_" + name] = gf
+    # realistic offsets (2.574e-5 GHz, spin.jl:164): the regime the engine's per-knot Frechet table serves; T1 and T1 + constant T2
+    da_small = 2.574e-5 * rng.standard_normal(S)
+    out["da_small"] = da_small
+    for name, t2, gc in (("t1_small", False, 0.0), ("t1t2c_small", True, GAMMAC)):
+        rho = np.empty((S, G + 1, 2, 2), dtype=np.complex128)
+        for s in range(S):
+            res = ref.sim_density_ode([F(a) for a in controls], F(dt), G, ref.FQ, F(da_small[s]),
+                                      [[mp.mpc(complex(rho0[s, i, j])) for j in range(2)] for i in range(2)],
+                                      t1=True, t2=t2, gamma_c=F(gc), gamma_f=F(0.0))
+            for g, m in enumerate(res):
+                rho[s, g] = [[complex(m[0][0]), complex(m[0][1])], [complex(m[1][0]), complex(m[1][1])]]
+            print(name, "sample", s, flush=True)
+        out["rho_" + name] = rho
     np.savez_compressed(os.path.join(HERE, "lindblad_t2.npz"), **out)
 
 

@@ -674,3 +674,60 @@ def test_evaluate_adev_matches_serial_oracle_loop(engine, oracle):
         f = oracle.mc_noise(controls, dt, rbq.GATE_XPIBY2, gates, spin.FQ, noise, spin.DT_NOISE_INV, psi0)
         ge[k] = 1 - f[0, -1]
     assert np.max(np.abs(res["gate_errors"] - ge)) < 5e-12            # 3 x 5680 chained Pade exponentials on the oracle side
+
+
+# ---- Lindblad sweeps with realistic per-realisation offsets: the per-knot Frechet table path ---------------------------------
+@pytest.mark.parametrize("name", ["sin301_dt0.1", "sin1001_dt0.1", "y2_dt0.01", "ragged_2049"])
+@pytest.mark.parametrize("gate_count", [1, 3, 6], ids=["g1", "g3", "g6compose"])
+@pytest.mark.parametrize("channels", [rbq.LINDBLAD_T1, rbq.LINDBLAD_T1 | rbq.LINDBLAD_T2], ids=["t1", "t1t2c"])
+def test_lindblad_table_path_matches_series_path_and_oracle(engine, oracle, name, gate_count, channels):
+    """Offsets of the size the reference's noise model gives (2.574e-5 GHz) take the table step (E_k + d L1_k + d^2 L2_k +
+    d^3 L3_k per knot); a few realisations far outside the table's range share warps with them and take the series step, as
+    do the knots next to a kink of the T1 table.  Both forms must agree to rounding, and with the oracle at the Lindblad bar."""
+    controls, dt, gate = PULSES[name]
+    S = 777                                                   # ragged: 24 full warps + 9 threads
+    rho0 = _rand_rho(S, 31, mixed=True)
+    rng = np.random.default_rng(6)
+    da = 2.574e-5 * rng.standard_normal(S)
+    da[5::97] = 3e-3 * rng.standard_normal(da[5::97].shape[0])    # out-of-range realisations: their warps fall back
+    gc = spin.GAMMAC if channels & rbq.LINDBLAD_T2 else 0.0
+    fid, rho, st = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, da, rho0, channels=channels, t2_gamma_c=gc)
+    engine.set_option("RBQ_LINDBLAD_TABLE", "0")
+    fid2, rho2, st2 = engine.lindblad(controls, dt, gate, gate_count, spin.FQ, da, rho0, channels=channels, t2_gamma_c=gc)
+    nk = controls.shape[0]
+    assert np.max(np.abs(rho - rho2)) < max(2e-13, 1e-16 * nk * gate_count), name
+    assert np.max(np.abs(fid - fid2)) < max(1e-12, 1e-15 * nk * gate_count), name
+    assert st.count == st2.count == S and abs(st.sum - st2.sum) < 1e-11 * S
+    sub = slice(0, 120)
+    rfid, rrho = oracle.lindblad_knots(controls, dt, gate, gate_count, spin.FQ, da[sub], rho0[sub], channels=channels, gamma_c=gc)
+    assert np.max(np.abs(rho[sub] - rrho)) < 5e-12 and np.max(np.abs(fid[sub] - rfid)) < 5e-12, name
+
+
+def test_lindblad_table_path_matches_50_digit_golden(engine):
+    z = np.load(GOLDEN + "/lindblad_t2.npz")
+    G = int(z["gate_count"])
+    for name, ch, gc in (("t1_small", rbq.LINDBLAD_T1, 0.0), ("t1t2c_small", rbq.LINDBLAD_T1 | rbq.LINDBLAD_T2, float(z["gamma_c"]))):
+        for opt in (None, "0"):
+            engine.set_option("RBQ_LINDBLAD_TABLE", opt)
+            fid, rho, _ = engine.lindblad(z["controls"], float(z["dt"]), int(z["gate"]), G, float(z["fq"]), z["da_small"], z["rho0"],
+                                          channels=ch, t2_gamma_c=gc)
+            assert np.max(np.abs(rho - z["rho_" + name][:, G])) < 1e-13, (name, opt)
+
+
+def test_lindblad_table_path_full_size_balanced_grid(engine, oracle):
+    """BASELINE configs[3] at full size (1e5 realisations, P_sin(1001)): spot rows against the oracle, every fidelity finite and
+    in [0, 1], and the statistics equal those of the returned fidelities."""
+    controls, dt, gate = PULSES["sin1001_dt0.1"]
+    S = 100_000
+    rng = np.random.default_rng(0)
+    psi = rng.random((S, 2)) + 1j * rng.random((S, 2))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho0 = np.einsum("si,sj->sij", psi, psi.conj())
+    da = 2.574e-5 * rng.standard_normal(S)
+    fid, rho, st = engine.lindblad(controls, dt, rbq.GATE_XPIBY2, 1, spin.FQ, da, rho0)
+    assert st.count == S and np.all(np.isfinite(fid)) and fid.min() >= 0.0 and fid.max() <= 1.0 + 1e-12
+    e = 1.0 - fid[:, -1]
+    assert abs(st.sum - e.sum()) <= 1e-12 * abs(e.sum()) + 1e-15 and st.min == e.min() and st.max == e.max()
+    pick = np.concatenate([np.arange(0, 64), np.arange(S - 64, S), rng.integers(0, S, 128)])
+    _, _, rrho = oracle.lindblad_t1(controls, dt, rbq.GATE_XPIBY2, 1, spin.FQ, da[pick], rho0[pick])
+    assert np.max(np.abs(rho[pick] - rrho)) < 5e-12

@@ -245,6 +245,7 @@ def test_jacobians_staged_kernel_equals_direct(engine, oracle, name, model, monk
     X = np.stack([p[0] for p in pts])
     U = np.stack([p[1] for p in pts])
     dt = rng.choice([0.1, 0.01], K)
+    engine.set_option("RBQ_JAC_STRUCTURED", "0")     # the generic forward-mode kernels (the unscented models default to the structured ones)
     engine.set_option("RBQ_JAC_STAGED", "0")
     direct = engine.jacobians(model.params, X, U, dt).copy()
     engine.set_option("RBQ_JAC_STAGED", "1")
@@ -404,3 +405,49 @@ def test_packed_batch_rollout_equals_warp_rollout(engine, oracle, name, model, m
     assert np.array_equal(Xw, Xp), name
     Xr = oracle.rollout(model.params, x0[:5], U[:5], dt)
     assert _relerr(Xp[:5], Xr) < 5e-12, name
+
+
+@pytest.mark.parametrize("name,model", [mm for mm in MODELS if mm[1].params.model_id in (30, 25) and mm[1].params.sample_state_count == 1],
+                         ids=lambda v: v if isinstance(v, str) else "")
+@pytest.mark.parametrize("K", [1, 63, 3001])
+def test_structured_unscented_jacobians_equal_generic_forward_mode(engine, oracle, name, model, K):
+    """spin30 / spin25 with one sample state assemble [A_k B_k] from the block structure (value path once per knot, sparse
+    seeds through mean -> covariance -> Cholesky -> resample -> normalise; one bulk store per block).  Same derivatives as the
+    generic tangent kernel and as the oracle's dual numbers; K = 3001 makes every persistent block loop over several knots
+    (both stage buffers in use), K = 1 and 63 leave blocks idle."""
+    rng = np.random.default_rng(_seed(name, 77) + K)
+    pts = [_random_point(model, rng) for _ in range(min(K, 200))]
+    X = np.stack([pts[i % len(pts)][0] for i in range(K)]) * (1 + 1e-3 * rng.standard_normal((K, 1)))
+    U = np.stack([pts[i % len(pts)][1] for i in range(K)])
+    dt = rng.choice([0.1, 0.01], K)
+    t = dt * rng.integers(0, 9, K)                      # spin25: knot index 0..8 selects the filter start-up branch
+    structured = engine.jacobians(model.params, X, U, dt, t=t).copy()
+    engine.set_option("RBQ_JAC_STRUCTURED", "0")
+    generic = engine.jacobians(model.params, X, U, dt, t=t).copy()
+    scale = np.max(np.abs(generic), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(structured - generic) / scale) < 1e-12, name
+    pick = rng.integers(0, K, min(K, 24))
+    ref = oracle.jacobians(model.params, X[pick], U[pick], dt[pick], t=t[pick])
+    rs = np.max(np.abs(ref), axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(structured[pick] - ref) / rs) < JAC_RTOL, name
+
+
+def test_structured_unscented_jacobians_unaligned_output_falls_back(engine, oracle):
+    """A device output buffer that starts on an odd double cannot take bulk stores: the launcher must use the generic kernel."""
+    import torch
+
+    model = spin.Spin30Model()
+    n, m, K = model.n, model.m, 40
+    rng = np.random.default_rng(3)
+    pts = [_random_point(model, rng) for _ in range(K)]
+    X = np.stack([p[0] for p in pts]); U = np.stack([p[1] for p in pts]); dt = np.full(K, 0.1)
+    dev = torch.device("cuda", 0)
+    engine.use_torch_stream()
+    dX, dU, ddt = (torch.from_numpy(a).to(dev) for a in (X, U, dt))
+    buf = torch.zeros(K * n * (n + m) + 1, dtype=torch.float64, device=dev)
+    engine.jacobians_dev(model.params, K, dX, dU, ddt, buf[1:])
+    engine.synchronize()
+    got = buf[1:].cpu().numpy().reshape(K, n + m, n).transpose(0, 2, 1)
+    ref = engine.jacobians(model.params, X, U, dt)
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
+    engine.set_stream(0)
