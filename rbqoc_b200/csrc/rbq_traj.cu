@@ -9,6 +9,7 @@
 #include "rbq_internal.h"
 #include "rbq_models.cuh"
 #include "rbq_warp_rollout.cuh"
+#include "rbq_scan_rollout.cuh"
 
 namespace rbq {
 
@@ -248,7 +249,26 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
     // 0.60 / 4.2 ms one warp each; spin12 0.50 against 0.55 ms at 4096 but 6.6 against 3.9 ms at 32768 (43 doubles per
     // knot leave as scattered 32-byte stores), so the 10-block models switch back above 8192
     const bool packed_default = B >= 16 && (fam0 != RBQ_MODEL_SPIN12 || B <= 8192);
-    if (independent_blocks && (h->opt.rollout_packed >= 0 ? h->opt.rollout_packed != 0 : packed_default)) {
+    // few trajectories: each as a prefix product over its knots (rbq_scan_rollout.cuh) instead of a walk along them.
+    // Open loop only; the blocks of these families evolve linearly.  RBQ_ROLLOUT_SCAN=0/1 forces the choice.
+    const int64_t steps = N - 1;
+    const bool scan_ok = independent_blocks && steps >= 1 && steps <= (int64_t)SCAN_T * SCAN_MAX_PER && B <= 65535;
+    const bool scan_default = B < 16 && steps >= 64;
+    if (scan_ok && (h->opt.rollout_scan >= 0 ? h->opt.rollout_scan != 0 : scan_default)) {
+        WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
+        const int per = (int)((steps + SCAN_T - 1) / SCAN_T);
+        const size_t smem = scan_rollout_smem(steps);
+        cudaError_t e;
+        if (fam0 == RBQ_MODEL_SPIN12) {
+            e = cudaFuncSetAttribute(scan_rollout_kernel<RBQ_MODEL_SPIN12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            scan_rollout_kernel<RBQ_MODEL_SPIN12><<<(unsigned)B, SCAN_T, smem, h->stream>>>(a, per);
+        } else {
+            e = cudaFuncSetAttribute(scan_rollout_kernel<RBQ_MODEL_SPIN13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            scan_rollout_kernel<RBQ_MODEL_SPIN13><<<(unsigned)B, SCAN_T, smem, h->stream>>>(a, per);
+        }
+    } else if (independent_blocks && (h->opt.rollout_packed >= 0 ? h->opt.rollout_packed != 0 : packed_default)) {
         // one thread per (trajectory, block): all lanes busy (see packed_rollout_kernel); 32-thread blocks spread small
         // batches over the SMs
         WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};

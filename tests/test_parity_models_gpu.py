@@ -451,3 +451,30 @@ def test_structured_unscented_jacobians_unaligned_output_falls_back(engine, orac
     ref = engine.jacobians(model.params, X, U, dt)
     assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
     engine.set_stream(0)
+
+
+@pytest.mark.parametrize("name,model", [mm for mm in MODELS if mm[1].params.model_id in (13, 15, 12, 18)], ids=lambda v: v if isinstance(v, str) else "")
+@pytest.mark.parametrize("N", [2, 66, 1001, 5681])
+def test_scan_rollout_equals_stepwise_rollout_and_oracle(engine, oracle, name, model, N):
+    """Open-loop rollouts of one (or a few) trajectories run as a prefix product of quaternions over the knots
+    (rbq_scan_rollout.cuh); the step-by-step kernels and the oracle walk the knots.  Same control chain bit for bit (it is
+    still evaluated sequentially), states equal to product-order rounding."""
+    rng = np.random.default_rng(_seed(name, 5) + N)
+    n, m = model.n, model.m
+    B = 3
+    x0 = np.stack([_random_point(model, rng)[0] for _ in range(B)])
+    x0[:, 8:11] = rng.uniform(-0.05, 0.05, (B, 3))
+    U = rng.uniform(-2e-3, 2e-3, (B, N - 1, m))
+    if model.params.model_id == 15 and model.params.time_optimal:
+        U[:, :, 1] = rng.uniform(0.2, 0.4, (B, N - 1))
+    dt = rng.choice([0.1, 0.01], N - 1)
+    engine.set_option("RBQ_ROLLOUT_SCAN", "1")
+    Xs = engine.rollout(model.params, x0, U, dt)
+    engine.set_option("RBQ_ROLLOUT_SCAN", "0")
+    engine.set_option("RBQ_ROLLOUT_PACKED", "0")
+    Xw = engine.rollout(model.params, x0, U, dt)
+    cb = slice(8, 11)
+    assert np.array_equal(Xs[:, :, cb], Xw[:, :, cb]), name           # the control chain is the same sequence of operations
+    assert _relerr(Xs, Xw) < 1e-13 + 2e-16 * N, name
+    Xr = oracle.rollout(model.params, x0, U, dt)
+    assert _relerr(Xs, Xr) < 1e-12, name
