@@ -12,10 +12,12 @@
 // ~250 multiply-adds instead of the ~1500 a generic tangent pushes through the whole 56-state step.  So:
 //   unscented_values_kernel   one THREAD per knot: the value path once (not once per seed column), the intermediate values
 //                             the tangents need written as a 136-double record
-//   unscented_tangent_kernel  one 64-thread block per knot (persistent over knots): lanes 0..39 the sigma-point columns, lane 40
-//                             d/da, lane 41 d/d(noise amplitude), the rest the structural entries; the block is assembled in
-//                             shared memory (zeros written once: the sparsity pattern never changes) and leaves by ONE bulk TMA
-//                             store (cp.async.bulk.global.shared::cta), double buffered against the next knot's arithmetic.
+//   unscented_tangent_kernel  one 64-thread block per knot (persistent over knots): lanes 0..39 the sigma-point columns, the
+//                             rest the structural entries; the dense directions (d/da, spin25: d/d noise amplitude and the
+//                             tap columns) are linear combinations of the sigma-point columns (a 41 x 40 mat-vec out of shared
+//                             memory); the block is assembled in shared memory (zeros written once: the sparsity pattern never
+//                             changes) and leaves by ONE bulk TMA store (cp.async.bulk.global.shared::cta), double buffered
+//                             against the next knot's arithmetic; the next knot's record is prefetched into registers.
 // Derivatives are exact derivatives of the closed-form step; they equal the reference's dual numbers to ~1e-14 (tests: 1e-10).
 // sm_100a only.
 #include "rbq_internal.h"
@@ -33,8 +35,31 @@ constexpr int UR_INV = 68;    // 1 / L_jj
 constexpr int UR_U = 72;      // the 10 normalised outputs
 constexpr int UR_N = 112;     // their 1 / norm before normalisation
 constexpr int UR_DN = 122;    // mean - nominal state
-constexpr int UR_YK = 126;    // spin25: namp * d yk / d (xp1, xp2, xp3, yp1, yp2, yp3)
-constexpr int UR_SIZE = 136;
+constexpr int UR_YK = 126;    // spin25: d yk / d (xp1, xp2, xp3, yp1, yp2, yp3)
+constexpr int UR_W = 136;     // w_j = M_j' (dM_j/da) s_j^in: 10 x 4 (the amplitude direction in sigma-point coordinates)
+constexpr int UR_ST = 176;    // values of the structural entries, in the order of structural_positions()
+constexpr int UR_SIZE = 256;
+constexpr int UJ_NST30 = 70, UJ_NST25 = 60;
+// destination (column-major index into the n x (n+m) block) of structural entry e; the values kernel writes the values in
+// the same order.  spin30: 48 E-block entries, 12 amplitude-column entries of the nominal states, 6 chain entries, 4 penalty
+// entries against the nominal state; spin25: 32 + 8 + 6 + 4, then the yk row (6) and the four tap shifts.
+__constant__ unsigned short c_stpos[2][3][72];      // [spin25?][nominal block][entry]: every upload of a slice writes the same values
+static void structural_positions(bool s25, int nom, unsigned short* pos) {
+    const int N = s25 ? 58 : 56, OFF = s25 ? 17 : 15, ACOL = s25 ? 9 : 13, NB = s25 ? 2 : 3, CB = s25 ? 8 : 12;
+    int e = 0;
+    for (int b = 0; b < NB; ++b) for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) pos[e++] = (unsigned short)((4 * b + c) * N + 4 * b + r);
+    for (int b = 0; b < NB; ++b) for (int r = 0; r < 4; ++r) pos[e++] = (unsigned short)(ACOL * N + 4 * b + r);
+    for (int r = 0; r < 3; ++r) {
+        pos[e++] = (unsigned short)((CB + r) * N + CB + r);                       // 1 on the diagonal
+        pos[e++] = (unsigned short)((r == 2 ? N : CB + r + 1) * N + CB + r);      // dt next to it (the last one in the control column)
+    }
+    for (int i = 0; i < 4; ++i) pos[e++] = (unsigned short)((nom + i) * N + OFF + 40);
+    if (s25) {
+        for (int q = 0; q < 6; ++q) pos[e++] = (unsigned short)((11 + q) * N + 14);
+        const int rr[4] = {12, 13, 15, 16};
+        for (int q = 0; q < 4; ++q) pos[e++] = (unsigned short)((rr[q] - 1) * N + rr[q]);
+    }
+}
 #define URTRI(i, k) ((i) * ((i) + 1) / 2 + (k))
 
 // entry (r, c) of the 4x4 iso matrix c I + sp N0 + sq N1 (rows of prop_apply)
@@ -67,7 +92,7 @@ struct UnscentedJacArgs {
 };
 
 template <int MODEL>
-__global__ void __launch_bounds__(128) unscented_values_kernel(const UnscentedJacArgs a) {
+__global__ void __launch_bounds__(64) unscented_values_kernel(const UnscentedJacArgs a) {
     constexpr bool S25 = MODEL == RBQ_MODEL_SPIN25;
     constexpr int OFF = S25 ? 17 : 15, ACOL = S25 ? 9 : 13;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,8 +203,48 @@ __global__ void __launch_bounds__(128) unscented_values_kernel(const UnscentedJa
         for (int i = 0; i < 4; ++i) { rec[UR_U + 4 * j + i] = vp[i] * np; rec[UR_U + 4 * (j + 5) + i] = vm[i] * nm; }
     }
     const int nom = p.nominal_offset[0];
+    double dn[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rec[UR_DN + i] = sm[i] - x[nom + i];
+    for (int i = 0; i < 4; ++i) { dn[i] = sm[i] - x[nom + i]; rec[UR_DN + i] = dn[i]; }
+    // the amplitude direction in sigma-point coordinates: w_j = M_j' (dM_j/da) s_j^in (spin25: its entries 16..19 and 36..39
+    // are also the noise-amplitude direction, with opposite signs)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int sel = j == 4 ? 3 : (j == 9 ? 6 : 0);
+        double t[4], w[4];
+        iso_apply(de + sel, x + OFF + 4 * j, t);
+        const double et[3] = {e[sel], -e[sel + 1], -e[sel + 2]};      // the transpose
+        iso_apply(et, t, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rec[UR_W + 4 * j + i] = w[i];
+    }
+    // structural entries, in the order of structural_positions()
+    constexpr int NB = S25 ? 2 : 3;
+    double* st = rec + UR_ST;
+    int q = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st[q++] = iso_entry(e, r, c);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        double t[4];
+        iso_apply(de, x + 4 * b, t);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) st[q++] = t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { st[q++] = 1.0; st[q++] = dt; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st[q++] = -2.0 * p.S_diag[i] * dn[i];
+    if (S25) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st[q++] = rec[UR_YK + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[q++] = 1.0;
+    }
 }
 
 // Given the tangent of the mean (dsm) and of the packed covariance (dP), the tangents of the chunk's 41 outputs.
@@ -237,33 +302,45 @@ template <int N> RBQ_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wai
 RBQ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int UJ_THREADS = 64;
+// The dense directions need no differentiation of their own.  The chunk's outputs depend on the propagated sigma points s_j
+// only, and a seed e_i in sigma point j gives ds_j = M_j e_i (the 40 sparse columns).  A change of the amplitude gives
+// ds_j = (dM_j/da) s_j^in = M_j w_j with w_j = M_j' (dM_j/da) s_j^in (M_j is orthogonal), so by linearity
+//     column(a) = sum_{j,i} w_j[i] column(j, i):
+// a 41 x 40 matrix-vector product over the columns already sitting in the staging buffer, one row per lane.  The same holds
+// for spin25's noise amplitude (only points 5 and 10 move, with opposite signs), of which the six tap columns are multiples.
+// One staging buffer per block and as many blocks per SM as shared memory holds (8 / 7): the kernel is a chain of short
+// dependent sections, and knots in flight are what hides them.
 template <int MODEL>
 __global__ void __launch_bounds__(UJ_THREADS) unscented_tangent_kernel(const UnscentedJacArgs a) {
     constexpr bool S25 = MODEL == RBQ_MODEL_SPIN25;
-    constexpr int OFF = S25 ? 17 : 15, ACOL = S25 ? 9 : 13, NB = S25 ? 2 : 3, CB = S25 ? 8 : 12;
-    constexpr int N = S25 ? 58 : 56, NM = N + 1, BLK = N * NM;
+    constexpr int OFF = S25 ? 17 : 15, ACOL = S25 ? 9 : 13;
+    constexpr int N = S25 ? 58 : 56, NM = N + 1, BLK = N * NM, NST = S25 ? UJ_NST25 : UJ_NST30;
+    constexpr int NREC = UR_SIZE / UJ_THREADS;      // record doubles each thread moves (256 / 64)
     extern __shared__ __align__(128) double sm_[];
-    double* stage0 = sm_;                       // [2][BLK]
-    double* rec = sm_ + 2 * BLK;                // [UR_SIZE]
-    double* xs = rec + UR_SIZE;                 // [N + 2]: x, dt
-    double* scratch = xs + N + 2;               // [41]: the d/d(noise amplitude) column of spin25
+    double* stage = sm_;                        // [BLK]
+    double* rec = sm_ + BLK;                    // [UR_SIZE]
     const int tid = threadIdx.x;
     const rbq_model_params& p = a.p;
-    for (int i = tid; i < 2 * BLK; i += UJ_THREADS) stage0[i] = 0.0;
+    for (int i = tid; i < BLK; i += UJ_THREADS) stage[i] = 0.0;
     const double alpha = p.alpha, cf = 1.0 / (2.0 * p.alpha * p.alpha);
     const double Sd[4] = {p.S_diag[0], p.S_diag[1], p.S_diag[2], p.S_diag[3]};
-    const int nom = p.nominal_offset[0];
-    int buf = 0;
-    for (int64_t k = blockIdx.x; k < a.K; k += gridDim.x, buf ^= 1) {
-        double* stage = stage0 + buf * BLK;
-        // the bulk store issued two knots ago must have finished READING this buffer
-        if (tid == 0) bulk_wait_read<1>();
+    const int nomb = p.nominal_offset[0] >> 2;
+    // the next knot's record travels in registers while this knot is being worked on
+    double nrec[NREC];
+    auto fetch = [&](int64_t k) {
+        if (k < a.K) {
+#pragma unroll
+            for (int q = 0; q < NREC; ++q) nrec[q] = a.rec[k * UR_SIZE + tid + q * UJ_THREADS];
+        }
+    };
+    fetch(blockIdx.x);
+    for (int64_t k = blockIdx.x; k < a.K; k += gridDim.x) {
+#pragma unroll
+        for (int q = 0; q < NREC; ++q) rec[tid + q * UJ_THREADS] = nrec[q];
+        // the bulk store of the previous knot must have finished READING the staging buffer
+        if (tid == 0) bulk_wait_read<0>();
         __syncthreads();
-        for (int i = tid; i < UR_SIZE; i += UJ_THREADS) rec[i] = a.rec[k * UR_SIZE + i];
-        if (tid < N) xs[tid] = a.X[k * N + tid];
-        if (tid == N) xs[N] = a.dt[k];
-        __syncthreads();
-        const double dt = xs[N];
+        fetch(k + gridDim.x);
         if (tid < 40) {
             // seed in sigma point j0, component i0: ds = column i0 of M_j0
             const int j0 = tid >> 2, i0 = tid & 3;
@@ -277,74 +354,30 @@ __global__ void __launch_bounds__(UJ_THREADS) unscented_tangent_kernel(const Uns
 #pragma unroll
                 for (int c = 0; c <= i; ++c) dP[URTRI(i, c)] = cf * fma(mcol[i], dj[c], dj[i] * mcol[c]);
             chunk_tangent_tail(rec, alpha, Sd, dsm, dP, stage + (size_t)(OFF + tid) * N + OFF, 1.0);
-        } else if (tid == 40 || (S25 && tid == 41)) {
-            // dense directions: the amplitude (every propagator moves), and for spin25 the noise amplitude (points 5 and 10 only)
-            const bool namp_dir = tid == 41;
-            double ds[10][4], dsm[4] = {0, 0, 0, 0}, dP[10];
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const bool pn = (j == 4 || j == 9);
-                if (namp_dir && !pn) { ds[j][0] = ds[j][1] = ds[j][2] = ds[j][3] = 0.0; continue; }
-                iso_apply(rec + UR_DE + (j == 4 ? 3 : (j == 9 ? 6 : 0)), xs + OFF + 4 * j, ds[j]);
-                if (namp_dir && j == 9) { ds[j][0] = -ds[j][0]; ds[j][1] = -ds[j][1]; ds[j][2] = -ds[j][2]; ds[j][3] = -ds[j][3]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dsm[i] += ds[j][i];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dsm[i] *= 0.1;
-#pragma unroll
-            for (int i = 0; i < 10; ++i) dP[i] = 0.0;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const double* dj = rec + UR_D + 4 * j;
-                double ddj[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ddj[i] = ds[j][i] - dsm[i];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int c = 0; c <= i; ++c) dP[URTRI(i, c)] = fma(ddj[i], dj[c], fma(dj[i], ddj[c], dP[URTRI(i, c)]));
-            }
-#pragma unroll
-            for (int i = 0; i < 10; ++i) dP[i] *= cf;
-            chunk_tangent_tail(rec, alpha, Sd, dsm, dP, namp_dir ? scratch : stage + (size_t)ACOL * N + OFF, 1.0);
-        } else {
-            // structural entries, dealt over the remaining lanes
-            constexpr int FIRST = S25 ? 42 : 41, NL = UJ_THREADS - FIRST;
-            constexpr int E_END = 16 * NB, A_END = E_END + 4 * NB, C_END = A_END + 6, P_END = C_END + 4, F_END = P_END + (S25 ? 10 : 0);
-            for (int e = tid - FIRST; e < F_END; e += NL) {
-                if (e < E_END) {                                   // blkdiag(E, E[, E])
-                    const int b = e >> 4, r = (e >> 2) & 3, c = e & 3;
-                    stage[(size_t)(4 * b + c) * N + 4 * b + r] = iso_entry(rec + UR_E, r, c);
-                } else if (e < A_END) {                            // (dE/da) psi_b in the amplitude column
-                    const int q = e - E_END, b = q >> 2, r = q & 3;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc = fma(iso_entry(rec + UR_DE, r, c), xs[4 * b + c], acc);
-                    stage[(size_t)ACOL * N + 4 * b + r] = acc;
-                } else if (e < C_END) {                            // [int a, a, da] Euler chain (spin13.jl:49-51) and B = dt e_last
-                    const int q = e - A_END, r = q >> 1;
-                    if (q & 1) stage[(size_t)(CB + r + 1 + (r == 2 ? N - CB - 3 : 0)) * N + CB + r] = dt;   // (cb+r, cb+r+1), last one in column n
-                    else stage[(size_t)(CB + r) * N + CB + r] = 1.0;
-                } else if (e < P_END) {                            // penalty row against the nominal state of the INPUT
-                    const int i = e - C_END;
-                    stage[(size_t)(nom + i) * N + OFF + 40] = -2.0 * Sd[i] * rec[UR_DN + i];
-                } else if (S25) {                                  // pink-filter taps (spin25.jl:194-219)
-                    const int q = e - P_END;
-                    if (q < 6) stage[(size_t)(11 + q) * N + 14] = rec[UR_YK + q];                  // yk row
-                    else {
-                        const int sh[4][2] = {{12, 11}, {13, 12}, {15, 14}, {16, 15}};               // tap shifts (row, column)
-                        stage[(size_t)sh[q - 6][1] * N + sh[q - 6][0]] = 1.0;
-                    }
-                }
-            }
         }
-        if (S25) {
-            __syncthreads();
-            // the six tap columns of the chunk rows: namp * (d yk / d tap) * (d chunk / d noise amplitude)
-            for (int i = tid; i < 6 * 41; i += UJ_THREADS) {
-                const int f = i / 41, r = i - 41 * f;
-                stage[(size_t)(11 + f) * N + OFF + r] = p.namp * rec[UR_YK + f] * scratch[r];
+        // structural entries: values from the record, destinations from the constant table
+        for (int e = tid; e < NST; e += UJ_THREADS) stage[c_stpos[S25 ? 1 : 0][nomb][e]] = rec[UR_ST + e];
+        __syncthreads();
+        if (tid < 41) {
+            // amplitude column of the chunk rows: one row per lane, sum over the 40 sigma-point columns
+            const double* rowp = stage + (size_t)OFF * N + OFF + tid;
+            const double* wv = rec + UR_W;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 40; c += 4) {
+                acc0 = fma(rowp[(size_t)c * N], wv[c], acc0);
+                acc1 = fma(rowp[(size_t)(c + 1) * N], wv[c + 1], acc1);
+                acc2 = fma(rowp[(size_t)(c + 2) * N], wv[c + 2], acc2);
+                acc3 = fma(rowp[(size_t)(c + 3) * N], wv[c + 3], acc3);
+            }
+            stage[(size_t)ACOL * N + OFF + tid] = (acc0 + acc1) + (acc2 + acc3);
+            if (S25) {
+                // noise amplitude: points 5 (+) and 10 (-) only; the six tap columns are namp * (d yk / d tap) times it
+                double an = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) an = fma(rowp[(size_t)(16 + i) * N], wv[16 + i], fma(-rowp[(size_t)(36 + i) * N], wv[36 + i], an));
+#pragma unroll
+                for (int f = 0; f < 6; ++f) stage[(size_t)(11 + f) * N + OFF + tid] = p.namp * rec[UR_YK + f] * an;
             }
         }
         fence_async_smem();
@@ -363,19 +396,28 @@ size_t unscented_record_bytes(int64_t K) { return sizeof(double) * UR_SIZE * (si
 int launch_jacobians_unscented(rbq_handle* h, const rbq_model_params& p, int64_t K, const double* d_X, const double* d_U,
                                const double* d_t, const double* d_dt, double* d_rec, double* d_AB) {
     const int n = model_state_dim(p), m = model_control_dim(p);
+    const bool s25 = p.model_id == RBQ_MODEL_SPIN25;
     UnscentedJacArgs a{p, n, m, K, d_X, d_U, d_t, d_dt, d_rec, d_AB};
-    const unsigned vblocks = (unsigned)((K + 127) / 128);
-    const size_t smem = sizeof(double) * (2 * (size_t)n * (n + m) + UR_SIZE + n + 2 + 41 + 3);
-    const int64_t resident = (int64_t)h->sm_count * (p.model_id == RBQ_MODEL_SPIN25 ? 3 : 4);
+    {   // destinations of the structural entries (they depend on the nominal offset only); 144 bytes, stream ordered
+        unsigned short pos[72] = {0};
+        structural_positions(s25, p.nominal_offset[0], pos);
+        const int nb = p.nominal_offset[0] >> 2;
+        if (nb < 0 || nb > 2 || (p.nominal_offset[0] & 3)) return RBQ_E_MODEL;
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_stpos, pos, sizeof(pos), ((s25 ? 3 : 0) + nb) * sizeof(pos), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const unsigned vblocks = (unsigned)((K + 63) / 64);
+    const size_t smem = sizeof(double) * ((size_t)n * (n + m) + UR_SIZE);
+    const int64_t resident = (int64_t)h->sm_count * (s25 ? 7 : 8);
     const unsigned tblocks = (unsigned)(K < resident ? K : resident);
     cudaError_t e;
-    if (p.model_id == RBQ_MODEL_SPIN30) {
-        unscented_values_kernel<RBQ_MODEL_SPIN30><<<vblocks, 128, 0, h->stream>>>(a);
+    if (!s25) {
+        unscented_values_kernel<RBQ_MODEL_SPIN30><<<vblocks, 64, 0, h->stream>>>(a);
         e = cudaFuncSetAttribute(unscented_tangent_kernel<RBQ_MODEL_SPIN30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         unscented_tangent_kernel<RBQ_MODEL_SPIN30><<<tblocks, UJ_THREADS, smem, h->stream>>>(a);
     } else {
-        unscented_values_kernel<RBQ_MODEL_SPIN25><<<vblocks, 128, 0, h->stream>>>(a);
+        unscented_values_kernel<RBQ_MODEL_SPIN25><<<vblocks, 64, 0, h->stream>>>(a);
         e = cudaFuncSetAttribute(unscented_tangent_kernel<RBQ_MODEL_SPIN25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         unscented_tangent_kernel<RBQ_MODEL_SPIN25><<<tblocks, UJ_THREADS, smem, h->stream>>>(a);

@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(MC_THREADS) lindblad_kernel(const LindbladArgs
 //     r <- E_hi r + (E_lo + d (L1 + d (L2 + d L3))) r          27 + 18 = 45 FP64 instructions
 // instead of the ~105 of the 13-term series.  Rows with flag != 0 (the offset range straddles a kink of the T1 table or of
 // |a|, the curvature terms are not negligible, or ||M dt|| > 1) and realisations with |d| > da_tab take the series step.
-constexpr int LT_ROW = 48;      // doubles per table row: E_hi, E_lo, L1, L2, L3 (9 each, row-major), a_k, flag, pad
+constexpr int LT_ROW = 48;      // doubles per table row: E_hi, E_lo, L1, L2, L3 (9 each, row-major), a_k, flag, kappa
 constexpr int LT_TILE = 32;     // knots per shared-memory tile (12 KB), two tiles in flight
 struct dd { double h, l; };
 RBQ_DEV dd dd_two_sum(double a, double b) { const double s = __dadd_rn(a, b), bb = __dadd_rn(s, -a); return {s, __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb))}; }
@@ -1073,9 +1073,10 @@ __global__ void __launch_bounds__(128) lindblad_table_kernel(const double* __res
         const double Tp = t1_interp<double>(a + da_tab, 1e3), Tm = t1_interp<double>(a - da_tab, 1e3);
         const double lin_p = fma(T.d[0], da_tab, T.v), lin_m = fma(-T.d[0], da_tab, T.v);
         if (fabs(Tp - lin_p) > 1e-9 * T.v || fabs(Tm - lin_m) > 1e-9 * T.v) flag = true;
-        const double x = rho * da_tab;
-        if (x * x * x * x * g1 > 1e-18) flag = true;      // the dropped fourth-order curvature term
     }
+    // the dropped fourth-order curvature term of gamma_1 dt is g1 (rho d)^4: the sweep kernel compares kappa d_max^4, with
+    // d_max the largest offset of the WARP, against 2e-17 (2e-14 after 1000 knots if every knot were at the limit)
+    const double kappa = g1 * (rho * rho) * (rho * rho);
     const double gphi = t2_on ? dt * t2_gamma_c : 0.0;
     const double wz = w2 * fq, wx = w2 * a;
     if (!(w2 * (fabs(fq) + fabs(a) + da_tab) + 2.0 * g1 + gphi <= 1.0)) flag = true;   // the sweep kernel sub-steps such knots
@@ -1139,17 +1140,20 @@ __global__ void __launch_bounds__(128) lindblad_table_kernel(const double* __res
     for (int i = 0; i < 9; ++i) {
         row[i] = A0[i].h; row[9 + i] = A0[i].l; row[18 + i] = A[0][i]; row[27 + i] = A[1][i]; row[36 + i] = A[2][i];
     }
-    row[45] = a; row[46] = flag ? 1.0 : 0.0; row[47] = 0.0;
+    row[45] = a; row[46] = flag ? 1.0 : 0.0; row[47] = kappa;
 }
 
 // series step for one (sub-stepped if needed) knot with the realisation's own amplitude: the fallback of the table kernel
 template <int NV>
 RBQ_DEV void bloch_series_knot(double c1, double fq, double dt, bool t1_on, double gphi_rate, const double* __restrict__ invk,
-                               const unsigned char* __restrict__ cells, double (&r)[NV][3]) {
+                               const double* __restrict__ bmax, const unsigned char* __restrict__ cells, double (&r)[NV][3]) {
     const double b = 2.0 * RBQ_PI * dt * (fabs(fq) + fabs(c1)) + dt * ((t1_on ? 2.0 / 269.03e3 : 0.0) + gphi_rate);
     const int nsub = b == b && b > 1.0 ? (int)fmin(ceil(b), 4096.0) : 1;
-    const int kmax = b == b ? taylor_terms(b / (double)nsub) : 60;
-    const double h = dt / (double)nsub, w2h = 2.0 * RBQ_PI * h;
+    const double bs = nsub == 1 ? b : b / (double)nsub;
+    // series length from the block's table of bounds (bmax[k] = largest b with b^(k+1)/(k+1)! < 1e-18): no divisions here
+    int kmax = 60;
+    if (bs == bs) { kmax = 1; while (kmax < 30 && bs > bmax[kmax]) ++kmax; if (bs > bmax[kmax]) kmax = taylor_terms(bs); }
+    const double h = nsub == 1 ? dt : dt / (double)nsub, w2h = 2.0 * RBQ_PI * h;
     BlochGen m;
     m.wz = w2h * fq; m.wxa = m.wxb = w2h * c1;
     const double g1 = t1_on ? h / t1_ns_fast(c1, cells) : 0.0;
@@ -1167,10 +1171,16 @@ __global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
     __shared__ BlockPartial red_s[16];
     __shared__ double invk_s[64];
+    __shared__ double bmax_s[32];
     __shared__ unsigned char t1cells_s[244];
     const int tid = threadIdx.x, nth = blockDim.x;
     for (int b = tid; b < RBQ_HIST_BINS; b += nth) hist_s[b] = 0;
     if (tid < 64) invk_s[tid] = tid ? 1.0 / (double)tid : 0.0;
+    if (tid < 32) {   // bmax[k]: (1e-18 (k+1)!)^(1/(k+1)), a hair inside
+        double lf = 0.0;
+        for (int i = 2; i <= tid + 1; ++i) lf += log((double)i);
+        bmax_s[tid] = 0.999 * exp((log(1e-18) + lf) / (double)(tid + 1));
+    }
     t1_cells_init(t1cells_s, tid, nth);
     PulsePipeT<LT_TILE, LT_ROW> pipe;
     pipe.init(tile_s, bar_s, table, a.nk);
@@ -1197,6 +1207,15 @@ __global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs
             for (int x = 0; x < 3; ++x) st[i][c][x] = NV == 1 ? r0[i][x] : (c == x ? 1.0 : 0.0);
     }
     const bool warp_table = __all_sync(0xffffffffu, in_range);
+    double dmax4;
+    {
+        double dm = 0.0;
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) dm = fmax(dm, fabs(d[i]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        dmax4 = (dm * dm) * (dm * dm);
+    }
     const int64_t passes = NV == 1 ? a.gate_count : 1;
     for (int64_t g = 0; g < passes; ++g) {
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
@@ -1205,8 +1224,8 @@ __global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs
             for (int j = 0; j < len; ++j) {
                 const double2* __restrict__ row = reinterpret_cast<const double2*>(tile + j * LT_ROW);
                 const double2 af = row[22];                            // (E/L3 tail, a_k) sits in row[22] = doubles 44, 45
-                const double flag = tile[j * LT_ROW + 46];
-                if (warp_table && flag == 0.0) {
+                const double2 fk = row[23];                            // (flag, kappa)
+                if (warp_table && fk.x == 0.0 && fk.y * dmax4 <= 2e-17) {
                     double tb[46];
 #pragma unroll
                     for (int q = 0; q < 23; ++q) { const double2 v = row[q]; tb[2 * q] = v.x; tb[2 * q + 1] = v.y; }
@@ -1227,7 +1246,7 @@ __global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < SPT; ++i) bloch_series_knot<NV>(af.y + d[i], a.fq, a.dt, t1_on, gphi_rate, invk_s, t1cells_s, st[i]);
+                    for (int i = 0; i < SPT; ++i) bloch_series_knot<NV>(af.y + d[i], a.fq, a.dt, t1_on, gphi_rate, invk_s, bmax_s, t1cells_s, st[i]);
                 }
             }
             pipe.release(g + 1 < passes || ti + 1 < pipe.ntiles);

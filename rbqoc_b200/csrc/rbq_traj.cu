@@ -323,7 +323,8 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     // unscented models with one sample state (every run of the reference): the block is assembled from its structure, the value
     // path evaluated once per knot instead of once per seed column (rbq_jac_unscented.cu); RBQ_JAC_STRUCTURED=0 keeps the
     // generic forward-mode kernel below (tests compare the two)
-    if (unscented && p.sample_state_count == 1 && h->opt.jac_structured && (reinterpret_cast<uintptr_t>(d_AB) & 15) == 0) {
+    const bool nom_ok = (p.nominal_offset[0] & 3) == 0 && p.nominal_offset[0] >= 0 && p.nominal_offset[0] <= (fam == RBQ_MODEL_SPIN25 ? 4 : 8);
+    if (unscented && p.sample_state_count == 1 && nom_ok && h->opt.jac_structured && (reinterpret_cast<uintptr_t>(d_AB) & 15) == 0) {
         void* rec = nullptr;
         const int rc = rbq_scratch(h, RBQ_SCR_JACREC, unscented_record_bytes(K), &rec);
         if (rc) return rc;
