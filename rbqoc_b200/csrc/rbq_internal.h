@@ -23,6 +23,7 @@ struct rbq_handle {
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
     // centre (qubit frequency, amplitude offset) the static sweep's knot table is expanded around: rbq_set_sweep_centre
     double centre_fq, centre_da;
+    unsigned stpos_mask;           // which slices of the structured-Jacobian position table this handle has uploaded
     // tuning / A-B switches: read from the environment ONCE in rbq_create (RBQ_* names), changed afterwards only through
     // rbq_set_option; never read from the environment inside a call.  -1 = "library default / heuristic".
     struct {

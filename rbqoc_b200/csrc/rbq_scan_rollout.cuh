@@ -69,24 +69,16 @@ __global__ void __launch_bounds__(SCAN_T) scan_rollout_kernel(const WarpRolloutA
     // 1. control chain: sequential, same multiply-adds as control_chain() of the step kernels
     if (tid == 0) {
         double ci = x0[cb], ca = x0[cb + 1], cd = x0[cb + 2];
-        // eight knots at a time: their dt and u are loaded first, so that the shared-memory latency is paid once per batch and
-        // a knot costs the latency of one multiply-add (the three updates of a knot only need the previous knot's values)
-        constexpr int CHB = 8;
-        for (int64_t k8 = 0; k8 < NS; k8 += CHB) {
-            double dtb[CHB], ub[CHB];
-#pragma unroll
-            for (int j = 0; j < CHB; ++j) { const int64_t k = k8 + j < NS ? k8 + j : NS - 1; dtb[j] = dt_s[k]; ub[j] = u_s[k]; }
-#pragma unroll
-            for (int j = 0; j < CHB; ++j) {
-                const int64_t k = k8 + j;
-                if (k < NS) {
-                    a_s[k] = ca;
-                    const double ni = fma(ca, dtb[j], ci), na = fma(cd, dtb[j], ca), nd = fma(ub[j], dtb[j], cd);
-                    ci = ni; ca = na; cd = nd;
-                    double* Xn = X + (k + 1) * n;
-                    Xn[cb] = ci; Xn[cb + 1] = ca; Xn[cb + 2] = cd;
-                }
-            }
+        // the next knot's dt and u are loaded while this knot's three multiply-adds run (they only need the previous knot's values)
+        double dtn = NS > 0 ? dt_s[0] : 0.0, un = NS > 0 ? u_s[0] : 0.0;
+        for (int64_t k = 0; k < NS; ++k) {
+            const double dt = dtn, u = un;
+            if (k + 1 < NS) { dtn = dt_s[k + 1]; un = u_s[k + 1]; }
+            a_s[k] = ca;
+            const double ni = fma(ca, dt, ci), na = fma(cd, dt, ca), nd = fma(u, dt, cd);
+            ci = ni; ca = na; cd = nd;
+            double* Xn = X + (k + 1) * n;
+            Xn[cb] = ci; Xn[cb + 1] = ca; Xn[cb + 2] = cd;
         }
     }
     __syncthreads();
