@@ -49,10 +49,11 @@ FLOPS_PER_STEP_SU2 = 25.0
 FP64_INSTR_PER_STEP_SU2 = 14.0
 FP64_INSTR3_PER_STEP_SU2 = 11.0   # of those, instructions with three fresh 64-bit register operands (3 issue cycles, not 2)
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
-# FP64 instructions per density-step of the Lindblad table step (lindblad_kernel): 27 DFMA (Horner of the 9
-# entries of E_k + da (L1_k + da (L2_k + da L3_k))) + 3 DMUL + 6 DFMA (apply) = 36 instructions = 69 flop
-LINDBLAD_INSTR_PER_STEP = 36.0
-LINDBLAD_FLOPS_PER_STEP = 69.0
+# FP64 instructions per density-step of the Lindblad table step (lindblad_tab_kernel): 27 DFMA (Horner of the 9
+# entries of E_lo + da (L1 + da (L2 + da L3))) + 3 DMUL + 6 DFMA (the small part applied) + 9 DFMA (E_hi applied) = 45
+# instructions = 87 flop
+LINDBLAD_INSTR_PER_STEP = 45.0
+LINDBLAD_FLOPS_PER_STEP = 87.0
 
 
 def sample_clocks(stop, out):
@@ -314,7 +315,7 @@ def measured_configs(eng, rbq, spin, torch, dev, stream, flush, orc, peaks, fp64
         "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
                      "fp64_instr_per_density_step": LINDBLAD_INSTR_PER_STEP, "flops_per_density_step": LINDBLAD_FLOPS_PER_STEP,
                      "fp64_pipe_issue_util": S * K1 * LINDBLAD_INSTR_PER_STEP / (ms_l * 1e-3) * 2e-12 / fp64_peak if fp64_peak else None,
-                     "how": "table step: 36 FP64 instructions per density-step counted in the SASS of lindblad_kernel (DESIGN.md §4.4)"},
+                     "how": "table step: 45 FP64 instructions (42 DFMA + 3 DMUL = 87 flop) per density-step counted in the SASS of lindblad_tab_kernel (DESIGN.md §4.4); knots next to a kink of the T1 table take the longer series step"},
         "cpu_baseline": {"value": Sc * K1 / (cpu_l * 1e-3), "unit": "density-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{Sc} of the {S} realisations in {cpu_l:.0f} ms (integrate_prop_lindbladt1!: complex 4x4 Pade exp + product per knot)",
                          "one_thread": {"value": 128 * K1 / (cpu_l1 * 1e-3), "cores": 1}},

@@ -67,6 +67,20 @@ extern "C" {
 #define RBQ_ALGO_PADE 1 /* reference algorithm: generic 4x4 Pade-3/5/7/9/13 + LU solve
                            (StaticArrays 0.12.5 `exp`, the call at spin13.jl:46)      */
 
+/* integrator of the augmented state.  EXP: the discrete_dynamics of the model's reference file (matrix exponential + Euler
+ * chain), registered there under the tag RK3 (rbqoc.jl:49-54).  RK2 / RK3 / RK4: RobotDynamics' explicit Runge-Kutta steps
+ * (RobotDynamics 0.2.1, external; rbqoc.jl:41-54 IT_RDI) of the CONTINUOUS dynamics RD.dynamics(model, x, u, t) as the reference's
+ * RK variants define them (spin15_standalone.jl:263-312; derivative states as spin19.jl:66-129 / spin21.jl:63-109):
+ *     psi' = (fq H0 + a H1) psi,  (int a)' = a,  a' = da,  da' = u1,  [decay aware] (int gamma)' = 1 / T1(a) (T1 in ns,
+ *     amp_t1_spline),  [derivative order o] (d^o psi)' = o H_d d^(o-1) psi + (fq H0 + a H1) d^o psi  (H_d = H0: spin11, H1: spin17),
+ *     [time optimal] everything times u2^2 with the solver's dt (spin15_standalone.jl:283-287).
+ * Models: spin13, spin15, spin11, spin17.  Open-loop rollouts, per-knot steps and Jacobians; the closed-loop rollout kernels
+ * implement the exponential step only. */
+#define RBQ_INTEGRATOR_EXP 0
+#define RBQ_INTEGRATOR_RK2 2
+#define RBQ_INTEGRATOR_RK3 3
+#define RBQ_INTEGRATOR_RK4 4
+
 /* Lindblad channels (bit mask) */
 #define RBQ_LINDBLAD_T1 1 /* amplitude damping up+down at gamma_1 = 1/T1(a)  spin.jl:529-531 */
 #define RBQ_LINDBLAD_T2 2 /* pure dephasing Gamma(t) = gamma_c + 2 gamma_f^2 t  spin.jl:542-554 */
@@ -96,7 +110,8 @@ typedef struct rbq_model_params {
     int32_t nominal_offset[RBQ_MAX_SAMPLE_STATES]; /* spin30: 0-based first index of
                                    the nominal state of sample state i
                                    (= nominal_idxs[i][1]-1, spin30.jl:62,168)         */
-    int32_t reserved[2];
+    int32_t integrator;         /* RBQ_INTEGRATOR_*: how x_{k+1} is formed (default 0 = the exponential step of the model file) */
+    int32_t reserved;
     double fq;                  /* GHz                                                */
     double fq_samples[2];       /* spin12: (FQ+fq_cov), (FQ-fq_cov)  spin12.jl:204-205 */
     double namp;                /* spin18                                             */
@@ -342,6 +357,21 @@ int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs,
 int rbq_mc_timeline(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
                     const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
                     const double* noise, int64_t noise_len, const double* psi0, double* fid, rbq_stats* stats);
+/* the same with the iso states themselves at t = 0 and at every save point: states[S*(nsave+1)*4] (or NULL) -- what
+ * run_sim_fine_deqjl (spin.jl:1389-1478) stores as "states" on its save_step grid */
+int rbq_mc_timeline_states(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
+                           const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
+                           const double* noise, int64_t noise_len, const double* psi0, double* fid, double* states, rbq_stats* stats);
+/* run_sim_deqjl / run_sim_fine_deqjl for the density dynamics: dynamics_lindbladnodis_deqjl (channels = 0),
+ * dynamics_lindbladt1_deqjl (RBQ_LINDBLAD_T1) and dynamics_lindbladt2_deqjl (RBQ_LINDBLAD_T2, Gamma(t) = t2_gamma_c +
+ * 2 t2_gamma_f^2 t with t running from the start of the timeline) -- spin.jl:488-518, 542-554 -- over the same kind of
+ * segment timeline (amplitude constant inside a segment).  Exact for the time-independent channels; one fourth-order Magnus
+ * step per segment for the running rate.  rho0[S*8] as in rbq_lindblad; fid[S*(nsave+1)] Uhlmann sqrt-fidelity against the
+ * 4-cyclic targets (or NULL); rho_saves[S*(nsave+1)*8] the densities (column-major vec, (re,im)) at t = 0 and every save point
+ * (or NULL). */
+int rbq_lindblad_timeline(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, const int64_t* save_after,
+                          int64_t nsave, int gate, int64_t S, double fq, const double* da, const double* rho0, int channels,
+                          double t2_gamma_c, double t2_gamma_f, double* fid, double* rho_saves, rbq_stats* stats);
 int rbq_lindblad_segments(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, int gate,
                           int64_t gate_count, int64_t S, double fq, const double* da, const double* rho0, int channels,
                           double t2_gamma_c, double* fid, double* rho_out, rbq_stats* stats);

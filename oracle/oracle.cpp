@@ -466,7 +466,72 @@ template <class T> void step_spin25(const rbq_model_params* p, const T* x, const
         unscented_transform(p, x, 17 + 41 * c, p->nominal_offset[c], E, Ep, En, p->fq_cov, xn);
 }
 
+// ------------------------------------------------------------------------------------------
+// The reference's Runge-Kutta variants: RD.dynamics(model, x, u, t) integrated by RobotDynamics' explicit RK2 / RK3 / RK4
+// (RobotDynamics 0.2.1 @ SchusterLab/rbqoc-stable, Manifest.toml:1283-1289, un-vendored: restated from its published
+// tableaux -- RK2 midpoint; RK3 k3 at x - k1 + 2 k2, weights (1,4,1)/6; classic RK4; IT_RDI at rbqoc.jl:49-54).
+// Continuous dynamics: spin15_standalone.jl:263-312 (nominal + decay aware + time optimal, T1 in ns via amp_t1_spline, the
+// time-optimal form multiplies every component by u2^2); derivative states as spin19.jl:66-129 / spin21.jl:63-109
+// ((d^o psi)' = o H_d d^(o-1) psi + H d^o psi), here with the full generator H = fq H0 + a H1 of the spin13 layout.
+// ------------------------------------------------------------------------------------------
+template <class T> void mul_generator(double fq, const T& a, const T* x, T* y) {
+    for (int i = 0; i < 4; ++i) {
+        T s = T(0.0);
+        for (int k = 0; k < 4; ++k) s = s + (T(fq * (PI * N0[i][k])) + a * (PI * N1[i][k])) * x[k];
+        y[i] = s;
+    }
+}
+template <class T> void continuous_dynamics(const rbq_model_params* p, int n, const T* x, const T* u, T* dx) {
+    const T a = x[9];
+    mul_generator<T>(p->fq, a, x, dx);
+    mul_generator<T>(p->fq, a, x + 4, dx + 4);
+    dx[8] = a; dx[9] = x[10]; dx[10] = u[0];
+    if (p->model_id == RBQ_MODEL_SPIN15) {
+        if (p->decay_aware) dx[11] = 1.0 / amp_t1_spline<T>(a);
+        if (p->time_optimal) { const T s = u[1] * u[1]; for (int i = 0; i < n; ++i) dx[i] = dx[i] * s; }
+    } else if (p->model_id == RBQ_MODEL_SPIN11 || p->model_id == RBQ_MODEL_SPIN17) {
+        const double (*Hd)[4] = p->model_id == RBQ_MODEL_SPIN17 ? N1 : N0;
+        for (int o = 1; o <= p->derivative_order && o <= 2; ++o) {
+            const T* src = o == 1 ? x : x + 11;
+            T* dst = dx + 11 + 4 * (o - 1);
+            mul_generator<T>(p->fq, a, x + 11 + 4 * (o - 1), dst);
+            for (int i = 0; i < 4; ++i) {
+                T g = T(0.0);
+                for (int k = 0; k < 4; ++k) g = g + src[k] * (PI * Hd[i][k]);
+                dst[i] = dst[i] + g * (double)o;
+            }
+        }
+    }
+}
+template <class T> int step_rk(const rbq_model_params* p, const T* x, const T* u, const T& dt, T* xn) {
+    const int n = state_dim(p);
+    if (n < 0 || n > 32) return RBQ_E_MODEL;
+    if (!(p->model_id == RBQ_MODEL_SPIN13 || p->model_id == RBQ_MODEL_SPIN15 || p->model_id == RBQ_MODEL_SPIN11 || p->model_id == RBQ_MODEL_SPIN17)) return RBQ_E_MODEL;
+    std::vector<T> k1(n), k2(n), k3(n), k4(n), xt(n);
+    continuous_dynamics<T>(p, n, x, u, k1.data());
+    if (p->integrator == RBQ_INTEGRATOR_RK2) {
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * dt * 0.5;
+        continuous_dynamics<T>(p, n, xt.data(), u, k2.data());
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + k2[i] * dt;
+    } else if (p->integrator == RBQ_INTEGRATOR_RK3) {
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * dt * 0.5;
+        continuous_dynamics<T>(p, n, xt.data(), u, k2.data());
+        for (int i = 0; i < n; ++i) xt[i] = x[i] - k1[i] * dt + k2[i] * dt * 2.0;
+        continuous_dynamics<T>(p, n, xt.data(), u, k3.data());
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + (k1[i] * dt + k2[i] * dt * 4.0 + k3[i] * dt) / 6.0;
+    } else if (p->integrator == RBQ_INTEGRATOR_RK4) {
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * dt * 0.5;
+        continuous_dynamics<T>(p, n, xt.data(), u, k2.data());
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * dt * 0.5;
+        continuous_dynamics<T>(p, n, xt.data(), u, k3.data());
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * dt;
+        continuous_dynamics<T>(p, n, xt.data(), u, k4.data());
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + (k1[i] * dt + k2[i] * dt * 2.0 + k3[i] * dt * 2.0 + k4[i] * dt) / 6.0;
+    } else return RBQ_E_MODEL;
+    return 0;
+}
 template <class T> int step(const rbq_model_params* p, const T* x, const T* u, double time, const T& dt, T* xn) {
+    if (p->integrator != RBQ_INTEGRATOR_EXP) return step_rk<T>(p, x, u, dt, xn);
     switch (p->model_id) {
     case RBQ_MODEL_SPIN25: step_spin25(p, x, u, time, dt, xn); return 0;
     case RBQ_MODEL_SPIN13: step_spin13(p, x, u, dt, xn); return 0;
@@ -1024,7 +1089,7 @@ int orc_mc_noise_segments(const double* amps, const double* durs, const int32_t*
 // extended-precision state, as in integrate_prop_schroedda!); fidelities at t = 0 and after save_after[g] segments
 int orc_mc_timeline(const double* amps, const double* durs, const int32_t* nidx, int64_t nseg, const int64_t* save_after, int64_t nsave,
                     int gate, int64_t S, const double* fq, const double* da, const double* noise, int64_t noise_len,
-                    const double* psi0, double* fid) {
+                    const double* psi0, double* fid, double* states) {
     cplx g[2][2]; if (!gate_matrix(gate, g)) return RBQ_E_GATE;
     if (noise) for (int64_t j = 0; j < nseg; ++j) if (nidx[j] < 0 || nidx[j] >= noise_len) return RBQ_E_SIZE;
 #pragma omp parallel for schedule(static)
@@ -1033,7 +1098,9 @@ int orc_mc_timeline(const double* amps, const double* durs, const int32_t* nidx,
         for (int i = 0; i < 4; ++i) { s0[i] = psi0[4 * s + i]; st[i] = s0[i]; }
         gate_targets(gate, s0, tg);
         double* f = fid + s * (nsave + 1);
+        double* sr = states ? states + s * (nsave + 1) * 4 : nullptr;      // the states at the save points (run_sim_fine_deqjl)
         f[0] = (double)fidelity_vec_iso2<xreal>(st, tg[0]);
+        if (sr) for (int i = 0; i < 4; ++i) sr[i] = (double)st[i];
         int64_t j = 0;
         for (int64_t q = 1; q <= nsave; ++q) {
             for (; j < save_after[q - 1]; ++j) {
@@ -1046,6 +1113,7 @@ int orc_mc_timeline(const double* amps, const double* durs, const int32_t* nidx,
                 for (int i = 0; i < 4; ++i) st[i] = nx[i];
             }
             f[q] = (double)fidelity_vec_iso2<xreal>(st, tg[q % 4]);
+            if (sr) for (int i = 0; i < 4; ++i) sr[4 * q + i] = (double)st[i];
         }
     }
     return 0;

@@ -35,7 +35,8 @@ class ModelParams(C.Structure):
         ("sample_state_count", C.c_int32),
         ("algo", C.c_int32),
         ("nominal_offset", C.c_int32 * MAX_SAMPLE_STATES),
-        ("reserved", C.c_int32 * 2),
+        ("integrator", C.c_int32),
+        ("reserved", C.c_int32),
         ("fq", C.c_double),
         ("fq_samples", C.c_double * 2),
         ("namp", C.c_double),
@@ -357,7 +358,7 @@ def mc_noise_segments(amps, durs, nidx, gate, gate_count, fq, noise, psi0):
     return fid
 
 
-def mc_timeline(amps, durs, nidx, save_after, gate, fq, da, noise, psi0):
+def mc_timeline(amps, durs, nidx, save_after, gate, fq, da, noise, psi0, want_states=False):
     amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
     save_after = np.ascontiguousarray(save_after, dtype=np.int64)
     da = None if da is None else _f64(da)
@@ -370,11 +371,12 @@ def mc_timeline(amps, durs, nidx, save_after, gate, fq, da, noise, psi0):
         nidx = None
     S, nsave = fq.shape[0], save_after.shape[0]
     fid = np.empty((S, nsave + 1))
+    states = np.empty((S, nsave + 1, 4)) if want_states else None
     rc = lib().orc_mc_timeline(_p(amps), _p(durs), _p(nidx), C.c_int64(amps.shape[0]), _p(save_after), C.c_int64(nsave), int(gate),
-                               C.c_int64(S), _p(fq), _p(da), _p(noise), C.c_int64(nlen), _p(psi0), _p(fid))
+                               C.c_int64(S), _p(fq), _p(da), _p(noise), C.c_int64(nlen), _p(psi0), _p(fid), _p(states))
     if rc:
         raise ValueError(f"orc_mc_timeline rc={rc}")
-    return fid
+    return (fid, states) if want_states else fid
 
 
 def lindblad_segments(amps, durs, gate, gate_count, fq, da, rho0):

@@ -21,6 +21,7 @@ MODEL_SPIN11, MODEL_SPIN12, MODEL_SPIN13, MODEL_SPIN15 = 11, 12, 13, 15
 MODEL_SPIN17, MODEL_SPIN18, MODEL_SPIN25, MODEL_SPIN30 = 17, 18, 25, 30
 ALGO_SU2, ALGO_PADE = 0, 1
 LINDBLAD_T1, LINDBLAD_T2 = 1, 2
+INTEGRATOR_EXP, INTEGRATOR_RK2, INTEGRATOR_RK3, INTEGRATOR_RK4 = 0, 2, 3, 4
 REG_CONTROL, REG_STATE = 0, 1
 CON_BOUND, CON_GOAL, CON_NORM = 0, 1, 2
 E_NULL, E_MODEL, E_SIZE, E_GATE, E_ALGO, E_NODEVICE, E_ALIGN = -1, -2, -3, -4, -5, -6, -7
@@ -37,7 +38,8 @@ class ModelParams(C.Structure):
         ("sample_state_count", C.c_int32),
         ("algo", C.c_int32),
         ("nominal_offset", C.c_int32 * MAX_SAMPLE_STATES),
-        ("reserved", C.c_int32 * 2),
+        ("integrator", C.c_int32),
+        ("reserved", C.c_int32),
         ("fq", C.c_double),
         ("fq_samples", C.c_double * 2),
         ("namp", C.c_double),
@@ -133,6 +135,8 @@ SIGNATURES = {
     "rbq_mc_static_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _P, _P, _P, _P, _SP]),
     "rbq_mc_noise_segments": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _I64, _P, _P, _SP]),
     "rbq_mc_timeline": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, C.c_int, _I64, _P, _P, _P, _I64, _P, _P, _SP]),
+    "rbq_mc_timeline_states": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, C.c_int, _I64, _P, _P, _P, _I64, _P, _P, _P, _SP]),
+    "rbq_lindblad_timeline": (C.c_int, [_P, _P, _P, _I64, _P, _I64, C.c_int, _I64, _D, _P, _P, C.c_int, _D, _D, _P, _P, _SP]),
     "rbq_lindblad_segments": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _D, _P, _P, C.c_int, _D, _P, _P, _SP]),
     "rbq_backward_pass": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),
     "rbq_backward_pass_dev": (C.c_int, [_P, C.c_int, C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _D, C.c_int, _P, _P, _P, _P]),

@@ -997,6 +997,11 @@ int rbq_mc_noise_segments(rbq_handle* h, const double* amps, const double* durs,
 int rbq_mc_timeline(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
                     const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
                     const double* noise, int64_t noise_len, const double* psi0, double* fid, rbq_stats* stats) {
+    return rbq_mc_timeline_states(h, amps, durs, noise_idx, nseg, save_after, nsave, gate, S, fq, da, noise, noise_len, psi0, fid, nullptr, stats);
+}
+int rbq_mc_timeline_states(rbq_handle* h, const double* amps, const double* durs, const int32_t* noise_idx, int64_t nseg,
+                           const int64_t* save_after, int64_t nsave, int gate, int64_t S, const double* fq, const double* da,
+                           const double* noise, int64_t noise_len, const double* psi0, double* fid, double* states, rbq_stats* stats) {
     ENTER(h);
     SegmentArgs a;
     void *dfid = nullptr, *dst = nullptr;
@@ -1031,10 +1036,49 @@ int rbq_mc_timeline(rbq_handle* h, const double* amps, const double* durs, const
         }
         a.fq = (double*)dfq; a.da = da ? (double*)dda : nullptr; a.psi0 = (double*)dpsi;
         a.noise = (double*)dn; a.nidx = (int32_t*)didx; a.noise_len = noise_len;
+        void* dstates = nullptr;
+        if (states) { CKL(dev_buf(h, B_OUT1, sizeof(double) * 4 * S * (nsave + 1), &dstates)); a.states_out = (double*)dstates; }
         int nblocks = 0;
         CKL(launch_timeline(h, a, (const int64_t*)dsave, nsave, &nblocks));
         if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
         if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * (nsave + 1), cudaMemcpyDeviceToHost, h->stream));
+        if (states) CK(cudaMemcpyAsync(states, dstates, sizeof(double) * 4 * S * (nsave + 1), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RBQ_OK;
+}
+int rbq_lindblad_timeline(rbq_handle* h, const double* amps, const double* durs, int64_t nseg, const int64_t* save_after,
+                          int64_t nsave, int gate, int64_t S, double fq, const double* da, const double* rho0, int channels,
+                          double t2_gamma_c, double t2_gamma_f, double* fid, double* rho_saves, rbq_stats* stats) {
+    ENTER(h);
+    if (channels & ~(RBQ_LINDBLAD_T1 | RBQ_LINDBLAD_T2)) return fail(h, RBQ_E_MODEL, "rbq_lindblad_timeline: unknown channel bits %d", channels);
+    SegmentArgs a;
+    void *dfid = nullptr, *dst = nullptr;
+    if (nsave < 0 || !save_after) return fail(h, nsave < 0 ? RBQ_E_SIZE : RBQ_E_NULL, "rbq_lindblad_timeline: save_after/nsave");
+    CKL(segments_common(h, "rbq_lindblad_timeline", amps, durs, nseg, gate, nsave, S, &a, &dfid, &dst, fid, stats, nsave + 1));
+    int64_t prev = 0;
+    for (int64_t g = 0; g < nsave; ++g) {
+        if (save_after[g] < prev || save_after[g] > nseg) return fail(h, RBQ_E_SIZE, "rbq_lindblad_timeline: save_after[%lld]=%lld not ascending within [0,%lld]", (long long)g, (long long)save_after[g], (long long)nseg);
+        prev = save_after[g];
+    }
+    if (S > 0) {
+        if (!rho0) return fail(h, RBQ_E_NULL, "rbq_lindblad_timeline: rho0 is NULL");
+        void *dda, *drho, *dsave, *dsaves = nullptr;
+        CKL(dev_buf(h, B_IN2, sizeof(double) * S, &dda)); CKL(dev_buf(h, B_IN3, sizeof(double) * 8 * S, &drho));
+        CKL(dev_buf(h, B_QUAT, sizeof(int64_t) * (size_t)(nsave > 0 ? nsave : 1), &dsave));
+        if (da) CK(cudaMemcpyAsync(dda, da, sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(drho, rho0, sizeof(double) * 8 * S, cudaMemcpyHostToDevice, h->stream));
+        if (nsave > 0) CK(cudaMemcpyAsync(dsave, save_after, sizeof(int64_t) * nsave, cudaMemcpyHostToDevice, h->stream));
+        if (rho_saves) CKL(dev_buf(h, B_OUT1, sizeof(double) * 8 * S * (nsave + 1), &dsaves));
+        a.fq_scalar = fq; a.da = da ? (double*)dda : nullptr; a.rho0 = (double*)drho; a.rho_saves = (double*)dsaves;
+        a.channels = channels; a.t2_gamma_c = (channels & RBQ_LINDBLAD_T2) ? t2_gamma_c : 0.0;
+        a.t2_gamma_f = (channels & RBQ_LINDBLAD_T2) ? t2_gamma_f : 0.0;
+        int nblocks = 0;
+        CKL(launch_timeline(h, a, (const int64_t*)dsave, nsave, &nblocks));
+        if (stats) CKL(launch_stats_finalize(h, a.partials, nblocks, (rbq_stats*)dst));
+        if (fid) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * (nsave + 1), cudaMemcpyDeviceToHost, h->stream));
+        if (rho_saves) CK(cudaMemcpyAsync(rho_saves, dsaves, sizeof(double) * 8 * S * (nsave + 1), cudaMemcpyDeviceToHost, h->stream));
     }
     if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -102,7 +102,9 @@ struct SegmentArgs {
     int64_t gate_count, S;
     const double* fq; double fq_scalar; const double* da; const double* psi0; const double* rho0;
     const double* noise; const int32_t* nidx; int64_t noise_len;   // optional: amplitude += noise[s][nidx[j]]
-    int channels; double t2_gamma_c;
+    int channels; double t2_gamma_c, t2_gamma_f;
+    double* states_out;          // timeline: iso states at every save point, S x (nsave+1) x 4, or NULL
+    double* rho_saves;           // density timeline: vec(rho) at every save point, S x (nsave+1) x 8, or NULL
     double* fid; double* rho_out; BlockPartial* partials; unsigned long long* hist;
     GateIso gate; GateRot rot;
 };

@@ -1435,8 +1435,10 @@ __global__ void __launch_bounds__(MC_THREADS) mc_timeline_kernel(const SegmentAr
 #pragma unroll
     for (int k = 0; k < 3; ++k) mv4_to(a.gate.g[k], psi0, tg[k + 1]);
     double* frow = (a.fid && live) ? a.fid + s * (nsave + 1) : nullptr;
+    double* srow = (a.states_out && live) ? a.states_out + s * (nsave + 1) * 4 : nullptr;     // run_sim_fine_deqjl's "states"
     double f = fidelity_vec_iso2(st, tg[0]);
     if (frow) frow[0] = f;
+    if (srow) { srow[0] = st[0]; srow[1] = st[1]; srow[2] = st[2]; srow[3] = st[3]; }
     const double norm0 = fma(st[3], st[3], fma(st[2], st[2], fma(st[1], st[1], st[0] * st[0])));
     int64_t j = 0;
     for (int64_t g = 1; g <= nsave; ++g) {
@@ -1455,6 +1457,81 @@ __global__ void __launch_bounds__(MC_THREADS) mc_timeline_kernel(const SegmentAr
         const int k = (int)(g & 3);
         f = fidelity_vec_iso2(st, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
         if (frow) frow[g] = f;
+        if (srow) { srow[4 * g] = st[0]; srow[4 * g + 1] = st[1]; srow[4 * g + 2] = st[2]; srow[4 * g + 3] = st[3]; }
+    }
+    if (a.partials) {
+        ThreadStats ts;
+        if (live) ts.add(1.0 - f, hist_s);
+        __syncthreads();
+        block_stats_flush(ts, hist_s, red_s, a.partials, a.hist);
+    }
+}
+// The density-matrix counterpart: the exact solution of the ODEs dynamics_lindbladnodis_deqjl / lindbladt1_deqjl / lindbladt2_deqjl
+// (spin.jl:488-518, 542-554) that run_sim_deqjl / run_sim_fine_deqjl (spin.jl:1277-1478) hand to Vern9, over a segment timeline
+// with save points.  Bloch picture; one Magnus step per (sub-)segment, exact for the time-independent channels and of fourth
+// order in the segment length for the running dephasing rate (see BlochGen).  channels = 0: no dissipation.
+__global__ void __launch_bounds__(MC_THREADS) lindblad_timeline_kernel(const SegmentArgs a, const int64_t* __restrict__ save_after, int64_t nsave) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[MC_THREADS / 32];
+    __shared__ double invk_s[64];
+    __shared__ unsigned char t1cells_s[244];
+    for (int b = threadIdx.x; b < RBQ_HIST_BINS; b += MC_THREADS) hist_s[b] = 0;
+    if (threadIdx.x < 64) invk_s[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    t1_cells_init(t1cells_s, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;
+    const double da = a.da ? a.da[sc] : 0.0;
+    const bool t1_on = (a.channels & RBQ_LINDBLAD_T1) != 0, t2_on = (a.channels & RBQ_LINDBLAD_T2) != 0;
+    const double gf2 = t2_on ? a.t2_gamma_f * a.t2_gamma_f : 0.0;
+    const double* q = a.rho0 + 8 * sc;
+    const double tr0 = q[0] + q[6];
+    double r0[3] = {q[2] + q[4], q[3] - q[5], q[0] - q[6]}, tg[4][3];
+    double rr[1][3] = {{r0[0], r0[1], r0[2]}};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tg[0][i] = r0[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mv3_to(a.rot.r[k], r0, tg[k + 1]);
+    double* frow = (a.fid && live) ? a.fid + s * (nsave + 1) : nullptr;
+    double* drow = (a.rho_saves && live) ? a.rho_saves + s * (nsave + 1) * 8 : nullptr;
+    auto record = [&](int64_t g) {
+        const int k = (int)(g & 3);
+        const double f = fidelity_bloch(tr0, rr[0], tr0, k == 0 ? tg[0] : (k == 1 ? tg[1] : (k == 2 ? tg[2] : tg[3])));
+        if (frow) frow[g] = f;
+        if (drow) {
+            double* o = drow + 8 * g;
+            o[0] = 0.5 * (tr0 + rr[0][2]); o[1] = 0.0;
+            o[2] = 0.5 * rr[0][0];         o[3] = 0.5 * rr[0][1];
+            o[4] = 0.5 * rr[0][0];         o[5] = -0.5 * rr[0][1];
+            o[6] = 0.5 * (tr0 - rr[0][2]); o[7] = 0.0;
+        }
+        return f;
+    };
+    double f = record(0);
+    double t0 = 0.0;
+    int64_t j = 0;
+    for (int64_t g = 1; g <= nsave; ++g) {
+        const int64_t end = save_after[g - 1];
+        for (; j < end; ++j) {
+            const double dt = a.durs[j], c1 = a.amps[j] + da;
+            const double gmax = (t1_on ? 2.0 / 269.03e3 : 0.0) + (t2_on ? a.t2_gamma_c + 2.0 * gf2 * (t0 + dt) : 0.0);
+            const double bnd = 2.0 * RBQ_PI * dt * (fabs(a.fq_scalar) + fabs(c1)) + dt * gmax;
+            const int sub = bnd == bnd && bnd > 1.0 ? (int)fmin(ceil(bnd), 4096.0) : 1;
+            const double h = dt / (double)sub, w2h = 2.0 * RBQ_PI * h;
+            const int kmax = bnd == bnd ? taylor_terms(bnd / (double)sub) : 60;
+            const double wx = w2h * c1, g1 = t1_on ? h / t1_ns_fast(c1, t1cells_s) : 0.0;
+            const double e = gf2 * h * h * wx * (1.0 / 6.0);          // Magnus commutator term of the running rate
+            for (int r = 0; r < sub; ++r) {
+                BlochGen m;
+                m.wz = w2h * a.fq_scalar; m.wxa = wx - e; m.wxb = wx + e;
+                const double gphi = t2_on ? h * (a.t2_gamma_c + 2.0 * gf2 * (t0 + ((double)r + 0.5) * h)) : 0.0;
+                m.g2 = g1 + gphi; m.g1 = 2.0 * g1;
+                bloch_advance<1>(m, kmax, invk_s, rr);
+            }
+            t0 += dt;
+        }
+        f = record(g);
     }
     if (a.partials) {
         ThreadStats ts;
@@ -1692,7 +1769,8 @@ int launch_segments(rbq_handle* h, const SegmentArgs& a, bool lindblad, int* nbl
 int launch_timeline(rbq_handle* h, const SegmentArgs& a, const int64_t* d_save_after, int64_t nsave, int* nblocks_out) {
     const int blocks = (int)((a.S + MC_THREADS - 1) / MC_THREADS);
     if (nblocks_out) *nblocks_out = blocks;
-    mc_timeline_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_save_after, nsave);
+    if (a.rho0) lindblad_timeline_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_save_after, nsave);
+    else mc_timeline_kernel<<<blocks, MC_THREADS, 0, h->stream>>>(a, d_save_after, nsave);
     h->launches++;
     return (int)cudaGetLastError();
 }

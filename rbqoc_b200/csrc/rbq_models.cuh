@@ -34,6 +34,11 @@ __host__ __device__ inline int model_state_dim(const rbq_model_params& p) {
 }
 __host__ __device__ inline int model_control_dim(const rbq_model_params& p) {
     if (model_state_dim(p) < 0) return RBQ_E_MODEL;
+    if (p.integrator != RBQ_INTEGRATOR_EXP) {   // RK steps exist for the models with a continuous RD.dynamics in the reference
+        const bool known = p.integrator == RBQ_INTEGRATOR_RK2 || p.integrator == RBQ_INTEGRATOR_RK3 || p.integrator == RBQ_INTEGRATOR_RK4;
+        const bool fam = p.model_id == RBQ_MODEL_SPIN13 || p.model_id == RBQ_MODEL_SPIN15 || p.model_id == RBQ_MODEL_SPIN11 || p.model_id == RBQ_MODEL_SPIN17;
+        if (!known || !fam) return RBQ_E_MODEL;
+    }
     if (p.model_id == RBQ_MODEL_SPIN15) return 1 + (p.time_optimal ? 1 : 0);
     return 1;
 }
@@ -271,9 +276,83 @@ template <class T, class IO> RBQ_DEV void step_spin25(const rbq_model_params& p,
     for (int c = 0; c < p.sample_state_count; ++c) unscented_chunk<T>(p, io, 17 + 41 * c, p.nominal_offset[c], E, Ep, En);
 }
 
+// ---- explicit Runge-Kutta steps of the continuous dynamics (RBQ_INTEGRATOR_RK2/3/4, see include/rbq.h) ---------------------------
+// RD.dynamics of the reference's RK variants (spin15_standalone.jl:263-312, spin19.jl:66-129, spin21.jl:63-109) on the layout of
+// spin13 / spin15 / spin11 / spin17: psi1 0..3, psi2 4..7, [int a, a, da] 8..10, then int gamma (spin15 decay aware) or the
+// derivative states of psi1 (4 per order).
+constexpr int RK_MAX_N = 19;
+template <class T> RBQ_DEV void apply_H(double wf, const T& wa, const T* x, T* y) {
+    // (fq H0 + a H1) x with the pi folded into wf = pi fq, wa = pi a: rows of prop_apply without the cosine term
+    y[0] = tfma(wa, x[3], x[2] * wf);
+    y[1] = tfma(wa, x[2], x[3] * (-wf));
+    y[2] = tfma(-wa, x[1], x[0] * (-wf));
+    y[3] = tfma(-wa, x[0], x[1] * wf);
+}
+template <class T> RBQ_DEV void continuous_dynamics(const rbq_model_params& p, int n, const T* x, const T* u, T* dx) {
+    const T a = x[9];
+    const double wf = RBQ_PI * p.fq;
+    const T wa = a * RBQ_PI;
+    apply_H<T>(wf, wa, x, dx);
+    apply_H<T>(wf, wa, x + 4, dx + 4);
+    dx[8] = a; dx[9] = x[10]; dx[10] = u[0];
+    if (p.model_id == RBQ_MODEL_SPIN15) {
+        if (p.decay_aware) dx[11] = 1.0 / t1_interp<T>(a, 1e3);      // amp_t1_spline: ns (spin15_standalone.jl:272, 300)
+        if (p.time_optimal) {
+            const T s = u[1] * u[1];
+            for (int i = 0; i < n; ++i) dx[i] = dx[i] * s;
+        }
+    } else if (p.model_id == RBQ_MODEL_SPIN11 || p.model_id == RBQ_MODEL_SPIN17) {
+        const bool h1 = p.model_id == RBQ_MODEL_SPIN17;
+        for (int o = 1; o <= p.derivative_order && o <= 2; ++o) {
+            const T* src = o == 1 ? x : x + 11;
+            T* dst = dx + 11 + 4 * (o - 1);
+            T g[4];
+            if (h1) apply_N1<T>(src[0], src[1], src[2], src[3], g[0], g[1], g[2], g[3]);
+            else apply_N0<T>(src[0], src[1], src[2], src[3], g[0], g[1], g[2], g[3]);
+            apply_H<T>(wf, wa, x + 11 + 4 * (o - 1), dst);
+            const double f = RBQ_PI * (double)o;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = dst[i] + g[i] * f;
+        }
+    }
+}
+template <class T, class IO> RBQ_DEV void step_rk(const rbq_model_params& p, IO& io, int n, int m, double dt) {
+    T x[RK_MAX_N], u[2], k1[RK_MAX_N], k2[RK_MAX_N], k3[RK_MAX_N], xt[RK_MAX_N];
+    for (int i = 0; i < n; ++i) x[i] = io.x(i);
+    for (int j = 0; j < m; ++j) u[j] = io.u(j);
+    continuous_dynamics<T>(p, n, x, u, k1);
+    if (p.integrator == RBQ_INTEGRATOR_RK2) {            // midpoint
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * (0.5 * dt);
+        continuous_dynamics<T>(p, n, xt, u, k2);
+        for (int i = 0; i < n; ++i) io.out(i, x[i] + k2[i] * dt);
+    } else if (p.integrator == RBQ_INTEGRATOR_RK3) {     // k3 at x - k1 + 2 k2, weights (1, 4, 1) / 6
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * (0.5 * dt);
+        continuous_dynamics<T>(p, n, xt, u, k2);
+        for (int i = 0; i < n; ++i) xt[i] = x[i] - k1[i] * dt + k2[i] * (2.0 * dt);
+        continuous_dynamics<T>(p, n, xt, u, k3);
+        for (int i = 0; i < n; ++i) io.out(i, x[i] + (k1[i] + k2[i] * 4.0 + k3[i]) * (dt / 6.0));
+    } else {                                             // classic RK4
+        T k4[RK_MAX_N];
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * (0.5 * dt);
+        continuous_dynamics<T>(p, n, xt, u, k2);
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * (0.5 * dt);
+        continuous_dynamics<T>(p, n, xt, u, k3);
+        for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * dt;
+        continuous_dynamics<T>(p, n, xt, u, k4);
+        for (int i = 0; i < n; ++i) io.out(i, x[i] + (k1[i] + k2[i] * 2.0 + k3[i] * 2.0 + k4[i]) * (dt / 6.0));
+    }
+}
+__host__ __device__ inline bool model_supports_rk(const rbq_model_params& p) {
+    return p.model_id == RBQ_MODEL_SPIN13 || p.model_id == RBQ_MODEL_SPIN15 || p.model_id == RBQ_MODEL_SPIN11 || p.model_id == RBQ_MODEL_SPIN17;
+}
+
 // MODEL is the reference file number (RBQ_MODEL_*); one kernel instantiation per model family.
 // `time` is used by spin25 only (every other reference model ignores its time argument).
 template <int MODEL, class T, class IO> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double time, double dt) {
+    if ((MODEL == RBQ_MODEL_SPIN13 || MODEL == RBQ_MODEL_SPIN15 || MODEL == RBQ_MODEL_SPIN11) && p.integrator != RBQ_INTEGRATOR_EXP) {
+        step_rk<T>(p, io, model_state_dim(p), model_control_dim(p), dt);
+        return;
+    }
     if (MODEL == RBQ_MODEL_SPIN13) step_spin13<T>(p, io, dt);
     else if (MODEL == RBQ_MODEL_SPIN12) step_spin12_18<T>(p, io, dt);   // also spin18
     else if (MODEL == RBQ_MODEL_SPIN15) step_spin15<T>(p, io, dt);

@@ -4,13 +4,12 @@
 // In an open-loop rollout the control chain [int a, a, da] is driven by u alone (spin13.jl:49-51), so every knot's propagator
 // E_k = exp(dt_k (f H0 + a_k H1)) is known before any state is: psi_k = (E_{k-1} ... E_0) psi_0.  The E_k are iso images of
 // SU(2) elements, closed under multiplication and determined by their first column (a quaternion), so the whole trajectory is
-//   1. the control chain, sequentially on one thread (three multiply-adds per knot, the same operations in the same order as the
-//      step-by-step kernels: the amplitudes are bit-identical to theirs),
+//   1. the control chain as three block-wide prefix sums (da from u, a from da, the integral from a),
 //   2. all propagators in parallel (one knot-segment per thread),
 //   3. an inclusive scan of quaternion products over the block (warp shuffles, then the 32 warp totals),
 //   4. psi_k = Q_k psi_0 for every block of the state, written knot by knot.
 // The warp-per-trajectory kernel walks the knots one after the other (0.19 us per knot: 190 us for 1001 knots); this one
-// takes the time of step 1 plus a few microseconds.  Product order differs from the sequential chain by rounding only
+// takes a few microseconds beyond its launch.  Product order differs from the sequential chain by rounding only
 // (~1e-16 per level of the tree); closed-loop rollouts cannot use it (the feedback K dx couples psi into a).
 #pragma once
 #include "rbq_warp_rollout.cuh"
@@ -66,20 +65,53 @@ __global__ void __launch_bounds__(SCAN_T) scan_rollout_kernel(const WarpRolloutA
     }
     for (int i = tid; i < n; i += SCAN_T) X[i] = x0[i];
     __syncthreads();
-    // 1. control chain: sequential, same multiply-adds as control_chain() of the step kernels
-    if (tid == 0) {
-        double ci = x0[cb], ca = x0[cb + 1], cd = x0[cb + 2];
-        // the next knot's dt and u are loaded while this knot's three multiply-adds run (they only need the previous knot's values)
-        double dtn = NS > 0 ? dt_s[0] : 0.0, un = NS > 0 ? u_s[0] : 0.0;
-        for (int64_t k = 0; k < NS; ++k) {
-            const double dt = dtn, u = un;
-            if (k + 1 < NS) { dtn = dt_s[k + 1]; un = u_s[k + 1]; }
-            a_s[k] = ca;
-            const double ni = fma(ca, dt, ci), na = fma(cd, dt, ca), nd = fma(u, dt, cd);
-            ci = ni; ca = na; cd = nd;
-            double* Xn = X + (k + 1) * n;
-            Xn[cb] = ci; Xn[cb + 1] = ca; Xn[cb + 2] = cd;
+    // 1. control chain [int a, a, da] (spin13.jl:49-51): three first-order recurrences v_{k+1} = fma(src_k, dt_k, v_k), each a
+    //    block-wide prefix sum (a thread walks its own knots with the same multiply-adds the step kernels use; only the value
+    //    it starts from is summed in tree order, so the chain differs from a sequential walk by ~1e-16 relative).  da first
+    //    (driven by u), then a (driven by da), then the integral (driven by a).
+    {
+        const int64_t c0 = (int64_t)tid * per, c1 = c0 + per < NS ? c0 + per : NS;
+        auto exclusive = [&](double v) {          // exclusive prefix sum of v over the block's threads
+            double inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) gsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                double w = lane < SCAN_T / 32 ? gsum[lane] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(FULL, w, o); if (lane >= o) w += t; }
+                gsum[lane] = w;
+            }
+            __syncthreads();
+            double ex = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) ex = 0.0;
+            if (warp > 0) ex += gsum[warp - 1];
+            __syncthreads();                      // gsum is reused by the next scan
+            return ex;
+        };
+        // da: u_s[k] is replaced by da_{k+1}
+        double tot = 0.0;
+        for (int64_t k = c0; k < c1; ++k) tot = fma(u_s[k], dt_s[k], tot);
+        double v = x0[cb + 2] + exclusive(tot);
+        double da_first = v;                      // da at this thread's first knot
+        for (int64_t k = c0; k < c1; ++k) { v = fma(u_s[k], dt_s[k], v); u_s[k] = v; X[(k + 1) * n + cb + 2] = v; }
+        // a: a_s[k] = amplitude at knot k (k = 0..NS), driven by da_k = (k ? u_s[k-1] : da_0)
+        tot = 0.0;
+        {
+            double dk = da_first;
+            for (int64_t k = c0; k < c1; ++k) { tot = fma(dk, dt_s[k], tot); dk = u_s[k]; }
         }
+        v = x0[cb + 1] + exclusive(tot);
+        {
+            double dk = da_first;
+            for (int64_t k = c0; k < c1; ++k) { a_s[k] = v; v = fma(dk, dt_s[k], v); dk = u_s[k]; X[(k + 1) * n + cb + 1] = v; }
+        }
+        // integral of a
+        tot = 0.0;
+        for (int64_t k = c0; k < c1; ++k) tot = fma(a_s[k], dt_s[k], tot);
+        v = x0[cb] + exclusive(tot);
+        for (int64_t k = c0; k < c1; ++k) { v = fma(a_s[k], dt_s[k], v); X[(k + 1) * n + cb] = v; }
     }
     __syncthreads();
     // chain c: generator f_c H0 + (a + da_c) H1

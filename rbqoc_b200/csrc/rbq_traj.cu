@@ -244,7 +244,10 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
     const int fam0 = family(p.model_id);
-    const bool independent_blocks = fam0 == RBQ_MODEL_SPIN13 || fam0 == RBQ_MODEL_SPIN15 || fam0 == RBQ_MODEL_SPIN12;
+    // the block-parallel / warp / scan kernels implement the exponential step; Runge-Kutta steps go through model_step (one thread
+    // per trajectory)
+    const bool rk = p.integrator != RBQ_INTEGRATOR_EXP;
+    const bool independent_blocks = !rk && (fam0 == RBQ_MODEL_SPIN13 || fam0 == RBQ_MODEL_SPIN15 || fam0 == RBQ_MODEL_SPIN12);
     // measured (tools/proto/rollout_batch.py, 1001 knots): spin13 4096 / 32768 trajectories 0.33 / 2.3 ms packed against
     // 0.60 / 4.2 ms one warp each; spin12 0.50 against 0.55 ms at 4096 but 6.6 against 3.9 ms at 32768 (43 doubles per
     // knot leave as scattered 32-byte stores), so the 10-block models switch back above 8192
@@ -278,7 +281,7 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
         if (fam0 == RBQ_MODEL_SPIN13) packed_rollout_kernel<RBQ_MODEL_SPIN13><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
         else if (fam0 == RBQ_MODEL_SPIN15) packed_rollout_kernel<RBQ_MODEL_SPIN15><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
         else packed_rollout_kernel<RBQ_MODEL_SPIN12><<<blocks, pt, 0, h->stream>>>(a, nb, pt);
-    } else if (B <= WARP_ROLLOUT_MAX) {
+    } else if (B <= WARP_ROLLOUT_MAX && !rk) {
         WarpRolloutArgs a{p, n, m, N, B, t0, d_x0, d_U, nullptr, nullptr, d_dt, nullptr, d_X, nullptr};
 #define CALL(M) { cudaError_t e_ = launch_warp_rollout<M, false>(a, (unsigned)B, 0, h->stream); if (e_ != cudaSuccess) return (int)e_; }
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
@@ -299,6 +302,7 @@ int launch_closedloop(rbq_handle* h, const rbq_model_params& p, int64_t N, const
                       double* d_X, double* d_Uout) {
     const int n = model_state_dim(p), m = model_control_dim(p);
     if (n < 0 || m < 0) return RBQ_E_MODEL;
+    if (p.integrator != RBQ_INTEGRATOR_EXP) return RBQ_E_MODEL;     // closed-loop kernels: exponential step only (include/rbq.h)
     // one step-size candidate per warp, one warp per block so that candidates spread over SMs
     WarpRolloutArgs a{p, n, m, N, nalpha, 0.0, d_Xref, d_Uref, d_K, d_d, d_dt, d_alphas, d_X, d_Uout};
     const size_t smem = closedloop_smem_bytes(n, m);

@@ -350,9 +350,10 @@ class Engine:
                                                  C.byref(st)), "rbq_mc_noise_segments")
         return fid, st
 
-    def mc_timeline(self, amps, durs, save_after, gate, fq, psi0, da=None, noise=None, noise_idx=None):
+    def mc_timeline(self, amps, durs, save_after, gate, fq, psi0, da=None, noise=None, noise_idx=None, want_states=False):
         """run_sim_deqjl's piecewise-constant ODE solved exactly (spin.jl:424-467, 1277-1380): segments (amps, durs[, noise_idx]),
-        fidelities at t = 0 and after save_after[g] segments -> (S, nsave + 1)."""
+        fidelities at t = 0 and after save_after[g] segments -> (S, nsave + 1).  want_states: also the iso states at those
+        times, (S, nsave + 1, 4) (run_sim_fine_deqjl's "states"), returned as a third value."""
         amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
         save_after = np.ascontiguousarray(save_after, dtype=np.int64)
         da = None if da is None else _f64(da)
@@ -367,11 +368,33 @@ class Engine:
                 raise ValueError("noise (S, noise_len) with one noise_idx per segment")
             nlen = noise.shape[1]
         fid = np.empty((S, nsave + 1))
+        states = np.empty((S, nsave + 1, 4)) if want_states else None
         st = Stats()
-        self._ck(self._lib.rbq_mc_timeline(self._h, _ptr(amps), _ptr(durs), _ptr(nidx), amps.shape[0], _ptr(save_after), nsave,
-                                           int(gate), S, _ptr(fq), _ptr(da), _ptr(noise), nlen, _ptr(psi0), _ptr(fid), C.byref(st)),
-                 "rbq_mc_timeline")
-        return fid, st
+        self._ck(self._lib.rbq_mc_timeline_states(self._h, _ptr(amps), _ptr(durs), _ptr(nidx), amps.shape[0], _ptr(save_after), nsave,
+                                                  int(gate), S, _ptr(fq), _ptr(da), _ptr(noise), nlen, _ptr(psi0), _ptr(fid),
+                                                  _ptr(states), C.byref(st)), "rbq_mc_timeline_states")
+        return (fid, st, states) if want_states else (fid, st)
+
+    def lindblad_timeline(self, amps, durs, save_after, gate, fq, rho0, da=None, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0,
+                          t2_gamma_f=0.0):
+        """The density ODEs of run_sim_deqjl / run_sim_fine_deqjl (spin.jl:488-518, 542-554) over a segment timeline.
+        rho0 (S,2,2) complex -> fid (S, nsave+1), rho (S, nsave+1, 2, 2), stats."""
+        amps, durs = _f64(amps), _f64(durs)
+        save_after = np.ascontiguousarray(save_after, dtype=np.int64)
+        nsave = save_after.shape[0]
+        rho0 = np.ascontiguousarray(rho0, dtype=np.complex128)
+        S = rho0.shape[0]
+        vec = np.ascontiguousarray(rho0.transpose(0, 2, 1).reshape(S, 4))
+        da = None if da is None else _f64(da)
+        if amps.shape != durs.shape or (da is not None and da.shape != (S,)):
+            raise ValueError("amps/durs one entry per segment, da (S,)")
+        fid = np.empty((S, nsave + 1))
+        out = np.empty((S, nsave + 1, 4), dtype=np.complex128)
+        st = Stats()
+        self._ck(self._lib.rbq_lindblad_timeline(self._h, _ptr(amps), _ptr(durs), amps.shape[0], _ptr(save_after), nsave, int(gate), S,
+                                                 float(fq), _ptr(da), _ptr(vec), int(channels), float(t2_gamma_c), float(t2_gamma_f),
+                                                 _ptr(fid), _ptr(out), C.byref(st)), "rbq_lindblad_timeline")
+        return fid, out.reshape(S, nsave + 1, 2, 2).transpose(0, 1, 3, 2).copy(), st
 
     def lindblad_segments(self, amps, durs, gate, gate_count, fq, da, rho0, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0):
         amps, durs = _f64(amps), _f64(durs)

@@ -50,6 +50,7 @@ class GateType(enum.IntEnum):     # spin.jl:29-34
 
 class DynamicsType(enum.IntEnum):  # spin.jl:36-58 (same integer values): the members run_sim_prop integrates (DT_INT, spin.jl:986-996)
     schroed = 1
+    lindbladnodis = 2
     lindbladt1 = 3
     ypiby2nodis = 4
     ypiby2t1 = 5
@@ -64,6 +65,38 @@ class DynamicsType(enum.IntEnum):  # spin.jl:36-58 (same integer values): the me
 
 class RK3:                        # integrator tag the reference always dispatches on (rbqoc.jl:49-54)
     pass
+
+
+class RK2:                        # RobotDynamics' other tags (IT_RDI, rbqoc.jl:49-54)
+    pass
+
+
+class RK4:
+    pass
+
+
+class IntegratorType(enum.IntEnum):   # rbqoc.jl:41-46
+    rk2 = 1
+    rk3 = 2
+    rk4 = 3
+
+
+_INTEGRATOR_ID = {None: _lib.INTEGRATOR_EXP, IntegratorType.rk2: _lib.INTEGRATOR_RK2, IntegratorType.rk3: _lib.INTEGRATOR_RK3,
+                  IntegratorType.rk4: _lib.INTEGRATOR_RK4}
+
+
+def with_integrator(model: "Model", integrator) -> "Model":
+    """The model with its CONTINUOUS dynamics (RD.dynamics of the reference's RK variants, spin15_standalone.jl:263-312,
+    spin19.jl:66-129, spin21.jl:63-109) stepped by RobotDynamics' explicit RK2 / RK3 / RK4 (`integrator_type` of those files'
+    run_traj) instead of the file's own exponential discrete_dynamics.  integrator None restores the exponential step.
+    spin13 / spin15 / spin11 / spin17 only."""
+    import copy
+
+    m = copy.deepcopy(model)
+    m.params.integrator = _INTEGRATOR_ID[None if integrator is None else IntegratorType(integrator)]
+    if control_dim(m) < 0:
+        raise ValueError("this model has no Runge-Kutta variant")
+    return m
 
 
 # real isomorphism helpers (rbqoc.jl:189-210)
@@ -489,18 +522,21 @@ def run_sim_prop(gate_count, gate_type, controls, dt_inv, fq=FQ, da=None, namp=N
     }
 
 
-def deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv=None):
+def deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv=None, save_times=None):
     """Segment list of the ODE run_sim_deqjl integrates (spin.jl:424-467, 1277-1380).  Its right-hand side reads
     controls[floor(t controls_dt_inv) mod control_knot_count] (the pulse repeats with period knot_count / dt_inv, which is NOT
     the gate time when gate_time * dt_inv is not an integer -- the reference's own wrap-around, kept) and, for schroedda,
-    noise_offsets[floor(t noise_dt_inv)]; states are saved at multiples of gate_time.  Between the breakpoints of those three
-    grids the right-hand side is constant.  Returns (amps, durs, noise_idx or None, save_after)."""
+    noise_offsets[floor(t noise_dt_inv)]; states are saved at multiples of gate_time (or at `save_times`, as
+    run_sim_fine_deqjl's save_step grid).  Between the breakpoints of those three grids the right-hand side is constant.
+    Returns (amps, durs, noise_idx or None, save_after)."""
     controls = np.asarray(controls, dtype=np.float64).reshape(-1)
     count = int(math.floor(gate_time * controls_dt_inv))                  # control_knot_count, spin.jl:1299
     if count < 1 or count > controls.shape[0]:
         raise ValueError("gate_time * controls_dt_inv must select between 1 and len(controls) knots")
     t_end = gate_time * gate_count
-    saves = gate_time * np.arange(1, gate_count + 1)
+    saves = gate_time * np.arange(1, gate_count + 1) if save_times is None else np.asarray(save_times, dtype=np.float64)
+    if saves.size and (np.any(np.diff(saves) <= 0) or saves[0] <= 0 or saves[-1] > t_end * (1 + 1e-15)):
+        raise ValueError("save times must be increasing inside (0, evolution time]")
     pts = [np.arange(0, int(math.floor(t_end * controls_dt_inv)) + 1) / controls_dt_inv, saves]
     if noise_dt_inv:
         pts.append(np.arange(0, int(math.floor(t_end * noise_dt_inv)) + 1) / noise_dt_inv)
@@ -519,35 +555,89 @@ def deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_in
     return amps, durs, nidx, np.minimum(save_after, durs.shape[0]).astype(np.int64)
 
 
-def run_sim_deqjl(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq=FQ, da=None, namp=NAMP_PREFACTOR,
-                  noise_dt_inv=DT_NOISE_INV, seed=0, state_seed=None, dynamics_type=DynamicsType.schroed, noise=None,
-                  engine: Engine | None = None):
-    """run_sim_deqjl (spin.jl:1277-1380) for dynamics_type schroed / schroedda, batched over seeds.  The reference lets Vern9
-    integrate a piecewise-constant right-hand side to reltol = abstol = 1e-12; this evaluates the exact solution of the same ODE
-    (the ordered product of segment exponentials, `deqjl_timeline`), so the two agree to the solver's tolerance.  `gate_time`
-    replaces the evolution time grab_controls reads from the pulse file."""
+def gen_rand_density_iso(seed=0, engine: Engine | None = None):
+    """spin.jl:1141-1158 as the complex 2x2 density (the reference stores its 4x4 real iso image): seed 0 is the fixed state
+    (|0> + |1>)/sqrt(2), any other seed a random pure state (Philox here, see gen_rand_state_iso)."""
+    if seed == 0:
+        psi = np.array([_R2, _R2], dtype=np.complex128)
+    else:
+        psi = get_vec_uniso(gen_rand_state_iso(seed, engine))
+    return np.outer(psi, psi.conj())
+
+
+_DENSITY_CHANNELS = {DynamicsType.lindbladnodis: 0, DynamicsType.lindbladt1: _lib.LINDBLAD_T1, DynamicsType.lindbladt2: _lib.LINDBLAD_T2}
+
+
+def _deqjl_run(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq, da, namp, noise_dt_inv, seed, state_seed,
+               dynamics_type, noise, engine, save_times, want_states, t2_gamma_c, t2_gamma_f):
     eng = engine or default_engine()
     gate_type = GateType(gate_type)
     dynamics_type = DynamicsType(dynamics_type)
-    if dynamics_type not in (DynamicsType.schroed, DynamicsType.schroedda):
-        raise ValueError("run_sim_deqjl mirrors the Schroedinger dynamics (schroed, schroedda)")
-    scalar = np.isscalar(seed)
     seeds = np.atleast_1d(np.asarray(seed, dtype=np.int64))
     sseeds = seeds if state_seed is None else np.broadcast_to(np.atleast_1d(np.asarray(state_seed, dtype=np.int64)), seeds.shape)
     S = seeds.shape[0]
     fqs = np.broadcast_to(np.asarray(fq, dtype=np.float64), (S,)).copy()
     das = None if da is None else np.broadcast_to(np.asarray(da, dtype=np.float64), (S,)).copy()
-    psi0 = np.stack([gen_rand_state_iso(int(s), eng) for s in sseeds])
     noisy = dynamics_type == DynamicsType.schroedda
-    amps, durs, nidx, save_after = deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv if noisy else None)
+    amps, durs, nidx, save_after = deqjl_timeline(controls, controls_dt_inv, gate_time, gate_count, noise_dt_inv if noisy else None,
+                                                  save_times)
+    if dynamics_type in _DENSITY_CHANNELS:
+        if not np.all(fqs == fqs[0]):
+            raise ValueError("the density dynamics use one fq (FQ_NEGI_H0_ISO, spin.jl:495-512)")
+        rho0 = np.stack([gen_rand_density_iso(int(s), eng) for s in sseeds])
+        ch = _DENSITY_CHANNELS[dynamics_type]
+        t2 = ch == _lib.LINDBLAD_T2
+        fid, rho, st = eng.lindblad_timeline(amps, durs, save_after, gate_type, float(fqs[0]), rho0, da=das, channels=ch,
+                                             t2_gamma_c=t2_gamma_c if t2 else 0.0, t2_gamma_f=t2_gamma_f if t2 else 0.0)
+        return fid, st, rho
+    if dynamics_type not in (DynamicsType.schroed, DynamicsType.schroedda):
+        raise ValueError("run_sim_deqjl mirrors schroed, schroedda, lindbladnodis, lindbladt1 and lindbladt2")
+    psi0 = np.stack([gen_rand_state_iso(int(s), eng) for s in sseeds])
     if noisy and noise is None:
         nlen = int(math.ceil(gate_time * gate_count * noise_dt_inv)) + 1                  # spin.jl:1305
         noise = np.concatenate([eng.pink_noise(int(s), 1, 0, namp, noise_dt_inv, nlen) for s in seeds])
-    fid, st = eng.mc_timeline(amps, durs, save_after, gate_type, fqs, psi0, da=das, noise=noise if noisy else None,
-                              noise_idx=nidx if noisy else None)
-    return {"gate_count": gate_count, "gate_type": int(gate_type), "gate_time": gate_time, "seed": seed,
-            "fidelities": fid[0] if scalar else fid, "stats": st, "dt": 1.0 / controls_dt_inv, "namp": namp,
-            "noise_dt_inv": noise_dt_inv}
+    out = eng.mc_timeline(amps, durs, save_after, gate_type, fqs, psi0, da=das, noise=noise if noisy else None,
+                          noise_idx=nidx if noisy else None, want_states=want_states)
+    return (out[0], out[1], out[2]) if want_states else (out[0], out[1], None)
+
+
+def run_sim_deqjl(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq=FQ, da=None, namp=NAMP_PREFACTOR,
+                  noise_dt_inv=DT_NOISE_INV, seed=0, state_seed=None, dynamics_type=DynamicsType.schroed, noise=None,
+                  engine: Engine | None = None, t2_gamma_c=GAMMAC, t2_gamma_f=GAMMAF_PREFACTOR):
+    """run_sim_deqjl (spin.jl:1277-1380), batched over seeds, for dynamics_type schroed / schroedda (iso states) and
+    lindbladnodis / lindbladt1 / lindbladt2 (densities, gen_rand_density_iso: seed 0 is the fixed |+> state).  The reference
+    lets Vern9 integrate a right-hand side that is piecewise constant in the controls to reltol = abstol = 1e-12; this evaluates
+    the exact solution of the same ODE (the ordered product of segment exponentials, `deqjl_timeline`; the running dephasing
+    rate of lindbladt2 by a fourth-order Magnus step per segment), so the two agree to the solver's tolerance.  `gate_time`
+    replaces the evolution time grab_controls reads from the pulse file.  Density runs also return "densities"."""
+    scalar = np.isscalar(seed)
+    fid, st, extra = _deqjl_run(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq, da, namp, noise_dt_inv, seed,
+                                state_seed, dynamics_type, noise, engine, None, False, t2_gamma_c, t2_gamma_f)
+    res = {"gate_count": gate_count, "gate_type": int(GateType(gate_type)), "gate_time": gate_time, "seed": seed,
+           "fidelities": fid[0] if scalar else fid, "stats": st, "dt": 1.0 / controls_dt_inv, "namp": namp,
+           "noise_dt_inv": noise_dt_inv, "dynamics_type": int(DynamicsType(dynamics_type))}
+    if extra is not None:
+        res["densities"] = extra[0] if scalar else extra
+    return res
+
+
+def run_sim_fine_deqjl(controls, controls_dt_inv, gate_time, gate_count=1, gate_type=GateType.xpiby2, save_step=1e-1, fq=FQ,
+                       da=None, namp=NAMP_PREFACTOR, noise_dt_inv=DT_NOISE_INV, seed=0, dynamics_type=DynamicsType.schroed,
+                       noise=None, engine: Engine | None = None, t2_gamma_c=GAMMAC, t2_gamma_f=GAMMAF_PREFACTOR):
+    """run_sim_fine_deqjl (spin.jl:1389-1478; the Fig. 4b / 3d driver, figures.jl:638-646, 760-764): the states themselves on
+    the save_step grid, t = 0, save_step, 2 save_step, ... <= gate_time * gate_count.  Returns {"states": (n_save, 4) iso states
+    or (n_save, 2, 2) complex densities (the reference stores their 4x4 iso image: get_mat_iso), "save_times", ...}; batched
+    over seeds like run_sim_deqjl (leading axis S for array seeds)."""
+    scalar = np.isscalar(seed)
+    t_end = gate_time * gate_count
+    count = int(math.floor(t_end / save_step * (1 + 1e-15)))
+    save_times = save_step * np.arange(1, count + 1)
+    save_times = save_times[save_times <= t_end * (1 + 1e-15)]
+    fid, st, states = _deqjl_run(gate_count, gate_type, controls, controls_dt_inv, gate_time, fq, da, namp, noise_dt_inv, seed, None,
+                                 dynamics_type, noise, engine, save_times, True, t2_gamma_c, t2_gamma_f)
+    return {"gate_count": gate_count, "gate_time": gate_time, "seed": seed, "states": states[0] if scalar else states,
+            "save_times": np.concatenate([[0.0], save_times]), "dt": 1.0 / controls_dt_inv, "namp": namp,
+            "noise_dt_inv": noise_dt_inv, "dynamics_type": int(DynamicsType(dynamics_type))}
 
 
 def evaluate_fqdev(controls, dt_inv, fq_cov=FQ * 1e-2, trial_count=1000, gate_type=GateType.zpiby2,

@@ -540,3 +540,37 @@ def test_density_ode_oracle_matches_50_digit_golden(orc):
         _, rho = orc.lindblad_knots(z["controls"], float(z["dt"]), int(z["gate"]), G, float(z["fq"]), z["da"], z["rho0"], channels=ch,
                                     gamma_c=float(z["gamma_c"]), gamma_f=float(z["gf_" + name]))
         assert np.max(np.abs(rho - z["rho_" + name][:, G])) < 1e-15, name
+
+
+def test_runge_kutta_steps_converge_at_their_order(orc):
+    """The RK restatement (RobotDynamics tableaux over the continuous dynamics of spin15_standalone.jl:263-312) against an
+    independent fine-grid solution of the same ODE (constant u, so the amplitude is the exact quadratic a(t); the iso states by
+    exponential midpoint steps 400x finer): the error falls at the tableau's order -- the tableaux are the right ones, the
+    continuous dynamics the right vector field."""
+    from rbqoc_b200 import spin
+
+    base = spin.Spin13Model()
+    x0 = spin.spin13_x0(); x0[8:11] = [0.0, 0.2, 0.05]
+    T, u = 2.0, 0.01
+    H0, H1 = np.pi * np.array(orc_N0()), np.pi * np.array(orc_N1())
+    nf = 16000
+    hf = T / nf
+    psi = np.stack([x0[0:4], x0[4:8]], axis=1)
+    for j in range(nf):
+        tm = (j + 0.5) * hf
+        a = x0[9] + x0[10] * tm + 0.5 * u * tm * tm
+        psi = scipy.linalg.expm(hf * (FQ * H0 + a * H1)) @ psi
+    ref = np.concatenate([psi[:, 0], psi[:, 1]])
+    errs = {}
+    for integ, order in ((spin.IntegratorType.rk2, 2), (spin.IntegratorType.rk3, 3), (spin.IntegratorType.rk4, 4)):
+        e = []
+        for N in (21, 41):
+            dt = T / (N - 1)
+            X = orc.rollout(spin.with_integrator(base, integ).params, x0, np.full((N - 1, 1), u), np.full(N - 1, dt))
+            e.append(np.max(np.abs(X[-1, :8] - ref)))
+            # the control chain is a polynomial of degree <= 2 in t: RK3 and RK4 integrate it exactly
+            if order >= 3:
+                assert abs(X[-1, 9] - (x0[9] + x0[10] * T + 0.5 * u * T * T)) < 1e-14
+        errs[order] = e
+        assert np.log2(e[0] / e[1]) > order - 0.4, (order, e)
+    assert errs[4][1] < errs[3][1] < errs[2][1]

@@ -731,3 +731,52 @@ def test_lindblad_table_path_full_size_balanced_grid(engine, oracle):
     pick = np.concatenate([np.arange(0, 64), np.arange(S - 64, S), rng.integers(0, S, 128)])
     _, _, rrho = oracle.lindblad_t1(controls, dt, rbq.GATE_XPIBY2, 1, spin.FQ, da[pick], rho0[pick])
     assert np.max(np.abs(rho[pick] - rrho)) < 5e-12
+
+
+# ---- run_sim_deqjl for the density dynamics and run_sim_fine_deqjl (spin.jl:488-518, 542-554, 1277-1478) -----------------------
+@pytest.mark.parametrize("dyn,ch", [(spin.DynamicsType.lindbladnodis, 0), (spin.DynamicsType.lindbladt1, 1), (spin.DynamicsType.lindbladt2, 2)],
+                         ids=["lindbladnodis", "lindbladt1", "lindbladt2"])
+def test_run_sim_deqjl_density_dynamics_match_the_ode_oracle(engine, oracle, dyn, ch):
+    """gate_time is not a whole number of control knots, so the reference's `mod control_knot_count` wrap-around and the cuts at
+    the save times are both exercised; seed 0 is the reference's fixed |+> density."""
+    controls, cdi, gate_time, gates = spin.pulse_sin(241)[:-1], 10.0, 23.87, 3
+    seeds = np.array([0, 1, 2, 7])
+    res = spin.run_sim_deqjl(gates, spin.GateType.ypiby2, controls, cdi, gate_time, seed=seeds, dynamics_type=dyn, engine=engine)
+    amps, durs, _, save_after = spin.deqjl_timeline(controls, cdi, gate_time, gates)
+    rho0 = np.stack([spin.gen_rand_density_iso(int(s), engine) for s in seeds])
+    t2 = ch == 2
+    rfid, rrho = oracle.lindblad_ode(amps, durs, save_after, rbq.GATE_YPIBY2, spin.FQ, None, rho0, channels=ch,
+                                     gamma_c=spin.GAMMAC if t2 else 0.0, gamma_f=spin.GAMMAF_PREFACTOR if t2 else 0.0)
+    assert np.allclose(rho0[0], 0.5 * np.ones((2, 2)))
+    assert np.max(np.abs(res["densities"] - rrho)) < 5e-12
+    assert np.max(np.abs(res["fidelities"] - rfid)) < 1e-8       # pure targets: sqrt(eps) conditioning of the sqrt-fidelity
+    if ch == 0:     # no dissipation: purity is conserved
+        pur = np.einsum("sgij,sgji->sg", res["densities"], res["densities"]).real
+        assert np.max(np.abs(pur - 1.0)) < 1e-12
+
+
+def test_run_sim_fine_deqjl_states_on_the_save_step_grid(engine, oracle):
+    """run_sim_fine_deqjl (Fig. 4b driver): iso states / densities every save_step along the pulse, against the oracle's
+    segment walk (states) and exact ODE solution (densities)."""
+    controls, cdi, gate_time = spin.controls_ypiby2(100.0), 100.0, spin.TTOT_YPIBY2_JL
+    seeds = np.array([1, 2, 3])
+    for dyn in (spin.DynamicsType.schroed, spin.DynamicsType.schroedda):
+        out = spin.run_sim_fine_deqjl(controls, cdi, gate_time, gate_count=1, seed=seeds, dynamics_type=dyn, save_step=0.1, engine=engine)
+        nsave = out["save_times"].shape[0] - 1
+        assert nsave == int(np.floor(gate_time / 0.1)) and out["states"].shape == (3, nsave + 1, 4)
+        noisy = dyn == spin.DynamicsType.schroedda
+        amps, durs, nidx, save_after = spin.deqjl_timeline(controls, cdi, gate_time, 1, 10.0 if noisy else None, out["save_times"][1:])
+        psi0 = np.stack([spin.gen_rand_state_iso(int(s), engine) for s in seeds])
+        noise = None
+        if noisy:
+            nlen = int(np.ceil(gate_time * 10.0)) + 1
+            noise = np.concatenate([oracle.pink_noise(int(s), 1, 0, spin.NAMP_PREFACTOR, 10.0, nlen) for s in seeds])
+        _, rstates = oracle.mc_timeline(amps, durs, nidx, save_after, rbq.GATE_XPIBY2, np.full(3, spin.FQ), None, noise, psi0, want_states=True)
+        assert np.max(np.abs(out["states"] - rstates)) < 2e-12, dyn
+        assert np.max(np.abs(np.linalg.norm(out["states"], axis=2) - 1.0)) < 1e-13
+    out = spin.run_sim_fine_deqjl(controls, cdi, gate_time, gate_count=2, seed=seeds, dynamics_type=spin.DynamicsType.lindbladt1, save_step=0.5,
+                                  engine=engine)
+    amps, durs, _, save_after = spin.deqjl_timeline(controls, cdi, gate_time, 2, None, out["save_times"][1:])
+    rho0 = np.stack([spin.gen_rand_density_iso(int(s), engine) for s in seeds])
+    _, rrho = oracle.lindblad_ode(amps, durs, save_after, rbq.GATE_XPIBY2, spin.FQ, None, rho0, channels=1)
+    assert out["states"].shape == rrho.shape and np.max(np.abs(out["states"] - rrho)) < 5e-12

@@ -457,8 +457,8 @@ def test_structured_unscented_jacobians_unaligned_output_falls_back(engine, orac
 @pytest.mark.parametrize("N", [2, 66, 1001, 5681])
 def test_scan_rollout_equals_stepwise_rollout_and_oracle(engine, oracle, name, model, N):
     """Open-loop rollouts of one (or a few) trajectories run as a prefix product of quaternions over the knots
-    (rbq_scan_rollout.cuh); the step-by-step kernels and the oracle walk the knots.  Same control chain bit for bit (it is
-    still evaluated sequentially), states equal to product-order rounding."""
+    (rbq_scan_rollout.cuh), the control chain as three prefix sums; the step-by-step kernels and the oracle walk the knots.
+    Equal to summation / product-order rounding."""
     rng = np.random.default_rng(_seed(name, 5) + N)
     n, m = model.n, model.m
     B = 3
@@ -474,7 +474,49 @@ def test_scan_rollout_equals_stepwise_rollout_and_oracle(engine, oracle, name, m
     engine.set_option("RBQ_ROLLOUT_PACKED", "0")
     Xw = engine.rollout(model.params, x0, U, dt)
     cb = slice(8, 11)
-    assert np.array_equal(Xs[:, :, cb], Xw[:, :, cb]), name           # the control chain is the same sequence of operations
+    assert _relerr(Xs[:, :, cb], Xw[:, :, cb]) < 1e-14, name          # the control chain: prefix sums against the sequential walk
     assert _relerr(Xs, Xw) < 1e-13 + 2e-16 * N, name
     Xr = oracle.rollout(model.params, x0, U, dt)
     assert _relerr(Xs, Xr) < 1e-12, name
+
+
+# ---- Runge-Kutta steps of the continuous dynamics (RBQ_INTEGRATOR_RK2/3/4; spin15_standalone.jl:263-312, rbqoc.jl:41-54) -------
+RK_MODELS = [mm for mm in MODELS if mm[1].params.model_id in (13, 15, 11, 17)]
+
+
+@pytest.mark.parametrize("name,model", RK_MODELS, ids=lambda v: v if isinstance(v, str) else "")
+@pytest.mark.parametrize("integ", [spin.IntegratorType.rk2, spin.IntegratorType.rk3, spin.IntegratorType.rk4], ids=["rk2", "rk3", "rk4"])
+def test_runge_kutta_steps_jacobians_and_rollouts_match_oracle(engine, oracle, name, model, integ):
+    mrk = spin.with_integrator(model, integ)
+    rng = np.random.default_rng(_seed(name, 300 + int(integ)))
+    n, m = mrk.n, mrk.m
+    for dt in (0.1, 0.01):
+        x, u = _random_point(mrk, rng)
+        xn = engine.discrete_dynamics(mrk.params, x, u, 0.0, dt)
+        assert _relerr(xn, oracle.step(mrk.params, x, u, dt)) < 1e-13, (name, dt)
+        J = engine.discrete_jacobian(mrk.params, x, u, 0.0, dt)
+        Jr = oracle.jacobian(mrk.params, x, u, dt)
+        assert np.max(np.abs(J - Jr)) / np.max(np.abs(Jr)) < JAC_RTOL, (name, dt)
+    B, N = 3, 40
+    x0 = np.stack([_random_point(mrk, rng)[0] for _ in range(B)])
+    U = rng.uniform(-2e-2, 2e-2, (B, N - 1, m))
+    if mrk.params.model_id == 15 and mrk.params.time_optimal:
+        U[:, :, 1] = rng.uniform(0.8, 1.2, (B, N - 1))
+    dtv = np.full(N - 1, 0.05)
+    X = engine.rollout(mrk.params, x0, U, dtv)
+    assert _relerr(X, oracle.rollout(mrk.params, x0, U, dtv)) < 1e-12, name
+    K = 70
+    Xk = np.stack([_random_point(mrk, rng)[0] for _ in range(K)]); Uk = np.stack([_random_point(mrk, rng)[1] for _ in range(K)])
+    AB = engine.jacobians(mrk.params, Xk, Uk, np.full(K, 0.1))
+    ABr = oracle.jacobians(mrk.params, Xk, Uk, np.full(K, 0.1))
+    assert np.max(np.abs(AB - ABr)) / np.max(np.abs(ABr)) < JAC_RTOL, name
+
+
+def test_runge_kutta_is_refused_where_it_does_not_exist(engine):
+    with pytest.raises(ValueError):
+        spin.with_integrator(spin.Spin30Model(), spin.IntegratorType.rk4)
+    mrk = spin.with_integrator(spin.Spin13Model(), spin.IntegratorType.rk3)
+    N = 5
+    X = np.tile(spin.spin13_x0(), (N, 1)); U = np.zeros((N - 1, 1))
+    with pytest.raises(rbq.RbqError):       # the closed-loop kernels implement the exponential step only
+        engine.rollout_closedloop(mrk.params, X, U, np.zeros((N - 1, 1, 11)), np.zeros((N - 1, 1)), np.full(N - 1, 0.1), np.array([1.0]))
