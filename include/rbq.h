@@ -282,6 +282,22 @@ int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, 
                          int64_t gate_count, int64_t first, int64_t S, uint64_t seed, double fq0,
                          double fq_rel_sigma, double fq_rel_clip, double da_sigma, int algo,
                          double* fid, rbq_stats* stats);
+/* ---- single-process multi-device sweeps ("rbq_create(device_ids[], n) with the communicator inside the handle").
+ * A group owns one handle per listed CUDA device (a device may be listed more than once).  A group sweep shards the global
+ * sample range [first, first+S) contiguously over the members, launches every member's share before waiting for any (one host
+ * thread drives all GPUs), and merges the members' statistics in member order on the host -- the same numbers any sharding
+ * gives, because the samples are keyed by their global index.  No device-to-device traffic: the only exchange is the 2.1 KB
+ * rbq_stats per member.  (One process per GPU + NCCL, rbqoc_b200/dist.py, is the other supported shape.) */
+typedef struct rbq_group rbq_group;
+int rbq_group_create(const int* devices, int n, rbq_group** out);
+int rbq_group_destroy(rbq_group* g);
+int rbq_group_size(const rbq_group* g);
+rbq_handle* rbq_group_handle(rbq_group* g, int member);
+const char* rbq_group_last_error(const rbq_group* g);
+/* rbq_mc_static_philox over the group; fid[S*(gate_count+1)] (host, or NULL) is filled in global sample order */
+int rbq_group_mc_static_philox(rbq_group* g, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                               int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                               double da_sigma, int algo, double* fid, rbq_stats* stats);
 int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0,
                        double fq_rel_sigma, double fq_rel_clip, double da_sigma, double* fq,
                        double* da, double* psi0);

@@ -33,7 +33,8 @@ struct ModelParams                      # rbq_model_params (128 bytes)
     sample_state_count::Int32
     algo::Int32
     nominal_offset::NTuple{4,Int32}
-    reserved::NTuple{2,Int32}
+    integrator::Int32                   # 0 = the model file's exponential step; 2 / 3 / 4 = RobotDynamics RK2 / RK3 / RK4 of RD.dynamics
+    reserved::Int32
     fq::Float64
     fq_samples::NTuple{2,Float64}
     namp::Float64
@@ -54,8 +55,8 @@ end
 
 const FQ = 1.4e-2
 _params(id; DO=0, DA=false, TO=false, ssc=1, nominal=(0, 0, 0, 0), fq=FQ, fq_samples=(0.0, 0.0), namp=0.0,
-        fq_cov=0.0, alpha=1.0, S=(1.0, 1.0, 1.0, 1.0)) =
-    ModelParams(id, DO, DA, TO, ssc, 0, Int32.(nominal), (Int32(0), Int32(0)), fq, fq_samples, namp, fq_cov, alpha, S)
+        fq_cov=0.0, alpha=1.0, S=(1.0, 1.0, 1.0, 1.0), integrator=0) =
+    ModelParams(id, DO, DA, TO, ssc, 0, Int32.(nominal), Int32(integrator), Int32(0), fq, fq_samples, namp, fq_cov, alpha, S)
 
 params_spin13() = _params(13)
 params_spin12(fq_cov=FQ * 1e-2) = _params(12; fq_samples=(FQ + fq_cov, FQ - fq_cov))            # spin12.jl:204-205
@@ -341,28 +342,149 @@ host_unregister(A::Array) = check(ccall((:rbq_host_unregister, LIB), Cint, (Ptr{
 set_sweep_centre(fq0::Real, da0::Real=0.0) =
     check(ccall((:rbq_set_sweep_centre, LIB), Cint, (Ptr{Cvoid}, Float64, Float64), handle().ptr, fq0, da0), "rbq_set_sweep_centre")
 
+"Batched run_sim_prop(...; seed, state_seed) with the samples drawn on the device (Philox keyed by the global sample index): seeds in, fidelities / statistics out."
+function mc_static_philox(controls::Vector{Float64}, dt::Real, gate::Integer, gate_count::Integer, first::Integer, S::Integer,
+                          seed::Integer; fq0::Real=FQ, fq_rel_sigma::Real=0.01, fq_rel_clip::Real=0.03, da_sigma::Real=2.574e-5,
+                          algo::Integer=0, want_fid::Bool=true)
+    fid = want_fid ? Matrix{Float64}(undef, gate_count + 1, S) : nothing
+    st = Ref{Stats}()
+    fp = want_fid ? pointer(fid) : Ptr{Float64}(C_NULL)
+    GC.@preserve controls fid check(ccall((:rbq_mc_static_philox, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Cint, Int64, Int64, Int64, UInt64, Float64, Float64, Float64, Float64, Cint,
+         Ptr{Float64}, Ptr{Stats}),
+        handle().ptr, controls, length(controls), dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma, algo,
+        fp, st), "rbq_mc_static_philox")
+    return fid, st[]
+end
+
+"run_sim_deqjl / run_sim_fine_deqjl for the density dynamics (lindbladnodis: channels 0, lindbladt1: 1, lindbladt2: 2) over a segment timeline."
+function lindblad_timeline(amps::Vector{Float64}, durs::Vector{Float64}, save_after::Vector{Int64}, gate::Integer, fq::Real,
+                           da::Union{Nothing,Vector{Float64}}, rho0::Array{ComplexF64,3}; channels::Integer=1,
+                           t2_gamma_c::Real=0.0, t2_gamma_f::Real=0.0)
+    S, nsave = size(rho0, 3), length(save_after)
+    fid = Matrix{Float64}(undef, nsave + 1, S)
+    rho = Array{ComplexF64,4}(undef, 2, 2, nsave + 1, S)
+    st = Ref{Stats}()
+    dap = da === nothing ? Ptr{Float64}(C_NULL) : pointer(da)
+    GC.@preserve amps durs save_after da rho0 fid rho check(ccall((:rbq_lindblad_timeline, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Int64, Cint, Int64, Float64, Ptr{Float64}, Ptr{ComplexF64}, Cint,
+         Float64, Float64, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Stats}),
+        handle().ptr, amps, durs, length(amps), save_after, nsave, gate, S, fq, dap, rho0, channels, t2_gamma_c, t2_gamma_f, fid, rho, st),
+        "rbq_lindblad_timeline")
+    return fid, rho, st[]
+end
+
+"One tuning / A-B switch of the handle (same names and values as the RBQ_* environment variables latched at creation)."
+set_option(name::AbstractString, value::Union{Nothing,AbstractString}=nothing) =
+    check(ccall((:rbq_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring), handle().ptr, name, value === nothing ? C_NULL : value),
+          "rbq_set_option")
+
+# ---- trajectory-level specialisations: what makes the drop-in FASTER, not just equal -------------------------------------
+# A per-knot ccall costs 20-30 us (two synchronous PCIe round trips) -- more than the CPU step it replaces -- so the per-knot
+# methods below exist for API completeness; the solver's two hot loops are intercepted whole:
+#   TO.dynamics_expansion!(RK3, D, model, Z)   all N-1 Jacobians in ONE rbq_jacobians call           (Altro: every iLQR iteration, PN)
+#   RD.rollout!(RK3, model, Z, x0)             the open-loop rollout in ONE rbq_rollout call        (Altro: initial rollout)
+# The closed-loop forward pass (Altro `rollout!(solver, alpha)`) stays on the per-knot path unless the caller batches its
+# line search through `rollout_closedloop` (include/rbq.h).
+# [from memory -- RobotDynamics 0.2.1 / TrajectoryOptimization 0.3.2 @ SchusterLab/rbqoc-stable are not vendored]: a KnotPoint
+# has fields z (the concatenated [x; u] StaticVector), _x, _u (index ranges), dt, t; a DynamicsExpansion has the n x (n+m) matrix
+# field ∇f and views A_, B_ of it plus tmpA, tmpB.  julia/selfcheck.jl asserts these names before anything else runs.
+const KNOT_FIELDS = (:z, :_x, :_u, :dt, :t)
+const EXPANSION_FIELDS = (:∇f, :A_, :B_, :tmpA, :tmpB)
+
+mutable struct TrajBuffers              # page-locked is not needed here: plain Julia arrays, reused across iterations
+    n::Int; m::Int; N::Int
+    X::Matrix{Float64}; U::Matrix{Float64}; dts::Vector{Float64}; ts::Vector{Float64}; AB::Array{Float64,3}
+end
+const BUFFERS = Dict{Tuple{Int,Int,Int},TrajBuffers}()
+function buffers(n, m, N)
+    get!(BUFFERS, (n, m, N)) do
+        TrajBuffers(n, m, N, zeros(n, N), zeros(m, N - 1), zeros(N - 1), zeros(N - 1), zeros(n, n + m, N - 1))
+    end
+end
+
+"Gather a TO.Traj (vector of KnotPoints) into the engine's knot-major arrays."
+function gather!(b::TrajBuffers, Z)
+    for k = 1:b.N
+        zk = Z[k]
+        b.X[:, k] .= RD.state(zk)
+        if k < b.N
+            b.U[:, k] .= RD.control(zk)
+            b.dts[k] = zk.dt
+            b.ts[k] = zk.t
+        end
+    end
+    return b
+end
+
+"All knot-point Jacobians of a trajectory in one engine call, scattered into the solver's DynamicsExpansion objects."
+function dynamics_expansion!(D::AbstractVector, p::ModelParams, Z)
+    N = length(Z)
+    n, m = state_dim(p), control_dim(p)
+    b = gather!(buffers(n, m, N), Z)
+    jacobians!(b.AB, p, b.X, b.U, b.dts, b.ts)
+    for k in eachindex(D)
+        D[k].∇f .= view(b.AB, :, :, k)
+        D[k].tmpA .= D[k].A_      # what TO.dynamics_expansion! does after every discrete_jacobian! (error-state expansion)
+        D[k].tmpB .= D[k].B_
+    end
+    return nothing
+end
+
+"Open-loop rollout of a trajectory in one engine call: Z[k+1].x = discrete_dynamics(RK3, model, Z[k])."
+function rollout_traj!(p::ModelParams, Z, x0)
+    N = length(Z)
+    n, m = state_dim(p), control_dim(p)
+    b = gather!(buffers(n, m, N), Z)
+    rollout!(b.X, p, x0, b.U, b.dts)
+    for k = 1:N
+        RD.set_state!(Z[k], SVector{n}(view(b.X, :, k)))
+    end
+    return nothing
+end
+
 # ---- the macro a reference script uses ---------------------------------------------------------------------
 """
     RbqEngine.@accelerate Model params_expr
+    RbqEngine.@accelerate Model{DA,TO} where {DA,TO} params_expr
 
 Adds, for the script's own `Model` type, methods that forward to the engine:
 `RD.discrete_dynamics(::Type{RD.RK3}, ::Model, x, u, t, dt)` for Float64 arguments (dual-number calls from ForwardDiff
-still reach the script's generic method) and `RD.discrete_jacobian!(::Type{RD.RK3}, ∇f, ::Model, z)`.
-`params_expr` is evaluated with `model` in scope, e.g. `RbqEngine.params_spin30(model.S, model.nominal_idxs, model.fq_cov,
-model.alpha, model.sample_state_count)`.
+still reach the script's generic method), `RD.discrete_jacobian!(::Type{RD.RK3}, ∇f, ::Model, z)`, and the two
+trajectory-level loops `TO.dynamics_expansion!(RK3, D, ::Model, Z)` / `RD.rollout!(RK3, ::Model, Z, x0)`.
+`params_expr` is evaluated inside each method with the method's own `model` argument in scope (the argument is
+deliberately NOT hygienic), e.g. `RbqEngine.params_spin30(model.S, model.nominal_idxs, model.fq_cov, model.alpha,
+model.sample_state_count)`; type parameters named in the `where` clause are in scope too
+(`RbqEngine.params_spin15(DA, TO)`).
 """
 macro accelerate(M, pexpr)
+    wh = Any[]
+    if M isa Expr && M.head == :where          # `Model{DA,TO} where {DA,TO}` arrives as one :where expression
+        wh = M.args[2:end]
+        M = M.args[1]
+    end
+    model = esc(:model)                         # the method argument is visible to params_expr on purpose
+    MT = esc(M)
+    whs = map(esc, wh)
+    P = esc(pexpr)
+    TOexp = esc(:(TO.dynamics_expansion!))      # the reference scripts bind `const TO = TrajectoryOptimization` (spin13.jl:15)
     quote
-        function RobotDynamics.discrete_dynamics(::Type{RobotDynamics.RK3}, model::$(esc(M)),
+        function RobotDynamics.discrete_dynamics(::Type{RobotDynamics.RK3}, $model::$MT,
                                                  x::StaticVector{<:Any,Float64}, u::StaticVector{<:Any,Float64},
-                                                 t::Real, dt::Real)
-            p = let model = model; $(esc(pexpr)); end
-            return RbqEngine.discrete_dynamics(p, x, u, t, dt)
+                                                 t::Real, dt::Real) where {$(whs...)}
+            return RbqEngine.discrete_dynamics($P, x, u, t, dt)
         end
-        function RobotDynamics.discrete_jacobian!(::Type{RobotDynamics.RK3}, ∇f, model::$(esc(M)),
-                                                  z::RobotDynamics.AbstractKnotPoint{Float64})
-            p = let model = model; $(esc(pexpr)); end
-            return RbqEngine.discrete_jacobian!(∇f, p, RobotDynamics.state(z), RobotDynamics.control(z), z.t, z.dt)
+        function RobotDynamics.discrete_jacobian!(::Type{RobotDynamics.RK3}, ∇f, $model::$MT,
+                                                  z::RobotDynamics.AbstractKnotPoint{Float64}) where {$(whs...)}
+            return RbqEngine.discrete_jacobian!(∇f, $P, RobotDynamics.state(z), RobotDynamics.control(z), z.t, z.dt)
+        end
+        function RobotDynamics.rollout!(::Type{RobotDynamics.RK3}, $model::$MT,
+                                        Z::AbstractVector{<:RobotDynamics.AbstractKnotPoint{Float64}}, x0) where {$(whs...)}
+            return RbqEngine.rollout_traj!($P, Z, x0)
+        end
+        function $TOexp(::Type{RobotDynamics.RK3}, D::AbstractVector, $model::$MT,
+                        Z::AbstractVector{<:RobotDynamics.AbstractKnotPoint{Float64}}) where {$(whs...)}
+            return RbqEngine.dynamics_expansion!(D, $P, Z)
         end
     end
 end

@@ -9,8 +9,8 @@ dist.py   sample sharding across ranks + the one small all-gather of statistics
 from . import _lib
 from ._lib import (ALGO_PADE, ALGO_SU2, GATE_XPI, GATE_XPIBY2, GATE_YPIBY2, GATE_ZPIBY2, LINDBLAD_T1, LINDBLAD_T2,
                    REG_CONTROL, REG_STATE, CON_BOUND, CON_GOAL, CON_NORM, Constraint, ModelParams, RbqError, Stats)
-from .engine import Engine, stats_from_words, stats_merge, STATS_INT64_WORDS
+from .engine import Engine, EngineGroup, stats_from_words, stats_merge, STATS_INT64_WORDS
 
-__all__ = ["Engine", "ModelParams", "Stats", "RbqError", "stats_from_words", "stats_merge", "STATS_INT64_WORDS",
+__all__ = ["Engine", "EngineGroup", "ModelParams", "Stats", "RbqError", "stats_from_words", "stats_merge", "STATS_INT64_WORDS",
            "ALGO_SU2", "ALGO_PADE", "GATE_ZPIBY2", "GATE_YPIBY2", "GATE_XPIBY2", "GATE_XPI", "LINDBLAD_T1",
            "LINDBLAD_T2", "REG_CONTROL", "REG_STATE", "CON_BOUND", "CON_GOAL", "CON_NORM", "Constraint"]

@@ -120,6 +120,12 @@ SIGNATURES = {
                                            C.c_int, _P, _P]),
     "rbq_mc_static_philox": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _I64, C.c_uint64, _D, _D, _D, _D,
                                        C.c_int, _P, _SP]),
+    "rbq_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "rbq_group_destroy": (C.c_int, [_P]),
+    "rbq_group_size": (C.c_int, [_P]),
+    "rbq_group_handle": (_P, [_P, C.c_int]),
+    "rbq_group_last_error": (C.c_char_p, [_P]),
+    "rbq_group_mc_static_philox": (C.c_int, [_P, _P, _I64, _D, C.c_int, _I64, _I64, _I64, C.c_uint64, _D, _D, _D, _D, C.c_int, _P, _SP]),
     "rbq_philox_samples": (C.c_int, [_P, _I64, _I64, C.c_uint64, _D, _D, _D, _D, _P, _P, _P]),
     "rbq_stats_reset_dev": (C.c_int, [_P, _P]),
     "rbq_stats_merge": (C.c_int, [_SP, _SP]),

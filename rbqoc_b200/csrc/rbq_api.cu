@@ -654,6 +654,103 @@ int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, 
     CK(cudaStreamSynchronize(h->stream));
     return RBQ_OK;
 }
+// ---- single-process multi-device group ------------------------------------------------------------------------------------
+struct rbq_group {
+    int n;
+    rbq_handle* h[64];
+    cudaStream_t own_stream[64];     // members get their own non-blocking stream so that their work overlaps
+    char err[512];
+};
+int rbq_group_create(const int* devices, int n, rbq_group** out) {
+    if (!devices || !out) return RBQ_E_NULL;
+    *out = nullptr;
+    if (n < 1 || n > 64) return RBQ_E_SIZE;
+    rbq_group* g = new (std::nothrow) rbq_group();
+    if (!g) return RBQ_E_SIZE;
+    memset(g, 0, sizeof(*g));
+    for (int i = 0; i < n; ++i) {
+        int rc = rbq_create(devices[i], &g->h[i]);
+        if (rc == RBQ_OK && (cudaSetDevice(devices[i]) != cudaSuccess ||
+                             cudaStreamCreateWithFlags(&g->own_stream[i], cudaStreamNonBlocking) != cudaSuccess)) rc = RBQ_E_NODEVICE;
+        if (rc != RBQ_OK) {
+            g->n = i + (g->h[i] ? 1 : 0);
+            rbq_group_destroy(g);
+            return rc;
+        }
+        g->h[i]->stream = g->own_stream[i];
+        g->n = i + 1;
+    }
+    *out = g;
+    return RBQ_OK;
+}
+int rbq_group_destroy(rbq_group* g) {
+    if (!g) return RBQ_E_NULL;
+    for (int i = 0; i < g->n; ++i) {
+        if (!g->h[i]) continue;
+        const int dev = g->h[i]->device;
+        rbq_destroy(g->h[i]);
+        if (g->own_stream[i]) { cudaSetDevice(dev); cudaStreamDestroy(g->own_stream[i]); }
+    }
+    delete g;
+    return RBQ_OK;
+}
+int rbq_group_size(const rbq_group* g) { return g ? g->n : RBQ_E_NULL; }
+rbq_handle* rbq_group_handle(rbq_group* g, int member) { return (g && member >= 0 && member < g->n) ? g->h[member] : nullptr; }
+const char* rbq_group_last_error(const rbq_group* g) { return g ? g->err : "null group"; }
+int rbq_group_mc_static_philox(rbq_group* g, const double* controls, int64_t nknots, double dt, int gate, int64_t gate_count,
+                               int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip,
+                               double da_sigma, int algo, double* fid, rbq_stats* stats) {
+    if (!g) return RBQ_E_NULL;
+    g->err[0] = 0;
+    if (S < 0 || first < 0) { snprintf(g->err, sizeof(g->err), "rbq_group_mc_static_philox: first=%lld S=%lld", (long long)first, (long long)S); return RBQ_E_SIZE; }
+    const int64_t G1 = gate_count + 1;
+    const int64_t base = S / g->n, rem = S % g->n;
+    void* dst[64] = {nullptr};
+    void* dfid[64] = {nullptr};
+    int64_t off[65];
+    off[0] = 0;
+    for (int i = 0; i < g->n; ++i) off[i + 1] = off[i] + base + (i < rem ? 1 : 0);
+    auto fail_with = [&](int i, int rc) { snprintf(g->err, sizeof(g->err), "member %d (device %d): %s", i, g->h[i]->device, g->h[i]->err); return rc; };
+    // 1. enqueue every member's share (uploads, kernels, downloads) without waiting
+    for (int i = 0; i < g->n; ++i) {
+        rbq_handle* h = g->h[i];
+        const int64_t cnt = off[i + 1] - off[i];
+        if (cudaSetDevice(h->device) != cudaSuccess) return fail_with(i, RBQ_E_NODEVICE);
+        h->err[0] = 0;
+        int rc = check_mc(h, "rbq_group_mc_static_philox", controls, nknots, dt, gate_count, cnt, algo);
+        if (rc) return fail_with(i, rc);
+        void* dc;
+        if ((rc = dev_buf(h, B_IN0, sizeof(double) * nknots, &dc))) return fail_with(i, rc);
+        if (fid && cnt > 0 && (rc = dev_buf(h, B_OUT0, sizeof(double) * cnt * G1, &dfid[i]))) return fail_with(i, rc);
+        if ((rc = dev_buf(h, B_STATS, sizeof(rbq_stats), &dst[i]))) return fail_with(i, rc);
+        if ((rc = rbq_stats_reset_dev(h, (rbq_stats*)dst[i]))) return fail_with(i, rc);
+        if (cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return fail_with(i, (int)cudaGetLastError());
+        rc = rbq_mc_static_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first + off[i], cnt, seed, fq0, fq_rel_sigma, fq_rel_clip,
+                                      da_sigma, algo, (double*)dfid[i], (rbq_stats*)dst[i]);
+        if (rc) return fail_with(i, rc);
+        if (fid && cnt > 0 &&
+            cudaMemcpyAsync(fid + off[i] * G1, dfid[i], sizeof(double) * cnt * G1, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+            return fail_with(i, (int)cudaGetLastError());
+    }
+    // 2. wait for each, merge the statistics in member order
+    rbq_stats total;
+    memset(&total, 0, sizeof(total));
+    total.min = INFINITY; total.max = -INFINITY;
+    for (int i = 0; i < g->n; ++i) {
+        rbq_handle* h = g->h[i];
+        rbq_stats part;
+        if (cudaSetDevice(h->device) != cudaSuccess) return fail_with(i, RBQ_E_NODEVICE);
+        if (cudaMemcpyAsync(&part, dst[i], sizeof(part), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) {
+            snprintf(h->err, sizeof(h->err), "%s", cudaGetErrorString(cudaGetLastError()));
+            return fail_with(i, 1);
+        }
+        rbq_stats_merge(&total, &part);
+    }
+    if (stats) *stats = total;
+    return RBQ_OK;
+}
+
 int rbq_philox_samples(rbq_handle* h, int64_t first, int64_t S, uint64_t seed, double fq0, double fq_rel_sigma,
                        double fq_rel_clip, double da_sigma, double* fq, double* da, double* psi0) {
     ENTER(h);

@@ -525,6 +525,44 @@ class Engine:
                  "rbq_lindblad_dev")
 
 
+class EngineGroup:
+    """One process, several GPUs: an `rbq_group` (one handle per listed device) for sweeps that shard by global sample index.
+    The other supported shape is one process per GPU with torch.distributed (rbqoc_b200/dist.py)."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        g = C.c_void_p()
+        rc = self._lib.rbq_group_create(devs, len(devices), C.byref(g))
+        if rc:
+            raise RbqError(rc, "rbq_group_create", "every member needs an sm_100 CUDA device; there is no CPU fallback")
+        self._g = g
+        self.devices = [int(d) for d in devices]
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.rbq_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mc_static_philox(self, controls, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma, fq_rel_clip, da_sigma,
+                         algo=_lib.ALGO_SU2, want_fid=False):
+        controls = _f64(controls)
+        fid = np.empty((S, gate_count + 1)) if want_fid else None
+        st = Stats()
+        rc = self._lib.rbq_group_mc_static_philox(self._g, _ptr(controls), controls.shape[0], float(dt), int(gate), int(gate_count),
+                                                  int(first), int(S), int(seed), float(fq0), float(fq_rel_sigma), float(fq_rel_clip),
+                                                  float(da_sigma), int(algo), _ptr(fid), C.byref(st))
+        if rc:
+            raise RbqError(rc, "rbq_group_mc_static_philox", self._lib.rbq_group_last_error(self._g).decode(errors="replace"))
+        return fid, st
+
+
 STATS_INT64_WORDS = C.sizeof(Stats) // 8   # a device rbq_stats is a torch.int64 tensor of this many words
 
 

@@ -780,3 +780,25 @@ def test_run_sim_fine_deqjl_states_on_the_save_step_grid(engine, oracle):
     rho0 = np.stack([spin.gen_rand_density_iso(int(s), engine) for s in seeds])
     _, rrho = oracle.lindblad_ode(amps, durs, save_after, rbq.GATE_XPIBY2, spin.FQ, None, rho0, channels=1)
     assert out["states"].shape == rrho.shape and np.max(np.abs(out["states"] - rrho)) < 5e-12
+
+
+def test_single_process_device_group_equals_one_handle(engine):
+    """rbq_group: one process driving several handles (here every visible GPU, and the first one twice more so that the
+    sharding is exercised on a single-GPU box too).  Samples are keyed by their global index, so the group's fidelities are
+    bit-identical to one handle's and the merged statistics equal up to the order of the partial sums."""
+    import torch
+
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    devs = list(range(torch.cuda.device_count())) + [0, 0]
+    grp = rbq.EngineGroup(devs)
+    try:
+        first, S, seed = 1234, 10_007, 5        # not divisible by the member count
+        fid_g, st_g = grp.mc_static_philox(controls, dt, gate, 2, first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5, want_fid=True)
+        fid_1, st_1 = engine.mc_static_philox(controls, dt, gate, 2, first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5, want_fid=True)
+        assert np.array_equal(fid_g, fid_1)
+        assert st_g.count == st_1.count == S and st_g.hist[:] == st_1.hist[:] and st_g.min == st_1.min and st_g.max == st_1.max
+        assert abs(st_g.sum - st_1.sum) < 1e-12 * st_1.sum
+        _, st_e = grp.mc_static_philox(controls, dt, gate, 2, 0, 1, seed, spin.FQ, 0.01, 0.03, 2.574e-5)     # fewer samples than members
+        assert st_e.count == 1
+    finally:
+        grp.close()

@@ -6,6 +6,7 @@ entry of the block).  Every call goes through the C ABI (librbq.so) via rbqoc_b2
 import numpy as np
 import pytest
 
+import rbqoc_b200 as rbq
 from rbqoc_b200 import spin
 from _cases import MODEL_KW, golden_model_cases, relerr
 
