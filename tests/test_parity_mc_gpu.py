@@ -784,8 +784,8 @@ def test_run_sim_fine_deqjl_states_on_the_save_step_grid(engine, oracle):
 
 def test_single_process_device_group_equals_one_handle(engine):
     """rbq_group: one process driving several handles (here every visible GPU, and the first one twice more so that the
-    sharding is exercised on a single-GPU box too).  Samples are keyed by their global index, so the group's fidelities are
-    bit-identical to one handle's and the merged statistics equal up to the order of the partial sums."""
+    sharding is exercised on a single-GPU box too).  Samples are keyed by their global index, so the group's fidelities equal
+    one handle's to rounding and the merged statistics up to the order of the partial sums."""
     import torch
 
     controls, dt, gate = PULSES["sin301_dt0.1"]
@@ -795,8 +795,11 @@ def test_single_process_device_group_equals_one_handle(engine):
         first, S, seed = 1234, 10_007, 5        # not divisible by the member count
         fid_g, st_g = grp.mc_static_philox(controls, dt, gate, 2, first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5, want_fid=True)
         fid_1, st_1 = engine.mc_static_philox(controls, dt, gate, 2, first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5, want_fid=True)
-        assert np.array_equal(fid_g, fid_1)
-        assert st_g.count == st_1.count == S and st_g.hist[:] == st_1.hist[:] and st_g.min == st_1.min and st_g.max == st_1.max
+        # same samples whatever the sharding; which warp a sample shares (and so which of the equally accurate step classes
+        # it takes) depends on where its shard starts, hence rounding-level differences only
+        assert np.max(np.abs(fid_g - fid_1)) < 1e-14
+        assert st_g.count == st_1.count == S and abs(st_g.min - st_1.min) < 1e-14 and abs(st_g.max - st_1.max) < 1e-14
+        assert np.abs(np.array(st_g.hist[:]) - np.array(st_1.hist[:])).sum() <= 4      # a sample on a bin edge may move
         assert abs(st_g.sum - st_1.sum) < 1e-12 * st_1.sum
         _, st_e = grp.mc_static_philox(controls, dt, gate, 2, 0, 1, seed, spin.FQ, 0.01, 0.03, 2.574e-5)     # fewer samples than members
         assert st_e.count == 1
