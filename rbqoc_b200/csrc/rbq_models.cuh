@@ -348,8 +348,10 @@ __host__ __device__ inline bool model_supports_rk(const rbq_model_params& p) {
 
 // MODEL is the reference file number (RBQ_MODEL_*); one kernel instantiation per model family.
 // `time` is used by spin25 only (every other reference model ignores its time argument).
-template <int MODEL, class T, class IO> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double time, double dt) {
-    if ((MODEL == RBQ_MODEL_SPIN13 || MODEL == RBQ_MODEL_SPIN15 || MODEL == RBQ_MODEL_SPIN11) && p.integrator != RBQ_INTEGRATOR_EXP) {
+// RK: the Runge-Kutta steps are compiled into their own kernel instantiations only (inside the exponential-step kernels their
+// mere presence cost 150 registers and a 4.6 KB stack frame)
+template <int MODEL, class T, class IO, bool RK = false> RBQ_DEV void model_step(const rbq_model_params& p, IO& io, double time, double dt) {
+    if constexpr (RK) {
         step_rk<T>(p, io, model_state_dim(p), model_control_dim(p), dt);
         return;
     }

@@ -44,7 +44,7 @@ template <int NT> struct TangentIO {
 };
 
 // ---- kernels ------------------------------------------------------------------------------------
-template <int MODEL>
+template <int MODEL, bool RK = false>
 __global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n, int m, int64_t B, int64_t N, double t0,
                                                       const double* __restrict__ x0, const double* __restrict__ U,
                                                       const double* __restrict__ dt, double* __restrict__ X) {
@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(128) rollout_kernel(rbq_model_params p, int n,
     double time = t0;
     for (int64_t k = 0; k + 1 < N; ++k) {
         ValueIO io{Xb + k * n, Ub + k * m, Xb + (k + 1) * n};
-        model_step<MODEL, double>(p, io, time, dt[k]);
+        model_step<MODEL, double, ValueIO, RK>(p, io, time, dt[k]);
         time = time + dt[k];
     }
 }
 
-template <int MODEL, int NT>
+template <int MODEL, int NT, bool RK = false>
 __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int n, int m, int lanes_per_knot,
                                                         int64_t K, const double* __restrict__ X,
                                                         const double* __restrict__ U, const double* __restrict__ tk,
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) jacobians_kernel(rbq_model_params p, int 
     if (k >= K) return;
     const int lane = (int)(t - k * lanes_per_knot);
     TangentIO<NT> io{X + k * n, U + k * m, AB + (size_t)k * n * (n + m), n, n + m, lane * NT};
-    model_step<MODEL, Tan<NT>>(p, io, tk ? tk[k] : 0.0, dt[k]);
+    model_step<MODEL, Tan<NT>, TangentIO<NT>, RK>(p, io, tk ? tk[k] : 0.0, dt[k]);
 }
 
 // Same computation, but a block stages the [A_k B_k] blocks of G consecutive knots in shared memory and writes them out
@@ -286,6 +286,16 @@ int launch_rollout(rbq_handle* h, const rbq_model_params& p, int64_t B, int64_t 
 #define CALL(M) { cudaError_t e_ = launch_warp_rollout<M, false>(a, (unsigned)B, 0, h->stream); if (e_ != cudaSuccess) return (int)e_; }
         RBQ_DISPATCH_FAMILY(family(p.model_id), CALL)
 #undef CALL
+    } else if (rk) {
+        // Runge-Kutta steps of the continuous dynamics: one thread per trajectory through model_step<.., RK = true>
+        const int threads = 32;
+        const unsigned blocks = (unsigned)((B + threads - 1) / threads);
+        switch (fam0) {
+        case RBQ_MODEL_SPIN13: rollout_kernel<RBQ_MODEL_SPIN13, true><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, t0, d_x0, d_U, d_dt, d_X); break;
+        case RBQ_MODEL_SPIN15: rollout_kernel<RBQ_MODEL_SPIN15, true><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, t0, d_x0, d_U, d_dt, d_X); break;
+        case RBQ_MODEL_SPIN11: rollout_kernel<RBQ_MODEL_SPIN11, true><<<blocks, threads, 0, h->stream>>>(p, n, m, B, N, t0, d_x0, d_U, d_dt, d_X); break;
+        default: return RBQ_E_MODEL;
+        }
     } else {
         const int threads = 128;
         const unsigned blocks = (unsigned)((B + threads - 1) / threads);
@@ -323,6 +333,19 @@ int launch_jacobians(rbq_handle* h, const rbq_model_params& p, int64_t K, const 
     const int fam = family(p.model_id);
     // columns per lane: 4 for the small models, 2 for the 43/56+-state ones (register budget)
     int nt = (fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25 || fam == RBQ_MODEL_SPIN12) ? 2 : 4;
+    if (p.integrator != RBQ_INTEGRATOR_EXP) {
+        // Runge-Kutta variants: generic forward mode through step_rk, 4 seed columns per lane, direct stores
+        const int lpk4 = (n + m + 3) / 4, threads = 128;
+        const unsigned blocks = (unsigned)((K * lpk4 + threads - 1) / threads);
+        switch (fam) {
+        case RBQ_MODEL_SPIN13: jacobians_kernel<RBQ_MODEL_SPIN13, 4, true><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk4, K, d_X, d_U, d_t, d_dt, d_AB); break;
+        case RBQ_MODEL_SPIN15: jacobians_kernel<RBQ_MODEL_SPIN15, 4, true><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk4, K, d_X, d_U, d_t, d_dt, d_AB); break;
+        case RBQ_MODEL_SPIN11: jacobians_kernel<RBQ_MODEL_SPIN11, 4, true><<<blocks, threads, 0, h->stream>>>(p, n, m, lpk4, K, d_X, d_U, d_t, d_dt, d_AB); break;
+        default: return RBQ_E_MODEL;
+        }
+        h->launches++;
+        return (int)cudaGetLastError();
+    }
     const bool unscented = fam == RBQ_MODEL_SPIN30 || fam == RBQ_MODEL_SPIN25;
     // unscented models with one sample state (every run of the reference): the block is assembled from its structure, the value
     // path evaluated once per knot instead of once per seed column (rbq_jac_unscented.cu); RBQ_JAC_STRUCTURED=0 keeps the
