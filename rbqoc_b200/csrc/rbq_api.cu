@@ -112,7 +112,7 @@ static bool make_gate_tables(int gate, GateIso* gi, GateRot* gr) {
 
 // ---- tuning options: latched from the environment in rbq_create, changed later only by rbq_set_option ----------------
 static const char* const kOptionNames[] = {"RBQ_NO_TABLE_CLASS", "RBQ_MC_ZEROCOPY", "RBQ_MC_CHUNK_WAVES", "RBQ_MC_VARIANT", "RBQ_PEAK_MODE",
-                                           "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE",
+                                           "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_LINDBLAD_SPT",
                                            "RBQ_ROLLOUT_PACKED", "RBQ_ROLLOUT_SCAN", "RBQ_JAC_NT_UNSCENTED", "RBQ_JAC_STRUCTURED",
                                            "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED", "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS"};
 int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
@@ -134,6 +134,7 @@ int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
     else if (is("RBQ_NOISE_GATE_PARALLEL")) h->opt.noise_gate_parallel = unset ? -1 : (v != 0);
     else if (is("RBQ_LINDBLAD_NO_SHARED_MAP")) h->opt.lindblad_shared_map = unset ? 1 : (v == 0);
     else if (is("RBQ_LINDBLAD_TABLE")) h->opt.lindblad_table = unset ? 1 : (v != 0);
+    else if (is("RBQ_LINDBLAD_SPT")) h->opt.lindblad_spt = (v == 1 || v == 2) ? v : -1;
     else if (is("RBQ_ROLLOUT_PACKED")) h->opt.rollout_packed = unset ? -1 : (v != 0);
     else if (is("RBQ_ROLLOUT_SCAN")) h->opt.rollout_scan = unset ? -1 : (v != 0);
     else if (is("RBQ_JAC_NT_UNSCENTED")) h->opt.jac_nt_unscented = (v == 2) ? 2 : 1;

@@ -35,6 +35,7 @@ struct rbq_handle {
         int noise_gate_parallel;   // RBQ_NOISE_GATE_PARALLEL 0: never the gate-parallel pair
         int lindblad_shared_map;   // RBQ_LINDBLAD_NO_SHARED_MAP (inverted): 0 = every realisation composes its own map
         int lindblad_table;        // RBQ_LINDBLAD_TABLE      0: series step only (no per-knot Frechet table)
+        int lindblad_spt;          // RBQ_LINDBLAD_SPT        realisations per thread of the table sweep (1 or 2)
         int rollout_packed;        // RBQ_ROLLOUT_PACKED      0 / 1 force
         int rollout_scan;          // RBQ_ROLLOUT_SCAN        0 / 1 force the prefix-product open-loop rollout
         int jac_nt_unscented;      // RBQ_JAC_NT_UNSCENTED    generic unscented Jacobian kernel: tangents per lane (1 or 2)

@@ -1163,13 +1163,13 @@ RBQ_DEV void bloch_series_knot(double c1, double fq, double dt, bool t1_on, doub
 
 // SPT realisations per thread (they share the table row's registers), NV = 1 (the state itself, gate_count <= 3) or 3 (the
 // one-gate map's three columns, applied gate_count times afterwards)
-template <int SPT, int NV>
-__global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs a, int channels, const double* __restrict__ table,
-                                                              double da_tab) {
+template <int SPT, int NV, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT, 1) lindblad_tab_kernel(const LindbladArgs a, int channels, const double* __restrict__ table,
+                                                               double da_tab) {
     __shared__ __align__(128) double tile_s[2 * LT_TILE * LT_ROW];
     __shared__ __align__(8) uint64_t bar_s[2];
     __shared__ unsigned hist_s[RBQ_HIST_BINS];
-    __shared__ BlockPartial red_s[16];
+    __shared__ BlockPartial red_s[MAXT / 32];
     __shared__ double invk_s[64];
     __shared__ double bmax_s[32];
     __shared__ unsigned char t1cells_s[244];
@@ -1221,7 +1221,7 @@ __global__ void __launch_bounds__(512, 1) lindblad_tab_kernel(const LindbladArgs
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
             const double* tile = pipe.acquire(ti, g + 1 < passes);
             const int len = pipe.tile_len(ti);
-            for (int j = 0; j < len; ++j) {
+            for (int j = 0; j < len; ++j) {      // (unrolling by 2 was measured: 0.613 against 0.583 ms for 1e5 x 1000)
                 const double2* __restrict__ row = reinterpret_cast<const double2*>(tile + j * LT_ROW);
                 const double2 af = row[22];                            // (E/L3 tail, a_k) sits in row[22] = doubles 44, 45
                 const double2 fk = row[23];                            // (flag, kappa)
@@ -1798,10 +1798,14 @@ int launch_lindblad_table(rbq_handle* h, const LindbladArgs& a, int channels, co
     // whole run.  Spread the warps evenly: `waves` blocks per SM, every block the same number of warps (<= 16: 128 registers).
     const bool compose = a.gate_count > 3;
     const int64_t warps1 = (a.S + 31) / 32;
-    const int spt = (!compose && warps1 >= (int64_t)h->sm_count * 8) ? 2 : 1;      // two realisations share a table row's loads
+    // one realisation per thread and up to 24 warps per SM (85 registers), or two per thread sharing a row's loads and up to 16
+    // warps (102 registers): RBQ_LINDBLAD_SPT picks, default by measurement (profiles/README.md)
+    int spt = (!compose && warps1 >= (int64_t)h->sm_count * 8) ? 2 : 1;
+    if (!compose && h->opt.lindblad_spt > 0) spt = h->opt.lindblad_spt == 2 ? 2 : 1;
+    const int maxw = (spt == 1 && !compose) ? 24 : 16;
     const int64_t warps = (a.S + 32 * spt - 1) / (32 * spt);
     const int64_t per_sm = (warps + h->sm_count - 1) / h->sm_count;
-    const int64_t waves = (per_sm + 15) / 16;
+    const int64_t waves = (per_sm + maxw - 1) / maxw;
     int wpb = (int)((warps + h->sm_count * waves - 1) / (h->sm_count * waves));
     if (wpb < 1) wpb = 1;
     const int threads = 32 * wpb;
@@ -1809,7 +1813,7 @@ int launch_lindblad_table(rbq_handle* h, const LindbladArgs& a, int channels, co
     if (nblocks_out) *nblocks_out = blocks;
     if (compose) lindblad_tab_kernel<1, 3><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
     else if (spt == 2) lindblad_tab_kernel<2, 1><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
-    else lindblad_tab_kernel<1, 1><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
+    else lindblad_tab_kernel<1, 1, 768><<<blocks, threads, 0, h->stream>>>(a, channels, d_table, da_tab);
     h->launches += 2;
     return (int)cudaGetLastError();
 }

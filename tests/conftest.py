@@ -32,7 +32,7 @@ def engine():
 
 
 ENGINE_OPTIONS = ("RBQ_NO_TABLE_CLASS", "RBQ_MC_ZEROCOPY", "RBQ_MC_CHUNK_WAVES", "RBQ_MC_VARIANT", "RBQ_PEAK_MODE",
-                  "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_ROLLOUT_PACKED",
+                  "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_LINDBLAD_SPT", "RBQ_ROLLOUT_PACKED",
                   "RBQ_ROLLOUT_SCAN", "RBQ_JAC_NT_UNSCENTED", "RBQ_JAC_STRUCTURED", "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED",
                   "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS")
 

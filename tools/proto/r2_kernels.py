@@ -9,6 +9,8 @@ dev = torch.device("cuda", 0)
 eng = rbq.Engine(0); eng.use_torch_stream()
 d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 what = sys.argv[1:] or ["lindblad", "jac30", "rollout"]
+if what == ["all"]:
+    what = ["mc_static", "lindblad", "jac30", "rollout"]
 reps = int(os.environ.get("REPS", "5"))
 def timed(fn):
     for _ in range(2): fn()
@@ -19,6 +21,15 @@ def timed(fn):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 N = 1001
+if "mc_static" in what:
+    S = 1 << 20
+    controls = spin.pulse_sin(N)[:-1]
+    fq, da, psi0 = eng.philox_samples(0, S, 2026, spin.FQ, 0.01, 0.03, 2.574e-5)
+    dcn, dfq, dda, dpsi = d(controls), d(fq), d(da), d(psi0)
+    dfid = torch.empty(S, 2, dtype=torch.float64, device=dev)
+    dst = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
+    ms = timed(lambda: eng.mc_static_dev(dcn, N - 1, 0.1, rbq.GATE_ZPIBY2, 1, S, dfq, dda, dpsi, rbq.ALGO_SU2, dfid, dst))
+    print(f"mc_static S={S}: {ms:.4f} ms  {S * (N - 1) / ms * 1e-6:.2f} G trajectory-steps/s", flush=True)
 if "lindblad" in what:
     S = 100_000
     rng = np.random.default_rng(0)
@@ -34,6 +45,12 @@ if "lindblad" in what:
         ms = timed(lambda: eng.lindblad_dev(dcn, N - 1, 0.1, rbq.GATE_XPIBY2, 1, S, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst))
         print(f"lindblad S={S} table={opt}: {ms:.4f} ms  {S * (N - 1) / ms * 1e-6:.2f} G density-steps/s", flush=True)
     eng.set_option("RBQ_LINDBLAD_TABLE", None)
+    for spt in ("1", "2"):
+        eng.set_option("RBQ_LINDBLAD_SPT", spt)
+        for Sx in (S, 20000, 50000):
+            ms = timed(lambda: eng.lindblad_dev(dcn, N - 1, 0.1, rbq.GATE_XPIBY2, 1, Sx, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst))
+            print(f"lindblad S={Sx} spt={spt}: {ms:.4f} ms  {Sx * (N - 1) / ms * 1e-6:.2f} G density-steps/s", flush=True)
+    eng.set_option("RBQ_LINDBLAD_SPT", None)
 if "jac30" in what:
     for mname, model, x0, B in (("spin30", spin.Spin30Model(), spin.spin30_x0(), 128), ("spin25", spin.Spin25Model(), spin.spin25_x0(), 128)):
         n, m = model.n, model.m
