@@ -766,17 +766,32 @@ class SaveType(enum.IntEnum):                        # rbqoc.jl:27-31
 
 def read_save(save):
     """rbqoc.jl:129-139.  `save` is either the mapping read_save would return (key -> array / scalar, arrays with the shapes
-    Julia sees, index lists 1-based as stored) or a path to the .h5 file.  Reading a path needs h5py, which this image does
-    not have (and the reference ships no .h5 file to test against): arrays are transposed on the way in because HDF5.jl
-    stores Julia's column-major arrays with reversed dimensions."""
+    Julia sees, index lists 1-based as stored) or a path to the .h5 file, read by `h5lite` (the HDF5 subset those files use;
+    no libhdf5 / h5py in this image).  Arrays are transposed on the way in because HDF5.jl stores Julia's column-major
+    arrays with reversed dimensions."""
     if isinstance(save, (str, bytes)) or hasattr(save, "__fspath__"):
-        try:
-            import h5py
-        except ImportError as exc:
-            raise RuntimeError("reading a .h5 pulse file needs h5py; pass the mapping of its datasets instead") from exc
-        with h5py.File(save, "r") as f:
-            return {k: (np.asarray(v).T if getattr(v, "ndim", 0) > 1 else np.asarray(v)[()]) for k, v in f.items()}
+        from . import h5lite
+        f = h5lite.File(save)
+        return {k: (v.T if isinstance(v, np.ndarray) and v.ndim > 1 else v) for k, v in f.items()}
     return save
+
+
+def write_save(path, result):
+    """The write side of the same schema (`spin13.jl:196-233`: `h5open(path, "cw") do f; for (k, v) in result; write(f, k, v)`):
+    `result` holds arrays with the shapes Julia sees; they are stored with reversed dimensions as HDF5.jl does, so that
+    `read_save(path)` returns `result` and h5py would show the transposed arrays.  Entries that are None (Julia `nothing`,
+    e.g. `benchmark_result`) are skipped."""
+    from . import h5lite
+    out = {}
+    for k, v in result.items():
+        if v is None:
+            continue
+        if isinstance(v, (str, dict)):
+            out[k] = v
+        else:
+            a = np.asarray(v)
+            out[k] = np.ascontiguousarray(a.T) if a.ndim > 1 else (a if a.ndim else a[()])
+    h5lite.write(path, out)
 
 
 def _cols(idx):
