@@ -47,7 +47,9 @@ PARITY_TOL = 1e-12
 #     1 DFMA (eps) + 2 DFMA (T) + 1 DADD (q) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v) = 14 FP64 instructions = 25 flop
 FLOPS_PER_STEP_SU2 = 25.0
 FP64_INSTR_PER_STEP_SU2 = 14.0
-FP64_INSTR3_PER_STEP_SU2 = 11.0   # of those, instructions with three fresh 64-bit register operands (3 issue cycles, not 2)
+# operand-delivery model of the shipped loop (tools/sass_fp64_cost.py on librbq.so: per knot 0.6 instructions with <= 1 register
+# operand to fetch at 2.0 pipe cycles, 8.1 with two at 2.42, 5.25 with three at 3.24; profiles/r1_fp64_microbench.txt)
+FP64_MODEL_CYCLES_PER_STEP_SU2 = 37.92
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # FP64 instructions per density-step of the Lindblad table step (lindblad_tab_kernel): 27 DFMA (Horner of the 9
 # entries of E_lo + da (L1 + da (L2 + da L3))) + 3 DMUL + 6 DFMA (the small part applied) + 9 DFMA (E_hi applied) = 45
@@ -654,11 +656,12 @@ def main():
                                          "(r1: 50.4 MB read + 1.8 MB written against 64 MB algorithmic; the 16 MB of fidelities stay in L2)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
-                         # register-operand model of the FP64 pipe (profiles/r1_fp64_microbench.txt): 2 issue cycles per warp-DFMA
-                         # with <= 2 fresh 64-bit register operands, ~3 with 3 (the register file feeds two per slot)
-                         "issue_model": {"cycles_per_warp_step_floor": (FP64_INSTR_PER_STEP_SU2 - FP64_INSTR3_PER_STEP_SU2) * 2 + FP64_INSTR3_PER_STEP_SU2 * 3,
+                         # register-operand model of the FP64 pipe: a warp-wide instruction holds the pipe 2.0 / 2.42 / 3.24 cycles
+                         # with <= 1 / 2 / 3 register operands to fetch (operands kept by the reuse cache are free)
+                         "issue_model": {"cycles_per_warp_step_floor": FP64_MODEL_CYCLES_PER_STEP_SU2,
+                                         "cycles_per_warp_step_all_operands_reused": 2.0 * FP64_INSTR_PER_STEP_SU2,
                                          "cycles_per_warp_step_measured": (clk["sm_mhz"] or 1965.0) * 1e6 * 4 * 148 * (kern_ms * 1e-3) / (S * NK / 32.0),
-                                         "note": "floor / measured = fraction of the operand-bandwidth-limited issue rate"},
+                                         "note": "floor = what the SASS of the shipped loop costs under the measured operand-delivery model (tools/sass_fp64_cost.py); floor / measured = how close the kernel runs to it"},
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,
                          "kernel_ms": kern_ms,
                          "hbm": {"achieved_gbs": S * BYTES_PER_SAMPLE / (kern_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),

@@ -365,6 +365,98 @@ RBQ_DEV void delta_tile(const double* __restrict__ tile, int len, const double (
         for (int c = 0; c < 4; ++c) v[i][c] *= inv;
     }
 }
+// The same step for one sample per thread, laid out for the register file (tools/sass_fp64_cost.py, profiles/README.md): a warp-wide
+// FP64 instruction holds the pipe for 2.0 cycles when at most one of its register operands must be fetched, 2.42 with two, 3.24
+// with three; an operand is free when the previous instruction carried it in the same slot (operand reuse cache).  So the batch
+// runs in two phases that the scheduler cannot interleave (`once` is 1 at run time, unknown at compile time: the second phase is
+// a loop body of its own): first the scalars of all U knots level by level, each level's sample-invariant operands in fixed slots
+// (dq2 and e0, dq, p), then the U dependent updates, every group of four sharing its multiplier and the first instruction of the
+// second group taking its multiplicand from the last one of the first.
+#ifndef RBQ_DELTA_PHASED
+#define RBQ_DELTA_PHASED 1
+#endif
+#ifndef RBQ_DELTA_PAIR
+#define RBQ_DELTA_PAIR 0
+#endif
+#ifndef RBQ_DELTA_U
+#define RBQ_DELTA_U 8
+#endif
+// FP64 operations as volatile PTX: the compiler keeps volatile statements in program order
+RBQ_DEV double vfma(double a, double b, double c) { double d; asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c)); return d; }
+RBQ_DEV double vadd(double a, double b) { double d; asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b)); return d; }
+RBQ_DEV double vmul(double a, double b) { double d; asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b)); return d; }
+template <int U>
+RBQ_DEV void delta_tile_phased(const double* __restrict__ tile, int len, double p, double dq, double dq2, double e0, double (&v)[4],
+                               int once) {
+    asm volatile("" : "+d"(dq2));               // (keeps dq2 in its register: the compiler would recompute dq + dq per batch)
+    int j = 0;
+    for (; j + U <= len; j += U) {
+        double tp[U], tq[U];
+        {
+            double eps[U], q[U], h[U];
+            const double* __restrict__ r = tile + ST_EPK * j;
+            double r0[U], r1[U], r2[U], r3[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double2 lo = *reinterpret_cast<const double2*>(r + ST_EPK * u), hi = *reinterpret_cast<const double2*>(r + ST_EPK * u + 2);
+                r0[u] = lo.x; r1[u] = lo.y; r2[u] = hi.x; r3[u] = hi.y;
+            }
+#if RBQ_DELTA_PAIR
+#pragma unroll
+            for (int u = 0; u < U; u += RBQ_DELTA_PAIR) {
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) eps[u + w] = vfma(r0[u + w], dq2, e0);
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) q[u + w] = vadd(r0[u + w], dq);
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) h[u + w] = vfma(r3[u + w], eps[u + w], r2[u + w]);
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) h[u + w] = vfma(h[u + w], eps[u + w], r1[u + w]);
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) tp[u + w] = vmul(h[u + w], p);
+#pragma unroll
+                for (int w = 0; w < RBQ_DELTA_PAIR; ++w) tq[u + w] = vmul(h[u + w], q[u + w]);
+            }
+#else
+#pragma unroll
+            for (int u = 0; u < U; ++u) eps[u] = vfma(r0[u], dq2, e0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = vadd(r0[u], dq);
+#pragma unroll
+            for (int u = 0; u < U; ++u) h[u] = vfma(r3[u], eps[u], r2[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) h[u] = vfma(h[u], eps[u], r1[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) tp[u] = vmul(h[u], p);
+#pragma unroll
+            for (int u = 0; u < U; ++u) tq[u] = vmul(h[u], q[u]);
+#endif
+        }
+        for (int rep = 0; rep < once; ++rep) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+                const double x0 = fma(tp[u], a2, a0);
+                const double x3 = fma(tp[u], a1, a3);
+                const double x2 = fma(-tp[u], a0, a2);
+                const double x1 = fma(-tp[u], a3, a1);
+                v[0] = fma(tq[u], a3, x0);
+                v[2] = fma(-tq[u], a1, x2);
+                v[3] = fma(-tq[u], a0, x3);
+                v[1] = fma(tq[u], a2, x1);
+            }
+        }
+    }
+    for (; j < len; ++j) {
+        const double* __restrict__ r = tile + ST_EPK * j;
+        const double eps = fma(r[0], dq2, e0);
+        const double t = fma(fma(r[3], eps, r[2]), eps, r[1]);
+        tan_apply(t * p, t * (r[0] + dq), v);
+    }
+    const double inv = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] *= inv;
+}
 // the 4x4 iso matrix whose first column is v (real iso of an SU(2) element)
 RBQ_DEV void iso_from_column(const double* v, double* E) {
     E[0] = v[0];  E[1] = -v[1]; E[2] = -v[2];  E[3] = -v[3];
@@ -462,7 +554,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
         for (int ti = 0; ti < pipe.ntiles; ++ti) {
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
-            if (cls < 0) delta_tile<SPT, UNR>(tile, len, p, qd, qd2, e0, v);
+            if (cls < 0) {
+                if constexpr (SPT == 1 && RBQ_DELTA_PHASED) delta_tile_phased<RBQ_DELTA_U>(tile, len, p[0], qd[0], qd2[0], e0[0], v[0], 1 - a.no_table_class);
+                else delta_tile<SPT, UNR>(tile, len, p, qd, qd2, e0, v);
+            }
             else if (cls == 0) tan_tile<RBQ_TANA_DEG, SPT, UNR>(tile, len, p, p2, qd, v, cfA);
             else if (cls == 1) tan_tile<RBQ_TANB_DEG, SPT, UNR>(tile, len, p, p2, qd, v, cfB);
             else if (cls == 2) su2_tile<8, SPT>(tile, len, p, p2, qd, v);
@@ -1678,11 +1773,13 @@ static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int*
     const int sm_count = h->sm_count;
     *spt = 1; *minb = 1; *threads = 256;
     if (algo != RBQ_ALGO_SU2) return;
-    int v = 171;   // measured best of the compiled variants (tools/tune_mc.py, tools/proto/bv.sh): 1 sample per thread, 128-thread blocks, 7 per SM
+    // measured best of the compiled variants (tools/tune_mc.py): 1 sample per thread, 128-thread blocks, 6 per SM (80 registers: at
+    // 72 the scheduler interleaves the updates of neighbouring knots and loses the operand reuse, 1.169 against 1.070 ms)
+    int v = 161;
     if (h->opt.mc_variant > 0) v = h->opt.mc_variant;
     *spt = v / 100; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
     const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 7 || *minb == 8)));
-    if (!ok) { *spt = 1; *minb = 7; *threads = 128; }
+    if (!ok) { *spt = 1; *minb = 6; *threads = 128; }
     // small sweeps: one sample per thread so that every SM gets blocks
     if (S < (int64_t)sm_count * 4 * *threads * *spt) *spt = 1;
 }
@@ -1729,7 +1826,7 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
         case 212: RBQ_GO(2, 1, 256); break; case 222: RBQ_GO(2, 2, 256); break; case 232: RBQ_GO(2, 3, 256); break; case 242: RBQ_GO(2, 4, 256); break;
         case 141: RBQ_GO(1, 4, 128); break; case 161: RBQ_GO(1, 6, 128); break; case 171: RBQ_GO(1, 7, 128); break; case 181: RBQ_GO(1, 8, 128); break;
         case 241: RBQ_GO(2, 4, 128); break; case 261: RBQ_GO(2, 6, 128); break; case 281: RBQ_GO(2, 8, 128); break;
-        default: RBQ_GO(1, 7, 128); break;
+        default: RBQ_GO(1, 6, 128); break;
         }
     } else if (algo == RBQ_ALGO_PADE) {
         mc_static_kernel<RBQ_ALGO_PADE, 1, 1, 256><<<blocks, 256, 0, h->stream>>>(a);
