@@ -114,7 +114,7 @@ static bool make_gate_tables(int gate, GateIso* gi, GateRot* gr) {
 static const char* const kOptionNames[] = {"RBQ_NO_TABLE_CLASS", "RBQ_MC_ZEROCOPY", "RBQ_MC_CHUNK_WAVES", "RBQ_MC_VARIANT", "RBQ_PEAK_MODE",
                                            "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_LINDBLAD_SPT",
                                            "RBQ_ROLLOUT_PACKED", "RBQ_ROLLOUT_SCAN", "RBQ_JAC_NT_UNSCENTED", "RBQ_JAC_STRUCTURED",
-                                           "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED", "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS"};
+                                           "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED", "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS", "RBQ_BP_CLUSTER"};
 int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
     const bool unset = !value || !*value;
     const int v = unset ? -1 : atoi(value);
@@ -144,6 +144,7 @@ int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
     else if (is("RBQ_BP_TMA")) h->opt.bp_tma = v;
     else if (is("RBQ_BP_GENERIC")) h->opt.bp_generic = unset ? 0 : (v != 0);
     else if (is("RBQ_BP_WARPS")) h->opt.bp_warps = v;
+    else if (is("RBQ_BP_CLUSTER")) h->opt.bp_cluster = unset ? 0 : v;
     else return RBQ_E_NULL;
     return RBQ_OK;
 }

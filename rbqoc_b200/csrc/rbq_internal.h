@@ -45,6 +45,7 @@ struct rbq_handle {
         int bp_tma;                // RBQ_BP_TMA              staging mode mask of the backward pass
         int bp_generic;            // RBQ_BP_GENERIC          1: any-shape kernels only
         int bp_warps;              // RBQ_BP_WARPS            1 / 8 force warp-per-problem or block-per-problem
+        int bp_cluster;            // RBQ_BP_CLUSTER          1 / 2 / 4 CTAs per problem (reference shapes n = 43, 56, 58 with one control)
     } opt;
 };
 // option parsing shared by rbq_create (environment) and rbq_set_option; value NULL or "" restores the default

@@ -36,6 +36,18 @@ RBQ_DEV void cp_async16(double* smem_dst, const double* gsrc) {
 RBQ_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 RBQ_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// thread-block cluster primitives (CL > 1: one problem split over the column strips of CL CTAs, see backward_pass_kernel)
+RBQ_DEV uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+RBQ_DEV uint32_t cluster_map(const void* local, uint32_t rank) {          // address of the same variable in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+RBQ_DEV void st_cluster(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+RBQ_DEV void st_cluster(uint32_t addr, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+RBQ_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+RBQ_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // phase timing for tuning (make EXTRA=-DRBQ_BP_PROFILE; read with rbq_debug_bp_prof): cycles of thread 0 between barriers
 #ifdef RBQ_BP_PROFILE
 __device__ long long g_bp_prof[16];
@@ -73,7 +85,21 @@ constexpr int BP_GSLOTS = 8;           // tiles of the second product per warp: 
 template <int NW_> RBQ_DEV void bp_sync() { if (NW_ == 1) __syncwarp(); else __syncthreads(); }
 template <int NW_> RBQ_DEV bool bp_sync_or(bool pred) { return NW_ == 1 ? __any_sync(0xffffffffu, pred) != 0 : __syncthreads_or(pred) != 0; }
 
-template <int NW, int MODE, int MM, int NN>
+// tiles of the second product one warp of a CL-CTA cluster has to run (the largest share over the ranks): CTA `rank` owns the
+// column strips rank, rank + CL, ...; a strip jt has its lower tiles (ctiles - jt) plus, for the strip that holds the gradient
+// column, the jtc tiles above the diagonal
+__host__ __device__ constexpr int bp_cluster_gslots(int n, int m, int cl, int nw) {
+    const int ctiles = ((n + m + 8) & ~7) / 8, jtc = (n + m) >> 3;
+    int worst = 0;
+    for (int r = 0; r < cl; ++r) {
+        int cnt = 0;
+        for (int jt = r; jt < ctiles; jt += cl) cnt += ctiles - jt + (jt == jtc ? jtc : 0);
+        worst = cnt > worst ? cnt : worst;
+    }
+    return (worst + nw - 1) / nw;
+}
+
+template <int NW, int MODE, int MM, int NN, int CL = 1>
 // two problems per SM where the shared memory allows it (n <= 44: under 100 KB each): batches of mid-size problems then run
 // two per SM at a time, which needs the kernel within 128 registers
 __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 2 : 1)) backward_pass_kernel(const BackwardArgs a) {
@@ -85,7 +111,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     const int n = NN ? NN : a.n, m = MM ? MM : a.m, nm = n + m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n4 = up4(n), n8 = up8(n), q8 = up8(nm + 1), ld = n8 + 4, ldg = q8 + 4;
     const int cs = nm;                 // spare column: G(:, cs) = [A B]' s + e, i.e. the gradient g rides in the second product
-    const int64_t N = a.N, b = blockIdx.x;
+    // CL > 1 (shape-specialised, one control): the problem is split over a cluster of CL CTAs.  Every CTA holds all of S, s and
+    // [A B]; CTA `rank` computes the column strips rank, rank + CL, ... of T and of G (the lower tiles; the strip with the
+    // gradient column also above the diagonal), the owner of that strip computes the gains and sends K, Quu K and Qxu to the
+    // others, every CTA updates the entries of S below its strips' diagonal and writes them, mirrored, into every copy of S
+    // through distributed shared memory.  Two cluster barriers per knot.
+    static_assert(CL == 1 || (NN != 0 && MM == 1 && NW > 1), "cluster form: specialised shapes with one control");
+    const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
+    const int64_t N = a.N, b = blockIdx.x / CL;
     double* S = sm;                    // S(r, kk) at kk * ld + r   (symmetric)
     double* sv = S + ld * n4;
     double* AB = sv + n8;              // [A B](kk, c) at c * ld + kk
@@ -95,9 +128,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     double* Kk = G + ldg * q8;         // K(p, j) at j * m + p
     double* QuuK = Kk + BP_MAX_M * n8;
     double* dk = QuuK + BP_MAX_M * n8;
-    double* Qd = dk + BP_MAX_M;        // dense landing zone of the cost Hessian block: n*n + 2 doubles, 16-byte aligned
+    double* Hq = dk + BP_MAX_M;        // Qxu as received from the CTA that computed it (cluster form)
+    double* Qd = Hq + n8;              // dense landing zone of the cost Hessian block: n*n + 2 doubles, 16-byte aligned
     __shared__ double dv_s[2];
     __shared__ __align__(8) uint64_t bar_s[2];       // bulk-copy arrival: [0] Jacobian block, [1] cost Hessian block
+    __shared__ int fail_s;                           // cluster form: the owner's "Quu not positive definite" verdict
 
     const double* ABg = a.AB + b * (N - 1) * (int64_t)(n * nm);
     const double* Exxg = a.Exx + b * N * (int64_t)(n * n);
@@ -111,7 +146,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     // zero everything once (the padding is never written again), then the terminal value function
     const int total = ld * n4 + n8 + 2 * ld * q8 + ldg * q8;
     for (int i = tid; i < total; i += BP_THREADS) sm[i] = 0.0;
-    if (tid == BP_THREADS - 1) { dv_s[0] = 0.0; dv_s[1] = 0.0; mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_fence_init(); }
+    if (tid == BP_THREADS - 1) { fail_s = 0; dv_s[0] = 0.0; dv_s[1] = 0.0; mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_fence_init(); }
     bp_sync<NW>();
     for (int j = wid; j < n; j += NW)
         for (int i = lane; i < n; i += 32)
@@ -206,10 +241,18 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     const int fr = lane >> 2, fc = lane & 3;          // fragment coordinates of this lane
     // tiles of the second product dealt to this warp: the lower triangle row by row, then the tiles above the diagonal in
     // the strip jtc that holds the gradient column cs
-    const int jtc = cs >> 3, nlow = ctiles * (ctiles + 1) / 2, ntile = nlow + jtc;
+    const int jtc = cs >> 3, nlow = ctiles * (ctiles + 1) / 2;
+    const uint32_t owner = (uint32_t)jtc % CL;        // the CTA whose strips hold Qxu and the gradient
+    int ntile = nlow + jtc;
+    if (CL > 1) {
+        ntile = 0;
+        for (int jt = (int)rank; jt < ctiles; jt += CL) ntile += ctiles - jt + (jt == jtc ? jtc : 0);
+    }
     // every warp runs GC = ceil(ntile / NW) slots without predicates (GC is a constant in the shape-specialised kernels); a
     // warp that was dealt one tile fewer repeats its last one (same values stored twice), a warp without tiles sits out
-    const int gt0 = ntile * wid / NW, gcnt = ntile * (wid + 1) / NW - gt0, GC = (ntile + NW - 1) / NW;
+    const int gt0 = ntile * wid / NW, gcnt = ntile * (wid + 1) / NW - gt0;
+    constexpr int GC_CL = bp_cluster_gslots(NN, MM, CL, NW);
+    const int GC = CL > 1 ? GC_CL : (ntile + NW - 1) / NW;
     int gt_r[BP_GSLOTS], gt_c[BP_GSLOTS];
     const double* gt_a[BP_GSLOTS];
     const double* gt_b[BP_GSLOTS];
@@ -217,7 +260,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     for (int s_ = 0; s_ < BP_GSLOTS; ++s_) {
         int idx = gt0 + (s_ < gcnt ? s_ : gcnt - 1), t = 0, jt = 0;
         if (idx < 0) idx = 0;
-        if (idx >= nlow) { t = idx - nlow; jt = jtc; }
+        if (CL > 1) {                                   // own strips in turn: the lower tiles, then (strip jtc) the upper ones
+            for (jt = (int)rank; jt < ctiles; jt += CL) {
+                const int low = ctiles - jt, cnt = low + (jt == jtc ? jtc : 0);
+                if (idx < cnt) { t = idx < low ? jt + idx : idx - low; break; }
+                idx -= cnt;
+            }
+            if (jt >= ctiles) { jt = (int)rank; t = jt; }
+        } else if (idx >= nlow) { t = idx - nlow; jt = jtc; }
         else { while (idx > t) { idx -= t + 1; ++t; } jt = idx; }
         gt_r[s_] = t; gt_c[s_] = jt;
         gt_a[s_] = AB + (8 * t + fr) * lda + fc;
@@ -227,11 +277,23 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
 #ifdef RBQ_BP_PROFILE
     long long tprev = clock64();
 #endif
+    // cluster form: where S, s, K, Quu K, Qxu, d and the verdict live in the other CTAs
+    uint32_t rS[CL], rsv[CL], rKk[CL], rQuuK[CL], rHq[CL], rfail[CL];
+    if (CL > 1) {
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+            rS[c] = cluster_map(S, c); rsv[c] = cluster_map(sv, c); rKk[c] = cluster_map(Kk, c); rQuuK[c] = cluster_map(QuuK, c);
+            rHq[c] = cluster_map(Hq, c); rfail[c] = cluster_map(&fail_s, c);
+        }
+        cluster_arrive();                                           // pairs with the wait at the top of the first knot
+    }
+    bool arrived = CL > 1;
     uint32_t phase = 0;
     for (int64_t k = N - 2; k >= 0; --k, phase ^= 1u) {
         cp_async_wait_all();
         if (tma_j || dense_j) mbar_wait(&bar_s[0], phase);
-        bp_sync<NW>();                                             // AB_k, S, sv visible; G and g are free again
+        if (CL > 1) { cluster_wait(); arrived = false; }          // every copy of S and s complete (local and remote writes)
+        else bp_sync<NW>();                                        // AB_k, S, sv visible; G and g are free again
         BP_PROF(0)
         stage_cost(k);
         double ex0 = 0.0, ex1 = 0.0;
@@ -240,6 +302,32 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             if (tid + BP_THREADS < n_extra) ex1 = *extra_src(tid + BP_THREADS, k);
         }
         // ---- T = S [A B]: warp -> one 8-column strip, all row tiles; A fragments from S (symmetric), B fragments from [A B] ----
+        if constexpr (CL > 1) {
+            // own strips only; the warps left over split a strip's row tiles between them
+            constexpr int CT = ((NN + MM + 8) & ~7) / 8, RT = ((NN + 7) & ~7) / 8, OWN = (CT + CL - 1) / CL;
+            constexpr int RG = NW / OWN >= 1 ? NW / OWN : 1, TPI = (RT + RG - 1) / RG;
+            for (int item = wid; item < OWN * RG; item += NW) {
+                const int ct = (int)rank + CL * (item / RG), t0 = (item % RG) * TPI;
+                if (ct >= CT) continue;
+                double acc[TPI][2];
+#pragma unroll
+                for (int t = 0; t < TPI; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                const double* bp = AB + (8 * ct + fr) * lda + fc;
+                const double* ap = S + fc * ld + fr + 8 * t0;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const double bf = bp[4 * ks];
+#pragma unroll
+                    for (int t = 0; t < TPI; ++t)
+                        if (t0 + t < RT) dmma884(acc[t][0], acc[t][1], ap[4 * ks * ld + 8 * t], bf);
+                }
+#pragma unroll
+                for (int t = 0; t < TPI; ++t)
+                    if (t0 + t < RT) {
+                        T[(8 * ct + 2 * fc) * ld + 8 * (t0 + t) + fr] = acc[t][0];
+                        T[(8 * ct + 2 * fc + 1) * ld + 8 * (t0 + t) + fr] = acc[t][1];
+                    }
+            }
+        } else
         for (int ct = wid; ct < ctiles; ct += NW) {
             double acc[BP_MAX_TILES - 1][2];
 #pragma unroll
@@ -298,11 +386,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         }
         BP_PROF(2)
         BP_PROF(3)
-        bp_sync<NW>();
+        if (CL == 1 || rank == owner) bp_sync<NW>();               // (cluster form: only the owner's gains read G here)
         BP_PROF(4)
         // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
         bool ok = true;
-        if (m == 1 && tid <= n) {
+        if (CL > 1 && rank != owner) {
+            // the gains arrive from the owner
+        } else if (m == 1 && tid <= n) {
             // one control (every reference model but the time-optimal spin15): Quu_reg is a scalar, its "factorisation" one
             // reciprocal -- a much shorter dependent chain than the general path's sqrt, divisions and guarded loops
             const int j = tid;
@@ -325,6 +415,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             if (ok) {
                 if (j < n) { Kk[j] = x; Kg[k * (int64_t)n + j] = x; QuuK[j] = quu * x; }
                 else { dk[0] = x; dg[k] = x; }
+            }
+            if (CL > 1) {
+                const double qxu = j < n ? G[n * ldg + j] : 0.0;
+#pragma unroll
+                for (int c = 0; c < CL; ++c) {
+                    if (c == (int)rank) continue;
+                    if (!ok) st_cluster(rfail[c], 1);
+                    else if (j < n) { st_cluster(rKk[c] + 8 * j, x); st_cluster(rQuuK[c] + 8 * j, quu * x); st_cluster(rHq[c] + 8 * j, qxu); }
+                }
+                if (!ok) fail_s = 1;
             }
         } else if (tid <= n) {
             const int j = tid;
@@ -410,6 +510,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             }
         }
         BP_PROF(5)
+        if (CL > 1) {
+            cluster_arrive(); cluster_wait();                      // gains (or the verdict) visible in every CTA; G complete
+            if (fail_s) { bad = k; break; }
+        } else
         if (bp_sync_or<NW>(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
         BP_PROF(6)
         // the Jacobian block is no longer needed: fetch the next one behind the value update
@@ -420,6 +524,40 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         // contracts symmetric errors through the closed loop (A - BK) but maps an antisymmetric part as A' . A, which grows
         // whenever rho(A) > 1 -- without (S + S')/2 the rounding-level asymmetry of Qxx wrecks a 180-knot pass.  Lane -> row i (its K, Quu K and Qux entries stay in registers), the
         // warp walks the columns j (whose entries are warp-uniform broadcasts).
+        if constexpr (CL > 1) {
+            // entries on and below the diagonal of the own column strips (G(i, j) and its mirror are both local), written to
+            // (i, j) and (j, i) of every CTA's S: lane -> row, warp -> column
+            const double* hq = rank == owner ? G + n * ldg : Hq;
+            constexpr int CT = ((NN + MM + 8) & ~7) / 8, OWN = (CT + CL - 1) / CL;
+            double ki[2], qi[2], hi[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int i = lane + 32 * h2;
+                const bool on = i < n;
+                ki[h2] = on ? Kk[i] : 0.0; qi[h2] = on ? 0.5 * QuuK[i] : 0.0; hi[h2] = on ? hq[i] : 0.0;
+            }
+            for (int jj = wid; jj < 8 * OWN; jj += NW) {
+                const int j = 8 * ((int)rank + CL * (jj >> 3)) + (jj & 7);
+                if (j >= n) continue;
+                const double cj = fma(0.5, QuuK[j], hq[j]), kj = Kk[j];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int i = lane + 32 * h2;
+                    if (i < j || i >= n) continue;
+                    // inside a diagonal tile the two triangles were computed separately: average them; below it G(i, j) is the
+                    // value both triangles share (its mirror need not exist here: the strip of the gradient column is not mirrored)
+                    double v = G[j * ldg + i];
+                    if ((i >> 3) == (j >> 3)) v = 0.5 * (v + G[i * ldg + j]);
+                    v = fma(ki[h2], cj, v);                                    // K'(Quu K)/2 + K'Qux
+                    v = fma(kj, qi[h2] + hi[h2], v);                           // (Quu K)'K/2 + Qux'K
+#pragma unroll
+                    for (int c = 0; c < CL; ++c) {
+                        if (c == (int)rank) { S[j * ld + i] = v; S[i * ld + j] = v; }
+                        else { st_cluster(rS[c] + 8 * (j * ld + i), v); st_cluster(rS[c] + 8 * (i * ld + j), v); }
+                    }
+                }
+            }
+        } else
         for (int i = lane; i < n; i += 32) {
             double ki[BP_MAX_M], qi[BP_MAX_M], hi[BP_MAX_M];
 #pragma unroll
@@ -441,6 +579,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             }
         }
         BP_PROF(9)
+        if (CL == 1 || rank == owner)
         for (int i = BP_THREADS - 1 - tid; i < n; i += BP_THREADS) {   // dealt from the last thread down: the first warps carry the tail of the pass above
             double v = g[i];
             for (int p = 0; p < m; ++p) {
@@ -450,8 +589,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
                 v = fma(G[(n + p) * ldg + i], dk[p], v);                   // Qux' d
             }
             sv[i] = v;                                                    // sv is not read again before the next knot
+            if (CL > 1) {
+#pragma unroll
+                for (int c = 0; c < CL; ++c) if (c != (int)rank) st_cluster(rsv[c] + 8 * i, v);
+            }
         }
-        if (tid == BP_THREADS - 1) {
+        if (tid == BP_THREADS - 1 && (CL == 1 || rank == owner)) {
             double d0 = 0.0, d1 = 0.0;
             for (int p = 0; p < m; ++p) {
                 d0 = fma(dk[p], g[n + p], d0);
@@ -463,10 +606,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         }
         BP_PROF(7)
         // the barrier at the top of the loop orders these writes against the next knot's reads
+        if (CL > 1) { cluster_arrive(); arrived = true; }
     }
     cp_async_wait_all();
+    if (CL > 1 && arrived) cluster_wait();                         // nobody leaves while a peer may still write into its copy of S
     bp_sync<NW>();
-    if (tid == BP_THREADS - 1) {
+    if (tid == BP_THREADS - 1 && (CL == 1 || rank == owner)) {
         a.dV[2 * b] = dv_s[0]; a.dV[2 * b + 1] = dv_s[1];
         a.fail[b] = bad;
     }
@@ -474,7 +619,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
 
 size_t backward_pass_smem(int n, int m) {
     const size_t n4 = (size_t)((n + 3) & ~3), n8 = (size_t)((n + 7) & ~7), q8 = (size_t)((n + m + 8) & ~7), ld = n8 + 4, ldg = q8 + 4;
-    return sizeof(double) * (ld * n4 + n8 + 2 * ld * q8 + ldg * q8 + 2 * BP_MAX_M * n8 + BP_MAX_M + (size_t)n * n + 2);
+    return sizeof(double) * (ld * n4 + n8 + 2 * ld * q8 + ldg * q8 + 2 * BP_MAX_M * n8 + BP_MAX_M + n8 + (size_t)n * n + 2);
 }
 
 // staging mode for a problem shape and its buffers (see backward_pass_kernel); RBQ_BP_TMA masks the bits (0 = cp.async only)
@@ -491,13 +636,33 @@ static int bp_stage_mode(const rbq_handle* h, int n, int m, const double* d_AB, 
     return mode;
 }
 
-template <int NW, int MODE, int MM, int NN>
+template <int NW, int MODE, int MM, int NN, int CL = 1>
 static cudaError_t bp_launch2(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream) {
-    auto kern = backward_pass_kernel<NW, MODE, MM, NN>;
+    auto kern = backward_pass_kernel<NW, MODE, MM, NN, CL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)B, 32 * NW, smem, stream>>>(a);
-    return cudaGetLastError();
+    if constexpr (CL == 1) {
+        kern<<<(unsigned)B, 32 * NW, smem, stream>>>(a);
+        return cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(32 * NW); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, a);
+    }
+}
+// one problem (or a few) of a reference shape with one control: the cluster form, CL CTAs per problem
+template <int CL>
+static cudaError_t bp_launch_cluster(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream, int mode, bool* done) {
+    *done = true;
+    if (mode == (BP_DENSE_J | BP_TMA_C) && a.n == 43) return bp_launch2<BP_WARPS_LARGE, BP_DENSE_J | BP_TMA_C, 1, 43, CL>(a, B, smem, stream);
+    if (mode == (BP_TMA_J | BP_TMA_C) && a.n == 56) return bp_launch2<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C, 1, 56, CL>(a, B, smem, stream);
+    if (mode == (BP_TMA_J | BP_TMA_C) && a.n == 58) return bp_launch2<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C, 1, 58, CL>(a, B, smem, stream);
+    *done = false;
+    return cudaSuccess;
 }
 // the shapes of the reference models (n = 11, 12, 15, 19, 43, 56, 58 with one control) get kernels with n known at compile time: tile
 // loops fully unrolled, constant strides.  RBQ_BP_GENERIC=1 forces the any-shape kernels (tests compare the two).
@@ -544,7 +709,17 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     bool small = n <= 16 && B > 2 * (int64_t)h->sm_count;
     if (h->opt.bp_warps > 0) small = n <= 16 && h->opt.bp_warps == 1;
     cudaError_t e;
-    if (small) {
+    // few large problems: split each over a cluster of CTAs (RBQ_BP_CLUSTER = 1 / 2 / 4 forces the size; default: as many
+    // CTAs per problem as keeps every problem resident at once, up to 4)
+    int cl = 1;
+    if (!small && m == 1 && !h->opt.bp_generic && (n == 43 || n == 56 || n == 58)) {
+        cl = h->opt.bp_cluster > 0 ? h->opt.bp_cluster : (4 * B <= h->sm_count ? 4 : (2 * B <= h->sm_count ? 2 : 1));
+    }
+    bool done = false;
+    if (cl == 2) e = bp_launch_cluster<2>(a, B, smem, h->stream, bp_stage_mode(h, n, m, d_AB, d_Exx), &done);
+    else if (cl == 4) e = bp_launch_cluster<4>(a, B, smem, h->stream, bp_stage_mode(h, n, m, d_AB, d_Exx), &done);
+    if (done) {
+    } else if (small) {
         e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream, !h->opt.bp_generic);
     } else {
         switch (bp_stage_mode(h, n, m, d_AB, d_Exx)) {

@@ -151,3 +151,39 @@ def test_backward_pass_dev_unaligned_buffers_fall_back(engine):
     Kh = K.cpu().numpy().reshape(N - 1, n, m).swapaxes(-1, -2)
     assert _rel(Kh, Kr) < 1e-10 and _rel(d.cpu().numpy().reshape(N - 1, m), dr) < 1e-10
     assert np.allclose(dV.cpu().numpy(), dVr, rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,N", [(43, 61), (56, 47), (58, 33)])
+@pytest.mark.parametrize("reg", [rbq.REG_CONTROL, rbq.REG_STATE], ids=["control_reg", "state_reg"])
+def test_backward_pass_cluster_form_matches_oracle_and_single_cta(engine, n, N, reg):
+    """Few large problems run as a cluster of 2 or 4 CTAs per problem (column strips of T and G split over the CTAs, S kept
+    in every CTA and updated through distributed shared memory).  Same recursion: every cluster size agrees with the oracle at
+    the usual 1e-10 and with the one-CTA kernel to rounding; a failing knot is reported by every form."""
+    from oracle import riccati
+
+    rng = np.random.default_rng(4000 + n)
+    probs = [_lq_problem(rng, N, n, 1) for _ in range(3)]
+    stack = lambda i: np.stack([p[i] for p in probs])
+    AB, Q, q, R, Eux, r = (stack(i) for i in (2, 3, 4, 5, 6, 8))
+    ref = [riccati.backward_pass(p[2], p[3], p[4], p[5], p[6], p[8], rho=0.23, reg_type=reg) for p in probs]
+    outs = {}
+    for cl in ("1", "2", "4"):
+        engine.set_option("RBQ_BP_CLUSTER", cl)
+        outs[cl] = engine.backward_pass(AB, Q, q, R, Eux, r, rho=0.23, reg_type=reg)
+    engine.set_option("RBQ_BP_CLUSTER", None)
+    auto = engine.backward_pass(AB[0], Q[0], q[0], R[0], Eux[0], r[0], rho=0.23, reg_type=reg)      # one problem: the default picks a cluster
+    assert auto[3] == -1 and _rel(auto[0], ref[0][0]) < 1e-10 and _rel(auto[1], ref[0][1]) < 1e-10
+    for cl, (K, d, dV, fail) in outs.items():
+        assert list(fail) == [-1] * 3, cl
+        for b, (Kr, dr, dVr, fr) in enumerate(ref):
+            assert _rel(K[b], Kr) < 1e-10 and _rel(d[b], dr) < 1e-10 and np.allclose(dV[b], dVr, rtol=1e-10), (cl, b)
+        assert _rel(K, outs["1"][0]) < 1e-11
+    R2 = R.copy(); R2[1, N // 2] = -1e12
+    failr = riccati.backward_pass(AB[1], Q[1], q[1], R2[1], Eux[1], r[1], rho=0.23, reg_type=reg)[3]
+    assert failr == N // 2
+    for cl in ("1", "2", "4"):
+        engine.set_option("RBQ_BP_CLUSTER", cl)
+        K, d, dV, fail = engine.backward_pass(AB, Q, q, R2, Eux, r, rho=0.23, reg_type=reg)
+        assert list(fail) == [-1, failr, -1], cl
+        assert _rel(K[1, failr + 1:], outs["1"][0][1, failr + 1:]) < 1e-11
+    engine.set_option("RBQ_BP_CLUSTER", None)
