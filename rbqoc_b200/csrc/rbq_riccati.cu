@@ -45,13 +45,20 @@ RBQ_DEV uint32_t cluster_map(const void* local, uint32_t rank) {          // add
 }
 RBQ_DEV void st_cluster(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 RBQ_DEV void st_cluster(uint32_t addr, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// bulk copy from this CTA's shared memory into a peer's, completing bytes on the peer's mbarrier (both cluster addresses)
+RBQ_DEV void bulk_s2peer(uint32_t dst_cluster, const void* src, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+                 "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+RBQ_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 RBQ_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 RBQ_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // phase timing for tuning (make EXTRA=-DRBQ_BP_PROFILE; read with rbq_debug_bp_prof): cycles of thread 0 between barriers
 #ifdef RBQ_BP_PROFILE
-__device__ long long g_bp_prof[16];
-#define BP_PROF(i) if (tid == 0) { long long c_ = clock64(); g_bp_prof[i] += c_ - tprev; tprev = c_; }
+__device__ long long g_bp_prof[32];       // [0, 16): the first CTA of a problem, [16, 32): the CTA that computes the gains (cluster form)
+#define BP_PROF(i) if (tid == 0 && (rank == 0 || rank == owner)) { long long c_ = clock64(); g_bp_prof[(rank == 0 ? 0 : 16) + i] += c_ - tprev; tprev = c_; }
 #else
 #define BP_PROF(i)
 #endif
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     __shared__ double dv_s[2];
     __shared__ __align__(8) uint64_t bar_s[2];       // bulk-copy arrival: [0] Jacobian block, [1] cost Hessian block
     __shared__ int fail_s;                           // cluster form: the owner's "Quu not positive definite" verdict
+    __shared__ __align__(8) uint64_t bar_x;          // cluster form: arrival of the other CTAs' parts of S (and of s)
 
     const double* ABg = a.AB + b * (N - 1) * (int64_t)(n * nm);
     const double* Exxg = a.Exx + b * N * (int64_t)(n * n);
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     // zero everything once (the padding is never written again), then the terminal value function
     const int total = ld * n4 + n8 + 2 * ld * q8 + ldg * q8;
     for (int i = tid; i < total; i += BP_THREADS) sm[i] = 0.0;
-    if (tid == BP_THREADS - 1) { fail_s = 0; dv_s[0] = 0.0; dv_s[1] = 0.0; mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_fence_init(); }
+    if (tid == BP_THREADS - 1) { fail_s = 0; dv_s[0] = 0.0; dv_s[1] = 0.0; mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(&bar_x, 1); mbar_fence_init(); }
     bp_sync<NW>();
     for (int j = wid; j < n; j += NW)
         for (int i = lane; i < n; i += 32)
@@ -278,21 +286,50 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
     long long tprev = clock64();
 #endif
     // cluster form: where S, s, K, Quu K, Qxu, d and the verdict live in the other CTAs
-    uint32_t rS[CL], rsv[CL], rKk[CL], rQuuK[CL], rHq[CL], rfail[CL];
+    uint32_t rS[CL], rsv[CL], rKk[CL], rQuuK[CL], rHq[CL], rfail[CL], rbar[CL];
+    uint32_t inbound = 0, xphase = 0;                               // bytes of S and s the other CTAs send per knot
     if (CL > 1) {
 #pragma unroll
         for (int c = 0; c < CL; ++c) {
             rS[c] = cluster_map(S, c); rsv[c] = cluster_map(sv, c); rKk[c] = cluster_map(Kk, c); rQuuK[c] = cluster_map(QuuK, c);
-            rHq[c] = cluster_map(Hq, c); rfail[c] = cluster_map(&fail_s, c);
+            rHq[c] = cluster_map(Hq, c); rfail[c] = cluster_map(&fail_s, c); rbar[c] = cluster_map(&bar_x, c);
         }
-        cluster_arrive();                                           // pairs with the wait at the top of the first knot
+        for (int j = 0; j < n; ++j)
+            if ((uint32_t)(j >> 3) % CL != rank) inbound += (uint32_t)((n8 - (j & ~1)) * sizeof(double));
+        if (rank != owner) inbound += (uint32_t)(n8 * sizeof(double));
+        cluster_arrive(); cluster_wait();                           // every CTA's shared memory is initialised
     }
-    bool arrived = CL > 1;
     uint32_t phase = 0;
     for (int64_t k = N - 2; k >= 0; --k, phase ^= 1u) {
         cp_async_wait_all();
         if (tma_j || dense_j) mbar_wait(&bar_s[0], phase);
-        if (CL > 1) { cluster_wait(); arrived = false; }          // every copy of S and s complete (local and remote writes)
+        if constexpr (CL > 1) {
+            // the CTAs exchange the lower triangle of S column by column (bulk copies between shared memories, landing on
+            // bar_x) and each mirrors it into the upper one itself, tile by tile (lane -> 8 rows x 4 columns: 2-way conflicts)
+            if (k < N - 2) { mbar_wait(&bar_x, xphase); xphase ^= 1u; }
+            BP_PROF(11)
+            constexpr int RT_ = ((NN + 7) & ~7) / 8, NT_ = RT_ * (RT_ + 1) / 2, PER_ = (NT_ + NW - 1) / NW;
+            double mv[PER_][2];
+            int mt[PER_][2];
+#pragma unroll
+            for (int u = 0; u < PER_; ++u) {
+                int idx = wid + NW * u, ti = 0;
+                if (idx >= NT_) idx = NT_ - 1;                      // (a repeated tile rewrites the same values)
+                while (idx > ti) { idx -= ti + 1; ++ti; }
+                mt[u][0] = ti; mt[u][1] = idx;                      // tile row ti >= tile column idx
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+                    mv[u][h2] = S[(8 * idx + (lane >> 3) + 4 * h2) * ld + 8 * ti + (lane & 7)];
+            }
+#pragma unroll
+            for (int u = 0; u < PER_; ++u)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = 8 * mt[u][0] + (lane & 7), c = 8 * mt[u][1] + (lane >> 3) + 4 * h2;
+                    if (r > c && r < n) S[r * ld + c] = mv[u][h2];          // (S has n4 columns: nothing beyond row n is mirrored)
+                }
+            __syncthreads();
+        }
         else bp_sync<NW>();                                        // AB_k, S, sv visible; G and g are free again
         BP_PROF(0)
         stage_cost(k);
@@ -391,7 +428,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
         bool ok = true;
         if (CL > 1 && rank != owner) {
-            // the gains arrive from the owner
+            // the gains arrive from the owner; meanwhile fetch the next Jacobian block (this CTA is done reading the current one)
+            __syncthreads();
+            if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
         } else if (m == 1 && tid <= n) {
             // one control (every reference model but the time-optimal spin15): Quu_reg is a scalar, its "factorisation" one
             // reciprocal -- a much shorter dependent chain than the general path's sqrt, divisions and guarded loops
@@ -512,12 +551,17 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         BP_PROF(5)
         if (CL > 1) {
             cluster_arrive(); cluster_wait();                      // gains (or the verdict) visible in every CTA; G complete
-            if (fail_s) { bad = k; break; }
+            if (fail_s) {
+                bad = k;
+                // (the other CTAs already asked for the next Jacobian block: let it land before leaving)
+                if (rank != owner && k > 0 && (tma_j || dense_j)) mbar_wait(&bar_s[0], phase ^ 1u);
+                break;
+            }
         } else
         if (bp_sync_or<NW>(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
         BP_PROF(6)
         // the Jacobian block is no longer needed: fetch the next one behind the value update
-        if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
+        if (CL == 1 || rank == owner) { if (k > 0) stage_jacobian(k - 1); else cp_async_commit(); }
         BP_PROF(8)
         // ---- value update: V = Qxx + sym(K'Quu K + K'Qux + Qux'K) into the scratch, then S = (V + V')/2 ----
         // S = sym(Qxx) + sym(K'Quu K + K'Qux + Qux'K), written in one pass.  The symmetrisation is not cosmetic: the recursion
@@ -525,8 +569,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         // whenever rho(A) > 1 -- without (S + S')/2 the rounding-level asymmetry of Qxx wrecks a 180-knot pass.  Lane -> row i (its K, Quu K and Qux entries stay in registers), the
         // warp walks the columns j (whose entries are warp-uniform broadcasts).
         if constexpr (CL > 1) {
-            // entries on and below the diagonal of the own column strips (G(i, j) and its mirror are both local), written to
-            // (i, j) and (j, i) of every CTA's S: lane -> row, warp -> column
+            // entries on and below the diagonal of the own column strips: lane -> row, warp -> column.  They are sent to the other
+            // CTAs below; the upper triangle is mirrored by each CTA at the top of the next knot
             const double* hq = rank == owner ? G + n * ldg : Hq;
             constexpr int CT = ((NN + MM + 8) & ~7) / 8, OWN = (CT + CL - 1) / CL;
             double ki[2], qi[2], hi[2];
@@ -550,11 +594,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
                     if ((i >> 3) == (j >> 3)) v = 0.5 * (v + G[i * ldg + j]);
                     v = fma(ki[h2], cj, v);                                    // K'(Quu K)/2 + K'Qux
                     v = fma(kj, qi[h2] + hi[h2], v);                           // (Quu K)'K/2 + Qux'K
-#pragma unroll
-                    for (int c = 0; c < CL; ++c) {
-                        if (c == (int)rank) { S[j * ld + i] = v; S[i * ld + j] = v; }
-                        else { st_cluster(rS[c] + 8 * (j * ld + i), v); st_cluster(rS[c] + 8 * (i * ld + j), v); }
-                    }
+                    S[j * ld + i] = v;
+                    if ((i >> 3) == (j >> 3)) S[i * ld + j] = v;               // (a column is sent from an even row: keep the diagonal tile whole)
                 }
             }
         } else
@@ -589,10 +630,6 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
                 v = fma(G[(n + p) * ldg + i], dk[p], v);                   // Qux' d
             }
             sv[i] = v;                                                    // sv is not read again before the next knot
-            if (CL > 1) {
-#pragma unroll
-                for (int c = 0; c < CL; ++c) if (c != (int)rank) st_cluster(rsv[c] + 8 * i, v);
-            }
         }
         if (tid == BP_THREADS - 1 && (CL == 1 || rank == owner)) {
             double d0 = 0.0, d1 = 0.0;
@@ -606,10 +643,25 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         }
         BP_PROF(7)
         // the barrier at the top of the loop orders these writes against the next knot's reads
-        if (CL > 1) { cluster_arrive(); arrived = true; }
+        if (CL > 1 && k > 0) {
+            // send the own columns of S (from the even row at or above the diagonal down to the padding) and, from the owner,
+            // s to every other CTA: one bulk copy each, dealt over the lanes of all warps; the receivers wait on their bar_x
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) mbar_expect_tx(&bar_x, inbound);
+            constexpr int CT = ((NN + MM + 8) & ~7) / 8, OWN = (CT + CL - 1) / CL;
+            const int ncopy = (8 * OWN + (rank == owner ? 1 : 0)) * (CL - 1);
+            for (int cidx = wid + NW * lane; cidx < ncopy; cidx += NW * 32) {
+                const int jj = cidx / (CL - 1), pc = cidx % (CL - 1), peer = pc + (pc >= (int)rank ? 1 : 0);
+                if (jj == 8 * OWN) { bulk_s2peer(rsv[peer], sv, (uint32_t)(n8 * sizeof(double)), rbar[peer]); continue; }
+                const int j = 8 * ((int)rank + CL * (jj >> 3)) + (jj & 7);
+                if (j >= n) continue;
+                const int off = j * ld + (j & ~1);
+                bulk_s2peer(rS[peer] + 8 * off, S + off, (uint32_t)((n8 - (j & ~1)) * sizeof(double)), rbar[peer]);
+            }
+        }
     }
     cp_async_wait_all();
-    if (CL > 1 && arrived) cluster_wait();                         // nobody leaves while a peer may still write into its copy of S
     bp_sync<NW>();
     if (tid == BP_THREADS - 1 && (CL == 1 || rank == owner)) {
         a.dV[2 * b] = dv_s[0]; a.dV[2 * b + 1] = dv_s[1];
@@ -713,7 +765,8 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     // CTAs per problem as keeps every problem resident at once, up to 4)
     int cl = 1;
     if (!small && m == 1 && !h->opt.bp_generic && (n == 43 || n == 56 || n == 58)) {
-        cl = h->opt.bp_cluster > 0 ? h->opt.bp_cluster : (4 * B <= h->sm_count ? 4 : (2 * B <= h->sm_count ? 2 : 1));
+        // (clusters of 4 fit 132 of the 148 SMs: 33 problems at a time)
+        cl = h->opt.bp_cluster > 0 ? h->opt.bp_cluster : (4 * B <= h->sm_count - 20 ? 4 : (2 * B <= h->sm_count ? 2 : 1));
     }
     bool done = false;
     if (cl == 2) e = bp_launch_cluster<2>(a, B, smem, h->stream, bp_stage_mode(h, n, m, d_AB, d_Exx), &done);
@@ -736,8 +789,8 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
 }  // namespace rbq
 #ifdef RBQ_BP_PROFILE
 extern "C" int rbq_debug_bp_prof(long long* out, int reset) {
-    cudaMemcpyFromSymbol(out, rbq::g_bp_prof, sizeof(long long) * 16);
-    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(rbq::g_bp_prof, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out, rbq::g_bp_prof, sizeof(long long) * 32);
+    if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(rbq::g_bp_prof, z, sizeof(z)); }
     return 0;
 }
 #endif

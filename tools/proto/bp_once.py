@@ -24,11 +24,14 @@ print("n", n, "us per knot (best of 10)", best * 1e3 / (N - 1), "fail", fl.tolis
 
 if hasattr(eng._lib, "rbq_debug_bp_prof"):
     import ctypes as C
-    buf = (C.c_longlong * 16)()
+    buf = (C.c_longlong * 32)()
     eng._lib.rbq_debug_bp_prof(buf, 1)
     eng.backward_pass_dev(n, m, N, B, AB, Exx, Ex, Euu, Eux, Eu, 1e-3, 0, K, dd, dV, fl); torch.cuda.synchronize()
     eng._lib.rbq_debug_bp_prof(buf, 0)
-    names = ["wait AB + sync", "T = S AB", "G tiles (thread 0)", "g rows (thread 0)", "barrier", "gains", "barrier_or", "symmetrise", "stage next jacobian", "V pass", "sv/dV (other threads)", "barrier"]
-    tot = sum(buf[:12])
-    for i in range(12): print(f"  {names[i]:20s} {buf[i] / (N - 1):9.0f} cycles/knot  {100 * buf[i] / tot:5.1f}%")
-    print("  total cycles/knot", tot / (N - 1))
+    names = ["wait AB + sync/mirror", "T = S AB", "G tiles (thread 0)", "g rows (thread 0)", "barrier", "gains", "barrier_or", "symmetrise", "stage next jacobian", "V pass", "sv/dV (other threads)", "cluster wait (top)"]
+    for off, who in ((0, "first CTA"), (16, "gains CTA (cluster form)")):
+        tot = sum(buf[off:off + 12])
+        if tot == 0: continue
+        print(" ", who)
+        for i in range(12): print(f"  {names[i]:20s} {buf[off + i] / (N - 1):9.0f} cycles/knot  {100 * buf[off + i] / tot:5.1f}%")
+        print("  total cycles/knot", tot / (N - 1))
