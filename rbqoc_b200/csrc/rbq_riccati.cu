@@ -299,6 +299,21 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         if (rank != owner) inbound += (uint32_t)(n8 * sizeof(double));
         cluster_arrive(); cluster_wait();                           // every CTA's shared memory is initialised
     }
+    // cluster form: the tiles of S this warp mirrors at the top of a knot (source and destination offsets of its two elements)
+    constexpr int MIR_RT = ((NN + 7) & ~7) / 8, MIR_NT = MIR_RT * (MIR_RT + 1) / 2, MIR_PER = CL > 1 ? (MIR_NT + NW - 1) / NW : 0;
+    int mir_src[MIR_PER > 0 ? MIR_PER : 1], mir_dst[MIR_PER > 0 ? MIR_PER : 1][2];
+#pragma unroll
+    for (int u = 0; u < MIR_PER; ++u) {
+        int idx = wid + NW * u, ti = 0;
+        if (idx >= MIR_NT) idx = MIR_NT - 1;                        // (a repeated tile rewrites the same values)
+        while (idx > ti) { idx -= ti + 1; ++ti; }                   // tile row ti >= tile column idx
+        mir_src[u] = (8 * idx + (lane >> 3)) * ld + 8 * ti + (lane & 7);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int r = 8 * ti + (lane & 7), c = 8 * idx + (lane >> 3) + 4 * h2;
+            mir_dst[u][h2] = (r > c && r < n) ? r * ld + c : -1;    // (S has n4 columns: nothing beyond row n is mirrored)
+        }
+    }
     uint32_t phase = 0;
     for (int64_t k = N - 2; k >= 0; --k, phase ^= 1u) {
         cp_async_wait_all();
@@ -308,26 +323,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             // bar_x) and each mirrors it into the upper one itself, tile by tile (lane -> 8 rows x 4 columns: 2-way conflicts)
             if (k < N - 2) { mbar_wait(&bar_x, xphase); xphase ^= 1u; }
             BP_PROF(11)
-            constexpr int RT_ = ((NN + 7) & ~7) / 8, NT_ = RT_ * (RT_ + 1) / 2, PER_ = (NT_ + NW - 1) / NW;
-            double mv[PER_][2];
-            int mt[PER_][2];
+            double mv[MIR_PER > 0 ? MIR_PER : 1][2];
 #pragma unroll
-            for (int u = 0; u < PER_; ++u) {
-                int idx = wid + NW * u, ti = 0;
-                if (idx >= NT_) idx = NT_ - 1;                      // (a repeated tile rewrites the same values)
-                while (idx > ti) { idx -= ti + 1; ++ti; }
-                mt[u][0] = ti; mt[u][1] = idx;                      // tile row ti >= tile column idx
+            for (int u = 0; u < MIR_PER; ++u)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) mv[u][h2] = S[mir_src[u] + 4 * h2 * ld];
+#pragma unroll
+            for (int u = 0; u < MIR_PER; ++u)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2)
-                    mv[u][h2] = S[(8 * idx + (lane >> 3) + 4 * h2) * ld + 8 * ti + (lane & 7)];
-            }
-#pragma unroll
-            for (int u = 0; u < PER_; ++u)
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int r = 8 * mt[u][0] + (lane & 7), c = 8 * mt[u][1] + (lane >> 3) + 4 * h2;
-                    if (r > c && r < n) S[r * ld + c] = mv[u][h2];          // (S has n4 columns: nothing beyond row n is mirrored)
-                }
+                    if (mir_dst[u][h2] >= 0) S[mir_dst[u][h2]] = mv[u][h2];
             __syncthreads();
         }
         else bp_sync<NW>();                                        // AB_k, S, sv visible; G and g are free again
@@ -346,22 +351,30 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             for (int item = wid; item < OWN * RG; item += NW) {
                 const int ct = (int)rank + CL * (item / RG), t0 = (item % RG) * TPI;
                 if (ct >= CT) continue;
-                double acc[TPI][2];
+                // a warp has only TPI tiles: two accumulator chains per tile (even and odd contraction steps), or the
+                // dependent DMMAs of one chain would set the pace
+                double acc[2][TPI][2];
 #pragma unroll
-                for (int t = 0; t < TPI; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                for (int t = 0; t < TPI; ++t) { acc[0][t][0] = 0.0; acc[0][t][1] = 0.0; acc[1][t][0] = 0.0; acc[1][t][1] = 0.0; }
                 const double* bp = AB + (8 * ct + fr) * lda + fc;
                 const double* ap = S + fc * ld + fr + 8 * t0;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const double bf = bp[4 * ks];
+                for (int ks = 0; ks < ksteps; ks += 2) {
+                    const double bf0 = bp[4 * ks];
 #pragma unroll
                     for (int t = 0; t < TPI; ++t)
-                        if (t0 + t < RT) dmma884(acc[t][0], acc[t][1], ap[4 * ks * ld + 8 * t], bf);
+                        if (t0 + t < RT) dmma884(acc[0][t][0], acc[0][t][1], ap[4 * ks * ld + 8 * t], bf0);
+                    if (ks + 1 < ksteps) {
+                        const double bf1 = bp[4 * ks + 4];
+#pragma unroll
+                        for (int t = 0; t < TPI; ++t)
+                            if (t0 + t < RT) dmma884(acc[1][t][0], acc[1][t][1], ap[(4 * ks + 4) * ld + 8 * t], bf1);
+                    }
                 }
 #pragma unroll
                 for (int t = 0; t < TPI; ++t)
                     if (t0 + t < RT) {
-                        T[(8 * ct + 2 * fc) * ld + 8 * (t0 + t) + fr] = acc[t][0];
-                        T[(8 * ct + 2 * fc + 1) * ld + 8 * (t0 + t) + fr] = acc[t][1];
+                        T[(8 * ct + 2 * fc) * ld + 8 * (t0 + t) + fr] = acc[0][t][0] + acc[1][t][0];
+                        T[(8 * ct + 2 * fc + 1) * ld + 8 * (t0 + t) + fr] = acc[0][t][1] + acc[1][t][1];
                     }
             }
         } else
@@ -406,6 +419,24 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
                     const double* s1 = dq && c + 1 < n ? Qk + (c + 1) * n + r : G + (c + 1) * ldg + r;
                     acc[s_][0] = *s0; acc[s_][1] = *s1;
                 }
+            if (CL > 1) {
+                double acc2[BP_GSLOTS][2];                                         // second chain: the odd contraction steps
+#pragma unroll
+                for (int s_ = 0; s_ < BP_GSLOTS; ++s_) { acc2[s_][0] = 0.0; acc2[s_][1] = 0.0; }
+                for (int ks = 0; ks < ksteps; ks += 2) {
+#pragma unroll
+                    for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                        if (s_ < GC) dmma884(acc[s_][0], acc[s_][1], gt_a[s_][4 * ks], gt_b[s_][4 * ks]);
+                    if (ks + 1 < ksteps) {
+#pragma unroll
+                        for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                            if (s_ < GC) dmma884(acc2[s_][0], acc2[s_][1], gt_a[s_][4 * ks + 4], gt_b[s_][4 * ks + 4]);
+                    }
+                }
+#pragma unroll
+                for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
+                    if (s_ < GC) { acc[s_][0] += acc2[s_][0]; acc[s_][1] += acc2[s_][1]; }
+            } else
             for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
                 for (int s_ = 0; s_ < BP_GSLOTS; ++s_)
@@ -424,6 +455,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         BP_PROF(2)
         BP_PROF(3)
         if (CL == 1 || rank == owner) bp_sync<NW>();               // (cluster form: only the owner's gains read G here)
+        // cluster form: the CTAs that wait for the gains ask for the next Jacobian block meanwhile (the owner after the
+        // barrier: issuing the copies before its gains delays the barrier for everybody, 3.67 -> 3.84 us per knot at n = 56)
+        const bool early = CL > 1 && rank != owner;
         BP_PROF(4)
         // ---- gains: every thread factors the (tiny) regularised Quu itself, thread j solves for column j of K, thread n for d ----
         bool ok = true;
@@ -554,14 +588,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
             if (fail_s) {
                 bad = k;
                 // (the other CTAs already asked for the next Jacobian block: let it land before leaving)
-                if (rank != owner && k > 0 && (tma_j || dense_j)) mbar_wait(&bar_s[0], phase ^ 1u);
+                if (early && k > 0 && (tma_j || dense_j)) mbar_wait(&bar_s[0], phase ^ 1u);
                 break;
             }
         } else
         if (bp_sync_or<NW>(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
         BP_PROF(6)
         // the Jacobian block is no longer needed: fetch the next one behind the value update
-        if (CL == 1 || rank == owner) { if (k > 0) stage_jacobian(k - 1); else cp_async_commit(); }
+        if (!early) { if (k > 0) stage_jacobian(k - 1); else cp_async_commit(); }
         BP_PROF(8)
         // ---- value update: V = Qxx + sym(K'Quu K + K'Qux + Qux'K) into the scratch, then S = (V + V')/2 ----
         // S = sym(Qxx) + sym(K'Quu K + K'Qux + Qux'K), written in one pass.  The symmetrisation is not cosmetic: the recursion
