@@ -302,7 +302,16 @@ def measured_configs(eng, rbq, spin, torch, dev, stream, flush, orc, peaks, fp64
     dro = torch.empty(S, 8, dtype=torch.float64, device=dev)
     dst = torch.zeros(rbq.STATS_INT64_WORDS, dtype=torch.int64, device=dev)
     ms_l = dev_ms(lambda: eng.lindblad_dev(dcn, K1, 0.1, rbq.GATE_XPIBY2, 1, S, spin.FQ, dda, drho, rbq.LINDBLAD_T1, 0.0, 0.0, dfid, dro, dst))
-    e2e_l = host_ms(lambda: eng.lindblad(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h, rho0), reps=3)
+    # e2e: the C ABI with host buffers in its own layout, page-locked (7.2 MB up, 8 MB down inside the timed call); the pageable
+    # numpy form with the wrapper's transposes is reported beside it
+    p_da, p_vec = eng.pinned_empty(S), eng.pinned_empty((S, 8))
+    p_fid, p_ro = eng.pinned_empty((S, 2)), eng.pinned_empty((S, 8))
+    p_da[:] = da_h; p_vec[:] = vec
+    e2e_l = host_ms(lambda: eng.lindblad_into(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, p_da, p_vec, p_fid, p_ro), reps=5)
+    e2e_l_pageable = host_ms(lambda: eng.lindblad(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h, rho0), reps=3)
+    fid_chk, _, _ = eng.lindblad(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h[:64], rho0[:64])
+    if not np.array_equal(fid_chk, p_fid[:64]):
+        raise SystemExit("lindblad: the page-locked ABI call and the numpy wrapper disagree")
     Sc = 2000
     orc.set_num_threads(threads)
     cpu_l = cpu_ms(lambda: orc.lindblad_t1(controls, 0.1, rbq.GATE_XPIBY2, 1, spin.FQ, da_h[:Sc], rho0[:Sc], nthreads=threads), reps=2)
@@ -313,7 +322,8 @@ def measured_configs(eng, rbq, spin, torch, dev, stream, flush, orc, peaks, fp64
                     "1 gate, sqrt-fidelity + final density per realisation",
         "value": S * K1 / (ms_l * 1e-3), "unit": "density-steps/s", "ms": ms_l,
         "e2e": {"value": S * K1 / (e2e_l * 1e-3), "unit": "density-steps/s", "ms": e2e_l, "h2d_bytes": S * 72 + K1 * 8, "d2h_bytes": S * 80 + 2096,
-                "api": "rbq_lindblad (host pointers, pageable numpy buffers)"},
+                "api": "rbq_lindblad (host pointers, page-locked buffers in the ABI's layout)",
+                "pageable_numpy_wrapper_ms": e2e_l_pageable},
         "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
                      "fp64_instr_per_density_step": LINDBLAD_INSTR_PER_STEP, "flops_per_density_step": LINDBLAD_FLOPS_PER_STEP,
                      "fp64_pipe_issue_util": S * K1 * LINDBLAD_INSTR_PER_STEP / (ms_l * 1e-3) * 2e-12 / fp64_peak if fp64_peak else None,

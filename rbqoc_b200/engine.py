@@ -321,6 +321,21 @@ class Engine:
                                         _ptr(fid), _ptr(out), C.byref(st)), "rbq_lindblad")
         return fid, out.reshape(S, 2, 2).transpose(0, 2, 1).copy(), st
 
+    def lindblad_into(self, controls, dt, gate, gate_count, fq, da, vec, fid, rho_out, channels=_lib.LINDBLAD_T1, t2_gamma_c=0.0,
+                      t2_gamma_f=0.0):
+        """rbq_lindblad on buffers already in the ABI's layout and owned by the caller (page-locked ones from `pinned_empty`
+        travel at the full PCIe rate): vec (S, 8) doubles = column-major vec(rho0) as (re, im) pairs, fid (S, gate_count+1),
+        rho_out (S, 8).  Nothing is allocated, transposed or copied on the host.  Returns the statistics."""
+        S = vec.shape[0]
+        if vec.dtype != np.float64 or vec.shape != (S, 8) or fid.shape != (S, gate_count + 1) or rho_out.shape != (S, 8) or \
+                not (vec.flags.c_contiguous and fid.flags.c_contiguous and rho_out.flags.c_contiguous):
+            raise ValueError("lindblad_into: vec (S,8), fid (S,gate_count+1), rho_out (S,8) contiguous float64")
+        st = Stats()
+        self._ck(self._lib.rbq_lindblad(self._h, _ptr(controls), controls.shape[0], float(dt), int(gate), int(gate_count), S,
+                                        float(fq), _ptr(da), _ptr(vec), int(channels), float(t2_gamma_c), float(t2_gamma_f),
+                                        _ptr(fid), _ptr(rho_out), C.byref(st)), "rbq_lindblad")
+        return st
+
     # ---- analytic gates: segments with their own durations (spin.jl:562-594, 651-670, 765-785) -------------------------
     def mc_static_segments(self, amps, durs, gate, gate_count, fq, da, psi0):
         amps, durs, fq, psi0 = _f64(amps), _f64(durs), _f64(fq), _f64(psi0)
