@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
             const double* tile = pipe.acquire(ti, false);
             const int len = pipe.tile_len(ti);
             if (cls < 0) {
-                if constexpr (SPT == 1 && RBQ_DELTA_PHASED) delta_tile_phased<RBQ_DELTA_U>(tile, len, p[0], qd[0], qd2[0], e0[0], v[0], 1 - a.no_table_class);
+                if constexpr (SPT == 1 && RBQ_DELTA_PHASED) delta_tile_phased<RBQ_DELTA_U>(tile, len, p[0], qd[0], qd2[0], e0[0], v[0], 1 | a.no_table_class);   // = 1, opaque to the compiler
                 else delta_tile<SPT, UNR>(tile, len, p, qd, qd2, e0, v);
             }
             else if (cls == 0) tan_tile<RBQ_TANA_DEG, SPT, UNR>(tile, len, p, p2, qd, v, cfA);

@@ -53,8 +53,11 @@ class File:
         else:
             with open(source, "rb") as fh:
                 self.buf = fh.read()
-        self._find_superblock()
-        self._links = self._group_links(self.root_header, self.root_btree, self.root_heap)
+        try:
+            self._find_superblock()
+            self._links = self._group_links(self.root_header, self.root_btree, self.root_heap)
+        except (IndexError, ValueError, struct.error, TypeError) as exc:      # truncated or foreign bytes behind a valid signature
+            raise H5FormatError(f"damaged HDF5 file: {exc}") from exc
 
     # -- low level
     def _u(self, off, n):
@@ -460,9 +463,12 @@ class File:
             not any(m[0] == 0x08 for m in self._messages(header))
 
     def _load(self, header):
-        if self._is_group(header):
-            return {k: self._load(a) for k, a in sorted(self._group_links(header).items())}
-        return self._read_dataset(header)
+        try:
+            if self._is_group(header):
+                return {k: self._load(a) for k, a in sorted(self._group_links(header).items())}
+            return self._read_dataset(header)
+        except (IndexError, struct.error, zlib.error) as exc:
+            raise H5FormatError(f"damaged HDF5 object at {header}: {exc}") from exc
 
     def keys(self):
         return sorted(self._links)

@@ -93,6 +93,8 @@ def test_round_trip_types_groups_and_user_block(tmp_path):
         h5lite.File(b"not an hdf5 file" * 100)
     with pytest.raises(TypeError):
         h5lite.write(None, {"o": np.array([object()])})
+    with pytest.raises(h5lite.H5FormatError):                  # a file cut off in the middle of its metadata
+        h5lite.File(data[:len(data) // 2])["f8"]
 
 
 # ---- hand-assembled files for the layouts the writer never produces -----------------------------------------------------
