@@ -805,6 +805,7 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     bool done = false;
     if (cl == 2) e = bp_launch_cluster<2>(a, B, smem, h->stream, bp_stage_mode(h, n, m, d_AB, d_Exx), &done);
     else if (cl == 4) e = bp_launch_cluster<4>(a, B, smem, h->stream, bp_stage_mode(h, n, m, d_AB, d_Exx), &done);
+    if (done && e != cudaSuccess) { cudaGetLastError(); done = false; }   // a cluster that cannot be placed: one CTA per problem instead
     if (done) {
     } else if (small) {
         e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream, !h->opt.bp_generic);
