@@ -356,6 +356,16 @@ RBQ_DEV void philox_uniform2(uint64_t index, uint64_t seed, uint32_t j, uint32_t
     u0 = u53(o[0], o[1]);
     u1 = u53(o[2], o[3]);
 }
+// 1/sqrt(x) for a normal, positive x without the library routine's call, special-case tests and second Newton step: the
+// hardware seed (MUFU.RSQ64H, relative error below 2^-22) and one third-order correction
+// y <- y + y e (1/2 + 3/8 e), e = 1 - x y^2, which leaves ~2^-66 before the final rounding.  Five dependent FP64 instructions
+// after the seed; used where a reciprocal square root sits on a knot-to-knot dependency chain (unscented rollouts).
+RBQ_DEV double rsqrt_lean(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
 RBQ_DEV void philox_normal2(uint64_t index, uint64_t seed, uint32_t j, uint32_t stream, double& z0, double& z1) {
     double u0, u1;
     philox_uniform2(index, seed, j, stream, u0, u1);

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                     double dd = P[RBQ_TRI(j, j)];
 #pragma unroll
                     for (int kk = 0; kk < j; ++kk) dd = fma(-L[RBQ_TRI(j, kk)], L[RBQ_TRI(j, kk)], dd);
-                    const double inv = rsqrt(dd);        // one reciprocal square root instead of sqrt + divide
+                    const double inv = rsqrt_lean(dd);   // one reciprocal square root instead of sqrt + divide (a failed factorisation still gives NaN)
                     L[RBQ_TRI(j, j)] = dd * inv;
 #pragma unroll
                     for (int i = j + 1; i < 4; ++i) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                     v[i] = fma(sgn, col, sm[i]);
                 }
 #undef RBQ_TRI
-                const double rn = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+                const double rn = rsqrt_lean(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
                 if (sigma_lane) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { psi[c][i] = v[i] * rn; Xn[off + 41 * c + i] = psi[c][i]; }

@@ -14,3 +14,9 @@ dX = torch.empty(1, N, model.n, dtype=torch.float64, device=dev)
 for _ in range(4):
     eng.rollout_dev(model.params, 1, N, dx0, dU, ddt, dX)
 torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+best = 1e9
+for _ in range(10):
+    a.record(); eng.rollout_dev(model.params, 1, N, dx0, dU, ddt, dX); b.record(); torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+print(f"spin30 open-loop rollout, {N} knots: {best * 1e3:.1f} us ({best * 1e3 / (N - 1):.3f} us per knot)")
