@@ -49,7 +49,7 @@ FLOPS_PER_STEP_SU2 = 25.0
 FP64_INSTR_PER_STEP_SU2 = 14.0
 # operand-delivery model of the shipped loop (tools/sass_fp64_cost.py on librbq.so: per knot 0.6 instructions with <= 1 register
 # operand to fetch at 2.0 pipe cycles, 8.1 with two at 2.42, 5.25 with three at 3.24; profiles/r1_fp64_microbench.txt)
-FP64_MODEL_CYCLES_PER_STEP_SU2 = 37.92
+FP64_MODEL_CYCLES_PER_STEP_SU2 = 37.82
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # FP64 instructions per density-step of the Lindblad table step (lindblad_tab_kernel): 27 DFMA (Horner of the 9
 # entries of E_lo + da (L1 + da (L2 + da L3))) + 3 DMUL + 6 DFMA (the small part applied) + 9 DFMA (E_hi applied) = 45
