@@ -71,7 +71,14 @@ struct BackwardArgs {
 };
 
 // staging modes of backward_pass_kernel (template parameter MODE)
-constexpr int BP_TMA_J = 1, BP_TMA_C = 2, BP_DENSE_J = 4;
+constexpr int BP_TMA_J = 1, BP_TMA_C = 2, BP_DENSE_J = 4, BP_REG_J = 8, BP_REG_C = 16, BP_REG = BP_REG_J | BP_REG_C;
+// BP_REG_J / BP_REG_C: the Jacobian block / the cost blocks travel through registers.  Every thread loads its few elements of the
+// next knot's blocks at the top of a knot (plain coalesced loads: nothing waits on them) and stores them into shared memory where
+// the existing barriers already separate a buffer's readers from its next writer -- the Jacobian block after the gains, the cost
+// blocks after the top barrier of the next knot.  A cp.async instruction holds its warp ~270 cycles whatever its width and a
+// small problem issues five per warp and knot (n = 11: 1.21 -> 0.82 us per knot with BP_REG); the per-column bulk copies of an
+// even-n Jacobian block occupy every warp for ~700 cycles (n = 56: BP_REG_J | BP_TMA_C).
+__host__ __device__ constexpr int bp_reg_count(int elems, int threads) { return (elems + threads - 1) / threads; }
 
 // Shared-memory layout (doubles), all column-major.  Rows are padded with zeros to a multiple of 8 (the DMMA tile), the
 // contraction length to a multiple of 4; the leading dimensions ld = n8 + 4 and ldg = q8 + 4 are = 4 (mod 8), which makes every
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         if (e < m * m) { G[(n + e / m) * ldg + n + e % m] = v; return; }
         g[e - m * m] = v;
     };
-    if (N > 1) stage_jacobian(N - 2);
+    if (N > 1 && !(MODE & BP_REG_J)) stage_jacobian(N - 2);
 
     const int rtiles = n8 / 8, ctiles = q8 / 8, ksteps = n4 / 4;
     const int fr = lane >> 2, fc = lane & 3;          // fragment coordinates of this lane
@@ -299,6 +306,55 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         if (rank != owner) inbound += (uint32_t)(n8 * sizeof(double));
         cluster_arrive(); cluster_wait();                           // every CTA's shared memory is initialised
     }
+    // BP_REG: this thread's elements of a knot's Jacobian block (pa) and cost blocks (pc): where they come from (element of knot
+    // 0 + a per-knot stride) and where they go in shared memory
+    constexpr bool reg_j = (MODE & BP_REG_J) != 0, reg_c = (MODE & BP_REG_C) != 0;
+    constexpr int PA = !reg_j ? 1 : (NN ? bp_reg_count(NN * (NN + (MM ? MM : BP_MAX_M)), BP_THREADS) : 3);
+    constexpr int PC = !reg_c ? 1 : (NN ? bp_reg_count((NN + (MM ? MM : BP_MAX_M)) * (NN + (MM ? MM : BP_MAX_M) + 1), BP_THREADS) : 4);
+    double pa[PA], pc[PC];
+    int pa_dst[PA], pc_dst[PC], pc_str[PC];
+    const double* pc_src[PC];
+#pragma unroll
+    for (int r = 0; r < PA; ++r) {
+        const int idx = tid + r * BP_THREADS;
+        pa_dst[r] = reg_j && idx < n * nm ? (idx / n) * lda + idx % n : -1;
+        pa[r] = 0.0;
+    }
+    {
+#pragma unroll
+        for (int r = 0; r < PC; ++r) {
+            const int e = tid + r * BP_THREADS;
+            pc[r] = 0.0; pc_dst[r] = -1; pc_str[r] = 0; pc_src[r] = Exg;
+            if (!reg_c) continue;
+            if (e < nm * nm) {                                            // G(i, j), both triangles from the stored lower one
+                const int i = e % nm, j = e / nm, lo = i < j ? i : j, hi = i < j ? j : i;
+                pc_dst[r] = j * ldg + i;
+                if (hi < n) { pc_src[r] = Exxg + lo * n + hi; pc_str[r] = n * n; }
+                else if (lo < n) { pc_src[r] = Euxg + lo * m + (hi - n); pc_str[r] = m * n; }
+                else { pc_src[r] = Euug + (lo - n) * m + (hi - n); pc_str[r] = m * m; }
+            } else if (e < nm * nm + nm) {                                // the gradient column
+                const int i = e - nm * nm;
+                pc_dst[r] = cs * ldg + i;
+                if (i < n) { pc_src[r] = Exg + i; pc_str[r] = n; } else { pc_src[r] = Eug + (i - n); pc_str[r] = m; }
+            }
+        }
+    }
+    auto reg_fetch = [&](int64_t kk) {
+        const double* src = ABg + kk * (int64_t)(n * nm);
+#pragma unroll
+        for (int r = 0; r < PA; ++r) if (pa_dst[r] >= 0) pa[r] = src[tid + r * BP_THREADS];
+#pragma unroll
+        for (int r = 0; r < PC; ++r) if (pc_dst[r] >= 0) pc[r] = pc_src[r][kk * (int64_t)pc_str[r]];
+    };
+    auto reg_commit_jacobian = [&]() {
+#pragma unroll
+        for (int r = 0; r < PA; ++r) if (pa_dst[r] >= 0) AB[pa_dst[r]] = pa[r];
+    };
+    auto reg_commit_cost = [&]() {
+#pragma unroll
+        for (int r = 0; r < PC; ++r) if (pc_dst[r] >= 0) G[pc_dst[r]] = pc[r];
+    };
+    if ((reg_j || reg_c) && N > 1) { reg_fetch(N - 2); reg_commit_jacobian(); }   // (the cost blocks wait in pc for the first knot's barrier)
     // cluster form: the tiles of S this warp mirrors at the top of a knot (source and destination offsets of its two elements)
     constexpr int MIR_RT = ((NN + 7) & ~7) / 8, MIR_NT = MIR_RT * (MIR_RT + 1) / 2, MIR_PER = CL > 1 ? (MIR_NT + NW - 1) / NW : 0;
     int mir_src[MIR_PER > 0 ? MIR_PER : 1], mir_dst[MIR_PER > 0 ? MIR_PER : 1][2];
@@ -337,7 +393,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         }
         else bp_sync<NW>();                                        // AB_k, S, sv visible; G and g are free again
         BP_PROF(0)
-        stage_cost(k);
+        if (reg_c) reg_commit_cost(); else stage_cost(k);
+        if ((reg_j || reg_c) && k > 0) reg_fetch(k - 1);
         double ex0 = 0.0, ex1 = 0.0;
         if (tma_c) {
             if (tid < n_extra) ex0 = *extra_src(tid, k);
@@ -464,7 +521,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         if (CL > 1 && rank != owner) {
             // the gains arrive from the owner; meanwhile fetch the next Jacobian block (this CTA is done reading the current one)
             __syncthreads();
-            if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
+            if (reg_j) { if (k > 0) reg_commit_jacobian(); }
+            else if (k > 0) stage_jacobian(k - 1); else cp_async_commit();
         } else if (m == 1 && tid <= n) {
             // one control (every reference model but the time-optimal spin15): Quu_reg is a scalar, its "factorisation" one
             // reciprocal -- a much shorter dependent chain than the general path's sqrt, divisions and guarded loops
@@ -595,7 +653,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 8 : (NN != 0 && NN <= 44 ? 
         if (bp_sync_or<NW>(!ok)) { bad = k; break; }            // Quu_reg not positive definite: stop here (uniform)
         BP_PROF(6)
         // the Jacobian block is no longer needed: fetch the next one behind the value update
-        if (!early) { if (k > 0) stage_jacobian(k - 1); else cp_async_commit(); }
+        if (reg_j) { if (k > 0 && !early) reg_commit_jacobian(); }
+        else if (!early) { if (k > 0) stage_jacobian(k - 1); else cp_async_commit(); }
         BP_PROF(8)
         // ---- value update: V = Qxx + sym(K'Quu K + K'Qux + Qux'K) into the scratch, then S = (V + V')/2 ----
         // S = sym(Qxx) + sym(K'Quu K + K'Qux + Qux'K), written in one pass.  The symmetrisation is not cosmetic: the recursion
@@ -715,9 +774,12 @@ static int bp_stage_mode(const rbq_handle* h, int n, int m, const double* d_AB, 
     if (n >= 28) {
         const bool ab16 = (reinterpret_cast<uintptr_t>(d_AB) & 15) == 0, exx16 = (reinterpret_cast<uintptr_t>(d_Exx) & 15) == 0;
         if (ab16 && ((n * nm) & 1) == 0 && ((n & 1) || (n & 7) == 4)) mode |= BP_DENSE_J;   // every block 16-byte aligned
+        // (BP_REG_J for the even shapes n = 56 / 58 was measured: 5.75 -> 5.81 us per knot on one CTA, 3.67 -> 3.76 on four: the
+        // 13 loads + 13 stores per thread cost what the 57 bulk copies cost)
         else if (ab16 && (n & 1) == 0) mode |= BP_TMA_J;                                      // every column 16-byte aligned
         if (exx16 && m * n + m * m + n + m <= 2 * 32 * BP_WARPS_LARGE) mode |= BP_TMA_C;
     }
+    else if (n * nm <= 3 * 32 * BP_WARPS_LARGE && nm * (nm + 1) <= 4 * 32 * BP_WARPS_LARGE) mode = BP_REG;
     if (h->opt.bp_tma >= 0) mode &= h->opt.bp_tma;
     return mode;
 }
@@ -755,14 +817,17 @@ static cudaError_t bp_launch_cluster(const BackwardArgs& a, int64_t B, size_t sm
 template <int NW, int MODE>
 static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cudaStream_t stream, bool specialised) {
     if (a.m == 2 && specialised) {                                      // spin15 time-optimal: u = (d2a/dt2, sqrt(dt))
-        if constexpr (MODE == 0) {
+        if constexpr (MODE == 0 || MODE == BP_REG) {
             if (a.n == 11) return bp_launch2<NW, MODE, 2, 11>(a, B, smem, stream);
             if (a.n == 12) return bp_launch2<NW, MODE, 2, 12>(a, B, smem, stream);
         }
     }
-    if (a.m != 1) return bp_launch2<NW, MODE, 0, 0>(a, B, smem, stream);
+    if (a.m != 1) {
+        if constexpr (NW == BP_WARPS_SMALL && MODE == BP_REG) return bp_launch2<NW, 0, 0, 0>(a, B, smem, stream);
+        else return bp_launch2<NW, MODE, 0, 0>(a, B, smem, stream);
+    }
     if (specialised) {
-        if constexpr (MODE == 0) {
+        if constexpr (MODE == 0 || MODE == BP_REG) {
             if (a.n == 11) return bp_launch2<NW, MODE, 1, 11>(a, B, smem, stream);
             if (a.n == 12) return bp_launch2<NW, MODE, 1, 12>(a, B, smem, stream);      // spin15, decay aware
             if (a.n == 15) return bp_launch2<NW, MODE, 1, 15>(a, B, smem, stream);      // spin11 / spin17, first order
@@ -778,7 +843,8 @@ static cudaError_t bp_launch(const BackwardArgs& a, int64_t B, size_t smem, cuda
             if (a.n == 58) return bp_launch2<NW, MODE, 1, 58>(a, B, smem, stream);
         }
     }
-    return bp_launch2<NW, MODE, 1, 0>(a, B, smem, stream);
+    if constexpr (NW == BP_WARPS_SMALL && MODE == BP_REG) return bp_launch2<NW, 0, 1, 0>(a, B, smem, stream);   // (register staging of the one-warp form: specialised shapes only)
+    else return bp_launch2<NW, MODE, 1, 0>(a, B, smem, stream);
 }
 
 int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, const double* d_AB, const double* d_Exx,
@@ -808,12 +874,14 @@ int launch_backward_pass(rbq_handle* h, int n, int m, int64_t N, int64_t B, cons
     if (done && e != cudaSuccess) { cudaGetLastError(); done = false; }   // a cluster that cannot be placed: one CTA per problem instead
     if (done) {
     } else if (small) {
-        e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream, !h->opt.bp_generic);
+        if (bp_stage_mode(h, n, m, d_AB, d_Exx) == BP_REG) e = bp_launch<BP_WARPS_SMALL, BP_REG>(a, B, smem, h->stream, !h->opt.bp_generic);
+        else e = bp_launch<BP_WARPS_SMALL, 0>(a, B, smem, h->stream, !h->opt.bp_generic);
     } else {
         switch (bp_stage_mode(h, n, m, d_AB, d_Exx)) {
             case BP_DENSE_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_DENSE_J | BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
             case BP_TMA_J | BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_J | BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
             case BP_TMA_C: e = bp_launch<BP_WARPS_LARGE, BP_TMA_C>(a, B, smem, h->stream, !h->opt.bp_generic); break;
+            case BP_REG: e = bp_launch<BP_WARPS_LARGE, BP_REG>(a, B, smem, h->stream, !h->opt.bp_generic); break;
             default: e = bp_launch<BP_WARPS_LARGE, 0>(a, B, smem, h->stream, !h->opt.bp_generic); break;
         }
     }
