@@ -1,0 +1,53 @@
+"""The shipped sweep kernel's hot loop, priced by the operand-delivery model of the FP64 pipe (tools/sass_fp64_cost.py, measured
+table in profiles/r1_fp64_microbench.txt).  No GPU needed: the SASS of the in-tree librbq.so is read with cuobjdump.  The model
+matched every measured variant of this loop to 2 %, so this is the performance regression test that runs on the CPU: a
+toolchain or source change that brings back the interleaved schedule (40+ cycles per knot) fails here."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_table_step_of_the_default_sweep_kernel_costs_what_the_bench_claims():
+    import sass_fp64_cost as sc
+
+    lib = os.path.join(ROOT, "rbqoc_b200", "librbq.so")
+    if not os.path.exists(lib):
+        pytest.skip("librbq.so not built")
+    title, ins = sc.function_sass(lib, "mc_static_kernelILi0ELi1ELi6ELi128")
+    assert "mc_static_kernel" in title
+    loops = []
+    for addr, text in ins:
+        m = sc.re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(?:!?UP\d+,\s*)?0x([0-9a-f]+)", text)
+        if m and int(m.group(1), 16) < addr:
+            loops.append((int(m.group(1), 16), addr))
+    table_loops = [r for r in set(loops) if sc.model(ins, *r)[0] == 112]        # 8 knots x 14 FP64 instructions
+    assert table_loops, "no loop of 8 x 14 FP64 instructions in the default sweep kernel"
+    n, hist, cycles = sc.model(ins, *sorted(table_loops)[0])
+    per_knot = cycles / 8.0
+    assert n == 112
+    # bench.py reports this figure as roofline.issue_model.cycles_per_warp_step_floor
+    sys.path.insert(0, ROOT)
+    import bench
+    assert abs(per_knot - bench.FP64_MODEL_CYCLES_PER_STEP_SU2) < 0.25, (per_knot, hist)
+    assert per_knot < 38.5                                                       # the round-1 schedule cost 39.98
+
+
+def test_cost_model_counts_reuse_and_fresh_operands():
+    import sass_fp64_cost as sc
+
+    ins = [(0x00, "DFMA R4, R2.reuse, R6, R8"),          # three fetched operands
+           (0x10, "DFMA R10, R2, R12, R14"),             # R2 comes from the reuse cache: two
+           (0x20, "LDS.128 R16, [R0+UR4]"),              # (anything in between clears the cache)
+           (0x30, "DMUL R20, R2, R2"),                   # one distinct register
+           (0x40, "DADD R22, R20, 1"),                   # immediate operands are free
+           (0x50, "BRA 0x0")]
+    n, hist, cycles = sc.model(ins, 0x00, 0x50)
+    assert n == 4 and hist == {0: 0, 1: 2, 2: 1, 3: 1}
+    assert cycles == pytest.approx(3.24 + 2.42 + 2.0 + 2.0)
