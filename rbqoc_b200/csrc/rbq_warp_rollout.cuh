@@ -19,6 +19,11 @@ RBQ_DEV double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+template <int W> RBQ_DEV double sum_lanes(double v) {   // total over the first W lanes, left on each of them (W = 4, 8, 16, 32)
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
 RBQ_DEV double sum16(double v) {   // lanes 0..15 (the xor butterfly leaves the total on each of them)
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -66,6 +71,11 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
     constexpr int NNOM = S25 ? 2 : 3;                          // nominal blocks (lanes 10..)
     const int ssc = U30 ? (SSC ? SSC : p.sample_state_count) : 1;
     const int cb = (U30 && !S25) ? 12 : 8;                     // [int a, a, da] chain base
+    // closed loop: the lanes that hold state are 0 .. TAIL (blocks first, then one lane for the scalar tail), so the feedback law's
+    // dot product is a butterfly over FBW lanes only -- 2 shuffle stages instead of 5 for spin13 / spin15.  Lanes beyond FBW hold
+    // no state and store nothing; the control they carry is not the trajectory's.
+    constexpr int TAIL = (MODEL == RBQ_MODEL_SPIN13 || MODEL == RBQ_MODEL_SPIN15) ? 2 : (MODEL == RBQ_MODEL_SPIN11 ? 4 : (MODEL == RBQ_MODEL_SPIN12 ? 10 : 13));
+    constexpr int FBW = TAIL < 4 ? 4 : (TAIL < 8 ? 8 : 16);
 
     // ---- lane roles ---------------------------------------------------------------------------------
     int off = -1;                 // state offset of this lane's block (chunk 0 for sigma lanes)
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                             if (m > 1) s1 = fma(Kk[idx * m + 1], dx, s1);
                         }
             }
-            if (lane == 15) {   // scalar tail of the state: chain, decay accumulator, unscented penalties (lanes 0..15 hold them)
+            if (lane == TAIL) { // scalar tail of the state: chain, decay accumulator, unscented penalties
                 const double tail[3] = {ci - xr[cb], ca - xr[cb + 1], cd - xr[cb + 2]};
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { s0 = fma(Kk[(cb + i) * m], tail[i], s0); if (m > 1) s1 = fma(Kk[(cb + i) * m + 1], tail[i], s1); }
@@ -184,9 +194,9 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                     for (int i = 0; i < 6; ++i) s0 = fma(Kk[(11 + i) * m], taps[i] - xr[11 + i], s0);
                 }
             }
-            s0 = warp_sum(s0);
+            s0 = sum_lanes<FBW>(s0);
             u0 = sU[kt * m] + fma(alpha, sD[kt * m], s0);
-            if (m > 1) { s1 = warp_sum(s1); u1 = sU[kt * m + 1] + fma(alpha, sD[kt * m + 1], s1); }
+            if (m > 1) { s1 = sum_lanes<FBW>(s1); u1 = sU[kt * m + 1] + fma(alpha, sD[kt * m + 1], s1); }
             if (lane == 0) { Uo[k * m] = u0; if (m > 1) Uo[k * m + 1] = u1; }
         } else {
             u0 = u0_n; u1 = u1_n;
