@@ -180,7 +180,24 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
             const double* __restrict__ Kk = sK + kt * m * n;
             const double* __restrict__ xr = sX + kt * n;
             double s0 = 0.0, s1 = 0.0;
-            if (has_block) {
+            if (!U30) {
+                // every lane runs the same four multiply-adds on "its" four state entries -- a block lane its block, the tail
+                // lane [int a, a, da(, decay)] -- with the weights of the unused slots selected to zero: no divergent region in
+                // front of the butterfly, so the propagator of this knot (which does not depend on u_k) overlaps it
+                // (8 candidates x 1001 knots: spin13 0.41 -> 0.31 ms, spin12 0.54 -> 0.45 ms).  The same scheme with per-lane
+                // index tables for the unscented models' penalties and filter taps was slower (spin30 1.22 -> 1.48 ms).
+                const int fidx = has_block ? off : cb;
+                const int fcnt = has_block ? 4 : (lane == TAIL ? (DA ? 4 : 3) : 0);
+                const double fv[4] = {has_block ? psi[0][0] : ci, has_block ? psi[0][1] : ca, has_block ? psi[0][2] : cd, has_block ? psi[0][3] : gacc};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int idx = fidx + (i < 3 || has_block || DA ? i : 0);       // (stays inside the state when the tail has 3 entries)
+                    const double dx = fv[i] - xr[idx];
+                    const double k0 = i < fcnt ? Kk[idx * m] : 0.0;
+                    s0 = fma(k0, dx, s0);
+                    if (m > 1) { const double k1 = i < fcnt ? Kk[idx * m + 1] : 0.0; s1 = fma(k1, dx, s1); }
+                }
+            } else if (has_block) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
                     if (c == 0 || (sigma_lane && c < ssc))
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                             if (m > 1) s1 = fma(Kk[idx * m + 1], dx, s1);
                         }
             }
-            if (lane == TAIL) { // scalar tail of the state: chain, decay accumulator, unscented penalties
+            if (U30 && lane == TAIL) { // scalar tail of the state: chain, decay accumulator, unscented penalties
                 const double tail[3] = {ci - xr[cb], ca - xr[cb + 1], cd - xr[cb + 2]};
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { s0 = fma(Kk[(cb + i) * m], tail[i], s0); if (m > 1) s1 = fma(Kk[(cb + i) * m + 1], tail[i], s1); }
