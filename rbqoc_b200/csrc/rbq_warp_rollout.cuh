@@ -197,6 +197,18 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                     s0 = fma(k0, dx, s0);
                     if (m > 1) { const double k1 = i < fcnt ? Kk[idx * m + 1] : 0.0; s1 = fma(k1, dx, s1); }
                 }
+            } else if (NCH == 1) {
+                // the unscented models with one sigma-point chunk (every reference run): same scheme, the tail lane's fourth entry
+                // is the chunk's penalty
+                const bool tl = lane == TAIL;
+                const double fv[4] = {has_block ? psi[0][0] : ci, has_block ? psi[0][1] : ca, has_block ? psi[0][2] : cd, has_block ? psi[0][3] : pen[0]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int idx = has_block ? off + i : (i < 3 ? cb + i : UB + 40);
+                    const double dx = fv[i] - xr[idx];
+                    const double k0 = (has_block || tl) ? Kk[idx * m] : 0.0;
+                    s0 = fma(k0, dx, s0);
+                }
             } else if (has_block) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
@@ -209,7 +221,12 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                             if (m > 1) s1 = fma(Kk[idx * m + 1], dx, s1);
                         }
             }
-            if (U30 && lane == TAIL) { // scalar tail of the state: chain, decay accumulator, unscented penalties
+            if (U30 && NCH == 1 && S25 && lane == TAIL) {   // spin25: the pink-filter taps
+                const double taps[6] = {fx1, fx2, fx3, fy1, fy2, fy3};
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s0 = fma(Kk[(11 + i) * m], taps[i] - xr[11 + i], s0);
+            }
+            if (U30 && NCH > 1 && lane == TAIL) { // scalar tail of the state: chain, decay accumulator, unscented penalties
                 const double tail[3] = {ci - xr[cb], ca - xr[cb + 1], cd - xr[cb + 2]};
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { s0 = fma(Kk[(cb + i) * m], tail[i], s0); if (m > 1) s1 = fma(Kk[(cb + i) * m + 1], tail[i], s1); }
@@ -283,17 +300,23 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                 for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
             }
         } else {
-            // nominal lanes 10..
-            if (lane >= 10 && lane < 10 + NNOM) {
-                prop_apply<double>(E, in0[0], in0[1], in0[2], in0[3], psi[0][0], psi[0][1], psi[0][2], psi[0][3]);
+            // every lane applies its propagator to its (chunk 0) block -- lanes without one hold zeros -- so that no divergent
+            // region sits between the propagator and the reductions; the nominal lanes 10.. keep the result and store it
+            double e0[4];
+            prop_apply<double>(E, in0[0], in0[1], in0[2], in0[3], e0[0], e0[1], e0[2], e0[3]);
+            const bool nominal_lane = lane >= 10 && lane < 10 + NNOM;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) Xn[off + i] = psi[0][i];
+            for (int i = 0; i < 4; ++i) {
+                if (nominal_lane) { psi[0][i] = e0[i]; Xn[off + i] = e0[i]; }
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 if (c >= ssc) break;
                 double s[4] = {0.0, 0.0, 0.0, 0.0};
-                if (sigma_lane) prop_apply<double>(E, psi[c][0], psi[c][1], psi[c][2], psi[c][3], s[0], s[1], s[2], s[3]);
+                if (c == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s[i] = sigma_lane ? e0[i] : 0.0;
+                } else if (sigma_lane) prop_apply<double>(E, psi[c][0], psi[c][1], psi[c][2], psi[c][3], s[0], s[1], s[2], s[3]);
                 double sm[4], dv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { sm[i] = 0.1 * sum16(s[i]); dv[i] = sigma_lane ? s[i] - sm[i] : 0.0; }
@@ -336,9 +359,10 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
                 }
 #undef RBQ_TRI
                 const double rn = rsqrt_lean(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
-                if (sigma_lane) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { psi[c][i] = v[i] * rn; Xn[off + 41 * c + i] = psi[c][i]; }
+                for (int i = 0; i < 4; ++i) {
+                    const double vn = v[i] * rn;
+                    if (sigma_lane) { psi[c][i] = vn; Xn[off + 41 * c + i] = vn; }
                 }
                 // penalty with the nominal state AT KNOT k (lane 10 + nominal block)
                 const int nl = 10 + (p.nominal_offset[c] >> 2);
