@@ -317,11 +317,42 @@ __global__ void __launch_bounds__(32) warp_rollout_kernel(const WarpRolloutArgs 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) s[i] = sigma_lane ? e0[i] : 0.0;
                 } else if (sigma_lane) prop_apply<double>(E, psi[c][0], psi[c][1], psi[c][2], psi[c][3], s[0], s[1], s[2], s[3]);
-                double sm[4], dv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { sm[i] = 0.1 * sum16(s[i]); dv[i] = sigma_lane ? s[i] - sm[i] : 0.0; }
+                double sm[4];
                 double P[10];   // packed lower triangle 00 10 11 20 21 22 30 31 32 33
-                {
+                if constexpr (!CLOSED) {
+                    // mean and covariance in ONE butterfly pass: deviations are taken from a reference point that is known without
+                    // a reduction -- the midpoint of the two frequency-shifted points, which were both resampled AT the previous
+                    // mean and so sit within O(spread^2) of the new one -- and the first and second moments of those deviations
+                    // are summed together (14 independent butterflies): mean = ref + delta, P = cf (M2 - 10 delta delta'),
+                    // delta = sum(d') / 10.  The correction term is far below M2, so nothing cancels; the dependent chain is one
+                    // shuffle stage + one butterfly instead of two butterflies (open loop, 1001 knots: 0.92 -> 0.77 ms).  In the
+                    // closed-loop kernel the same change measured slower (8 candidates: 1.18 -> 1.35 ms), so it keeps two passes.
+                    double ref[4], dp[4], dl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ref[i] = 0.5 * (__shfl_sync(FULL, s[i], 4) + __shfl_sync(FULL, s[i], 9));
+                        dp[i] = sigma_lane ? s[i] - ref[i] : 0.0;
+                    }
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int kk = 0; kk <= i; ++kk) P[q++] = sum16(dp[i] * dp[kk]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { dl[i] = 0.1 * sum16(dp[i]); sm[i] = ref[i] + dl[i]; }
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int kk = 0; kk <= i; ++kk) { P[q] = cf * fma(-10.0 * dl[i], dl[kk], P[q]); ++q; }
+                    }
+                } else {
+                    double dv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { sm[i] = 0.1 * sum16(s[i]); dv[i] = sigma_lane ? s[i] - sm[i] : 0.0; }
                     int q = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
