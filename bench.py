@@ -41,15 +41,20 @@ SEED = 2026
 PHILOX = (0.01, 0.03, 2.574e-5)   # fq_rel_sigma, fq_rel_clip, da_sigma (figures.jl:261,386; spin.jl:164)
 PARITY_N = 10_000
 PARITY_TOL = 1e-12
-# flops the closed-form kernel executes per trajectory-step on this grid (FMA = 2), counted in the SASS [DESIGN.md §4.2] and
-# cross-checked against ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/):
-#   knot-table step (samples near the sweep centre -- every warp of this workload but ~0.3 %):
+# flops per trajectory-step on this grid (FMA = 2), counted in the SASS [DESIGN.md §4.2] and cross-checked against ncu
+# smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/):
+#   knot-table step (samples near the sweep centre -- every warp of this workload but ~0.3 %), ALGORITHMIC count:
 #     1 DFMA (eps) + 2 DFMA (T) + 1 DADD (q) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v) = 14 FP64 instructions = 25 flop
+#   the shipped constant-memory form (mc_static_ctab_kernel) evaluates T as c2 (eps (eps + rho) + sigma), one table value per
+#   instruction: 1 DADD + 1 DFMA + 1 DMUL instead of 2 DFMA = 15 instructions = 26 flop EXECUTED; the roofline numerator stays
+#   the algorithmic 25, the pipe utilisation uses the executed 15
 FLOPS_PER_STEP_SU2 = 25.0
-FP64_INSTR_PER_STEP_SU2 = 14.0
-# operand-delivery model of the shipped loop (tools/sass_fp64_cost.py on librbq.so: per knot 0.6 instructions with <= 1 register
-# operand to fetch at 2.0 pipe cycles, 8.1 with two at 2.42, 5.25 with three at 3.24; profiles/r1_fp64_microbench.txt)
-FP64_MODEL_CYCLES_PER_STEP_SU2 = 37.82
+FP64_INSTR_PER_STEP_SU2 = 15.0
+FLOPS_EXECUTED_PER_STEP_SU2 = 26.0
+# operand-delivery model of the shipped loop (tools/sass_fp64_cost.py on librbq.so; tools/proto/regbank.cu measured on B200: a
+# warp-wide FP64 instruction holds the pipe 2.0 cycles with up to two register operands to fetch, 2.9 with three): per knot
+# 12.75 instructions at 2.0 and 2.25 at 2.9
+FP64_MODEL_CYCLES_PER_STEP_SU2 = 32.03
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # FP64 instructions per density-step of the Lindblad table step (lindblad_tab_kernel): 27 DFMA (Horner of the 9
 # entries of E_lo + da (L1 + da (L2 + da L3))) + 3 DMUL + 6 DFMA (the small part applied) + 9 DFMA (E_hi applied) = 45
@@ -653,7 +658,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(S=S), "samples_per_gpu": S, "knots": NK,
-                       "algo": "su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre)",
+                       "algo": "su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre), "
+                               "table rows as uniform-register operands from constant memory",
                        "l2": "flushed between steps (256 MiB memset, untimed)",
                        "sharding": ("contiguous sample ranges per rank; per step ONE all-gather of the 2.1 KB statistics, copied to pinned host "
                                     "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},
@@ -666,13 +672,16 @@ def main():
                                          "(r1: 50.4 MB read + 1.8 MB written against 64 MB algorithmic; the 16 MB of fidelities stay in L2)",
                          "fp64_pipe_issue_util": S * NK * FP64_INSTR_PER_STEP_SU2 / (kern_ms * 1e-3) * 2e-12 / peak_tflops if peak_tflops else None,
                          "peak_source": "measured live: rbq_fp64_peak DFMA saturation loop (MEASURED_PEAKS.json has no FP64 entry)",
-                         # register-operand model of the FP64 pipe: a warp-wide instruction holds the pipe 2.0 / 2.42 / 3.24 cycles
-                         # with <= 1 / 2 / 3 register operands to fetch (operands kept by the reuse cache are free)
+                         # register-operand model of the FP64 pipe: a warp-wide instruction holds the pipe 2.0 cycles with up to two
+                         # register operands to fetch, 2.9 with three (operands kept by the reuse cache, uniform registers and
+                         # immediates are free)
                          "issue_model": {"cycles_per_warp_step_floor": FP64_MODEL_CYCLES_PER_STEP_SU2,
                                          "cycles_per_warp_step_all_operands_reused": 2.0 * FP64_INSTR_PER_STEP_SU2,
                                          "cycles_per_warp_step_measured": (clk["sm_mhz"] or 1965.0) * 1e6 * 4 * 148 * (kern_ms * 1e-3) / (S * NK / 32.0),
                                          "note": "floor = what the SASS of the shipped loop costs under the measured operand-delivery model (tools/sass_fp64_cost.py); floor / measured = how close the kernel runs to it"},
                          "flops_per_trajectory_step": FLOPS_PER_STEP_SU2, "fp64_instr_per_trajectory_step": FP64_INSTR_PER_STEP_SU2,
+                         "flops_executed_per_trajectory_step": FLOPS_EXECUTED_PER_STEP_SU2,
+                         "frac_executed_flops": (S * NK * FLOPS_EXECUTED_PER_STEP_SU2 / (kern_ms * 1e-3) * 1e-12 / peak_tflops) if peak_tflops else None,
                          "kernel_ms": kern_ms,
                          "hbm": {"achieved_gbs": S * BYTES_PER_SAMPLE / (kern_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "algorithmic bytes; shows the path is not HBM bound"}},

@@ -199,6 +199,7 @@ int rbq_destroy(rbq_handle* h) {
     if (!h) return RBQ_E_NULL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    ctab_forget(h);
     for (int i = 0; i < RBQ_NBUF; ++i) if (h->dbuf[i]) cudaFree(h->dbuf[i]);
     free(h->idx_host);
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(h->copy_stream[i]);
@@ -480,14 +481,21 @@ int rbq_stats_merge(rbq_stats* a, const rbq_stats* b) {
 // build the knot table (expanded around the sweep centre) and fill everything of McStaticArgs that does not depend on
 // the sample range
 static int mc_static_prepare(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
-                             int64_t partial_blocks, rbq_stats* d_stats, double f0, double a0, McStaticArgs* a) {
+                             int64_t partial_blocks, rbq_stats* d_stats, double f0, double a0, int64_t launch_samples,
+                             McStaticArgs* a) {
     memset(a, 0, sizeof(*a));
     if (!make_gate_tables(gate, &a->gate, nullptr)) return fail(h, RBQ_E_GATE, "unknown gate %d", gate);
     void *tb = nullptr, *sc = nullptr;
-    CKL(dev_buf(h, B_PULSE, sizeof(double) * 4 * (size_t)nk + 32, &tb));
+    CKL(dev_buf(h, B_PULSE, sizeof(double) * 8 * (size_t)nk + 32, &tb));
     CKL(dev_buf(h, B_SCALARS, 256, &sc));
-    CKL(launch_static_table(h, d_controls, nk, dt, f0, a0, (double*)tb, (double*)sc));
+    CKL(launch_static_table(h, d_controls, nk, dt, f0, a0, (double*)tb, (double*)sc, (double*)tb + 4 * (size_t)nk));
     a->table = (const double*)tb; a->scal = (const double*)sc;
+    a->table_m = (const double*)tb + 4 * (size_t)nk; a->table_gen = ++h->table_gen;
+    {   // quaternion scratch of the constant-memory form, sized for the largest launch of this call
+        void* qb = nullptr;
+        CKL(dev_buf(h, B_QUAT, sizeof(double) * 4 * (size_t)(launch_samples > 0 ? launch_samples : 1), &qb));
+        a->quat = (double*)qb;
+    }
     a->no_table_class = h->opt.no_table_class;
     a->nk = nk; a->dt = dt; a->gate_count = gate_count;
     if (d_stats) {
@@ -506,11 +514,12 @@ static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, d
     if (S == 0) { GateIso gi; return make_gate_tables(gate, &gi, nullptr) ? RBQ_OK : fail(h, RBQ_E_GATE, "unknown gate %d", gate); }
     // Philox sweeps are centred on their own (fq0, 0), explicit samples on the handle's centre (rbq_set_sweep_centre)
     CKL(mc_static_prepare(h, d_controls, nk, dt, gate, gate_count, mc_static_blocks(h, S, algo), d_stats,
-                          philox ? fq0 : h->centre_fq, philox ? 0.0 : h->centre_da, &a));
+                          philox ? fq0 : h->centre_fq, philox ? 0.0 : h->centre_da, S, &a));
     a.first = first; a.S = S;
     a.fq = d_fq; a.da = d_da; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.fq0 = fq0; a.fq_rel_sigma = fq_rel_sigma; a.fq_rel_clip = fq_rel_clip; a.da_sigma = da_sigma;
     a.fid = d_fid;
+    a.host_io = h->host_io_call;
     int nblocks = 0;
     CKL(launch_mc_static(h, a, algo, &nblocks));
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
@@ -570,8 +579,10 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
             CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc0));
             if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst0)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst0)); }
             CK(cudaMemcpyAsync(dc0, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+            h->host_io_call = 1;
             int rc = mc_static_core(h, (double*)dc0, nknots, dt, gate, gate_count, 0, S, (double*)mfq, (double*)mda, (double*)mpsi,
                                     0, 0, 0, 0, 0, 0, algo, (double*)mfid, (rbq_stats*)dst0);
+            h->host_io_call = 0;
             if (rc) return rc;
             if (stats) CK(cudaMemcpyAsync(stats, dst0, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -591,14 +602,15 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
         const int64_t wave = mc_static_wave_samples(h, algo);
         int64_t nchunks = 0;
         while (mc_chunk_begin(h, nchunks, wave, S) < S) ++nchunks;
-        int64_t total_blocks = 0;
+        int64_t total_blocks = 0, largest = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
             const int64_t s0 = mc_chunk_begin(h, c, wave, S), cnt = mc_chunk_begin(h, c + 1, wave, S) - s0;
             total_blocks += mc_static_blocks(h, cnt, algo);
+            largest = cnt > largest ? cnt : largest;
         }
         McStaticArgs a;
         CKL(mc_static_prepare(h, (double*)dc, nknots, dt, gate, gate_count, total_blocks, (rbq_stats*)dst, h->centre_fq,
-                              h->centre_da, &a));
+                              h->centre_da, largest, &a));
         BlockPartial* partials0 = a.partials;
         // event choreography: copy_stream[0] uploads, h->stream computes, copy_stream[1] downloads
         cudaStream_t up = h->copy_stream[0], down = h->copy_stream[1];
@@ -648,8 +660,10 @@ int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, 
     if (direct) dfid = mfid;
     if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
+    h->host_io_call = direct ? 1 : 0;
     int rc = rbq_mc_static_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma,
                                       fq_rel_clip, da_sigma, algo, (double*)dfid, (rbq_stats*)dst);
+    h->host_io_call = 0;
     if (rc) return rc;
     if (fid && S > 0 && !direct) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
     if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));

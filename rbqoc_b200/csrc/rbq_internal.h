@@ -23,6 +23,8 @@ struct rbq_handle {
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
     // centre (qubit frequency, amplitude offset) the static sweep's knot table is expanded around: rbq_set_sweep_centre
     double centre_fq, centre_da;
+    int host_io_call;              // set by the zero-copy entry points around their call into the device-pointer core
+    uint64_t table_gen;            // counts the knot tables this handle has built (owner tag of the constant-memory copy)
     unsigned stpos_mask;           // which slices of the structured-Jacobian position table this handle has uploaded
     // tuning / A-B switches: read from the environment ONCE in rbq_create (RBQ_* names), changed afterwards only through
     // rbq_set_option; never read from the environment inside a call.  -1 = "library default / heuristic".
@@ -69,6 +71,9 @@ struct GateRot { double r[3][9]; };    // the same gates as SO(3) rotations of t
 
 struct McStaticArgs {
     const double* table; int64_t nk; double dt;   // knot table (q_j, c0_j, c1_j, c2_j), see static_table_kernel
+    const double* table_m; uint64_t table_gen;    // rows of the factored form, or NULL; serial number of this table (per handle)
+    double* quat;                                 // scratch of the constant-memory form: 4 doubles per sample of this launch, or NULL
+    int host_io;                                  // sample / fidelity pointers are page-locked host memory (zero-copy call)
     int64_t gate_count; int64_t first; int64_t S;
     const double* fq; const double* da; const double* psi0;   // explicit samples
     int philox; uint64_t seed; double fq0, fq_rel_sigma, fq_rel_clip, da_sigma;
@@ -115,7 +120,8 @@ struct SegmentArgs {
 int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, double* d_amax);
 // knot table of the static sweep, expanded around the sweep centre (f0, a0)
 int launch_static_table(rbq_handle* h, const double* d_controls, int64_t nk, double dt, double f0, double a0, double* d_table,
-                        double* d_scal);
+                        double* d_scal, double* d_table_m = nullptr);
+void ctab_forget(const rbq_handle* h);   // a handle that goes away gives up the constant-memory table (rbq_destroy)
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise(rbq_handle* h, const McNoiseArgs& a, int algo, int* nblocks_out);
 int launch_mc_noise_gate_parallel(rbq_handle* h, const McNoiseArgs& a, double* d_quat, int* nblocks_out);

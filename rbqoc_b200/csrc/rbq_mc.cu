@@ -7,6 +7,7 @@
 // The pulse is staged into shared memory tile by tile with 1-D bulk TMA copies
 // (cp.async.bulk + mbarrier, double buffered); all threads of a block walk the pulse in lock step.
 // sm_100a only.
+#include <mutex>
 #include "rbq_internal.h"
 #include <stdlib.h>
 
@@ -196,7 +197,7 @@ constexpr double DELTA_R3 = 0.057;        // >= (third derivative of T)/6 on [0,
 constexpr double DELTA_TOL = 5e-17;       // admitted relative truncation of T per knot
 __global__ void __launch_bounds__(1024) static_table_kernel(const double* __restrict__ controls, int64_t nk, double dt,
                                                             double f0_in, double a0_in, double* __restrict__ table,
-                                                            double* __restrict__ scal) {
+                                                            double* __restrict__ scal, double* __restrict__ table_m) {
     __shared__ double red[3][32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double f0 = isfinite(f0_in) ? f0_in : 0.0, a0 = isfinite(a0_in) ? a0_in : 0.0;
@@ -209,6 +210,9 @@ __global__ void __launch_bounds__(1024) static_table_kernel(const double* __rest
         double c0, c1, c2;
         tan_taylor(x <= DELTA_XMAX ? x : DELTA_XMAX, c0, c1, c2);   // rows beyond the range are only read for q_j
         table[4 * j] = q; table[4 * j + 1] = c0; table[4 * j + 2] = c1; table[4 * j + 3] = c2;
+        // the same quadratic with its leading coefficient factored out, T = c2 (eps (eps + rho) + sigma): the rows of the
+        // constant-memory form of the sweep (mc_static_ctab_kernel), in which every instruction takes one table value
+        if (table_m) { table_m[4 * j] = q; table_m[4 * j + 1] = c1 / c2; table_m[4 * j + 2] = c0 / c2; table_m[4 * j + 3] = c2; }
         amax = fmax(amax, fabs(a)); qmax = fmax(qmax, fabs(q));
         xmax = x == x ? fmax(xmax, x) : INFINITY;                    // NaN controls switch the table class off
     }
@@ -372,6 +376,9 @@ RBQ_DEV void delta_tile(const double* __restrict__ tile, int len, const double (
 // a loop body of its own): first the scalars of all U knots level by level, each level's sample-invariant operands in fixed slots
 // (dq2 and e0, dq, p), then the U dependent updates, every group of four sharing its multiplier and the first instruction of the
 // second group taking its multiplicand from the last one of the first.
+#ifndef RBQ_MC_DEFAULT_VARIANT
+#define RBQ_MC_DEFAULT_VARIANT 2161
+#endif
 #ifndef RBQ_DELTA_PHASED
 #define RBQ_DELTA_PHASED 1
 #endif
@@ -605,6 +612,148 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
         const int64_t s = base + (int64_t)i * THREADS + tid;
         double* row = a.fid ? a.fid + s * (a.gate_count + 1) : nullptr;
         const double f = gate_train(E[i], psi0[i], a.gate, a.gate_count, row);
+        if (a.partials) st.add(1.0 - f, hist_s);
+    }
+    if (a.partials) {
+        __syncthreads();
+        block_stats_flush(st, hist_s, red_s, a.partials, a.hist);
+    }
+}
+
+// ---- static-parameter sweep, knot table in constant memory -----------------------------------------------------------------
+// Why: the FP64 pipe takes one 64-bit register operand per cycle from the register file (tools/proto/regbank.cu: a warp-wide
+// DFMA holds the pipe 2.0 cycles with up to two fetched register operands, 2.9 with three), and the LDS.128 that bring the
+// table rows into registers write through the same file (tools/proto/ldsprobe.cu).  Table values that arrive as uniform-register
+// operands (LDCU from constant memory) cost neither: no instruction of the scalar phase has more than two register operands,
+// whatever order the scheduler picks.  The table of one pulse (32 B per knot) lives in g_ctab, up to CT_MAX knots per launch.
+constexpr int CT_MAX = 2000;
+__constant__ double g_ctab[4 * CT_MAX];
+
+// FORM 0: rows (q_j, c0, c1, c2), T = c0 + eps (c1 + eps c2)        (c1 goes through a register)
+// FORM 1: rows (q_j, rho, sigma, c2), T = c2 (eps (eps + rho) + sigma)  (one table value per instruction, 15 FP64 instructions per knot)
+template <int U, int FORM>
+RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e0, double (&v)[4], int once) {
+    asm volatile("" : "+d"(dq2));
+    for (int t0 = 0; t0 < nk; t0 += ST_TILE) {          // the norm is restored in the rhythm of the shared-memory form: per ST_TILE knots
+        const int len = nk - t0 < ST_TILE ? nk - t0 : ST_TILE;
+        int j = 0;
+        for (; j + U <= len; j += U) {
+            double tp[U], tq[U];
+            const int jb = t0 + j;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = 4 * (jb + u);
+                const double eps = fma(g_ctab[k], dq2, e0);
+                const double q = g_ctab[k] + dq;
+                double t;
+                if (FORM == 0) t = fma(fma(g_ctab[k + 3], eps, g_ctab[k + 2]), eps, g_ctab[k + 1]);
+                else t = fma(eps, eps + g_ctab[k + 1], g_ctab[k + 2]) * g_ctab[k + 3];
+                tp[u] = t * p; tq[u] = t * q;
+            }
+            for (int rep = 0; rep < once; ++rep) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+                    const double x0 = fma(tp[u], a2, a0);
+                    const double x3 = fma(tp[u], a1, a3);
+                    const double x2 = fma(-tp[u], a0, a2);
+                    const double x1 = fma(-tp[u], a3, a1);
+                    v[0] = fma(tq[u], a3, x0);
+                    v[2] = fma(-tq[u], a1, x2);
+                    v[3] = fma(-tq[u], a0, x3);
+                    v[1] = fma(tq[u], a2, x1);
+                }
+            }
+        }
+        for (; j < len; ++j) {
+            const int k = 4 * (t0 + j);
+            const double eps = fma(g_ctab[k], dq2, e0);
+            double t;
+            if (FORM == 0) t = fma(fma(g_ctab[k + 3], eps, g_ctab[k + 2]), eps, g_ctab[k + 1]);
+            else t = fma(eps, eps + g_ctab[k + 1], g_ctab[k + 2]) * g_ctab[k + 3];
+            tan_apply(t * p, t * (g_ctab[k] + dq), v);
+        }
+        const double inv = rsqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] *= inv;
+    }
+}
+// One sample per thread.  A block whose warps all take the table step (the verdict of mc_static_kernel, per sample) reads the
+// table from constant memory; any other block walks the shared-memory tiles exactly like mc_static_kernel.  The kernel ends with
+// the sample's unit quaternion (32 B to a.quat); fidelities and statistics are mc_static_finish_kernel's: with that epilogue in
+// the same kernel the compiler loads the table rows into ordinary registers again (ptxas 12.9; both orders of the initial-state
+// fetch were tried), and the two extra passes over 32 B per sample cost 1 % of a 1000-knot sweep.
+template <int MINB, int THREADS, int U, int FORM>
+__global__ void __launch_bounds__(THREADS, MINB) mc_static_ctab_kernel(const McStaticArgs a) {
+    __shared__ __align__(128) double tile_s[2 * ST_TILE * ST_EPK];
+    __shared__ __align__(8) uint64_t bar_s[2];
+    const int tid = threadIdx.x;
+    const int64_t s = (int64_t)blockIdx.x * THREADS + tid;
+    const double w = RBQ_PI * a.dt;
+    const double a0 = a.scal[2], qmax = a.scal[3], p0 = w * a.scal[1];
+    const bool table_ok = a.scal[4] != 0.0 && !a.no_table_class;
+    const bool live = s < a.S;
+    double fq = 0.0, da = 0.0;
+    if (live) {
+        if (a.philox) sample_static((uint64_t)(a.first + s), a.seed, a.fq0, a.fq_rel_sigma, a.fq_rel_clip, a.da_sigma, fq, da);
+        else { fq = a.fq[s]; da = a.da ? a.da[s] : 0.0; }
+    }
+    const double p = w * fq, p2 = p * p, qd = w * (da - a0), qd2 = 2.0 * qd, e0 = fma(qd, qd, (p - p0) * (p + p0));
+    const double epsb = fma(fabs(qd2), qmax, fabs(e0));
+    const bool delta_ok = table_ok && DELTA_R3 * epsb * epsb * epsb <= DELTA_TOL;
+    const double qb = qmax + fabs(qd);
+    const double xb = fma(qb, qb, p2);
+    const int cls = warp_max_class(delta_ok ? -1 : (xb == xb ? degree_class(xb) : 3));
+    double v[4] = {1.0, 0.0, 0.0, 0.0};
+    // (the vote tells the compiler that the branch is warp-uniform: uniform-register loads are only generated in such regions)
+    if (__all_sync(0xffffffffu, __syncthreads_and(cls < 0))) {
+        delta_const_sweep<U, FORM>((int)a.nk, p, qd, qd2, e0, v, 1 | a.no_table_class);
+    } else {
+        const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS;
+        PulsePipeT<ST_TILE, ST_EPK> pipe;
+        pipe.init(tile_s, bar_s, a.table, a.nk);
+        double pp[1] = {p}, pp2[1] = {p2}, pqd[1] = {qd}, vv[1][4] = {{1.0, 0.0, 0.0, 0.0}};
+        for (int ti = 0; ti < pipe.ntiles; ++ti) {
+            const double* tile = pipe.acquire(ti, false);
+            const int len = pipe.tile_len(ti);
+            if (cls < 0) delta_tile_phased<RBQ_DELTA_U>(tile, len, p, qd, qd2, e0, vv[0], 1 | a.no_table_class);
+            else if (cls == 0) tan_tile<RBQ_TANA_DEG, 1, 8>(tile, len, pp, pp2, pqd, vv, cfA);
+            else if (cls == 1) tan_tile<RBQ_TANB_DEG, 1, 8>(tile, len, pp, pp2, pqd, vv, cfB);
+            else if (cls == 2) su2_tile<8, 1>(tile, len, pp, pp2, pqd, vv);
+            else su2_tile<0, 1>(tile, len, pp, pp2, pqd, vv);
+            pipe.release(ti + 1 < pipe.ntiles);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = vv[0][c];
+    }
+    if (live) reinterpret_cast<double4*>(a.quat)[s] = make_double4(v[0], v[1], v[2], v[3]);
+}
+// second half of the constant-memory form: quaternion -> gate propagator -> compute_fidelities -> statistics, the same
+// arithmetic and the same block geometry (one BlockPartial per THREADS samples) as mc_static_kernel's epilogue
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) mc_static_finish_kernel(const McStaticArgs a) {
+    __shared__ unsigned hist_s[RBQ_HIST_BINS];
+    __shared__ BlockPartial red_s[THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int b = tid; b < RBQ_HIST_BINS; b += THREADS) hist_s[b] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * THREADS + tid;
+    ThreadStats st;
+    if (s < a.S) {
+        const double4 q = reinterpret_cast<const double4*>(a.quat)[s];
+        double v[4] = {q.x, q.y, q.z, q.w}, psi0[4], E[16];
+        if (a.philox) sample_psi0((uint64_t)(a.first + s), a.seed, psi0);
+        else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) psi0[c] = a.psi0[4 * s + c];
+        }
+        // the exact product is a unit quaternion: dividing out |v| removes the radial rounding error (see mc_static_kernel)
+        const double inv = 1.0 / sqrt(fma(v[3], v[3], fma(v[2], v[2], fma(v[1], v[1], v[0] * v[0]))));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] *= inv;
+        iso_from_column(v, E);
+        double* row = a.fid ? a.fid + s * (a.gate_count + 1) : nullptr;
+        const double f = gate_train(E, psi0, a.gate, a.gate_count, row);
         if (a.partials) st.add(1.0 - f, hist_s);
     }
     if (a.partials) {
@@ -1769,19 +1918,28 @@ __global__ void __launch_bounds__(32) fp64_latency_kernel(int iters, double* __r
 // ---- launchers -----------------------------------------------------------------------------------------------------------
 // (samples per thread, min resident blocks per SM, block size) of the closed-form kernel;
 // RBQ_MC_VARIANT=<spt><minb><threads/128> overrides the default for tuning runs
-static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int* spt, int* minb, int* threads) {
+static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int* spt, int* minb, int* threads, int* form = nullptr,
+                                  int* knots = nullptr) {
     const int sm_count = h->sm_count;
     *spt = 1; *minb = 1; *threads = 256;
+    if (form) *form = 0;
+    if (knots) *knots = 8;
     if (algo != RBQ_ALGO_SU2) return;
     // measured best of the compiled variants (tools/tune_mc.py): 1 sample per thread, 128-thread blocks, 6 per SM (80 registers: at
-    // 72 the scheduler interleaves the updates of neighbouring knots and loses the operand reuse, 1.169 against 1.070 ms)
-    int v = 161;
+    // 72 the scheduler interleaves the updates of neighbouring knots and loses the operand reuse, 1.169 against 1.070 ms).
+    // Digits of the variant: <knots per batch><table form><samples per thread><blocks per SM><threads / 128>; table form 0 = rows
+    // through shared memory (mc_static_kernel), 1 / 2 = rows in constant memory, Horner / factored quadratic (mc_static_ctab_kernel)
+    int v = RBQ_MC_DEFAULT_VARIANT;
     if (h->opt.mc_variant > 0) v = h->opt.mc_variant;
-    *spt = v / 100; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
+    *spt = (v / 100) % 10; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
+    int f = (v / 1000) % 10, u = (v / 10000) % 10;
     const bool ok = (*spt == 1 || *spt == 2) && ((*threads == 256 && *minb >= 1 && *minb <= 4) || (*threads == 128 && (*minb == 4 || *minb == 6 || *minb == 7 || *minb == 8)));
-    if (!ok) { *spt = 1; *minb = 6; *threads = 128; }
+    if (!ok) { *spt = 1; *minb = 6; *threads = 128; f = 0; }
     // small sweeps: one sample per thread so that every SM gets blocks
     if (S < (int64_t)sm_count * 4 * *threads * *spt) *spt = 1;
+    if (f < 0 || f > 2 || *spt != 1 || *threads != 128 || (*minb != 6 && *minb != 8)) f = 0;
+    if (form) *form = f;
+    if (knots) *knots = u == 4 ? 4 : 8;
 }
 int mc_static_blocks(const rbq_handle* h, int64_t S, int algo) {
     int spt, minb, threads;
@@ -1809,18 +1967,67 @@ int launch_pulse_prep(rbq_handle* h, const double* d_controls, int64_t nk, doubl
     return (int)cudaGetLastError();
 }
 int launch_static_table(rbq_handle* h, const double* d_controls, int64_t nk, double dt, double f0, double a0, double* d_table,
-                        double* d_scal) {
-    static_table_kernel<<<1, 1024, 0, h->stream>>>(d_controls, nk, dt, f0, a0, d_table, d_scal);
+                        double* d_scal, double* d_table_m) {
+    static_table_kernel<<<1, 1024, 0, h->stream>>>(d_controls, nk, dt, f0, a0, d_table, d_scal, d_table_m);
     h->launches++;
     return (int)cudaGetLastError();
 }
+// g_ctab is one per device: the upload of a handle's table, the launch that reads it and the event that marks the read are
+// issued under one lock, and an upload waits for the last reader of the previous owner's table
+constexpr int CT_MAX_DEV = 64;
+static std::mutex g_ctab_mu;
+static const rbq_handle* g_ctab_owner[CT_MAX_DEV];
+static uint64_t g_ctab_gen[CT_MAX_DEV];
+static int g_ctab_form[CT_MAX_DEV];
+static cudaEvent_t g_ctab_ev[CT_MAX_DEV];
+void ctab_forget(const rbq_handle* h) {
+    std::lock_guard<std::mutex> lk(g_ctab_mu);
+    for (int d = 0; d < CT_MAX_DEV; ++d) if (g_ctab_owner[d] == h) g_ctab_owner[d] = nullptr;
+}
+typedef void (*ctab_sweep_fn)(const McStaticArgs);
+// The pair of kernels of the constant-memory form (device-resident samples and fidelities; calls whose buffers are page-locked
+// host memory keep the one-kernel form, whose blocks hide their PCIe reads and writes behind the arithmetic of their neighbours:
+// cutting the pair into slices with the finish kernels on a second stream measured 1.24 against 1.12 ms end to end)
+static int launch_mc_static_ctab(rbq_handle* h, const McStaticArgs& a, int blocks, ctab_sweep_fn sweep, int form) {
+    const int d = h->device;
+    std::lock_guard<std::mutex> lk(g_ctab_mu);
+    if (g_ctab_owner[d] != h || g_ctab_gen[d] != a.table_gen || g_ctab_form[d] != form) {
+        cudaError_t e = cudaSuccess;
+        if (!g_ctab_ev[d]) e = cudaEventCreateWithFlags(&g_ctab_ev[d], cudaEventDisableTiming);
+        else e = cudaStreamWaitEvent(h->stream, g_ctab_ev[d], 0);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(g_ctab, form == 1 ? a.table : a.table_m, sizeof(double) * 4 * (size_t)a.nk, 0,
+                                                          cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) { g_ctab_owner[d] = nullptr; return (int)e; }
+        g_ctab_owner[d] = h; g_ctab_gen[d] = a.table_gen; g_ctab_form[d] = form;
+    }
+    sweep<<<blocks, 128, 0, h->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(g_ctab_ev[d], h->stream);      // the table's last reader
+    if (e != cudaSuccess) return (int)e;
+    mc_static_finish_kernel<128><<<blocks, 128, 0, h->stream>>>(a);
+    h->launches += 2;
+    return (int)cudaGetLastError();
+}
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
-    int spt, minb, threads;
-    static_variant(h, a.S, algo, &spt, &minb, &threads);
+    int spt, minb, threads, form, knots;
+    static_variant(h, a.S, algo, &spt, &minb, &threads, &form, &knots);
     const int blocks = mc_static_blocks(h, a.S, algo);
     if (nblocks_out) *nblocks_out = blocks;
 #define RBQ_GO(SPT_, MINB_, T_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_, T_><<<blocks, T_, 0, h->stream>>>(a)
-    if (algo == RBQ_ALGO_SU2) {
+    if (algo == RBQ_ALGO_SU2 && form > 0 && !a.host_io && a.nk <= CT_MAX && a.table_m && a.quat && h->device >= 0 && h->device < CT_MAX_DEV) {
+        ctab_sweep_fn fn;
+        switch (knots * 100 + form * 10 + minb) {
+        case 816: fn = mc_static_ctab_kernel<6, 128, 8, 0>; break;
+        case 826: fn = mc_static_ctab_kernel<6, 128, 8, 1>; break;
+        case 818: fn = mc_static_ctab_kernel<8, 128, 8, 0>; break;
+        case 828: fn = mc_static_ctab_kernel<8, 128, 8, 1>; break;
+        case 416: fn = mc_static_ctab_kernel<6, 128, 4, 0>; break;
+        case 426: fn = mc_static_ctab_kernel<6, 128, 4, 1>; break;
+        case 418: fn = mc_static_ctab_kernel<8, 128, 4, 0>; break;
+        default: fn = mc_static_ctab_kernel<8, 128, 4, 1>; break;
+        }
+        return launch_mc_static_ctab(h, a, blocks, fn, form);
+    } else if (algo == RBQ_ALGO_SU2) {
         switch (spt * 100 + minb * 10 + threads / 128) {
         case 112: RBQ_GO(1, 1, 256); break; case 122: RBQ_GO(1, 2, 256); break; case 132: RBQ_GO(1, 3, 256); break; case 142: RBQ_GO(1, 4, 256); break;
         case 212: RBQ_GO(2, 1, 256); break; case 222: RBQ_GO(2, 2, 256); break; case 232: RBQ_GO(2, 3, 256); break; case 242: RBQ_GO(2, 4, 256); break;

@@ -471,11 +471,23 @@ def test_table_class_golden_and_sweep_centre(engine, monkeypatch):
 @pytest.mark.parametrize("gate_count", [1, 3], ids=["pair_store", "row_store"])
 def test_mc_static_zero_copy_equals_streamed(engine, monkeypatch, gate_count):
     """Page-locked sample buffers are read (and the fidelities written) by the kernel itself over PCIe; pageable ones are
-    streamed in chunks.  Same kernel, same samples, same bits; the launch count shows which form ran."""
+    streamed in chunks.  Same kernel (RBQ_MC_VARIANT 161: table rows through shared memory in both forms), same samples, same
+    bits; the launch count shows which form ran.  With the default variant the streamed form reads the table from constant
+    memory and evaluates the same quadratic in factored form: equal to rounding."""
     controls, dt, gate = PULSES["sin301_dt0.1"]
     S = 20000 + 13
     fq, da, psi0 = _samples(S, seed=31)
+    fid_d, st_d = engine.mc_static(controls, dt, gate, gate_count, fq, da, psi0)           # default variant, streamed
+    engine.set_option("RBQ_MC_VARIANT", "161")
+    try:
+        _zero_copy_equals_streamed(engine, controls, dt, gate, gate_count, S, fq, da, psi0, fid_d, st_d)
+    finally:
+        engine.set_option("RBQ_MC_VARIANT", "")
+
+
+def _zero_copy_equals_streamed(engine, controls, dt, gate, gate_count, S, fq, da, psi0, fid_d, st_d):
     fid_s, st_s = engine.mc_static(controls, dt, gate, gate_count, fq, da, psi0)           # pageable -> streamed
+    assert np.max(np.abs(fid_s - fid_d)) < 2e-14 and st_s.count == st_d.count and abs(st_s.sum - st_d.sum) <= 1e-12 * abs(st_d.sum)
     pfq, pda, ppsi = engine.pinned_empty(S), engine.pinned_empty(S), engine.pinned_empty((S, 4))
     pfid = engine.pinned_empty((S, gate_count + 1))
     pfq[:], pda[:], ppsi[:] = fq, da, psi0
@@ -566,11 +578,20 @@ def test_run_sim_deqjl_agrees_with_run_sim_prop_where_the_grids_coincide(engine)
 
 def test_host_register_enables_zero_copy_for_caller_owned_arrays(engine):
     """rbq_host_register page-locks memory the caller already owns (a Julia Array, a numpy array): the sweep then takes the
-    zero-copy form (one sweep kernel instead of one per chunk) and returns the same bits."""
+    zero-copy form (one sweep kernel instead of one per chunk) and returns the same bits (both forms through the shared-memory
+    kernel, RBQ_MC_VARIANT 161)."""
     controls, dt, gate = PULSES["sin301_dt0.1"]
     S = 300000                                             # several one-wave chunks in the streamed form
     fq, da, psi0 = _samples(S, seed=51)
     fid = np.empty((S, 2))
+    engine.set_option("RBQ_MC_VARIANT", "161")
+    try:
+        _host_register_zero_copy(engine, controls, dt, gate, S, fq, da, psi0, fid)
+    finally:
+        engine.set_option("RBQ_MC_VARIANT", "")
+
+
+def _host_register_zero_copy(engine, controls, dt, gate, S, fq, da, psi0, fid):
     before = engine.launch_count
     f_s, st_s = engine.mc_static(controls, dt, gate, 1, fq, da, psi0, fid_out=fid)
     streamed = engine.launch_count - before
@@ -805,3 +826,55 @@ def test_single_process_device_group_equals_one_handle(engine):
         assert st_e.count == 1
     finally:
         grp.close()
+
+
+# ---- constant-memory form of the static sweep (mc_static_ctab_kernel + mc_static_finish_kernel) ------------------------------
+@pytest.mark.parametrize("variant", ["2161", "2181", "42161", "1161"])
+def test_constant_memory_form_matches_shared_memory_form_and_oracle(engine, oracle, variant):
+    """Table rows as uniform-register operands from constant memory (variants 2xxx: the quadratic factored as
+    c2 (eps (eps + rho) + sigma); 1xxx: Horner) against the rows through shared memory (161), the oracle, and the 50-digit
+    golden; ragged sample count, a knot count that is no multiple of the batch, recorded gates 1 and 3."""
+    controls, dt, gate = PULSES["sin301_dt0.1"]
+    controls = controls[:297]                                 # 297 = 37 batches of 8 + 1: the tail loop runs
+    S = 5000 + 19
+    fq, da, psi0 = _samples(S, seed=77)
+    try:
+        for gates in (1, 3):
+            engine.set_option("RBQ_MC_VARIANT", "161")
+            f0, s0 = engine.mc_static(controls, dt, gate, gates, fq, da, psi0)
+            engine.set_option("RBQ_MC_VARIANT", variant)
+            before = engine.launch_count
+            f1, s1 = engine.mc_static(controls, dt, gate, gates, fq, da, psi0)
+            assert engine.launch_count - before > 0
+            assert np.max(np.abs(f1 - f0)) < 2e-14 and s1.count == s0.count == S and abs(s1.sum - s0.sum) <= 1e-12 * s0.sum
+            assert sum(s1.hist[:]) == S
+            ref = oracle.mc_static(controls, dt, gate, gates, fq[:400], da[:400], psi0[:400])
+            assert np.max(np.abs(f1[:400] - ref)) < FID_RTOL
+        z = np.load(GOLDEN + "/mc_static.npz")
+        fg, _ = engine.mc_static(z["controls"], float(z["dt"]), int(z["gate"]), int(z["gate_count"]), z["fq"], z["da"], z["psi0"])
+        assert np.max(np.abs(fg - z["fid"])) < 1e-13
+    finally:
+        engine.set_option("RBQ_MC_VARIANT", "")
+
+
+def test_constant_memory_table_is_shared_correctly_between_handles(engine):
+    """The constant-memory table is one per device: two handles with different pulses, called alternately on their own
+    streams, each get their own pulse's result (owner tag + event in launch_mc_static_ctab)."""
+    other = rbq.Engine(0)
+    try:
+        c1, dt, gate = PULSES["sin301_dt0.1"]
+        c2 = 0.5 * c1[::-1].copy()
+        S = 3000
+        fq, da, psi0 = _samples(S, seed=78)
+        a1, _ = engine.mc_static(c1, dt, gate, 1, fq, da, psi0)
+        b1, _ = other.mc_static(c2, dt, gate, 1, fq, da, psi0)
+        assert not np.array_equal(a1, b1)
+        for _ in range(3):
+            a2, _ = engine.mc_static(c1, dt, gate, 1, fq, da, psi0)
+            b2, _ = other.mc_static(c2, dt, gate, 1, fq, da, psi0)
+            assert np.array_equal(a2, a1) and np.array_equal(b2, b1)
+        # the same handle with a new pulse of the same length: the table is uploaded again
+        a3, _ = engine.mc_static(c2, dt, gate, 1, fq, da, psi0)
+        assert np.array_equal(a3, b1)
+    finally:
+        other.close()

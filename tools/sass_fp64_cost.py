@@ -10,7 +10,7 @@ import re
 import subprocess
 import sys
 
-COST = {0: 2.0, 1: 2.0, 2: 2.42, 3: 3.24}
+COST = {0: 2.0, 1: 2.0, 2: 2.0, 3: 2.9}
 
 
 def function_sass(lib, name):
