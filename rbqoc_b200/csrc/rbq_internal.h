@@ -74,6 +74,7 @@ struct McStaticArgs {
     const double* table_m; uint64_t table_gen;    // rows of the factored form, or NULL; serial number of this table (per handle)
     double* quat;                                 // scratch of the constant-memory form: 4 doubles per sample of this launch, or NULL
     int host_io;                                  // sample / fidelity pointers are page-locked host memory (zero-copy call)
+    int64_t win_first; int win_knots;             // constant-memory form: the window of knots this launch covers (set by the launcher)
     int64_t gate_count; int64_t first; int64_t S;
     const double* fq; const double* da; const double* psi0;   // explicit samples
     int philox; uint64_t seed; double fq0, fq_rel_sigma, fq_rel_clip, da_sigma;

@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_kernel(const McStatic
 // operands (LDCU from constant memory) cost neither: no instruction of the scalar phase has more than two register operands,
 // whatever order the scheduler picks.  The table of one pulse (32 B per knot) lives in g_ctab, up to CT_MAX knots per launch.
 constexpr int CT_MAX = 2000;
+constexpr int CT_WIN = 7 * ST_TILE;   // knots per launch of a pulse that does not fit
 __constant__ double g_ctab[4 * CT_MAX];
 
 // FORM 0: rows (q_j, c0, c1, c2), T = c0 + eps (c1 + eps c2)        (c1 goes through a register)
@@ -707,7 +708,14 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_ctab_kernel(const McS
     double v[4] = {1.0, 0.0, 0.0, 0.0};
     // (the vote tells the compiler that the branch is warp-uniform: uniform-register loads are only generated in such regions)
     if (__all_sync(0xffffffffu, __syncthreads_and(cls < 0))) {
-        delta_const_sweep<U, FORM>((int)a.nk, p, qd, qd2, e0, v, 1 | a.no_table_class);
+        // pulses longer than the constant-memory table take one launch per window of knots; the quaternion travels through a.quat
+        if (a.win_first > 0 && live) {
+            const double4 q = reinterpret_cast<const double4*>(a.quat)[s];
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+        delta_const_sweep<U, FORM>(a.win_knots, p, qd, qd2, e0, v, 1 | a.no_table_class);
+    } else if (a.win_first > 0) {
+        return;                                          // this block walked the whole pulse in the first window's launch
     } else {
         const double cfA[RBQ_TANA_DEG + 1] = RBQ_TANA_COEFS, cfB[RBQ_TANB_DEG + 1] = RBQ_TANB_COEFS;
         PulsePipeT<ST_TILE, ST_EPK> pipe;
@@ -1979,6 +1987,7 @@ static std::mutex g_ctab_mu;
 static const rbq_handle* g_ctab_owner[CT_MAX_DEV];
 static uint64_t g_ctab_gen[CT_MAX_DEV];
 static int g_ctab_form[CT_MAX_DEV];
+static int64_t g_ctab_first[CT_MAX_DEV];      // first knot of the window that is loaded
 static cudaEvent_t g_ctab_ev[CT_MAX_DEV];
 void ctab_forget(const rbq_handle* h) {
     std::lock_guard<std::mutex> lk(g_ctab_mu);
@@ -1989,24 +1998,31 @@ typedef void (*ctab_sweep_fn)(const McStaticArgs);
 // host memory keep the one-kernel form, whose blocks hide their PCIe reads and writes behind the arithmetic of their neighbours:
 // cutting the pair into 4 to 16 slices with the finish kernels on a second, highest-priority stream measured 1.21 to 1.25 ms against
 // 1.12 ms end to end for 2^20 samples with seeds in, 1.6 to 1.8 against 1.17 ms with sample arrays)
-static int launch_mc_static_ctab(rbq_handle* h, const McStaticArgs& a, int blocks, ctab_sweep_fn sweep, int form) {
+static int launch_mc_static_ctab(rbq_handle* h, const McStaticArgs& a0, int blocks, ctab_sweep_fn sweep, int form) {
     const int d = h->device;
     std::lock_guard<std::mutex> lk(g_ctab_mu);
-    if (g_ctab_owner[d] != h || g_ctab_gen[d] != a.table_gen || g_ctab_form[d] != form) {
-        cudaError_t e = cudaSuccess;
-        if (!g_ctab_ev[d]) e = cudaEventCreateWithFlags(&g_ctab_ev[d], cudaEventDisableTiming);
-        else e = cudaStreamWaitEvent(h->stream, g_ctab_ev[d], 0);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(g_ctab, form == 1 ? a.table : a.table_m, sizeof(double) * 4 * (size_t)a.nk, 0,
-                                                          cudaMemcpyDeviceToDevice, h->stream);
-        if (e != cudaSuccess) { g_ctab_owner[d] = nullptr; return (int)e; }
-        g_ctab_owner[d] = h; g_ctab_gen[d] = a.table_gen; g_ctab_form[d] = form;
+    McStaticArgs a = a0;
+    // one launch per window of knots (the whole pulse when it fits); windows are multiples of ST_TILE, the norm-restoring rhythm
+    const int64_t win = a.nk <= CT_MAX ? a.nk : CT_WIN;
+    cudaError_t e = cudaSuccess;
+    for (int64_t k0 = 0; k0 < a.nk && e == cudaSuccess; k0 += win) {
+        a.win_first = k0; a.win_knots = (int)(a.nk - k0 < win ? a.nk - k0 : win);
+        if (g_ctab_owner[d] != h || g_ctab_gen[d] != a.table_gen || g_ctab_form[d] != form || g_ctab_first[d] != k0) {
+            if (!g_ctab_ev[d]) e = cudaEventCreateWithFlags(&g_ctab_ev[d], cudaEventDisableTiming);
+            else e = cudaStreamWaitEvent(h->stream, g_ctab_ev[d], 0);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(g_ctab, (form == 1 ? a.table : a.table_m) + 4 * k0, sizeof(double) * 4 * (size_t)a.win_knots,
+                                                              0, cudaMemcpyDeviceToDevice, h->stream);
+            if (e != cudaSuccess) { g_ctab_owner[d] = nullptr; return (int)e; }
+            g_ctab_owner[d] = h; g_ctab_gen[d] = a.table_gen; g_ctab_form[d] = form; g_ctab_first[d] = k0;
+        }
+        sweep<<<blocks, 128, 0, h->stream>>>(a);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(g_ctab_ev[d], h->stream);      // the table's last reader
+        h->launches++;
     }
-    sweep<<<blocks, 128, 0, h->stream>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaEventRecord(g_ctab_ev[d], h->stream);      // the table's last reader
     if (e != cudaSuccess) return (int)e;
     mc_static_finish_kernel<128><<<blocks, 128, 0, h->stream>>>(a);
-    h->launches += 2;
+    h->launches++;
     return (int)cudaGetLastError();
 }
 int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblocks_out) {
@@ -2015,7 +2031,7 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
     const int blocks = mc_static_blocks(h, a.S, algo);
     if (nblocks_out) *nblocks_out = blocks;
 #define RBQ_GO(SPT_, MINB_, T_) mc_static_kernel<RBQ_ALGO_SU2, SPT_, MINB_, T_><<<blocks, T_, 0, h->stream>>>(a)
-    if (algo == RBQ_ALGO_SU2 && form > 0 && !a.host_io && a.nk <= CT_MAX && a.table_m && a.quat && h->device >= 0 && h->device < CT_MAX_DEV) {
+    if (algo == RBQ_ALGO_SU2 && form > 0 && !a.host_io && a.table_m && a.quat && h->device >= 0 && h->device < CT_MAX_DEV) {
         ctab_sweep_fn fn;
         switch (knots * 100 + form * 10 + minb) {
         case 816: fn = mc_static_ctab_kernel<6, 128, 8, 0>; break;

@@ -878,3 +878,28 @@ def test_constant_memory_table_is_shared_correctly_between_handles(engine):
         assert np.array_equal(a3, b1)
     finally:
         other.close()
+
+
+def test_constant_memory_form_windows_of_a_long_pulse(engine, oracle):
+    """A pulse longer than the constant-memory table (2000 knots) is swept in windows of 1792 knots, one launch each, the
+    quaternion travelling through scratch; blocks with out-of-range warps walk the whole pulse in the first launch."""
+    nk = 2 * 1792 + 517                                      # three windows, the last one partial and no multiple of 8
+    t = np.arange(nk) * 0.01
+    controls = 0.02 * np.sin(2 * np.pi * t / (nk * 0.01)) + 0.004 * np.sin(2 * np.pi * 7 * t / (nk * 0.01))
+    S = 3000 + 5
+    fq, da, psi0 = _samples(S, seed=79)
+    da[np.arange(S) % 640 < 32] += 0.2                       # every 20th warp leaves the table's range: its block takes the tile path
+    try:
+        engine.set_option("RBQ_MC_VARIANT", "161")
+        f0, s0 = engine.mc_static(controls, 0.01, rbq.GATE_XPIBY2, 2, fq, da, psi0)
+        engine.set_option("RBQ_MC_VARIANT", "2161")
+        before = engine.launch_count
+        f1, s1 = engine.mc_static(controls, 0.01, rbq.GATE_XPIBY2, 2, fq, da, psi0)
+        assert engine.launch_count - before >= 3 + 1           # three sweep launches + the finish kernel (+ table, statistics)
+    finally:
+        engine.set_option("RBQ_MC_VARIANT", "")
+    assert np.max(np.abs(f1 - f0)) < 5e-14 and s1.count == S and abs(s1.sum - s0.sum) <= 1e-12 * s0.sum
+    far = np.arange(S) % 640 < 32
+    assert np.array_equal(f1[far], f0[far])                  # the tile path is the same code in both kernels
+    ref = oracle.mc_static(controls, 0.01, rbq.GATE_XPIBY2, 2, fq[:200], da[:200], psi0[:200])
+    assert np.max(np.abs(f1[:200] - ref)) < max(FID_RTOL, 2.5e-15 * nk)
