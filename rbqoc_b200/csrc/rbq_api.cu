@@ -509,7 +509,9 @@ static int mc_static_prepare(rbq_handle* h, const double* d_controls, int64_t nk
 static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, double dt, int gate, int64_t gate_count,
                           int64_t first, int64_t S, const double* d_fq, const double* d_da, const double* d_psi0, int philox,
                           uint64_t seed, double fq0, double fq_rel_sigma, double fq_rel_clip, double da_sigma, int algo,
-                          double* d_fid, rbq_stats* d_stats) {
+                          double* d_fid, rbq_stats* d_stats, int host_io = 0) {
+    // host_io: the sample / fidelity pointers are device addresses of page-locked HOST memory (the zero-copy entry points):
+    // such a sweep keeps the one-kernel form, whose blocks hide their PCIe traffic behind their neighbours' arithmetic
     McStaticArgs a;
     if (S == 0) { GateIso gi; return make_gate_tables(gate, &gi, nullptr) ? RBQ_OK : fail(h, RBQ_E_GATE, "unknown gate %d", gate); }
     // Philox sweeps are centred on their own (fq0, 0), explicit samples on the handle's centre (rbq_set_sweep_centre)
@@ -519,7 +521,7 @@ static int mc_static_core(rbq_handle* h, const double* d_controls, int64_t nk, d
     a.fq = d_fq; a.da = d_da; a.psi0 = d_psi0;
     a.philox = philox; a.seed = seed; a.fq0 = fq0; a.fq_rel_sigma = fq_rel_sigma; a.fq_rel_clip = fq_rel_clip; a.da_sigma = da_sigma;
     a.fid = d_fid;
-    a.host_io = h->host_io_call;
+    a.host_io = host_io;
     int nblocks = 0;
     CKL(launch_mc_static(h, a, algo, &nblocks));
     if (d_stats) CKL(launch_stats_finalize(h, a.partials, nblocks, d_stats));
@@ -579,10 +581,8 @@ int rbq_mc_static(rbq_handle* h, const double* controls, int64_t nknots, double 
             CKL(dev_buf(h, B_IN0, sizeof(double) * nknots, &dc0));
             if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst0)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst0)); }
             CK(cudaMemcpyAsync(dc0, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
-            h->host_io_call = 1;
             int rc = mc_static_core(h, (double*)dc0, nknots, dt, gate, gate_count, 0, S, (double*)mfq, (double*)mda, (double*)mpsi,
-                                    0, 0, 0, 0, 0, 0, algo, (double*)mfid, (rbq_stats*)dst0);
-            h->host_io_call = 0;
+                                    0, 0, 0, 0, 0, 0, algo, (double*)mfid, (rbq_stats*)dst0, 1);
             if (rc) return rc;
             if (stats) CK(cudaMemcpyAsync(stats, dst0, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -660,10 +660,9 @@ int rbq_mc_static_philox(rbq_handle* h, const double* controls, int64_t nknots, 
     if (direct) dfid = mfid;
     if (stats) { CKL(dev_buf(h, B_STATS, sizeof(rbq_stats), &dst)); CKL(rbq_stats_reset_dev(h, (rbq_stats*)dst)); }
     CK(cudaMemcpyAsync(dc, controls, sizeof(double) * nknots, cudaMemcpyHostToDevice, h->stream));
-    h->host_io_call = direct ? 1 : 0;
-    int rc = rbq_mc_static_philox_dev(h, (double*)dc, nknots, dt, gate, gate_count, first, S, seed, fq0, fq_rel_sigma,
-                                      fq_rel_clip, da_sigma, algo, (double*)dfid, (rbq_stats*)dst);
-    h->host_io_call = 0;
+    if (first < 0) return fail(h, RBQ_E_SIZE, "rbq_mc_static_philox: first=%lld", (long long)first);
+    int rc = mc_static_core(h, (double*)dc, nknots, dt, gate, gate_count, first, S, nullptr, nullptr, nullptr, 1, seed, fq0,
+                            fq_rel_sigma, fq_rel_clip, da_sigma, algo, (double*)dfid, (rbq_stats*)dst, direct ? 1 : 0);
     if (rc) return rc;
     if (fid && S > 0 && !direct) CK(cudaMemcpyAsync(fid, dfid, sizeof(double) * S * G1, cudaMemcpyDeviceToHost, h->stream));
     if (stats) CK(cudaMemcpyAsync(stats, dst, sizeof(rbq_stats), cudaMemcpyDeviceToHost, h->stream));

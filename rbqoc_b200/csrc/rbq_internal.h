@@ -23,7 +23,6 @@ struct rbq_handle {
     int64_t idx_nk, idx_gates, idx_len; double idx_dt, idx_ndi;
     // centre (qubit frequency, amplitude offset) the static sweep's knot table is expanded around: rbq_set_sweep_centre
     double centre_fq, centre_da;
-    int host_io_call;              // set by the zero-copy entry points around their call into the device-pointer core
     uint64_t table_gen;            // counts the knot tables this handle has built (owner tag of the constant-memory copy)
     unsigned stpos_mask;           // which slices of the structured-Jacobian position table this handle has uploaded
     // tuning / A-B switches: read from the environment ONCE in rbq_create (RBQ_* names), changed afterwards only through

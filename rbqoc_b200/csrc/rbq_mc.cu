@@ -2184,7 +2184,8 @@ int launch_fp64_peak(rbq_handle* h, int iters, double* d_sink, int* nthreads_out
     }
     h->launches++;
     if (nthreads_out) *nthreads_out = blocks * 256;
-    if (flops_per_thread_iter) *flops_per_thread_iter = 8 * PEAK_CHAINS * 2;
+    // (modes 5 and up rescale their chains once per iteration: 16 more FP64 instructions on top of the 128)
+    if (flops_per_thread_iter) *flops_per_thread_iter = (8 * PEAK_CHAINS + (mode >= 5 && mode <= 8 ? PEAK_CHAINS : 0)) * 2;
     return (int)cudaGetLastError();
 }
 

@@ -1,4 +1,6 @@
-"""FP64 pipe microbenchmarks: instruction-issue rate (as 'TFLOP/s if every instruction were a DFMA') per form."""
+"""FP64 pipe microbenchmarks: instruction-issue rate (as 'TFLOP/s if every instruction were a DFMA') per form.
+The per-operand-count table the cost model uses comes from tools/proto/regbank.cu (stand-alone, controls the register numbers);
+this script is the quick check through the library (rbq_fp64_peak with RBQ_PEAK_MODE)."""
 import os
 import sys
 
