@@ -1,5 +1,6 @@
 // rbq_mc.cu — Monte-Carlo robustness kernels (one thread per sample, FP64-pipe bound):
 //   mc_static_kernel   run_sim_prop(...; dynamics_type=schroed)    spin.jl:438-452, 1553-1608
+//   mc_static_ctab_kernel + mc_static_finish_kernel: the same sweep with its knot table in constant memory (device-resident calls)
 //   mc_noise_kernel    run_sim_prop(...; dynamics_type=schroedda)  spin.jl:469-484
 //   lindblad_kernel    run_sim_prop(...; dynamics_type=lindbladt1) spin.jl:521-539 (+ T2 of 542-554)
 //   compute_fidelities / fidelity_vec_iso2 / fidelity_mat fused into each (spin.jl:1035-1037,
