@@ -163,9 +163,9 @@ int rbq_host_unregister(rbq_handle* h, void* ptr);
 /* Tuning / A-B switches.  The library reads its RBQ_* environment variables ONCE, in rbq_create, into the handle; no call
  * reads the environment afterwards.  rbq_set_option changes one switch of one handle later on (same names and value
  * syntax as the environment variables; value NULL or "" restores the default).  Names: RBQ_NO_TABLE_CLASS, RBQ_MC_ZEROCOPY,
- * RBQ_MC_CHUNK_WAVES ("first,rest"), RBQ_MC_VARIANT, RBQ_PEAK_MODE, RBQ_NOISE_GATE_PARALLEL, RBQ_LINDBLAD_NO_SHARED_MAP,
+ * RBQ_MC_CHUNK_WAVES ("first,rest"), RBQ_MC_VARIANT, RBQ_PEAK_MODE, RBQ_NOISE_GATE_PARALLEL, RBQ_NOISE_MATERIALISE, RBQ_LINDBLAD_NO_SHARED_MAP,
  * RBQ_LINDBLAD_TABLE, RBQ_LINDBLAD_SPT, RBQ_ROLLOUT_PACKED, RBQ_ROLLOUT_SCAN, RBQ_JAC_NT_UNSCENTED, RBQ_JAC_STRUCTURED, RBQ_JAC_STAGE_KB,
- * RBQ_JAC_STAGED, RBQ_BP_TMA, RBQ_BP_GENERIC, RBQ_BP_WARPS.  Every switch selects between kernels that meet the same parity
+ * RBQ_JAC_STAGED, RBQ_BP_TMA, RBQ_BP_GENERIC, RBQ_BP_WARPS, RBQ_BP_CLUSTER.  Every switch selects between kernels that meet the same parity
  * bound; none changes results beyond rounding.  Unknown names / malformed values return RBQ_E_SIZE. */
 int rbq_set_option(rbq_handle* h, const char* name, const char* value);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`). */

@@ -112,7 +112,7 @@ static bool make_gate_tables(int gate, GateIso* gi, GateRot* gr) {
 
 // ---- tuning options: latched from the environment in rbq_create, changed later only by rbq_set_option ----------------
 static const char* const kOptionNames[] = {"RBQ_NO_TABLE_CLASS", "RBQ_MC_ZEROCOPY", "RBQ_MC_CHUNK_WAVES", "RBQ_MC_VARIANT", "RBQ_PEAK_MODE",
-                                           "RBQ_NOISE_GATE_PARALLEL", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_LINDBLAD_SPT",
+                                           "RBQ_NOISE_GATE_PARALLEL", "RBQ_NOISE_MATERIALISE", "RBQ_LINDBLAD_NO_SHARED_MAP", "RBQ_LINDBLAD_TABLE", "RBQ_LINDBLAD_SPT",
                                            "RBQ_ROLLOUT_PACKED", "RBQ_ROLLOUT_SCAN", "RBQ_JAC_NT_UNSCENTED", "RBQ_JAC_STRUCTURED",
                                            "RBQ_JAC_STAGE_KB", "RBQ_JAC_STAGED", "RBQ_BP_TMA", "RBQ_BP_GENERIC", "RBQ_BP_WARPS", "RBQ_BP_CLUSTER"};
 int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
@@ -130,6 +130,7 @@ int rbq_apply_option(rbq_handle* h, const char* name, const char* value) {
         }
     }
     else if (is("RBQ_MC_VARIANT")) h->opt.mc_variant = v;
+    else if (is("RBQ_NOISE_MATERIALISE")) h->opt.noise_materialise = unset ? 1 : (v != 0);
     else if (is("RBQ_PEAK_MODE")) h->opt.peak_mode = unset ? 0 : v;
     else if (is("RBQ_NOISE_GATE_PARALLEL")) h->opt.noise_gate_parallel = unset ? -1 : (v != 0);
     else if (is("RBQ_LINDBLAD_NO_SHARED_MAP")) h->opt.lindblad_shared_map = unset ? 1 : (v == 0);
@@ -856,15 +857,27 @@ static int mc_noise_core(rbq_handle* h, const double* d_controls, int64_t nk, do
     // propagators can (see mc_noise_gate_kernel).  Large sweeps keep the single-kernel form (no scratch, same throughput).
     bool gate_parallel = algo == RBQ_ALGO_SU2 && gate_count >= 2 && gate_count <= 65535 && S < (int64_t)h->sm_count * 4096 &&
                          (double)S * (double)gate_count * 32.0 <= 2.0e9;
-    if (philox && (double)S * (double)noise_len * 8.0 > 2.0e9) gate_parallel = false;   // materialised noise rows must stay modest
-    if (h->opt.noise_gate_parallel == 0) gate_parallel = false;
+    // Seed-in sweeps in the gate-parallel form need their noise rows in memory (the pink filter is sequential in time, a gate's
+    // thread cannot start in the middle of it): they are materialised first (pink_white_kernel + pink_filter_kernel) whenever they
+    // fit -- a quarter of the free device memory, at most 32 GB.  The single-kernel form keeps generating its noise inside the
+    // sweep: materialising measured slower there (2^20 samples x 1 gate: 16.5 against 13.2 ms; 65 536 x 1: 1.21 against 1.02).
+    bool materialise = false;
+    if (philox && gate_parallel) {
+        const double bytes = (double)S * (double)noise_len * 8.0;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        const double have = (double)free_b + (double)h->dcap[B_NOISE];        // the scratch this handle already holds counts as free
+        materialise = h->opt.noise_materialise != 0 && bytes <= 32.0e9 && bytes <= 0.25 * have;
+        if (!materialise) gate_parallel = false;
+    }
+    if (h->opt.noise_gate_parallel == 0) { gate_parallel = false; materialise = false; }
+    if (materialise) {
+        void* dn;
+        CKL(dev_buf(h, B_NOISE, sizeof(double) * (size_t)S * (size_t)noise_len, &dn));
+        CKL(launch_pink_noise(h, first, S, seed, namp, noise_dt_inv, noise_len, (double*)dn));
+        a.noise = (const double*)dn;
+    }
     if (gate_parallel) {
-        if (philox) {   // the pink filter is sequential in time: materialise each sample's noise row first
-            void* dn;
-            CKL(dev_buf(h, B_NOISE, sizeof(double) * (size_t)S * (size_t)noise_len, &dn));
-            CKL(launch_pink_noise(h, first, S, seed, namp, noise_dt_inv, noise_len, (double*)dn));
-            a.noise = (const double*)dn;
-        }
         void* dq;
         CKL(dev_buf(h, B_QUAT, sizeof(double) * 4 * (size_t)S * (size_t)gate_count, &dq));
         CKL(launch_mc_noise_gate_parallel(h, a, (double*)dq, &nblocks));

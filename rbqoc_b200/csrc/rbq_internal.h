@@ -34,6 +34,7 @@ struct rbq_handle {
         int mc_variant;            // RBQ_MC_VARIANT          <spt><minb><threads/128> of mc_static_kernel
         int peak_mode;             // RBQ_PEAK_MODE           operand form of the DFMA saturation loop
         int noise_gate_parallel;   // RBQ_NOISE_GATE_PARALLEL 0: never the gate-parallel pair
+        int noise_materialise;     // RBQ_NOISE_MATERIALISE   0: seed-in noise sweeps generate their pink noise inside the sweep kernel
         int lindblad_shared_map;   // RBQ_LINDBLAD_NO_SHARED_MAP (inverted): 0 = every realisation composes its own map
         int lindblad_table;        // RBQ_LINDBLAD_TABLE      0: series step only (no per-knot Frechet table)
         int lindblad_spt;          // RBQ_LINDBLAD_SPT        realisations per thread of the table sweep (1 or 2)

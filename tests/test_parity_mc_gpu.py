@@ -243,6 +243,11 @@ def test_pink_noise_matches_oracle_and_drives_sweep(engine, oracle, gate_paralle
     got = engine.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
     ref = oracle.pink_noise(40, 33, 5, spin.NAMP_PREFACTOR, 10.0, nlen)
     assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
+    # ragged shapes of the two-pass generator (rows that do not fill a 32-row tile, odd lengths, one sample, one entry)
+    for first, S, nl in ((0, 70, 67), (7, 1, 1), (3, 32, 64), (11, 5, 33)):
+        got = engine.pink_noise(first, S, 9, spin.NAMP_PREFACTOR, 10.0, nl)
+        ref = oracle.pink_noise(first, S, 9, spin.NAMP_PREFACTOR, 10.0, nl)
+        assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
     # on-the-fly generation inside the sweep == the materialised noise fed through rbq_mc_noise
     controls, dt, gate, gc = spin.pulse_sin(301)[:-1], 0.1, rbq.GATE_XPIBY2, 4
     S, first, seed, namp = 130, 40, 5, spin.NAMP_PREFACTOR * 1e3

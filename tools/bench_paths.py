@@ -73,7 +73,7 @@ ms = timed(lambda: eng.mc_noise_dev(dc, nk, dt, rbq.GATE_XPIBY2, gates, S, spin.
 out("mc_noise su2 (explicit noise rows) P_X2 x 20 gates", ms, S * nk * gates, "trajectory-steps/s", S=S, knots=nk, gates=gates)
 ms = timed(lambda: eng.mc_pink_philox_dev(dc, nk, dt, rbq.GATE_XPIBY2, gates, 0, S, 3, spin.FQ, spin.NAMP_PREFACTOR, ndi,
                                           rbq.ALGO_SU2, dfid, stats), reps=3, warm=1)
-out("mc_pink_philox su2 (noise generated on the fly) P_X2 x 20 gates", ms, S * nk * gates, "trajectory-steps/s", S=S, knots=nk,
+out("mc_pink_philox su2 (seeds in: noise rows materialised on the device, gate-parallel form) P_X2 x 20 gates", ms, S * nk * gates, "trajectory-steps/s", S=S, knots=nk,
     gates=gates)
 
 # gen_3b shape proper: 1000 seeds x 200 gates x 5680 knots (figures.jl:504-505, 551-561): sequential vs gate-parallel form
