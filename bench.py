@@ -45,16 +45,15 @@ PARITY_TOL = 1e-12
 # smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on (profiles/):
 #   knot-table step (samples near the sweep centre -- every warp of this workload but ~0.3 %), ALGORITHMIC count:
 #     1 DFMA (eps) + 2 DFMA (T) + 1 DADD (q) + 2 DMUL (T p, T q) + 8 DFMA (v += T G v) = 14 FP64 instructions = 25 flop
-#   the shipped constant-memory form (mc_static_ctab_kernel) evaluates T as c2 (eps (eps + rho) + sigma), one table value per
-#   instruction: 1 DADD + 1 DFMA + 1 DMUL instead of 2 DFMA = 15 instructions = 26 flop EXECUTED; the roofline numerator stays
-#   the algorithmic 25, the pipe utilisation uses the executed 15
+#   the shipped constant-memory form (mc_static_ctab_kernel) executes exactly these 14 (q_j, c0, c2 as uniform-register operands,
+#   c1 through shared memory); its all-uniform variant (RBQ_MC_VARIANT=2161) factors the quadratic and executes 15 / 26
 FLOPS_PER_STEP_SU2 = 25.0
-FP64_INSTR_PER_STEP_SU2 = 15.0
-FLOPS_EXECUTED_PER_STEP_SU2 = 26.0
+FP64_INSTR_PER_STEP_SU2 = 14.0
+FLOPS_EXECUTED_PER_STEP_SU2 = 25.0
 # operand-delivery model of the shipped loop (tools/sass_fp64_cost.py on librbq.so; tools/proto/regbank.cu measured on B200: a
 # warp-wide FP64 instruction holds the pipe 2.0 cycles with up to two register operands to fetch, 2.9 with three): per knot
-# 12.75 instructions at 2.0 and 2.25 at 2.9
-FP64_MODEL_CYCLES_PER_STEP_SU2 = 32.03
+# 11.75 instructions at 2.0 and 2.25 at 2.9
+FP64_MODEL_CYCLES_PER_STEP_SU2 = 30.03
 BYTES_PER_SAMPLE = 8 + 8 + 32 + 16   # fq, da, psi0 in; 2 fidelities out
 # FP64 instructions per density-step of the Lindblad table step (lindblad_tab_kernel): 27 DFMA (Horner of the 9
 # entries of E_lo + da (L1 + da (L2 + da L3))) + 3 DMUL + 6 DFMA (the small part applied) + 9 DFMA (E_hi applied) = 45
@@ -659,7 +658,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(S=S), "samples_per_gpu": S, "knots": NK,
                        "algo": "su2 closed form, tan form, knot-table step (local quadratic of tan(theta)/theta around the sweep centre), "
-                               "table rows as uniform-register operands from constant memory",
+                               "table rows as uniform-register operands from constant memory (c1 through shared memory)",
                        "l2": "flushed between steps (256 MiB memset, untimed)",
                        "sharding": ("contiguous sample ranges per rank; per step ONE all-gather of the 2.1 KB statistics, copied to pinned host "
                                     "memory and merged on the host while the next step computes") if world > 1 else "single GPU"},

@@ -378,7 +378,7 @@ RBQ_DEV void delta_tile(const double* __restrict__ tile, int len, const double (
 // (dq2 and e0, dq, p), then the U dependent updates, every group of four sharing its multiplier and the first instruction of the
 // second group taking its multiplicand from the last one of the first.
 #ifndef RBQ_MC_DEFAULT_VARIANT
-#define RBQ_MC_DEFAULT_VARIANT 2161
+#define RBQ_MC_DEFAULT_VARIANT 3161
 #endif
 #ifndef RBQ_DELTA_PHASED
 #define RBQ_DELTA_PHASED 1
@@ -631,10 +631,13 @@ constexpr int CT_MAX = 2000;
 constexpr int CT_WIN = 7 * ST_TILE;   // knots per launch of a pulse that does not fit
 __constant__ double g_ctab[4 * CT_MAX];
 
-// FORM 0: rows (q_j, c0, c1, c2), T = c0 + eps (c1 + eps c2)        (c1 goes through a register)
+// FORM 0: rows (q_j, c0, c1, c2), T = c0 + eps (c1 + eps c2)        (two table values in one instruction: ptxas loads the rows
+//         with vector LDC.64, 82 cycles per knot -- kept for A/B only)
 // FORM 1: rows (q_j, rho, sigma, c2), T = c2 (eps (eps + rho) + sigma)  (one table value per instruction, 15 FP64 instructions per knot)
+// FORM 2: rows (q_j, c0, c1, c2) with c1 read from shared memory (c1_s, one LDS.128 per two knots) and q_j, c0, c2 as uniform
+//         operands: Horner again, 14 instructions, the arithmetic -- and the bits -- of mc_static_kernel's table step
 template <int U, int FORM>
-RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e0, double (&v)[4], int once) {
+RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e0, double (&v)[4], int once, const double* __restrict__ c1_s) {
     asm volatile("" : "+d"(dq2));
     for (int t0 = 0; t0 < nk; t0 += ST_TILE) {          // the norm is restored in the rhythm of the shared-memory form: per ST_TILE knots
         const int len = nk - t0 < ST_TILE ? nk - t0 : ST_TILE;
@@ -649,6 +652,7 @@ RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e
                 const double q = g_ctab[k] + dq;
                 double t;
                 if (FORM == 0) t = fma(fma(g_ctab[k + 3], eps, g_ctab[k + 2]), eps, g_ctab[k + 1]);
+                else if (FORM == 2) t = fma(fma(g_ctab[k + 3], eps, c1_s[jb + u]), eps, g_ctab[k + 1]);
                 else t = fma(eps, eps + g_ctab[k + 1], g_ctab[k + 2]) * g_ctab[k + 3];
                 tp[u] = t * p; tq[u] = t * q;
             }
@@ -672,6 +676,7 @@ RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e
             const double eps = fma(g_ctab[k], dq2, e0);
             double t;
             if (FORM == 0) t = fma(fma(g_ctab[k + 3], eps, g_ctab[k + 2]), eps, g_ctab[k + 1]);
+            else if (FORM == 2) t = fma(fma(g_ctab[k + 3], eps, c1_s[t0 + j]), eps, g_ctab[k + 1]);
             else t = fma(eps, eps + g_ctab[k + 1], g_ctab[k + 2]) * g_ctab[k + 3];
             tan_apply(t * p, t * (g_ctab[k] + dq), v);
         }
@@ -714,7 +719,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mc_static_ctab_kernel(const McS
             const double4 q = reinterpret_cast<const double4*>(a.quat)[s];
             v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         }
-        delta_const_sweep<U, FORM>(a.win_knots, p, qd, qd2, e0, v, 1 | a.no_table_class);
+        static_assert(2 * ST_TILE * ST_EPK >= CT_MAX, "the tile buffer holds one window's c1 column");
+        if (FORM == 2) {                                // this window's c1 column: 8 B per knot into the (otherwise idle) tile buffer
+            for (int i = tid; i < a.win_knots; i += THREADS) tile_s[i] = a.table[4 * (a.win_first + i) + 2];
+            __syncthreads();
+        }
+        delta_const_sweep<U, FORM>(a.win_knots, p, qd, qd2, e0, v, 1 | a.no_table_class, tile_s);
     } else if (a.win_first > 0) {
         return;                                          // this block walked the whole pulse in the first window's launch
     } else {
@@ -1980,7 +1990,8 @@ static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int*
     // measured best of the compiled variants (tools/tune_mc.py): 1 sample per thread, 128-thread blocks, 6 per SM (80 registers: at
     // 72 the scheduler interleaves the updates of neighbouring knots and loses the operand reuse, 1.169 against 1.070 ms).
     // Digits of the variant: <knots per batch><table form><samples per thread><blocks per SM><threads / 128>; table form 0 = rows
-    // through shared memory (mc_static_kernel), 1 / 2 = rows in constant memory, Horner / factored quadratic (mc_static_ctab_kernel)
+    // through shared memory (mc_static_kernel), 1 / 2 / 3 = rows in constant memory (mc_static_ctab_kernel): Horner with vector
+    // loads / factored quadratic / Horner with c1 through shared memory (the default: 14 instructions, the bits of form 0)
     int v = RBQ_MC_DEFAULT_VARIANT;
     if (h->opt.mc_variant > 0) v = h->opt.mc_variant;
     *spt = (v / 100) % 10; *minb = (v / 10) % 10; *threads = 128 * (v % 10);
@@ -1989,7 +2000,7 @@ static inline void static_variant(const rbq_handle* h, int64_t S, int algo, int*
     if (!ok) { *spt = 1; *minb = 6; *threads = 128; f = 0; }
     // small sweeps: one sample per thread so that every SM gets blocks
     if (S < (int64_t)sm_count * 4 * *threads * *spt) *spt = 1;
-    if (f < 0 || f > 2 || *spt != 1 || *threads != 128 || (*minb != 6 && *minb != 8)) f = 0;
+    if (f < 0 || f > 3 || *spt != 1 || *threads != 128 || (*minb != 6 && *minb != 8)) f = 0;
     if (form) *form = f;
     if (knots) *knots = u == 4 ? 4 : 8;
 }
@@ -2054,7 +2065,7 @@ static int launch_mc_static_ctab(rbq_handle* h, const McStaticArgs& a0, int bloc
         if (g_ctab_owner[d] != h || g_ctab_gen[d] != a.table_gen || g_ctab_form[d] != form || g_ctab_first[d] != k0) {
             if (!g_ctab_ev[d]) e = cudaEventCreateWithFlags(&g_ctab_ev[d], cudaEventDisableTiming);
             else e = cudaStreamWaitEvent(h->stream, g_ctab_ev[d], 0);
-            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(g_ctab, (form == 1 ? a.table : a.table_m) + 4 * k0, sizeof(double) * 4 * (size_t)a.win_knots,
+            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(g_ctab, (form == 2 ? a.table_m : a.table) + 4 * k0, sizeof(double) * 4 * (size_t)a.win_knots,
                                                               0, cudaMemcpyDeviceToDevice, h->stream);
             if (e != cudaSuccess) { g_ctab_owner[d] = nullptr; return (int)e; }
             g_ctab_owner[d] = h; g_ctab_gen[d] = a.table_gen; g_ctab_form[d] = form; g_ctab_first[d] = k0;
@@ -2078,6 +2089,9 @@ int launch_mc_static(rbq_handle* h, const McStaticArgs& a, int algo, int* nblock
     if (algo == RBQ_ALGO_SU2 && form > 0 && !a.host_io && a.table_m && a.quat && h->device >= 0 && h->device < CT_MAX_DEV) {
         ctab_sweep_fn fn;
         switch (knots * 100 + form * 10 + minb) {
+        case 836: fn = mc_static_ctab_kernel<6, 128, 8, 2>; break;
+        case 838: fn = mc_static_ctab_kernel<8, 128, 8, 2>; break;
+        case 436: fn = mc_static_ctab_kernel<6, 128, 4, 2>; break;
         case 816: fn = mc_static_ctab_kernel<6, 128, 8, 0>; break;
         case 826: fn = mc_static_ctab_kernel<6, 128, 8, 1>; break;
         case 818: fn = mc_static_ctab_kernel<8, 128, 8, 0>; break;

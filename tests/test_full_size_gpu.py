@@ -98,19 +98,22 @@ def test_full_size_lindblad_map_properties(engine):
 
 def test_full_sweep_zero_copy_streamed_and_polynomial_forms_agree(engine, sweep, monkeypatch):
     """The 1M-sample sweep through page-locked buffers (zero-copy: one kernel reads / writes over PCIe, table rows through shared
-    memory as T = c0 + eps (c1 + eps c2)) agrees with the streamed form (table rows from constant memory, the same quadratic
-    factored as c2 (eps (eps + rho) + sigma)) to rounding on every sample, and bit for bit when both run the shared-memory kernel;
-    the polynomial step (table class off) agrees with the knot-table step to rounding as well."""
+    memory) returns the bits of the streamed form (two kernels, table rows from constant memory: the same 14 operations per knot in
+    the same order), whichever kernel the streamed form is given; the all-uniform variant (2161: the quadratic factored as
+    c2 (eps (eps + rho) + sigma)) and the polynomial step (table class off) agree with them to rounding."""
     controls, fq, da, psi0, fid, st = sweep
     pfq, pda, ppsi = engine.pinned_empty(S_FULL), engine.pinned_empty(S_FULL), engine.pinned_empty((S_FULL, 4))
     pfid = engine.pinned_empty((S_FULL, 2))
     pfq[:], pda[:], ppsi[:] = fq, da, psi0
     fz, stz = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, pfq, pda, ppsi, fid_out=pfid)
-    assert np.max(np.abs(fz - fid)) < 2e-14 and stz.count == S_FULL and abs(stz.sum - st.sum) < 1e-12 * st.sum
+    assert np.array_equal(fz, fid) and stz.sum == st.sum and stz.hist[:] == st.hist[:]
     engine.set_option("RBQ_MC_VARIANT", "161")           # the streamed form through the shared-memory kernel: the same bits
     fs, sts = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
+    engine.set_option("RBQ_MC_VARIANT", "2161")          # ... through the all-uniform constant-memory variant: rounding
+    fu, stu = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
     engine.set_option("RBQ_MC_VARIANT", "")
     assert np.array_equal(fz, fs) and stz.sum == sts.sum and stz.hist[:] == sts.hist[:]
+    assert np.max(np.abs(fu - fid)) < 2e-14 and stu.count == S_FULL and abs(stu.sum - st.sum) < 1e-12 * st.sum
     engine.set_option("RBQ_NO_TABLE_CLASS", "1")
     fp, stp = engine.mc_static(controls, 0.1, rbq.GATE_XPIBY2, 1, fq, da, psi0)
     assert np.max(np.abs(fp - fid)) < 2e-14 and stp.count == S_FULL
