@@ -119,16 +119,21 @@ RBQ_DEV void sweep(int nk, double p, double dq, double dq2, double e0, double (&
         for (int c = 0; c < 4; ++c) v[c] *= inv;
     }
 }
-__global__ void __launch_bounds__(128, MINB) k(int nk, int once, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ c1g) {
-    const int s = blockIdx.x * 128 + threadIdx.x;
-    double v[4] = {1.0, 0.0, 0.0, 0.0};
+#ifndef PERSIST
+#define PERSIST 0      // 1: one block per resident slot walks several groups of 128 samples (the c1 copy and its barrier once per block)
+#endif
+__global__ void __launch_bounds__(128, MINB) k(int nk, int once, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ c1g, int ngroups) {
     __shared__ double c1_s[CT_MAX];
 #if MODE == 3
     for (int i = threadIdx.x; i < nk; i += 128) c1_s[i] = c1g[i];
     __syncthreads();
 #endif
-    sweep(nk, in[4 * s], in[4 * s + 1], in[4 * s + 2], in[4 * s + 3], v, once, c1_s);
-    out[s] = v[0] + v[1] + v[2] + v[3];
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int s = grp * 128 + threadIdx.x;
+        double v[4] = {1.0, 0.0, 0.0, 0.0};
+        sweep(nk, in[4 * s], in[4 * s + 1], in[4 * s + 2], in[4 * s + 3], v, once, c1_s);
+        out[s] = v[0] + v[1] + v[2] + v[3];
+    }
 }
 int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DSMEM);
@@ -145,13 +150,13 @@ int main() {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     float best = 1e9;
     for (int rep = 0; rep < 3; ++rep) {
-        k<<<S / 128, 128, DSMEM>>>(nk, 1, in, out, c1g);
+        k<<<PERSIST ? 148 * PERSIST : S / 128, 128, DSMEM>>>(nk, 1, in, out, c1g, S / 128);
         cudaEventRecord(a);
-        for (int i = 0; i < 10; ++i) k<<<S / 128, 128, DSMEM>>>(nk, 1, in, out, c1g);
+        for (int i = 0; i < 10; ++i) k<<<PERSIST ? 148 * PERSIST : S / 128, 128, DSMEM>>>(nk, 1, in, out, c1g, S / 128);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b); ms /= 10; best = ms < best ? ms : best;
     }
-    printf("U=%d MODE=%d MINB=%d DSMEM=%d: %.4f ms per 2^20 x %d sweep, %.2f cycles per knot per warp at 1965 MHz\n", KU, MODE, MINB, DSMEM, best, nk,
+    printf("U=%d MODE=%d MINB=%d DSMEM=%d PERSIST=%d: %.4f ms per 2^20 x %d sweep, %.2f cycles per knot per warp at 1965 MHz\n", KU, MODE, MINB, DSMEM, PERSIST, best, nk,
            best * 1.965e6 / ((double)S / 32 * nk / (148 * 4)));
     return 0;
 }
