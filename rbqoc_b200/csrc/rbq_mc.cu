@@ -688,8 +688,10 @@ RBQ_DEV void delta_const_sweep(int nk, double p, double dq, double dq2, double e
 // One sample per thread.  A block whose warps all take the table step (the verdict of mc_static_kernel, per sample) reads the
 // table from constant memory; any other block walks the shared-memory tiles exactly like mc_static_kernel.  The kernel ends with
 // the sample's unit quaternion (32 B to a.quat); fidelities and statistics are mc_static_finish_kernel's: with that epilogue in
-// the same kernel the compiler loads the table rows into ordinary registers again (ptxas 12.9; both orders of the initial-state
-// fetch were tried), and the two extra passes over 32 B per sample cost 1 % of a 1000-knot sweep.
+// the same kernel the compiler loads the table rows into ordinary registers again (ptxas 12.9: a dot product of the quaternion
+// with the loaded initial state still keeps the uniform loads, iso_from_column + one matrix-vector product + the fidelity does
+// not, whatever the register cap and wherever the initial state is fetched), and the two extra passes over 32 B per sample cost
+// 2.5 % of a 1000-knot sweep.
 template <int MINB, int THREADS, int U, int FORM>
 __global__ void __launch_bounds__(THREADS, MINB) mc_static_ctab_kernel(const McStaticArgs a) {
     __shared__ __align__(128) double tile_s[2 * ST_TILE * ST_EPK];
