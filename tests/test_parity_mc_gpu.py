@@ -909,3 +909,16 @@ def test_constant_memory_form_windows_of_a_long_pulse(engine, oracle):
     assert np.array_equal(f1, f0) and s1.count == S and s1.sum == s0.sum     # Horner form: the same operations, window by window
     ref = oracle.mc_static(controls, 0.01, rbq.GATE_XPIBY2, 2, fq[:200], da[:200], psi0[:200])
     assert np.max(np.abs(f1[:200] - ref)) < max(FID_RTOL, 2.5e-15 * nk)
+
+
+def test_constant_memory_form_seed_in_call_equals_sample_arrays_across_windows(engine):
+    """rbq_mc_static_philox (samples drawn in the kernel from their global Philox index) against rbq_mc_static on the arrays
+    rbq_philox_samples returns, on a pulse that needs several constant-memory windows and with a non-zero first index: the same
+    fidelities bit for bit, the same statistics."""
+    controls, dt, gate = PULSES["x2_dt0.01"]                  # 5680 knots: four windows
+    first, S, seed = 12345, 3000 + 7, 99
+    fq, da, psi0 = engine.philox_samples(first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5)
+    f_a, st_a = engine.mc_static(controls, dt, gate, 2, fq, da, psi0)
+    f_p, st_p = engine.mc_static_philox(controls, dt, gate, 2, first, S, seed, spin.FQ, 0.01, 0.03, 2.574e-5, want_fid=True)
+    assert np.array_equal(f_a, f_p)
+    assert st_a.count == st_p.count == S and st_a.sum == st_p.sum and st_a.hist[:] == st_p.hist[:]
